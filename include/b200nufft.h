@@ -1,0 +1,152 @@
+/* b200nufft.h -- C ABI of libb200nufft.so, the sm_100a table-interpolation
+ * NUFFT engine behind torchkbnufft's table-mode API.
+ *
+ * Boundary rules
+ *  - extern "C", plain pointers and sizes only (no torch / C++ types);
+ *  - every `*_dev` / grid / kdata pointer is DEVICE memory owned by the caller;
+ *    the library never allocates or frees caller-visible memory -- plans live
+ *    in a caller-provided workspace sized by b2n_points_workspace_bytes();
+ *  - `stream` is a cudaStream_t passed as void*; all work is enqueued on it and
+ *    no call synchronises the device (CUDA-graph capturable) except where noted;
+ *  - return value: 0 = OK, < 0 = argument error (B2N_E_*), > 0 = cudaError_t;
+ *    b2n_last_error() returns a thread-local message for the last failure;
+ *  - complex data is interleaved (re, im) float (B2N_C64) or double (B2N_C128);
+ *  - no CPU fallback exists: without a CUDA device every compute entry fails.
+ *
+ * Each entry point names the reference interface it replaces; paths are
+ * relative to the reference checkout (mmuckley/torchkbnufft).
+ */
+#ifndef B200NUFFT_H
+#define B200NUFFT_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define B2N_API __attribute__((visibility("default")))
+#else
+#define B2N_API
+#endif
+
+#define B2N_ABI_VERSION 1
+#define B2N_MAX_DIMS 3
+#define B2N_MAX_NUMPOINTS 16 /* max neighbours J per dimension */
+
+enum b2n_dtype { B2N_C64 = 0, B2N_C128 = 1 };
+/* grid memory layout: (B, C, *K) as in the reference, or channel-last (B, *K, C) */
+enum b2n_layout { B2N_COIL_MAJOR = 0, B2N_CHANNEL_LAST = 1 };
+/* adjoint accumulation mode */
+enum b2n_adjoint_mode {
+  B2N_ADJ_ATOMIC = 0, /* scatter with L2 reductions; order not reproducible (like index_add_ on CUDA) */
+  B2N_ADJ_SORTED = 1  /* gather per grid cell over the cell-sorted point list; bit-reproducible */
+};
+
+enum b2n_error {
+  B2N_OK = 0,
+  B2N_E_ARG = -1,       /* bad argument (null pointer, bad enum, size <= 0) */
+  B2N_E_RANGE = -2,     /* size exceeds an engine limit (dims, J, 32-bit cell keys) */
+  B2N_E_WORKSPACE = -3, /* workspace too small or misaligned */
+  B2N_E_UNSUPPORTED = -4
+};
+
+/* Geometry of one NUFFT operator: what KbModule registers as buffers
+ * (torchkbnufft/modules/_kbmodule.py:53-62; built by init_fn, _nufft/utils.py:257-358). */
+typedef struct b2n_geom {
+  int32_t ndim;                         /* 1..3 */
+  int32_t dtype;                        /* enum b2n_dtype */
+  int64_t grid_size[B2N_MAX_DIMS];      /* K_d, oversampled grid */
+  int32_t numpoints[B2N_MAX_DIMS];      /* J_d */
+  int32_t table_oversamp[B2N_MAX_DIMS]; /* L_d */
+  int64_t table_len[B2N_MAX_DIMS];      /* J_d*L_d + 1 */
+  const void *table_dev[B2N_MAX_DIMS];  /* device, interleaved complex of `dtype` */
+  double n_shift[B2N_MAX_DIMS];         /* fftshift phase offsets (values of the real-dtype buffer) */
+} b2n_geom;
+
+/* A trajectory plan: points sorted by wrapped base grid cell with everything that
+ * depends on omega alone precomputed once (the reference recomputes all of it on
+ * every call: tm / base_offset at _nufft/interp.py:171-177 and :663-670, the
+ * per-offset table lookups of calc_coef_and_indices :129-148, sort_data :566-584,
+ * the phase :200-203).  All pointers point into the caller's workspace. */
+typedef struct b2n_points {
+  int64_t n_points;    /* M, points per trajectory */
+  int64_t n_traj;      /* 1 (shared trajectory) or B (one per batch element) */
+  int32_t ndim;
+  int32_t dtype;
+  int32_t coef_stride; /* complex entries per point record = sum_d J_d */
+  int32_t reserved;
+  int32_t *perm;       /* [n_traj*M]        sorted slot -> point index inside its trajectory */
+  int32_t *base;       /* [n_traj*M][ndim]  wrapped base cell, in [0, K_d) */
+  void *coef;          /* [n_traj*M][coef_stride] complex table values T_d[t_d(j)], dims concatenated */
+  void *phase;         /* [n_traj*M]        complex exp(i sum_d omega_d n_shift_d) */
+  int32_t *cell_start; /* [n_traj*prod(K)+1] CSR offsets of the sorted list per base cell */
+  uint32_t *keys;      /* [n_traj*M]        sorted keys (traj*prod(K) + base cell) */
+} b2n_points;
+
+B2N_API int b2n_abi_version(void);
+B2N_API const char *b2n_last_error(void);
+/* number of CUDA devices visible; 0 when there is none or the driver is unusable
+ * (b2n_last_error() then says why) */
+B2N_API int b2n_device_count(void);
+
+/* ---- trajectory plan -------------------------------------------------------- */
+/* Bytes of device workspace b2n_points_build needs (plan arrays + sort scratch). */
+B2N_API int b2n_points_workspace_bytes(const b2n_geom *geom, int64_t n_points, int64_t n_traj, size_t *bytes);
+
+/* Build the plan for `omega_dev` ([n_traj][ndim][M], real dtype of geom->dtype,
+ * radians/voxel).  Replaces, once per trajectory, the per-call coordinate work of
+ * table_interp_one_batch (_nufft/interp.py:171-177), calc_coef_and_indices
+ * (:129-148) and sort_one_batch (:552-562; integer cell keys, stable). */
+B2N_API int b2n_points_build(const b2n_geom *geom, const void *omega_dev, int64_t n_points, int64_t n_traj,
+                     void *workspace_dev, size_t workspace_bytes, b2n_points *out, void *stream);
+
+/* Debug / parity export of the reference's integer indices for every neighbour
+ * offset w (row-major): arr_ind[W][M] (flat wrapped grid index, int64) and
+ * tab_idx[W][ndim][M] (table index incl. centre, int32; may be NULL).
+ * reference: calc_coef_and_indices, _nufft/interp.py:89-150.  Single trajectory. */
+B2N_API int b2n_export_indices(const b2n_geom *geom, const void *omega_dev, int64_t n_points, int64_t *arr_ind_dev,
+                       int32_t *tab_idx_dev, void *stream);
+
+/* ---- table interpolation ---------------------------------------------------- */
+/* Forward gather, grid -> points.  grid: (B, C, *K) or (B, *K, C) per `grid_layout`;
+ * kdata out: (B, C, M).  reference: table_interp, _nufft/interp.py:315-403. */
+B2N_API int b2n_interp_forward(const b2n_geom *geom, const b2n_points *pts, const void *grid_dev, int64_t n_batch,
+                       int64_t n_coils, int grid_layout, void *kdata_dev, void *stream);
+
+/* Adjoint spread, points -> grid (grid fully overwritten).
+ * reference: table_interp_adjoint, _nufft/interp.py:587-726 (+ accum_tensor_index_add :407-419). */
+B2N_API int b2n_interp_adjoint(const b2n_geom *geom, const b2n_points *pts, const void *kdata_dev, int64_t n_batch,
+                       int64_t n_coils, int grid_layout, int mode, void *grid_dev, void *stream);
+
+/* ---- fused steps around the FFT --------------------------------------------- */
+/* grid = zero_pad_end( image * smaps * scaling ) * scale.
+ *   image (B, Ci, *N) with Ci == C, or Ci == 1 broadcast over coils (SENSE);
+ *   smaps (Bs, C, *N) or NULL, Bs in {1, B};  scaling (*N) complex or NULL.
+ * reference: SENSE multiply modules/kbnufft.py:182-183 + fft_and_scale
+ * _nufft/fft.py:66-76 (multiply, F.pad); `scale` folds the 'ortho' factor. */
+B2N_API int b2n_apod_pad(int ndim, int dtype, const int64_t *im_size, const int64_t *grid_size, int64_t n_batch,
+                 int64_t n_coils, const void *image_dev, int64_t image_coils, const void *smaps_dev,
+                 int64_t smaps_batch, const void *scaling_dev, double scale, int grid_layout, void *grid_dev,
+                 void *stream);
+
+/* image = sum_c? ( crop_first_N(grid) * conj(scaling) * conj(smaps) ) * scale.
+ *   with smaps: out (B, 1, *N) (coil combine); without: out (B, C, *N).
+ * reference: ifft_and_scale _nufft/fft.py:113-118 (crop_dims :25-32) + coil
+ * combine modules/kbnufft.py:404-405. */
+B2N_API int b2n_crop_apod_coilsum(int ndim, int dtype, const int64_t *im_size, const int64_t *grid_size, int64_t n_batch,
+                          int64_t n_coils, const void *grid_dev, int grid_layout, const void *smaps_dev,
+                          int64_t smaps_batch, const void *scaling_dev, double scale, void *image_dev,
+                          void *stream);
+
+/* spectrum[b][c][k] *= kernel[bk][k] * scale, in place; kernel_batch in {1, B}.
+ * reference: the Toeplitz filter multiply of fft_filter, _nufft/fft.py:164-173. */
+B2N_API int b2n_spectrum_mul(int dtype, void *spectrum_dev, const void *kernel_dev, int64_t n_batch, int64_t n_coils,
+                     int64_t n_grid, int64_t kernel_batch, int grid_layout, double scale, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200NUFFT_H */

@@ -1,0 +1,96 @@
+"""The drop-in boundary without a GPU: the C-ABI library loads and exports every
+symbol include/b200nufft.h declares, argument errors come back as negative status
+codes (no compute without a device), the product never touches the oracle, and CPU
+tensors / a missing library fail loudly instead of falling back."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+import torchkbnufft_b200 as tkbn
+from conftest import ROOT
+from torchkbnufft_b200 import _lib
+
+
+def header_symbols():
+    text = open(os.path.join(ROOT, "include", "b200nufft.h")).read()
+    return sorted(set(re.findall(r"B2N_API\s+[\w\s\*]+?\b(b2n_\w+)\s*\(", text)))
+
+
+def test_header_declares_expected_entry_points():
+    syms = header_symbols()
+    for name in ("b2n_points_build", "b2n_interp_forward", "b2n_interp_adjoint", "b2n_export_indices",
+                 "b2n_apod_pad", "b2n_crop_apod_coilsum", "b2n_spectrum_mul"):
+        assert name in syms
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _lib.load()
+    for name in header_symbols():
+        assert hasattr(lib, name), name
+    assert sorted(_lib.SIGNATURES) == header_symbols()  # ctypes binding covers the whole header
+    assert lib.b2n_abi_version() == _lib.ABI_VERSION
+
+
+def test_struct_layouts_match_header_sizes():
+    # b2n_geom: 2*int32 + 3*int64 + 3*int32 + 3*int32 + 3*int64 + 3*ptr + 3*double
+    assert ctypes.sizeof(_lib.Geom) == 8 + 24 + 12 + 12 + 24 + 24 + 24
+    assert ctypes.sizeof(_lib.Points) == 16 + 16 + 6 * 8
+
+
+def test_argument_errors_are_status_codes():
+    lib = _lib.load()
+    g = _lib.Geom()
+    g.ndim = 7
+    n = ctypes.c_size_t(0)
+    assert lib.b2n_points_workspace_bytes(ctypes.byref(g), 10, 1, ctypes.byref(n)) == -2  # B2N_E_RANGE
+    assert b"ndim" in lib.b2n_last_error()
+    g.ndim, g.dtype = 2, 0
+    for d in range(2):
+        g.grid_size[d], g.numpoints[d], g.table_oversamp[d] = 16, 6, 1024
+    status = lib.b2n_points_workspace_bytes(ctypes.byref(g), 100, 1, ctypes.byref(n))
+    if lib.b2n_device_count() > 0:
+        assert status == 0 and n.value > 100 * (4 + 8 + 12 * 8 + 8)
+    else:  # the sort-scratch query needs a device: a positive cudaError_t, never a fake answer
+        assert status > 0 and b"CUDA error" in lib.b2n_last_error()
+    g.numpoints[1] = 99
+    assert lib.b2n_points_workspace_bytes(ctypes.byref(g), 100, 1, ctypes.byref(n)) == -2
+    assert lib.b2n_interp_forward(None, None, None, 1, 1, 0, None, None) == -1  # B2N_E_ARG
+    assert lib.b2n_spectrum_mul(5, None, None, 1, 1, 1, 1, 0, 1.0, None) == -1
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "torchkbnufft_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "kbnufft_oracle" not in text and "cpu_engine_shim" not in text, f
+
+
+def test_cpu_tensors_fail_loudly():
+    ob = tkbn.KbNufft(im_size=(8, 8))
+    image = torch.randn(1, 1, 8, 8, dtype=torch.complex64)
+    omega = torch.rand(2, 10)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ob(image, omega)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        tkbn.KbInterpAdjoint(im_size=(8, 8))(torch.randn(1, 1, 10, dtype=torch.complex64), omega)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        tkbn.ToepNufft()(image, torch.randn(16, 16, dtype=torch.complex64))
+
+
+def test_missing_library_fails_loudly(monkeypatch):
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", "/nonexistent/libb200nufft.so")
+    with pytest.raises(_lib.EngineError, match="no CPU/PyTorch fallback"):
+        _lib.load()
+
+
+def test_spmat_mode_is_out_of_scope():
+    with pytest.raises(NotImplementedError):
+        tkbn.calc_tensor_spmatrix(torch.rand(2, 4), (8, 8))
+    with pytest.raises(NotImplementedError):
+        tkbn.functional.kb_spmat_interp(torch.zeros(1), (None, None))

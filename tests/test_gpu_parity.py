@@ -1,0 +1,320 @@
+"""Parity of the CUDA engine (through the ctypes/C-ABI path) on a B200.
+
+Checkers: (a) the reference's stored outputs (tests/golden/*.npz), (b) the CPU
+oracle on the same seeded inputs, (c) size-independent properties at BASELINE's
+full sizes.  Tolerances (north_star): complex64 rel-L2 <= 1e-5 forward and <= 1e-4
+adjoint; integer grid / table indices bit-exact; complex128 <= 1e-12.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import kbnufft_oracle as orc
+import torchkbnufft_b200 as tkbn
+from conftest import GOLDEN, module_kwargs, rel_l2
+from golden_cases import CASES, case_inputs
+from torchkbnufft_b200 import _lib, workloads
+from torchkbnufft_b200._nufft import fft as eng_fft
+from torchkbnufft_b200._nufft import interp as eng_interp
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+PRECS = {"c64": (np.complex64, torch.complex64), "c128": (np.complex128, torch.complex128)}
+FWD_TOL = {"c64": 1e-5, "c128": 1e-12}
+ADJ_TOL = {"c64": 1e-4, "c128": 1e-12}
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+
+
+def host(t):
+    return t.detach().cpu().numpy()
+
+
+@pytest.fixture(autouse=True)
+def _native_library_is_loaded():
+    assert os.path.exists(_lib.LIB_PATH), "libb200nufft.so missing: GPU tests must run the native engine"
+    _lib.load()
+    yield
+
+
+@pytest.mark.parametrize("prec", ["c64", "c128"])
+@pytest.mark.parametrize("name", list(CASES))
+def test_cases_match_reference(name, prec, ref_cases):
+    case = CASES[name]
+    cd, td = PRECS[prec]
+    inp = case_inputs(case, cd)
+    kw = module_kwargs(case, td)
+    key = f"{name}_{prec}_"
+    D = lambda k: dev(inp[k])
+    interp, interp_adj = tkbn.KbInterp(**kw).to(DEV), tkbn.KbInterpAdjoint(**kw).to(DEV)
+    nu, na = tkbn.KbNufft(**kw).to(DEV), tkbn.KbNufftAdjoint(**kw).to(DEV)
+    assert rel_l2(host(interp(D("grid"), D("omega"))), ref_cases[key + "interp"]) <= FWD_TOL[prec]
+    for mode in ("atomic", "sorted"):
+        tkbn.set_adjoint_mode(mode)
+        try:
+            assert rel_l2(host(interp_adj(D("kdata"), D("omega"))), ref_cases[key + "interp_adj"]) <= ADJ_TOL[prec]
+            for norm in (None, "ortho"):
+                tag = "ortho" if norm else "none"
+                out = na(D("kdata"), D("omega"), smaps=D("smaps"), norm=norm)
+                assert rel_l2(host(out), ref_cases[key + f"sense_adj_{tag}"]) <= ADJ_TOL[prec]
+        finally:
+            tkbn.set_adjoint_mode("atomic")
+    for norm in (None, "ortho"):
+        tag = "ortho" if norm else "none"
+        out = nu(D("image"), D("omega"), smaps=D("smaps"), norm=norm)
+        assert rel_l2(host(out), ref_cases[key + f"sense_fwd_{tag}"]) <= FWD_TOL[prec]
+    assert rel_l2(host(nu(D("image_multi"), D("omega"))), ref_cases[key + "nufft_fwd_nosmap"]) <= FWD_TOL[prec]
+    opts = dict(grid_size=case.get("grid_size"), numpoints=case.get("numpoints", 6),
+                table_oversamp=case.get("table_oversamp", 2 ** 10))
+    if case.get("toep", True):
+        for norm in (None, "ortho"):
+            tag = "ortho" if norm else "none"
+            kern = tkbn.calc_toeplitz_kernel(D("omega"), case["im_size"], norm=norm, **opts)
+            assert rel_l2(host(kern), ref_cases[key + f"toep_kernel_{tag}"]) <= ADJ_TOL[prec]
+            got = host(tkbn.ToepNufft()(D("image"), dev(ref_cases[key + f"toep_kernel_{tag}"]), smaps=D("smaps"),
+                                        norm=norm))
+            ref = ref_cases[key + f"toep_apply_{tag}"]
+            assert rel_l2(got[: ref.shape[0]], ref) <= FWD_TOL[prec]
+        kern = tkbn.calc_toeplitz_kernel(D("omega"), case["im_size"], weights=D("weights"), norm="ortho", **opts)
+        assert rel_l2(host(kern), ref_cases[key + "toep_kernel_weighted"]) <= ADJ_TOL[prec]
+    dcomp = tkbn.calc_density_compensation_function(D("omega"), case["im_size"], num_iterations=3,
+                                                    n_shift=case.get("n_shift"), **opts)
+    assert rel_l2(host(dcomp), ref_cases[key + "dcomp"]) <= ADJ_TOL[prec]
+
+
+@pytest.mark.parametrize("prec", ["c64", "c128"])
+@pytest.mark.parametrize("name", [n for n, c in CASES.items() if c["omega"] != "batched"])
+def test_integer_indices_bit_exact(name, prec, ref_cases):
+    """Grid and table indices of every neighbour offset equal the reference's
+    calc_coef_and_indices output (and the oracle's) exactly."""
+    case = CASES[name]
+    cd, td = PRECS[prec]
+    inp = case_inputs(case, cd)
+    ob = tkbn.KbInterp(**module_kwargs(case, td)).to(DEV)
+    arr_ind, tab_idx = eng_interp.export_indices(dev(inp["omega"]), ob.tables, ob.n_shift, ob.numpoints,
+                                                 ob.table_oversamp, ob.grid_size)
+    assert np.array_equal(host(arr_ind), ref_cases[f"{name}_{prec}_arr_ind"])
+    o_arr, o_tab = orc.calc_coef_and_indices(inp["omega"], inp["grid_size"], ob.numpoints.tolist(),
+                                             ob.table_oversamp.tolist())
+    assert np.array_equal(host(tab_idx).astype(np.int64), o_tab)
+
+
+@pytest.mark.parametrize("which", ["interp", "nufft"])
+def test_reference_pickle_goldens(which):
+    """The reference's own known-answer tests (tests/test_interp.py:16-31,
+    tests/test_nufft.py:15-30), float64, torch.allclose defaults."""
+    data = np.load(os.path.join(GOLDEN, f"ref_{which}_golden.npz"))
+    for i in range(int(data["n_cases"])):
+        image, ktraj, kdata = data[f"image_{i}"], data[f"ktraj_{i}"], data[f"kdata_{i}"]
+        im_size = image.shape[2:]
+        if which == "interp":
+            ob = tkbn.KbInterp(im_size=im_size, grid_size=im_size, dtype=torch.complex128).to(DEV)
+        else:
+            ob = tkbn.KbNufft(im_size=im_size, dtype=torch.complex128).to(DEV)
+        # real-view float64 inputs, as the reference's test feeds them
+        out = ob(torch.view_as_real(dev(image)), dev(ktraj))
+        assert torch.allclose(out.cpu(), torch.view_as_real(torch.from_numpy(kdata)))
+
+
+@pytest.mark.parametrize("layout", [_lib.COIL_MAJOR, _lib.CHANNEL_LAST])
+@pytest.mark.parametrize("name", ["d1", "d2_mixed", "d3", "d2_batched", "d2_radial"])
+def test_layouts_and_modes_agree_with_oracle(name, layout):
+    case = CASES[name]
+    inp = case_inputs(case, np.complex64)
+    ob = tkbn.KbInterp(**module_kwargs(case, torch.complex64)).to(DEV)
+    args = (ob.tables, ob.n_shift, ob.numpoints, ob.table_oversamp)
+    tables = [host(t) for t in ob.tables]
+    J, L, ns = ob.numpoints.tolist(), ob.table_oversamp.tolist(), host(ob.n_shift)
+    grid = dev(inp["grid"])
+    d = len(case["im_size"])
+    to_layout = (lambda g: g.movedim(1, -1).contiguous()) if layout == _lib.CHANNEL_LAST else (lambda g: g)
+    from_layout = (lambda g: g.movedim(-1, 1)) if layout == _lib.CHANNEL_LAST else (lambda g: g)
+    want = orc.table_interp(inp["grid"], inp["omega"], tables, ns, J, L)
+    got = eng_interp.table_interp(to_layout(grid), dev(inp["omega"]), *args, layout=layout)
+    assert rel_l2(host(got), want) <= 1e-5
+    want = orc.table_interp_adjoint(inp["kdata"], inp["omega"], tables, ns, J, L, inp["grid_size"])
+    outs = {}
+    for mode in ("atomic", "sorted"):
+        got = eng_interp.table_interp_adjoint(dev(inp["kdata"]), dev(inp["omega"]), *args, None, ob.grid_size,
+                                              layout=layout, mode=mode)
+        outs[mode] = host(from_layout(got))
+        assert rel_l2(outs[mode], want) <= 1e-4
+    again = eng_interp.table_interp_adjoint(dev(inp["kdata"]), dev(inp["omega"]), *args, None, ob.grid_size,
+                                            layout=layout, mode="sorted")
+    assert np.array_equal(host(from_layout(again)), outs["sorted"])  # sorted mode is bit-reproducible
+
+
+def test_fused_fft_side_kernels_match_torch():
+    torch.manual_seed(0)
+    for dt, tol in ((torch.complex64, 1e-6), (torch.complex128, 1e-14)):
+        for N, K, B, C in (((7,), (12,), 2, 3), ((6, 9), (8, 16), 2, 4), ((4, 5, 6), (7, 5, 9), 1, 3)):
+            image = torch.randn((B, 1) + N, dtype=dt, device=DEV)
+            multi = torch.randn((B, C) + N, dtype=dt, device=DEV)
+            smaps = torch.randn((1, C) + N, dtype=dt, device=DEV)
+            smaps_b = torch.randn((B, C) + N, dtype=dt, device=DEV)
+            scal = torch.randn(N, dtype=dt, device=DEV)
+            grid = torch.randn((B, C) + K, dtype=dt, device=DEV)
+            pad = []
+            for k, n in zip(reversed(K), reversed(N)):
+                pad += [0, k - n]
+            crop = (slice(None), slice(None)) + tuple(slice(0, n) for n in N)
+            for sm in (smaps, smaps_b):
+                want = torch.nn.functional.pad(image * sm * scal * 0.5, pad)
+                assert rel_l2(host(eng_fft.apod_pad(image, K, sm, scal, 0.5)), host(want)) <= tol
+                cl = eng_fft.apod_pad(image, K, sm.movedim(1, -1).contiguous(), scal, 0.5, layout=_lib.CHANNEL_LAST)
+                assert rel_l2(host(cl.movedim(-1, 1)), host(want)) <= tol
+                want = torch.sum(grid[crop] * scal.conj() * sm.conj(), 1, keepdim=True) * 0.25
+                assert rel_l2(host(eng_fft.crop_apod_coilsum(grid, N, sm, scal, 0.25)), host(want)) <= tol
+                cl = eng_fft.crop_apod_coilsum(grid.movedim(1, -1).contiguous(), N, sm.movedim(1, -1).contiguous(),
+                                               scal, 0.25, layout=_lib.CHANNEL_LAST)
+                assert rel_l2(host(cl), host(want)) <= tol
+            want = torch.nn.functional.pad(multi * scal, pad)
+            assert rel_l2(host(eng_fft.apod_pad(multi, K, None, scal, 1.0)), host(want)) <= tol
+            assert rel_l2(host(eng_fft.apod_pad(multi, K, None, None, 1.0)), host(torch.nn.functional.pad(multi, pad))) == 0
+            want = grid[crop] * scal.conj()
+            assert rel_l2(host(eng_fft.crop_apod_coilsum(grid, N, None, scal, 1.0)), host(want)) <= tol
+            for kern in (torch.randn(K, dtype=dt, device=DEV), torch.randn((B,) + K, dtype=dt, device=DEV)):
+                kb = kern if kern.ndim == len(K) else kern.unsqueeze(1)
+                want = grid * kb * 2.0
+                assert rel_l2(host(eng_fft.spectrum_mul_(grid.clone(), kern, 2.0)), host(want)) <= tol
+                cl = eng_fft.spectrum_mul_(grid.movedim(1, -1).contiguous(), kern, 2.0, layout=_lib.CHANNEL_LAST)
+                assert rel_l2(host(cl.movedim(-1, 1)), host(want)) <= tol
+
+
+def test_cfg1_full_size_against_reference(ref_cfg1):
+    """BASELINE config 1 (256^2, M = 205 824, complex64) against the reference's stored outputs."""
+    wl = workloads.WORKLOADS["cfg1"]
+    image, smaps, kdata, omega = workloads.make_inputs(wl, seed=0)
+    grid = workloads.complex_normal(np.random.default_rng(1), (1, 1) + wl.grid_size)
+    kw = dict(im_size=wl.im_size, dtype=torch.complex64)
+    interp, interp_adj = tkbn.KbInterp(**kw).to(DEV), tkbn.KbInterpAdjoint(**kw).to(DEV)
+    nu, na = tkbn.KbNufft(**kw).to(DEV), tkbn.KbNufftAdjoint(**kw).to(DEV)
+    step = int(ref_cfg1["step"])
+    om = dev(omega)
+    arr_ind, _ = eng_interp.export_indices(om, interp.tables, interp.n_shift, interp.numpoints, interp.table_oversamp,
+                                           interp.grid_size)
+    assert np.array_equal(host(arr_ind)[:, ::step], ref_cfg1["arr_ind_sub"])
+    assert rel_l2(host(interp(dev(grid), om))[..., ::step], ref_cfg1["interp_sub"]) <= 1e-5
+    assert rel_l2(host(nu(dev(image), om))[..., ::step], ref_cfg1["nufft_sub"]) <= 1e-5
+    for mode in ("atomic", "sorted"):
+        tkbn.set_adjoint_mode(mode)
+        try:
+            adj = host(interp_adj(dev(kdata), om))
+            assert rel_l2(adj[..., :48, :48], ref_cfg1["interp_adj_centre"]) <= 1e-4
+            assert rel_l2(adj[..., 100:104, :], ref_cfg1["interp_adj_rows"]) <= 1e-4
+            assert abs(np.linalg.norm(adj.astype(np.complex128)) / float(ref_cfg1["interp_adj_norm"]) - 1) <= 1e-5
+            assert rel_l2(host(na(dev(kdata), om))[..., ::4, ::4], ref_cfg1["nufft_adj"]) <= 1e-4
+        finally:
+            tkbn.set_adjoint_mode("atomic")
+
+
+def test_cfg2_full_size_against_oracle_and_properties():
+    """BASELINE config 2 (the benchmark workload): SENSE forward/adjoint vs the oracle,
+    plus adjointness, linearity and atomic-vs-sorted agreement at full size."""
+    wl = workloads.WORKLOADS["cfg2"]
+    image, smaps, kdata, omega = workloads.make_inputs(wl, seed=0)
+    nu = tkbn.KbNufft(im_size=wl.im_size, dtype=torch.complex64).to(DEV)
+    na = tkbn.KbNufftAdjoint(im_size=wl.im_size, dtype=torch.complex64).to(DEV)
+    tables = [host(t) for t in nu.tables]
+    J, L, ns = nu.numpoints.tolist(), nu.table_oversamp.tolist(), host(nu.n_shift)
+    scaling = host(nu.scaling_coef)
+    threads = os.cpu_count() or 1
+    want_f = orc.nufft_forward(image, omega, tables, ns, J, L, scaling, wl.im_size, wl.grid_size, smaps=smaps,
+                               nthreads=threads)
+    want_a = orc.nufft_adjoint(kdata, omega, tables, ns, J, L, scaling, wl.im_size, wl.grid_size, smaps=smaps,
+                               nthreads=threads)
+    x, s, y, om = dev(image), dev(smaps), dev(kdata), dev(omega)
+    got_f = nu(x, om, smaps=s)
+    assert rel_l2(host(got_f), want_f) <= 1e-5
+    outs = {}
+    for mode in ("atomic", "sorted"):
+        tkbn.set_adjoint_mode(mode)
+        try:
+            outs[mode] = na(y, om, smaps=s)
+            assert rel_l2(host(outs[mode]), want_a) <= 1e-4
+        finally:
+            tkbn.set_adjoint_mode("atomic")
+    assert rel_l2(host(outs["atomic"]), host(outs["sorted"])) <= 1e-5
+    # <A x, y> = <x, A^H y> (float64 accumulation of complex64 results)
+    lhs = torch.sum(got_f.to(torch.complex128).conj() * y.to(torch.complex128))
+    rhs = torch.sum(x.to(torch.complex128).conj() * outs["sorted"].to(torch.complex128))
+    assert float(abs(lhs - rhs) / abs(lhs)) <= 1e-5
+    # linearity
+    x2 = dev(workloads.complex_normal(np.random.default_rng(5), image.shape))
+    lin = nu(x + 2.0 * x2, om, smaps=s)
+    assert rel_l2(host(lin), host(got_f + 2.0 * nu(x2, om, smaps=s))) <= 1e-5
+
+
+def test_cfg4_shape_3d_properties_reduced():
+    """3-D kooshball at reduced size (the oracle finishes in seconds): forward and both
+    adjoint modes vs the oracle, adjointness."""
+    wl = workloads.Workload("cfg4s", (32, 32, 32), 4, 1, 512, 64, "koosh", "reduced 3-D kooshball")
+    image, smaps, kdata, omega = workloads.make_inputs(wl, seed=3)
+    nu = tkbn.KbNufft(im_size=wl.im_size, dtype=torch.complex64).to(DEV)
+    na = tkbn.KbNufftAdjoint(im_size=wl.im_size, dtype=torch.complex64).to(DEV)
+    tables = [host(t) for t in nu.tables]
+    J, L, ns = nu.numpoints.tolist(), nu.table_oversamp.tolist(), host(nu.n_shift)
+    scaling = host(nu.scaling_coef)
+    threads = os.cpu_count() or 1
+    x, s, y, om = dev(image), dev(smaps), dev(kdata), dev(omega)
+    want_f = orc.nufft_forward(image, omega, tables, ns, J, L, scaling, wl.im_size, wl.grid_size, smaps=smaps,
+                               nthreads=threads)
+    assert rel_l2(host(nu(x, om, smaps=s)), want_f) <= 1e-5
+    want_a = orc.nufft_adjoint(kdata, omega, tables, ns, J, L, scaling, wl.im_size, wl.grid_size, smaps=smaps,
+                               nthreads=threads)
+    for mode in ("atomic", "sorted"):
+        tkbn.set_adjoint_mode(mode)
+        try:
+            assert rel_l2(host(na(y, om, smaps=s)), want_a) <= 1e-4
+        finally:
+            tkbn.set_adjoint_mode("atomic")
+
+
+def test_edge_shapes():
+    kw = dict(im_size=(8, 6), dtype=torch.complex64)
+    interp, adj = tkbn.KbInterp(**kw).to(DEV), tkbn.KbInterpAdjoint(**kw).to(DEV)
+    grid = torch.randn(2, 3, 16, 12, dtype=torch.complex64, device=DEV)
+    # a single sample; the same sample repeated (collisions); (1, d, M) broadcast; non-contiguous input
+    om1 = torch.tensor([[0.3], [-2.0]], device=DEV)
+    assert interp(grid, om1).shape == (2, 3, 1)
+    om_rep = om1.repeat(1, 257)
+    out = interp(grid, om_rep)
+    assert torch.allclose(out, out[..., :1].expand_as(out))
+    y = torch.ones(2, 3, 257, dtype=torch.complex64, device=DEV)
+    for mode in ("atomic", "sorted"):
+        tkbn.set_adjoint_mode(mode)
+        try:
+            g = adj(y, om_rep)
+            g1 = adj(y[..., :1], om1)
+            assert rel_l2(host(g), host(g1) * 257) <= 1e-5
+        finally:
+            tkbn.set_adjoint_mode("atomic")
+    assert torch.equal(interp(grid, om_rep[None]), out)
+    nc = torch.randn(2, 3, 12, 16, dtype=torch.complex64, device=DEV).transpose(-1, -2)
+    assert torch.equal(interp(nc, om_rep), interp(nc.contiguous(), om_rep))
+    # empty trajectory
+    om0 = torch.zeros(2, 0, device=DEV)
+    assert interp(grid, om0).shape == (2, 3, 0)
+    z = adj(torch.zeros(2, 3, 0, dtype=torch.complex64, device=DEV), om0)
+    assert z.shape == (2, 3, 16, 12) and float(z.abs().max()) == 0.0
+    # dtype transfer smoke (tests/test_interp.py:340-362)
+    ob64 = tkbn.KbNufft(im_size=(8, 6)).to(DEV).to(torch.float64)
+    img = torch.randn(1, 1, 8, 6, dtype=torch.complex128, device=DEV)
+    assert ob64(img, om_rep.double()).dtype == torch.complex128
+
+
+def test_plan_cache_tracks_trajectory_edits():
+    kw = dict(im_size=(8, 8), dtype=torch.complex64)
+    interp = tkbn.KbInterp(**kw).to(DEV)
+    grid = torch.randn(1, 1, 16, 16, dtype=torch.complex64, device=DEV)
+    om = (torch.rand(2, 50, device=DEV) - 0.5) * 6
+    a = interp(grid, om)
+    assert torch.equal(interp(grid, om), a)  # cached plan, identical result
+    om.mul_(0.5)  # in-place edit bumps the version -> new plan
+    b = interp(grid, om)
+    assert not torch.equal(a, b)
+    assert torch.equal(b, interp(grid, om.clone()))

@@ -1,0 +1,86 @@
+"""Autograd wrappers of the fused steps around the FFT and of the Toeplitz filter.
+
+In the reference these steps are plain differentiable ATen ops
+(``_nufft/fft.py:36-118``, ``modules/kbnufft.py:182-183``, ``:404-405``,
+``:441-484``); here each is one kernel, so each gets an explicit backward.  The
+two fused steps are exact adjoints of one another (the reference's inverse FFT is
+unnormalised, ``_nufft/fft.py:19``), which makes every backward a single call of
+the opposite kernel.  Sensitivity maps and the scaling coefficients are treated as
+constants here; callers route through plain torch ops when those need gradients.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+from torch.autograd import Function
+
+from .._nufft import fft as _fft
+
+
+class ApodPad(Function):
+    """``image (B, 1|C, *N) -> zero_pad(image * smaps * scaling_coef) * scale``."""
+
+    @staticmethod
+    def forward(ctx, image, smaps, scaling_coef, grid_size, scale):
+        ctx.save_for_backward(smaps, scaling_coef)
+        ctx.im_size = tuple(image.shape[2:])
+        ctx.scale = scale
+        return _fft.apod_pad(image, grid_size, smaps, scaling_coef, scale)
+
+    @staticmethod
+    def backward(ctx, grad_grid):
+        smaps, scaling_coef = ctx.saved_tensors
+        grad = _fft.crop_apod_coilsum(grad_grid, ctx.im_size, smaps, scaling_coef, ctx.scale)
+        return grad, None, None, None, None
+
+
+class CropApodCoilsum(Function):
+    """``grid (B, C, *K) -> sum_c crop(grid) * conj(scaling_coef) * conj(smaps) * scale``."""
+
+    @staticmethod
+    def forward(ctx, grid, smaps, scaling_coef, im_size, scale):
+        ctx.save_for_backward(smaps, scaling_coef)
+        ctx.grid_size = tuple(grid.shape[2:])
+        ctx.n_coils = grid.shape[1]
+        ctx.scale = scale
+        return _fft.crop_apod_coilsum(grid, im_size, smaps, scaling_coef, scale)
+
+    @staticmethod
+    def backward(ctx, grad_image):
+        smaps, scaling_coef = ctx.saved_tensors
+        grad = _fft.apod_pad(grad_image, ctx.grid_size, smaps, scaling_coef, ctx.scale, n_coils=ctx.n_coils)
+        return grad, None, None, None, None
+
+
+def toeplitz_apply(image, kernel, smaps, normalized: bool):
+    """``sum_c conj(S_c) crop(IFFT(kernel * FFT(pad(S_c * image))))`` for the whole
+    batch at once (the reference loops over the batch in Python,
+    ``modules/kbnufft.py:441-484``).  kernel is ``(*K2)`` or ``(B, *K2)``."""
+    ndim = image.ndim - 2
+    grid_size = tuple(kernel.shape[-ndim:])
+    n_grid = 1
+    for k in grid_size:
+        n_grid *= k
+    grid = _fft.apod_pad(image, grid_size, smaps, None, 1.0)
+    grid = _fft.fft_grid(grid, ndim, inverse=False)
+    # 'ortho' scales both transforms by 1/sqrt(prod K2): fold 1/prod(K2) into the filter pass
+    _fft.spectrum_mul_(grid, kernel, (1.0 / n_grid) if normalized else 1.0)
+    grid = _fft.fft_grid(grid, ndim, inverse=True)
+    return _fft.crop_apod_coilsum(grid, image.shape[2:], smaps, None, 1.0)
+
+
+class ToeplitzFilter(Function):
+    """Differentiable (w.r.t. ``image``) fused Toeplitz normal operator."""
+
+    @staticmethod
+    def forward(ctx, image, kernel, smaps, normalized):
+        ctx.save_for_backward(kernel, smaps)
+        ctx.normalized = normalized
+        return toeplitz_apply(image, kernel, smaps, normalized)
+
+    @staticmethod
+    def backward(ctx, grad):
+        kernel, smaps = ctx.saved_tensors
+        # the operator is S^H P^H F^H D F P S; its adjoint swaps D for conj(D)
+        return toeplitz_apply(grad.contiguous(), kernel.conj().resolve_conj(), smaps, ctx.normalized), None, None, None

@@ -1,0 +1,117 @@
+"""ctypes binding of ``libb200nufft.so`` (the C ABI declared in ``include/b200nufft.h``).
+
+The engine is CUDA-only by design: there is no CPU implementation and no silent
+fallback.  If the shared library is missing, or a tensor lives on the CPU, the
+calls below raise -- they never route around the kernels.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, Structure, c_char_p, c_double, c_int, c_int32, c_int64, c_size_t, c_void_p
+from typing import Optional
+
+MAX_DIMS = 3
+MAX_NUMPOINTS = 16
+C64, C128 = 0, 1
+COIL_MAJOR, CHANNEL_LAST = 0, 1
+ADJ_ATOMIC, ADJ_SORTED = 0, 1
+ABI_VERSION = 1
+
+_CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")
+LIB_PATH = os.path.join(_CSRC, "libb200nufft.so")
+
+
+class Geom(Structure):
+    """struct b2n_geom"""
+
+    _fields_ = [
+        ("ndim", c_int32),
+        ("dtype", c_int32),
+        ("grid_size", c_int64 * MAX_DIMS),
+        ("numpoints", c_int32 * MAX_DIMS),
+        ("table_oversamp", c_int32 * MAX_DIMS),
+        ("table_len", c_int64 * MAX_DIMS),
+        ("table_dev", c_void_p * MAX_DIMS),
+        ("n_shift", c_double * MAX_DIMS),
+    ]
+
+
+class Points(Structure):
+    """struct b2n_points"""
+
+    _fields_ = [
+        ("n_points", c_int64),
+        ("n_traj", c_int64),
+        ("ndim", c_int32),
+        ("dtype", c_int32),
+        ("coef_stride", c_int32),
+        ("reserved", c_int32),
+        ("perm", c_void_p),
+        ("base", c_void_p),
+        ("coef", c_void_p),
+        ("phase", c_void_p),
+        ("cell_start", c_void_p),
+        ("keys", c_void_p),
+    ]
+
+
+class EngineError(RuntimeError):
+    """A libb200nufft call returned a non-zero status."""
+
+
+# every symbol include/b200nufft.h declares: (restype, argtypes)
+_I64P = POINTER(c_int64)
+SIGNATURES = {
+    "b2n_abi_version": (c_int, []),
+    "b2n_last_error": (c_char_p, []),
+    "b2n_device_count": (c_int, []),
+    "b2n_points_workspace_bytes": (c_int, [POINTER(Geom), c_int64, c_int64, POINTER(c_size_t)]),
+    "b2n_points_build": (c_int, [POINTER(Geom), c_void_p, c_int64, c_int64, c_void_p, c_size_t, POINTER(Points),
+                                 c_void_p]),
+    "b2n_export_indices": (c_int, [POINTER(Geom), c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
+    "b2n_interp_forward": (c_int, [POINTER(Geom), POINTER(Points), c_void_p, c_int64, c_int64, c_int, c_void_p,
+                                   c_void_p]),
+    "b2n_interp_adjoint": (c_int, [POINTER(Geom), POINTER(Points), c_void_p, c_int64, c_int64, c_int, c_int,
+                                   c_void_p, c_void_p]),
+    "b2n_apod_pad": (c_int, [c_int, c_int, _I64P, _I64P, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_int64,
+                             c_void_p, c_double, c_int, c_void_p, c_void_p]),
+    "b2n_crop_apod_coilsum": (c_int, [c_int, c_int, _I64P, _I64P, c_int64, c_int64, c_void_p, c_int, c_void_p,
+                                      c_int64, c_void_p, c_double, c_void_p, c_void_p]),
+    "b2n_spectrum_mul": (c_int, [c_int, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int, c_double,
+                                 c_void_p]),
+}
+
+_lib: Optional[ctypes.CDLL] = None
+
+
+def load() -> ctypes.CDLL:
+    """Load the engine; raise if it has not been built (no fallback exists)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise EngineError(
+            f"{LIB_PATH} not found. The B200 NUFFT engine has no CPU/PyTorch fallback: build it with "
+            "`python -m torchkbnufft_b200._build` (needs nvcc) before calling any operator."
+        )
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (restype, argtypes) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the library lacks a declared symbol
+        fn.restype = restype
+        fn.argtypes = argtypes
+    if lib.b2n_abi_version() != ABI_VERSION:
+        raise EngineError(f"libb200nufft ABI {lib.b2n_abi_version()} != expected {ABI_VERSION}; rebuild")
+    _lib = lib
+    return lib
+
+
+def check(status: int, what: str) -> None:
+    if status != 0:
+        msg = load().b2n_last_error()
+        raise EngineError(f"{what} failed with status {status}: {msg.decode() if msg else '?'}")
+
+
+def i64_array(values) -> ctypes.Array:
+    vals = [int(v) for v in values]
+    return (c_int64 * len(vals))(*vals)

@@ -1,0 +1,146 @@
+"""The FFT stage of the NUFFT with its element-wise neighbours fused.
+
+Reference (``torchkbnufft/_nufft/fft.py``): ``fft_and_scale`` :36-76 is
+mul -> F.pad -> fftn, ``ifft_and_scale`` :80-118 is ifftn -> index_select per dim ->
+mul, ``fft_filter`` :121-173 is pad -> fftn -> mul -> ifftn -> crop; the SENSE
+coil multiply / coil sum sit in the modules (``modules/kbnufft.py:182-183``,
+``:404-405``).  Here the scaling, SENSE multiply, zero-pad (resp. crop, conjugate
+multiplies and coil sum) are ONE kernel on each side of a cuFFT transform, and the
+'ortho' factor is folded into that kernel so cuFFT never runs a scaling pass.
+
+The raw (non-differentiable) host calls live here; autograd wrappers are in
+``_autograd/nufft.py``.
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+from typing import Optional, Sequence
+
+import torch
+from torch import Tensor
+
+from .. import _lib
+from .plan import current_stream_ptr, engine_dtype, host_ints, require_cuda
+
+
+def check_norm(norm: Optional[str]) -> bool:
+    if norm is not None and norm != "ortho":
+        raise ValueError("Only option for norm is 'ortho'.")
+    return norm == "ortho"
+
+
+def _sizes(v) -> list:
+    return list(host_ints(v))
+
+
+def apod_pad(image: Tensor, grid_size: Sequence[int], smaps: Optional[Tensor] = None,
+             scaling_coef: Optional[Tensor] = None, scale: float = 1.0, n_coils: Optional[int] = None,
+             layout: int = _lib.COIL_MAJOR) -> Tensor:
+    """``zero_pad_end(image * smaps * scaling_coef) * scale`` in one pass.
+
+    image ``(B, Ci, *N)`` with ``Ci in {1, C}``; smaps ``(Bs, C, *N)`` (channel-last
+    ``(Bs, *N, C)`` when ``layout`` is channel-last); returns the grid ``(B, C, *K)``
+    or ``(B, *K, C)``."""
+    require_cuda(image, "image")
+    lib = _lib.load()
+    image = image.contiguous()
+    B, Ci = image.shape[:2]
+    im_size = list(image.shape[2:])
+    grid_size = _sizes(grid_size)
+    if smaps is not None:
+        smaps = smaps.contiguous()
+        C = smaps.shape[-1] if layout == _lib.CHANNEL_LAST else smaps.shape[1]
+        Bs = smaps.shape[0]
+    else:
+        C = Ci if n_coils is None else n_coils
+        Bs = 1
+    shape = [B] + grid_size + [C] if layout == _lib.CHANNEL_LAST else [B, C] + grid_size
+    out = torch.empty(shape, dtype=image.dtype, device=image.device)
+    if out.numel() == 0:
+        return out
+    if scaling_coef is not None:
+        scaling_coef = scaling_coef.contiguous()
+    with torch.cuda.device(image.device):
+        _lib.check(
+            lib.b2n_apod_pad(len(im_size), engine_dtype(image.dtype), _lib.i64_array(im_size), _lib.i64_array(grid_size),
+                             B, C, image.data_ptr(), Ci, smaps.data_ptr() if smaps is not None else None, Bs,
+                             scaling_coef.data_ptr() if scaling_coef is not None else None, float(scale), layout,
+                             out.data_ptr(), current_stream_ptr(image.device)),
+            "b2n_apod_pad",
+        )
+    return out
+
+
+def crop_apod_coilsum(grid: Tensor, im_size: Sequence[int], smaps: Optional[Tensor] = None,
+                      scaling_coef: Optional[Tensor] = None, scale: float = 1.0,
+                      layout: int = _lib.COIL_MAJOR) -> Tensor:
+    """``sum_c crop(grid) * conj(scaling_coef) * conj(smaps) * scale`` in one pass;
+    without smaps the coil axis is kept.  Returns ``(B, 1 or C, *N)``."""
+    require_cuda(grid, "grid")
+    lib = _lib.load()
+    grid = grid.contiguous()
+    im_size = _sizes(im_size)
+    B = grid.shape[0]
+    if layout == _lib.CHANNEL_LAST:
+        C, grid_size = grid.shape[-1], list(grid.shape[1:-1])
+    else:
+        C, grid_size = grid.shape[1], list(grid.shape[2:])
+    Bs = 1
+    if smaps is not None:
+        smaps = smaps.contiguous()
+        Bs = smaps.shape[0]
+    out = torch.empty([B, 1 if smaps is not None else C] + im_size, dtype=grid.dtype, device=grid.device)
+    if out.numel() == 0:
+        return out
+    if scaling_coef is not None:
+        scaling_coef = scaling_coef.contiguous()
+    with torch.cuda.device(grid.device):
+        _lib.check(
+            lib.b2n_crop_apod_coilsum(len(im_size), engine_dtype(grid.dtype), _lib.i64_array(im_size),
+                                      _lib.i64_array(grid_size), B, C, grid.data_ptr(), layout,
+                                      smaps.data_ptr() if smaps is not None else None, Bs,
+                                      scaling_coef.data_ptr() if scaling_coef is not None else None, float(scale),
+                                      out.data_ptr(), current_stream_ptr(grid.device)),
+            "b2n_crop_apod_coilsum",
+        )
+    return out
+
+
+def spectrum_mul_(spectrum: Tensor, kernel: Tensor, scale: float = 1.0, layout: int = _lib.COIL_MAJOR) -> Tensor:
+    """In-place ``spectrum[b, c] *= kernel[b or 0] * scale`` (Toeplitz filter)."""
+    require_cuda(spectrum, "spectrum")
+    assert spectrum.is_contiguous()
+    kernel = kernel.contiguous()
+    B = spectrum.shape[0]
+    C = spectrum.shape[-1] if layout == _lib.CHANNEL_LAST else spectrum.shape[1]
+    n_grid = spectrum.numel() // max(B * C, 1)
+    kb = kernel.numel() // max(n_grid, 1)
+    if spectrum.numel() == 0:
+        return spectrum
+    with torch.cuda.device(spectrum.device):
+        _lib.check(
+            _lib.load().b2n_spectrum_mul(engine_dtype(spectrum.dtype), spectrum.data_ptr(), kernel.data_ptr(), B, C,
+                                         n_grid, kb, layout, float(scale), current_stream_ptr(spectrum.device)),
+            "b2n_spectrum_mul",
+        )
+    return spectrum
+
+
+def fft_grid(grid: Tensor, ndim: int, inverse: bool) -> Tensor:
+    """Unnormalised cuFFT transform over the last ``ndim`` axes of a coil-major grid.
+    (``norm='backward'`` on the forward and ``norm='forward'`` on the inverse both
+    mean "no scaling pass"; reference: fft_fn / ifft_fn, ``_nufft/fft.py:9-22``.)"""
+    dims = list(range(-ndim, 0))
+    if inverse:
+        return torch.fft.ifftn(grid, dim=dims, norm="forward")
+    return torch.fft.fftn(grid, dim=dims, norm="backward")
+
+
+def ortho_scale(grid_size: Sequence[int], normalized: bool) -> float:
+    if not normalized:
+        return 1.0
+    n = 1
+    for k in grid_size:
+        n *= int(k)
+    return 1.0 / math.sqrt(n)

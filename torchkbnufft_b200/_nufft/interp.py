@@ -1,0 +1,166 @@
+"""Table interpolation backends: host entry points into the sm_100a kernels.
+
+Same call signatures and error behaviour as the reference's
+``torchkbnufft/_nufft/interp.py`` (``table_interp`` :315-403,
+``table_interp_adjoint`` :587-726) so the autograd Functions and everything above
+them are drop-in; the work itself is one kernel launch per direction on a cached
+trajectory plan instead of ``prod(J)`` passes of ATen index/mul/add ops.
+
+There is deliberately no CPU implementation here (see ``plan.require_cuda``).
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import List, Optional
+
+import torch
+from torch import Tensor
+
+from .. import _lib
+from .plan import current_stream_ptr, get_geometry, get_plan, normalize_omega, require_cuda
+
+ADJOINT_MODES = {"atomic": _lib.ADJ_ATOMIC, "sorted": _lib.ADJ_SORTED}
+_default_adjoint_mode = os.environ.get("B200NUFFT_ADJOINT_MODE", "atomic")
+
+
+def set_adjoint_mode(mode: str) -> None:
+    """Select the adjoint accumulation mode: ``"atomic"`` (fastest; like
+    ``index_add_`` on CUDA the summation order is not reproducible) or ``"sorted"``
+    (deterministic: every grid cell gathers its samples in a fixed order)."""
+    global _default_adjoint_mode
+    if mode not in ADJOINT_MODES:
+        raise ValueError(f"adjoint mode must be one of {sorted(ADJOINT_MODES)}")
+    _default_adjoint_mode = mode
+
+
+def get_adjoint_mode() -> str:
+    return _default_adjoint_mode
+
+
+def _check_offsets(offsets: Optional[Tensor], n_offsets: int, ndim: int) -> None:
+    # The engine always visits the full row-major neighbourhood (the only thing the
+    # reference's modules ever pass, _nufft/utils.py:329); a custom subset is rejected.
+    if offsets is not None and tuple(offsets.shape) != (n_offsets, ndim):
+        raise ValueError(
+            f"offsets must list all {n_offsets} neighbour offsets (shape {(n_offsets, ndim)}), got {tuple(offsets.shape)}"
+        )
+
+
+def table_interp(
+    image: Tensor,
+    omega: Tensor,
+    tables: List[Tensor],
+    n_shift: Tensor,
+    numpoints: Tensor,
+    table_oversamp: Tensor,
+    offsets: Optional[Tensor] = None,
+    min_kspace_per_fork: int = 1024,
+    layout: int = _lib.COIL_MAJOR,
+    n_coils: Optional[int] = None,
+) -> Tensor:
+    """Interpolate gridded data ``image (B, C, *K)`` to the off-grid locations
+    ``omega`` (``(d, M)`` or ``(B, d, M)``, radians/voxel); returns ``(B, C, M)``.
+
+    ``min_kspace_per_fork`` is accepted for signature parity and ignored (it tunes
+    the reference's CPU thread forking).  ``layout``/``n_coils`` are engine
+    extensions used by the fused NUFFT path for channel-last grids ``(B, *K, C)``.
+    """
+    require_cuda(image, "image")
+    require_cuda(omega, "omega")
+    if not image.is_complex():
+        raise TypeError("image must be complex (use the functional API for real views).")
+    omega = normalize_omega(omega, image.shape[0], "image")
+    if layout == _lib.CHANNEL_LAST:
+        grid_size = image.shape[1:-1]
+        C = image.shape[-1]
+    else:
+        grid_size = image.shape[2:]
+        C = image.shape[1]
+    geo = get_geometry(tables, n_shift, numpoints, table_oversamp, tuple(grid_size))
+    if geo.cdtype != image.dtype:
+        raise TypeError(f"image dtype {image.dtype} does not match table dtype {geo.cdtype}")
+    if omega.shape[-2] != geo.ndim:
+        raise ValueError(f"omega has {omega.shape[-2]} coordinate rows for a {geo.ndim}-D grid")
+    _check_offsets(offsets, geo.n_offsets, geo.ndim)
+    plan = get_plan(geo, omega)
+    B = image.shape[0]
+    image = image.contiguous()
+    out = torch.empty((B, C, plan.n_points), dtype=image.dtype, device=image.device)
+    if out.numel() == 0:
+        return out
+    with torch.cuda.device(image.device):
+        _lib.check(
+            _lib.load().b2n_interp_forward(ctypes.byref(geo.struct), ctypes.byref(plan.struct), image.data_ptr(), B, C,
+                                           layout, out.data_ptr(), current_stream_ptr(image.device)),
+            "b2n_interp_forward",
+        )
+    return out
+
+
+def table_interp_adjoint(
+    data: Tensor,
+    omega: Tensor,
+    tables: List[Tensor],
+    n_shift: Tensor,
+    numpoints: Tensor,
+    table_oversamp: Tensor,
+    offsets: Optional[Tensor],
+    grid_size: Tensor,
+    layout: int = _lib.COIL_MAJOR,
+    mode: Optional[str] = None,
+) -> Tensor:
+    """Spread off-grid ``data (B, C, M)`` at ``omega`` onto the grid; returns
+    ``(B, C, *grid_size)`` (or ``(B, *grid_size, C)`` for the channel-last layout)."""
+    require_cuda(data, "data")
+    require_cuda(omega, "omega")
+    if not data.is_complex():
+        raise TypeError("data must be complex (use the functional API for real views).")
+    omega = normalize_omega(omega, data.shape[0], "data")
+    geo = get_geometry(tables, n_shift, numpoints, table_oversamp, grid_size)
+    if geo.cdtype != data.dtype:
+        raise TypeError(f"data dtype {data.dtype} does not match table dtype {geo.cdtype}")
+    if omega.shape[-2] != geo.ndim:
+        raise ValueError(f"omega has {omega.shape[-2]} coordinate rows for a {geo.ndim}-D grid")
+    if omega.shape[-1] != data.shape[-1]:
+        raise ValueError("omega and data disagree on the number of k-space samples")
+    _check_offsets(offsets, geo.n_offsets, geo.ndim)
+    plan = get_plan(geo, omega)
+    B, C = data.shape[:2]
+    data = data.contiguous()
+    if layout == _lib.CHANNEL_LAST:
+        shape = [B] + geo.grid_size + [C]
+    else:
+        shape = [B, C] + geo.grid_size
+    out = torch.empty(shape, dtype=data.dtype, device=data.device)
+    if out.numel() == 0:
+        return out
+    mode_id = ADJOINT_MODES[_default_adjoint_mode if mode is None else mode]
+    with torch.cuda.device(data.device):
+        _lib.check(
+            _lib.load().b2n_interp_adjoint(ctypes.byref(geo.struct), ctypes.byref(plan.struct), data.data_ptr(), B, C,
+                                           layout, mode_id, out.data_ptr(), current_stream_ptr(data.device)),
+            "b2n_interp_adjoint",
+        )
+    return out
+
+
+def export_indices(omega: Tensor, tables, n_shift, numpoints, table_oversamp, grid_size):
+    """Parity/debug export of the integer indices the reference's
+    ``calc_coef_and_indices`` (``_nufft/interp.py:89-150``) produces for every
+    neighbour offset: ``arr_ind (W, M)`` int64 and ``tab_idx (W, d, M)`` int32."""
+    require_cuda(omega, "omega")
+    if omega.ndim != 2:
+        raise ValueError("export_indices takes a single (d, M) trajectory")
+    geo = get_geometry(tables, n_shift, numpoints, table_oversamp, grid_size)
+    om = omega.contiguous()
+    M = om.shape[1]
+    arr_ind = torch.empty((geo.n_offsets, M), dtype=torch.int64, device=om.device)
+    tab_idx = torch.empty((geo.n_offsets, geo.ndim, M), dtype=torch.int32, device=om.device)
+    with torch.cuda.device(om.device):
+        _lib.check(
+            _lib.load().b2n_export_indices(ctypes.byref(geo.struct), om.data_ptr(), M, arr_ind.data_ptr(),
+                                           tab_idx.data_ptr(), current_stream_ptr(om.device)),
+            "b2n_export_indices",
+        )
+    return arr_ind, tab_idx

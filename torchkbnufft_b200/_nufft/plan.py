@@ -1,0 +1,192 @@
+"""Operator geometry and trajectory plans (host side of ``b2n_geom`` / ``b2n_points``).
+
+The reference recomputes the normalised coordinates, table lookups, the point sort
+and the fftshift phase on every call (``torchkbnufft/_nufft/interp.py:171-177``,
+``:129-148``, ``:552-584``, ``:663-686``).  Iterative reconstructions call the
+operator many times on one trajectory, so the engine builds that state once per
+``(geometry, omega)`` pair and keeps it in a small LRU cache.  Cache entries hold
+strong references to the tensors they were built from, so a ``data_ptr`` cannot be
+recycled under a live entry; in-place edits are seen through the tensor version.
+"""
+from __future__ import annotations
+
+import ctypes
+from collections import OrderedDict
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+from torch import Tensor
+
+from .. import _lib
+
+_GEOM_CACHE: "OrderedDict[tuple, Geometry]" = OrderedDict()
+_PLAN_CACHE: "OrderedDict[tuple, TrajectoryPlan]" = OrderedDict()
+_GRID_SIZE_CACHE: dict = {}
+GEOM_CACHE_SIZE = 32
+PLAN_CACHE_SIZE = 8
+
+
+def require_cuda(t: Tensor, what: str) -> None:
+    """The engine has no CPU path; refuse CPU tensors loudly."""
+    if not t.is_cuda:
+        raise RuntimeError(
+            f"torchkbnufft_b200 is a CUDA-only (sm_100a) engine with no CPU fallback: `{what}` is on "
+            f"{t.device}. Move the module and its inputs to a CUDA device."
+        )
+
+
+def engine_dtype(cdtype: torch.dtype) -> int:
+    if cdtype == torch.complex64:
+        return _lib.C64
+    if cdtype == torch.complex128:
+        return _lib.C128
+    raise TypeError(f"unsupported complex dtype {cdtype}")
+
+
+def current_stream_ptr(device: torch.device) -> ctypes.c_void_p:
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _tkey(t: Tensor) -> tuple:
+    return (t.data_ptr(), t._version, tuple(t.shape), tuple(t.stride()), t.dtype, t.device.index)
+
+
+class Geometry:
+    """Host copy of the operator buffers + the ``b2n_geom`` struct."""
+
+    def __init__(self, tables: Sequence[Tensor], n_shift: Tensor, numpoints: Tensor, table_oversamp: Tensor,
+                 grid_size: Sequence[int]):
+        self.ndim = len(tables)
+        if not 1 <= self.ndim <= _lib.MAX_DIMS:
+            raise ValueError(f"only 1-3 dimensions are supported, got {self.ndim}")
+        self.cdtype = tables[0].dtype
+        self.device = tables[0].device
+        # one host read of the small buffers per geometry (cached afterwards)
+        self.numpoints = [int(v) for v in numpoints.tolist()]
+        self.table_oversamp = [int(v) for v in table_oversamp.tolist()]
+        self.n_shift = [float(v) for v in n_shift.tolist()]
+        self.grid_size = [int(v) for v in grid_size]
+        if not (len(self.numpoints) == len(self.table_oversamp) == len(self.n_shift) == len(self.grid_size)
+                == self.ndim):
+            raise ValueError("tables, n_shift, numpoints, table_oversamp and grid_size must agree in length")
+        self.tables = [t.contiguous() for t in tables]  # strong refs keep the pointers valid
+        self.n_grid = 1
+        for k in self.grid_size:
+            self.n_grid *= k
+        self.n_offsets = 1
+        for j in self.numpoints:
+            self.n_offsets *= j
+        g = _lib.Geom()
+        g.ndim = self.ndim
+        g.dtype = engine_dtype(self.cdtype)
+        for d in range(self.ndim):
+            g.grid_size[d] = self.grid_size[d]
+            g.numpoints[d] = self.numpoints[d]
+            g.table_oversamp[d] = self.table_oversamp[d]
+            g.table_len[d] = self.tables[d].numel()
+            g.table_dev[d] = self.tables[d].data_ptr()
+            g.n_shift[d] = self.n_shift[d]
+        self.struct = g
+        self.key: tuple = ()
+
+
+def host_ints(sizes) -> Tuple[int, ...]:
+    """Integer tuple of a size argument.  Device tensors (module buffers) are read
+    once and then looked up by identity so the hot path never synchronises."""
+    if not isinstance(sizes, Tensor):
+        return tuple(int(k) for k in sizes)
+    tkey = _tkey(sizes)
+    hit = _GRID_SIZE_CACHE.get(tkey)
+    if hit is None:
+        hit = (tuple(int(k) for k in sizes.tolist()), sizes)  # keep the tensor alive with its key
+        if len(_GRID_SIZE_CACHE) > 8 * GEOM_CACHE_SIZE:
+            _GRID_SIZE_CACHE.clear()
+        _GRID_SIZE_CACHE[tkey] = hit
+    return hit[0]
+
+
+def get_geometry(tables: Sequence[Tensor], n_shift: Tensor, numpoints: Tensor, table_oversamp: Tensor,
+                 grid_size) -> Geometry:
+    """Cached :class:`Geometry` for a set of operator buffers.  ``grid_size`` may be a
+    tensor (read once) or a sequence of ints."""
+    # sizes as ints: the forward (sizes from image.shape) and the adjoint (grid_size buffer)
+    # then share one geometry and one trajectory plan
+    gkey = host_ints(grid_size)
+    key = (tuple(_tkey(t) for t in tables), _tkey(n_shift), _tkey(numpoints), _tkey(table_oversamp), gkey)
+    geo = _GEOM_CACHE.get(key)
+    if geo is not None:
+        _GEOM_CACHE.move_to_end(key)
+        return geo
+    for t in tables:
+        require_cuda(t, "tables")
+    geo = Geometry(tables, n_shift, numpoints, table_oversamp, gkey)
+    geo.key = key
+    geo._refs = (n_shift, numpoints, table_oversamp)  # keep key pointers alive
+    _GEOM_CACHE[key] = geo
+    while len(_GEOM_CACHE) > GEOM_CACHE_SIZE:
+        _GEOM_CACHE.popitem(last=False)
+    return geo
+
+
+class TrajectoryPlan:
+    """Device-resident ``b2n_points`` plan for one ``(geometry, omega)`` pair."""
+
+    def __init__(self, geo: Geometry, omega: Tensor):
+        lib = _lib.load()
+        self.geo = geo
+        self.omega = omega  # strong ref (see module docstring)
+        om = omega
+        if om.ndim == 2:
+            self.n_traj = 1
+            self.n_points = om.shape[1]
+        else:
+            self.n_traj = om.shape[0]
+            self.n_points = om.shape[2]
+        om = om.contiguous()
+        nbytes = ctypes.c_size_t(0)
+        _lib.check(lib.b2n_points_workspace_bytes(ctypes.byref(geo.struct), self.n_points, self.n_traj,
+                                                  ctypes.byref(nbytes)), "b2n_points_workspace_bytes")
+        self.workspace = torch.empty(max(int(nbytes.value), 256), dtype=torch.uint8, device=omega.device)
+        self.struct = _lib.Points()
+        with torch.cuda.device(omega.device):
+            _lib.check(
+                lib.b2n_points_build(ctypes.byref(geo.struct), om.data_ptr(), self.n_points, self.n_traj,
+                                     self.workspace.data_ptr(), self.workspace.numel(), ctypes.byref(self.struct),
+                                     current_stream_ptr(omega.device)),
+                "b2n_points_build",
+            )
+        # the build reads `om` asynchronously; keep a possible contiguous copy alive with the plan
+        self._om_contig = om
+        self.workspace.record_stream(torch.cuda.current_stream(omega.device))
+
+
+def get_plan(geo: Geometry, omega: Tensor) -> TrajectoryPlan:
+    key = (geo.key, _tkey(omega))
+    plan = _PLAN_CACHE.get(key)
+    if plan is not None:
+        _PLAN_CACHE.move_to_end(key)
+        return plan
+    plan = TrajectoryPlan(geo, omega)
+    _PLAN_CACHE[key] = plan
+    while len(_PLAN_CACHE) > PLAN_CACHE_SIZE:
+        _PLAN_CACHE.popitem(last=False)
+    return plan
+
+
+def clear_caches() -> None:
+    """Drop every cached geometry and trajectory plan (frees their device memory)."""
+    _PLAN_CACHE.clear()
+    _GEOM_CACHE.clear()
+    _GRID_SIZE_CACHE.clear()
+
+
+def normalize_omega(omega: Tensor, n_batch: int, what: str) -> Tensor:
+    """Trajectory validation shared by both directions
+    (reference: ``_nufft/interp.py:345-356`` and ``:621-633``)."""
+    if omega.ndim not in (2, 3):
+        raise ValueError("omega must have 2 or 3 dimensions.")
+    if omega.ndim == 3 and omega.shape[0] == 1:
+        omega = omega[0]  # a single trajectory is broadcast over the batch
+    if omega.ndim == 3 and not omega.shape[0] == n_batch:
+        raise ValueError(f"If omega has batch dim, omega batch dimension must match {what}.")
+    return omega

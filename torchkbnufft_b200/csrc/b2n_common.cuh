@@ -1,0 +1,61 @@
+// b2n_common.cuh -- shared helpers for libb200nufft (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/b200nufft.h"
+
+#ifdef __CUDACC__
+#define B2N_HD __host__ __device__ __forceinline__
+#define B2N_D __device__ __forceinline__
+#else
+#define B2N_HD inline
+#define B2N_D inline
+#endif
+
+namespace b2n {
+
+// thread-local error text returned by b2n_last_error()
+void set_error(const char *fmt, ...);
+int fail_arg(int code, const char *fmt, ...);
+int check_cuda(cudaError_t err, const char *what);
+
+#define B2N_CUDA_OK(expr)                                  \
+  do {                                                     \
+    int _rc = ::b2n::check_cuda((expr), #expr);            \
+    if (_rc != 0) return _rc;                              \
+  } while (0)
+
+#define B2N_LAUNCH_OK(name)                                \
+  do {                                                     \
+    int _rc = ::b2n::check_cuda(cudaGetLastError(), name); \
+    if (_rc != 0) return _rc;                              \
+  } while (0)
+
+template <typename T> struct cplx { T x, y; };
+template <> struct __align__(8) cplx<float> { float x, y; };
+template <> struct __align__(16) cplx<double> { double x, y; };
+
+template <typename T> B2N_HD cplx<T> cmul(cplx<T> a, cplx<T> b) {
+  cplx<T> r;
+  r.x = a.x * b.x - a.y * b.y;
+  r.y = a.x * b.y + a.y * b.x;
+  return r;
+}
+template <typename T> B2N_HD cplx<T> cconj(cplx<T> a) {
+  cplx<T> r;
+  r.x = a.x;
+  r.y = -a.y;
+  return r;
+}
+// acc += a * b
+template <typename T> B2N_HD void cmac(cplx<T> &acc, cplx<T> a, cplx<T> b) {
+  acc.x += a.x * b.x - a.y * b.y;
+  acc.y += a.x * b.y + a.y * b.x;
+}
+
+static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+}  // namespace b2n

@@ -1,0 +1,337 @@
+// b2n_points.cu -- trajectory plan: coordinate arithmetic, cell sort, per-point records.
+//
+// Everything that depends on the trajectory alone is computed here once and kept in
+// a caller-owned workspace (b2n_points): the reference redoes it on every call
+// (torchkbnufft/_nufft/interp.py:171-177, :129-148, :552-584, :663-686).
+#include <cub/device/device_radix_sort.cuh>
+
+#include <stdarg.h>
+#include <string.h>
+
+#include "b2n_common.cuh"
+#include "b2n_math.cuh"
+
+namespace b2n {
+
+static thread_local char g_error[512] = "";
+
+void set_error(const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_error, sizeof(g_error), fmt, ap);
+  va_end(ap);
+}
+
+int fail_arg(int code, const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_error, sizeof(g_error), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+int check_cuda(cudaError_t err, const char *what) {
+  if (err == cudaSuccess) return 0;
+  set_error("CUDA error %d (%s) at %s", (int)err, cudaGetErrorString(err), what);
+  return (int)err;
+}
+
+// device-side copy of the geometry in the working precision
+template <typename T> struct GeomT {
+  int ndim;
+  int J[B2N_MAX_DIMS];
+  int L[B2N_MAX_DIMS];
+  int coef_off[B2N_MAX_DIMS];
+  int coef_stride;
+  int64_t K[B2N_MAX_DIMS];
+  int64_t Kprod;
+  int64_t table_len[B2N_MAX_DIMS];
+  const cplx<T> *table[B2N_MAX_DIMS];
+  T n_shift[B2N_MAX_DIMS];
+};
+
+template <typename T> static GeomT<T> make_geom(const b2n_geom *g) {
+  GeomT<T> r;
+  memset(&r, 0, sizeof(r));
+  r.ndim = g->ndim;
+  r.Kprod = 1;
+  int off = 0;
+  for (int d = 0; d < g->ndim; ++d) {
+    r.J[d] = g->numpoints[d];
+    r.L[d] = g->table_oversamp[d];
+    r.K[d] = g->grid_size[d];
+    r.Kprod *= g->grid_size[d];
+    r.table_len[d] = g->table_len[d];
+    r.table[d] = (const cplx<T> *)g->table_dev[d];
+    r.n_shift[d] = (T)g->n_shift[d];
+    r.coef_off[d] = off;
+    off += g->numpoints[d];
+  }
+  r.coef_stride = off;
+  return r;
+}
+
+int validate_geom(const b2n_geom *g, bool need_tables) {
+  if (!g) return fail_arg(B2N_E_ARG, "geom is NULL");
+  if (g->ndim < 1 || g->ndim > B2N_MAX_DIMS) return fail_arg(B2N_E_RANGE, "ndim=%d not in 1..3", g->ndim);
+  if (g->dtype != B2N_C64 && g->dtype != B2N_C128) return fail_arg(B2N_E_ARG, "bad dtype %d", g->dtype);
+  for (int d = 0; d < g->ndim; ++d) {
+    if (g->grid_size[d] < 1) return fail_arg(B2N_E_ARG, "grid_size[%d]=%lld", d, (long long)g->grid_size[d]);
+    if (g->numpoints[d] < 1 || g->numpoints[d] > B2N_MAX_NUMPOINTS)
+      return fail_arg(B2N_E_RANGE, "numpoints[%d]=%d not in 1..%d", d, g->numpoints[d], B2N_MAX_NUMPOINTS);
+    if (g->table_oversamp[d] < 1) return fail_arg(B2N_E_ARG, "table_oversamp[%d]=%d", d, g->table_oversamp[d]);
+    if (need_tables) {
+      if (!g->table_dev[d]) return fail_arg(B2N_E_ARG, "table_dev[%d] is NULL", d);
+      if (g->table_len[d] < (int64_t)g->numpoints[d] * g->table_oversamp[d] + 1)
+        return fail_arg(B2N_E_ARG, "table_len[%d]=%lld shorter than J*L+1", d, (long long)g->table_len[d]);
+    }
+  }
+  return 0;
+}
+
+// ---- kernels ----------------------------------------------------------------
+template <typename T>
+__global__ void k_point_keys(GeomT<T> g, const T *__restrict__ omega, int64_t M, int64_t total,
+                             uint32_t *__restrict__ keys, uint32_t *__restrict__ idx) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int64_t t = i / M, m = i - t * M;
+  const T *om = omega + t * g.ndim * M + m;
+  int64_t cell = 0;
+  for (int d = 0; d < g.ndim; ++d) {
+    T tm;
+    int64_t base;
+    locate<T>(om[d * M], g.K[d], g.J[d], tm, base);
+    cell = cell * g.K[d] + wrap_cell(base, g.K[d]);
+  }
+  keys[i] = (uint32_t)(t * g.Kprod + cell);
+  idx[i] = (uint32_t)i;
+}
+
+template <typename T>
+__global__ void k_point_records(GeomT<T> g, const T *__restrict__ omega, int64_t M, int64_t total,
+                                const uint32_t *__restrict__ sorted_idx, int32_t *__restrict__ perm,
+                                int32_t *__restrict__ base_out, cplx<T> *__restrict__ coef,
+                                cplx<T> *__restrict__ phase) {
+  const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= total) return;
+  const int64_t i = sorted_idx[s];
+  const int64_t t = i / M, m = i - t * M;
+  const T *om = omega + t * g.ndim * M + m;
+  perm[s] = (int32_t)m;
+  T omv[B2N_MAX_DIMS];
+  for (int d = 0; d < g.ndim; ++d) {
+    omv[d] = om[d * M];
+    T tm;
+    int64_t base;
+    locate<T>(omv[d], g.K[d], g.J[d], tm, base);
+    base_out[s * g.ndim + d] = (int32_t)wrap_cell(base, g.K[d]);
+    cplx<T> *rec = coef + s * g.coef_stride + g.coef_off[d];
+    for (int j = 0; j < g.J[d]; ++j) {
+      int64_t ti = table_index<T>(tm, base + j, g.J[d], g.L[d]);
+      if (ti < 0) ti += g.table_len[d];  // torch indexing wraps a negative index
+      ti = ti < 0 ? 0 : (ti >= g.table_len[d] ? g.table_len[d] - 1 : ti);
+      rec[j] = g.table[d][ti];
+    }
+  }
+  const T arg = phase_arg<T>(omv, g.ndim, g.n_shift);
+  T sn, cs;
+  sincos(arg, &sn, &cs);
+  cplx<T> p;
+  p.x = cs;
+  p.y = sn;
+  phase[s] = p;
+}
+
+// cell_start[c] = first sorted slot whose key >= c  (c in [0, n_cells])
+__global__ void k_cell_start(const uint32_t *__restrict__ keys, int64_t total, int64_t n_cells,
+                             int32_t *__restrict__ cell_start) {
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c > n_cells) return;
+  int64_t lo = 0, hi = total;
+  while (lo < hi) {
+    const int64_t mid = (lo + hi) >> 1;
+    if ((int64_t)keys[mid] < c) lo = mid + 1; else hi = mid;
+  }
+  cell_start[c] = (int32_t)lo;
+}
+
+template <typename T>
+__global__ void k_export_indices(GeomT<T> g, const T *__restrict__ omega, int64_t M, int64_t W,
+                                 int64_t *__restrict__ arr_ind, int32_t *__restrict__ tab_idx) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= W * M) return;
+  const int64_t w = i / M, m = i - w * M;
+  int j[B2N_MAX_DIMS];
+  int64_t rem = w;
+  for (int d = g.ndim - 1; d >= 0; --d) {
+    j[d] = (int)(rem % g.J[d]);
+    rem /= g.J[d];
+  }
+  int64_t flat = 0;
+  for (int d = 0; d < g.ndim; ++d) {
+    T tm;
+    int64_t base;
+    locate<T>(omega[d * M + m], g.K[d], g.J[d], tm, base);
+    const int64_t cell = base + j[d];
+    if (tab_idx) tab_idx[(w * g.ndim + d) * M + m] = (int32_t)table_index<T>(tm, cell, g.J[d], g.L[d]);
+    flat = flat * g.K[d] + wrap_cell(cell, g.K[d]);
+  }
+  arr_ind[i] = flat;
+}
+
+// ---- workspace carving --------------------------------------------------------
+struct Carve {
+  size_t perm, base, coef, phase, cell_start, keys, keys_in, idx_in, idx_out, cub, total, cub_bytes;
+};
+
+static int sort_bits(int64_t n_keys) {
+  int bits = 1;
+  while (bits < 32 && ((int64_t)1 << bits) < n_keys) ++bits;
+  return bits;
+}
+
+static int carve(const b2n_geom *g, int64_t M, int64_t n_traj, Carve *c) {
+  int64_t Kp = 1;
+  int stride = 0;
+  for (int d = 0; d < g->ndim; ++d) {
+    Kp *= g->grid_size[d];
+    stride += g->numpoints[d];
+  }
+  const int64_t total = M * n_traj, n_cells = Kp * n_traj;
+  if (total >= ((int64_t)1 << 31) - 1 || n_cells >= ((int64_t)1 << 32) - 1)
+    return fail_arg(B2N_E_RANGE, "n_traj*M=%lld or n_traj*prod(K)=%lld exceeds the 32-bit plan limit",
+                    (long long)total, (long long)n_cells);
+  const size_t csz = g->dtype == B2N_C64 ? 8 : 16;
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    size_t at = off;
+    off = align_up(off + bytes, 256);
+    return at;
+  };
+  c->perm = take(sizeof(int32_t) * total);
+  c->base = take(sizeof(int32_t) * total * g->ndim);
+  c->coef = take(csz * total * stride);
+  c->phase = take(csz * total);
+  c->cell_start = take(sizeof(int32_t) * (n_cells + 1));
+  c->keys = take(sizeof(uint32_t) * total);
+  c->keys_in = take(sizeof(uint32_t) * total);
+  c->idx_in = take(sizeof(uint32_t) * total);
+  c->idx_out = take(sizeof(uint32_t) * total);
+  size_t cub_bytes = 0;
+  cudaError_t err = cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, (const uint32_t *)nullptr, (uint32_t *)nullptr,
+                                                    (const uint32_t *)nullptr, (uint32_t *)nullptr, (int)total, 0,
+                                                    sort_bits(n_cells));
+  if (err != cudaSuccess) return check_cuda(err, "cub::DeviceRadixSort::SortPairs(size query)");
+  c->cub_bytes = cub_bytes;
+  c->cub = take(cub_bytes + 256);
+  c->total = off;
+  return 0;
+}
+
+template <typename T>
+static int build_impl(const b2n_geom *geom, const void *omega, int64_t M, int64_t n_traj, char *ws, const Carve &c,
+                      b2n_points *out, cudaStream_t st) {
+  GeomT<T> g = make_geom<T>(geom);
+  const int64_t total = M * n_traj, n_cells = g.Kprod * n_traj;
+  out->n_points = M;
+  out->n_traj = n_traj;
+  out->ndim = geom->ndim;
+  out->dtype = geom->dtype;
+  out->coef_stride = g.coef_stride;
+  out->reserved = 0;
+  out->perm = (int32_t *)(ws + c.perm);
+  out->base = (int32_t *)(ws + c.base);
+  out->coef = ws + c.coef;
+  out->phase = ws + c.phase;
+  out->cell_start = (int32_t *)(ws + c.cell_start);
+  out->keys = (uint32_t *)(ws + c.keys);
+  uint32_t *keys_in = (uint32_t *)(ws + c.keys_in), *idx_in = (uint32_t *)(ws + c.idx_in),
+           *idx_out = (uint32_t *)(ws + c.idx_out);
+  const int threads = 256;
+  if (total > 0) {
+    k_point_keys<T><<<(unsigned)ceil_div(total, threads), threads, 0, st>>>(g, (const T *)omega, M, total, keys_in,
+                                                                            idx_in);
+    B2N_LAUNCH_OK("k_point_keys");
+    size_t cub_bytes = c.cub_bytes;
+    // stable LSD radix sort on the integer cell key: points of one cell keep their original order
+    B2N_CUDA_OK(cub::DeviceRadixSort::SortPairs(ws + c.cub, cub_bytes, keys_in, out->keys, idx_in, idx_out, (int)total,
+                                                0, sort_bits(n_cells), st));
+    k_point_records<T><<<(unsigned)ceil_div(total, threads), threads, 0, st>>>(
+        g, (const T *)omega, M, total, idx_out, out->perm, out->base, (cplx<T> *)out->coef, (cplx<T> *)out->phase);
+    B2N_LAUNCH_OK("k_point_records");
+  }
+  k_cell_start<<<(unsigned)ceil_div(n_cells + 1, threads), threads, 0, st>>>(out->keys, total, n_cells,
+                                                                             out->cell_start);
+  B2N_LAUNCH_OK("k_cell_start");
+  return 0;
+}
+
+}  // namespace b2n
+
+using namespace b2n;
+
+extern "C" int b2n_abi_version(void) { return B2N_ABI_VERSION; }
+extern "C" const char *b2n_last_error(void) { return g_error; }
+
+extern "C" int b2n_device_count(void) {
+  int n = 0;
+  cudaError_t err = cudaGetDeviceCount(&n);
+  if (err != cudaSuccess) {
+    check_cuda(err, "cudaGetDeviceCount");  // records the reason for b2n_last_error()
+    (void)cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+extern "C" int b2n_points_workspace_bytes(const b2n_geom *geom, int64_t n_points, int64_t n_traj, size_t *bytes) {
+  int rc = validate_geom(geom, false);
+  if (rc) return rc;
+  if (!bytes || n_points < 0 || n_traj < 1) return fail_arg(B2N_E_ARG, "bad n_points/n_traj/bytes");
+  Carve c;
+  rc = carve(geom, n_points, n_traj, &c);
+  if (rc) return rc;
+  *bytes = c.total;
+  return 0;
+}
+
+extern "C" int b2n_points_build(const b2n_geom *geom, const void *omega_dev, int64_t n_points, int64_t n_traj,
+                                void *workspace_dev, size_t workspace_bytes, b2n_points *out, void *stream) {
+  int rc = validate_geom(geom, true);
+  if (rc) return rc;
+  if (!out || n_points < 0 || n_traj < 1) return fail_arg(B2N_E_ARG, "bad n_points/n_traj/out");
+  if (n_points > 0 && !omega_dev) return fail_arg(B2N_E_ARG, "omega_dev is NULL");
+  Carve c;
+  rc = carve(geom, n_points, n_traj, &c);
+  if (rc) return rc;
+  if (!workspace_dev || workspace_bytes < c.total || ((uintptr_t)workspace_dev & 255))
+    return fail_arg(B2N_E_WORKSPACE, "workspace needs %zu bytes, 256-byte aligned (got %zu)", c.total,
+                    workspace_bytes);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (geom->dtype == B2N_C64) return build_impl<float>(geom, omega_dev, n_points, n_traj, (char *)workspace_dev, c, out, st);
+  return build_impl<double>(geom, omega_dev, n_points, n_traj, (char *)workspace_dev, c, out, st);
+}
+
+extern "C" int b2n_export_indices(const b2n_geom *geom, const void *omega_dev, int64_t n_points, int64_t *arr_ind_dev,
+                                  int32_t *tab_idx_dev, void *stream) {
+  int rc = validate_geom(geom, false);
+  if (rc) return rc;
+  if (!omega_dev || !arr_ind_dev || n_points < 0) return fail_arg(B2N_E_ARG, "bad omega/arr_ind/n_points");
+  int64_t W = 1;
+  for (int d = 0; d < geom->ndim; ++d) W *= geom->numpoints[d];
+  if (n_points == 0) return 0;
+  const int threads = 256;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (geom->dtype == B2N_C64) {
+    GeomT<float> g = make_geom<float>(geom);
+    k_export_indices<float><<<(unsigned)ceil_div(W * n_points, threads), threads, 0, st>>>(
+        g, (const float *)omega_dev, n_points, W, arr_ind_dev, tab_idx_dev);
+  } else {
+    GeomT<double> g = make_geom<double>(geom);
+    k_export_indices<double><<<(unsigned)ceil_div(W * n_points, threads), threads, 0, st>>>(
+        g, (const double *)omega_dev, n_points, W, arr_ind_dev, tab_idx_dev);
+  }
+  B2N_LAUNCH_OK("k_export_indices");
+  return 0;
+}

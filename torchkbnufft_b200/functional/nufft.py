@@ -1,0 +1,106 @@
+"""Functional NUFFT API (stateless), mirroring ``torchkbnufft/functional/nufft.py``
+(``kb_table_nufft`` :126-191, ``kb_table_nufft_adjoint`` :194-260) and
+``fft_filter`` (``_nufft/fft.py:121-173``)."""
+from __future__ import annotations
+
+from typing import List, Optional, Tuple
+
+import torch
+from torch import Tensor
+
+from .._autograd.interp import KbTableInterpAdjoint, KbTableInterpForward
+from .._autograd.nufft import ApodPad, CropApodCoilsum, ToeplitzFilter
+from .._nufft import fft as _fft
+from .._nufft.plan import host_ints as _ints
+from .interp import _SPMAT_MSG, with_complex_view
+
+
+def sense_nufft_forward(image: Tensor, smaps: Optional[Tensor], scaling_coef: Tensor, grid_size, omega: Tensor,
+                        tables: List[Tensor], n_shift: Tensor, numpoints: Tensor, table_oversamp: Tensor,
+                        offsets: Tensor, norm: Optional[str] = None) -> Tensor:
+    """Complex-only core of the forward NUFFT with the optional SENSE multiply fused
+    into the apodisation/zero-pad kernel."""
+    normalized = _fft.check_norm(norm)
+    if image.shape[0] == 0:
+        raise ValueError("image has an empty batch dimension")
+    if smaps is not None and (image.shape[1] != 1 or smaps.requires_grad):
+        image, smaps = image * smaps, None  # general broadcast / d(smaps): plain torch multiply
+    grid_size = _ints(grid_size)
+    grid = ApodPad.apply(image, smaps, scaling_coef, grid_size, _fft.ortho_scale(grid_size, normalized))
+    grid = _fft.fft_grid(grid, len(grid_size), inverse=False)
+    return KbTableInterpForward.apply(grid, omega, tables, n_shift, numpoints, table_oversamp, offsets)
+
+
+def sense_nufft_adjoint(data: Tensor, smaps: Optional[Tensor], scaling_coef: Tensor, im_size, grid_size,
+                        omega: Tensor, tables: List[Tensor], n_shift: Tensor, numpoints: Tensor,
+                        table_oversamp: Tensor, offsets: Tensor, norm: Optional[str] = None) -> Tensor:
+    """Complex-only core of the adjoint NUFFT with crop, conjugate apodisation and the
+    SENSE coil combination fused into one kernel."""
+    normalized = _fft.check_norm(norm)
+    grid_sizes = _ints(grid_size)
+    grid = KbTableInterpAdjoint.apply(data, omega, tables, n_shift, numpoints, table_oversamp, offsets, grid_size)
+    grid = _fft.fft_grid(grid, len(grid_sizes), inverse=True)
+    scale = _fft.ortho_scale(grid_sizes, normalized)
+    if smaps is not None and smaps.requires_grad:
+        image = CropApodCoilsum.apply(grid, None, scaling_coef, _ints(im_size), scale)
+        return torch.sum(image * smaps.conj(), dim=1, keepdim=True)
+    return CropApodCoilsum.apply(grid, smaps, scaling_coef, _ints(im_size), scale)
+
+
+def kb_table_nufft(image: Tensor, scaling_coef: Tensor, im_size: Tensor, grid_size: Tensor, omega: Tensor,
+                   tables: List[Tensor], n_shift: Tensor, numpoints: Tensor, table_oversamp: Tensor, offsets: Tensor,
+                   norm: Optional[str] = None) -> Tensor:
+    """Forward NUFFT with table interpolation: ``image (B, C, *N)`` -> ``(B, C, M)``."""
+    return with_complex_view(
+        lambda x: sense_nufft_forward(x, None, scaling_coef, grid_size, omega, tables, n_shift, numpoints,
+                                      table_oversamp, offsets, norm),
+        image,
+    )
+
+
+def kb_table_nufft_adjoint(data: Tensor, scaling_coef: Tensor, im_size: Tensor, grid_size: Tensor, omega: Tensor,
+                           tables: List[Tensor], n_shift: Tensor, numpoints: Tensor, table_oversamp: Tensor,
+                           offsets: Tensor, norm: Optional[str] = None) -> Tensor:
+    """Adjoint NUFFT with table interpolation: ``data (B, C, M)`` -> ``(B, C, *N)``."""
+    return with_complex_view(
+        lambda x: sense_nufft_adjoint(x, None, scaling_coef, im_size, grid_size, omega, tables, n_shift, numpoints,
+                                      table_oversamp, offsets, norm),
+        data,
+    )
+
+
+def toeplitz_filter(image: Tensor, kernel: Tensor, smaps: Optional[Tensor], norm: Optional[str]) -> Tensor:
+    """Complex-only batched Toeplitz normal operator (fused kernels + cuFFT)."""
+    normalized = _fft.check_norm(norm)
+    if kernel.requires_grad or (smaps is not None and smaps.requires_grad):
+        # differentiable-in-everything composition out of the same fused pieces
+        ndim = image.ndim - 2
+        grid_size = tuple(kernel.shape[-ndim:])
+        n_grid = 1
+        for k in grid_size:
+            n_grid *= k
+        x = image if smaps is None else image * smaps
+        grid = _fft.fft_grid(ApodPad.apply(x, None, None, grid_size, 1.0), ndim, inverse=False)
+        kern = kernel if kernel.ndim == ndim else kernel.unsqueeze(1)
+        grid = _fft.fft_grid(grid * kern * ((1.0 / n_grid) if normalized else 1.0), ndim, inverse=True)
+        out = CropApodCoilsum.apply(grid, None, None, tuple(image.shape[2:]), 1.0)
+        return out if smaps is None else torch.sum(out * smaps.conj(), dim=1, keepdim=True)
+    if smaps is not None and image.shape[1] != 1:
+        raise ValueError("with smaps, image must have a single coil dimension (B, 1, *N)")
+    return ToeplitzFilter.apply(image, kernel, smaps, normalized)
+
+
+def fft_filter(image: Tensor, kernel: Tensor, norm: Optional[str] = "ortho") -> Tensor:
+    """``crop(IFFT(kernel * FFT(zero_pad(image))))`` on the grid of ``kernel``
+    (reference: ``_nufft/fft.py:121-173``)."""
+    return toeplitz_filter(image, kernel, None, norm)
+
+
+def kb_spmat_nufft(image: Tensor, scaling_coef: Tensor, im_size: Tensor, grid_size: Tensor,
+                   interp_mats: Tuple[Tensor, Tensor], norm: Optional[str] = None) -> Tensor:
+    raise NotImplementedError(_SPMAT_MSG)
+
+
+def kb_spmat_nufft_adjoint(data: Tensor, scaling_coef: Tensor, im_size: Tensor, grid_size: Tensor,
+                           interp_mats: Tuple[Tensor, Tensor], norm: Optional[str] = None) -> Tensor:
+    raise NotImplementedError(_SPMAT_MSG)
