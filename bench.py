@@ -1,0 +1,382 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: forward + adjoint SENSE NUFFT (complex64).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg2] [--impl b200|reference]
+
+One *step* = one forward SENSE NUFFT (image -> k-space) followed by one adjoint SENSE
+NUFFT (k-space -> coil-combined image) of the workload, through the public modules
+(``KbNufft`` / ``KbNufftAdjoint``).  The metric is non-uniform points per second
+counted in coil-points: ``2 * B * C * M`` per step and per GPU.  With N > 1 every
+rank runs its own slices (batch sharding, no data-path collective): weak scaling.
+
+Rank 0 prints ONE JSON line (see the keys below).  ``--impl reference`` times the
+CPU oracle port of the reference's algorithm on the host cores instead.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "NU points/sec (fwd+adj SENSE NUFFT, c64)"
+UNIT = "coil-points/s"
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def algorithmic_bytes(wl, B):
+    """compulsory HBM traffic, every tensor touched once, each FFT one
+    read + one write of the oversampled grid (complex64 = 8 B, omega float32)."""
+    N = int(np.prod(wl.im_size))
+    K = int(np.prod(wl.grid_size))
+    C, M, d = wl.n_coils, wl.n_points, len(wl.im_size)
+    fwd = 8 * (B * N + C * N + N + 4 * B * C * K + B * C * M) + 4 * d * M
+    adj = 8 * (B * C * M + 3 * B * C * K + B * C * N + C * N + B * N + N) + 4 * d * M
+    interp = 8 * (B * C * K + B * C * M) + 4 * d * M  # each direction, interpolation kernel alone
+    return fwd, adj, interp
+
+
+class ClockSampler:
+    """nvidia-smi clock / throttle-reason sampling during the timed region."""
+
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu_index = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.gpu_index)], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        try:
+            for line in open(self.path):
+                parts = [p.strip() for p in line.split(",")]
+                if len(parts) < 9:
+                    continue
+                try:
+                    sm.append(float(parts[1]))
+                    smax.append(float(parts[2]))
+                except ValueError:
+                    continue
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"),
+                                     parts[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(smax), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+def oracle_pair_seconds(wl, B, steps, warmup, threads):
+    """Time the CPU oracle (port of the reference's algorithm) on the same workload."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import torch
+
+    import kbnufft_oracle as orc
+    from torchkbnufft_b200 import workloads
+    from torchkbnufft_b200._nufft import utils
+
+    image, smaps, kdata, omega = workloads.make_inputs(wl, seed=0, n_batch=B)
+    pre = utils.init_fn(im_size=wl.im_size, dtype=torch.complex64)
+    scaling = utils.compute_scaling_coefs(pre.im_size.tolist(), pre.grid_size.tolist(), pre.numpoints.tolist(),
+                                          pre.alpha.tolist(), pre.order.tolist()).to(torch.complex64).numpy()
+    tables = [t.numpy() for t in pre.tables]
+    J, L, ns = pre.numpoints.tolist(), pre.table_oversamp.tolist(), pre.n_shift.numpy()
+    args = (omega, tables, ns, J, L, scaling, wl.im_size, wl.grid_size)
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        k = orc.nufft_forward(image, *args, smaps=smaps, nthreads=threads)
+        orc.nufft_adjoint(k, *args, smaps=smaps, nthreads=threads)
+        if it >= warmup:
+            times.append(time.perf_counter() - t0)
+    return times
+
+
+def run_reference(args, wl, rank):
+    """--impl reference: the oracle port on all host cores (rank 0 only)."""
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    B = wl.n_batch
+    frac = 1.0
+    sample = wl
+    # bound the sample so the whole run ends within minutes (3-D / batched configs)
+    est_units = 2 * B * wl.n_coils * wl.n_points * int(np.prod([6] * len(wl.im_size)))
+    if est_units > 4e9:
+        frac = 4e9 / est_units
+        sample = wl.scaled(frac)
+    times = oracle_pair_seconds(sample, B, args.steps, max(1, args.warmup), threads)
+    units = 2 * B * sample.n_coils * sample.n_points
+    total = sum(times)
+    value = units * len(times) / total
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "c64", "data": "synthetic",
+        "config": {"workload": wl.name, "description": wl.description, "batch_per_gpu": B,
+                   "sample": f"{sample.n_spokes}/{wl.n_spokes} spokes" if frac < 1 else "full workload"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"full {wl.name} fwd+adj pair x{len(times)}" if frac == 1.0 else
+                         f"{sample.n_spokes} of {wl.n_spokes} spokes, fwd+adj pair x{len(times)}"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--workload", default="cfg2")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--adjoint-mode", default=None, choices=["atomic", "sorted"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--breakdown", action="store_true", help="print per-stage device times to stderr")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    from torchkbnufft_b200 import workloads
+
+    wl = workloads.WORKLOADS[args.workload]
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, wl, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    import torchkbnufft_b200 as tkbn
+    from torchkbnufft_b200 import _lib
+    from torchkbnufft_b200._nufft import fft as eng_fft
+    from torchkbnufft_b200._nufft import interp as eng_interp
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (the engine has no CPU path); "
+                         "use --impl reference for the CPU oracle timing")
+    _lib.load()  # fail loudly if the native library is missing
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    if args.adjoint_mode:
+        tkbn.set_adjoint_mode(args.adjoint_mode)
+
+    B = wl.n_batch if world == 1 else max(1, wl.n_batch // world) if wl.n_batch > 1 else 1
+    image, smaps, kdata, omega = workloads.make_inputs(wl, seed=rank, n_batch=B)
+    omega = wl.trajectory(np.float32)
+    nu = tkbn.KbNufft(im_size=wl.im_size, dtype=torch.complex64).to(dev)
+    na = tkbn.KbNufftAdjoint(im_size=wl.im_size, dtype=torch.complex64).to(dev)
+    x, s, y, om = (torch.from_numpy(a).to(dev) for a in (image, smaps, kdata, omega))
+    flush = torch.empty(512 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def step():
+        k = nu(x, om, smaps=s)
+        return k, na(k, om, smaps=s)
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+
+    # ---- timed region: exactly K steps, device time, L2 flushed between steps -----------------
+    # Events also bracket the two interpolation kernels (the dominant kernels) inside the step.
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    sampler = ClockSampler(local_rank)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler.start()
+    eng_interp.kernel_timer = eng_interp.KernelTimer()  # events around the two interpolation launches
+    for i in range(args.steps):
+        flush.fill_(i & 0xFF)
+        starts[i].record()
+        step()
+        ends[i].record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    clocks = sampler.stop()
+    timer, eng_interp.kernel_timer = eng_interp.kernel_timer, None
+    step_ms = [a.elapsed_time(b) for a, b in zip(starts, ends)]
+    total_ms = sum(step_ms)
+    if world > 1:
+        t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    units_per_step = 2 * B * wl.n_coils * wl.n_points
+    value = world * units_per_step * args.steps / (total_ms * 1e-3)
+
+    # ---- per-stage device times (same launches, separate pass) --------------------------------
+    geo_args = (nu.tables, nu.n_shift, nu.numpoints, nu.table_oversamp)
+    grid_size = tuple(wl.grid_size)
+    ndim = len(grid_size)
+
+    def stage_times(reps):
+        names = ["apod_pad", "fft", "interp_fwd", "interp_adj", "ifft", "crop_coilsum"]
+        acc = {n: [] for n in names}
+        for r in range(reps):
+            flush.fill_(r & 0xFF)
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(7)]
+            ev[0].record()
+            g = eng_fft.apod_pad(x, grid_size, s, nu.scaling_coef, 1.0)
+            ev[1].record()
+            g = eng_fft.fft_grid(g, ndim, inverse=False)
+            ev[2].record()
+            k = eng_interp.table_interp(g, om, *geo_args)
+            ev[3].record()
+            g2 = eng_interp.table_interp_adjoint(k, om, *geo_args, None, nu.grid_size)
+            ev[4].record()
+            g2 = eng_fft.fft_grid(g2, ndim, inverse=True)
+            ev[5].record()
+            eng_fft.crop_apod_coilsum(g2, wl.im_size, s, nu.scaling_coef, 1.0)
+            ev[6].record()
+            torch.cuda.synchronize()
+            for j, n in enumerate(names):
+                acc[n].append(ev[j].elapsed_time(ev[j + 1]))
+        return {n: statistics.mean(v) for n, v in acc.items()}
+
+    stages = stage_times(max(5, min(20, args.steps)))
+    fwd_b, adj_b, interp_b = algorithmic_bytes(wl, B)
+    peak, peak_src = load_peaks()
+    live = {n: timer.mean_ms(n) for n in ("interp_fwd", "interp_adj")}  # measured inside the timed steps
+    dom = "interp_adj" if live["interp_adj"] >= live["interp_fwd"] else "interp_fwd"
+    achieved = interp_b / (live[dom] * 1e-3) / 1e9
+    pair_achieved = (fwd_b + adj_b) / (total_ms / args.steps * 1e-3) / 1e9
+
+    # ---- end to end through the public API with HOST buffers ----------------------------------
+    e2e = None
+    try:
+        hx, hs, hy, hom = (torch.from_numpy(a).pin_memory() for a in (image, smaps, kdata, omega))
+        dx, ds, dy, dom_t = (torch.empty_like(t, device=dev) for t in (hx, hs, hy, hom))
+        hk = torch.empty((B, wl.n_coils, wl.n_points), dtype=torch.complex64).pin_memory()
+        hi = torch.empty((B, 1) + tuple(wl.im_size), dtype=torch.complex64).pin_memory()
+
+        def e2e_step():
+            dx.copy_(hx, non_blocking=True)
+            ds.copy_(hs, non_blocking=True)
+            dom_t.copy_(hom, non_blocking=True)  # new trajectory contents -> plan is rebuilt
+            hk.copy_(nu(dx, dom_t, smaps=ds), non_blocking=True)
+            dy.copy_(hk, non_blocking=True)
+            hi.copy_(na(dy, dom_t, smaps=ds), non_blocking=True)
+
+        for _ in range(3):
+            e2e_step()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        n_e2e = max(5, min(20, args.steps))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n_e2e):
+            e2e_step()
+        e1.record()
+        torch.cuda.synchronize()
+        e2e_ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e2e_ms = float(t.item())
+        h2d = sum(t.numel() * t.element_size() for t in (hx, hs, hom, hy))
+        d2h = sum(t.numel() * t.element_size() for t in (hk, hi))
+        e2e = {"value": world * units_per_step * n_e2e / (e2e_ms * 1e-3), "unit": UNIT,
+               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / n_e2e,
+               "note": "pinned host buffers; image, smaps, trajectory and k-space copied every step, "
+                       "trajectory plan rebuilt every step"}
+    except Exception as exc:  # pragma: no cover
+        e2e = {"error": repr(exc)}
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        sample = wl
+        est = 2 * B * wl.n_coils * wl.n_points * 6 ** ndim
+        if est > 2e9:
+            sample = wl.scaled(2e9 / est)
+        times = oracle_pair_seconds(sample, B, 3, 1, threads)
+        cpu_units = 2 * B * sample.n_coils * sample.n_points
+        cpu_baseline = {"value": cpu_units / statistics.mean(times), "unit": UNIT, "cores": threads, "kind": "port",
+                        "sample": (f"full {wl.name} fwd+adj pair x3" if sample is wl else
+                                   f"{sample.n_spokes} of {wl.n_spokes} spokes, fwd+adj pair x3")}
+
+    if rank == 0:
+        if args.breakdown:
+            print("stage ms:", {k: round(v, 4) for k, v in stages.items()}, file=sys.stderr)
+            print("step ms: min %.4f median %.4f max %.4f" % (min(step_ms), statistics.median(step_ms), max(step_ms)),
+                  file=sys.stderr)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "c64", "data": "synthetic",
+            "config": {"workload": wl.name, "description": wl.description, "batch_per_gpu": B,
+                       "coils": wl.n_coils, "points": wl.n_points, "im_size": list(wl.im_size),
+                       "grid_size": list(wl.grid_size), "numpoints": 6, "adjoint_mode": tkbn.get_adjoint_mode(),
+                       "parallelism": f"batch-sharded x{world} (no collective)",
+                       "l2": "512 MiB buffer written between timed steps (L2 flush)",
+                       "plan": "trajectory plan cached across steps (built in warm-up)"},
+            "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "kernel_ms": live[dom], "kernels_ms_in_step": live,
+                         "algorithmic_bytes": interp_b,
+                         "pair_algorithmic_bytes": fwd_b + adj_b, "pair_achieved": pair_achieved,
+                         "pair_frac": pair_achieved / peak},
+            "stages_ms": {k: round(v, 5) for k, v in stages.items()},
+            "cpu_baseline": cpu_baseline,
+            "e2e": e2e,
+            "gpu_launches": 4 * args.steps,
+            "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

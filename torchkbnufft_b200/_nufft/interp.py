@@ -38,6 +38,27 @@ def get_adjoint_mode() -> str:
     return _default_adjoint_mode
 
 
+class KernelTimer:
+    """Optional CUDA-event bracket around the two interpolation launches, for
+    benchmarks (``bench.py`` installs one during its timed region)."""
+
+    def __init__(self):
+        self.events = {}
+
+    def bracket(self, name: str, device):
+        start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        self.events.setdefault(name, []).append((start, stop))
+        start.record(torch.cuda.current_stream(device))
+        return stop
+
+    def mean_ms(self, name: str) -> float:
+        pairs = self.events.get(name, [])
+        return sum(a.elapsed_time(b) for a, b in pairs) / max(len(pairs), 1)
+
+
+kernel_timer: Optional[KernelTimer] = None
+
+
 def _check_offsets(offsets: Optional[Tensor], n_offsets: int, ndim: int) -> None:
     # The engine always visits the full row-major neighbourhood (the only thing the
     # reference's modules ever pass, _nufft/utils.py:329); a custom subset is rejected.
@@ -90,11 +111,14 @@ def table_interp(
     if out.numel() == 0:
         return out
     with torch.cuda.device(image.device):
+        stop = kernel_timer.bracket("interp_fwd", image.device) if kernel_timer is not None else None
         _lib.check(
             _lib.load().b2n_interp_forward(ctypes.byref(geo.struct), ctypes.byref(plan.struct), image.data_ptr(), B, C,
                                            layout, out.data_ptr(), current_stream_ptr(image.device)),
             "b2n_interp_forward",
         )
+        if stop is not None:
+            stop.record(torch.cuda.current_stream(image.device))
     return out
 
 
@@ -137,11 +161,14 @@ def table_interp_adjoint(
         return out
     mode_id = ADJOINT_MODES[_default_adjoint_mode if mode is None else mode]
     with torch.cuda.device(data.device):
+        stop = kernel_timer.bracket("interp_adj", data.device) if kernel_timer is not None else None
         _lib.check(
             _lib.load().b2n_interp_adjoint(ctypes.byref(geo.struct), ctypes.byref(plan.struct), data.data_ptr(), B, C,
                                            layout, mode_id, out.data_ptr(), current_stream_ptr(data.device)),
             "b2n_interp_adjoint",
         )
+        if stop is not None:
+            stop.record(torch.cuda.current_stream(data.device))
     return out
 
 
