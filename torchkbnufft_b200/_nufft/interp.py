@@ -156,6 +156,8 @@ def table_interp_adjoint(
         shape = [B] + geo.grid_size + [C]
     else:
         shape = [B, C] + geo.grid_size
+    if data.numel() == 0 or plan.n_points == 0:
+        return torch.zeros(shape, dtype=data.dtype, device=data.device)  # nothing to spread
     out = torch.empty(shape, dtype=data.dtype, device=data.device)
     if out.numel() == 0:
         return out
