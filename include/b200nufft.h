@@ -66,25 +66,46 @@ typedef struct b2n_geom {
   double n_shift[B2N_MAX_DIMS];         /* fftshift phase offsets (values of the real-dtype buffer) */
 } b2n_geom;
 
-/* A trajectory plan: points sorted by wrapped base grid cell with everything that
- * depends on omega alone precomputed once (the reference recomputes all of it on
- * every call: tm / base_offset at _nufft/interp.py:171-177 and :663-670, the
- * per-offset table lookups of calc_coef_and_indices :129-148, sort_data :566-584,
- * the phase :200-203).  All pointers point into the caller's workspace. */
+/* A trajectory plan: points sorted by the TILE of their wrapped base grid cell (then by
+ * cell inside the tile, then by original order) with everything that depends on omega
+ * alone precomputed once.  The reference recomputes all of it on every call: tm /
+ * base_offset at _nufft/interp.py:171-177 and :663-670, the per-offset table lookups of
+ * calc_coef_and_indices :129-148, sort_data :566-584, the phase :200-203.
+ * Tiled cell index of base cell g: tile_id(g) * prod(tile) + local(g), row-major in both.
+ * Work is cut into sub-problems of at most sub_cap consecutive points of one tile (the
+ * dense centre of a radial trajectory yields many sub-problems, the periphery one).
+ * All pointers point into the caller's workspace. */
 typedef struct b2n_points {
   int64_t n_points;    /* M, points per trajectory */
   int64_t n_traj;      /* 1 (shared trajectory) or B (one per batch element) */
   int32_t ndim;
   int32_t dtype;
   int32_t coef_stride; /* complex entries per point record = sum_d J_d */
-  int32_t reserved;
+  int32_t sub_cap;     /* max points per sub-problem */
+  int32_t tile[B2N_MAX_DIMS];    /* tile edge (in base cells) per dimension */
+  int32_t n_tiles[B2N_MAX_DIMS]; /* tiles per dimension = ceil(K_d / tile_d) */
+  int64_t n_cells;     /* per trajectory: prod(n_tiles) * prod(tile)  (>= prod K) */
+  int64_t n_sub_max;   /* capacity of the sub_* arrays (upper bound on *n_sub) */
   int32_t *perm;       /* [n_traj*M]        sorted slot -> point index inside its trajectory */
+  int32_t *inv_perm;   /* [n_traj*M]        traj*M + point index -> sorted slot */
   int32_t *base;       /* [n_traj*M][ndim]  wrapped base cell, in [0, K_d) */
   void *coef;          /* [n_traj*M][coef_stride] complex table values T_d[t_d(j)], dims concatenated */
   void *phase;         /* [n_traj*M]        complex exp(i sum_d omega_d n_shift_d) */
-  int32_t *cell_start; /* [n_traj*prod(K)+1] CSR offsets of the sorted list per base cell */
-  uint32_t *keys;      /* [n_traj*M]        sorted keys (traj*prod(K) + base cell) */
+  int32_t *cell_start; /* [n_traj*n_cells+1] CSR offsets of the sorted list per tiled base cell */
+  uint32_t *keys;      /* [n_traj*M]        sorted keys (traj*n_cells + tiled base cell) */
+  int32_t *sub_tile;   /* [n_sub_max]       traj*prod(n_tiles) + tile id of each sub-problem */
+  int32_t *sub_start;  /* [n_sub_max]       first sorted slot */
+  int32_t *sub_count;  /* [n_sub_max]       number of points (<= sub_cap) */
+  int32_t *n_sub;      /* device scalar: number of sub-problems actually used */
 } b2n_points;
+
+/* engine options (process-wide; for A/B measurements and tests) */
+enum b2n_option {
+  B2N_OPT_TILED_KERNELS = 0, /* 1 (default): use the shared-memory tiled kernels where they apply */
+  B2N_OPT_COUNT
+};
+B2N_API int b2n_set_option(int option, int value);
+B2N_API int b2n_get_option(int option);
 
 B2N_API int b2n_abi_version(void);
 B2N_API const char *b2n_last_error(void);
@@ -111,15 +132,23 @@ B2N_API int b2n_export_indices(const b2n_geom *geom, const void *omega_dev, int6
                        int32_t *tab_idx_dev, void *stream);
 
 /* ---- table interpolation ---------------------------------------------------- */
+/* Bytes of optional device scratch for b2n_interp_forward / b2n_interp_adjoint: the tiled
+ * kernels keep the k-space samples in plan order, channel-last ([slot][coil]), in it.
+ * Without scratch (NULL / too small) the calls still work, through the generic kernels. */
+B2N_API int b2n_interp_scratch_bytes(const b2n_geom *geom, const b2n_points *pts, int64_t n_batch, int64_t n_coils,
+                                     size_t *bytes);
+
 /* Forward gather, grid -> points.  grid: (B, C, *K) or (B, *K, C) per `grid_layout`;
  * kdata out: (B, C, M).  reference: table_interp, _nufft/interp.py:315-403. */
 B2N_API int b2n_interp_forward(const b2n_geom *geom, const b2n_points *pts, const void *grid_dev, int64_t n_batch,
-                       int64_t n_coils, int grid_layout, void *kdata_dev, void *stream);
+                               int64_t n_coils, int grid_layout, void *kdata_dev, void *scratch_dev,
+                               size_t scratch_bytes, void *stream);
 
 /* Adjoint spread, points -> grid (grid fully overwritten).
  * reference: table_interp_adjoint, _nufft/interp.py:587-726 (+ accum_tensor_index_add :407-419). */
 B2N_API int b2n_interp_adjoint(const b2n_geom *geom, const b2n_points *pts, const void *kdata_dev, int64_t n_batch,
-                       int64_t n_coils, int grid_layout, int mode, void *grid_dev, void *stream);
+                               int64_t n_coils, int grid_layout, int mode, void *grid_dev, void *scratch_dev,
+                               size_t scratch_bytes, void *stream);
 
 /* ---- fused steps around the FFT --------------------------------------------- */
 /* grid = zero_pad_end( image * smaps * scaling ) * scale.

@@ -37,7 +37,7 @@ def test_library_exports_every_declared_symbol():
 def test_struct_layouts_match_header_sizes():
     # b2n_geom: 2*int32 + 3*int64 + 3*int32 + 3*int32 + 3*int64 + 3*ptr + 3*double
     assert ctypes.sizeof(_lib.Geom) == 8 + 24 + 12 + 12 + 24 + 24 + 24
-    assert ctypes.sizeof(_lib.Points) == 16 + 16 + 6 * 8
+    assert ctypes.sizeof(_lib.Points) == 16 + 16 + 12 + 12 + 16 + 11 * 8
 
 
 def test_argument_errors_are_status_codes():
@@ -57,7 +57,7 @@ def test_argument_errors_are_status_codes():
         assert status > 0 and b"CUDA error" in lib.b2n_last_error()
     g.numpoints[1] = 99
     assert lib.b2n_points_workspace_bytes(ctypes.byref(g), 100, 1, ctypes.byref(n)) == -2
-    assert lib.b2n_interp_forward(None, None, None, 1, 1, 0, None, None) == -1  # B2N_E_ARG
+    assert lib.b2n_interp_forward(None, None, None, 1, 1, 0, None, None, 0, None) == -1  # B2N_E_ARG
     assert lib.b2n_spectrum_mul(5, None, None, 1, 1, 1, 1, 0, 1.0, None) == -1
 
 

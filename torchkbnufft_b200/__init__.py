@@ -12,7 +12,7 @@ from . import functional, modules
 from ._math import absolute, complex_mult, complex_sign, conj_complex_mult, imag_exp, inner_product
 from ._nufft import utils as nufft_utils
 from ._nufft.dcomp import calc_density_compensation_function
-from ._nufft.interp import get_adjoint_mode, set_adjoint_mode
+from ._nufft.interp import get_adjoint_mode, get_tiled_kernels, set_adjoint_mode, set_tiled_kernels
 from ._nufft.plan import clear_caches
 from ._nufft.spmat import calc_tensor_spmatrix
 from ._nufft.toep import calc_toeplitz_kernel
@@ -36,8 +36,10 @@ __all__ = [
     "conj_complex_mult",
     "functional",
     "get_adjoint_mode",
+    "get_tiled_kernels",
     "imag_exp",
     "inner_product",
     "modules",
     "set_adjoint_mode",
+    "set_tiled_kernels",
 ]

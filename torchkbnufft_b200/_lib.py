@@ -17,6 +17,7 @@ C64, C128 = 0, 1
 COIL_MAJOR, CHANNEL_LAST = 0, 1
 ADJ_ATOMIC, ADJ_SORTED = 0, 1
 ABI_VERSION = 1
+OPT_TILED_KERNELS = 0
 
 _CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")
 LIB_PATH = os.path.join(_CSRC, "libb200nufft.so")
@@ -46,13 +47,22 @@ class Points(Structure):
         ("ndim", c_int32),
         ("dtype", c_int32),
         ("coef_stride", c_int32),
-        ("reserved", c_int32),
+        ("sub_cap", c_int32),
+        ("tile", c_int32 * MAX_DIMS),
+        ("n_tiles", c_int32 * MAX_DIMS),
+        ("n_cells", c_int64),
+        ("n_sub_max", c_int64),
         ("perm", c_void_p),
+        ("inv_perm", c_void_p),
         ("base", c_void_p),
         ("coef", c_void_p),
         ("phase", c_void_p),
         ("cell_start", c_void_p),
         ("keys", c_void_p),
+        ("sub_tile", c_void_p),
+        ("sub_start", c_void_p),
+        ("sub_count", c_void_p),
+        ("n_sub", c_void_p),
     ]
 
 
@@ -66,14 +76,17 @@ SIGNATURES = {
     "b2n_abi_version": (c_int, []),
     "b2n_last_error": (c_char_p, []),
     "b2n_device_count": (c_int, []),
+    "b2n_set_option": (c_int, [c_int, c_int]),
+    "b2n_get_option": (c_int, [c_int]),
     "b2n_points_workspace_bytes": (c_int, [POINTER(Geom), c_int64, c_int64, POINTER(c_size_t)]),
     "b2n_points_build": (c_int, [POINTER(Geom), c_void_p, c_int64, c_int64, c_void_p, c_size_t, POINTER(Points),
                                  c_void_p]),
     "b2n_export_indices": (c_int, [POINTER(Geom), c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
+    "b2n_interp_scratch_bytes": (c_int, [POINTER(Geom), POINTER(Points), c_int64, c_int64, POINTER(c_size_t)]),
     "b2n_interp_forward": (c_int, [POINTER(Geom), POINTER(Points), c_void_p, c_int64, c_int64, c_int, c_void_p,
-                                   c_void_p]),
+                                   c_void_p, c_size_t, c_void_p]),
     "b2n_interp_adjoint": (c_int, [POINTER(Geom), POINTER(Points), c_void_p, c_int64, c_int64, c_int, c_int,
-                                   c_void_p, c_void_p]),
+                                   c_void_p, c_void_p, c_size_t, c_void_p]),
     "b2n_apod_pad": (c_int, [c_int, c_int, _I64P, _I64P, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_int64,
                              c_void_p, c_double, c_int, c_void_p, c_void_p]),
     "b2n_crop_apod_coilsum": (c_int, [c_int, c_int, _I64P, _I64P, c_int64, c_int64, c_void_p, c_int, c_void_p,

@@ -8,59 +8,9 @@
 // the fftshift phase.  The accumulation order over offsets is the reference's
 // (row-major offsets; coefficient = running product over dimensions).
 #include "b2n_common.cuh"
+#include "b2n_interp.cuh"
 
 namespace b2n {
-
-int validate_geom(const b2n_geom *g, bool need_tables);
-
-template <typename T> struct InterpArgs {
-  int J[B2N_MAX_DIMS];
-  int coef_off[B2N_MAX_DIMS];
-  int coef_stride;
-  int64_t K[B2N_MAX_DIMS];
-  int64_t Kprod;
-  int64_t M, n_traj, B, C;
-  const int32_t *perm;
-  const int32_t *base;
-  const cplx<T> *coef;
-  const cplx<T> *phase;
-  const int32_t *cell_start;
-};
-
-template <typename T>
-static int make_args(const b2n_geom *g, const b2n_points *p, int64_t B, int64_t C, InterpArgs<T> *a) {
-  int rc = validate_geom(g, false);
-  if (rc) return rc;
-  if (!p || !p->perm || !p->base || !p->coef || !p->phase || !p->cell_start)
-    return fail_arg(B2N_E_ARG, "points plan is NULL or not built");
-  if (p->ndim != g->ndim || p->dtype != g->dtype) return fail_arg(B2N_E_ARG, "plan/geometry mismatch");
-  if (B < 1 || C < 1) return fail_arg(B2N_E_ARG, "n_batch=%lld n_coils=%lld", (long long)B, (long long)C);
-  if (p->n_traj != 1 && p->n_traj != B)
-    return fail_arg(B2N_E_ARG, "plan has %lld trajectories but n_batch=%lld", (long long)p->n_traj, (long long)B);
-  int off = 0;
-  a->Kprod = 1;
-  for (int d = 0; d < B2N_MAX_DIMS; ++d) {
-    a->J[d] = d < g->ndim ? g->numpoints[d] : 1;
-    a->K[d] = d < g->ndim ? g->grid_size[d] : 1;
-    a->coef_off[d] = off;
-    if (d < g->ndim) {
-      off += g->numpoints[d];
-      a->Kprod *= g->grid_size[d];
-    }
-  }
-  a->coef_stride = off;
-  if (off != p->coef_stride) return fail_arg(B2N_E_ARG, "plan coef_stride mismatch");
-  a->M = p->n_points;
-  a->n_traj = p->n_traj;
-  a->B = B;
-  a->C = C;
-  a->perm = p->perm;
-  a->base = p->base;
-  a->coef = (const cplx<T> *)p->coef;
-  a->phase = (const cplx<T> *)p->phase;
-  a->cell_start = p->cell_start;
-  return 0;
-}
 
 template <bool CL> B2N_D int64_t grid_addr(int64_t b, int64_t c, int64_t cell, int64_t C, int64_t Kprod) {
   return CL ? (b * Kprod + cell) * C + c : (b * C + c) * Kprod + cell;
@@ -191,7 +141,7 @@ __global__ void __launch_bounds__(128) k_adj_sorted_generic(InterpArgs<T> a, con
   for (int64_t r = blockIdx.y; r < rows; r += gridDim.y) {
     const int64_t b = r / a.C, c = r - b * a.C;
     const int64_t t = a.n_traj == 1 ? 0 : b;
-    const int32_t *cs = a.cell_start + t * a.Kprod;
+    const int32_t *cs = a.cell_start + t * a.tiling.n_cells;
     const cplx<T> *row = kdata + (b * a.C + c) * a.M;
     cplx<T> acc = {T(0), T(0)};
     for (int j0 = 0; j0 < a.J[0]; ++j0) {
@@ -200,9 +150,8 @@ __global__ void __launch_bounds__(128) k_adj_sorted_generic(InterpArgs<T> a, con
         const int64_t b1 = ND > 1 ? wrap_down(g[1] - j1, a.K[1]) : 0;
         for (int j2 = 0; j2 < (ND > 2 ? a.J[2] : 1); ++j2) {
           const int64_t b2 = ND > 2 ? wrap_down(g[2] - j2, a.K[2]) : 0;
-          int64_t key = b0;
-          if (ND > 1) key = key * a.K[1] + b1;
-          if (ND > 2) key = key * a.K[2] + b2;
+          const int64_t bc[B2N_MAX_DIMS] = {b0, b1, b2};
+          const int64_t key = tiled_cell(a.tiling, bc);
           const int32_t lo = cs[key], hi = cs[key + 1];
           for (int32_t s = lo; s < hi; ++s) {
             const cplx<T> *rec = a.coef + (int64_t)s * a.coef_stride;
@@ -278,26 +227,64 @@ static int adjoint_t(const b2n_geom *g, const b2n_points *p, const void *kdata, 
   }
 }
 
+size_t tiled_scratch_bytes(const b2n_geom *g, const b2n_points *p, int64_t B, int64_t C);
+int tiled_forward(const b2n_geom *g, const b2n_points *p, const void *grid, int64_t B, int64_t C, int layout,
+                  void *kdata, void *scratch, size_t scratch_bytes, cudaStream_t st);
+int tiled_adjoint(const b2n_geom *g, const b2n_points *p, const void *kdata, int64_t B, int64_t C, int layout,
+                  void *grid, void *scratch, size_t scratch_bytes, cudaStream_t st);
+
+static int g_options[B2N_OPT_COUNT] = {1};
+
 }  // namespace b2n
 
 using namespace b2n;
 
+extern "C" int b2n_set_option(int option, int value) {
+  if (option < 0 || option >= B2N_OPT_COUNT) return fail_arg(B2N_E_ARG, "unknown option %d", option);
+  g_options[option] = value;
+  return 0;
+}
+
+extern "C" int b2n_get_option(int option) {
+  if (option < 0 || option >= B2N_OPT_COUNT) return fail_arg(B2N_E_ARG, "unknown option %d", option);
+  return g_options[option];
+}
+
+extern "C" int b2n_interp_scratch_bytes(const b2n_geom *geom, const b2n_points *pts, int64_t n_batch, int64_t n_coils,
+                                        size_t *bytes) {
+  if (!geom || !pts || !bytes || n_batch < 1 || n_coils < 1) return fail_arg(B2N_E_ARG, "bad scratch query");
+  *bytes = g_options[B2N_OPT_TILED_KERNELS] ? tiled_scratch_bytes(geom, pts, n_batch, n_coils) : 0;
+  return 0;
+}
+
 extern "C" int b2n_interp_forward(const b2n_geom *geom, const b2n_points *pts, const void *grid_dev, int64_t n_batch,
-                                  int64_t n_coils, int grid_layout, void *kdata_dev, void *stream) {
+                                  int64_t n_coils, int grid_layout, void *kdata_dev, void *scratch_dev,
+                                  size_t scratch_bytes, void *stream) {
   if (!geom || !grid_dev || !kdata_dev) return fail_arg(B2N_E_ARG, "NULL geom/grid/kdata");
   if (grid_layout != B2N_COIL_MAJOR && grid_layout != B2N_CHANNEL_LAST) return fail_arg(B2N_E_ARG, "bad layout");
   cudaStream_t st = (cudaStream_t)stream;
+  if (g_options[B2N_OPT_TILED_KERNELS] && pts) {
+    const int rc = tiled_forward(geom, pts, grid_dev, n_batch, n_coils, grid_layout, kdata_dev, scratch_dev,
+                                 scratch_bytes, st);
+    if (rc != 1) return rc;  // 1 = not eligible, use the generic kernel
+  }
   if (geom->dtype == B2N_C64) return forward_t<float>(geom, pts, grid_dev, n_batch, n_coils, grid_layout, kdata_dev, st);
   if (geom->dtype == B2N_C128) return forward_t<double>(geom, pts, grid_dev, n_batch, n_coils, grid_layout, kdata_dev, st);
   return fail_arg(B2N_E_ARG, "bad dtype");
 }
 
 extern "C" int b2n_interp_adjoint(const b2n_geom *geom, const b2n_points *pts, const void *kdata_dev, int64_t n_batch,
-                                  int64_t n_coils, int grid_layout, int mode, void *grid_dev, void *stream) {
+                                  int64_t n_coils, int grid_layout, int mode, void *grid_dev, void *scratch_dev,
+                                  size_t scratch_bytes, void *stream) {
   if (!geom || !grid_dev || !kdata_dev) return fail_arg(B2N_E_ARG, "NULL geom/grid/kdata");
   if (grid_layout != B2N_COIL_MAJOR && grid_layout != B2N_CHANNEL_LAST) return fail_arg(B2N_E_ARG, "bad layout");
   if (mode != B2N_ADJ_ATOMIC && mode != B2N_ADJ_SORTED) return fail_arg(B2N_E_ARG, "bad adjoint mode %d", mode);
   cudaStream_t st = (cudaStream_t)stream;
+  if (g_options[B2N_OPT_TILED_KERNELS] && pts && mode == B2N_ADJ_ATOMIC) {
+    const int rc = tiled_adjoint(geom, pts, kdata_dev, n_batch, n_coils, grid_layout, grid_dev, scratch_dev,
+                                 scratch_bytes, st);
+    if (rc != 1) return rc;
+  }
   if (geom->dtype == B2N_C64)
     return adjoint_t<float>(geom, pts, kdata_dev, n_batch, n_coils, grid_layout, mode, grid_dev, st);
   if (geom->dtype == B2N_C128)

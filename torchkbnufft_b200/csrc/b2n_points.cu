@@ -10,6 +10,8 @@
 
 #include "b2n_common.cuh"
 #include "b2n_math.cuh"
+#include "b2n_tiling.cuh"
+#include <cub/device/device_scan.cuh>
 
 namespace b2n {
 
@@ -91,27 +93,52 @@ int validate_geom(const b2n_geom *g, bool need_tables) {
 
 // ---- kernels ----------------------------------------------------------------
 template <typename T>
-__global__ void k_point_keys(GeomT<T> g, const T *__restrict__ omega, int64_t M, int64_t total,
+__global__ void k_point_keys(GeomT<T> g, Tiling tl, const T *__restrict__ omega, int64_t M, int64_t total,
                              uint32_t *__restrict__ keys, uint32_t *__restrict__ idx) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const int64_t t = i / M, m = i - t * M;
   const T *om = omega + t * g.ndim * M + m;
-  int64_t cell = 0;
+  int64_t cell[B2N_MAX_DIMS] = {0, 0, 0};
   for (int d = 0; d < g.ndim; ++d) {
     T tm;
     int64_t base;
     locate<T>(om[d * M], g.K[d], g.J[d], tm, base);
-    cell = cell * g.K[d] + wrap_cell(base, g.K[d]);
+    cell[d] = wrap_cell(base, g.K[d]);
   }
-  keys[i] = (uint32_t)(t * g.Kprod + cell);
+  keys[i] = (uint32_t)(t * tl.n_cells + tiled_cell(tl, cell));
   idx[i] = (uint32_t)i;
+}
+
+// sub-problems: per (trajectory, tile) the sorted points are cut into chunks of <= cap
+__global__ void k_tile_chunks(const int32_t *__restrict__ cell_start, int64_t n_tiles_all, int TT, int cap,
+                              int32_t *__restrict__ n_chunks) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_tiles_all) return;
+  const int32_t n = cell_start[(t + 1) * TT] - cell_start[t * TT];
+  n_chunks[t] = (n + cap - 1) / cap;
+}
+
+__global__ void k_fill_subs(const int32_t *__restrict__ cell_start, const int32_t *__restrict__ n_chunks,
+                            const int32_t *__restrict__ offsets, int64_t n_tiles_all, int TT, int cap,
+                            int32_t *__restrict__ sub_tile, int32_t *__restrict__ sub_start,
+                            int32_t *__restrict__ sub_count, int32_t *__restrict__ n_sub) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_tiles_all) return;
+  const int32_t lo = cell_start[t * TT], n = cell_start[(t + 1) * TT] - lo;
+  const int32_t off = offsets[t], nc = n_chunks[t];
+  for (int32_t j = 0; j < nc; ++j) {
+    sub_tile[off + j] = (int32_t)t;
+    sub_start[off + j] = lo + j * cap;
+    sub_count[off + j] = min(cap, n - j * cap);
+  }
+  if (t == n_tiles_all - 1) *n_sub = off + nc;
 }
 
 template <typename T>
 __global__ void k_point_records(GeomT<T> g, const T *__restrict__ omega, int64_t M, int64_t total,
                                 const uint32_t *__restrict__ sorted_idx, int32_t *__restrict__ perm,
-                                int32_t *__restrict__ base_out, cplx<T> *__restrict__ coef,
+                                int32_t *__restrict__ inv_perm, int32_t *__restrict__ base_out, cplx<T> *__restrict__ coef,
                                 cplx<T> *__restrict__ phase) {
   const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= total) return;
@@ -119,6 +146,7 @@ __global__ void k_point_records(GeomT<T> g, const T *__restrict__ omega, int64_t
   const int64_t t = i / M, m = i - t * M;
   const T *om = omega + t * g.ndim * M + m;
   perm[s] = (int32_t)m;
+  inv_perm[i] = (int32_t)s;
   T omv[B2N_MAX_DIMS];
   for (int d = 0; d < g.ndim; ++d) {
     omv[d] = om[d * M];
@@ -182,8 +210,14 @@ __global__ void k_export_indices(GeomT<T> g, const T *__restrict__ omega, int64_
 
 // ---- workspace carving --------------------------------------------------------
 struct Carve {
-  size_t perm, base, coef, phase, cell_start, keys, keys_in, idx_in, idx_out, cub, total, cub_bytes;
+  size_t perm, inv_perm, base, coef, phase, cell_start, keys, sub_tile, sub_start, sub_count, n_sub;
+  size_t keys_in, idx_in, idx_out, chunks, offsets, cub, total, cub_bytes;
+  int64_t n_sub_max;
+  int sub_cap;
+  Tiling tiling;
 };
+
+static int default_sub_cap(int ndim) { return ndim == 3 ? 128 : 128; }
 
 static int sort_bits(int64_t n_keys) {
   int bits = 1;
@@ -192,13 +226,13 @@ static int sort_bits(int64_t n_keys) {
 }
 
 static int carve(const b2n_geom *g, int64_t M, int64_t n_traj, Carve *c) {
-  int64_t Kp = 1;
   int stride = 0;
-  for (int d = 0; d < g->ndim; ++d) {
-    Kp *= g->grid_size[d];
-    stride += g->numpoints[d];
-  }
-  const int64_t total = M * n_traj, n_cells = Kp * n_traj;
+  for (int d = 0; d < g->ndim; ++d) stride += g->numpoints[d];
+  c->tiling = make_tiling(g->ndim, g->grid_size);
+  c->sub_cap = default_sub_cap(g->ndim);
+  const int64_t total = M * n_traj, n_cells = c->tiling.n_cells * n_traj;
+  const int64_t n_tiles_all = c->tiling.n_tiles * n_traj;
+  c->n_sub_max = n_tiles_all + total / c->sub_cap + 1;
   if (total >= ((int64_t)1 << 31) - 1 || n_cells >= ((int64_t)1 << 32) - 1)
     return fail_arg(B2N_E_RANGE, "n_traj*M=%lld or n_traj*prod(K)=%lld exceeds the 32-bit plan limit",
                     (long long)total, (long long)n_cells);
@@ -210,11 +244,18 @@ static int carve(const b2n_geom *g, int64_t M, int64_t n_traj, Carve *c) {
     return at;
   };
   c->perm = take(sizeof(int32_t) * total);
+  c->inv_perm = take(sizeof(int32_t) * total);
   c->base = take(sizeof(int32_t) * total * g->ndim);
   c->coef = take(csz * total * stride);
   c->phase = take(csz * total);
   c->cell_start = take(sizeof(int32_t) * (n_cells + 1));
   c->keys = take(sizeof(uint32_t) * total);
+  c->sub_tile = take(sizeof(int32_t) * c->n_sub_max);
+  c->sub_start = take(sizeof(int32_t) * c->n_sub_max);
+  c->sub_count = take(sizeof(int32_t) * c->n_sub_max);
+  c->n_sub = take(sizeof(int32_t));
+  c->chunks = take(sizeof(int32_t) * n_tiles_all);
+  c->offsets = take(sizeof(int32_t) * n_tiles_all);
   c->keys_in = take(sizeof(uint32_t) * total);
   c->idx_in = take(sizeof(uint32_t) * total);
   c->idx_out = take(sizeof(uint32_t) * total);
@@ -223,6 +264,10 @@ static int carve(const b2n_geom *g, int64_t M, int64_t n_traj, Carve *c) {
                                                     (const uint32_t *)nullptr, (uint32_t *)nullptr, (int)total, 0,
                                                     sort_bits(n_cells));
   if (err != cudaSuccess) return check_cuda(err, "cub::DeviceRadixSort::SortPairs(size query)");
+  size_t scan_bytes = 0;
+  err = cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, (const int32_t *)nullptr, (int32_t *)nullptr, (int)n_tiles_all);
+  if (err != cudaSuccess) return check_cuda(err, "cub::DeviceScan::ExclusiveSum(size query)");
+  if (scan_bytes > cub_bytes) cub_bytes = scan_bytes;
   c->cub_bytes = cub_bytes;
   c->cub = take(cub_bytes + 256);
   c->total = off;
@@ -233,14 +278,26 @@ template <typename T>
 static int build_impl(const b2n_geom *geom, const void *omega, int64_t M, int64_t n_traj, char *ws, const Carve &c,
                       b2n_points *out, cudaStream_t st) {
   GeomT<T> g = make_geom<T>(geom);
-  const int64_t total = M * n_traj, n_cells = g.Kprod * n_traj;
+  const Tiling &tl = c.tiling;
+  const int64_t total = M * n_traj, n_cells = tl.n_cells * n_traj, n_tiles_all = tl.n_tiles * n_traj;
   out->n_points = M;
   out->n_traj = n_traj;
   out->ndim = geom->ndim;
   out->dtype = geom->dtype;
   out->coef_stride = g.coef_stride;
-  out->reserved = 0;
+  out->sub_cap = c.sub_cap;
+  for (int d = 0; d < B2N_MAX_DIMS; ++d) {
+    out->tile[d] = tl.T[d];
+    out->n_tiles[d] = tl.nt[d];
+  }
+  out->n_cells = tl.n_cells;
+  out->n_sub_max = c.n_sub_max;
+  out->sub_tile = (int32_t *)(ws + c.sub_tile);
+  out->sub_start = (int32_t *)(ws + c.sub_start);
+  out->sub_count = (int32_t *)(ws + c.sub_count);
+  out->n_sub = (int32_t *)(ws + c.n_sub);
   out->perm = (int32_t *)(ws + c.perm);
+  out->inv_perm = (int32_t *)(ws + c.inv_perm);
   out->base = (int32_t *)(ws + c.base);
   out->coef = ws + c.coef;
   out->phase = ws + c.phase;
@@ -250,20 +307,30 @@ static int build_impl(const b2n_geom *geom, const void *omega, int64_t M, int64_
            *idx_out = (uint32_t *)(ws + c.idx_out);
   const int threads = 256;
   if (total > 0) {
-    k_point_keys<T><<<(unsigned)ceil_div(total, threads), threads, 0, st>>>(g, (const T *)omega, M, total, keys_in,
-                                                                            idx_in);
+    k_point_keys<T><<<(unsigned)ceil_div(total, threads), threads, 0, st>>>(g, tl, (const T *)omega, M, total,
+                                                                            keys_in, idx_in);
     B2N_LAUNCH_OK("k_point_keys");
     size_t cub_bytes = c.cub_bytes;
     // stable LSD radix sort on the integer cell key: points of one cell keep their original order
     B2N_CUDA_OK(cub::DeviceRadixSort::SortPairs(ws + c.cub, cub_bytes, keys_in, out->keys, idx_in, idx_out, (int)total,
                                                 0, sort_bits(n_cells), st));
     k_point_records<T><<<(unsigned)ceil_div(total, threads), threads, 0, st>>>(
-        g, (const T *)omega, M, total, idx_out, out->perm, out->base, (cplx<T> *)out->coef, (cplx<T> *)out->phase);
+        g, (const T *)omega, M, total, idx_out, out->perm, out->inv_perm, out->base, (cplx<T> *)out->coef, (cplx<T> *)out->phase);
     B2N_LAUNCH_OK("k_point_records");
   }
   k_cell_start<<<(unsigned)ceil_div(n_cells + 1, threads), threads, 0, st>>>(out->keys, total, n_cells,
                                                                              out->cell_start);
   B2N_LAUNCH_OK("k_cell_start");
+  int32_t *chunks = (int32_t *)(ws + c.chunks), *offsets = (int32_t *)(ws + c.offsets);
+  k_tile_chunks<<<(unsigned)ceil_div(n_tiles_all, threads), threads, 0, st>>>(out->cell_start, n_tiles_all, tl.TT,
+                                                                              c.sub_cap, chunks);
+  B2N_LAUNCH_OK("k_tile_chunks");
+  size_t scan_bytes = c.cub_bytes;
+  B2N_CUDA_OK(cub::DeviceScan::ExclusiveSum(ws + c.cub, scan_bytes, chunks, offsets, (int)n_tiles_all, st));
+  k_fill_subs<<<(unsigned)ceil_div(n_tiles_all, threads), threads, 0, st>>>(
+      out->cell_start, chunks, offsets, n_tiles_all, tl.TT, c.sub_cap, out->sub_tile, out->sub_start, out->sub_count,
+      out->n_sub);
+  B2N_LAUNCH_OK("k_fill_subs");
   return 0;
 }
 
