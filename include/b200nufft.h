@@ -89,7 +89,8 @@ typedef struct b2n_points {
   int32_t *perm;       /* [n_traj*M]        sorted slot -> point index inside its trajectory */
   int32_t *inv_perm;   /* [n_traj*M]        traj*M + point index -> sorted slot */
   int32_t *base;       /* [n_traj*M][ndim]  wrapped base cell, in [0, K_d) */
-  void *coef;          /* [n_traj*M][coef_stride] complex table values T_d[t_d(j)], dims concatenated */
+  void *coef;          /* [n_traj*M][coef_stride] complex weights T_d[t_d(j)], dims concatenated; the
+                          fftshift phase of the point is folded into the dimension-0 entries */
   void *phase;         /* [n_traj*M]        complex exp(i sum_d omega_d n_shift_d) */
   int32_t *cell_start; /* [n_traj*n_cells+1] CSR offsets of the sorted list per tiled base cell */
   uint32_t *keys;      /* [n_traj*M]        sorted keys (traj*n_cells + tiled base cell) */
@@ -132,23 +133,15 @@ B2N_API int b2n_export_indices(const b2n_geom *geom, const void *omega_dev, int6
                        int32_t *tab_idx_dev, void *stream);
 
 /* ---- table interpolation ---------------------------------------------------- */
-/* Bytes of optional device scratch for b2n_interp_forward / b2n_interp_adjoint: the tiled
- * kernels keep the k-space samples in plan order, channel-last ([slot][coil]), in it.
- * Without scratch (NULL / too small) the calls still work, through the generic kernels. */
-B2N_API int b2n_interp_scratch_bytes(const b2n_geom *geom, const b2n_points *pts, int64_t n_batch, int64_t n_coils,
-                                     size_t *bytes);
-
 /* Forward gather, grid -> points.  grid: (B, C, *K) or (B, *K, C) per `grid_layout`;
  * kdata out: (B, C, M).  reference: table_interp, _nufft/interp.py:315-403. */
 B2N_API int b2n_interp_forward(const b2n_geom *geom, const b2n_points *pts, const void *grid_dev, int64_t n_batch,
-                               int64_t n_coils, int grid_layout, void *kdata_dev, void *scratch_dev,
-                               size_t scratch_bytes, void *stream);
+                               int64_t n_coils, int grid_layout, void *kdata_dev, void *stream);
 
 /* Adjoint spread, points -> grid (grid fully overwritten).
  * reference: table_interp_adjoint, _nufft/interp.py:587-726 (+ accum_tensor_index_add :407-419). */
 B2N_API int b2n_interp_adjoint(const b2n_geom *geom, const b2n_points *pts, const void *kdata_dev, int64_t n_batch,
-                               int64_t n_coils, int grid_layout, int mode, void *grid_dev, void *scratch_dev,
-                               size_t scratch_bytes, void *stream);
+                               int64_t n_coils, int grid_layout, int mode, void *grid_dev, void *stream);
 
 /* ---- fused steps around the FFT --------------------------------------------- */
 /* grid = zero_pad_end( image * smaps * scaling ) * scale.

@@ -57,7 +57,7 @@ def test_argument_errors_are_status_codes():
         assert status > 0 and b"CUDA error" in lib.b2n_last_error()
     g.numpoints[1] = 99
     assert lib.b2n_points_workspace_bytes(ctypes.byref(g), 100, 1, ctypes.byref(n)) == -2
-    assert lib.b2n_interp_forward(None, None, None, 1, 1, 0, None, None, 0, None) == -1  # B2N_E_ARG
+    assert lib.b2n_interp_forward(None, None, None, 1, 1, 0, None, None) == -1  # B2N_E_ARG
     assert lib.b2n_spectrum_mul(5, None, None, 1, 1, 1, 1, 0, 1.0, None) == -1
 
 

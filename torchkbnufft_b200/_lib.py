@@ -82,11 +82,10 @@ SIGNATURES = {
     "b2n_points_build": (c_int, [POINTER(Geom), c_void_p, c_int64, c_int64, c_void_p, c_size_t, POINTER(Points),
                                  c_void_p]),
     "b2n_export_indices": (c_int, [POINTER(Geom), c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
-    "b2n_interp_scratch_bytes": (c_int, [POINTER(Geom), POINTER(Points), c_int64, c_int64, POINTER(c_size_t)]),
     "b2n_interp_forward": (c_int, [POINTER(Geom), POINTER(Points), c_void_p, c_int64, c_int64, c_int, c_void_p,
-                                   c_void_p, c_size_t, c_void_p]),
+                                   c_void_p]),
     "b2n_interp_adjoint": (c_int, [POINTER(Geom), POINTER(Points), c_void_p, c_int64, c_int64, c_int, c_int,
-                                   c_void_p, c_void_p, c_size_t, c_void_p]),
+                                   c_void_p, c_void_p]),
     "b2n_apod_pad": (c_int, [c_int, c_int, _I64P, _I64P, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_int64,
                              c_void_p, c_double, c_int, c_void_p, c_void_p]),
     "b2n_crop_apod_coilsum": (c_int, [c_int, c_int, _I64P, _I64P, c_int64, c_int64, c_void_p, c_int, c_void_p,

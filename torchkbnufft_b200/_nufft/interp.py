@@ -69,17 +69,6 @@ class KernelTimer:
 kernel_timer: Optional[KernelTimer] = None
 
 
-def _scratch(geo, plan, n_batch: int, n_coils: int, device) -> Optional[Tensor]:
-    """Device scratch the tiled kernels want (k-space samples in plan order); the
-    caching allocator makes this a free-list pop on the steady state."""
-    nbytes = ctypes.c_size_t(0)
-    _lib.check(_lib.load().b2n_interp_scratch_bytes(ctypes.byref(geo.struct), ctypes.byref(plan.struct), n_batch,
-                                                    n_coils, ctypes.byref(nbytes)), "b2n_interp_scratch_bytes")
-    if nbytes.value == 0:
-        return None
-    return torch.empty(int(nbytes.value), dtype=torch.uint8, device=device)
-
-
 def _check_offsets(offsets: Optional[Tensor], n_offsets: int, ndim: int) -> None:
     # The engine always visits the full row-major neighbourhood (the only thing the
     # reference's modules ever pass, _nufft/utils.py:329); a custom subset is rejected.
@@ -131,14 +120,11 @@ def table_interp(
     out = torch.empty((B, C, plan.n_points), dtype=image.dtype, device=image.device)
     if out.numel() == 0:
         return out
-    scratch = _scratch(geo, plan, B, C, image.device)
     with torch.cuda.device(image.device):
         stop = kernel_timer.bracket("interp_fwd", image.device) if kernel_timer is not None else None
         _lib.check(
             _lib.load().b2n_interp_forward(ctypes.byref(geo.struct), ctypes.byref(plan.struct), image.data_ptr(), B, C,
-                                           layout, out.data_ptr(), scratch.data_ptr() if scratch is not None else None,
-                                           scratch.numel() if scratch is not None else 0,
-                                           current_stream_ptr(image.device)),
+                                           layout, out.data_ptr(), current_stream_ptr(image.device)),
             "b2n_interp_forward",
         )
         if stop is not None:
@@ -186,15 +172,11 @@ def table_interp_adjoint(
     if out.numel() == 0:
         return out
     mode_id = ADJOINT_MODES[_default_adjoint_mode if mode is None else mode]
-    scratch = _scratch(geo, plan, B, C, data.device) if mode_id == _lib.ADJ_ATOMIC else None
     with torch.cuda.device(data.device):
         stop = kernel_timer.bracket("interp_adj", data.device) if kernel_timer is not None else None
         _lib.check(
             _lib.load().b2n_interp_adjoint(ctypes.byref(geo.struct), ctypes.byref(plan.struct), data.data_ptr(), B, C,
-                                           layout, mode_id, out.data_ptr(),
-                                           scratch.data_ptr() if scratch is not None else None,
-                                           scratch.numel() if scratch is not None else 0,
-                                           current_stream_ptr(data.device)),
+                                           layout, mode_id, out.data_ptr(), current_stream_ptr(data.device)),
             "b2n_interp_adjoint",
         )
         if stop is not None:

@@ -37,7 +37,6 @@ __global__ void __launch_bounds__(128) k_fwd_generic(InterpArgs<T> a, const cplx
   if (s >= total) return;
   const int32_t *bs = a.base + s * ND;
   const cplx<T> *rec = a.coef + s * a.coef_stride;
-  const cplx<T> ph = a.phase[s];
   const int64_t m = a.perm[s];
   const int64_t rows = a.n_traj == 1 ? a.B * a.C : a.C;
   for (int64_t r = blockIdx.y; r < rows; r += gridDim.y) {
@@ -65,7 +64,7 @@ __global__ void __launch_bounds__(128) k_fwd_generic(InterpArgs<T> a, const cplx
         }
       }
     }
-    kdata[(b * a.C + c) * a.M + m] = cmul(acc, ph);
+    kdata[(b * a.C + c) * a.M + m] = acc;  // the fftshift phase is folded into the dim-0 weights
   }
 }
 
@@ -80,13 +79,12 @@ __global__ void __launch_bounds__(128) k_adj_atomic_generic(InterpArgs<T> a, con
   if (s >= total) return;
   const int32_t *bs = a.base + s * ND;
   const cplx<T> *rec = a.coef + s * a.coef_stride;
-  const cplx<T> phc = cconj(a.phase[s]);
   const int64_t m = a.perm[s];
   const int64_t rows = a.n_traj == 1 ? a.B * a.C : a.C;
   for (int64_t r = blockIdx.y; r < rows; r += gridDim.y) {
     const int64_t b = a.n_traj == 1 ? r / a.C : s / a.M;
     const int64_t c = a.n_traj == 1 ? r - b * a.C : r;
-    const cplx<T> val = cmul(kdata[(b * a.C + c) * a.M + m], phc);
+    const cplx<T> val = kdata[(b * a.C + c) * a.M + m];
     for (int j0 = 0; j0 < a.J[0]; ++j0) {
       const int64_t g0 = wrap_up(bs[0] + j0, a.K[0]);
       const cplx<T> c0 = rec[j0];
@@ -158,8 +156,7 @@ __global__ void __launch_bounds__(128) k_adj_sorted_generic(InterpArgs<T> a, con
             cplx<T> cc = rec[j0];
             if (ND > 1) cc = cmul(cc, rec[a.coef_off[1] + j1]);
             if (ND > 2) cc = cmul(cc, rec[a.coef_off[2] + j2]);
-            const cplx<T> val = cmul(row[a.perm[s]], cconj(a.phase[s]));
-            cmac(acc, cconj(cc), val);
+            cmac(acc, cconj(cc), row[a.perm[s]]);
           }
         }
       }
@@ -227,11 +224,10 @@ static int adjoint_t(const b2n_geom *g, const b2n_points *p, const void *kdata, 
   }
 }
 
-size_t tiled_scratch_bytes(const b2n_geom *g, const b2n_points *p, int64_t B, int64_t C);
 int tiled_forward(const b2n_geom *g, const b2n_points *p, const void *grid, int64_t B, int64_t C, int layout,
-                  void *kdata, void *scratch, size_t scratch_bytes, cudaStream_t st);
+                  void *kdata, cudaStream_t st);
 int tiled_adjoint(const b2n_geom *g, const b2n_points *p, const void *kdata, int64_t B, int64_t C, int layout,
-                  void *grid, void *scratch, size_t scratch_bytes, cudaStream_t st);
+                  void *grid, cudaStream_t st);
 
 static int g_options[B2N_OPT_COUNT] = {1};
 
@@ -250,22 +246,13 @@ extern "C" int b2n_get_option(int option) {
   return g_options[option];
 }
 
-extern "C" int b2n_interp_scratch_bytes(const b2n_geom *geom, const b2n_points *pts, int64_t n_batch, int64_t n_coils,
-                                        size_t *bytes) {
-  if (!geom || !pts || !bytes || n_batch < 1 || n_coils < 1) return fail_arg(B2N_E_ARG, "bad scratch query");
-  *bytes = g_options[B2N_OPT_TILED_KERNELS] ? tiled_scratch_bytes(geom, pts, n_batch, n_coils) : 0;
-  return 0;
-}
-
 extern "C" int b2n_interp_forward(const b2n_geom *geom, const b2n_points *pts, const void *grid_dev, int64_t n_batch,
-                                  int64_t n_coils, int grid_layout, void *kdata_dev, void *scratch_dev,
-                                  size_t scratch_bytes, void *stream) {
+                                  int64_t n_coils, int grid_layout, void *kdata_dev, void *stream) {
   if (!geom || !grid_dev || !kdata_dev) return fail_arg(B2N_E_ARG, "NULL geom/grid/kdata");
   if (grid_layout != B2N_COIL_MAJOR && grid_layout != B2N_CHANNEL_LAST) return fail_arg(B2N_E_ARG, "bad layout");
   cudaStream_t st = (cudaStream_t)stream;
   if (g_options[B2N_OPT_TILED_KERNELS] && pts) {
-    const int rc = tiled_forward(geom, pts, grid_dev, n_batch, n_coils, grid_layout, kdata_dev, scratch_dev,
-                                 scratch_bytes, st);
+    const int rc = tiled_forward(geom, pts, grid_dev, n_batch, n_coils, grid_layout, kdata_dev, st);
     if (rc != 1) return rc;  // 1 = not eligible, use the generic kernel
   }
   if (geom->dtype == B2N_C64) return forward_t<float>(geom, pts, grid_dev, n_batch, n_coils, grid_layout, kdata_dev, st);
@@ -274,15 +261,13 @@ extern "C" int b2n_interp_forward(const b2n_geom *geom, const b2n_points *pts, c
 }
 
 extern "C" int b2n_interp_adjoint(const b2n_geom *geom, const b2n_points *pts, const void *kdata_dev, int64_t n_batch,
-                                  int64_t n_coils, int grid_layout, int mode, void *grid_dev, void *scratch_dev,
-                                  size_t scratch_bytes, void *stream) {
+                                  int64_t n_coils, int grid_layout, int mode, void *grid_dev, void *stream) {
   if (!geom || !grid_dev || !kdata_dev) return fail_arg(B2N_E_ARG, "NULL geom/grid/kdata");
   if (grid_layout != B2N_COIL_MAJOR && grid_layout != B2N_CHANNEL_LAST) return fail_arg(B2N_E_ARG, "bad layout");
   if (mode != B2N_ADJ_ATOMIC && mode != B2N_ADJ_SORTED) return fail_arg(B2N_E_ARG, "bad adjoint mode %d", mode);
   cudaStream_t st = (cudaStream_t)stream;
   if (g_options[B2N_OPT_TILED_KERNELS] && pts && mode == B2N_ADJ_ATOMIC) {
-    const int rc = tiled_adjoint(geom, pts, kdata_dev, n_batch, n_coils, grid_layout, grid_dev, scratch_dev,
-                                 scratch_bytes, st);
+    const int rc = tiled_adjoint(geom, pts, kdata_dev, n_batch, n_coils, grid_layout, grid_dev, st);
     if (rc != 1) return rc;
   }
   if (geom->dtype == B2N_C64)

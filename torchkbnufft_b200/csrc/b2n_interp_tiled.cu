@@ -1,66 +1,123 @@
 // b2n_interp_tiled.cu -- shared-memory tiled gather / spread kernels (complex64, 2-D, J=6).
 //
-// Measured motivation (profiles/r01_a_*, r01_b_*): the per-point kernels pull every point's
-// J^d-cell footprint through L2 (590 MB for BASELINE config 2 against a 52 MB grid) and sit
-// on the L2->SM bandwidth; a first tiled version was bound by the latency of dependent
-// global loads inside its per-point loop.  This version keeps ALL global traffic of the main
-// kernels contiguous and asynchronous:
-//   * a CTA owns one sub-problem of the trajectory plan (<= sub_cap consecutive points whose
-//     base cell lies in one 16x16 tile) and stages that tile plus its J-1 halo once in shared
-//     memory with cp.async, transposed to channel-last [cell][coil] (+1 padding): a warp
-//     works on one point with lanes = (cell slot, coil), so every shared-memory access is a
-//     run of consecutive coils -> conflict-free;
-//   * the per-point plan records (separable weights cy[jy], cx[jx] and the base cell) are
-//     contiguous in plan order and are bulk-staged with 16-byte cp.async;
-//   * k-space samples cross the kernel boundary in plan order, channel-last ([slot][coil], in
-//     a scratch buffer): the forward stores / the adjoint stages one contiguous 128-byte line
-//     per point.  Two small transposing kernels convert between that order and the caller's
-//     (B, C, M) layout, fully coalesced on both sides, and apply the fftshift phase.
-// Adjoint accumulation: each of the 8 warps owns the tile rows r with r mod 8 == warp, so
-// the update is a plain shared-memory read-modify-write (shared float atomics are CAS loops
-// on sm_100a) with a fixed per-cell order; tiles are merged into the global grid with 8-byte
-// L2 reductions (RED.ADD.F32x2).
+// Measured motivation (profiles/r01_a..c): the per-point kernels pull every point's J^d-cell
+// footprint through L2 (590 MB for BASELINE config 2 against a 52 MB grid) and sit on the
+// L2->SM bandwidth; earlier tiled versions were bound first by the latency of dependent
+// global loads, then by instruction issue (index arithmetic of element-wise tile staging).
+//
+// Design:
+//   * a CTA owns one sub-problem of the trajectory plan: <= sub_cap consecutive points whose
+//     base cell lies in one 16x16 tile.  The tile plus its J-1 halo, for 16 coils, is staged
+//     in shared memory coil-major [coil][21 rows][22 cols] by TMA (two 8-plane
+//     cp.async.bulk.tensor boxes on an mbarrier); boundary tiles, which need the periodic
+//     wrap TMA cannot express, and odd/unaligned grids use a cp.async element path;
+//   * a warp works on ONE point with lanes = (coil, cell slot).  With the plane stride
+//     21*22 = 462 (= 14 mod 16 in 8-byte banks) and lanes ordered (coil_hi, x parity,
+//     coil_lo) every half-warp access of two x-adjacent cells x 8 coils hits 16 distinct
+//     bank pairs: conflict-free without padding, which is what lets TMA write the tile;
+//   * per-point plan records (separable weights cy[jy] -- with the fftshift phase folded in --
+//     and cx[jx], base cell, original sample index) are contiguous in plan order and are
+//     bulk-staged with cp.async; nothing in the hot loops reads global memory;
+//   * forward: warps take different points; results are stored straight to the caller's
+//     (B, C, M) array (8-byte scattered stores, merged in L2);
+//   * adjoint: k-space samples are gathered with cp.async one round ahead (sample indices two
+//     rounds ahead), each of the 8 warps owns the tile rows r with r mod 8 == warp, so the
+//     accumulation is a plain shared-memory read-modify-write with a fixed per-cell order
+//     (shared float atomics are CAS loops on sm_100a); the tile is merged into the global
+//     grid by TMA reduce-add (cp.reduce.async.bulk.tensor ... .add, FP32) -- element-wise
+//     RED.ADD.F32x2 on boundary tiles.
 //
 // reference loops replaced: torchkbnufft/_nufft/interp.py:185-203 and :689-724.
+#include <cuda.h>
+
 #include "b2n_common.cuh"
 #include "b2n_interp.cuh"
 
 namespace b2n {
 
-constexpr int kTile = 16;    // must match make_tiling() for ndim == 2
-constexpr int kWarps = 8;    // warps per CTA (== row-ownership modulus of the adjoint)
+constexpr int kTile = 16;   // must match make_tiling() for ndim == 2
+constexpr int kWarps = 8;   // warps per CTA (== row-ownership modulus of the adjoint)
 constexpr int kThreads = kWarps * 32;
-constexpr int kCap = 128;    // max points per sub-problem the forward kernel stages at once
-constexpr int kRound = 32;   // points per staging round of the adjoint kernel
+constexpr int kCap = 128;   // max points per sub-problem the forward kernel stages at once
+constexpr int kRound = 32;  // points per staging round of the adjoint kernel
+constexpr int kJ = 6;       // neighbours per dimension handled here
+constexpr int kSY = kTile + kJ - 1;      // 21 staged rows
+constexpr int kSX = kTile + kJ - 1 + 1;  // 22 staged columns (even: 16-byte rows for TMA)
+constexpr int kPS = kSY * kSX;           // plane stride, 462 float2
+constexpr int kNC = 2 * kJ;              // complex weights per point record
+constexpr int kBoxPlanes = 8;            // coil planes per TMA box
 
-B2N_D float2 cmulf(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
-B2N_D void cmacf(float2 &acc, float2 a, float2 b) {
-  acc.x += a.x * b.x - a.y * b.y;
-  acc.y += a.x * b.y + a.y * b.x;
+// ---- small device helpers -------------------------------------------------------------
+B2N_D void cmacf(float2 &acc, float2 a, float2 b) {  // acc += a * b, 4 FFMA
+  acc.x = fmaf(a.x, b.x, acc.x);
+  acc.x = fmaf(-a.y, b.y, acc.x);
+  acc.y = fmaf(a.x, b.y, acc.y);
+  acc.y = fmaf(a.y, b.x, acc.y);
 }
-// acc += conj(a) * b
-B2N_D void cmacf_conj(float2 &acc, float2 a, float2 b) {
-  acc.x += a.x * b.x + a.y * b.y;
-  acc.y += a.x * b.y - a.y * b.x;
+B2N_D void cmacf_conj(float2 &acc, float2 a, float2 b) {  // acc += conj(a) * b
+  acc.x = fmaf(a.x, b.x, acc.x);
+  acc.x = fmaf(a.y, b.y, acc.x);
+  acc.y = fmaf(a.x, b.y, acc.y);
+  acc.y = fmaf(-a.y, b.x, acc.y);
 }
 
-// ---- cp.async (LDGSTS) helpers ----------------------------------------------------------
-B2N_D void cp_async8(void *smem_dst, const void *gmem_src, bool valid) {
-  const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
-  const int src_size = valid ? 8 : 0;  // 0 -> the 8 destination bytes are zero-filled
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(dst), "l"(gmem_src), "r"(src_size) : "memory");
+B2N_D unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+B2N_D void cp_async4(void *dst, const void *src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(smem_u32(dst)), "l"(src) : "memory");
 }
-B2N_D void cp_async16(void *smem_dst, const void *gmem_src) {
-  const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(gmem_src) : "memory");
+B2N_D void cp_async8(void *dst, const void *src, bool valid) {
+  const int src_size = valid ? 8 : 0;  // 0 -> destination bytes are zero-filled
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(smem_u32(dst)), "l"(src), "r"(src_size) : "memory");
+}
+B2N_D void cp_async16(void *dst, const void *src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_u32(dst)), "l"(src) : "memory");
 }
 B2N_D void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 B2N_D void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
 
+B2N_D void mbar_init(uint64_t *bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+}
+B2N_D void mbar_expect_tx(uint64_t *bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+B2N_D void mbar_wait(uint64_t *bar, unsigned parity) {
+  unsigned done = 0;
+  for (unsigned spins = 0; !done; ++spins) {
+    asm volatile(
+        "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (spins > (1u << 22)) __trap();  // a TMA that never lands must not hang the device
+  }
+}
+// TMA: 4-D box (x in floats, y, coil, batch) global -> shared, completion on an mbarrier
+B2N_D void tma_load_4d(void *dst, const CUtensorMap *map, int x, int y, int c, int b, uint64_t *bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];\n" ::
+          "r"(smem_u32(dst)),
+      "l"(map), "r"(x), "r"(y), "r"(c), "r"(b), "r"(smem_u32(bar))
+      : "memory");
+}
+// TMA: shared -> global element-wise FP32 add of a 4-D box (out-of-range parts are dropped)
+B2N_D void tma_reduce_add_4d(const CUtensorMap *map, int x, int y, int c, int b, const void *src) {
+  asm volatile(
+      "cp.reduce.async.bulk.tensor.4d.global.shared::cta.add.tile.bulk_group [%0, {%1, %2, %3, %4}], [%5];\n" ::"l"(map),
+      "r"(x), "r"(y), "r"(c), "r"(b), "r"(smem_u32(src))
+      : "memory");
+}
+B2N_D void tma_store_commit_wait() {
+  asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
+  asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
+}
+B2N_D void fence_async_proxy() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
+
 struct SubProblem {
   int b, c0, y0, x0, start, count;
-  int64_t row0;  // scratch row of sorted slot 0 for this batch element
-  bool valid;
+  bool valid, interior;
 };
 
 // decode blockIdx -> (sub-problem, coil chunk, batch element)
@@ -76,311 +133,351 @@ template <int CC> B2N_D SubProblem decode(const InterpArgs<float> &a) {
   sp.x0 = tx * kTile;
   sp.c0 = blockIdx.y * CC;
   sp.b = a.n_traj == 1 ? (int)blockIdx.z : traj;
-  sp.row0 = a.n_traj == 1 ? (int64_t)sp.b * a.M : 0;  // batched plans: slots already span all trajectories
   sp.start = a.sub_start[blockIdx.x];
   sp.count = a.sub_count[blockIdx.x];
+  sp.interior = sp.y0 + kSY <= (int)a.K[0] && sp.x0 + kSX <= (int)a.K[1];
   return sp;
 }
 
-template <int JY, int JX> struct TileShape {
-  static constexpr int SY = kTile + JY - 1, SX = kTile + JX - 1;
-};
-// float2 slots of the staged tile, rounded up so that what follows stays 16-byte aligned
-template <int CC, int JY, int JX> constexpr int tile_slots() {
-  return ((TileShape<JY, JX>::SY * TileShape<JY, JX>::SX * (CC + 1)) + 1) & ~1;
+// lane -> (coil, cell slot).  CC == 16: (coil_hi, slot, coil_lo) so that a half-warp is two
+// x-adjacent cells x 8 coils (see the bank argument in the header); otherwise (slot, coil).
+template <int CC> B2N_D void lane_map(int lane, int &c, int &q) {
+  if (CC == 16) {
+    c = ((lane >> 4) << 3) | (lane & 7);
+    q = (lane >> 3) & 1;
+  } else {
+    c = lane % CC;
+    q = lane / CC;
+  }
 }
+template <int CC> constexpr int planes() { return CC < kBoxPlanes ? kBoxPlanes : CC; }
 
-// -----------------------------------------------------------------------------------------
-// forward: lanes = (q, c), q = (qy, qx) a QY x QX block of footprint cells, c a coil
-// -----------------------------------------------------------------------------------------
-template <int CC, int QY, int QX, int JY, int JX>
-__global__ void __launch_bounds__(kThreads) k_fwd_tiled_2d(InterpArgs<float> a, const float2 *__restrict__ grid,
-                                                           float2 *__restrict__ ysorted) {
-  constexpr int SY = TileShape<JY, JX>::SY, SX = TileShape<JY, JX>::SX, CS = CC + 1, NC = JY + JX;
-  constexpr int Q = QY * QX, NY = JY / QY, NX = JX / QX;
-  static_assert(JY % QY == 0 && JX % QX == 0 && Q * CC <= 32, "bad lane mapping");
-  static_assert((NC * 8) % 16 == 0, "plan records must be 16-byte multiples");
-  extern __shared__ __align__(16) float2 smem[];
-  float2 *tile = smem;                               // [SY*SX][CS]
-  float2 *s_coef = tile + tile_slots<CC, JY, JX>();  // [kCap][NC]
-  int2 *s_base = (int2 *)(s_coef + kCap * NC);       // [kCap]
-  const SubProblem sp = decode<CC>(a);
-  if (!sp.valid) return;
-  const int Ky = (int)a.K[0], Kx = (int)a.K[1];
-  const int C = (int)a.C;
-
-  // ---- stage everything asynchronously: tile (+halo, periodic wrap, transposed), records
-  for (int e = threadIdx.x; e < CC * SY * SX; e += kThreads) {
-    const int c = e / (SY * SX), rem = e - c * (SY * SX);
-    const int r = rem / SX, x = rem - r * SX;
+// element-wise staging of the tile with periodic wrap (boundary tiles / no tensor map)
+template <int CC>
+B2N_D void stage_tile_elementwise(float2 *tile, const float2 *__restrict__ grid, const SubProblem &sp, int C, int Ky,
+                                  int Kx) {
+  for (int e = threadIdx.x; e < CC * kPS; e += kThreads) {
+    const int c = e / kPS, rem = e - c * kPS;
+    const int r = rem / kSX, x = rem - r * kSX;
     int gy = sp.y0 + r, gx = sp.x0 + x;
     gy = gy < Ky ? gy : gy % Ky;
     gx = gx < Kx ? gx : gx % Kx;
     const bool on = sp.c0 + c < C;
-    cp_async8(&tile[rem * CS + c], &grid[((int64_t)(sp.b * C + (on ? sp.c0 + c : 0)) * Ky + gy) * Kx + gx], on);
+    cp_async8(&tile[e], &grid[((int64_t)(sp.b * C + (on ? sp.c0 + c : 0)) * Ky + gy) * Kx + gx], on);
   }
+}
+
+// -----------------------------------------------------------------------------------------
+// forward gather
+// -----------------------------------------------------------------------------------------
+template <int CC, int QY, int QX>
+__global__ void __launch_bounds__(kThreads) k_fwd_tiled_2d(InterpArgs<float> a, const float2 *__restrict__ grid,
+                                                           float2 *__restrict__ kdata,
+                                                           const __grid_constant__ CUtensorMap tmap, int use_tma) {
+  constexpr int Q = QY * QX, NY = kJ / QY, NX = kJ / QX;
+  static_assert(kJ % QY == 0 && kJ % QX == 0 && Q * CC <= 32, "bad lane mapping");
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float2 *tile = reinterpret_cast<float2 *>(smem_raw);                 // [planes][kSY][kSX]
+  float2 *s_coef = tile + planes<CC>() * kPS;                          // [kCap][kNC]
+  int2 *s_base = reinterpret_cast<int2 *>(s_coef + kCap * kNC);        // [kCap]
+  int *s_perm = reinterpret_cast<int *>(s_base + kCap);                // [kCap]
+  uint64_t *bar = reinterpret_cast<uint64_t *>(s_perm + kCap);
+  const SubProblem sp = decode<CC>(a);
+  if (!sp.valid) return;
+  const int Ky = (int)a.K[0], Kx = (int)a.K[1];
+  const int C = (int)a.C;
+  const bool tma = use_tma && sp.interior;
+
+  if (tma && threadIdx.x == 0) mbar_init(bar, 1);
+  // plan records of this sub-problem: contiguous in plan order
   {
     const float4 *src =
-        reinterpret_cast<const float4 *>(reinterpret_cast<const float2 *>(a.coef) + (int64_t)sp.start * NC);
+        reinterpret_cast<const float4 *>(reinterpret_cast<const float2 *>(a.coef) + (int64_t)sp.start * kNC);
     float4 *dst = reinterpret_cast<float4 *>(s_coef);
-    for (int e = threadIdx.x; e < sp.count * (NC / 2); e += kThreads) cp_async16(&dst[e], &src[e]);
+    for (int e = threadIdx.x; e < sp.count * (kNC / 2); e += kThreads) cp_async16(&dst[e], &src[e]);
     const int2 *bsrc = reinterpret_cast<const int2 *>(a.base) + sp.start;
-    for (int e = threadIdx.x; e < sp.count; e += kThreads) cp_async8(&s_base[e], &bsrc[e], true);
+    for (int e = threadIdx.x; e < sp.count; e += kThreads) {
+      cp_async8(&s_base[e], &bsrc[e], true);
+      cp_async4(&s_perm[e], &a.perm[sp.start + e]);
+    }
+  }
+  if (tma) {
+    __syncthreads();  // barrier initialised before anyone can wait on it
+    if (threadIdx.x == 0) {
+      mbar_expect_tx(bar, (unsigned)(planes<CC>() * kPS * sizeof(float2)));
+      for (int p = 0; p < planes<CC>(); p += kBoxPlanes)
+        tma_load_4d(tile + p * kPS, &tmap, 2 * sp.x0, sp.y0, sp.c0 + p, sp.b, bar);
+    }
+  } else {
+    stage_tile_elementwise<CC>(tile, grid, sp, C, Ky, Kx);
   }
   cp_async_commit();
   cp_async_wait_all();
+  if (tma) mbar_wait(bar, 0);
   __syncthreads();
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int c = lane % CC, q = lane / CC;
+  int c, q;
+  lane_map<CC>(lane, c, q);
   const bool lane_on = q < Q;  // lanes beyond the QY x QX block idle on cell (0, 0) and contribute zero
   const int qy = lane_on ? q / QX : 0, qx = lane_on ? q - (q / QX) * QX : 0;
+  const float2 *tplane = tile + c * kPS + qy * kSX + qx;
+  float2 *out = kdata + (int64_t)(sp.b * C + sp.c0 + c) * a.M;
+  const bool store = q == 0 && sp.c0 + c < C;
   for (int i = warp; i < sp.count; i += kWarps) {
     const int2 bs = s_base[i];
-    const int by = bs.x - sp.y0, bx = bs.y - sp.x0;
-    const float2 *rec = s_coef + i * NC;
+    const float2 *rec = s_coef + i * kNC;
     // this lane's weights: cy[jy] for jy = ny*QY + qy, cx[jx] for jx = nx*QX + qx
     float2 cy[NY], cx[NX];
 #pragma unroll
     for (int ny = 0; ny < NY; ++ny) cy[ny] = rec[ny * QY + qy];
 #pragma unroll
-    for (int nx = 0; nx < NX; ++nx) cx[nx] = rec[JY + nx * QX + qx];
+    for (int nx = 0; nx < NX; ++nx) cx[nx] = rec[kJ + nx * QX + qx];
+    const float2 *t0 = tplane + (bs.x - sp.y0) * kSX + (bs.y - sp.x0);
     float2 acc = make_float2(0.f, 0.f);
-    const float2 *t0 = tile + ((by + qy) * SX + bx + qx) * CS + c;
 #pragma unroll
     for (int ny = 0; ny < NY; ++ny) {
       float2 row = make_float2(0.f, 0.f);
 #pragma unroll
-      for (int nx = 0; nx < NX; ++nx) cmacf(row, cx[nx], t0[(ny * QY * SX + nx * QX) * CS]);
+      for (int nx = 0; nx < NX; ++nx) cmacf(row, cx[nx], t0[ny * QY * kSX + nx * QX]);
       cmacf(acc, cy[ny], row);
     }
     if (!lane_on) acc = make_float2(0.f, 0.f);
+    if (CC == 16) {
+      acc.x += __shfl_xor_sync(0xffffffffu, acc.x, 8);
+      acc.y += __shfl_xor_sync(0xffffffffu, acc.y, 8);
+    } else {
 #pragma unroll
-    for (int off = CC; off < 32; off <<= 1) {
-      acc.x += __shfl_xor_sync(0xffffffffu, acc.x, off);
-      acc.y += __shfl_xor_sync(0xffffffffu, acc.y, off);
+      for (int off = CC; off < 32; off <<= 1) {
+        acc.x += __shfl_xor_sync(0xffffffffu, acc.x, off);
+        acc.y += __shfl_xor_sync(0xffffffffu, acc.y, off);
+      }
     }
-    if (q == 0 && sp.c0 + c < C) ysorted[(sp.row0 + sp.start + i) * C + sp.c0 + c] = acc;
+    if (store) out[s_perm[i]] = acc;
   }
 }
 
 // -----------------------------------------------------------------------------------------
-// adjoint: warp w owns tile rows r with r % 8 == w; lanes = (qx, c), QX cells along x
+// adjoint spread
 // -----------------------------------------------------------------------------------------
-template <int CC, int JY, int JX>
-__global__ void __launch_bounds__(kThreads) k_adj_tiled_2d(InterpArgs<float> a, const float2 *__restrict__ ysorted,
-                                                           float2 *__restrict__ grid) {
-  constexpr int SY = TileShape<JY, JX>::SY, SX = TileShape<JY, JX>::SX, CS = CC + 1, NC = JY + JX;
-  constexpr int QX = 32 / CC, NX = (JX + QX - 1) / QX;
-  constexpr int STAGE = kRound * NC + kRound * CC + kRound;  // float2 slots per staging buffer
-  static_assert(JY <= kWarps, "row ownership needs JY <= warps per CTA");
-  extern __shared__ __align__(16) float2 smem[];
-  float2 *tile = smem;                               // [SY*SX][CS] accumulators
-  float2 *stage0 = tile + tile_slots<CC, JY, JX>();  // 2 x { coef[kRound][NC], val[kRound][CC], base[kRound] }
+template <int CC>
+__global__ void __launch_bounds__(kThreads) k_adj_tiled_2d(InterpArgs<float> a, const float2 *__restrict__ kdata,
+                                                           float2 *__restrict__ grid,
+                                                           const __grid_constant__ CUtensorMap tmap, int use_tma) {
+  constexpr int QX = 32 / CC, NX = (kJ + QX - 1) / QX;
+  constexpr int STAGE = kRound * kNC + kRound * CC + kRound;  // float2 slots: coef, val, base
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float2 *tile = reinterpret_cast<float2 *>(smem_raw);  // [planes][kSY][kSX] accumulators
+  float2 *stage0 = tile + planes<CC>() * kPS;           // 2 x STAGE
+  int *s_perm = reinterpret_cast<int *>(stage0 + 2 * STAGE);  // 3 x kRound sample indices
   const SubProblem sp = decode<CC>(a);
   if (!sp.valid) return;
   const int Ky = (int)a.K[0], Kx = (int)a.K[1];
   const int C = (int)a.C;
+  const int64_t M = a.M;
   const float2 *pcoef = reinterpret_cast<const float2 *>(a.coef);
+  const int rounds = (sp.count + kRound - 1) / kRound;
 
-  auto issue = [&](int round) {
-    float2 *buf = stage0 + (round & 1) * STAGE;
-    const int p0 = round * kRound, nb = min(kRound, sp.count - p0), s0 = sp.start + p0;
-    const float4 *src = reinterpret_cast<const float4 *>(pcoef + (int64_t)s0 * NC);
-    float4 *dst = reinterpret_cast<float4 *>(buf);
-    for (int e = threadIdx.x; e < nb * (NC / 2); e += kThreads) cp_async16(&dst[e], &src[e]);
-    float2 *val = buf + kRound * NC;
-    for (int e = threadIdx.x; e < nb * CC; e += kThreads) {
-      const int i = e / CC, cc = e - i * CC;
-      const bool on = sp.c0 + cc < C;
-      cp_async8(&val[e], &ysorted[(sp.row0 + s0 + i) * C + (on ? sp.c0 + cc : 0)], on);
+  auto issue_perm = [&](int round) {  // sample indices, two rounds ahead of their use
+    if (round < rounds) {
+      const int p0 = round * kRound, nb = min(kRound, sp.count - p0);
+      int *dst = s_perm + (round % 3) * kRound;
+      for (int e = threadIdx.x; e < nb; e += kThreads) cp_async4(&dst[e], &a.perm[sp.start + p0 + e]);
     }
-    int2 *sb = reinterpret_cast<int2 *>(val + kRound * CC);
-    const int2 *bsrc = reinterpret_cast<const int2 *>(a.base) + s0;
-    for (int e = threadIdx.x; e < nb; e += kThreads) cp_async8(&sb[e], &bsrc[e], true);
-    cp_async_commit();
+  };
+  auto issue_data = [&](int round) {  // weights, base cells and gathered samples, one round ahead
+    if (round < rounds) {
+      float2 *buf = stage0 + (round & 1) * STAGE;
+      const int p0 = round * kRound, nb = min(kRound, sp.count - p0), s0 = sp.start + p0;
+      const float4 *src = reinterpret_cast<const float4 *>(pcoef + (int64_t)s0 * kNC);
+      float4 *dst = reinterpret_cast<float4 *>(buf);
+      for (int e = threadIdx.x; e < nb * (kNC / 2); e += kThreads) cp_async16(&dst[e], &src[e]);
+      float2 *val = buf + kRound * kNC;
+      const int *perm = s_perm + (round % 3) * kRound;
+      for (int e = threadIdx.x; e < kRound * CC; e += kThreads) {
+        const int cc = e / kRound, i = e - cc * kRound;  // consecutive threads: consecutive points, one coil
+        const bool on = sp.c0 + cc < C && i < nb;
+        cp_async8(&val[i * CC + cc], &kdata[(int64_t)(sp.b * C + (on ? sp.c0 + cc : 0)) * M + (on ? perm[i] : 0)], on);
+      }
+      int2 *sb = reinterpret_cast<int2 *>(val + kRound * CC);
+      const int2 *bsrc = reinterpret_cast<const int2 *>(a.base) + s0;
+      for (int e = threadIdx.x; e < nb; e += kThreads) cp_async8(&sb[e], &bsrc[e], true);
+    }
   };
 
-  issue(0);
-  for (int e = threadIdx.x; e < SY * SX * CS; e += kThreads) tile[e] = make_float2(0.f, 0.f);
+  issue_perm(0);
+  issue_perm(1);
+  cp_async_commit();
+  for (int e = threadIdx.x; e < planes<CC>() * kPS; e += kThreads) tile[e] = make_float2(0.f, 0.f);
+  cp_async_wait_all();
+  __syncthreads();
+  issue_data(0);
+  cp_async_commit();
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int c = lane % CC, qx = lane / CC;
-  const int rounds = (sp.count + kRound - 1) / kRound;
+  int c, qx;
+  lane_map<CC>(lane, c, qx);
+  float2 *tplane = tile + c * kPS;
   for (int round = 0; round < rounds; ++round) {
     cp_async_wait_all();
-    __syncthreads();  // this round's data landed; everyone is done with the buffer refilled next
-    if (round + 1 < rounds) issue(round + 1);
+    __syncthreads();  // this round's data (and next round's indices) landed; buffers of round-1 are free
+    issue_data(round + 1);
+    issue_perm(round + 2);
+    cp_async_commit();
     const float2 *buf = stage0 + (round & 1) * STAGE;
-    const float2 *s_coef = buf, *s_val = buf + kRound * NC;
+    const float2 *s_coef = buf, *s_val = buf + kRound * kNC;
     const int2 *s_base = reinterpret_cast<const int2 *>(s_val + kRound * CC);
     const int nb = min(kRound, sp.count - round * kRound);
     for (int i = 0; i < nb; ++i) {
       const int2 bs = s_base[i];
       const int by = bs.x - sp.y0, bx = bs.y - sp.x0;
       const int jy = (warp - by) & (kWarps - 1);  // the footprint row this warp owns, if any
-      if (jy >= JY) continue;
+      if (jy >= kJ) continue;
       const float2 v = s_val[i * CC + c];
-      const float2 cyv = s_coef[i * NC + jy];
-      float2 *trow = tile + ((by + jy) * SX + bx) * CS + c;
-      const float2 u = make_float2(cyv.x * v.x + cyv.y * v.y, cyv.x * v.y - cyv.y * v.x);  // conj(cy) * v
+      const float2 cyv = s_coef[i * kNC + jy];
+      float2 *trow = tplane + (by + jy) * kSX + bx;
+      float2 u;  // conj(cy) * v   (cy carries the fftshift phase)
+      u.x = fmaf(cyv.x, v.x, cyv.y * v.y);
+      u.y = fmaf(cyv.x, v.y, -cyv.y * v.x);
       float2 t[NX], cxv[NX];
 #pragma unroll
       for (int nx = 0; nx < NX; ++nx) {  // all loads first: independent, latency overlaps
         const int jx = nx * QX + qx;
-        const bool on = JX % QX == 0 || jx < JX;
-        cxv[nx] = s_coef[i * NC + JY + (on ? jx : 0)];
-        t[nx] = trow[(on ? jx : 0) * CS];
+        const bool on = kJ % QX == 0 || jx < kJ;
+        cxv[nx] = s_coef[i * kNC + kJ + (on ? jx : 0)];
+        t[nx] = trow[on ? jx : 0];
       }
 #pragma unroll
       for (int nx = 0; nx < NX; ++nx) {
         const int jx = nx * QX + qx;
-        if (JX % QX == 0 || jx < JX) {
+        if (kJ % QX == 0 || jx < kJ) {
           cmacf_conj(t[nx], cxv[nx], u);  // += conj(cx) * conj(cy) * v
-          trow[jx * CS] = t[nx];
+          trow[jx] = t[nx];
         }
       }
       __syncwarp();
     }
   }
-  __syncthreads();
-  // merge the tile into the global grid: 8-byte L2 reductions, periodic wrap
-  for (int e = threadIdx.x; e < CC * SY * SX; e += kThreads) {
-    const int cc = e / (SY * SX), rem = e - cc * (SY * SX);
-    if (sp.c0 + cc >= C) break;
-    const float2 v = tile[rem * CS + cc];
-    if (v.x == 0.f && v.y == 0.f) continue;
-    const int r = rem / SX, x = rem - r * SX;
-    int gy = sp.y0 + r, gx = sp.x0 + x;
-    gy = gy < Ky ? gy : gy % Ky;
-    gx = gx < Kx ? gx : gx % Kx;
-    atomicAdd(&grid[((int64_t)(sp.b * C + sp.c0 + cc) * Ky + gy) * Kx + gx], v);
-  }
-}
-
-// -----------------------------------------------------------------------------------------
-// (B, C, M) caller order <-> plan order channel-last scratch, through a shared-memory
-// transpose: both the global reads and the global writes are coalesced.
-// TO_SORTED: ysorted[slot][c] = kdata[c][m] * conj(phase[slot])   (adjoint input)
-// else:      kdata[c][m] = ysorted[slot][c] * phase[slot]          (forward output)
-// -----------------------------------------------------------------------------------------
-template <bool TO_SORTED>
-__global__ void __launch_bounds__(256) k_reorder_kdata(InterpArgs<float> a, float2 *__restrict__ kdata,
-                                                       float2 *__restrict__ ysorted) {
-  constexpr int PM = 64, PC = 16;
-  __shared__ float2 buf[PC][PM + 1];
-  const int64_t M = a.M;
-  const int C = (int)a.C;
-  const int b = blockIdx.y;
-  const int64_t m0 = (int64_t)blockIdx.x * PM;
-  const int64_t traj_off = a.n_traj == 1 ? 0 : (int64_t)b * M;  // inv_perm / slots are global over trajectories
-  const int64_t row0 = a.n_traj == 1 ? (int64_t)b * M : 0;
-  const float2 *phase = reinterpret_cast<const float2 *>(a.phase);
-  for (int c0 = 0; c0 < C; c0 += PC) {
-    if (TO_SORTED) {
-      for (int e = threadIdx.x; e < PC * PM; e += 256) {
-        const int c = e / PM, i = e - c * PM;
-        if (c0 + c < C && m0 + i < M) buf[c][i] = kdata[((int64_t)b * C + c0 + c) * M + m0 + i];
-      }
-      __syncthreads();
-      for (int e = threadIdx.x; e < PC * PM; e += 256) {
-        const int i = e / PC, c = e - i * PC;
-        if (c0 + c < C && m0 + i < M) {
-          const int slot = a.inv_perm[traj_off + m0 + i];
-          const float2 ph = phase[slot];
-          ysorted[(row0 + slot) * C + c0 + c] = cmulf(buf[c][i], make_float2(ph.x, -ph.y));
-        }
-      }
-    } else {
-      for (int e = threadIdx.x; e < PC * PM; e += 256) {
-        const int i = e / PC, c = e - i * PC;
-        if (c0 + c < C && m0 + i < M) {
-          const int slot = a.inv_perm[traj_off + m0 + i];
-          buf[c][i] = cmulf(ysorted[(row0 + slot) * C + c0 + c], phase[slot]);
-        }
-      }
-      __syncthreads();
-      for (int e = threadIdx.x; e < PC * PM; e += 256) {
-        const int c = e / PM, i = e - c * PM;
-        if (c0 + c < C && m0 + i < M) kdata[((int64_t)b * C + c0 + c) * M + m0 + i] = buf[c][i];
-      }
-    }
+  // merge the tile into the global grid
+  if (use_tma && sp.interior) {
+    fence_async_proxy();  // generic-proxy writes to shared memory -> visible to the TMA engine
     __syncthreads();
+    if (threadIdx.x == 0) {
+      for (int p = 0; p < planes<CC>(); p += kBoxPlanes)
+        tma_reduce_add_4d(&tmap, 2 * sp.x0, sp.y0, sp.c0 + p, sp.b, tile + p * kPS);
+      tma_store_commit_wait();  // shared memory must stay valid until the engine has read it
+    }
+  } else {
+    __syncthreads();
+    for (int e = threadIdx.x; e < CC * kPS; e += kThreads) {
+      const int cc = e / kPS, rem = e - cc * kPS;
+      if (sp.c0 + cc >= C) break;
+      const int r = rem / kSX, x = rem - r * kSX;
+      if (x >= kSX - 1) continue;  // the 22nd column is padding for TMA, never written
+      const float2 v = tile[e];
+      if (v.x == 0.f && v.y == 0.f) continue;
+      int gy = sp.y0 + r, gx = sp.x0 + x;
+      gy = gy < Ky ? gy : gy % Ky;
+      gx = gx < Kx ? gx : gx % Kx;
+      atomicAdd(&grid[((int64_t)(sp.b * C + sp.c0 + cc) * Ky + gy) * Kx + gx], v);
+    }
   }
 }
 
-// ---- dispatch ---------------------------------------------------------------------------
+// ---- host side ------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+    (void)cudaGetLastError();
+  }
+  return fn;
+}
+
+// 4-D FP32 view of a coil-major complex64 grid (B, C, Ky, Kx): dims (2*Kx, Ky, C, B), box
+// (2*22, 21, 8, 1).  Returns false when TMA cannot describe it (odd Kx, unaligned base, ...).
+static bool make_grid_tmap(CUtensorMap *map, const void *grid, int64_t B, int64_t C, int64_t Ky, int64_t Kx) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn || (Kx & 1) || ((uintptr_t)grid & 15) || Ky < kSY || Kx < kSX) return false;
+  const cuuint64_t gdim[4] = {(cuuint64_t)(2 * Kx), (cuuint64_t)Ky, (cuuint64_t)C, (cuuint64_t)B};
+  const cuuint64_t gstride[3] = {(cuuint64_t)(Kx * 8), (cuuint64_t)(Ky * Kx * 8), (cuuint64_t)(C * Ky * Kx * 8)};
+  const cuuint32_t box[4] = {2 * kSX, kSY, kBoxPlanes, 1};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void *>(grid), gdim, gstride, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 static bool tiled_eligible(const b2n_geom *g, const b2n_points *p, int layout) {
-  return g->dtype == B2N_C64 && g->ndim == 2 && layout == B2N_COIL_MAJOR && g->numpoints[0] == 6 &&
-         g->numpoints[1] == 6 && p->tile[0] == kTile && p->tile[1] == kTile && p->n_points > 0 &&
+  return g->dtype == B2N_C64 && g->ndim == 2 && layout == B2N_COIL_MAJOR && g->numpoints[0] == kJ &&
+         g->numpoints[1] == kJ && p->tile[0] == kTile && p->tile[1] == kTile && p->n_points > 0 &&
          p->sub_cap <= kCap;
 }
 
-size_t tiled_scratch_bytes(const b2n_geom *g, const b2n_points *p, int64_t B, int64_t C) {
-  if (!tiled_eligible(g, p, B2N_COIL_MAJOR)) return 0;
-  return sizeof(float2) * (size_t)(B * C * p->n_points);
-}
-
-template <bool TO_SORTED>
-static int launch_reorder(const InterpArgs<float> &a, void *kdata, void *ysorted, cudaStream_t st) {
-  dim3 gd((unsigned)ceil_div(a.M, 64), (unsigned)a.B);
-  k_reorder_kdata<TO_SORTED><<<gd, 256, 0, st>>>(a, (float2 *)kdata, (float2 *)ysorted);
-  B2N_LAUNCH_OK("k_reorder_kdata");
-  return 0;
-}
-
 template <int CC, int QY, int QX>
-static int launch_fwd(const InterpArgs<float> &a, const void *grid, void *ysorted, cudaStream_t st) {
-  const size_t smem = sizeof(float2) * (tile_slots<CC, 6, 6>() + kCap * 12) + sizeof(int2) * kCap;
-  auto kern = k_fwd_tiled_2d<CC, QY, QX, 6, 6>;
+static int launch_fwd(const InterpArgs<float> &a, const void *grid, void *kdata, cudaStream_t st) {
+  const size_t smem = sizeof(float2) * (planes<CC>() * kPS + kCap * kNC) + sizeof(int2) * kCap + sizeof(int) * kCap + 16;
+  auto kern = k_fwd_tiled_2d<CC, QY, QX>;
   B2N_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CUtensorMap map;
+  memset(&map, 0, sizeof(map));
+  const int use_tma = make_grid_tmap(&map, grid, a.B, a.C, a.K[0], a.K[1]) ? 1 : 0;
   dim3 gd((unsigned)a.n_sub_max, (unsigned)ceil_div(a.C, CC), (unsigned)(a.n_traj == 1 ? a.B : 1));
-  kern<<<gd, kThreads, smem, st>>>(a, (const float2 *)grid, (float2 *)ysorted);
+  kern<<<gd, kThreads, smem, st>>>(a, (const float2 *)grid, (float2 *)kdata, map, use_tma);
   B2N_LAUNCH_OK("k_fwd_tiled_2d");
   return 0;
 }
 
-template <int CC>
-static int launch_adj(const InterpArgs<float> &a, const void *ysorted, void *grid, cudaStream_t st) {
-  const size_t smem = sizeof(float2) * (tile_slots<CC, 6, 6>() + 2 * (kRound * 12 + kRound * CC + kRound));
-  auto kern = k_adj_tiled_2d<CC, 6, 6>;
+template <int CC> static int launch_adj(const InterpArgs<float> &a, const void *kdata, void *grid, cudaStream_t st) {
+  const size_t smem =
+      sizeof(float2) * (planes<CC>() * kPS + 2 * (kRound * kNC + kRound * CC + kRound)) + sizeof(int) * 3 * kRound;
+  auto kern = k_adj_tiled_2d<CC>;
   B2N_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  B2N_CUDA_OK(cudaMemsetAsync(grid, 0, sizeof(float2) * (size_t)(a.B * a.C * a.Kprod), st));
+  CUtensorMap map;
+  memset(&map, 0, sizeof(map));
+  const int use_tma = make_grid_tmap(&map, grid, a.B, a.C, a.K[0], a.K[1]) ? 1 : 0;
   dim3 gd((unsigned)a.n_sub_max, (unsigned)ceil_div(a.C, CC), (unsigned)(a.n_traj == 1 ? a.B : 1));
-  kern<<<gd, kThreads, smem, st>>>(a, (const float2 *)ysorted, (float2 *)grid);
+  kern<<<gd, kThreads, smem, st>>>(a, (const float2 *)kdata, (float2 *)grid, map, use_tma);
   B2N_LAUNCH_OK("k_adj_tiled_2d");
   return 0;
 }
 
 // both return 1 when the tiled path does not apply (caller falls back to the generic kernels)
 int tiled_forward(const b2n_geom *g, const b2n_points *p, const void *grid, int64_t B, int64_t C, int layout,
-                  void *kdata, void *scratch, size_t scratch_bytes, cudaStream_t st) {
-  if (!tiled_eligible(g, p, layout) || !scratch || scratch_bytes < tiled_scratch_bytes(g, p, B, C)) return 1;
+                  void *kdata, cudaStream_t st) {
+  if (!tiled_eligible(g, p, layout)) return 1;
   InterpArgs<float> a;
   int rc = make_args<float>(g, p, B, C, &a);
   if (rc) return rc;
-  if (C > 8) rc = launch_fwd<16, 1, 2>(a, grid, scratch, st);
-  else if (C > 4) rc = launch_fwd<8, 2, 2>(a, grid, scratch, st);
-  else if (C > 2) rc = launch_fwd<4, 2, 3>(a, grid, scratch, st);
-  else if (C > 1) rc = launch_fwd<2, 2, 6>(a, grid, scratch, st);
-  else rc = launch_fwd<1, 3, 6>(a, grid, scratch, st);
-  if (rc) return rc;
-  return launch_reorder<false>(a, kdata, scratch, st);
+  if (C > 8) return launch_fwd<16, 1, 2>(a, grid, kdata, st);
+  if (C > 4) return launch_fwd<8, 2, 2>(a, grid, kdata, st);
+  if (C > 2) return launch_fwd<4, 2, 3>(a, grid, kdata, st);
+  if (C > 1) return launch_fwd<2, 2, 6>(a, grid, kdata, st);
+  return launch_fwd<1, 3, 6>(a, grid, kdata, st);
 }
 
 int tiled_adjoint(const b2n_geom *g, const b2n_points *p, const void *kdata, int64_t B, int64_t C, int layout,
-                  void *grid, void *scratch, size_t scratch_bytes, cudaStream_t st) {
-  if (!tiled_eligible(g, p, layout) || !scratch || scratch_bytes < tiled_scratch_bytes(g, p, B, C)) return 1;
+                  void *grid, cudaStream_t st) {
+  if (!tiled_eligible(g, p, layout)) return 1;
   InterpArgs<float> a;
   int rc = make_args<float>(g, p, B, C, &a);
   if (rc) return rc;
-  B2N_CUDA_OK(cudaMemsetAsync(grid, 0, sizeof(float2) * (size_t)(a.B * a.C * a.Kprod), st));
-  rc = launch_reorder<true>(a, const_cast<void *>(kdata), scratch, st);
-  if (rc) return rc;
-  if (C > 8) return launch_adj<16>(a, scratch, grid, st);
-  if (C > 4) return launch_adj<8>(a, scratch, grid, st);
-  if (C > 2) return launch_adj<4>(a, scratch, grid, st);
-  if (C > 1) return launch_adj<2>(a, scratch, grid, st);
-  return launch_adj<1>(a, scratch, grid, st);
+  if (C > 8) return launch_adj<16>(a, kdata, grid, st);
+  if (C > 4) return launch_adj<8>(a, kdata, grid, st);
+  if (C > 2) return launch_adj<4>(a, kdata, grid, st);
+  if (C > 1) return launch_adj<2>(a, kdata, grid, st);
+  return launch_adj<1>(a, kdata, grid, st);
 }
 
 }  // namespace b2n

@@ -148,8 +148,15 @@ __global__ void k_point_records(GeomT<T> g, const T *__restrict__ omega, int64_t
   perm[s] = (int32_t)m;
   inv_perm[i] = (int32_t)s;
   T omv[B2N_MAX_DIMS];
+  for (int d = 0; d < g.ndim; ++d) omv[d] = om[d * M];
+  const T arg = phase_arg<T>(omv, g.ndim, g.n_shift);
+  T sn, cs;
+  sincos(arg, &sn, &cs);
+  cplx<T> ph;
+  ph.x = cs;
+  ph.y = sn;
+  phase[s] = ph;
   for (int d = 0; d < g.ndim; ++d) {
-    omv[d] = om[d * M];
     T tm;
     int64_t base;
     locate<T>(omv[d], g.K[d], g.J[d], tm, base);
@@ -159,16 +166,12 @@ __global__ void k_point_records(GeomT<T> g, const T *__restrict__ omega, int64_t
       int64_t ti = table_index<T>(tm, base + j, g.J[d], g.L[d]);
       if (ti < 0) ti += g.table_len[d];  // torch indexing wraps a negative index
       ti = ti < 0 ? 0 : (ti >= g.table_len[d] ? g.table_len[d] - 1 : ti);
-      rec[j] = g.table[d][ti];
+      const cplx<T> tv = g.table[d][ti];
+      // the fftshift phase multiplies every weight of the point: fold it into dimension 0, so
+      // the gather needs no epilogue and the spread no prologue (conj of the product is used)
+      rec[j] = d == 0 ? cmul(tv, ph) : tv;
     }
   }
-  const T arg = phase_arg<T>(omv, g.ndim, g.n_shift);
-  T sn, cs;
-  sincos(arg, &sn, &cs);
-  cplx<T> p;
-  p.x = cs;
-  p.y = sn;
-  phase[s] = p;
 }
 
 // cell_start[c] = first sorted slot whose key >= c  (c in [0, n_cells])
