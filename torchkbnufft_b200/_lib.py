@@ -18,6 +18,7 @@ COIL_MAJOR, CHANNEL_LAST = 0, 1
 ADJ_ATOMIC, ADJ_SORTED = 0, 1
 ABI_VERSION = 1
 OPT_TILED_KERNELS = 0
+OPT_ADJ_ROW_OWNERSHIP = 1
 
 _CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")
 LIB_PATH = os.path.join(_CSRC, "libb200nufft.so")

@@ -229,7 +229,8 @@ int tiled_forward(const b2n_geom *g, const b2n_points *p, const void *grid, int6
 int tiled_adjoint(const b2n_geom *g, const b2n_points *p, const void *kdata, int64_t B, int64_t C, int layout,
                   void *grid, cudaStream_t st);
 
-static int g_options[B2N_OPT_COUNT] = {1};
+extern int g_adj_rowwarp;
+static int g_options[B2N_OPT_COUNT] = {1, 0};
 
 }  // namespace b2n
 
@@ -238,6 +239,7 @@ using namespace b2n;
 extern "C" int b2n_set_option(int option, int value) {
   if (option < 0 || option >= B2N_OPT_COUNT) return fail_arg(B2N_E_ARG, "unknown option %d", option);
   g_options[option] = value;
+  if (option == B2N_OPT_ADJ_ROW_OWNERSHIP) g_adj_rowwarp = value;
   return 0;
 }
 

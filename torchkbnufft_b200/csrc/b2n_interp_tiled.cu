@@ -224,36 +224,47 @@ __global__ void __launch_bounds__(kThreads) k_fwd_tiled_2d(InterpArgs<float> a, 
   const float2 *tplane = tile + c * kPS + qy * kSX + qx;
   float2 *out = kdata + (int64_t)(sp.b * C + sp.c0 + c) * a.M;
   const bool store = q == 0 && sp.c0 + c < C;
-  for (int i = warp; i < sp.count; i += kWarps) {
-    const int2 bs = s_base[i];
-    const float2 *rec = s_coef + i * kNC;
-    // this lane's weights: cy[jy] for jy = ny*QY + qy, cx[jx] for jx = nx*QX + qx
-    float2 cy[NY], cx[NX];
+  // PU points per warp iteration: their shared-memory loads are independent, which gives the
+  // scheduler the ILP that one point alone (a chain LDS -> FFMA -> FFMA -> SHFL) lacks
+  constexpr int PU = 2;
+  for (int i0 = warp * PU; i0 < sp.count; i0 += kWarps * PU) {
+    float2 acc[PU];
 #pragma unroll
-    for (int ny = 0; ny < NY; ++ny) cy[ny] = rec[ny * QY + qy];
+    for (int u = 0; u < PU; ++u) {
+      const int i = min(i0 + u, sp.count - 1);
+      const int2 bs = s_base[i];
+      const float2 *rec = s_coef + i * kNC;
+      // this lane's weights: cy[jy] for jy = ny*QY + qy, cx[jx] for jx = nx*QX + qx
+      float2 cy[NY], cx[NX];
 #pragma unroll
-    for (int nx = 0; nx < NX; ++nx) cx[nx] = rec[kJ + nx * QX + qx];
-    const float2 *t0 = tplane + (bs.x - sp.y0) * kSX + (bs.y - sp.x0);
-    float2 acc = make_float2(0.f, 0.f);
+      for (int ny = 0; ny < NY; ++ny) cy[ny] = rec[ny * QY + qy];
 #pragma unroll
-    for (int ny = 0; ny < NY; ++ny) {
-      float2 row = make_float2(0.f, 0.f);
+      for (int nx = 0; nx < NX; ++nx) cx[nx] = rec[kJ + nx * QX + qx];
+      const float2 *t0 = tplane + (bs.x - sp.y0) * kSX + (bs.y - sp.x0);
+      float2 even = make_float2(0.f, 0.f), odd = make_float2(0.f, 0.f);
 #pragma unroll
-      for (int nx = 0; nx < NX; ++nx) cmacf(row, cx[nx], t0[ny * QY * kSX + nx * QX]);
-      cmacf(acc, cy[ny], row);
-    }
-    if (!lane_on) acc = make_float2(0.f, 0.f);
-    if (CC == 16) {
-      acc.x += __shfl_xor_sync(0xffffffffu, acc.x, 8);
-      acc.y += __shfl_xor_sync(0xffffffffu, acc.y, 8);
-    } else {
+      for (int ny = 0; ny < NY; ++ny) {
+        float2 row = make_float2(0.f, 0.f);
 #pragma unroll
-      for (int off = CC; off < 32; off <<= 1) {
-        acc.x += __shfl_xor_sync(0xffffffffu, acc.x, off);
-        acc.y += __shfl_xor_sync(0xffffffffu, acc.y, off);
+        for (int nx = 0; nx < NX; ++nx) cmacf(row, cx[nx], t0[ny * QY * kSX + nx * QX]);
+        cmacf((ny & 1) ? odd : even, cy[ny], row);
       }
+      acc[u] = lane_on ? make_float2(even.x + odd.x, even.y + odd.y) : make_float2(0.f, 0.f);
     }
-    if (store) out[s_perm[i]] = acc;
+#pragma unroll
+    for (int u = 0; u < PU; ++u) {
+      if (CC == 16) {
+        acc[u].x += __shfl_xor_sync(0xffffffffu, acc[u].x, 8);
+        acc[u].y += __shfl_xor_sync(0xffffffffu, acc[u].y, 8);
+      } else {
+#pragma unroll
+        for (int off = CC; off < 32; off <<= 1) {
+          acc[u].x += __shfl_xor_sync(0xffffffffu, acc[u].x, off);
+          acc[u].y += __shfl_xor_sync(0xffffffffu, acc[u].y, off);
+        }
+      }
+      if (store && i0 + u < sp.count) out[s_perm[i0 + u]] = acc[u];
+    }
   }
 }
 
@@ -384,6 +395,147 @@ __global__ void __launch_bounds__(kThreads) k_adj_tiled_2d(InterpArgs<float> a, 
   }
 }
 
+// -----------------------------------------------------------------------------------------
+// adjoint spread, 16-coil chunks: warps partition the COILS (warp w owns coils p and p+4,
+// p = (w & 3) + 8 * (w >> 2)), lanes = (16 footprint cells, 2 coils).  Every warp visits
+// every point, so there is no ownership test and no divergence, and because coil planes
+// are disjoint between warps the read-modify-write needs no atomics.  The 36 conjugated
+// weight products of each staged point are formed once per round by the whole CTA.
+// Banks: cell n = 6r + x sits at r*22 + x = n (mod 16) in its plane and the two coils of a
+// warp are 4 planes = 8 (mod 16) apart, so a half-warp (8 cells x 2 coils) is conflict-free.
+// -----------------------------------------------------------------------------------------
+constexpr int kRoundC = 24;  // points per round of the coil-partitioned adjoint
+
+__global__ void __launch_bounds__(kThreads) k_adj_coilwarp_2d(InterpArgs<float> a, const float2 *__restrict__ kdata,
+                                                              float2 *__restrict__ grid,
+                                                              const __grid_constant__ CUtensorMap tmap, int use_tma) {
+  constexpr int CC = 16, W = kJ * kJ;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float2 *tile = reinterpret_cast<float2 *>(smem_raw);     // [16][kSY][kSX] accumulators
+  float2 *s_coef = tile + CC * kPS;                        // [kRoundC][kNC]   raw weights of the round
+  float2 *s_w = s_coef + kRoundC * kNC;                    // [kRoundC][W]     conj(cy[jy] * cx[jx])
+  float2 *s_val = s_w + kRoundC * W;                       // 2 x [kRoundC][CC] gathered samples
+  int2 *s_base = reinterpret_cast<int2 *>(s_val + 2 * kRoundC * CC);  // 2 x [kRoundC]
+  int *s_perm = reinterpret_cast<int *>(s_base + 2 * kRoundC);        // 3 x [kRoundC]
+  const SubProblem sp = decode<CC>(a);
+  if (!sp.valid) return;
+  const int Ky = (int)a.K[0], Kx = (int)a.K[1];
+  const int C = (int)a.C;
+  const int64_t M = a.M;
+  const float2 *pcoef = reinterpret_cast<const float2 *>(a.coef);
+  const int rounds = (sp.count + kRoundC - 1) / kRoundC;
+
+  auto issue_perm = [&](int round) {  // sample indices, two rounds ahead of their use
+    if (round < rounds) {
+      const int p0 = round * kRoundC, nb = min(kRoundC, sp.count - p0);
+      int *dst = s_perm + (round % 3) * kRoundC;
+      for (int e = threadIdx.x; e < nb; e += kThreads) cp_async4(&dst[e], &a.perm[sp.start + p0 + e]);
+    }
+  };
+  auto issue_coef = [&](int round) {
+    if (round < rounds) {
+      const int p0 = round * kRoundC, nb = min(kRoundC, sp.count - p0);
+      const float4 *src = reinterpret_cast<const float4 *>(pcoef + (int64_t)(sp.start + p0) * kNC);
+      float4 *dst = reinterpret_cast<float4 *>(s_coef);
+      for (int e = threadIdx.x; e < nb * (kNC / 2); e += kThreads) cp_async16(&dst[e], &src[e]);
+    }
+  };
+  auto issue_val = [&](int round) {  // gathered samples and base cells, one round ahead
+    if (round < rounds) {
+      const int p0 = round * kRoundC, nb = min(kRoundC, sp.count - p0);
+      float2 *val = s_val + (round & 1) * kRoundC * CC;
+      const int *perm = s_perm + (round % 3) * kRoundC;
+      for (int e = threadIdx.x; e < kRoundC * CC; e += kThreads) {
+        const int cc = e / kRoundC, i = e - cc * kRoundC;  // consecutive threads: consecutive points, one coil
+        const bool on = sp.c0 + cc < C && i < nb;
+        cp_async8(&val[i * CC + cc], &kdata[(int64_t)(sp.b * C + (on ? sp.c0 + cc : 0)) * M + (on ? perm[i] : 0)], on);
+      }
+      int2 *sb = s_base + (round & 1) * kRoundC;
+      const int2 *bsrc = reinterpret_cast<const int2 *>(a.base) + sp.start + p0;
+      for (int e = threadIdx.x; e < nb; e += kThreads) cp_async8(&sb[e], &bsrc[e], true);
+    }
+  };
+
+  issue_perm(0);
+  issue_perm(1);
+  issue_coef(0);
+  cp_async_commit();
+  for (int e = threadIdx.x; e < CC * kPS; e += kThreads) tile[e] = make_float2(0.f, 0.f);
+  cp_async_wait_all();
+  __syncthreads();
+  issue_val(0);
+  cp_async_commit();
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int qs = lane >> 1;
+  const int coil = (warp & 3) + 8 * (warp >> 2) + 4 * (lane & 1);
+  float2 *tplane = tile + coil * kPS;
+  int n_it[3], off_it[3];
+#pragma unroll
+  for (int it = 0; it < 3; ++it) {
+    const int n = min(it * 16 + qs, W - 1);
+    n_it[it] = n;
+    off_it[it] = (n / kJ) * kSX + (n % kJ);
+  }
+  const bool last_on = 2 * 16 + qs < W;
+  for (int round = 0; round < rounds; ++round) {
+    const int nb = min(kRoundC, sp.count - round * kRoundC);
+    cp_async_wait_all();
+    __syncthreads();  // raw weights, samples and base cells of this round landed; last round is fully consumed
+    for (int e = threadIdx.x; e < nb * W; e += kThreads) {  // conjugated separable products, once per point
+      const int i = e / W, n = e - i * W;
+      const float2 cy = s_coef[i * kNC + n / kJ], cx = s_coef[i * kNC + kJ + n % kJ];
+      s_w[e] = make_float2(cy.x * cx.x - cy.y * cx.y, -(cy.x * cx.y + cy.y * cx.x));
+    }
+    __syncthreads();  // products visible; raw weight buffer free again
+    issue_coef(round + 1);
+    issue_val(round + 1);
+    issue_perm(round + 2);
+    cp_async_commit();
+    const float2 *val = s_val + (round & 1) * kRoundC * CC;
+    const int2 *sb = s_base + (round & 1) * kRoundC;
+    for (int i = 0; i < nb; ++i) {
+      const int2 bs = sb[i];
+      float2 *tp = tplane + (bs.x - sp.y0) * kSX + (bs.y - sp.x0);
+      const float2 v = val[i * CC + coil];
+      const float2 *w = s_w + i * W;
+      float2 t0 = tp[off_it[0]], t1 = tp[off_it[1]], t2 = tp[off_it[2]];
+      cmacf(t0, w[n_it[0]], v);
+      cmacf(t1, w[n_it[1]], v);
+      tp[off_it[0]] = t0;
+      tp[off_it[1]] = t1;
+      if (last_on) {
+        cmacf(t2, w[n_it[2]], v);
+        tp[off_it[2]] = t2;
+      }
+      __syncwarp();
+    }
+  }
+  // merge the tile into the global grid
+  if (use_tma && sp.interior) {
+    fence_async_proxy();  // generic-proxy writes to shared memory -> visible to the TMA engine
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      for (int p = 0; p < CC; p += kBoxPlanes) tma_reduce_add_4d(&tmap, 2 * sp.x0, sp.y0, sp.c0 + p, sp.b, tile + p * kPS);
+      tma_store_commit_wait();  // shared memory must stay valid until the engine has read it
+    }
+  } else {
+    __syncthreads();
+    for (int e = threadIdx.x; e < CC * kPS; e += kThreads) {
+      const int cc = e / kPS, rem = e - cc * kPS;
+      if (sp.c0 + cc >= C) break;
+      const int r = rem / kSX, x = rem - r * kSX;
+      if (x >= kSX - 1) continue;  // the 22nd column is padding for TMA, never written
+      const float2 v = tile[e];
+      if (v.x == 0.f && v.y == 0.f) continue;
+      int gy = sp.y0 + r, gx = sp.x0 + x;
+      gy = gy < Ky ? gy : gy % Ky;
+      gx = gx < Kx ? gx : gx % Kx;
+      atomicAdd(&grid[((int64_t)(sp.b * C + sp.c0 + cc) * Ky + gy) * Kx + gx], v);
+    }
+  }
+}
+
 // ---- host side ------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
@@ -417,6 +569,8 @@ static bool make_grid_tmap(CUtensorMap *map, const void *grid, int64_t B, int64_
             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
+
+int g_adj_rowwarp = 0;  // A/B switch: 1 = row-ownership kernel also for 16-coil chunks
 
 static bool tiled_eligible(const b2n_geom *g, const b2n_points *p, int layout) {
   return g->dtype == B2N_C64 && g->ndim == 2 && layout == B2N_COIL_MAJOR && g->numpoints[0] == kJ &&
@@ -453,6 +607,21 @@ template <int CC> static int launch_adj(const InterpArgs<float> &a, const void *
   return 0;
 }
 
+static int launch_adj_coilwarp(const InterpArgs<float> &a, const void *kdata, void *grid, cudaStream_t st) {
+  constexpr int CC = 16;
+  const size_t smem = sizeof(float2) * (CC * kPS + kRoundC * kNC + kRoundC * kJ * kJ + 2 * kRoundC * CC) +
+                      sizeof(int2) * 2 * kRoundC + sizeof(int) * 3 * kRoundC;
+  B2N_CUDA_OK(cudaFuncSetAttribute(k_adj_coilwarp_2d, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  B2N_CUDA_OK(cudaMemsetAsync(grid, 0, sizeof(float2) * (size_t)(a.B * a.C * a.Kprod), st));
+  CUtensorMap map;
+  memset(&map, 0, sizeof(map));
+  const int use_tma = make_grid_tmap(&map, grid, a.B, a.C, a.K[0], a.K[1]) ? 1 : 0;
+  dim3 gd((unsigned)a.n_sub_max, (unsigned)ceil_div(a.C, CC), (unsigned)(a.n_traj == 1 ? a.B : 1));
+  k_adj_coilwarp_2d<<<gd, kThreads, smem, st>>>(a, (const float2 *)kdata, (float2 *)grid, map, use_tma);
+  B2N_LAUNCH_OK("k_adj_coilwarp_2d");
+  return 0;
+}
+
 // both return 1 when the tiled path does not apply (caller falls back to the generic kernels)
 int tiled_forward(const b2n_geom *g, const b2n_points *p, const void *grid, int64_t B, int64_t C, int layout,
                   void *kdata, cudaStream_t st) {
@@ -473,7 +642,7 @@ int tiled_adjoint(const b2n_geom *g, const b2n_points *p, const void *kdata, int
   InterpArgs<float> a;
   int rc = make_args<float>(g, p, B, C, &a);
   if (rc) return rc;
-  if (C > 8) return launch_adj<16>(a, kdata, grid, st);
+  if (C > 8) return g_adj_rowwarp ? launch_adj<16>(a, kdata, grid, st) : launch_adj_coilwarp(a, kdata, grid, st);
   if (C > 4) return launch_adj<8>(a, kdata, grid, st);
   if (C > 2) return launch_adj<4>(a, kdata, grid, st);
   if (C > 1) return launch_adj<2>(a, kdata, grid, st);
