@@ -171,7 +171,7 @@ B2N_D void stage_tile_elementwise(float2 *tile, const float2 *__restrict__ grid,
 // forward gather
 // -----------------------------------------------------------------------------------------
 template <int CC, int QY, int QX>
-__global__ void __launch_bounds__(kThreads) k_fwd_tiled_2d(InterpArgs<float> a, const float2 *__restrict__ grid,
+__global__ void __launch_bounds__(kThreads, 3) k_fwd_tiled_2d(InterpArgs<float> a, const float2 *__restrict__ grid,
                                                            float2 *__restrict__ kdata,
                                                            const __grid_constant__ CUtensorMap tmap, int use_tma) {
   constexpr int Q = QY * QX, NY = kJ / QY, NX = kJ / QX;
@@ -241,14 +241,23 @@ __global__ void __launch_bounds__(kThreads) k_fwd_tiled_2d(InterpArgs<float> a, 
 #pragma unroll
       for (int nx = 0; nx < NX; ++nx) cx[nx] = rec[kJ + nx * QX + qx];
       const float2 *t0 = tplane + (bs.x - sp.y0) * kSX + (bs.y - sp.x0);
+      // all footprint loads first, then NY independent row accumulators advanced together:
+      // 2*NY independent FFMA chains instead of 2 (the kernel was latency-bound, r01_d profile)
+      float2 g[NY][NX];
+#pragma unroll
+      for (int ny = 0; ny < NY; ++ny)
+#pragma unroll
+        for (int nx = 0; nx < NX; ++nx) g[ny][nx] = t0[ny * QY * kSX + nx * QX];
+      float2 row[NY];
+#pragma unroll
+      for (int ny = 0; ny < NY; ++ny) row[ny] = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int nx = 0; nx < NX; ++nx)
+#pragma unroll
+        for (int ny = 0; ny < NY; ++ny) cmacf(row[ny], cx[nx], g[ny][nx]);
       float2 even = make_float2(0.f, 0.f), odd = make_float2(0.f, 0.f);
 #pragma unroll
-      for (int ny = 0; ny < NY; ++ny) {
-        float2 row = make_float2(0.f, 0.f);
-#pragma unroll
-        for (int nx = 0; nx < NX; ++nx) cmacf(row, cx[nx], t0[ny * QY * kSX + nx * QX]);
-        cmacf((ny & 1) ? odd : even, cy[ny], row);
-      }
+      for (int ny = 0; ny < NY; ++ny) cmacf((ny & 1) ? odd : even, cy[ny], row[ny]);
       acc[u] = lane_on ? make_float2(even.x + odd.x, even.y + odd.y) : make_float2(0.f, 0.f);
     }
 #pragma unroll
@@ -406,7 +415,7 @@ __global__ void __launch_bounds__(kThreads) k_adj_tiled_2d(InterpArgs<float> a, 
 // -----------------------------------------------------------------------------------------
 constexpr int kRoundC = 24;  // points per round of the coil-partitioned adjoint
 
-__global__ void __launch_bounds__(kThreads) k_adj_coilwarp_2d(InterpArgs<float> a, const float2 *__restrict__ kdata,
+__global__ void __launch_bounds__(kThreads, 3) k_adj_coilwarp_2d(InterpArgs<float> a, const float2 *__restrict__ kdata,
                                                               float2 *__restrict__ grid,
                                                               const __grid_constant__ CUtensorMap tmap, int use_tma) {
   constexpr int CC = 16, W = kJ * kJ;
@@ -494,20 +503,30 @@ __global__ void __launch_bounds__(kThreads) k_adj_coilwarp_2d(InterpArgs<float> 
     cp_async_commit();
     const float2 *val = s_val + (round & 1) * kRoundC * CC;
     const int2 *sb = s_base + (round & 1) * kRoundC;
+    // software pipeline: the next point's base cell, sample and weights (read-only) are fetched
+    // while the current point's tile cells are updated (those must stay in program order)
+    int2 bs_n = sb[0];
+    float2 v_n = val[coil];
+    float2 w0_n = s_w[n_it[0]], w1_n = s_w[n_it[1]], w2_n = s_w[n_it[2]];
     for (int i = 0; i < nb; ++i) {
-      const int2 bs = sb[i];
+      const int2 bs = bs_n;
+      const float2 v = v_n, w0 = w0_n, w1 = w1_n, w2 = w2_n;
+      if (i + 1 < nb) {
+        bs_n = sb[i + 1];
+        v_n = val[(i + 1) * CC + coil];
+        const float2 *w = s_w + (i + 1) * W;
+        w0_n = w[n_it[0]];
+        w1_n = w[n_it[1]];
+        w2_n = w[n_it[2]];
+      }
       float2 *tp = tplane + (bs.x - sp.y0) * kSX + (bs.y - sp.x0);
-      const float2 v = val[i * CC + coil];
-      const float2 *w = s_w + i * W;
       float2 t0 = tp[off_it[0]], t1 = tp[off_it[1]], t2 = tp[off_it[2]];
-      cmacf(t0, w[n_it[0]], v);
-      cmacf(t1, w[n_it[1]], v);
+      cmacf(t0, w0, v);
+      cmacf(t1, w1, v);
+      cmacf(t2, w2, v);
       tp[off_it[0]] = t0;
       tp[off_it[1]] = t1;
-      if (last_on) {
-        cmacf(t2, w[n_it[2]], v);
-        tp[off_it[2]] = t2;
-      }
+      if (last_on) tp[off_it[2]] = t2;
       __syncwarp();
     }
   }
