@@ -174,6 +174,7 @@ def main():
     ap.add_argument("--adjoint-mode", default=None, choices=["atomic", "sorted"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--breakdown", action="store_true", help="print per-stage device times to stderr")
+    ap.add_argument("--opt", action="append", default=[], help="engine option id=value (A/B experiments)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -207,6 +208,9 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     if args.adjoint_mode:
         tkbn.set_adjoint_mode(args.adjoint_mode)
+    for kv in args.opt:
+        k, v = kv.split("=")
+        _lib.check(_lib.load().b2n_set_option(int(k), int(v)), "b2n_set_option")
 
     B = wl.n_batch if world == 1 else max(1, wl.n_batch // world) if wl.n_batch > 1 else 1
     image, smaps, kdata, omega = workloads.make_inputs(wl, seed=rank, n_batch=B)

@@ -105,10 +105,15 @@ enum b2n_option {
   B2N_OPT_TILED_KERNELS = 0, /* 1 (default): use the shared-memory tiled kernels where they apply */
   B2N_OPT_ADJ_ROW_OWNERSHIP = 1, /* 1: tiled adjoint with warp-owned rows also for 16-coil chunks (default 0:
                                     warps partition the coils) */
+  B2N_OPT_FWD_COIL_CHUNK = 2, /* 0 (default): 16 coils per CTA in the tiled forward; 8: two 8-coil CTAs */
   B2N_OPT_COUNT
 };
 B2N_API int b2n_set_option(int option, int value);
 B2N_API int b2n_get_option(int option);
+/* Development aid: when a device buffer of `capacity` records (6 x int64 each) is set, every CTA
+ * of the tiled kernels writes {SM id, points, t_start, t_staged, t_done, flags} (globaltimer ns)
+ * at its linear block index.  Pass NULL to switch tracing off (the default). */
+B2N_API int b2n_set_trace_buffer(void *records_dev, int64_t capacity);
 
 B2N_API int b2n_abi_version(void);
 B2N_API const char *b2n_last_error(void);

@@ -1,0 +1,48 @@
+"""Per-CTA timeline of the tiled forward kernel (development aid): python profiles/trace_cta.py"""
+import ctypes, sys, os
+import numpy as np, torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torchkbnufft_b200 as tkbn
+from torchkbnufft_b200 import _lib, workloads
+from torchkbnufft_b200._nufft import interp as eng
+
+wl = workloads.WORKLOADS["cfg2"]
+image, smaps, kdata, omega = workloads.make_inputs(wl, seed=0)
+dev = torch.device("cuda:0")
+ob = tkbn.KbInterp(im_size=wl.im_size, dtype=torch.complex64).to(dev)
+grid = torch.randn((1, wl.n_coils) + wl.grid_size, dtype=torch.complex64, device=dev)
+om = torch.from_numpy(omega).to(dev)
+args = (ob.tables, ob.n_shift, ob.numpoints, ob.table_oversamp)
+for _ in range(3):
+    eng.table_interp(grid, om, *args)
+cap = 8192
+buf = torch.zeros(cap * 6, dtype=torch.int64, device=dev)
+lib = _lib.load()
+flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev); flush.fill_(1)
+lib.b2n_set_trace_buffer(ctypes.c_void_p(buf.data_ptr()), cap)
+eng.table_interp(grid, om, *args)
+torch.cuda.synchronize()
+lib.b2n_set_trace_buffer(None, 0)
+r = buf.cpu().numpy().reshape(cap, 6)
+r = r[r[:, 2] > 0]
+t0 = r[:, 2].min()
+start, staged, done = (r[:, 2] - t0) / 1e3, (r[:, 3] - t0) / 1e3, (r[:, 4] - t0) / 1e3
+print(f"CTAs traced {len(r)}  kernel span {done.max():.1f} us")
+print(f"staging  mean {np.mean(staged - start):.2f} us  p50 {np.median(staged - start):.2f}  p95 {np.percentile(staged - start, 95):.2f}  max {np.max(staged - start):.2f}")
+print(f"compute  mean {np.mean(done - staged):.2f} us  p50 {np.median(done - staged):.2f}  p95 {np.percentile(done - staged, 95):.2f}  max {np.max(done - staged):.2f}")
+pts = r[:, 1]
+print(f"points per CTA mean {pts.mean():.1f} max {pts.max()}  compute ns/point {1e3 * np.sum(done - staged) / pts.sum():.1f}")
+for tma in (0, 1):
+    m = r[:, 5] == tma
+    if m.any():
+        print(f"tma={tma}: n={m.sum()} staging mean {np.mean((staged - start)[m]):.2f} us compute mean {np.mean((done - staged)[m]):.2f} us points {pts[m].mean():.1f}")
+# busy time per SM
+for q in (0, 25, 50, 75, 100):
+    print(f"start-time percentile {q}: {np.percentile(start, q):.1f} us   end-time percentile {q}: {np.percentile(done, q):.1f} us")
+sm_busy = {}
+for sm, a_, b_ in zip(r[:, 0], start, done):
+    sm_busy.setdefault(sm, []).append((a_, b_))
+ends = [max(b for _, b in v) for v in sm_busy.values()]
+print(f"SMs used {len(sm_busy)}  per-SM last end: min {min(ends):.1f} median {np.median(ends):.1f} max {max(ends):.1f} us")
+conc = np.mean([len(v) for v in sm_busy.values()])
+print(f"CTAs per SM mean {conc:.1f}")

@@ -19,6 +19,7 @@ ADJ_ATOMIC, ADJ_SORTED = 0, 1
 ABI_VERSION = 1
 OPT_TILED_KERNELS = 0
 OPT_ADJ_ROW_OWNERSHIP = 1
+OPT_FWD_COIL_CHUNK = 2
 
 _CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")
 LIB_PATH = os.path.join(_CSRC, "libb200nufft.so")
@@ -79,6 +80,7 @@ SIGNATURES = {
     "b2n_device_count": (c_int, []),
     "b2n_set_option": (c_int, [c_int, c_int]),
     "b2n_get_option": (c_int, [c_int]),
+    "b2n_set_trace_buffer": (c_int, [c_void_p, c_int64]),
     "b2n_points_workspace_bytes": (c_int, [POINTER(Geom), c_int64, c_int64, POINTER(c_size_t)]),
     "b2n_points_build": (c_int, [POINTER(Geom), c_void_p, c_int64, c_int64, c_void_p, c_size_t, POINTER(Points),
                                  c_void_p]),

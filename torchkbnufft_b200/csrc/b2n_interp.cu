@@ -229,8 +229,11 @@ int tiled_forward(const b2n_geom *g, const b2n_points *p, const void *grid, int6
 int tiled_adjoint(const b2n_geom *g, const b2n_points *p, const void *kdata, int64_t B, int64_t C, int layout,
                   void *grid, cudaStream_t st);
 
+long long *g_trace_buffer = nullptr;
+int64_t g_trace_capacity = 0;
 extern int g_adj_rowwarp;
-static int g_options[B2N_OPT_COUNT] = {1, 0};
+extern int g_fwd_chunk;
+static int g_options[B2N_OPT_COUNT] = {1, 0, 0};
 
 }  // namespace b2n
 
@@ -240,6 +243,13 @@ extern "C" int b2n_set_option(int option, int value) {
   if (option < 0 || option >= B2N_OPT_COUNT) return fail_arg(B2N_E_ARG, "unknown option %d", option);
   g_options[option] = value;
   if (option == B2N_OPT_ADJ_ROW_OWNERSHIP) g_adj_rowwarp = value;
+  if (option == B2N_OPT_FWD_COIL_CHUNK) g_fwd_chunk = value;
+  return 0;
+}
+
+extern "C" int b2n_set_trace_buffer(void *records_dev, int64_t capacity) {
+  g_trace_buffer = (long long *)records_dev;
+  g_trace_capacity = records_dev ? capacity : 0;
   return 0;
 }
 

@@ -6,6 +6,8 @@
 namespace b2n {
 
 int validate_geom(const b2n_geom *g, bool need_tables);
+extern long long *g_trace_buffer;
+extern int64_t g_trace_capacity;
 
 template <typename T> struct InterpArgs {
   int J[B2N_MAX_DIMS];
@@ -24,6 +26,8 @@ template <typename T> struct InterpArgs {
   int64_t n_sub_max;
   int sub_cap;
   Tiling tiling;
+  long long *trace;  // optional per-CTA timeline (b2n_set_trace_buffer), NULL in production
+  int64_t trace_cap;
 };
 
 template <typename T>
@@ -65,6 +69,8 @@ static inline int make_args(const b2n_geom *g, const b2n_points *p, int64_t B, i
   a->n_sub = p->n_sub;
   a->n_sub_max = p->n_sub_max;
   a->sub_cap = p->sub_cap;
+  a->trace = g_trace_buffer;
+  a->trace_cap = g_trace_capacity;
   a->tiling = make_tiling(g->ndim, g->grid_size);
   for (int d = 0; d < B2N_MAX_DIMS; ++d)
     if (a->tiling.T[d] != p->tile[d] || a->tiling.nt[d] != p->n_tiles[d])

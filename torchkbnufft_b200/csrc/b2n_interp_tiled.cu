@@ -115,6 +115,27 @@ B2N_D void tma_store_commit_wait() {
 }
 B2N_D void fence_async_proxy() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
 
+B2N_D long long gtime() {
+  long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+B2N_D int smid() {
+  int v;
+  asm volatile("mov.u32 %0, %%smid;" : "=r"(v));
+  return v;
+}
+// per-CTA timeline record (development aid, see b2n_set_trace_buffer)
+B2N_D void trace_write(const InterpArgs<float> &a, int points, long long t0, long long t1, long long t2, int flags) {
+  if (a.trace && threadIdx.x == 0) {
+    const int64_t id = ((int64_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+    if (id < a.trace_cap) {
+      long long *r = a.trace + id * 6;
+      r[0] = smid(); r[1] = points; r[2] = t0; r[3] = t1; r[4] = t2; r[5] = flags;
+    }
+  }
+}
+
 struct SubProblem {
   int b, c0, y0, x0, start, count;
   bool valid, interior;
@@ -182,6 +203,7 @@ __global__ void __launch_bounds__(kThreads, 3) k_fwd_tiled_2d(InterpArgs<float> 
   int2 *s_base = reinterpret_cast<int2 *>(s_coef + kCap * kNC);        // [kCap]
   int *s_perm = reinterpret_cast<int *>(s_base + kCap);                // [kCap]
   uint64_t *bar = reinterpret_cast<uint64_t *>(s_perm + kCap);
+  const long long t_start = a.trace ? gtime() : 0;
   const SubProblem sp = decode<CC>(a);
   if (!sp.valid) return;
   const int Ky = (int)a.K[0], Kx = (int)a.K[1];
@@ -215,6 +237,7 @@ __global__ void __launch_bounds__(kThreads, 3) k_fwd_tiled_2d(InterpArgs<float> 
   cp_async_wait_all();
   if (tma) mbar_wait(bar, 0);
   __syncthreads();
+  const long long t_staged = a.trace ? gtime() : 0;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int c, q;
@@ -274,6 +297,10 @@ __global__ void __launch_bounds__(kThreads, 3) k_fwd_tiled_2d(InterpArgs<float> 
       }
       if (store && i0 + u < sp.count) out[s_perm[i0 + u]] = acc[u];
     }
+  }
+  if (a.trace) {
+    __syncthreads();
+    trace_write(a, sp.count, t_start, t_staged, gtime(), tma ? 1 : 0);
   }
 }
 
@@ -589,7 +616,8 @@ static bool make_grid_tmap(CUtensorMap *map, const void *grid, int64_t B, int64_
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-int g_adj_rowwarp = 0;  // A/B switch: 1 = row-ownership kernel also for 16-coil chunks
+int g_adj_rowwarp = 0;
+int g_fwd_chunk = 0;     // A/B switch: forward coil chunk per CTA for C > 8 (0 = 16, 8 = two 8-coil CTAs)  // A/B switch: 1 = row-ownership kernel also for 16-coil chunks
 
 static bool tiled_eligible(const b2n_geom *g, const b2n_points *p, int layout) {
   return g->dtype == B2N_C64 && g->ndim == 2 && layout == B2N_COIL_MAJOR && g->numpoints[0] == kJ &&
@@ -648,7 +676,8 @@ int tiled_forward(const b2n_geom *g, const b2n_points *p, const void *grid, int6
   InterpArgs<float> a;
   int rc = make_args<float>(g, p, B, C, &a);
   if (rc) return rc;
-  if (C > 8) return launch_fwd<16, 1, 2>(a, grid, kdata, st);
+  if (C > 8 && g_fwd_chunk != 8) return launch_fwd<16, 1, 2>(a, grid, kdata, st);
+  if (C > 8) return launch_fwd<8, 2, 2>(a, grid, kdata, st);
   if (C > 4) return launch_fwd<8, 2, 2>(a, grid, kdata, st);
   if (C > 2) return launch_fwd<4, 2, 3>(a, grid, kdata, st);
   if (C > 1) return launch_fwd<2, 2, 6>(a, grid, kdata, st);

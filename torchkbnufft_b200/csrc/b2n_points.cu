@@ -174,6 +174,42 @@ __global__ void k_point_records(GeomT<T> g, const T *__restrict__ omega, int64_t
   }
 }
 
+// Longest-processing-time-first order of the sub-problems: CTAs are dispatched in block
+// index order, so the expensive ones (full chunks; tiles on the periodic boundary, which
+// cannot use TMA) must come first or they form the tail of every launch (measured:
+// profiles/r01_d, per-SM end times 36..59 us before this ordering).
+__global__ void k_sub_keys(const int32_t *__restrict__ sub_tile, const int32_t *__restrict__ sub_count,
+                           const int32_t *__restrict__ n_sub, int64_t n_slots, Tiling tl, int64_t K0, int64_t K1,
+                           int64_t K2, int cap, uint32_t *__restrict__ keys, uint32_t *__restrict__ idx) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_slots) return;
+  idx[i] = (uint32_t)i;
+  if (i >= *n_sub) {
+    keys[i] = 0xFFFFFFFFu;
+    return;
+  }
+  int64_t tid = sub_tile[i] % tl.n_tiles;
+  const int64_t t2 = tid % tl.nt[2]; tid /= tl.nt[2];
+  const int64_t t1 = tid % tl.nt[1]; tid /= tl.nt[1];
+  const int64_t t0 = tid;
+  // halo of J-1 (<= 15) cells past the tile must stay inside the grid for the TMA path
+  const bool interior = (t0 + 1) * tl.T[0] + 6 <= K0 && (tl.ndim < 2 || (t1 + 1) * tl.T[1] + 6 <= K1) &&
+                        (tl.ndim < 3 || (t2 + 1) * tl.T[2] + 6 <= K2);
+  keys[i] = (interior ? (uint32_t)(cap + 1) : 0u) + (uint32_t)(cap - sub_count[i]);
+}
+
+__global__ void k_sub_gather(const uint32_t *__restrict__ order, int64_t n_slots, const int32_t *__restrict__ in_tile,
+                             const int32_t *__restrict__ in_start, const int32_t *__restrict__ in_count,
+                             int32_t *__restrict__ sub_tile, int32_t *__restrict__ sub_start,
+                             int32_t *__restrict__ sub_count) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_slots) return;
+  const uint32_t j = order[i];
+  sub_tile[i] = in_tile[j];
+  sub_start[i] = in_start[j];
+  sub_count[i] = in_count[j];
+}
+
 // cell_start[c] = first sorted slot whose key >= c  (c in [0, n_cells])
 __global__ void k_cell_start(const uint32_t *__restrict__ keys, int64_t total, int64_t n_cells,
                              int32_t *__restrict__ cell_start) {
@@ -214,7 +250,8 @@ __global__ void k_export_indices(GeomT<T> g, const T *__restrict__ omega, int64_
 // ---- workspace carving --------------------------------------------------------
 struct Carve {
   size_t perm, inv_perm, base, coef, phase, cell_start, keys, sub_tile, sub_start, sub_count, n_sub;
-  size_t keys_in, idx_in, idx_out, chunks, offsets, cub, total, cub_bytes;
+  size_t keys_in, idx_in, idx_out, chunks, offsets, tmp_tile, tmp_start, tmp_count, sub_keys, sub_keys_out, sub_idx,
+      sub_order, cub, total, cub_bytes;
   int64_t n_sub_max;
   int sub_cap;
   Tiling tiling;
@@ -259,6 +296,13 @@ static int carve(const b2n_geom *g, int64_t M, int64_t n_traj, Carve *c) {
   c->n_sub = take(sizeof(int32_t));
   c->chunks = take(sizeof(int32_t) * n_tiles_all);
   c->offsets = take(sizeof(int32_t) * n_tiles_all);
+  c->tmp_tile = take(sizeof(int32_t) * c->n_sub_max);
+  c->tmp_start = take(sizeof(int32_t) * c->n_sub_max);
+  c->tmp_count = take(sizeof(int32_t) * c->n_sub_max);
+  c->sub_keys = take(sizeof(uint32_t) * c->n_sub_max);
+  c->sub_keys_out = take(sizeof(uint32_t) * c->n_sub_max);
+  c->sub_idx = take(sizeof(uint32_t) * c->n_sub_max);
+  c->sub_order = take(sizeof(uint32_t) * c->n_sub_max);
   c->keys_in = take(sizeof(uint32_t) * total);
   c->idx_in = take(sizeof(uint32_t) * total);
   c->idx_out = take(sizeof(uint32_t) * total);
@@ -271,6 +315,11 @@ static int carve(const b2n_geom *g, int64_t M, int64_t n_traj, Carve *c) {
   err = cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, (const int32_t *)nullptr, (int32_t *)nullptr, (int)n_tiles_all);
   if (err != cudaSuccess) return check_cuda(err, "cub::DeviceScan::ExclusiveSum(size query)");
   if (scan_bytes > cub_bytes) cub_bytes = scan_bytes;
+  size_t sub_sort_bytes = 0;
+  err = cub::DeviceRadixSort::SortPairs(nullptr, sub_sort_bytes, (const uint32_t *)nullptr, (uint32_t *)nullptr,
+                                        (const uint32_t *)nullptr, (uint32_t *)nullptr, (int)c->n_sub_max, 0, 32);
+  if (err != cudaSuccess) return check_cuda(err, "cub::DeviceRadixSort::SortPairs(sub-problem size query)");
+  if (sub_sort_bytes > cub_bytes) cub_bytes = sub_sort_bytes;
   c->cub_bytes = cub_bytes;
   c->cub = take(cub_bytes + 256);
   c->total = off;
@@ -330,10 +379,24 @@ static int build_impl(const b2n_geom *geom, const void *omega, int64_t M, int64_
   B2N_LAUNCH_OK("k_tile_chunks");
   size_t scan_bytes = c.cub_bytes;
   B2N_CUDA_OK(cub::DeviceScan::ExclusiveSum(ws + c.cub, scan_bytes, chunks, offsets, (int)n_tiles_all, st));
+  int32_t *tmp_tile = (int32_t *)(ws + c.tmp_tile), *tmp_start = (int32_t *)(ws + c.tmp_start),
+          *tmp_count = (int32_t *)(ws + c.tmp_count);
   k_fill_subs<<<(unsigned)ceil_div(n_tiles_all, threads), threads, 0, st>>>(
-      out->cell_start, chunks, offsets, n_tiles_all, tl.TT, c.sub_cap, out->sub_tile, out->sub_start, out->sub_count,
-      out->n_sub);
+      out->cell_start, chunks, offsets, n_tiles_all, tl.TT, c.sub_cap, tmp_tile, tmp_start, tmp_count, out->n_sub);
   B2N_LAUNCH_OK("k_fill_subs");
+  uint32_t *skeys = (uint32_t *)(ws + c.sub_keys), *skeys_out = (uint32_t *)(ws + c.sub_keys_out),
+           *sidx = (uint32_t *)(ws + c.sub_idx), *sorder = (uint32_t *)(ws + c.sub_order);
+  k_sub_keys<<<(unsigned)ceil_div(c.n_sub_max, threads), threads, 0, st>>>(tmp_tile, tmp_count, out->n_sub, c.n_sub_max,
+                                                                           tl, g.K[0], g.ndim > 1 ? g.K[1] : 1,
+                                                                           g.ndim > 2 ? g.K[2] : 1, c.sub_cap, skeys, sidx);
+  B2N_LAUNCH_OK("k_sub_keys");
+  size_t sort_bytes = c.cub_bytes;
+  B2N_CUDA_OK(cub::DeviceRadixSort::SortPairs(ws + c.cub, sort_bytes, skeys, skeys_out, sidx, sorder, (int)c.n_sub_max, 0,
+                                              32, st));
+  k_sub_gather<<<(unsigned)ceil_div(c.n_sub_max, threads), threads, 0, st>>>(sorder, c.n_sub_max, tmp_tile, tmp_start,
+                                                                             tmp_count, out->sub_tile, out->sub_start,
+                                                                             out->sub_count);
+  B2N_LAUNCH_OK("k_sub_gather");
   return 0;
 }
 
