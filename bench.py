@@ -175,6 +175,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--breakdown", action="store_true", help="print per-stage device times to stderr")
     ap.add_argument("--opt", action="append", default=[], help="engine option id=value (A/B experiments)")
+    ap.add_argument("--fused-fft", action="store_true", help="A/B: own pruned FFT passes instead of cuFFT + element-wise kernels")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -208,6 +209,8 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     if args.adjoint_mode:
         tkbn.set_adjoint_mode(args.adjoint_mode)
+    if args.fused_fft:
+        eng_fft.use_fused_fft = True
     for kv in args.opt:
         k, v = kv.split("=")
         _lib.check(_lib.load().b2n_set_option(int(k), int(v)), "b2n_set_option")
@@ -262,29 +265,44 @@ def main():
     grid_size = tuple(wl.grid_size)
     ndim = len(grid_size)
 
+    fused = eng_fft.fused_fft_available(torch.complex64, grid_size)
+
     def stage_times(reps):
-        names = ["apod_pad", "fft", "interp_fwd", "interp_adj", "ifft", "crop_coilsum"]
+        if fused:
+            names = ["fft_fwd_fused", "interp_fwd", "interp_adj", "fft_adj_fused"]
+        else:
+            names = ["apod_pad", "fft", "interp_fwd", "interp_adj", "ifft", "crop_coilsum"]
         acc = {n: [] for n in names}
         for r in range(reps):
             flush.fill_(r & 0xFF)
-            ev = [torch.cuda.Event(enable_timing=True) for _ in range(7)]
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(len(names) + 1)]
             ev[0].record()
-            g = eng_fft.apod_pad(x, grid_size, s, nu.scaling_coef, 1.0)
-            ev[1].record()
-            g = eng_fft.fft_grid(g, ndim, inverse=False)
-            ev[2].record()
-            k = eng_interp.table_interp(g, om, *geo_args)
-            ev[3].record()
-            g2 = eng_interp.table_interp_adjoint(k, om, *geo_args, None, nu.grid_size)
-            ev[4].record()
-            g2 = eng_fft.fft_grid(g2, ndim, inverse=True)
-            ev[5].record()
-            eng_fft.crop_apod_coilsum(g2, wl.im_size, s, nu.scaling_coef, 1.0)
-            ev[6].record()
+            if fused:
+                g = eng_fft.fused_fft_forward(x, grid_size, s, nu.scaling_coef, 1.0)
+                ev[1].record()
+                k = eng_interp.table_interp(g, om, *geo_args)
+                ev[2].record()
+                g2 = eng_interp.table_interp_adjoint(k, om, *geo_args, None, nu.grid_size)
+                ev[3].record()
+                eng_fft.fused_fft_adjoint(g2, wl.im_size, s, nu.scaling_coef, 1.0)
+                ev[4].record()
+            else:
+                g = eng_fft.apod_pad(x, grid_size, s, nu.scaling_coef, 1.0)
+                ev[1].record()
+                g = eng_fft.fft_grid(g, ndim, inverse=False)
+                ev[2].record()
+                k = eng_interp.table_interp(g, om, *geo_args)
+                ev[3].record()
+                g2 = eng_interp.table_interp_adjoint(k, om, *geo_args, None, nu.grid_size)
+                ev[4].record()
+                g2 = eng_fft.fft_grid(g2, ndim, inverse=True)
+                ev[5].record()
+                eng_fft.crop_apod_coilsum(g2, wl.im_size, s, nu.scaling_coef, 1.0)
+                ev[6].record()
             torch.cuda.synchronize()
             for j, n in enumerate(names):
                 acc[n].append(ev[j].elapsed_time(ev[j + 1]))
-        return {n: statistics.mean(v) for n, v in acc.items()}
+        return {n: statistics.median(v) for n, v in acc.items()}
 
     stages = stage_times(max(5, min(20, args.steps)))
     fwd_b, adj_b, interp_b = algorithmic_bytes(wl, B)
@@ -373,7 +391,7 @@ def main():
             "stages_ms": {k: round(v, 5) for k, v in stages.items()},
             "cpu_baseline": cpu_baseline,
             "e2e": e2e,
-            "gpu_launches": 4 * args.steps,
+            "gpu_launches": (7 if fused else 5) * args.steps,  # own kernels per step (memset / cuFFT not counted)
             "clocks": clocks,
         }
         print(json.dumps(line), flush=True)

@@ -175,6 +175,29 @@ B2N_API int b2n_crop_apod_coilsum(int ndim, int dtype, const int64_t *im_size, c
 B2N_API int b2n_spectrum_mul(int dtype, void *spectrum_dev, const void *kernel_dev, int64_t n_batch, int64_t n_coils,
                      int64_t n_grid, int64_t kernel_batch, int grid_layout, double scale, void *stream);
 
+/* ---- pruned, fused FFT passes (complex64, coil-major) --------------------------------
+ * Own shared-memory Stockham transforms, one dimension per pass, which skip the zero-padded
+ * inputs / cropped outputs and fuse the element-wise work of the steps above:
+ *   forward = b2n_apod_pad + fftn(norm=None) in ndim passes,
+ *   adjoint = ifftn(norm="forward") + b2n_crop_apod_coilsum (+ optional Toeplitz kernel
+ *             multiply on the way in) in ndim passes.
+ * b2n_fft_supported(n): 1 when length n factors into {2,3,5,7,11,13} and is <= 8192.
+ * work_dev: device scratch of b2n_fft_work_bytes() bytes (intermediate, partially
+ * transformed arrays); not needed for ndim == 1.
+ * reference: fft_and_scale / ifft_and_scale / fft_filter, _nufft/fft.py:36-173. */
+B2N_API int b2n_fft_supported(int64_t n);
+B2N_API int b2n_fft_work_bytes(int ndim, const int64_t *im_size, const int64_t *grid_size, int64_t n_batch,
+                               int64_t n_coils, size_t *bytes);
+B2N_API int b2n_fft_forward_fused(int ndim, const int64_t *im_size, const int64_t *grid_size, int64_t n_batch,
+                                  int64_t n_coils, const void *image_dev, int64_t image_coils,
+                                  const void *smaps_dev, int64_t smaps_batch, const void *scaling_dev, double scale,
+                                  void *grid_dev, void *work_dev, void *stream);
+B2N_API int b2n_fft_adjoint_fused(int ndim, const int64_t *im_size, const int64_t *grid_size, int64_t n_batch,
+                                  int64_t n_coils, const void *grid_dev, const void *kernel_dev,
+                                  int64_t kernel_batch, const void *smaps_dev, int64_t smaps_batch,
+                                  const void *scaling_dev, double scale, void *image_dev, void *work_dev,
+                                  void *stream);
+
 #ifdef __cplusplus
 }
 #endif

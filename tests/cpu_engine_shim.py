@@ -91,6 +91,7 @@ def oracle_engine():
         (eng_fft, "apod_pad", eng_fft.apod_pad),
         (eng_fft, "crop_apod_coilsum", eng_fft.crop_apod_coilsum),
         (eng_fft, "spectrum_mul_", eng_fft.spectrum_mul_),
+        (eng_fft, "fused_fft_available", eng_fft.fused_fft_available),
     ]
     try:
         for mod in (eng_interp, ag_interp):
@@ -99,6 +100,7 @@ def oracle_engine():
         eng_fft.apod_pad = _apod_pad
         eng_fft.crop_apod_coilsum = _crop_apod_coilsum
         eng_fft.spectrum_mul_ = _spectrum_mul_
+        eng_fft.fused_fft_available = lambda dtype, grid_size: False  # CPU stand-in uses torch.fft
         yield
     finally:
         for mod, name, fn in saved:

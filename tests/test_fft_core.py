@@ -1,0 +1,53 @@
+"""The engine's mixed-radix Stockham FFT building blocks (csrc/b2n_fft_core.cuh), compiled for
+the host, against numpy: every radix (2,3,4,5,7,8,11,13,16), forward and unnormalised inverse,
+the sizes of the BASELINE configs, and rejection of sizes with a prime factor > 13."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+
+@pytest.fixture(scope="module")
+def hostfft(tmp_path_factory):
+    out = tmp_path_factory.mktemp("hostfft") / "libfftcore.so"
+    src = os.path.join(ROOT, "tests", "fft_core_host.cpp")
+    cmd = ["/usr/bin/g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-I/usr/local/cuda/include", src, "-o", str(out)]
+    subprocess.run(cmd, check=True)
+    return ctypes.CDLL(str(out))
+
+
+def run(lib, x, inverse):
+    n = x.shape[0]
+    out = np.empty(n, np.complex64)
+    radix = (ctypes.c_int * 16)()
+    stages = lib.host_fft(n, int(inverse), x.ctypes.data_as(ctypes.c_void_p), out.ctypes.data_as(ctypes.c_void_p), radix)
+    return stages, out, list(radix[: max(stages, 0)])
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 4, 5, 6, 7, 8, 11, 13, 16, 24, 25, 26, 28, 30, 35, 40, 64, 112,
+                               128, 256, 384, 512, 640, 768, 1000, 1024, 1280, 2048, 4096])
+def test_stockham_matches_numpy(n, hostfft):
+    rng = np.random.default_rng(n)
+    x = (rng.standard_normal(n) + 1j * rng.standard_normal(n)).astype(np.complex64)
+    for inverse in (False, True):
+        stages, got, radix = run(hostfft, x, inverse)
+        assert stages >= 0 and int(np.prod(radix)) == n if n > 1 else True
+        want = np.fft.ifft(x.astype(np.complex128)) * n if inverse else np.fft.fft(x.astype(np.complex128))
+        err = np.linalg.norm(got - want) / np.linalg.norm(want)
+        assert err < 5e-7, (n, inverse, radix, err)
+
+
+def test_balanced_power_of_two_split(hostfft):
+    x = np.ones(512, np.complex64)
+    assert run(hostfft, x, False)[2] == [8, 8, 8]
+    assert run(hostfft, np.ones(640, np.complex64), False)[2] == [16, 8, 5]
+    assert run(hostfft, np.ones(768, np.complex64), False)[2] == [16, 16, 3]
+
+
+@pytest.mark.parametrize("n", [17, 19, 34, 57, 23 * 8, 1021])
+def test_unsupported_sizes_are_rejected(n, hostfft):
+    assert run(hostfft, np.ones(n, np.complex64), False)[0] == -1

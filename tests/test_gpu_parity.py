@@ -364,3 +364,47 @@ def test_tiled_kernels_match_generic_and_oracle(grid_size, B, C, batched):
         assert rel_l2(res[tiled][1], want_a) <= 1e-4, f"adjoint tiled={tiled}"
     assert rel_l2(res[True][0], res[False][0]) <= 2e-6
     assert rel_l2(res[True][1], res[False][1]) <= 2e-6
+
+
+@pytest.mark.parametrize("N, K", [((24,), (40,)), ((19,), (64,)), ((16, 12), (32, 24)), ((13, 18), (26, 35)),
+                                  ((320, 320), (640, 640)), ((33, 30), (70, 64)), ((8, 7, 6), (16, 14, 12)),
+                                  ((17, 19, 12), (36, 40, 24))])
+def test_fused_pruned_fft_matches_torch(N, K):
+    """Own Stockham passes (pruned inputs / cropped outputs, fused apodisation, SENSE multiply,
+    coil sum and Toeplitz kernel multiply) against torch.fft + plain torch ops, complex64."""
+    torch.manual_seed(1)
+    dt = torch.complex64
+    eng_fft.use_fused_fft = True
+    assert eng_fft.fused_fft_available(dt, K)
+    d = len(N)
+    dims = list(range(-d, 0))
+    pad = []
+    for k, n in zip(reversed(K), reversed(N)):
+        pad += [0, k - n]
+    crop = (slice(None), slice(None)) + tuple(slice(0, n) for n in N)
+    for B, C in ((1, 1), (2, 3), (1, 16)):
+        image = torch.randn((B, 1) + N, dtype=dt, device=DEV)
+        multi = torch.randn((B, C) + N, dtype=dt, device=DEV)
+        scal = torch.randn(N, dtype=dt, device=DEV)
+        grid = torch.randn((B, C) + K, dtype=dt, device=DEV)
+        for smaps in (torch.randn((1, C) + N, dtype=dt, device=DEV), torch.randn((B, C) + N, dtype=dt, device=DEV)):
+            want = torch.fft.fftn(torch.nn.functional.pad(image * smaps * scal * 0.5, pad), dim=dims)
+            got = eng_fft.fused_fft_forward(image, K, smaps, scal, 0.5)
+            assert rel_l2(host(got), host(want)) <= 2e-6
+            want = torch.sum(torch.fft.ifftn(grid, dim=dims, norm="forward")[crop] * scal.conj() * smaps.conj(), 1,
+                             keepdim=True) * 0.25
+            got = eng_fft.fused_fft_adjoint(grid, N, smaps, scal, 0.25)
+            assert rel_l2(host(got), host(want)) <= 2e-6
+            if d > 1:
+                for kern in (torch.randn(K, dtype=dt, device=DEV), torch.randn((B,) + K, dtype=dt, device=DEV)):
+                    kb = kern if kern.ndim == d else kern.unsqueeze(1)
+                    want = torch.sum(torch.fft.ifftn(grid * kb, dim=dims, norm="forward")[crop] * smaps.conj(), 1,
+                                     keepdim=True)
+                    got = eng_fft.fused_fft_adjoint(grid, N, smaps, None, 1.0, kernel=kern)
+                    assert rel_l2(host(got), host(want)) <= 2e-6
+        want = torch.fft.fftn(torch.nn.functional.pad(multi * scal, pad), dim=dims)
+        assert rel_l2(host(eng_fft.fused_fft_forward(multi, K, None, scal, 1.0)), host(want)) <= 2e-6
+        want = torch.fft.ifftn(grid, dim=dims, norm="forward")[crop] * scal.conj()
+        assert rel_l2(host(eng_fft.fused_fft_adjoint(grid, N, None, scal, 1.0)), host(want)) <= 2e-6
+    assert not eng_fft.fused_fft_available(dt, (57,)) and not eng_fft.fused_fft_available(torch.complex128, K)
+    eng_fft.use_fused_fft = False

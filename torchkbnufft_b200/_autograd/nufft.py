@@ -53,6 +53,41 @@ class CropApodCoilsum(Function):
         return grad, None, None, None, None
 
 
+class FusedFftForward(Function):
+    """``image -> fftn(zero_pad(image * smaps * scaling_coef)) * scale`` with the engine's own
+    pruned FFT passes; the backward is :class:`FusedFftAdjoint`'s forward (exact adjoint)."""
+
+    @staticmethod
+    def forward(ctx, image, smaps, scaling_coef, grid_size, scale):
+        ctx.save_for_backward(smaps, scaling_coef)
+        ctx.im_size = tuple(image.shape[2:])
+        ctx.scale = scale
+        return _fft.fused_fft_forward(image, grid_size, smaps, scaling_coef, scale)
+
+    @staticmethod
+    def backward(ctx, grad_grid):
+        smaps, scaling_coef = ctx.saved_tensors
+        return _fft.fused_fft_adjoint(grad_grid, ctx.im_size, smaps, scaling_coef, ctx.scale), None, None, None, None
+
+
+class FusedFftAdjoint(Function):
+    """``grid -> sum_c crop(ifftn_unnormalised(grid)) * conj(scaling_coef) * conj(smaps) * scale``."""
+
+    @staticmethod
+    def forward(ctx, grid, smaps, scaling_coef, im_size, scale):
+        ctx.save_for_backward(smaps, scaling_coef)
+        ctx.grid_size = tuple(grid.shape[2:])
+        ctx.n_coils = grid.shape[1]
+        ctx.scale = scale
+        return _fft.fused_fft_adjoint(grid, im_size, smaps, scaling_coef, scale)
+
+    @staticmethod
+    def backward(ctx, grad_image):
+        smaps, scaling_coef = ctx.saved_tensors
+        grad = _fft.fused_fft_forward(grad_image, ctx.grid_size, smaps, scaling_coef, ctx.scale, n_coils=ctx.n_coils)
+        return grad, None, None, None, None
+
+
 def toeplitz_apply(image, kernel, smaps, normalized: bool):
     """``sum_c conj(S_c) crop(IFFT(kernel * FFT(pad(S_c * image))))`` for the whole
     batch at once (the reference loops over the batch in Python,
@@ -62,6 +97,11 @@ def toeplitz_apply(image, kernel, smaps, normalized: bool):
     n_grid = 1
     for k in grid_size:
         n_grid *= k
+    if ndim > 1 and _fft.fused_fft_available(image.dtype, grid_size):
+        # pruned passes both ways, kernel multiply fused into the first inverse pass
+        grid = _fft.fused_fft_forward(image, grid_size, smaps, None, 1.0)
+        return _fft.fused_fft_adjoint(grid, image.shape[2:], smaps, None, (1.0 / n_grid) if normalized else 1.0,
+                                      kernel=kernel)
     grid = _fft.apod_pad(image, grid_size, smaps, None, 1.0)
     grid = _fft.fft_grid(grid, ndim, inverse=False)
     # 'ortho' scales both transforms by 1/sqrt(prod K2): fold 1/prod(K2) into the filter pass

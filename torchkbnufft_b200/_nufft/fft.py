@@ -144,3 +144,104 @@ def ortho_scale(grid_size: Sequence[int], normalized: bool) -> float:
     for k in grid_size:
         n *= int(k)
     return 1.0 / math.sqrt(n)
+
+
+# ---------------------------------------------------------------------------------------
+# pruned, fused FFT passes (own Stockham kernels, complex64): see csrc/b2n_fft.cu
+# ---------------------------------------------------------------------------------------
+_FFT_SUPPORTED: dict = {}
+use_fused_fft = False  # A/B switch; off until the Stockham passes beat cuFFT + element-wise kernels (profiles/r01_e)
+
+
+def fused_fft_available(dtype: torch.dtype, grid_size: Sequence[int]) -> bool:
+    """True when the engine's own FFT passes handle this transform (complex64, every grid
+    length a product of primes <= 13); otherwise callers use cuFFT around the fused
+    element-wise kernels."""
+    if not use_fused_fft or dtype != torch.complex64:
+        return False
+    lib = _lib.load()
+    for n in grid_size:
+        n = int(n)
+        if n not in _FFT_SUPPORTED:
+            _FFT_SUPPORTED[n] = bool(lib.b2n_fft_supported(n))
+        if not _FFT_SUPPORTED[n]:
+            return False
+    return True
+
+
+def _fft_work(im_size, grid_size, B, C, device) -> Optional[Tensor]:
+    nbytes = ctypes.c_size_t(0)
+    _lib.check(_lib.load().b2n_fft_work_bytes(len(im_size), _lib.i64_array(im_size), _lib.i64_array(grid_size), B, C,
+                                              ctypes.byref(nbytes)), "b2n_fft_work_bytes")
+    return torch.empty(int(nbytes.value), dtype=torch.uint8, device=device) if nbytes.value else None
+
+
+def fused_fft_forward(image: Tensor, grid_size: Sequence[int], smaps: Optional[Tensor] = None,
+                      scaling_coef: Optional[Tensor] = None, scale: float = 1.0,
+                      n_coils: Optional[int] = None) -> Tensor:
+    """``fftn(zero_pad(image * smaps * scaling_coef)) * scale`` (unnormalised transform) in
+    ``ndim`` pruned passes; returns the coil-major grid ``(B, C, *K)``."""
+    require_cuda(image, "image")
+    image = image.contiguous()
+    B, Ci = image.shape[:2]
+    im_size, grid_size = list(image.shape[2:]), _sizes(grid_size)
+    Bs = 1
+    if smaps is not None:
+        smaps = smaps.contiguous()
+        C, Bs = smaps.shape[1], smaps.shape[0]
+    else:
+        C = Ci if n_coils is None else n_coils
+    out = torch.empty([B, C] + grid_size, dtype=image.dtype, device=image.device)
+    if out.numel() == 0:
+        return out
+    if scaling_coef is not None:
+        scaling_coef = scaling_coef.contiguous()
+    work = _fft_work(im_size, grid_size, B, C, image.device)
+    with torch.cuda.device(image.device):
+        _lib.check(
+            _lib.load().b2n_fft_forward_fused(
+                len(im_size), _lib.i64_array(im_size), _lib.i64_array(grid_size), B, C, image.data_ptr(), Ci,
+                smaps.data_ptr() if smaps is not None else None, Bs,
+                scaling_coef.data_ptr() if scaling_coef is not None else None, float(scale), out.data_ptr(),
+                work.data_ptr() if work is not None else None, current_stream_ptr(image.device)),
+            "b2n_fft_forward_fused",
+        )
+    return out
+
+
+def fused_fft_adjoint(grid: Tensor, im_size: Sequence[int], smaps: Optional[Tensor] = None,
+                      scaling_coef: Optional[Tensor] = None, scale: float = 1.0,
+                      kernel: Optional[Tensor] = None) -> Tensor:
+    """``sum_c crop(ifftn_unnormalised(grid * kernel)) * conj(scaling_coef) * conj(smaps) * scale``
+    in ``ndim`` pruned passes; ``kernel`` (Toeplitz, ``(*K)`` or ``(B, *K)``) is optional.
+    Returns ``(B, 1, *N)`` with smaps, ``(B, C, *N)`` without."""
+    require_cuda(grid, "grid")
+    grid = grid.contiguous()
+    im_size = _sizes(im_size)
+    B, C = grid.shape[:2]
+    grid_size = list(grid.shape[2:])
+    Bs = 1
+    if smaps is not None:
+        smaps = smaps.contiguous()
+        Bs = smaps.shape[0]
+    out = torch.empty([B, 1 if smaps is not None else C] + im_size, dtype=grid.dtype, device=grid.device)
+    if out.numel() == 0:
+        return out
+    if scaling_coef is not None:
+        scaling_coef = scaling_coef.contiguous()
+    kb = 1
+    if kernel is not None:
+        kernel = kernel.contiguous()
+        kb = kernel.shape[0] if kernel.ndim > len(grid_size) else 1
+    work = _fft_work(im_size, grid_size, B, C, grid.device)
+    with torch.cuda.device(grid.device):
+        _lib.check(
+            _lib.load().b2n_fft_adjoint_fused(
+                len(im_size), _lib.i64_array(im_size), _lib.i64_array(grid_size), B, C, grid.data_ptr(),
+                kernel.data_ptr() if kernel is not None else None, kb,
+                smaps.data_ptr() if smaps is not None else None, Bs,
+                scaling_coef.data_ptr() if scaling_coef is not None else None, float(scale), out.data_ptr(),
+                work.data_ptr() if work is not None else None, current_stream_ptr(grid.device)),
+            "b2n_fft_adjoint_fused",
+        )
+    return out

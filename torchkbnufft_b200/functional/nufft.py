@@ -9,7 +9,7 @@ import torch
 from torch import Tensor
 
 from .._autograd.interp import KbTableInterpAdjoint, KbTableInterpForward
-from .._autograd.nufft import ApodPad, CropApodCoilsum, ToeplitzFilter
+from .._autograd.nufft import ApodPad, CropApodCoilsum, FusedFftAdjoint, FusedFftForward, ToeplitzFilter
 from .._nufft import fft as _fft
 from .._nufft.plan import host_ints as _ints
 from .interp import _SPMAT_MSG, with_complex_view
@@ -26,8 +26,12 @@ def sense_nufft_forward(image: Tensor, smaps: Optional[Tensor], scaling_coef: Te
     if smaps is not None and (image.shape[1] != 1 or smaps.requires_grad):
         image, smaps = image * smaps, None  # general broadcast / d(smaps): plain torch multiply
     grid_size = _ints(grid_size)
-    grid = ApodPad.apply(image, smaps, scaling_coef, grid_size, _fft.ortho_scale(grid_size, normalized))
-    grid = _fft.fft_grid(grid, len(grid_size), inverse=False)
+    scale = _fft.ortho_scale(grid_size, normalized)
+    if _fft.fused_fft_available(image.dtype, grid_size):
+        grid = FusedFftForward.apply(image, smaps, scaling_coef, grid_size, scale)
+    else:
+        grid = ApodPad.apply(image, smaps, scaling_coef, grid_size, scale)
+        grid = _fft.fft_grid(grid, len(grid_size), inverse=False)
     return KbTableInterpForward.apply(grid, omega, tables, n_shift, numpoints, table_oversamp, offsets)
 
 
@@ -39,12 +43,15 @@ def sense_nufft_adjoint(data: Tensor, smaps: Optional[Tensor], scaling_coef: Ten
     normalized = _fft.check_norm(norm)
     grid_sizes = _ints(grid_size)
     grid = KbTableInterpAdjoint.apply(data, omega, tables, n_shift, numpoints, table_oversamp, offsets, grid_size)
-    grid = _fft.fft_grid(grid, len(grid_sizes), inverse=True)
     scale = _fft.ortho_scale(grid_sizes, normalized)
+    fused = _fft.fused_fft_available(data.dtype, grid_sizes)
+    finish = FusedFftAdjoint if fused else CropApodCoilsum
+    if not fused:
+        grid = _fft.fft_grid(grid, len(grid_sizes), inverse=True)
     if smaps is not None and smaps.requires_grad:
-        image = CropApodCoilsum.apply(grid, None, scaling_coef, _ints(im_size), scale)
+        image = finish.apply(grid, None, scaling_coef, _ints(im_size), scale)
         return torch.sum(image * smaps.conj(), dim=1, keepdim=True)
-    return CropApodCoilsum.apply(grid, smaps, scaling_coef, _ints(im_size), scale)
+    return finish.apply(grid, smaps, scaling_coef, _ints(im_size), scale)
 
 
 def kb_table_nufft(image: Tensor, scaling_coef: Tensor, im_size: Tensor, grid_size: Tensor, omega: Tensor,
