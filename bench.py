@@ -311,6 +311,11 @@ def main():
     dom = "interp_adj" if live["interp_adj"] >= live["interp_fwd"] else "interp_fwd"
     achieved = interp_b / (live[dom] * 1e-3) / 1e9
     pair_achieved = (fwd_b + adj_b) / (total_ms / args.steps * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if wl.name == "cfg2" and B == 1 and os.path.exists(tpath):
+        with open(tpath) as f:
+            traffic = json.load(f).get(dom)  # DRAM bytes of one launch from the committed ncu --set full capture
 
     # ---- end to end through the public API with HOST buffers ----------------------------------
     e2e = None
@@ -383,7 +388,7 @@ def main():
                        "l2": "512 MiB buffer written between timed steps (L2 flush)",
                        "plan": "trajectory plan cached across steps (built in warm-up)"},
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "kernel_ms": live[dom], "kernels_ms_in_step": live,
                          "algorithmic_bytes": interp_b,
                          "pair_algorithmic_bytes": fwd_b + adj_b, "pair_achieved": pair_achieved,

@@ -19,10 +19,22 @@ cap = 8192
 buf = torch.zeros(cap * 6, dtype=torch.int64, device=dev)
 lib = _lib.load()
 flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev); flush.fill_(1)
+which = sys.argv[1] if len(sys.argv) > 1 else "fwd"
+if len(sys.argv) > 2:
+    lib.b2n_set_option(int(sys.argv[2].split("=")[0]), int(sys.argv[2].split("=")[1]))
+kd = torch.randn((1, wl.n_coils, wl.n_points), dtype=torch.complex64, device=dev)
+if which == "adj":
+    for _ in range(2):
+        eng.table_interp_adjoint(kd, om, *args, None, ob.grid_size, mode="atomic")
+    flush.fill_(2)
 lib.b2n_set_trace_buffer(ctypes.c_void_p(buf.data_ptr()), cap)
-eng.table_interp(grid, om, *args)
+if which == "adj":
+    eng.table_interp_adjoint(kd, om, *args, None, ob.grid_size, mode="atomic")
+else:
+    eng.table_interp(grid, om, *args)
 torch.cuda.synchronize()
 lib.b2n_set_trace_buffer(None, 0)
+print("kernel:", which, sys.argv[2:] )
 r = buf.cpu().numpy().reshape(cap, 6)
 r = r[r[:, 2] > 0]
 t0 = r[:, 2].min()
@@ -30,6 +42,13 @@ start, staged, done = (r[:, 2] - t0) / 1e3, (r[:, 3] - t0) / 1e3, (r[:, 4] - t0)
 print(f"CTAs traced {len(r)}  kernel span {done.max():.1f} us")
 print(f"staging  mean {np.mean(staged - start):.2f} us  p50 {np.median(staged - start):.2f}  p95 {np.percentile(staged - start, 95):.2f}  max {np.max(staged - start):.2f}")
 print(f"compute  mean {np.mean(done - staged):.2f} us  p50 {np.median(done - staged):.2f}  p95 {np.percentile(done - staged, 95):.2f}  max {np.max(done - staged):.2f}")
+if which == "fwd":
+    issued = ((r[:, 5] >> 8) & 0xFFFFF) / 1e3
+    records = (r[:, 0] >> 32) / 1e3
+    r[:, 0] &= 0xFFFFFFFF
+    r[:, 5] &= 0xFF
+    print(f"fwd staging detail: copies issued at +{np.median(issued):.2f} us, records landed at +{np.median(records):.2f} us, "
+          f"tile landed at +{np.median(staged - start):.2f} us (medians)")
 pts = r[:, 1]
 print(f"points per CTA mean {pts.mean():.1f} max {pts.max()}  compute ns/point {1e3 * np.sum(done - staged) / pts.sum():.1f}")
 for tma in (0, 1):

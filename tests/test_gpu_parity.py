@@ -351,14 +351,21 @@ def test_tiled_kernels_match_generic_and_oracle(grid_size, B, C, batched):
                                                                mode="atomic")))
     finally:
         tkbn.set_tiled_kernels(True)
-    # second tiled adjoint variant (warp-owned rows instead of warp-owned coils for 16-coil chunks)
+    # the other tiled adjoint variants (warp-owned rows / warp-owned coils) and the 8-coil forward chunks
     lib = _lib.load()
+    for variant in (1, 2):
+        try:
+            lib.b2n_set_option(_lib.OPT_ADJ_ROW_OWNERSHIP, variant)
+            alt = host(eng_interp.table_interp_adjoint(dev(kdata), dev(omega), *args, None, ob.grid_size, mode="atomic"))
+        finally:
+            lib.b2n_set_option(_lib.OPT_ADJ_ROW_OWNERSHIP, 0)
+        assert rel_l2(alt, want_a) <= 1e-4, f"adjoint variant {variant}"
     try:
-        lib.b2n_set_option(_lib.OPT_ADJ_ROW_OWNERSHIP, 1)
-        row_adj = host(eng_interp.table_interp_adjoint(dev(kdata), dev(omega), *args, None, ob.grid_size, mode="atomic"))
+        lib.b2n_set_option(_lib.OPT_FWD_COIL_CHUNK, 8)
+        alt = host(eng_interp.table_interp(dev(grid), dev(omega), *args))
     finally:
-        lib.b2n_set_option(_lib.OPT_ADJ_ROW_OWNERSHIP, 0)
-    assert rel_l2(row_adj, want_a) <= 1e-4
+        lib.b2n_set_option(_lib.OPT_FWD_COIL_CHUNK, 0)
+    assert rel_l2(alt, want_f) <= 1e-5
     for tiled in (True, False):
         assert rel_l2(res[tiled][0], want_f) <= 1e-5, f"forward tiled={tiled}"
         assert rel_l2(res[tiled][1], want_a) <= 1e-4, f"adjoint tiled={tiled}"

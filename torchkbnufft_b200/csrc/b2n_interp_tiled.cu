@@ -144,9 +144,14 @@ struct SubProblem {
 // decode blockIdx -> (sub-problem, coil chunk, batch element)
 template <int CC> B2N_D SubProblem decode(const InterpArgs<float> &a) {
   SubProblem sp;
-  sp.valid = (int)blockIdx.x < *a.n_sub;
-  if (!sp.valid) return sp;
+  // four independent loads (the descriptor arrays are allocated to gridDim.x entries), so the
+  // CTA pays one global-memory latency here instead of two dependent ones
+  const int n_sub = *a.n_sub;
   const int tile_all = a.sub_tile[blockIdx.x];
+  sp.start = a.sub_start[blockIdx.x];
+  sp.count = a.sub_count[blockIdx.x];
+  sp.valid = (int)blockIdx.x < n_sub;
+  if (!sp.valid) return sp;
   const int n_tiles = (int)a.tiling.n_tiles;
   const int traj = tile_all / n_tiles, tid = tile_all - traj * n_tiles;
   const int ty = tid / a.tiling.nt[1], tx = tid - ty * a.tiling.nt[1];
@@ -154,8 +159,6 @@ template <int CC> B2N_D SubProblem decode(const InterpArgs<float> &a) {
   sp.x0 = tx * kTile;
   sp.c0 = blockIdx.y * CC;
   sp.b = a.n_traj == 1 ? (int)blockIdx.z : traj;
-  sp.start = a.sub_start[blockIdx.x];
-  sp.count = a.sub_count[blockIdx.x];
   sp.interior = sp.y0 + kSY <= (int)a.K[0] && sp.x0 + kSX <= (int)a.K[1];
   return sp;
 }
@@ -210,7 +213,17 @@ __global__ void __launch_bounds__(kThreads, 3) k_fwd_tiled_2d(InterpArgs<float> 
   const int C = (int)a.C;
   const bool tma = use_tma && sp.interior;
 
-  if (tma && threadIdx.x == 0) mbar_init(bar, 1);
+  // the tile first (longest latency): one thread arms the mbarrier and issues the TMA boxes
+  if (tma) {
+    if (threadIdx.x == 0) {
+      mbar_init(bar, 1);
+      mbar_expect_tx(bar, (unsigned)(planes<CC>() * kPS * sizeof(float2)));
+      for (int p = 0; p < planes<CC>(); p += kBoxPlanes)
+        tma_load_4d(tile + p * kPS, &tmap, 2 * sp.x0, sp.y0, sp.c0 + p, sp.b, bar);
+    }
+  } else {
+    stage_tile_elementwise<CC>(tile, grid, sp, C, Ky, Kx);
+  }
   // plan records of this sub-problem: contiguous in plan order
   {
     const float4 *src =
@@ -223,20 +236,12 @@ __global__ void __launch_bounds__(kThreads, 3) k_fwd_tiled_2d(InterpArgs<float> 
       cp_async4(&s_perm[e], &a.perm[sp.start + e]);
     }
   }
-  if (tma) {
-    __syncthreads();  // barrier initialised before anyone can wait on it
-    if (threadIdx.x == 0) {
-      mbar_expect_tx(bar, (unsigned)(planes<CC>() * kPS * sizeof(float2)));
-      for (int p = 0; p < planes<CC>(); p += kBoxPlanes)
-        tma_load_4d(tile + p * kPS, &tmap, 2 * sp.x0, sp.y0, sp.c0 + p, sp.b, bar);
-    }
-  } else {
-    stage_tile_elementwise<CC>(tile, grid, sp, C, Ky, Kx);
-  }
   cp_async_commit();
+  const long long t_issued = a.trace ? gtime() : 0;
   cp_async_wait_all();
+  const long long t_records = a.trace ? gtime() : 0;
+  __syncthreads();  // everyone's copies landed; the mbarrier initialisation is visible to all
   if (tma) mbar_wait(bar, 0);
-  __syncthreads();
   const long long t_staged = a.trace ? gtime() : 0;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -300,7 +305,13 @@ __global__ void __launch_bounds__(kThreads, 3) k_fwd_tiled_2d(InterpArgs<float> 
   }
   if (a.trace) {
     __syncthreads();
-    trace_write(a, sp.count, t_start, t_staged, gtime(), tma ? 1 : 0);
+    // flags: bit 0 = TMA path; bits 8.. = ns from start to "all copies issued"; bits 32.. = ns to "records landed"
+    trace_write(a, sp.count, t_start, t_staged, gtime(),
+                (tma ? 1 : 0) | (int)(((t_issued - t_start) & 0xFFFFF) << 8));
+    if (a.trace && threadIdx.x == 0) {
+      const int64_t id = ((int64_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+      if (id < a.trace_cap) a.trace[id * 6 + 0] |= (long long)(t_records - t_start) << 32;
+    }
   }
 }
 
@@ -317,6 +328,7 @@ __global__ void __launch_bounds__(kThreads) k_adj_tiled_2d(InterpArgs<float> a, 
   float2 *tile = reinterpret_cast<float2 *>(smem_raw);  // [planes][kSY][kSX] accumulators
   float2 *stage0 = tile + planes<CC>() * kPS;           // 2 x STAGE
   int *s_perm = reinterpret_cast<int *>(stage0 + 2 * STAGE);  // 3 x kRound sample indices
+  const long long t_start = a.trace ? gtime() : 0;
   const SubProblem sp = decode<CC>(a);
   if (!sp.valid) return;
   const int Ky = (int)a.K[0], Kx = (int)a.K[1];
@@ -405,6 +417,7 @@ __global__ void __launch_bounds__(kThreads) k_adj_tiled_2d(InterpArgs<float> a, 
       __syncwarp();
     }
   }
+  const long long t_accum = a.trace ? gtime() : 0;
   // merge the tile into the global grid
   if (use_tma && sp.interior) {
     fence_async_proxy();  // generic-proxy writes to shared memory -> visible to the TMA engine
@@ -428,6 +441,10 @@ __global__ void __launch_bounds__(kThreads) k_adj_tiled_2d(InterpArgs<float> a, 
       gx = gx < Kx ? gx : gx % Kx;
       atomicAdd(&grid[((int64_t)(sp.b * C + sp.c0 + cc) * Ky + gy) * Kx + gx], v);
     }
+  }
+  if (a.trace) {
+    __syncthreads();
+    trace_write(a, sp.count, t_start, t_accum, gtime(), (use_tma && sp.interior) ? 1 : 0);
   }
 }
 
@@ -453,6 +470,7 @@ __global__ void __launch_bounds__(kThreads, 3) k_adj_coilwarp_2d(InterpArgs<floa
   float2 *s_val = s_w + kRoundC * W;                       // 2 x [kRoundC][CC] gathered samples
   int2 *s_base = reinterpret_cast<int2 *>(s_val + 2 * kRoundC * CC);  // 2 x [kRoundC]
   int *s_perm = reinterpret_cast<int *>(s_base + 2 * kRoundC);        // 3 x [kRoundC]
+  const long long t_start = a.trace ? gtime() : 0;
   const SubProblem sp = decode<CC>(a);
   if (!sp.valid) return;
   const int Ky = (int)a.K[0], Kx = (int)a.K[1];
@@ -557,6 +575,7 @@ __global__ void __launch_bounds__(kThreads, 3) k_adj_coilwarp_2d(InterpArgs<floa
       __syncwarp();
     }
   }
+  const long long t_accum = a.trace ? gtime() : 0;
   // merge the tile into the global grid
   if (use_tma && sp.interior) {
     fence_async_proxy();  // generic-proxy writes to shared memory -> visible to the TMA engine
@@ -579,6 +598,155 @@ __global__ void __launch_bounds__(kThreads, 3) k_adj_coilwarp_2d(InterpArgs<floa
       gx = gx < Kx ? gx : gx % Kx;
       atomicAdd(&grid[((int64_t)(sp.b * C + sp.c0 + cc) * Ky + gy) * Kx + gx], v);
     }
+  }
+  if (a.trace) {
+    __syncthreads();
+    trace_write(a, sp.count, t_start, t_accum, gtime(), (use_tma && sp.interior) ? 1 : 0);
+  }
+}
+
+// -----------------------------------------------------------------------------------------
+// adjoint spread, warp-private tiles: each warp of the CTA owns a private 8-coil accumulation
+// tile and visits EVERY point of the sub-problem with lanes = (2x2 footprint cells, 8 coils),
+// nine read-modify-write steps per point, all nine independent (distinct cells).  No two
+// warps ever touch the same shared-memory word, so there are no atomics and no ownership
+// tests, and the operand traffic per point (3 cy + 3 cx + sample + base cell) is the
+// smallest of the three variants: measured shared-memory wavefronts per point
+// (profiles/r01_e): warp-owned coils 167, warp-owned rows ~110, this one ~88 (floor 72 = the
+// read-modify-write of 36 cells x 16 coils itself).  Small CTAs (NW warps) also mean many
+// independent CTAs per SM, so one CTA's staging overlaps the others' accumulation.
+// Banks: plane stride 462 = 14 (mod 16): 8 coils -> 8 distinct even bank pairs; the two
+// x-adjacent cells of a half-warp take the even and the odd ones -> conflict-free.
+// -----------------------------------------------------------------------------------------
+template <int NW>
+__global__ void __launch_bounds__(NW * 32) k_adj_warptile_2d(InterpArgs<float> a, const float2 *__restrict__ kdata,
+                                                             float2 *__restrict__ grid,
+                                                             const __grid_constant__ CUtensorMap tmap, int use_tma) {
+  constexpr int CC = NW * 8, NT = NW * 32;
+  constexpr int STAGE = kRound * kNC + kRound * CC + kRound;  // float2 slots: coef, val, base
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float2 *tile = reinterpret_cast<float2 *>(smem_raw);         // [CC][kSY][kSX] accumulators
+  float2 *stage0 = tile + CC * kPS;                            // 2 x STAGE
+  int *s_perm = reinterpret_cast<int *>(stage0 + 2 * STAGE);   // 3 x kRound sample indices
+  const long long t_start = a.trace ? gtime() : 0;
+  const SubProblem sp = decode<CC>(a);
+  if (!sp.valid) return;
+  const int Ky = (int)a.K[0], Kx = (int)a.K[1];
+  const int C = (int)a.C;
+  const int64_t M = a.M;
+  const float2 *pcoef = reinterpret_cast<const float2 *>(a.coef);
+  const int rounds = (sp.count + kRound - 1) / kRound;
+
+  auto issue_perm = [&](int round) {  // sample indices, two rounds ahead of their use
+    if (round < rounds) {
+      const int p0 = round * kRound, nb = min(kRound, sp.count - p0);
+      int *dst = s_perm + (round % 3) * kRound;
+      for (int e = threadIdx.x; e < nb; e += NT) cp_async4(&dst[e], &a.perm[sp.start + p0 + e]);
+    }
+  };
+  auto issue_data = [&](int round) {  // weights, base cells and gathered samples, one round ahead
+    if (round < rounds) {
+      float2 *buf = stage0 + (round & 1) * STAGE;
+      const int p0 = round * kRound, nb = min(kRound, sp.count - p0), s0 = sp.start + p0;
+      const float4 *src = reinterpret_cast<const float4 *>(pcoef + (int64_t)s0 * kNC);
+      float4 *dst = reinterpret_cast<float4 *>(buf);
+      for (int e = threadIdx.x; e < nb * (kNC / 2); e += NT) cp_async16(&dst[e], &src[e]);
+      float2 *val = buf + kRound * kNC;
+      const int *perm = s_perm + (round % 3) * kRound;
+      for (int e = threadIdx.x; e < kRound * CC; e += NT) {
+        const int cc = e / kRound, i = e - cc * kRound;  // consecutive threads: consecutive points, one coil
+        const bool on = sp.c0 + cc < C && i < nb;
+        cp_async8(&val[i * CC + cc], &kdata[(int64_t)(sp.b * C + (on ? sp.c0 + cc : 0)) * M + (on ? perm[i] : 0)], on);
+      }
+      int2 *sb = reinterpret_cast<int2 *>(val + kRound * CC);
+      const int2 *bsrc = reinterpret_cast<const int2 *>(a.base) + s0;
+      for (int e = threadIdx.x; e < nb; e += NT) cp_async8(&sb[e], &bsrc[e], true);
+    }
+  };
+
+  issue_perm(0);
+  issue_perm(1);
+  cp_async_commit();
+  {
+    float4 *t4 = reinterpret_cast<float4 *>(tile);
+    for (int e = threadIdx.x; e < CC * kPS / 2; e += NT) t4[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  cp_async_wait_all();
+  __syncthreads();
+  issue_data(0);
+  cp_async_commit();
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c8 = lane & 7, q = lane >> 3, qy = q >> 1, qx = q & 1;
+  const int coil = warp * 8 + c8;
+  float2 *tplane = tile + coil * kPS + qy * kSX + qx;
+  for (int round = 0; round < rounds; ++round) {
+    cp_async_wait_all();
+    __syncthreads();  // this round's data (and next round's indices) landed; buffers of round-1 are free
+    issue_data(round + 1);
+    issue_perm(round + 2);
+    cp_async_commit();
+    const float2 *buf = stage0 + (round & 1) * STAGE;
+    const float2 *s_coef = buf, *s_val = buf + kRound * kNC;
+    const int2 *s_base = reinterpret_cast<const int2 *>(s_val + kRound * CC);
+    const int nb = min(kRound, sp.count - round * kRound);
+    for (int i = 0; i < nb; ++i) {
+      const int2 bs = s_base[i];
+      const float2 v = s_val[i * CC + coil];
+      const float2 *rec = s_coef + i * kNC;
+      float2 cyv[3], cxv[3], uy[3], t[3][3];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        cyv[k] = rec[2 * k + qy];
+        cxv[k] = rec[kJ + 2 * k + qx];
+      }
+      float2 *tp = tplane + (bs.x - sp.y0) * kSX + (bs.y - sp.x0);
+#pragma unroll
+      for (int ny = 0; ny < 3; ++ny)
+#pragma unroll
+        for (int nx = 0; nx < 3; ++nx) t[ny][nx] = tp[2 * ny * kSX + 2 * nx];
+#pragma unroll
+      for (int ny = 0; ny < 3; ++ny) {  // conj(cy) * v  (cy carries the fftshift phase)
+        uy[ny].x = fmaf(cyv[ny].x, v.x, cyv[ny].y * v.y);
+        uy[ny].y = fmaf(cyv[ny].x, v.y, -cyv[ny].y * v.x);
+      }
+#pragma unroll
+      for (int ny = 0; ny < 3; ++ny)
+#pragma unroll
+        for (int nx = 0; nx < 3; ++nx) {
+          cmacf_conj(t[ny][nx], cxv[nx], uy[ny]);
+          tp[2 * ny * kSX + 2 * nx] = t[ny][nx];
+        }
+      __syncwarp();
+    }
+  }
+  const long long t_accum = a.trace ? gtime() : 0;
+  // merge the tile into the global grid
+  if (use_tma && sp.interior) {
+    fence_async_proxy();  // generic-proxy writes to shared memory -> visible to the TMA engine
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      for (int p = 0; p < CC; p += kBoxPlanes) tma_reduce_add_4d(&tmap, 2 * sp.x0, sp.y0, sp.c0 + p, sp.b, tile + p * kPS);
+      tma_store_commit_wait();  // shared memory must stay valid until the engine has read it
+    }
+  } else {
+    __syncthreads();
+    for (int e = threadIdx.x; e < CC * kPS; e += NT) {
+      const int cc = e / kPS, rem = e - cc * kPS;
+      if (sp.c0 + cc >= C) break;
+      const int r = rem / kSX, x = rem - r * kSX;
+      if (x >= kSX - 1) continue;  // the 22nd column is padding for TMA, never written
+      const float2 v = tile[e];
+      if (v.x == 0.f && v.y == 0.f) continue;
+      int gy = sp.y0 + r, gx = sp.x0 + x;
+      gy = gy < Ky ? gy : gy % Ky;
+      gx = gx < Kx ? gx : gx % Kx;
+      atomicAdd(&grid[((int64_t)(sp.b * C + sp.c0 + cc) * Ky + gy) * Kx + gx], v);
+    }
+  }
+  if (a.trace) {
+    __syncthreads();
+    trace_write(a, sp.count, t_start, t_accum, gtime(), (use_tma && sp.interior) ? 1 : 0);
   }
 }
 
@@ -617,6 +785,7 @@ static bool make_grid_tmap(CUtensorMap *map, const void *grid, int64_t B, int64_
 }
 
 int g_adj_rowwarp = 0;
+int g_adj_chunk = 0;     // A/B switch: adjoint coil chunk per CTA for C > 8 (0 = 16, 8 = two 8-coil CTAs)
 int g_fwd_chunk = 0;     // A/B switch: forward coil chunk per CTA for C > 8 (0 = 16, 8 = two 8-coil CTAs)  // A/B switch: 1 = row-ownership kernel also for 16-coil chunks
 
 static bool tiled_eligible(const b2n_geom *g, const b2n_points *p, int layout) {
@@ -669,6 +838,22 @@ static int launch_adj_coilwarp(const InterpArgs<float> &a, const void *kdata, vo
   return 0;
 }
 
+template <int NW>
+static int launch_adj_warptile(const InterpArgs<float> &a, const void *kdata, void *grid, cudaStream_t st) {
+  constexpr int CC = NW * 8;
+  const size_t smem = sizeof(float2) * (CC * kPS + 2 * (kRound * kNC + kRound * CC + kRound)) + sizeof(int) * 3 * kRound;
+  auto kern = k_adj_warptile_2d<NW>;
+  B2N_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  B2N_CUDA_OK(cudaMemsetAsync(grid, 0, sizeof(float2) * (size_t)(a.B * a.C * a.Kprod), st));
+  CUtensorMap map;
+  memset(&map, 0, sizeof(map));
+  const int use_tma = make_grid_tmap(&map, grid, a.B, a.C, a.K[0], a.K[1]) ? 1 : 0;
+  dim3 gd((unsigned)a.n_sub_max, (unsigned)ceil_div(a.C, CC), (unsigned)(a.n_traj == 1 ? a.B : 1));
+  kern<<<gd, NW * 32, smem, st>>>(a, (const float2 *)kdata, (float2 *)grid, map, use_tma);
+  B2N_LAUNCH_OK("k_adj_warptile_2d");
+  return 0;
+}
+
 // both return 1 when the tiled path does not apply (caller falls back to the generic kernels)
 int tiled_forward(const b2n_geom *g, const b2n_points *p, const void *grid, int64_t B, int64_t C, int layout,
                   void *kdata, cudaStream_t st) {
@@ -690,7 +875,10 @@ int tiled_adjoint(const b2n_geom *g, const b2n_points *p, const void *kdata, int
   InterpArgs<float> a;
   int rc = make_args<float>(g, p, B, C, &a);
   if (rc) return rc;
-  if (C > 8) return g_adj_rowwarp ? launch_adj<16>(a, kdata, grid, st) : launch_adj_coilwarp(a, kdata, grid, st);
+  const bool wide = C > 8 && g_adj_chunk != 8;
+  if (g_adj_rowwarp == 0) return wide ? launch_adj_warptile<2>(a, kdata, grid, st) : launch_adj_warptile<1>(a, kdata, grid, st);
+  if (wide) return g_adj_rowwarp == 1 ? launch_adj<16>(a, kdata, grid, st) : launch_adj_coilwarp(a, kdata, grid, st);
+  if (C > 8) return launch_adj<8>(a, kdata, grid, st);
   if (C > 4) return launch_adj<8>(a, kdata, grid, st);
   if (C > 2) return launch_adj<4>(a, kdata, grid, st);
   if (C > 1) return launch_adj<2>(a, kdata, grid, st);
