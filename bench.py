@@ -53,7 +53,9 @@ def algorithmic_bytes(wl, B):
 
 
 class ClockSampler:
-    """nvidia-smi clock / throttle-reason sampling during the timed region."""
+    """SM clock / throttle-reason sampling DURING the timed region: an NVML polling thread
+    (5 ms period; the main thread sits in cudaDeviceSynchronize with the GIL released), with
+    nvidia-smi as a fallback when pynvml is unavailable."""
 
     FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
               "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -63,19 +65,68 @@ class ClockSampler:
         self.gpu_index = gpu_index
         self.proc = None
         self.path = None
+        self.thread = None
+        self.samples = []
+        self.reasons = set()
+        self.sm_max = None
+        self._stop = False
+
+    def _poll(self, nvml, handle):
+        bits = {
+            "hw_slowdown": getattr(nvml, "nvmlClocksEventReasonHwSlowdown", 0x8),
+            "hw_thermal_slowdown": getattr(nvml, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+            "sw_thermal_slowdown": getattr(nvml, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+            "sw_power_cap": getattr(nvml, "nvmlClocksEventReasonSwPowerCap", 0x4),
+        }
+        get_reasons = getattr(nvml, "nvmlDeviceGetCurrentClocksEventReasons",
+                              getattr(nvml, "nvmlDeviceGetCurrentClocksThrottleReasons", None))
+        while not self._stop:
+            try:
+                self.samples.append(float(nvml.nvmlDeviceGetClockInfo(handle, nvml.NVML_CLOCK_SM)))
+                if get_reasons is not None:
+                    mask = int(get_reasons(handle))
+                    for name, bit in bits.items():
+                        if mask & bit:
+                            self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.005)
 
     def start(self):
+        try:
+            import threading
+
+            import pynvml as nvml
+
+            nvml.nvmlInit()
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            index = int(visible.split(",")[self.gpu_index]) if visible and visible.split(",")[0].isdigit() \
+                else self.gpu_index
+            handle = nvml.nvmlDeviceGetHandleByIndex(index)
+            self.sm_max = float(nvml.nvmlDeviceGetMaxClockInfo(handle, nvml.NVML_CLOCK_SM))
+            self.thread = threading.Thread(target=self._poll, args=(nvml, handle), daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.thread = None
         try:
             fd, self.path = tempfile.mkstemp(suffix=".csv")
             os.close(fd)
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100",
+                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "20",
                  "-i", str(self.gpu_index)], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
 
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.thread is not None:
+            self._stop = True
+            self.thread.join(timeout=2)
+            if self.samples:
+                out.update(sm_mhz=statistics.median(self.samples), sm_max_mhz=self.sm_max,
+                           reasons=sorted(self.reasons), samples=len(self.samples), source="nvml")
+            return out
         if self.proc is None:
             return out
         self.proc.terminate()
@@ -102,7 +153,8 @@ class ClockSampler:
         except Exception:
             pass
         if sm:
-            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(smax), reasons=sorted(reasons), samples=len(sm))
+            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(smax), reasons=sorted(reasons), samples=len(sm),
+                       source="nvidia-smi")
         return out
 
 
@@ -167,7 +219,7 @@ def run_reference(args, wl, rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--workload", default="cfg2")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
