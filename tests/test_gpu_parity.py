@@ -360,12 +360,13 @@ def test_tiled_kernels_match_generic_and_oracle(grid_size, B, C, batched):
         finally:
             lib.b2n_set_option(_lib.OPT_ADJ_ROW_OWNERSHIP, 0)
         assert rel_l2(alt, want_a) <= 1e-4, f"adjoint variant {variant}"
-    try:
-        lib.b2n_set_option(_lib.OPT_FWD_COIL_CHUNK, 8)
-        alt = host(eng_interp.table_interp(dev(grid), dev(omega), *args))
-    finally:
-        lib.b2n_set_option(_lib.OPT_FWD_COIL_CHUNK, 0)
-    assert rel_l2(alt, want_f) <= 1e-5
+    for chunk in (8, 1):  # default 0 = one 16-coil CTA per sub-problem; 1 = persistent kernel; 8 = 8-coil CTAs
+        try:
+            lib.b2n_set_option(_lib.OPT_FWD_COIL_CHUNK, chunk)
+            alt = host(eng_interp.table_interp(dev(grid), dev(omega), *args))
+        finally:
+            lib.b2n_set_option(_lib.OPT_FWD_COIL_CHUNK, 0)
+        assert rel_l2(alt, want_f) <= 1e-5, f"forward variant {chunk}"
     for tiled in (True, False):
         assert rel_l2(res[tiled][0], want_f) <= 1e-5, f"forward tiled={tiled}"
         assert rel_l2(res[tiled][1], want_a) <= 1e-4, f"adjoint tiled={tiled}"

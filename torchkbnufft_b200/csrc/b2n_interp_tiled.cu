@@ -316,6 +316,200 @@ __global__ void __launch_bounds__(kThreads, 3) k_fwd_tiled_2d(InterpArgs<float> 
 }
 
 // -----------------------------------------------------------------------------------------
+// forward gather, persistent: one CTA per SM walks the (longest-first) sub-problem list with
+// TWO staging buffers, so the tile / records of item k+1 stream in (TMA + cp.async) while
+// item k is computed.  Measured motivation (profiles/trace_cta.py, r01_e): with one
+// sub-problem per CTA the staging phase (4 us) was as long as the compute phase (6 us) and,
+// with three CTAs per SM, was hidden only part of the time.
+// -----------------------------------------------------------------------------------------
+constexpr int kPersistBufs = 3;   // staging buffers of the persistent forward kernel (prefetch distance 2)
+constexpr int kPersistWarps = 24;
+constexpr int kPersistThreads = kPersistWarps * 32;
+
+struct StageBuf {
+  float2 *tile, *coef;
+  int2 *base;
+  int *perm;
+};
+
+template <int CC> struct Item {
+  int start, count, tile_all;
+};
+
+template <int CC, int QY, int QX>
+__global__ void __launch_bounds__(kPersistThreads, 1)
+    k_fwd_persist_2d(InterpArgs<float> a, const float2 *__restrict__ grid, float2 *__restrict__ kdata,
+                     const __grid_constant__ CUtensorMap tmap, int use_tma, int n_chunks, int n_batch) {
+  constexpr int Q = QY * QX, NY = kJ / QY, NX = kJ / QX;
+  constexpr int TILE_F2 = planes<CC>() * kPS;
+  constexpr int BUF_BYTES = TILE_F2 * 8 + kCap * kNC * 8 + kCap * 8 + kCap * 4;
+  static_assert(BUF_BYTES % 128 == 0, "staging buffers must keep 128-byte alignment for TMA");
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  constexpr int NBUF = kPersistBufs;
+  StageBuf buf[NBUF];
+#pragma unroll
+  for (int k = 0; k < NBUF; ++k) {
+    unsigned char *p = smem_raw + k * BUF_BYTES;
+    buf[k].tile = reinterpret_cast<float2 *>(p);
+    buf[k].coef = buf[k].tile + TILE_F2;
+    buf[k].base = reinterpret_cast<int2 *>(buf[k].coef + kCap * kNC);
+    buf[k].perm = reinterpret_cast<int *>(buf[k].base + kCap);
+  }
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + NBUF * BUF_BYTES);
+  const int Ky = (int)a.K[0], Kx = (int)a.K[1];
+  const int C = (int)a.C;
+  const int n_sub = *a.n_sub;
+  const int total = n_sub * n_chunks * n_batch;
+  if (threadIdx.x == 0)
+    for (int k = 0; k < NBUF; ++k) mbar_init(&bars[k], 1);
+  __syncthreads();
+
+  auto load_item = [&](int item, int &start, int &count, int &tile_all) {
+    if (item < total) {
+      const int x = item % n_sub;
+      start = a.sub_start[x];
+      count = a.sub_count[x];
+      tile_all = a.sub_tile[x];
+    } else {
+      start = count = tile_all = 0;
+    }
+  };
+  // decode an item into its sub-problem (coil chunk / batch element from the item index)
+  auto make_sp = [&](int item, int start, int count, int tile_all) {
+    SubProblem sp;
+    sp.valid = item < total;
+    const int yz = item / n_sub;
+    const int n_tiles = (int)a.tiling.n_tiles;
+    const int traj = tile_all / n_tiles, tid = tile_all - traj * n_tiles;
+    const int ty = tid / a.tiling.nt[1], tx = tid - ty * a.tiling.nt[1];
+    sp.y0 = ty * kTile;
+    sp.x0 = tx * kTile;
+    sp.c0 = (yz % n_chunks) * CC;
+    sp.b = a.n_traj == 1 ? yz / n_chunks : traj;
+    sp.start = start;
+    sp.count = count;
+    sp.interior = sp.y0 + kSY <= Ky && sp.x0 + kSX <= Kx;
+    return sp;
+  };
+  auto issue = [&](const SubProblem &sp, StageBuf &b, uint64_t *bar) {
+    if (sp.valid) {
+      const bool tma = use_tma && sp.interior;
+      if (tma) {
+        if (threadIdx.x == 0) {
+          mbar_expect_tx(bar, (unsigned)(TILE_F2 * sizeof(float2)));
+          for (int p = 0; p < planes<CC>(); p += kBoxPlanes)
+            tma_load_4d(b.tile + p * kPS, &tmap, 2 * sp.x0, sp.y0, sp.c0 + p, sp.b, bar);
+        }
+      } else {
+        for (int e = threadIdx.x; e < CC * kPS; e += kPersistThreads) {
+          const int c = e / kPS, rem = e - c * kPS;
+          const int r = rem / kSX, x = rem - r * kSX;
+          int gy = sp.y0 + r, gx = sp.x0 + x;
+          gy = gy < Ky ? gy : gy % Ky;
+          gx = gx < Kx ? gx : gx % Kx;
+          const bool on = sp.c0 + c < C;
+          cp_async8(&b.tile[e], &grid[((int64_t)(sp.b * C + (on ? sp.c0 + c : 0)) * Ky + gy) * Kx + gx], on);
+        }
+      }
+      const float4 *src =
+          reinterpret_cast<const float4 *>(reinterpret_cast<const float2 *>(a.coef) + (int64_t)sp.start * kNC);
+      float4 *dst = reinterpret_cast<float4 *>(b.coef);
+      for (int e = threadIdx.x; e < sp.count * (kNC / 2); e += kPersistThreads) cp_async16(&dst[e], &src[e]);
+      const int2 *bsrc = reinterpret_cast<const int2 *>(a.base) + sp.start;
+      for (int e = threadIdx.x; e < sp.count; e += kPersistThreads) {
+        cp_async8(&b.base[e], &bsrc[e], true);
+        cp_async4(&b.perm[e], &a.perm[sp.start + e]);
+      }
+    }
+    cp_async_commit();  // one group per item, even when empty, so that wait_group counts stay aligned
+  };
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int c, q;
+  lane_map<CC>(lane, c, q);
+  const bool lane_on = q < Q;
+  const int qy = lane_on ? q / QX : 0, qx = lane_on ? q - (q / QX) * QX : 0;
+
+  // software pipeline of depth NBUF-1: items k+1 .. k+NBUF-1 are in flight while item k is computed
+  const int G = gridDim.x;
+  constexpr int DR = NBUF + 2;  // descriptor ring: descriptors are fetched two items before they are issued
+  int it_id[DR], it_s[DR], it_n[DR], it_t[DR];  // slot = item ordinal % DR
+  unsigned phase[NBUF];
+#pragma unroll
+  for (int k = 0; k < NBUF; ++k) phase[k] = 0u;
+#pragma unroll
+  for (int k = 0; k < DR; ++k) {
+    it_id[k] = blockIdx.x + k * G;
+    load_item(it_id[k], it_s[k], it_n[k], it_t[k]);
+  }
+#pragma unroll
+  for (int k = 0; k < NBUF - 1; ++k) issue(make_sp(it_id[k], it_s[k], it_n[k], it_t[k]), buf[k], &bars[k]);
+  for (int k = 0;; ++k) {
+    const int cur = k % NBUF, dcur = k % DR;
+    if (it_id[dcur] >= total) break;
+    const SubProblem sp0 = make_sp(it_id[dcur], it_s[dcur], it_n[dcur], it_t[dcur]);
+    {
+      // refill the buffer whose item finished an iteration ago with item k + NBUF - 1
+      const int nb = (k + NBUF - 1) % NBUF, nd = (k + NBUF - 1) % DR;
+      issue(make_sp(it_id[nd], it_s[nd], it_n[nd], it_t[nd]), buf[nb], &bars[nb]);
+    }
+    // wait for the current item: all but the NBUF-1 newest cp.async groups, and the tile's mbarrier phase
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(NBUF - 1) : "memory");
+    __syncthreads();
+    if (use_tma && sp0.interior) {
+      mbar_wait(&bars[cur], phase[cur] & 1u);
+      ++phase[cur];
+    }
+
+    const StageBuf &b = buf[cur];
+    const float2 *tplane = b.tile + c * kPS + qy * kSX + qx;
+    float2 *out = kdata + (int64_t)(sp0.b * C + sp0.c0 + c) * a.M;
+    const bool store = q == 0 && sp0.c0 + c < C;
+    for (int i = warp; i < sp0.count; i += kPersistWarps) {
+      const int2 bs = b.base[i];
+      const float2 *rec = b.coef + i * kNC;
+      float2 cy[NY], cx[NX];
+#pragma unroll
+      for (int ny = 0; ny < NY; ++ny) cy[ny] = rec[ny * QY + qy];
+#pragma unroll
+      for (int nx = 0; nx < NX; ++nx) cx[nx] = rec[kJ + nx * QX + qx];
+      const float2 *tp = tplane + (bs.x - sp0.y0) * kSX + (bs.y - sp0.x0);
+      float2 g[NY][NX];
+#pragma unroll
+      for (int ny = 0; ny < NY; ++ny)
+#pragma unroll
+        for (int nx = 0; nx < NX; ++nx) g[ny][nx] = tp[ny * QY * kSX + nx * QX];
+      float2 row[NY];
+#pragma unroll
+      for (int ny = 0; ny < NY; ++ny) row[ny] = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int nx = 0; nx < NX; ++nx)
+#pragma unroll
+        for (int ny = 0; ny < NY; ++ny) cmacf(row[ny], cx[nx], g[ny][nx]);
+      float2 even = make_float2(0.f, 0.f), odd = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int ny = 0; ny < NY; ++ny) cmacf((ny & 1) ? odd : even, cy[ny], row[ny]);
+      float2 acc = lane_on ? make_float2(even.x + odd.x, even.y + odd.y) : make_float2(0.f, 0.f);
+      if (CC == 16) {
+        acc.x += __shfl_xor_sync(0xffffffffu, acc.x, 8);
+        acc.y += __shfl_xor_sync(0xffffffffu, acc.y, 8);
+      } else {
+#pragma unroll
+        for (int off = CC; off < 32; off <<= 1) {
+          acc.x += __shfl_xor_sync(0xffffffffu, acc.x, off);
+          acc.y += __shfl_xor_sync(0xffffffffu, acc.y, off);
+        }
+      }
+      if (store) out[b.perm[i]] = acc;
+    }
+    __syncthreads();  // everyone is done with this buffer before a later iteration refills it
+    // this descriptor slot now describes item k + DR (issued two iterations after the load)
+    it_id[dcur] += DR * G;
+    load_item(it_id[dcur], it_s[dcur], it_n[dcur], it_t[dcur]);
+  }
+}
+
+// -----------------------------------------------------------------------------------------
 // adjoint spread
 // -----------------------------------------------------------------------------------------
 template <int CC>
@@ -786,7 +980,7 @@ static bool make_grid_tmap(CUtensorMap *map, const void *grid, int64_t B, int64_
 
 int g_adj_rowwarp = 0;
 int g_adj_chunk = 0;     // A/B switch: adjoint coil chunk per CTA for C > 8 (0 = 16, 8 = two 8-coil CTAs)
-int g_fwd_chunk = 0;     // A/B switch: forward coil chunk per CTA for C > 8 (0 = 16, 8 = two 8-coil CTAs)  // A/B switch: 1 = row-ownership kernel also for 16-coil chunks
+int g_fwd_chunk = 0;     // A/B switch for C > 8: 0 = one 16-coil CTA per sub-problem, 1 = persistent kernel, 8 = 8-coil CTAs  // A/B switch: 1 = row-ownership kernel also for 16-coil chunks
 
 static bool tiled_eligible(const b2n_geom *g, const b2n_points *p, int layout) {
   return g->dtype == B2N_C64 && g->ndim == 2 && layout == B2N_COIL_MAJOR && g->numpoints[0] == kJ &&
@@ -805,6 +999,23 @@ static int launch_fwd(const InterpArgs<float> &a, const void *grid, void *kdata,
   dim3 gd((unsigned)a.n_sub_max, (unsigned)ceil_div(a.C, CC), (unsigned)(a.n_traj == 1 ? a.B : 1));
   kern<<<gd, kThreads, smem, st>>>(a, (const float2 *)grid, (float2 *)kdata, map, use_tma);
   B2N_LAUNCH_OK("k_fwd_tiled_2d");
+  return 0;
+}
+
+template <int CC, int QY, int QX>
+static int launch_fwd_persist(const InterpArgs<float> &a, const void *grid, void *kdata, cudaStream_t st) {
+  const size_t buf_bytes = sizeof(float2) * (planes<CC>() * kPS + kCap * kNC) + sizeof(int2) * kCap + sizeof(int) * kCap;
+  const size_t smem = kPersistBufs * buf_bytes + kPersistBufs * sizeof(uint64_t);
+  auto kern = k_fwd_persist_2d<CC, QY, QX>;
+  B2N_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CUtensorMap map;
+  memset(&map, 0, sizeof(map));
+  const int use_tma = make_grid_tmap(&map, grid, a.B, a.C, a.K[0], a.K[1]) ? 1 : 0;
+  int dev = 0, sms = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int n_chunks = (int)ceil_div(a.C, CC), n_batch = (int)(a.n_traj == 1 ? a.B : 1);
+  kern<<<sms, kPersistThreads, smem, st>>>(a, (const float2 *)grid, (float2 *)kdata, map, use_tma, n_chunks, n_batch);
+  B2N_LAUNCH_OK("k_fwd_persist_2d");
   return 0;
 }
 
@@ -861,6 +1072,7 @@ int tiled_forward(const b2n_geom *g, const b2n_points *p, const void *grid, int6
   InterpArgs<float> a;
   int rc = make_args<float>(g, p, B, C, &a);
   if (rc) return rc;
+  if (C > 8 && g_fwd_chunk == 1) return launch_fwd_persist<16, 1, 2>(a, grid, kdata, st);
   if (C > 8 && g_fwd_chunk != 8) return launch_fwd<16, 1, 2>(a, grid, kdata, st);
   if (C > 8) return launch_fwd<8, 2, 2>(a, grid, kdata, st);
   if (C > 4) return launch_fwd<8, 2, 2>(a, grid, kdata, st);
