@@ -43,53 +43,64 @@ static int make_pad_geom(int ndim, const int64_t *im_size, const int64_t *grid_s
 }
 
 // ---- image -> padded grid ------------------------------------------------------
-// coil-major: flat grid-stride loop over 16-byte output units (2 complex64 / 1 complex128)
-// so that every store is a full 128-bit write and the grid is written exactly once.
+// coil-major: one block row per (b, c, k0, k1) -- no per-element index decode -- and each thread
+// writes four 16-byte units spread over the row (all four stores in flight together), so
+// the grid is written exactly once with full 128-bit stores.
 template <typename T, typename I>
 __global__ void __launch_bounds__(256) k_apod_pad_cm(PadGeom g, const cplx<T> *__restrict__ image,
                                                      const cplx<T> *__restrict__ smaps,
                                                      const cplx<T> *__restrict__ scaling, T scale,
                                                      cplx<T> *__restrict__ grid) {
-  // I = int when every flat index fits 32 bits (64-bit integer division is ~10x slower)
   constexpr int VEC = 16 / (int)sizeof(cplx<T>);
+  constexpr int UNROLL = 4;
   const I K0 = (I)g.K[0], K1 = (I)g.K[1], K2 = (I)g.K[2], N0 = (I)g.N[0], N1 = (I)g.N[1], N2 = (I)g.N[2];
   const I C = (I)g.C, Ci = (I)g.Ci, Bs = (I)g.Bs, Np = (I)g.Nprod;
+  const I n_rows = (I)g.B * C * K0 * K1;
   const I units_per_row = (K2 + VEC - 1) / VEC;
-  const I n_units = (I)g.B * C * K0 * K1 * units_per_row;
-  for (I u = (I)blockIdx.x * blockDim.x + threadIdx.x; u < n_units; u += (I)gridDim.x * blockDim.x) {
-    I row = u / units_per_row;
-    const I k2 = (u - row * units_per_row) * VEC;
+  for (I row = blockIdx.x; row < n_rows; row += gridDim.x) {
     I t = row / K1;
     const I k1 = row - t * K1;
-    row = t;
-    t = row / K0;
-    const I k0 = row - t * K0;
-    row = t;
-    const I b = row / C, c = row - b * C;
-    cplx<T> v[VEC];
+    I r2 = t;
+    t = r2 / K0;
+    const I k0 = r2 - t * K0;
+    const I b = t / C, c = t - b * C;
     const bool row_inside = k0 < N0 && k1 < N1;
     const I nrow = (k0 * N1 + k1) * N2;
+    const cplx<T> *img = image + (b * Ci + (Ci == 1 ? 0 : c)) * Np + nrow;
+    const cplx<T> *smp = smaps ? smaps + ((Bs == 1 ? 0 : b) * C + c) * Np + nrow : nullptr;
+    const cplx<T> *scl = scaling ? scaling + nrow : nullptr;
+    cplx<T> *out = grid + (I)row * K2;
+    for (I u0 = threadIdx.x; u0 < units_per_row; u0 += blockDim.x * UNROLL) {
+      cplx<T> v[UNROLL][VEC];
 #pragma unroll
-    for (int e = 0; e < VEC; ++e) {
-      v[e].x = T(0);
-      v[e].y = T(0);
-      const I kk = k2 + e;
-      if (row_inside && kk < N2) {
-        const I n = nrow + kk;
-        cplx<T> w = image[(b * Ci + (Ci == 1 ? 0 : c)) * Np + n];
-        if (smaps) w = cmul(w, smaps[((Bs == 1 ? 0 : b) * C + c) * Np + n]);
-        if (scaling) w = cmul(w, scaling[n]);
-        v[e].x = w.x * scale;
-        v[e].y = w.y * scale;
+      for (int q = 0; q < UNROLL; ++q) {
+        const I k2 = (u0 + q * blockDim.x) * VEC;
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) {
+          v[q][e].x = T(0);
+          v[q][e].y = T(0);
+          if (row_inside && k2 + e < N2) {
+            cplx<T> w = img[k2 + e];
+            if (smp) w = cmul(w, smp[k2 + e]);
+            if (scl) w = cmul(w, scl[k2 + e]);
+            v[q][e].x = w.x * scale;
+            v[q][e].y = w.y * scale;
+          }
+        }
       }
-    }
-    cplx<T> *out = grid + (((b * C + c) * K0 + k0) * K1 + k1) * K2 + k2;
-    if (VEC == 2 && (K2 & 1) == 0) {
-      *reinterpret_cast<float4 *>(out) = *reinterpret_cast<const float4 *>(v);  // 16-byte aligned: K2 even
-    } else {
 #pragma unroll
-      for (int e = 0; e < VEC; ++e)
-        if (k2 + e < K2) out[e] = v[e];
+      for (int q = 0; q < UNROLL; ++q) {
+        const I u = u0 + q * blockDim.x;
+        if (u >= units_per_row) break;
+        const I k2 = u * VEC;
+        if (VEC == 2 && (K2 & 1) == 0) {
+          *reinterpret_cast<float4 *>(out + k2) = *reinterpret_cast<const float4 *>(v[q]);  // 16-byte aligned: K2 even
+        } else {
+#pragma unroll
+          for (int e = 0; e < VEC; ++e)
+            if (k2 + e < K2) out[k2 + e] = v[q][e];
+        }
+      }
     }
   }
 }
@@ -194,17 +205,15 @@ static int apod_pad_t(const PadGeom &g, const void *image, const void *smaps, co
     k_apod_pad_cl<T><<<gd, 256, 0, st>>>(g, (const cplx<T> *)image, (const cplx<T> *)smaps, (const cplx<T> *)scaling,
                                          (T)scale, (cplx<T> *)grid);
   } else {
-    constexpr int VEC = 16 / (int)sizeof(cplx<T>);
-    const int64_t n_units = g.B * g.C * g.K[0] * g.K[1] * ((g.K[2] + VEC - 1) / VEC);
-    int64_t blocks = ceil_div(n_units, 256 * 4);  // ~4 units per thread, capped at 16 CTAs per SM
-    if (blocks > 148 * 16) blocks = 148 * 16;
+    int64_t blocks = g.B * g.C * g.K[0] * g.K[1];  // one row per CTA iteration, at most 32 CTAs per SM
+    if (blocks > 148 * 32) blocks = 148 * 32;
     if (blocks < 1) blocks = 1;
     dim3 gd((unsigned)blocks);
     if (g.B * g.C * g.Kprod < ((int64_t)1 << 30))
-      k_apod_pad_cm<T, int><<<gd, 256, 0, st>>>(g, (const cplx<T> *)image, (const cplx<T> *)smaps,
+      k_apod_pad_cm<T, int><<<gd, 128, 0, st>>>(g, (const cplx<T> *)image, (const cplx<T> *)smaps,
                                                 (const cplx<T> *)scaling, (T)scale, (cplx<T> *)grid);
     else
-      k_apod_pad_cm<T, int64_t><<<gd, 256, 0, st>>>(g, (const cplx<T> *)image, (const cplx<T> *)smaps,
+      k_apod_pad_cm<T, int64_t><<<gd, 128, 0, st>>>(g, (const cplx<T> *)image, (const cplx<T> *)smaps,
                                                     (const cplx<T> *)scaling, (T)scale, (cplx<T> *)grid);
   }
   B2N_LAUNCH_OK("k_apod_pad");
