@@ -1,3 +1,3 @@
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "fused_fft_side or cases_match or cfg2 or golden" > gpurun_out/q_pytest.log 2>&1; tail -5 gpurun_out/q_pytest.log
-timeout 600 python bench.py --steps 50 --warmup 3 --breakdown --no-cpu-baseline 2>&1 | grep -E "stage ms|step ms"
+timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "tiled_3d or cfg4 or cases_match" > gpurun_out/q_pytest.log 2>&1; tail -12 gpurun_out/q_pytest.log
+timeout 900 python profiles/bench_configs.py cfg4 2>&1 | tail -3

@@ -416,3 +416,39 @@ def test_fused_pruned_fft_matches_torch(N, K):
         assert rel_l2(host(eng_fft.fused_fft_adjoint(grid, N, None, scal, 1.0)), host(want)) <= 2e-6
     assert not eng_fft.fused_fft_available(dt, (57,)) and not eng_fft.fused_fft_available(torch.complex128, K)
     eng_fft.use_fused_fft = False
+
+
+@pytest.mark.parametrize("grid_size", [(16, 16, 16), (24, 20, 28), (10, 12, 14), (13, 21, 9), (32, 8, 40)])
+@pytest.mark.parametrize("B, C, batched", [(1, 1, False), (2, 3, False), (1, 4, False), (1, 5, False), (2, 8, True)])
+def test_tiled_3d_kernels_match_generic_and_oracle(grid_size, B, C, batched):
+    """3-D shared-memory tiled kernels (complex64, J=6) against the generic kernels and the
+    oracle: partial tiles, grids smaller than a tile, wrap-around, dense sub-problems, coil tails."""
+    rng = np.random.default_rng(hash((grid_size, B, C)) & 0xFFFF)
+    im_size = tuple(max(2, k // 2) for k in grid_size)
+    ob = tkbn.KbInterp(im_size=im_size, grid_size=grid_size, dtype=torch.complex64).to(DEV)
+    M = 2500
+    shape = (B, 3, M) if batched else (3, M)
+    omega = rng.uniform(-np.pi, np.pi, size=shape)
+    omega[..., : M // 3] *= 0.08  # dense clump around k = 0
+    omega = np.ascontiguousarray(omega.astype(np.float32))
+    grid = workloads.complex_normal(rng, (B, C) + tuple(grid_size))
+    kdata = workloads.complex_normal(rng, (B, C, M))
+    args = (ob.tables, ob.n_shift, ob.numpoints, ob.table_oversamp)
+    tables = [host(t) for t in ob.tables]
+    J, L, ns = ob.numpoints.tolist(), ob.table_oversamp.tolist(), host(ob.n_shift)
+    want_f = orc.table_interp(grid, omega, tables, ns, J, L, nthreads=4)
+    want_a = orc.table_interp_adjoint(kdata, omega, tables, ns, J, L, grid_size, nthreads=4)
+    res = {}
+    try:
+        for tiled in (True, False):
+            tkbn.set_tiled_kernels(tiled)
+            res[tiled] = (host(eng_interp.table_interp(dev(grid), dev(omega), *args)),
+                          host(eng_interp.table_interp_adjoint(dev(kdata), dev(omega), *args, None, ob.grid_size,
+                                                               mode="atomic")))
+    finally:
+        tkbn.set_tiled_kernels(True)
+    for tiled in (True, False):
+        assert rel_l2(res[tiled][0], want_f) <= 1e-5, f"forward tiled={tiled}"
+        assert rel_l2(res[tiled][1], want_a) <= 1e-4, f"adjoint tiled={tiled}"
+    assert rel_l2(res[True][0], res[False][0]) <= 2e-6
+    assert rel_l2(res[True][1], res[False][1]) <= 2e-6

@@ -228,6 +228,10 @@ int tiled_forward(const b2n_geom *g, const b2n_points *p, const void *grid, int6
                   void *kdata, cudaStream_t st);
 int tiled_adjoint(const b2n_geom *g, const b2n_points *p, const void *kdata, int64_t B, int64_t C, int layout,
                   void *grid, cudaStream_t st);
+int tiled3_forward(const b2n_geom *g, const b2n_points *p, const void *grid, int64_t B, int64_t C, int layout,
+                   void *kdata, cudaStream_t st);
+int tiled3_adjoint(const b2n_geom *g, const b2n_points *p, const void *kdata, int64_t B, int64_t C, int layout,
+                   void *grid, cudaStream_t st);
 
 long long *g_trace_buffer = nullptr;
 int64_t g_trace_capacity = 0;
@@ -266,8 +270,10 @@ extern "C" int b2n_interp_forward(const b2n_geom *geom, const b2n_points *pts, c
   if (grid_layout != B2N_COIL_MAJOR && grid_layout != B2N_CHANNEL_LAST) return fail_arg(B2N_E_ARG, "bad layout");
   cudaStream_t st = (cudaStream_t)stream;
   if (g_options[B2N_OPT_TILED_KERNELS] && pts) {
-    const int rc = tiled_forward(geom, pts, grid_dev, n_batch, n_coils, grid_layout, kdata_dev, st);
+    int rc = tiled_forward(geom, pts, grid_dev, n_batch, n_coils, grid_layout, kdata_dev, st);
     if (rc != 1) return rc;  // 1 = not eligible, use the generic kernel
+    rc = tiled3_forward(geom, pts, grid_dev, n_batch, n_coils, grid_layout, kdata_dev, st);
+    if (rc != 1) return rc;
   }
   if (geom->dtype == B2N_C64) return forward_t<float>(geom, pts, grid_dev, n_batch, n_coils, grid_layout, kdata_dev, st);
   if (geom->dtype == B2N_C128) return forward_t<double>(geom, pts, grid_dev, n_batch, n_coils, grid_layout, kdata_dev, st);
@@ -281,7 +287,9 @@ extern "C" int b2n_interp_adjoint(const b2n_geom *geom, const b2n_points *pts, c
   if (mode != B2N_ADJ_ATOMIC && mode != B2N_ADJ_SORTED) return fail_arg(B2N_E_ARG, "bad adjoint mode %d", mode);
   cudaStream_t st = (cudaStream_t)stream;
   if (g_options[B2N_OPT_TILED_KERNELS] && pts && mode == B2N_ADJ_ATOMIC) {
-    const int rc = tiled_adjoint(geom, pts, kdata_dev, n_batch, n_coils, grid_layout, grid_dev, st);
+    int rc = tiled_adjoint(geom, pts, kdata_dev, n_batch, n_coils, grid_layout, grid_dev, st);
+    if (rc != 1) return rc;
+    rc = tiled3_adjoint(geom, pts, kdata_dev, n_batch, n_coils, grid_layout, grid_dev, st);
     if (rc != 1) return rc;
   }
   if (geom->dtype == B2N_C64)

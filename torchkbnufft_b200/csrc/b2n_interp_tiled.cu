@@ -28,10 +28,7 @@
 //     RED.ADD.F32x2 on boundary tiles.
 //
 // reference loops replaced: torchkbnufft/_nufft/interp.py:185-203 and :689-724.
-#include <cuda.h>
-
-#include "b2n_common.cuh"
-#include "b2n_interp.cuh"
+#include "b2n_tiled_common.cuh"
 
 namespace b2n {
 
@@ -46,95 +43,6 @@ constexpr int kSX = kTile + kJ - 1 + 1;  // 22 staged columns (even: 16-byte row
 constexpr int kPS = kSY * kSX;           // plane stride, 462 float2
 constexpr int kNC = 2 * kJ;              // complex weights per point record
 constexpr int kBoxPlanes = 8;            // coil planes per TMA box
-
-// ---- small device helpers -------------------------------------------------------------
-B2N_D void cmacf(float2 &acc, float2 a, float2 b) {  // acc += a * b, 4 FFMA
-  acc.x = fmaf(a.x, b.x, acc.x);
-  acc.x = fmaf(-a.y, b.y, acc.x);
-  acc.y = fmaf(a.x, b.y, acc.y);
-  acc.y = fmaf(a.y, b.x, acc.y);
-}
-B2N_D void cmacf_conj(float2 &acc, float2 a, float2 b) {  // acc += conj(a) * b
-  acc.x = fmaf(a.x, b.x, acc.x);
-  acc.x = fmaf(a.y, b.y, acc.x);
-  acc.y = fmaf(a.x, b.y, acc.y);
-  acc.y = fmaf(-a.y, b.x, acc.y);
-}
-
-B2N_D unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
-
-B2N_D void cp_async4(void *dst, const void *src) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(smem_u32(dst)), "l"(src) : "memory");
-}
-B2N_D void cp_async8(void *dst, const void *src, bool valid) {
-  const int src_size = valid ? 8 : 0;  // 0 -> destination bytes are zero-filled
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(smem_u32(dst)), "l"(src), "r"(src_size) : "memory");
-}
-B2N_D void cp_async16(void *dst, const void *src) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_u32(dst)), "l"(src) : "memory");
-}
-B2N_D void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
-B2N_D void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
-
-B2N_D void mbar_init(uint64_t *bar, unsigned count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-  asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
-}
-B2N_D void mbar_expect_tx(uint64_t *bar, unsigned bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-B2N_D void mbar_wait(uint64_t *bar, unsigned parity) {
-  unsigned done = 0;
-  for (unsigned spins = 0; !done; ++spins) {
-    asm volatile(
-        "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
-        : "=r"(done)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-    if (spins > (1u << 22)) __trap();  // a TMA that never lands must not hang the device
-  }
-}
-// TMA: 4-D box (x in floats, y, coil, batch) global -> shared, completion on an mbarrier
-B2N_D void tma_load_4d(void *dst, const CUtensorMap *map, int x, int y, int c, int b, uint64_t *bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];\n" ::
-          "r"(smem_u32(dst)),
-      "l"(map), "r"(x), "r"(y), "r"(c), "r"(b), "r"(smem_u32(bar))
-      : "memory");
-}
-// TMA: shared -> global element-wise FP32 add of a 4-D box (out-of-range parts are dropped)
-B2N_D void tma_reduce_add_4d(const CUtensorMap *map, int x, int y, int c, int b, const void *src) {
-  asm volatile(
-      "cp.reduce.async.bulk.tensor.4d.global.shared::cta.add.tile.bulk_group [%0, {%1, %2, %3, %4}], [%5];\n" ::"l"(map),
-      "r"(x), "r"(y), "r"(c), "r"(b), "r"(smem_u32(src))
-      : "memory");
-}
-B2N_D void tma_store_commit_wait() {
-  asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
-  asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
-}
-B2N_D void fence_async_proxy() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
-
-B2N_D long long gtime() {
-  long long t;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-  return t;
-}
-B2N_D int smid() {
-  int v;
-  asm volatile("mov.u32 %0, %%smid;" : "=r"(v));
-  return v;
-}
-// per-CTA timeline record (development aid, see b2n_set_trace_buffer)
-B2N_D void trace_write(const InterpArgs<float> &a, int points, long long t0, long long t1, long long t2, int flags) {
-  if (a.trace && threadIdx.x == 0) {
-    const int64_t id = ((int64_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
-    if (id < a.trace_cap) {
-      long long *r = a.trace + id * 6;
-      r[0] = smid(); r[1] = points; r[2] = t0; r[3] = t1; r[4] = t2; r[5] = flags;
-    }
-  }
-}
 
 struct SubProblem {
   int b, c0, y0, x0, start, count;
@@ -945,11 +853,7 @@ __global__ void __launch_bounds__(NW * 32) k_adj_warptile_2d(InterpArgs<float> a
 }
 
 // ---- host side ------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
-                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn encode_fn() {
+EncodeTiledFn tensor_map_encoder() {
   static EncodeTiledFn fn = nullptr;
   static bool tried = false;
   if (!tried) {
@@ -967,7 +871,7 @@ static EncodeTiledFn encode_fn() {
 // 4-D FP32 view of a coil-major complex64 grid (B, C, Ky, Kx): dims (2*Kx, Ky, C, B), box
 // (2*22, 21, 8, 1).  Returns false when TMA cannot describe it (odd Kx, unaligned base, ...).
 static bool make_grid_tmap(CUtensorMap *map, const void *grid, int64_t B, int64_t C, int64_t Ky, int64_t Kx) {
-  EncodeTiledFn fn = encode_fn();
+  EncodeTiledFn fn = tensor_map_encoder();
   if (!fn || (Kx & 1) || ((uintptr_t)grid & 15) || Ky < kSY || Kx < kSX) return false;
   const cuuint64_t gdim[4] = {(cuuint64_t)(2 * Kx), (cuuint64_t)Ky, (cuuint64_t)C, (cuuint64_t)B};
   const cuuint64_t gstride[3] = {(cuuint64_t)(Kx * 8), (cuuint64_t)(Ky * Kx * 8), (cuuint64_t)(C * Ky * Kx * 8)};
