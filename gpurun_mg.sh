@@ -1,0 +1,5 @@
+mkdir -p gpurun_out
+nvidia-smi -L | head -3
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus 2 --steps 100 --warmup 5 > gpurun_out/r1_bench_2gpu.log 2>&1; echo "exit $?"; tail -2 gpurun_out/r1_bench_2gpu.log | cut -c1-1500
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29518 bench.py --gpus 2 --impl reference --steps 3 --warmup 1 2>&1 | tail -1 | cut -c1-300
+timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29519 profiles/coil_shard_check.py 2>&1 | tail -4
