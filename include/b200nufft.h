@@ -188,17 +188,20 @@ B2N_API int b2n_spectrum_mul(int dtype, void *spectrum_dev, const void *kernel_d
  * transformed arrays); not needed for ndim == 1.
  * reference: fft_and_scale / ifft_and_scale / fft_filter, _nufft/fft.py:36-173. */
 B2N_API int b2n_fft_supported(int64_t n);
+/* Fill a caller buffer of n complex64 entries with exp(-2 pi i t / n) (computed in double). */
+B2N_API int b2n_fft_twiddles(int64_t n, void *twiddle_dev, void *stream);
 B2N_API int b2n_fft_work_bytes(int ndim, const int64_t *im_size, const int64_t *grid_size, int64_t n_batch,
                                int64_t n_coils, size_t *bytes);
+/* twiddle_dev: ndim device pointers, entry d = table of b2n_fft_twiddles(grid_size[d]) */
 B2N_API int b2n_fft_forward_fused(int ndim, const int64_t *im_size, const int64_t *grid_size, int64_t n_batch,
                                   int64_t n_coils, const void *image_dev, int64_t image_coils,
                                   const void *smaps_dev, int64_t smaps_batch, const void *scaling_dev, double scale,
-                                  void *grid_dev, void *work_dev, void *stream);
+                                  const void *const *twiddle_dev, void *grid_dev, void *work_dev, void *stream);
 B2N_API int b2n_fft_adjoint_fused(int ndim, const int64_t *im_size, const int64_t *grid_size, int64_t n_batch,
                                   int64_t n_coils, const void *grid_dev, const void *kernel_dev,
                                   int64_t kernel_batch, const void *smaps_dev, int64_t smaps_batch,
-                                  const void *scaling_dev, double scale, void *image_dev, void *work_dev,
-                                  void *stream);
+                                  const void *scaling_dev, double scale, const void *const *twiddle_dev,
+                                  void *image_dev, void *work_dev, void *stream);
 
 #ifdef __cplusplus
 }

@@ -98,10 +98,11 @@ SIGNATURES = {
                                  c_void_p]),
     "b2n_fft_supported": (c_int, [c_int64]),
     "b2n_fft_work_bytes": (c_int, [c_int, _I64P, _I64P, c_int64, c_int64, POINTER(c_size_t)]),
+    "b2n_fft_twiddles": (c_int, [c_int64, c_void_p, c_void_p]),
     "b2n_fft_forward_fused": (c_int, [c_int, _I64P, _I64P, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_int64,
-                                      c_void_p, c_double, c_void_p, c_void_p, c_void_p]),
+                                      c_void_p, c_double, POINTER(c_void_p), c_void_p, c_void_p, c_void_p]),
     "b2n_fft_adjoint_fused": (c_int, [c_int, _I64P, _I64P, c_int64, c_int64, c_void_p, c_void_p, c_int64, c_void_p,
-                                      c_int64, c_void_p, c_double, c_void_p, c_void_p, c_void_p]),
+                                      c_int64, c_void_p, c_double, POINTER(c_void_p), c_void_p, c_void_p, c_void_p]),
 }
 
 _lib: Optional[ctypes.CDLL] = None

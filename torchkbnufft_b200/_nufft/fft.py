@@ -169,6 +169,26 @@ def fused_fft_available(dtype: torch.dtype, grid_size: Sequence[int]) -> bool:
     return True
 
 
+_TWIDDLES: dict = {}
+
+
+def _twiddles(grid_size, device):
+    """Per-(device, length) twiddle tables exp(-2 pi i t / n), built once on the device."""
+    lib = _lib.load()
+    tabs = []
+    for n in grid_size:
+        key = (device.index, int(n))
+        t = _TWIDDLES.get(key)
+        if t is None:
+            t = torch.empty(int(n), dtype=torch.complex64, device=device)
+            with torch.cuda.device(device):
+                _lib.check(lib.b2n_fft_twiddles(int(n), t.data_ptr(), current_stream_ptr(device)), "b2n_fft_twiddles")
+            _TWIDDLES[key] = t
+        tabs.append(t)
+    ptrs = (ctypes.c_void_p * len(tabs))(*[t.data_ptr() for t in tabs])
+    return tabs, ptrs
+
+
 def _fft_work(im_size, grid_size, B, C, device) -> Optional[Tensor]:
     nbytes = ctypes.c_size_t(0)
     _lib.check(_lib.load().b2n_fft_work_bytes(len(im_size), _lib.i64_array(im_size), _lib.i64_array(grid_size), B, C,
@@ -197,12 +217,13 @@ def fused_fft_forward(image: Tensor, grid_size: Sequence[int], smaps: Optional[T
     if scaling_coef is not None:
         scaling_coef = scaling_coef.contiguous()
     work = _fft_work(im_size, grid_size, B, C, image.device)
+    _tabs, tw = _twiddles(grid_size, image.device)
     with torch.cuda.device(image.device):
         _lib.check(
             _lib.load().b2n_fft_forward_fused(
                 len(im_size), _lib.i64_array(im_size), _lib.i64_array(grid_size), B, C, image.data_ptr(), Ci,
                 smaps.data_ptr() if smaps is not None else None, Bs,
-                scaling_coef.data_ptr() if scaling_coef is not None else None, float(scale), out.data_ptr(),
+                scaling_coef.data_ptr() if scaling_coef is not None else None, float(scale), tw, out.data_ptr(),
                 work.data_ptr() if work is not None else None, current_stream_ptr(image.device)),
             "b2n_fft_forward_fused",
         )
@@ -234,13 +255,14 @@ def fused_fft_adjoint(grid: Tensor, im_size: Sequence[int], smaps: Optional[Tens
         kernel = kernel.contiguous()
         kb = kernel.shape[0] if kernel.ndim > len(grid_size) else 1
     work = _fft_work(im_size, grid_size, B, C, grid.device)
+    _tabs, tw = _twiddles(grid_size, grid.device)
     with torch.cuda.device(grid.device):
         _lib.check(
             _lib.load().b2n_fft_adjoint_fused(
                 len(im_size), _lib.i64_array(im_size), _lib.i64_array(grid_size), B, C, grid.data_ptr(),
                 kernel.data_ptr() if kernel is not None else None, kb,
                 smaps.data_ptr() if smaps is not None else None, Bs,
-                scaling_coef.data_ptr() if scaling_coef is not None else None, float(scale), out.data_ptr(),
+                scaling_coef.data_ptr() if scaling_coef is not None else None, float(scale), tw, out.data_ptr(),
                 work.data_ptr() if work is not None else None, current_stream_ptr(grid.device)),
             "b2n_fft_adjoint_fused",
         )

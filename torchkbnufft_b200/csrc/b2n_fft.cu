@@ -27,7 +27,9 @@
 namespace b2n {
 
 constexpr int kFftThreads = 256;
+constexpr int kColThreads = 512;  // column pass: 64 threads per column, radices <= 8 (64 registers per thread)
 constexpr int kColsPerCta = 8;
+constexpr int kRowsPerCta = 4;
 constexpr int kFftMaxN = 8192;
 
 B2N_HD int fft_pad(int i) { return i + (i >> 3); }  // 1 slot of padding per 8: stride-R stores stay conflict-free
@@ -36,127 +38,161 @@ struct FftStages {
   int n, n_stages, radix[kFftMaxStages];
 };
 
-enum RowMode { ROW_PLAIN = 0, ROW_FWD_FIRST = 1, ROW_ADJ_LAST = 2 };
+enum RowMode { ROW_PLAIN = 0, ROW_FWD_FIRST = 1 };
 
 struct RowArgs {
   FftStages st;
   int n_in, n_out;       // nonzero inputs / kept outputs per line
-  int L;                 // lines per CTA
-  int64_t lines;         // lines (ROW_ADJ_LAST: (batch, image row) pairs)
+  int64_t lines;         // number of lines
   int64_t rows_per_img;  // image rows per (batch, coil) = prod of the slower image dims
   int C, Ci, Bs;         // coils, image coils (1 or C), smaps batch (1 or B)
-  const float2 *in;      // ROW_PLAIN / ROW_ADJ_LAST: [..][n_in]
-  float2 *out;           // [..][n_out]
-  const float2 *image, *smaps, *scaling;
+  const float2 *in;      // ROW_PLAIN: [lines][n_in]
+  float2 *out;           // [lines][n_out]
+  const float2 *image, *smaps, *scaling;  // ROW_FWD_FIRST operands
+  const float2 *tw;      // twiddle table exp(-2 pi i t / n), t < n (b2n_fft_twiddles)
   float scale;
 };
 
-// twiddle table exp(-2 pi i t / n), built once per CTA in double precision
-B2N_D void build_twiddles(float2 *tw, int n) {
-  for (int t = threadIdx.x; t < n; t += blockDim.x) {
-    double s, c;
-    sincospi(-2.0 * (double)t / (double)n, &s, &c);
-    tw[t] = f2((float)c, (float)s);
+// One Stockham stage over this CTA's lines.  LOADF(line, i) / STOREF(line, i, v) access the
+// stage input / output (global memory in the first / last stage, shared memory otherwise).
+// Thread layout: `lanes_per_line` consecutive threads share a line and stride over its items,
+// so no per-item division is needed.
+template <int R, bool INV, typename LoadF, typename StoreF>
+B2N_D void fft_stage_lines(int n, int Ns, const float2 *tw, int line, int j_begin, int j_step, bool line_on,
+                           LoadF loadf, StoreF storef) {
+  const int per_line = n / R;
+  const int tmul = n / (Ns * R);
+  const bool pow2 = (Ns & (Ns - 1)) == 0;
+  if (!line_on) return;
+  for (int j = j_begin; j < per_line; j += j_step) {
+    const int k = pow2 ? (j & (Ns - 1)) : (j % Ns);
+    float2 v[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) v[r] = loadf(line, j + r * per_line);
+    if (Ns > 1) {
+      const int tstep = k * tmul;
+#pragma unroll
+      for (int r = 1; r < R; ++r) v[r] = cmul2(v[r], twid<INV>(tw[r * tstep]));
+    }
+    Dft<R, INV>::run(v, tw, n);
+    const int j0 = (j - k) * R + k;
+#pragma unroll
+    for (int r = 0; r < R; ++r) storef(line, j0 + r * Ns, v[r]);
   }
 }
 
-template <bool INV, int MODE>
-__global__ void __launch_bounds__(kFftThreads) k_fft_rows(RowArgs a) {
-  extern __shared__ __align__(16) float2 fsm[];
-  const int n = a.st.n, NP = fft_pad(n) + 1;
-  float2 *tw = fsm;                 // [n]
-  float2 *bufA = tw + n;            // [L][NP]
-  float2 *bufB = bufA + a.L * NP;   // [L][NP]
-  float2 *acc = bufB + a.L * NP;    // ROW_ADJ_LAST: [L][n_out] coil-sum accumulators
-  build_twiddles(tw, n);
-  const int64_t line0 = (int64_t)blockIdx.x * a.L;
-  const int nl = (int)min((int64_t)a.L, a.lines - line0);
-  const int n_coil_iter = MODE == ROW_ADJ_LAST ? a.C : 1;
-  if (MODE == ROW_ADJ_LAST)
-    for (int e = threadIdx.x; e < a.L * a.n_out; e += kFftThreads) acc[e] = f2(0.f, 0.f);
-  __syncthreads();
+#define B2N_FFT_RADIX_SWITCH(R_, CALL)          \
+  switch (R_) {                                 \
+    case 16: { constexpr int RR = 16; CALL; } break; \
+    case 8: { constexpr int RR = 8; CALL; } break;   \
+    case 4: { constexpr int RR = 4; CALL; } break;   \
+    case 2: { constexpr int RR = 2; CALL; } break;   \
+    case 3: { constexpr int RR = 3; CALL; } break;   \
+    case 5: { constexpr int RR = 5; CALL; } break;   \
+    case 7: { constexpr int RR = 7; CALL; } break;   \
+    case 11: { constexpr int RR = 11; CALL; } break; \
+    default: { constexpr int RR = 13; CALL; } break; \
+  }
 
-  for (int coil = 0; coil < n_coil_iter; ++coil) {
-    // global accessors of this CTA's lines
-    auto gload = [&](int line, int i) -> float2 {
-      if (i >= a.n_in) return f2(0.f, 0.f);  // zero padding is never read
-      const int64_t l = line0 + line;
+// column pass: radices <= 8 only (its factorisation never contains 16), so that the 64-register
+// budget of 512-thread CTAs is not blown by an unused radix-16 code path
+#define B2N_FFT_RADIX_SWITCH_COLS(R_, CALL)     \
+  switch (R_) {                                 \
+    case 8: { constexpr int RR = 8; CALL; } break;   \
+    case 4: { constexpr int RR = 4; CALL; } break;   \
+    case 2: { constexpr int RR = 2; CALL; } break;   \
+    case 3: { constexpr int RR = 3; CALL; } break;   \
+    case 5: { constexpr int RR = 5; CALL; } break;   \
+    case 7: { constexpr int RR = 7; CALL; } break;   \
+    case 11: { constexpr int RR = 11; CALL; } break; \
+    default: { constexpr int RR = 13; CALL; } break; \
+  }
+
+// -----------------------------------------------------------------------------------------
+// row pass: kRowsPerCta contiguous lines per CTA, 64 threads per line
+// -----------------------------------------------------------------------------------------
+template <bool INV, int MODE>
+__global__ void __launch_bounds__(kFftThreads, 3) k_fft_rows(RowArgs a) {
+  extern __shared__ __align__(16) float2 fsm[];
+  constexpr int L = kRowsPerCta, TPL = kFftThreads / L;
+  const int n = a.st.n, NP = fft_pad(n) + 1;
+  float2 *tw = fsm;             // [n]
+  float2 *bufA = tw + n;        // [L][NP]
+  float2 *bufB = bufA + L * NP; // [L][NP]
+  __shared__ const float2 *s_in[L], *s_sm[L], *s_sc[L];
+  __shared__ float2 *s_out[L];
+  for (int t = threadIdx.x; t < n; t += kFftThreads) tw[t] = a.tw[t];
+  const int64_t line0 = (int64_t)blockIdx.x * L;
+  if (threadIdx.x < L) {
+    const int64_t l = line0 + threadIdx.x;
+    if (l < a.lines) {
       if (MODE == ROW_FWD_FIRST) {
         const int64_t bc = l / a.rows_per_img, row = l - bc * a.rows_per_img;
         const int64_t b = bc / a.C, c = bc - b * a.C;
-        const int64_t pix = row * a.n_in + i;
-        float2 v = a.image[((b * a.Ci + (a.Ci == 1 ? 0 : c)) * a.rows_per_img) * a.n_in + pix];
-        if (a.smaps) v = cmul2(v, a.smaps[(((a.Bs == 1 ? 0 : b) * a.C + c) * a.rows_per_img) * a.n_in + pix]);
-        if (a.scaling) v = cmul2(v, a.scaling[pix]);
-        return f2(v.x * a.scale, v.y * a.scale);
-      } else if (MODE == ROW_ADJ_LAST) {
-        const int64_t b = l / a.rows_per_img, row = l - b * a.rows_per_img;
-        return a.in[(((b * a.C + coil) * a.rows_per_img) + row) * a.n_in + i];
+        s_in[threadIdx.x] = a.image + ((b * a.Ci + (a.Ci == 1 ? 0 : c)) * a.rows_per_img + row) * a.n_in;
+        s_sm[threadIdx.x] = a.smaps ? a.smaps + (((a.Bs == 1 ? 0 : b) * a.C + c) * a.rows_per_img + row) * a.n_in : nullptr;
+        s_sc[threadIdx.x] = a.scaling ? a.scaling + row * a.n_in : nullptr;
       } else {
-        return a.in[l * a.n_in + i];
+        s_in[threadIdx.x] = a.in + l * a.n_in;
+        s_sm[threadIdx.x] = nullptr;
+        s_sc[threadIdx.x] = a.scaling ? a.scaling + (l % a.rows_per_img) * a.n_out : nullptr;
       }
-    };
-    auto gstore = [&](int line, int i, float2 v) {
-      if (i >= a.n_out) return;  // cropped outputs are never written
-      const int64_t l = line0 + line;
-      if (MODE == ROW_ADJ_LAST) {
-        const int64_t b = l / a.rows_per_img, row = l - b * a.rows_per_img;
-        const int64_t pix = row * a.n_out + i;
-        if (a.smaps) {
-          const float2 s = a.smaps[(((a.Bs == 1 ? 0 : b) * a.C + coil) * a.rows_per_img) * a.n_out + pix];
-          v = cmul2(v, f2(s.x, -s.y));
-        }
-        float2 &t = acc[line * a.n_out + i];  // one owner thread per element: no race
-        t = cadd(t, v);
-      } else if (MODE == ROW_PLAIN && a.scaling) {
-        const int64_t row = l % a.rows_per_img;
-        const float2 s = a.scaling[row * a.n_out + i];
-        v = cmul2(v, f2(s.x, -s.y));
-        a.out[l * a.n_out + i] = f2(v.x * a.scale, v.y * a.scale);
-      } else if (MODE == ROW_FWD_FIRST) {
-        a.out[l * a.n_out + i] = v;  // scale was applied with the apodisation at load time
-      } else {
-        a.out[l * a.n_out + i] = f2(v.x * a.scale, v.y * a.scale);
-      }
-    };
-
-    if (a.st.n_stages == 0) {  // n == 1
-      for (int line = threadIdx.x; line < nl; line += kFftThreads) gstore(line, 0, gload(line, 0));
-    }
-    float2 *src = bufA, *dst = bufB;
-    int Ns = 1;
-    for (int s = 0; s < a.st.n_stages; ++s) {
-      const int R = a.st.radix[s], per_line = n / R;
-      const bool first = s == 0, last = s == a.st.n_stages - 1;
-      for (int it = threadIdx.x; it < nl * per_line; it += kFftThreads) {
-        const int line = it / per_line, j = it - line * per_line;
-        auto load = [&](int i) -> float2 { return first ? gload(line, i) : src[line * NP + fft_pad(i)]; };
-        auto store = [&](int i, float2 v) {
-          if (last) gstore(line, i, v);
-          else dst[line * NP + fft_pad(i)] = v;
-        };
-        fft_stage_item_any<INV>(R, n, Ns, j, tw, load, store);
-      }
-      __syncthreads();
-      float2 *t = src;
-      src = dst;
-      dst = t;
-      Ns *= R;
+      s_out[threadIdx.x] = a.out + l * a.n_out;
     }
   }
-  if (MODE == ROW_ADJ_LAST) {
-    // apodisation and store of the coil-combined rows
-    for (int e = threadIdx.x; e < nl * a.n_out; e += kFftThreads) {
-      const int line = e / a.n_out, i = e - line * a.n_out;
-      const int64_t l = line0 + line;
-      const int64_t row = l % a.rows_per_img;
-      float2 v = acc[e];
-      if (a.scaling) {
-        const float2 s = a.scaling[row * a.n_out + i];
-        v = cmul2(v, f2(s.x, -s.y));
-      }
-      a.out[l * a.n_out + i] = f2(v.x * a.scale, v.y * a.scale);
+  __syncthreads();
+  const int line = threadIdx.x / TPL, jb = threadIdx.x - line * TPL;
+  const bool line_on = line0 + line < a.lines;
+  const float2 *pin = line_on ? s_in[line] : nullptr, *psm = line_on ? s_sm[line] : nullptr,
+               *psc = line_on ? s_sc[line] : nullptr;
+  float2 *pout = line_on ? s_out[line] : nullptr;
+  const int n_in = a.n_in, n_out = a.n_out;
+  const float scale = a.scale;
+
+  auto gload = [&](int, int i) -> float2 {
+    if (i >= n_in) return f2(0.f, 0.f);  // zero padding is never read
+    float2 v = pin[i];
+    if (MODE == ROW_FWD_FIRST) {
+      if (psm) v = cmul2(v, psm[i]);
+      if (psc) v = cmul2(v, psc[i]);
+      v = f2(v.x * scale, v.y * scale);
     }
+    return v;
+  };
+  auto gstore = [&](int, int i, float2 v) {
+    if (i >= n_out) return;  // cropped outputs are never written
+    if (MODE == ROW_PLAIN) {
+      if (psc) v = cmul2(v, f2(psc[i].x, -psc[i].y));
+      v = f2(v.x * scale, v.y * scale);
+    }
+    pout[i] = v;
+  };
+
+  if (a.st.n_stages == 0) {  // n == 1
+    if (line_on && jb == 0) gstore(line, 0, gload(line, 0));
+    return;
+  }
+  float2 *src = bufA, *dst = bufB;
+  int Ns = 1;
+  for (int s = 0; s < a.st.n_stages; ++s) {
+    const int R = a.st.radix[s];
+    const bool first = s == 0, last = s == a.st.n_stages - 1;
+    auto sload = [&](int ln, int i) -> float2 { return src[ln * NP + fft_pad(i)]; };
+    auto sstore = [&](int ln, int i, float2 v) { dst[ln * NP + fft_pad(i)] = v; };
+    if (first && last) {
+      B2N_FFT_RADIX_SWITCH(R, (fft_stage_lines<RR, INV>(n, Ns, tw, line, jb, TPL, line_on, gload, gstore)))
+    } else if (first) {
+      B2N_FFT_RADIX_SWITCH(R, (fft_stage_lines<RR, INV>(n, Ns, tw, line, jb, TPL, line_on, gload, sstore)))
+    } else if (last) {
+      B2N_FFT_RADIX_SWITCH(R, (fft_stage_lines<RR, INV>(n, Ns, tw, line, jb, TPL, line_on, sload, gstore)))
+    } else {
+      B2N_FFT_RADIX_SWITCH(R, (fft_stage_lines<RR, INV>(n, Ns, tw, line, jb, TPL, line_on, sload, sstore)))
+    }
+    __syncthreads();
+    float2 *t = src;
+    src = dst;
+    dst = t;
+    Ns *= R;
   }
 }
 
@@ -168,53 +204,62 @@ struct ColArgs {
   float2 *out;       // [A][n_out][X]
   const float2 *mul; // optional [mul_batch][n][X] factor applied to the inputs (Toeplitz kernel)
   int64_t a_per_mul; // outer indices per mul batch entry (0: single kernel)
+  const float2 *tw;  // twiddle table of length n
   float scale;
 };
 
+// -----------------------------------------------------------------------------------------
+// column pass: 8 adjacent columns per CTA (64-byte global segments), 32 threads per column
+// -----------------------------------------------------------------------------------------
 template <bool INV>
-__global__ void __launch_bounds__(kFftThreads) k_fft_cols(ColArgs a) {
+__global__ void __launch_bounds__(kColThreads, 2) k_fft_cols(ColArgs a) {
   extern __shared__ __align__(16) float2 fsm[];
-  constexpr int LX = kColsPerCta;
+  constexpr int LX = kColsPerCta, TPL = kColThreads / LX;
   const int n = a.st.n, NP = fft_pad(n) + 1;
-  float2 *tw = fsm;            // [n]
-  float2 *bufA = tw + n;       // [NP][LX]
+  float2 *tw = fsm;          // [n]
+  float2 *bufA = tw + n;     // [NP][LX]
   float2 *bufB = bufA + NP * LX;
-  build_twiddles(tw, n);
+  for (int t = threadIdx.x; t < n; t += kColThreads) tw[t] = a.tw[t];
   const int64_t xblocks = (a.X + LX - 1) / LX;
   const int64_t oa = blockIdx.x / xblocks;
   const int64_t x0 = (blockIdx.x - oa * xblocks) * LX;
-  const float2 *in = a.in + oa * a.n_in * a.X + x0;
-  float2 *out = a.out + oa * a.n_out * a.X + x0;
-  const float2 *mul = a.mul ? a.mul + (a.a_per_mul ? (oa / a.a_per_mul) * (int64_t)n * a.X : 0) + x0 : nullptr;
-  const int nx = (int)min((int64_t)LX, a.X - x0);
+  const int l = threadIdx.x & (LX - 1), jb = threadIdx.x / LX;  // column index fastest: 64-byte global segments
+  const bool col_on = x0 + l < a.X;
+  const int X = (int)a.X, n_in = a.n_in, n_out = a.n_out;
+  const float2 *in = a.in + oa * a.n_in * a.X + x0 + l;
+  float2 *out = a.out + oa * a.n_out * a.X + x0 + l;
+  const float2 *mul = a.mul ? a.mul + (a.a_per_mul ? (oa / a.a_per_mul) * (int64_t)n * a.X : 0) + x0 + l : nullptr;
+  const float scale = a.scale;
   __syncthreads();
 
-  auto gload = [&](int l, int i) -> float2 {
-    if (i >= a.n_in || l >= nx) return f2(0.f, 0.f);
-    float2 v = in[(int64_t)i * a.X + l];
-    if (mul) v = cmul2(v, mul[(int64_t)i * a.X + l]);
+  auto gload = [&](int, int i) -> float2 {
+    if (i >= n_in) return f2(0.f, 0.f);
+    float2 v = in[i * X];
+    if (mul) v = cmul2(v, mul[i * X]);
     return v;
   };
-  auto gstore = [&](int l, int i, float2 v) {
-    if (i < a.n_out && l < nx) out[(int64_t)i * a.X + l] = f2(v.x * a.scale, v.y * a.scale);
+  auto gstore = [&](int, int i, float2 v) {
+    if (i < n_out) out[i * X] = f2(v.x * scale, v.y * scale);
   };
   if (a.st.n_stages == 0) {
-    for (int l = threadIdx.x; l < nx; l += kFftThreads) gstore(l, 0, gload(l, 0));
+    if (col_on && jb == 0) gstore(l, 0, gload(l, 0));
     return;
   }
   float2 *src = bufA, *dst = bufB;
   int Ns = 1;
   for (int s = 0; s < a.st.n_stages; ++s) {
-    const int R = a.st.radix[s], per_line = n / R;
+    const int R = a.st.radix[s];
     const bool first = s == 0, last = s == a.st.n_stages - 1;
-    for (int it = threadIdx.x; it < LX * per_line; it += kFftThreads) {
-      const int j = it / LX, l = it - j * LX;  // column index fastest: 64-byte global segments
-      auto load = [&](int i) -> float2 { return first ? gload(l, i) : src[fft_pad(i) * LX + l]; };
-      auto store = [&](int i, float2 v) {
-        if (last) gstore(l, i, v);
-        else dst[fft_pad(i) * LX + l] = v;
-      };
-      fft_stage_item_any<INV>(R, n, Ns, j, tw, load, store);
+    auto sload = [&](int ln, int i) -> float2 { return src[fft_pad(i) * LX + ln]; };
+    auto sstore = [&](int ln, int i, float2 v) { dst[fft_pad(i) * LX + ln] = v; };
+    if (first && last) {
+      B2N_FFT_RADIX_SWITCH_COLS(R, (fft_stage_lines<RR, INV>(n, Ns, tw, l, jb, TPL, col_on, gload, gstore)))
+    } else if (first) {
+      B2N_FFT_RADIX_SWITCH_COLS(R, (fft_stage_lines<RR, INV>(n, Ns, tw, l, jb, TPL, col_on, gload, sstore)))
+    } else if (last) {
+      B2N_FFT_RADIX_SWITCH_COLS(R, (fft_stage_lines<RR, INV>(n, Ns, tw, l, jb, TPL, col_on, sload, gstore)))
+    } else {
+      B2N_FFT_RADIX_SWITCH_COLS(R, (fft_stage_lines<RR, INV>(n, Ns, tw, l, jb, TPL, col_on, sload, sstore)))
     }
     __syncthreads();
     float2 *t = src;
@@ -224,26 +269,33 @@ __global__ void __launch_bounds__(kFftThreads) k_fft_cols(ColArgs a) {
   }
 }
 
+// twiddle table exp(-2 pi i t / n) in double precision, rounded once
+__global__ void k_fft_twiddles(float2 *tw, int n) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n) {
+    double s, c;
+    sincospi(-2.0 * (double)t / (double)n, &s, &c);
+    tw[t] = f2((float)c, (float)s);
+  }
+}
+
 // ---- host side ------------------------------------------------------------------------------
-static bool make_stages(int64_t n, FftStages *st) {
+static bool make_stages(int64_t n, FftStages *st, int max_pow2_bits = 4) {
   FftPlan p;
-  if (n < 1 || n > kFftMaxN || !fft_factorize((int)n, &p)) return false;
+  if (n < 1 || n > kFftMaxN || !fft_factorize((int)n, &p, max_pow2_bits)) return false;
   st->n = p.n;
   st->n_stages = p.n_stages;
   for (int i = 0; i < p.n_stages; ++i) st->radix[i] = p.radix[i];
   return true;
 }
 
-static int rows_lines_per_cta(int n) { return n <= 1024 ? 4 : (n <= 2048 ? 2 : 1); }
-
 template <bool INV, int MODE> static int launch_rows(RowArgs &a, cudaStream_t st) {
   if (a.lines <= 0) return 0;
-  a.L = rows_lines_per_cta(a.st.n);
   const int NP = fft_pad(a.st.n) + 1;
-  size_t smem = sizeof(float2) * ((size_t)a.st.n + 2 * (size_t)a.L * NP + (MODE == ROW_ADJ_LAST ? (size_t)a.L * a.n_out : 0));
+  const size_t smem = sizeof(float2) * ((size_t)a.st.n + 2 * (size_t)kRowsPerCta * NP);
   auto kern = k_fft_rows<INV, MODE>;
   B2N_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<(unsigned)ceil_div(a.lines, a.L), kFftThreads, smem, st>>>(a);
+  kern<<<(unsigned)ceil_div(a.lines, kRowsPerCta), kFftThreads, smem, st>>>(a);
   B2N_LAUNCH_OK("k_fft_rows");
   return 0;
 }
@@ -251,11 +303,11 @@ template <bool INV, int MODE> static int launch_rows(RowArgs &a, cudaStream_t st
 template <bool INV> static int launch_cols(ColArgs &a, cudaStream_t st) {
   if (a.A <= 0 || a.X <= 0) return 0;
   const int NP = fft_pad(a.st.n) + 1;
-  size_t smem = sizeof(float2) * ((size_t)a.st.n + 2 * (size_t)NP * kColsPerCta);
+  const size_t smem = sizeof(float2) * ((size_t)a.st.n + 2 * (size_t)NP * kColsPerCta);
   auto kern = k_fft_cols<INV>;
   B2N_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int64_t blocks = a.A * ceil_div(a.X, kColsPerCta);
-  kern<<<(unsigned)blocks, kFftThreads, smem, st>>>(a);
+  kern<<<(unsigned)blocks, kColThreads, smem, st>>>(a);
   B2N_LAUNCH_OK("k_fft_cols");
   return 0;
 }
@@ -264,11 +316,13 @@ struct FusedGeom {
   int ndim;
   int64_t N[3], K[3];  // image / grid sizes in dimension order (slowest first)
   int64_t B, C;
-  FftStages st[3];
+  FftStages st[3];      // row-pass factorisation (radices up to 16)
+  FftStages st_col[3];  // column-pass factorisation (radices up to 8: 64 registers per thread at 512 threads)
+  const float2 *tw[3];
 };
 
 static int make_fused_geom(int ndim, const int64_t *im_size, const int64_t *grid_size, int64_t B, int64_t C,
-                           FusedGeom *g) {
+                           const void *const *twiddle_dev, FusedGeom *g) {
   if (ndim < 1 || ndim > 3 || !im_size || !grid_size) return fail_arg(B2N_E_ARG, "bad ndim/im_size/grid_size");
   if (B < 1 || C < 1) return fail_arg(B2N_E_ARG, "n_batch=%lld n_coils=%lld", (long long)B, (long long)C);
   g->ndim = ndim;
@@ -278,32 +332,43 @@ static int make_fused_geom(int ndim, const int64_t *im_size, const int64_t *grid
     if (im_size[d] < 1 || grid_size[d] < im_size[d]) return fail_arg(B2N_E_ARG, "grid_size[%d] < im_size[%d]", d, d);
     g->N[d] = im_size[d];
     g->K[d] = grid_size[d];
-    if (!make_stages(grid_size[d], &g->st[d]))
+    if (!make_stages(grid_size[d], &g->st[d]) || !make_stages(grid_size[d], &g->st_col[d], 3))
       return fail_arg(B2N_E_UNSUPPORTED, "FFT length %lld is not supported (prime factor > 13 or > %d)",
                       (long long)grid_size[d], kFftMaxN);
+    if (twiddle_dev) {
+      if (!twiddle_dev[d]) return fail_arg(B2N_E_ARG, "twiddle_dev[%d] is NULL", d);
+      g->tw[d] = (const float2 *)twiddle_dev[d];
+    }
   }
+  if (B * C * grid_size[0] * (ndim > 1 ? grid_size[1] : 1) * (ndim > 2 ? grid_size[2] : 1) >= ((int64_t)1 << 31))
+    return fail_arg(B2N_E_RANGE, "grid too large for the 32-bit indexing of the fused FFT passes");
   return 0;
 }
 
-// intermediate buffers: after the row pass [B*C][N0..N_{d-2}][K_last]; 3-D adds [B*C][N0][K1][K2]
-static size_t fused_work_elems(const FusedGeom &g, size_t *t1_elems) {
-  size_t t1 = (size_t)g.B * g.C * g.K[g.ndim - 1];
-  for (int d = 0; d < g.ndim - 1; ++d) t1 *= g.N[d];
-  size_t t2 = g.ndim == 3 ? (size_t)g.B * g.C * g.N[0] * g.K[1] * g.K[2] : 0;
-  if (g.ndim == 1) t1 = 0;
-  if (t1_elems) *t1_elems = t1;
-  return t1 + t2;
+// scratch: T1 [B*C][N0..N_{d-2}][K_last] (ndim > 1), T2 [B*C][N0][K1][K2] (3-D), T3 [B*C][prod N] (adjoint
+// with smaps: cropped, un-combined image before the coil sum)
+static void fused_work_layout(const FusedGeom &g, size_t *t1, size_t *t2, size_t *t3) {
+  size_t e1 = (size_t)g.B * g.C * g.K[g.ndim - 1];
+  for (int d = 0; d < g.ndim - 1; ++d) e1 *= g.N[d];
+  if (g.ndim == 1) e1 = 0;
+  const size_t e2 = g.ndim == 3 ? (size_t)g.B * g.C * g.N[0] * g.K[1] * g.K[2] : 0;
+  size_t e3 = (size_t)g.B * g.C;
+  for (int d = 0; d < g.ndim; ++d) e3 *= g.N[d];
+  *t1 = e1;
+  *t2 = e2;
+  *t3 = e3;
 }
 
 static int fused_forward(const FusedGeom &g, const float2 *image, int64_t Ci, const float2 *smaps, int64_t Bs,
                          const float2 *scaling, float scale, float2 *grid, float2 *work, cudaStream_t st) {
   const int d = g.ndim;
-  size_t t1e;
-  fused_work_elems(g, &t1e);
+  size_t t1e, t2e, t3e;
+  fused_work_layout(g, &t1e, &t2e, &t3e);
   float2 *T1 = work, *T2 = work + t1e;
   RowArgs r;
   memset(&r, 0, sizeof(r));
   r.st = g.st[d - 1];
+  r.tw = g.tw[d - 1];
   r.n_in = (int)g.N[d - 1];
   r.n_out = (int)g.K[d - 1];
   r.rows_per_img = 1;
@@ -323,7 +388,8 @@ static int fused_forward(const FusedGeom &g, const float2 *image, int64_t Ci, co
   memset(&c, 0, sizeof(c));
   c.scale = 1.f;
   if (d == 2) {
-    c.st = g.st[0];
+    c.st = g.st_col[0];
+    c.tw = g.tw[0];
     c.n_in = (int)g.N[0];
     c.n_out = (int)g.K[0];
     c.A = g.B * g.C;
@@ -332,7 +398,8 @@ static int fused_forward(const FusedGeom &g, const float2 *image, int64_t Ci, co
     c.out = grid;
     return launch_cols<false>(c, st);
   }
-  c.st = g.st[1];  // 3-D: y pass on the N0 non-zero planes, then z pass
+  c.st = g.st_col[1];  // 3-D: y pass on the N0 non-zero planes, then z pass
+  c.tw = g.tw[1];
   c.n_in = (int)g.N[1];
   c.n_out = (int)g.K[1];
   c.A = g.B * g.C * g.N[0];
@@ -341,7 +408,8 @@ static int fused_forward(const FusedGeom &g, const float2 *image, int64_t Ci, co
   c.out = T2;
   rc = launch_cols<false>(c, st);
   if (rc) return rc;
-  c.st = g.st[0];
+  c.st = g.st_col[0];
+  c.tw = g.tw[0];
   c.n_in = (int)g.N[0];
   c.n_out = (int)g.K[0];
   c.A = g.B * g.C;
@@ -351,20 +419,25 @@ static int fused_forward(const FusedGeom &g, const float2 *image, int64_t Ci, co
   return launch_cols<false>(c, st);
 }
 
+int crop_apod_coilsum_c64(int ndim, const int64_t *im_size, const int64_t *grid_size, int64_t B, int64_t C,
+                          const void *grid, const void *smaps, int64_t Bs, const void *scaling, double scale,
+                          void *image, cudaStream_t st);  // b2n_fftops.cu
+
 // kernel (optional): Toeplitz factor multiplied into the loads of the first inverse pass
 static int fused_adjoint(const FusedGeom &g, const float2 *grid, const float2 *kernel, int64_t kernel_batch,
                          const float2 *smaps, int64_t Bs, const float2 *scaling, float scale, float2 *image,
                          float2 *work, cudaStream_t st) {
   const int d = g.ndim;
-  size_t t1e;
-  fused_work_elems(g, &t1e);
-  float2 *T1 = work, *T2 = work + t1e;
+  size_t t1e, t2e, t3e;
+  fused_work_layout(g, &t1e, &t2e, &t3e);
+  float2 *T1 = work, *T2 = work + t1e, *T3 = work + t1e + t2e;
   const float2 *rows_in = grid;
   ColArgs c;
   memset(&c, 0, sizeof(c));
   c.scale = 1.f;
   if (d == 3) {
-    c.st = g.st[0];
+    c.st = g.st_col[0];
+    c.tw = g.tw[0];
     c.n_in = (int)g.K[0];
     c.n_out = (int)g.N[0];
     c.A = g.B * g.C;
@@ -376,7 +449,8 @@ static int fused_adjoint(const FusedGeom &g, const float2 *grid, const float2 *k
     int rc = launch_cols<true>(c, st);
     if (rc) return rc;
     c.mul = nullptr;
-    c.st = g.st[1];
+    c.st = g.st_col[1];
+    c.tw = g.tw[1];
     c.n_in = (int)g.K[1];
     c.n_out = (int)g.N[1];
     c.A = g.B * g.C * g.N[0];
@@ -387,7 +461,8 @@ static int fused_adjoint(const FusedGeom &g, const float2 *grid, const float2 *k
     if (rc) return rc;
     rows_in = T1;
   } else if (d == 2) {
-    c.st = g.st[0];
+    c.st = g.st_col[0];
+    c.tw = g.tw[0];
     c.n_in = (int)g.K[0];
     c.n_out = (int)g.N[0];
     c.A = g.B * g.C;
@@ -405,23 +480,27 @@ static int fused_adjoint(const FusedGeom &g, const float2 *grid, const float2 *k
   RowArgs r;
   memset(&r, 0, sizeof(r));
   r.st = g.st[d - 1];
+  r.tw = g.tw[d - 1];
   r.n_in = (int)g.K[d - 1];
   r.n_out = (int)g.N[d - 1];
   r.rows_per_img = 1;
   for (int k = 0; k < d - 1; ++k) r.rows_per_img *= g.N[k];
-  r.C = (int)g.C;
-  r.Bs = (int)Bs;
-  r.in = rows_in;
-  r.out = image;
-  r.smaps = smaps;
-  r.scaling = scaling;
-  r.scale = scale;
-  if (smaps) {
-    r.lines = g.B * r.rows_per_img;
-    return launch_rows<true, ROW_ADJ_LAST>(r, st);
-  }
   r.lines = g.B * g.C * r.rows_per_img;
-  return launch_rows<true, ROW_PLAIN>(r, st);
+  r.C = (int)g.C;
+  r.in = rows_in;
+  if (!smaps) {  // no coil combination: crop * conj(scaling) * scale straight to the caller's image
+    r.out = image;
+    r.scaling = scaling;
+    r.scale = scale;
+    return launch_rows<true, ROW_PLAIN>(r, st);
+  }
+  // SENSE: cropped per-coil rows to scratch, then one pass multiplies conj(smaps) * conj(scaling)
+  // and sums the coils (every line of the row pass stays independent: full parallelism)
+  r.out = T3;
+  r.scale = 1.f;
+  int rc = launch_rows<true, ROW_PLAIN>(r, st);
+  if (rc) return rc;
+  return crop_apod_coilsum_c64(d, g.N, g.N, g.B, g.C, T3, smaps, Bs, scaling, scale, image, st);
 }
 
 }  // namespace b2n
@@ -433,22 +512,32 @@ extern "C" int b2n_fft_supported(int64_t n) {
   return make_stages(n, &st) ? 1 : 0;
 }
 
+extern "C" int b2n_fft_twiddles(int64_t n, void *twiddle_dev, void *stream) {
+  if (n < 1 || n > kFftMaxN || !twiddle_dev) return fail_arg(B2N_E_ARG, "bad twiddle request");
+  k_fft_twiddles<<<(unsigned)ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>((float2 *)twiddle_dev, (int)n);
+  B2N_LAUNCH_OK("k_fft_twiddles");
+  return 0;
+}
+
 extern "C" int b2n_fft_work_bytes(int ndim, const int64_t *im_size, const int64_t *grid_size, int64_t n_batch,
                                   int64_t n_coils, size_t *bytes) {
   FusedGeom g;
-  int rc = make_fused_geom(ndim, im_size, grid_size, n_batch, n_coils, &g);
+  int rc = make_fused_geom(ndim, im_size, grid_size, n_batch, n_coils, nullptr, &g);
   if (rc) return rc;
   if (!bytes) return fail_arg(B2N_E_ARG, "bytes is NULL");
-  *bytes = sizeof(float2) * fused_work_elems(g, nullptr);
+  size_t t1, t2, t3;
+  fused_work_layout(g, &t1, &t2, &t3);
+  *bytes = sizeof(float2) * (t1 + t2 + t3);
   return 0;
 }
 
 extern "C" int b2n_fft_forward_fused(int ndim, const int64_t *im_size, const int64_t *grid_size, int64_t n_batch,
                                      int64_t n_coils, const void *image_dev, int64_t image_coils,
                                      const void *smaps_dev, int64_t smaps_batch, const void *scaling_dev, double scale,
-                                     void *grid_dev, void *work_dev, void *stream) {
+                                     const void *const *twiddle_dev, void *grid_dev, void *work_dev, void *stream) {
   FusedGeom g;
-  int rc = make_fused_geom(ndim, im_size, grid_size, n_batch, n_coils, &g);
+  if (!twiddle_dev) return fail_arg(B2N_E_ARG, "twiddle_dev is NULL");
+  int rc = make_fused_geom(ndim, im_size, grid_size, n_batch, n_coils, twiddle_dev, &g);
   if (rc) return rc;
   if (!image_dev || !grid_dev || (ndim > 1 && !work_dev)) return fail_arg(B2N_E_ARG, "NULL image/grid/work");
   if (image_coils != 1 && image_coils != n_coils) return fail_arg(B2N_E_ARG, "image_coils must be 1 or n_coils");
@@ -461,12 +550,13 @@ extern "C" int b2n_fft_forward_fused(int ndim, const int64_t *im_size, const int
 extern "C" int b2n_fft_adjoint_fused(int ndim, const int64_t *im_size, const int64_t *grid_size, int64_t n_batch,
                                      int64_t n_coils, const void *grid_dev, const void *kernel_dev,
                                      int64_t kernel_batch, const void *smaps_dev, int64_t smaps_batch,
-                                     const void *scaling_dev, double scale, void *image_dev, void *work_dev,
-                                     void *stream) {
+                                     const void *scaling_dev, double scale, const void *const *twiddle_dev,
+                                     void *image_dev, void *work_dev, void *stream) {
   FusedGeom g;
-  int rc = make_fused_geom(ndim, im_size, grid_size, n_batch, n_coils, &g);
+  if (!twiddle_dev) return fail_arg(B2N_E_ARG, "twiddle_dev is NULL");
+  int rc = make_fused_geom(ndim, im_size, grid_size, n_batch, n_coils, twiddle_dev, &g);
   if (rc) return rc;
-  if (!image_dev || !grid_dev || (ndim > 1 && !work_dev)) return fail_arg(B2N_E_ARG, "NULL image/grid/work");
+  if (!image_dev || !grid_dev || !work_dev) return fail_arg(B2N_E_ARG, "NULL image/grid/work");
   if (smaps_dev && smaps_batch != 1 && smaps_batch != n_batch) return fail_arg(B2N_E_ARG, "smaps_batch must be 1 or n_batch");
   if (kernel_dev && kernel_batch != 1 && kernel_batch != n_batch) return fail_arg(B2N_E_ARG, "kernel_batch must be 1 or n_batch");
   return fused_adjoint(g, (const float2 *)grid_dev, (const float2 *)kernel_dev, kernel_dev ? kernel_batch : 1,

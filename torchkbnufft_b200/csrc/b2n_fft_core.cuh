@@ -25,13 +25,13 @@ struct FftPlan {
 
 // radices: powers of two in balanced chunks of <= 4 bits (largest first), then odd primes.
 // Returns false when n has a prime factor > 13 (caller falls back to cuFFT).
-static inline bool fft_factorize(int n, FftPlan *p) {
+static inline bool fft_factorize(int n, FftPlan *p, int max_pow2_bits = 4) {
   p->n = n;
   p->n_stages = 0;
   if (n < 1) return false;
   int e = 0;
   while (n % 2 == 0) { n /= 2; ++e; }
-  int chunks = (e + 3) / 4;
+  int chunks = (e + max_pow2_bits - 1) / max_pow2_bits;
   for (int i = 0; i < chunks; ++i) {
     const int bits = (e + (chunks - 1 - i)) / chunks;  // balanced split, larger chunks first
     p->radix[p->n_stages++] = 1 << bits;

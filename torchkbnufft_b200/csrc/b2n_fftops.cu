@@ -235,6 +235,16 @@ static int crop_t(const PadGeom &g, const void *grid, int layout, const void *sm
   return 0;
 }
 
+// complex64 coil-major entry used by the fused FFT path (b2n_fft.cu) for its final coil combination
+int crop_apod_coilsum_c64(int ndim, const int64_t *im_size, const int64_t *grid_size, int64_t B, int64_t C,
+                          const void *grid, const void *smaps, int64_t Bs, const void *scaling, double scale,
+                          void *image, cudaStream_t st) {
+  PadGeom g;
+  int rc = make_pad_geom(ndim, im_size, grid_size, B, C, C, smaps ? Bs : 1, &g);
+  if (rc) return rc;
+  return crop_t<float>(g, grid, B2N_COIL_MAJOR, smaps, scaling, scale, image, st);
+}
+
 }  // namespace b2n
 
 using namespace b2n;
