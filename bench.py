@@ -227,7 +227,10 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--breakdown", action="store_true", help="print per-stage device times to stderr")
     ap.add_argument("--opt", action="append", default=[], help="engine option id=value (A/B experiments)")
-    ap.add_argument("--fused-fft", action="store_true", help="A/B: own pruned FFT passes instead of cuFFT + element-wise kernels")
+    ap.add_argument("--fft", choices=["auto", "cufft", "own"], default="auto",
+                    help="FFT passes: auto (default; own compile-time planned passes when every grid length has a "
+                         "plan, else cuFFT), cufft (always cuFFT + element-wise kernels), own (own passes for any "
+                         "supported length)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -261,8 +264,7 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     if args.adjoint_mode:
         tkbn.set_adjoint_mode(args.adjoint_mode)
-    if args.fused_fft:
-        eng_fft.use_fused_fft = True
+    eng_fft.use_fused_fft = {"auto": "auto", "cufft": False, "own": True}[args.fft]
     for kv in args.opt:
         k, v = kv.split("=")
         _lib.check(_lib.load().b2n_set_option(int(k), int(v)), "b2n_set_option")

@@ -108,6 +108,8 @@ enum b2n_option {
   B2N_OPT_FWD_COIL_CHUNK = 2, /* tiled forward for C > 8: 0 (default) one 16-coil CTA per sub-problem, 1 persistent
                                  triple-buffered kernel (measured slower, kept for A/B), 8 two 8-coil CTAs */
   B2N_OPT_ADJ_COIL_CHUNK = 3, /* 0 (default): 16 coils per CTA in the tiled adjoint; 8: two 8-coil CTAs */
+  B2N_OPT_FAST_FFT = 4, /* 1 (default): fused FFT passes use the compile-time planned kernels for the lengths that
+                           have a plan (64, 128, 256, 320, 512, 640, 768, 1024); 0: run-time Stockham passes only */
   B2N_OPT_COUNT
 };
 B2N_API int b2n_set_option(int option, int value);
@@ -183,12 +185,14 @@ B2N_API int b2n_spectrum_mul(int dtype, void *spectrum_dev, const void *kernel_d
  *   forward = b2n_apod_pad + fftn(norm=None) in ndim passes,
  *   adjoint = ifftn(norm="forward") + b2n_crop_apod_coilsum (+ optional Toeplitz kernel
  *             multiply on the way in) in ndim passes.
- * b2n_fft_supported(n): 1 when length n factors into {2,3,5,7,11,13} and is <= 8192.
+ * b2n_fft_supported(n): 0 = not handled; 1 = length n factors into {2,3,5,7,11,13} and is <= 8192 (run-time
+ * Stockham passes); 2 = n also has a compile-time plan (register-resident passes, the fast path).
  * work_dev: device scratch of b2n_fft_work_bytes() bytes (intermediate, partially
  * transformed arrays); not needed for ndim == 1.
  * reference: fft_and_scale / ifft_and_scale / fft_filter, _nufft/fft.py:36-173. */
 B2N_API int b2n_fft_supported(int64_t n);
-/* Fill a caller buffer of n complex64 entries with exp(-2 pi i t / n) (computed in double). */
+/* Fill a caller buffer of 2*n complex64 entries: [0, n) = exp(-2 pi i t / n) (computed in double), [n, 2n) = the
+ * per-stage twiddle tables of the compile-time plan for length n (unused when n has none). */
 B2N_API int b2n_fft_twiddles(int64_t n, void *twiddle_dev, void *stream);
 B2N_API int b2n_fft_work_bytes(int ndim, const int64_t *im_size, const int64_t *grid_size, int64_t n_batch,
                                int64_t n_coils, size_t *bytes);

@@ -36,3 +36,63 @@ extern "C" int host_fft(int n, int inverse, const float *in, float *out, int *ra
   free(tw); free(x); free(y);
   return plan.n_stages;
 }
+
+// ---- compile-time planned passes (b2n_fft_fast.cuh): the kernel's phase sequence, one "thread"
+// at a time, with a plain array standing in for the shared exchange buffer ----------------------
+#include <vector>
+
+#include "../torchkbnufft_b200/csrc/b2n_fft_fast.cuh"
+
+template <class P, bool INV> static void run_fast(const float2 *a, const float2 *b, float2 *oa, float2 *ob) {
+  using namespace b2n::fast;
+  std::vector<float2> tws(P::N);
+  for (int e = 0; e < P::TW_COUNT; ++e) {
+    int r, k, period;
+    staged_twiddle_index<P>(e, &r, &k, &period);
+    const double ang = -2.0 * M_PI * (double)((long long)r * k % period) / (double)period;
+    tws[e].x = (float)cos(ang);
+    tws[e].y = (float)sin(ang);
+  }
+  std::vector<float4> sm(P::NP), regs((size_t)P::T * P::RMAX);
+  auto loadg = [&](int i) { return v4(a[i].x, a[i].y, b[i].x, b[i].y); };
+  auto storeg = [&](int i, float4 v) {
+    oa[i].x = v.x; oa[i].y = v.y; ob[i].x = v.z; ob[i].y = v.w;
+  };
+  for (int t = 0; t < P::I0; ++t) {
+    float4 v[P::RMAX];
+    for (int r = 0; r < P::R0; ++r) v[r] = loadg(t + r * P::I0);
+    dft<P::R0, INV>(v);
+    for (int r = 0; r < P::R0; ++r) sm[P::pad(t * P::R0 + r)] = v[r];
+  }
+  for (int t = 0; t < P::I1; ++t) {  // all loads before any store: the single-buffer hazard
+    float4 *v = &regs[(size_t)t * P::RMAX];
+    for (int r = 0; r < P::R1; ++r) v[r] = sm[P::pad(t + r * P::I1)];
+    stage_compute<P::R1, INV>(v, tws.data(), P::R0, t & (P::R0 - 1));
+  }
+  for (int t = 0; t < P::I1; ++t) {
+    float4 *v = &regs[(size_t)t * P::RMAX];
+    const int k1 = t & (P::R0 - 1), o1 = (t - k1) * P::R1 + k1;
+    for (int r = 0; r < P::R1; ++r) {
+      if (P::NS == 2) storeg(o1 + r * P::R0, v[r]);
+      else sm[P::pad(o1 + r * P::R0)] = v[r];
+    }
+  }
+  if constexpr (P::NS == 3) {
+    constexpr int Ns2 = P::R0 * P::R1;
+    for (int t = 0; t < P::I2; ++t) {
+      float4 v[P::RMAX];
+      for (int r = 0; r < P::R2; ++r) v[r] = sm[P::pad(t + r * P::I2)];
+      stage_compute<P::R2, INV>(v, tws.data() + P::TW2, Ns2, t);
+      for (int r = 0; r < P::R2; ++r) storeg(t + r * Ns2, v[r]);
+    }
+  }
+}
+
+// two lines in, two lines out; returns 0 when length n has no compile-time plan
+extern "C" int host_fft_fast(int n, int inverse, const float *a, const float *b, float *oa, float *ob) {
+  B2N_FAST_PLAN_SWITCH(n,
+                       (inverse ? run_fast<P, true>((const float2 *)a, (const float2 *)b, (float2 *)oa, (float2 *)ob)
+                                : run_fast<P, false>((const float2 *)a, (const float2 *)b, (float2 *)oa, (float2 *)ob)),
+                       return 0)
+  return 1;
+}

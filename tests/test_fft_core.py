@@ -51,3 +51,25 @@ def test_balanced_power_of_two_split(hostfft):
 @pytest.mark.parametrize("n", [17, 19, 34, 57, 23 * 8, 1021])
 def test_unsupported_sizes_are_rejected(n, hostfft):
     assert run(hostfft, np.ones(n, np.complex64), False)[0] == -1
+
+
+@pytest.mark.parametrize("n", [64, 128, 256, 320, 512, 640, 768, 1024])
+def test_compile_time_plans_match_numpy(n, hostfft):
+    """b2n_fft_fast.cuh: index maps, staged twiddles and the pair butterflies (incl. radix 10, 12, 16)."""
+    rng = np.random.default_rng(1000 + n)
+    a = (rng.standard_normal(n) + 1j * rng.standard_normal(n)).astype(np.complex64)
+    b = (rng.standard_normal(n) + 1j * rng.standard_normal(n)).astype(np.complex64)
+    for inverse in (False, True):
+        oa, ob = np.empty(n, np.complex64), np.empty(n, np.complex64)
+        p = lambda x: x.ctypes.data_as(ctypes.c_void_p)
+        assert hostfft.host_fft_fast(n, int(inverse), p(a), p(b), p(oa), p(ob)) == 1
+        for x, got in ((a, oa), (b, ob)):
+            want = np.fft.ifft(x.astype(np.complex128)) * n if inverse else np.fft.fft(x.astype(np.complex128))
+            err = np.linalg.norm(got - want) / np.linalg.norm(want)
+            assert err < 5e-7, (n, inverse, err)
+
+
+def test_lengths_without_a_plan_use_the_runtime_passes(hostfft):
+    z = np.zeros(96, np.complex64)
+    p = z.ctypes.data_as(ctypes.c_void_p)
+    assert hostfft.host_fft_fast(96, 0, p, p, p, p) == 0

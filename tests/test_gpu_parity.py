@@ -376,7 +376,11 @@ def test_tiled_kernels_match_generic_and_oracle(grid_size, B, C, batched):
 
 @pytest.mark.parametrize("N, K", [((24,), (40,)), ((19,), (64,)), ((16, 12), (32, 24)), ((13, 18), (26, 35)),
                                   ((320, 320), (640, 640)), ((33, 30), (70, 64)), ((8, 7, 6), (16, 14, 12)),
-                                  ((17, 19, 12), (36, 40, 24))])
+                                  ((17, 19, 12), (36, 40, 24)),
+                                  # lengths with a compile-time plan (b2n_fft_fast.cuh), mixed with run-time ones
+                                  ((300,), (512,)), ((129,), (256,)), ((33, 64), (64, 128)), ((160, 200), (320, 768)),
+                                  ((5, 500), (7, 1024)), ((64, 9), (128, 18)), ((31, 15), (64, 30)),
+                                  ((20, 33, 48), (64, 64, 128)), ((6, 128, 100), (12, 256, 320))])
 def test_fused_pruned_fft_matches_torch(N, K):
     """Own Stockham passes (pruned inputs / cropped outputs, fused apodisation, SENSE multiply,
     coil sum and Toeplitz kernel multiply) against torch.fft + plain torch ops, complex64."""
@@ -415,7 +419,29 @@ def test_fused_pruned_fft_matches_torch(N, K):
         want = torch.fft.ifftn(grid, dim=dims, norm="forward")[crop] * scal.conj()
         assert rel_l2(host(eng_fft.fused_fft_adjoint(grid, N, None, scal, 1.0)), host(want)) <= 2e-6
     assert not eng_fft.fused_fft_available(dt, (57,)) and not eng_fft.fused_fft_available(torch.complex128, K)
-    eng_fft.use_fused_fft = False
+    eng_fft.use_fused_fft = "auto"
+    assert eng_fft.fused_fft_available(dt, (640, 256)) and not eng_fft.fused_fft_available(dt, (640, 24))
+
+
+def test_fast_fft_plans_agree_with_runtime_passes():
+    """B2N_OPT_FAST_FFT on/off must give the same transform (different kernels, same maths)."""
+    torch.manual_seed(2)
+    dt = torch.complex64
+    lib = _lib.load()
+    N, K = (100, 320), (256, 640)
+    image = torch.randn((1, 1) + N, dtype=dt, device=DEV)
+    smaps = torch.randn((1, 5) + N, dtype=dt, device=DEV)
+    grid = torch.randn((1, 5) + K, dtype=dt, device=DEV)
+    res = {}
+    try:
+        for on in (1, 0):
+            lib.b2n_set_option(_lib.OPT_FAST_FFT, on)
+            assert lib.b2n_get_option(_lib.OPT_FAST_FFT) == on
+            res[on] = (host(eng_fft.fused_fft_forward(image, K, smaps, None, 1.0)),
+                       host(eng_fft.fused_fft_adjoint(grid, N, smaps, None, 1.0)))
+    finally:
+        lib.b2n_set_option(_lib.OPT_FAST_FFT, 1)
+    assert rel_l2(res[1][0], res[0][0]) <= 1e-6 and rel_l2(res[1][1], res[0][1]) <= 1e-6
 
 
 @pytest.mark.parametrize("grid_size", [(16, 16, 16), (24, 20, 28), (10, 12, 14), (13, 21, 9), (32, 8, 40)])

@@ -150,21 +150,24 @@ def ortho_scale(grid_size: Sequence[int], normalized: bool) -> float:
 # pruned, fused FFT passes (own Stockham kernels, complex64): see csrc/b2n_fft.cu
 # ---------------------------------------------------------------------------------------
 _FFT_SUPPORTED: dict = {}
-use_fused_fft = False  # A/B switch; off until the Stockham passes beat cuFFT + element-wise kernels (profiles/r01_e)
+# "auto" (default): own passes when every grid length has a compile-time plan (b2n_fft_fast.cuh; measured faster
+# than cuFFT + element-wise kernels, profiles/r01_g); True: whenever the lengths factor into primes <= 13 (the
+# run-time Stockham passes are slower than cuFFT, kept for A/B); False: always cuFFT.
+use_fused_fft = "auto"
 
 
 def fused_fft_available(dtype: torch.dtype, grid_size: Sequence[int]) -> bool:
-    """True when the engine's own FFT passes handle this transform (complex64, every grid
-    length a product of primes <= 13); otherwise callers use cuFFT around the fused
-    element-wise kernels."""
+    """True when the engine's own FFT passes are to be used for this transform (complex64 only);
+    otherwise callers use cuFFT around the fused element-wise kernels."""
     if not use_fused_fft or dtype != torch.complex64:
         return False
     lib = _lib.load()
+    need = 2 if use_fused_fft == "auto" else 1
     for n in grid_size:
         n = int(n)
         if n not in _FFT_SUPPORTED:
-            _FFT_SUPPORTED[n] = bool(lib.b2n_fft_supported(n))
-        if not _FFT_SUPPORTED[n]:
+            _FFT_SUPPORTED[n] = int(lib.b2n_fft_supported(n))  # 0 unsupported, 1 run-time passes, 2 compile-time plan
+        if _FFT_SUPPORTED[n] < need:
             return False
     return True
 
@@ -173,14 +176,15 @@ _TWIDDLES: dict = {}
 
 
 def _twiddles(grid_size, device):
-    """Per-(device, length) twiddle tables exp(-2 pi i t / n), built once on the device."""
+    """Per-(device, length) twiddle tables (2n entries: plain table + the staged tables of the
+    compile-time plan, see ``b2n_fft_twiddles``), built once on the device."""
     lib = _lib.load()
     tabs = []
     for n in grid_size:
         key = (device.index, int(n))
         t = _TWIDDLES.get(key)
         if t is None:
-            t = torch.empty(int(n), dtype=torch.complex64, device=device)
+            t = torch.zeros(2 * int(n), dtype=torch.complex64, device=device)
             with torch.cuda.device(device):
                 _lib.check(lib.b2n_fft_twiddles(int(n), t.data_ptr(), current_stream_ptr(device)), "b2n_fft_twiddles")
             _TWIDDLES[key] = t

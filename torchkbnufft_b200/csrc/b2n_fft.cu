@@ -23,6 +23,7 @@
 // Sizes with a prime factor > 13 are not handled (the Python layer then uses cuFFT).
 #include "b2n_common.cuh"
 #include "b2n_fft_core.cuh"
+#include "b2n_fft_fast.cuh"
 
 namespace b2n {
 
@@ -269,6 +270,134 @@ __global__ void __launch_bounds__(kColThreads, 2) k_fft_cols(ColArgs a) {
   }
 }
 
+// -----------------------------------------------------------------------------------------
+// fast passes: compile-time plans of b2n_fft_fast.cuh, two lines per thread
+// -----------------------------------------------------------------------------------------
+template <class P> struct FastCfg {
+  // row pass: LP line pairs per CTA (about 320 threads); column pass: PAIRS column pairs per CTA
+  static constexpr int LP = P::T >= 128 ? 2 : 320 / P::T;
+  static constexpr int ROW_THREADS = LP * P::T;
+  static constexpr int PAIRS = P::T >= 64 ? 4 : 256 / P::T;
+  static constexpr int COL_THREADS = PAIRS * P::T;
+  static constexpr int MINB = P::RMAX >= 16 ? 1 : 2;  // radix-16 butterflies on pairs want > 100 registers
+};
+
+B2N_D float2 row_operand(const float2 *in, const float2 *sm, const float2 *sc, int i, float scale) {
+  float2 v = in[i];
+  if (sm) v = cmul2(v, sm[i]);
+  if (sc) v = cmul2(v, sc[i]);
+  return f2(v.x * scale, v.y * scale);
+}
+
+template <class P, bool INV, int MODE>
+__global__ void __launch_bounds__(FastCfg<P>::ROW_THREADS, FastCfg<P>::MINB) k_fft_rows_fast(RowArgs a) {
+  extern __shared__ __align__(16) float4 fsm4[];
+  constexpr int LP = FastCfg<P>::LP;
+  const int lp = threadIdx.x / P::T, t = threadIdx.x - lp * P::T;
+  const int64_t lA = ((int64_t)blockIdx.x * LP + lp) * 2;
+  const bool onA = lA < a.lines, onB = lA + 1 < a.lines;
+  const float2 *inA = nullptr, *inB = nullptr, *smA = nullptr, *smB = nullptr, *scA = nullptr, *scB = nullptr;
+  float2 *outA = nullptr, *outB = nullptr;
+  auto setup = [&](int64_t l, const float2 *&in, const float2 *&sm, const float2 *&sc, float2 *&out) {
+    if (MODE == ROW_FWD_FIRST) {
+      const int64_t bc = l / a.rows_per_img, row = l - bc * a.rows_per_img;
+      const int64_t b = bc / a.C, c = bc - b * a.C;
+      in = a.image + ((b * a.Ci + (a.Ci == 1 ? 0 : c)) * a.rows_per_img + row) * a.n_in;
+      sm = a.smaps ? a.smaps + (((a.Bs == 1 ? 0 : b) * a.C + c) * a.rows_per_img + row) * a.n_in : nullptr;
+      sc = a.scaling ? a.scaling + row * a.n_in : nullptr;
+    } else {
+      in = a.in + l * a.n_in;
+      sc = a.scaling ? a.scaling + (l % a.rows_per_img) * a.n_out : nullptr;
+    }
+    out = a.out + l * a.n_out;
+  };
+  if (onA) setup(lA, inA, smA, scA, outA);
+  if (onB) setup(lA + 1, inB, smB, scB, outB);
+  const int n_in = a.n_in, n_out = a.n_out;
+  const float scale = a.scale;
+  auto loadg = [&](int i) -> float4 {
+    float4 v = fast::v4(0.f, 0.f, 0.f, 0.f);
+    if (i < n_in) {  // zero padding is never read
+      if (MODE == ROW_FWD_FIRST) {
+        if (onA) { const float2 x = row_operand(inA, smA, scA, i, scale); v.x = x.x; v.y = x.y; }
+        if (onB) { const float2 x = row_operand(inB, smB, scB, i, scale); v.z = x.x; v.w = x.y; }
+      } else {
+        if (onA) { const float2 x = inA[i]; v.x = x.x; v.y = x.y; }
+        if (onB) { const float2 x = inB[i]; v.z = x.x; v.w = x.y; }
+      }
+    }
+    return v;
+  };
+  auto storeg = [&](int i, float4 v) {
+    if (i >= n_out) return;  // cropped outputs are never written
+    if (MODE == ROW_PLAIN) {
+      if (onA) {
+        float2 x = f2(v.x, v.y);
+        if (scA) x = cmul2(x, f2(scA[i].x, -scA[i].y));
+        outA[i] = f2(x.x * scale, x.y * scale);
+      }
+      if (onB) {
+        float2 x = f2(v.z, v.w);
+        if (scB) x = cmul2(x, f2(scB[i].x, -scB[i].y));
+        outB[i] = f2(x.x * scale, x.y * scale);
+      }
+    } else {
+      if (onA) outA[i] = f2(v.x, v.y);
+      if (onB) outB[i] = f2(v.z, v.w);
+    }
+  };
+  fast::fft_line_pair<P, INV>(t, fsm4 + lp * P::NP, 1, a.tw + P::N, loadg, storeg);
+}
+
+template <class P, bool INV>
+__global__ void __launch_bounds__(FastCfg<P>::COL_THREADS, FastCfg<P>::MINB) k_fft_cols_fast(ColArgs a) {
+  extern __shared__ __align__(16) float4 fsm4[];
+  constexpr int PAIRS = FastCfg<P>::PAIRS;
+  const int p = threadIdx.x % PAIRS, t = threadIdx.x / PAIRS;  // pair index fastest: contiguous global segments
+  const int X = (int)a.X, X2 = X >> 1, n_in = a.n_in, n_out = a.n_out;
+  const int xblocks = (X + 2 * PAIRS - 1) / (2 * PAIRS);
+  const int64_t oa = blockIdx.x / xblocks;
+  const int x = ((int)(blockIdx.x - oa * xblocks) * PAIRS + p) * 2;
+  const bool on = x < X;
+  const float4 *in = reinterpret_cast<const float4 *>(a.in + oa * n_in * a.X + x);
+  float4 *out = reinterpret_cast<float4 *>(a.out + oa * n_out * a.X + x);
+  const float4 *mul =
+      a.mul ? reinterpret_cast<const float4 *>(a.mul + (a.a_per_mul ? (oa / a.a_per_mul) * (int64_t)P::N * a.X : 0) + x)
+            : nullptr;
+  const float scale = a.scale;
+  auto loadg = [&](int i) -> float4 {
+    if (!on || i >= n_in) return fast::v4(0.f, 0.f, 0.f, 0.f);
+    float4 v = in[i * X2];
+    if (mul) v = fast::vmul2(v, mul[i * X2]);
+    return v;
+  };
+  auto storeg = [&](int i, float4 v) {
+    if (on && i < n_out) out[i * X2] = fast::vscale(v, scale);
+  };
+  fast::fft_line_pair<P, INV>(t, fsm4 + p, PAIRS, a.tw + P::N, loadg, storeg);
+}
+
+// staged twiddle tables of the fast plans: entry e = exp(-2 pi i r k / period)
+__global__ void k_fft_twiddles_staged(float2 *tw, int R0, int R1, int R2) {
+  const int tw2 = (R1 - 1) * R0, count = tw2 + (R2 > 1 ? (R2 - 1) * R0 * R1 : 0);
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= count) return;
+  int r, k, period;
+  if (e < tw2) {
+    r = e / R0 + 1;
+    k = e % R0;
+    period = R0 * R1;
+  } else {
+    const int f = e - tw2;
+    r = f / (R0 * R1) + 1;
+    k = f % (R0 * R1);
+    period = R0 * R1 * R2;
+  }
+  double s, c;
+  sincospi(-2.0 * (double)((int64_t)r * k % period) / (double)period, &s, &c);
+  tw[e] = f2((float)c, (float)s);
+}
+
 // twiddle table exp(-2 pi i t / n) in double precision, rounded once
 __global__ void k_fft_twiddles(float2 *tw, int n) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -289,8 +418,36 @@ static bool make_stages(int64_t n, FftStages *st, int max_pow2_bits = 4) {
   return true;
 }
 
+int g_fast_fft = 1;  // B2N_OPT_FAST_FFT: compile-time planned passes where a plan exists
+
+template <class P, bool INV, int MODE> static int launch_rows_fast(RowArgs &a, cudaStream_t st) {
+  using Cfg = FastCfg<P>;
+  const size_t smem = sizeof(float4) * (size_t)Cfg::LP * P::NP;
+  auto kern = k_fft_rows_fast<P, INV, MODE>;
+  B2N_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<(unsigned)ceil_div(a.lines, 2 * Cfg::LP), Cfg::ROW_THREADS, smem, st>>>(a);
+  B2N_LAUNCH_OK("k_fft_rows_fast");
+  return 0;
+}
+
+template <class P, bool INV> static int launch_cols_fast(ColArgs &a, cudaStream_t st) {
+  using Cfg = FastCfg<P>;
+  const size_t smem = sizeof(float4) * (size_t)Cfg::PAIRS * P::NP;
+  auto kern = k_fft_cols_fast<P, INV>;
+  B2N_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int64_t blocks = a.A * ceil_div(a.X, 2 * Cfg::PAIRS);
+  kern<<<(unsigned)blocks, Cfg::COL_THREADS, smem, st>>>(a);
+  B2N_LAUNCH_OK("k_fft_cols_fast");
+  return 0;
+}
+
+static bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
 template <bool INV, int MODE> static int launch_rows(RowArgs &a, cudaStream_t st) {
   if (a.lines <= 0) return 0;
+  if (g_fast_fft) {
+    B2N_FAST_PLAN_SWITCH(a.st.n, return (launch_rows_fast<P, INV, MODE>(a, st)), (void)0)
+  }
   const int NP = fft_pad(a.st.n) + 1;
   const size_t smem = sizeof(float2) * ((size_t)a.st.n + 2 * (size_t)kRowsPerCta * NP);
   auto kern = k_fft_rows<INV, MODE>;
@@ -302,6 +459,9 @@ template <bool INV, int MODE> static int launch_rows(RowArgs &a, cudaStream_t st
 
 template <bool INV> static int launch_cols(ColArgs &a, cudaStream_t st) {
   if (a.A <= 0 || a.X <= 0) return 0;
+  if (g_fast_fft && a.X % 2 == 0 && aligned16(a.in) && aligned16(a.out) && aligned16(a.mul)) {
+    B2N_FAST_PLAN_SWITCH(a.st.n, return (launch_cols_fast<P, INV>(a, st)), (void)0)
+  }
   const int NP = fft_pad(a.st.n) + 1;
   const size_t smem = sizeof(float2) * ((size_t)a.st.n + 2 * (size_t)NP * kColsPerCta);
   auto kern = k_fft_cols<INV>;
@@ -509,13 +669,21 @@ using namespace b2n;
 
 extern "C" int b2n_fft_supported(int64_t n) {
   FftStages st;
-  return make_stages(n, &st) ? 1 : 0;
+  if (!make_stages(n, &st)) return 0;
+  B2N_FAST_PLAN_SWITCH((int)n, return 2, (void)0)
+  return 1;
 }
 
 extern "C" int b2n_fft_twiddles(int64_t n, void *twiddle_dev, void *stream) {
   if (n < 1 || n > kFftMaxN || !twiddle_dev) return fail_arg(B2N_E_ARG, "bad twiddle request");
   k_fft_twiddles<<<(unsigned)ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>((float2 *)twiddle_dev, (int)n);
   B2N_LAUNCH_OK("k_fft_twiddles");
+  // second half: per-stage tables of the compile-time plan for this length, when there is one
+  B2N_FAST_PLAN_SWITCH((int)n,
+                       (k_fft_twiddles_staged<<<(unsigned)ceil_div(P::TW_COUNT, 256), 256, 0, (cudaStream_t)stream>>>(
+                           (float2 *)twiddle_dev + n, P::R0, P::R1, P::R2)),
+                       (void)0)
+  B2N_LAUNCH_OK("k_fft_twiddles_staged");
   return 0;
 }
 

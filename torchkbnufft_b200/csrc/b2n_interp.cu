@@ -238,7 +238,8 @@ int64_t g_trace_capacity = 0;
 extern int g_adj_rowwarp;
 extern int g_fwd_chunk;
 extern int g_adj_chunk;
-static int g_options[B2N_OPT_COUNT] = {1, 0, 0, 0};
+extern int g_fast_fft;
+static int g_options[B2N_OPT_COUNT] = {1, 0, 0, 0, 1};
 
 }  // namespace b2n
 
@@ -250,6 +251,7 @@ extern "C" int b2n_set_option(int option, int value) {
   if (option == B2N_OPT_ADJ_ROW_OWNERSHIP) g_adj_rowwarp = value;
   if (option == B2N_OPT_FWD_COIL_CHUNK) g_fwd_chunk = value;
   if (option == B2N_OPT_ADJ_COIL_CHUNK) g_adj_chunk = value;
+  if (option == B2N_OPT_FAST_FFT) g_fast_fft = value;
   return 0;
 }
 
