@@ -43,7 +43,8 @@ extern "C" int host_fft(int n, int inverse, const float *in, float *out, int *ra
 
 #include "../torchkbnufft_b200/csrc/b2n_fft_fast.cuh"
 
-template <class P, bool INV> static void run_fast(const float2 *a, const float2 *b, float2 *oa, float2 *ob) {
+template <class P, bool INV, bool HIN = false>
+static void run_fast(const float2 *a, const float2 *b, float2 *oa, float2 *ob) {
   using namespace b2n::fast;
   std::vector<float2> tws(P::N);
   for (int e = 0; e < P::TW_COUNT; ++e) {
@@ -60,13 +61,18 @@ template <class P, bool INV> static void run_fast(const float2 *a, const float2 
   };
   for (int t = 0; t < P::I0; ++t) {
     float4 v[P::RMAX];
-    for (int r = 0; r < P::R0; ++r) v[r] = loadg(t + r * P::I0);
-    dft<P::R0, INV>(v);
-    for (int r = 0; r < P::R0; ++r) sm[P::pad(t * P::R0 + r)] = v[r];
+    if constexpr (HIN) {  // inputs beyond N/2 are zero padding: never read
+      for (int r = 0; r < P::R0 / 2; ++r) v[r] = loadg(t + r * P::I0);
+      dft_half_in<P::R0, INV>(v);
+    } else {
+      for (int r = 0; r < P::R0; ++r) v[r] = loadg(t + r * P::I0);
+      dft<P::R0, INV>(v);
+    }
+    for (int r = 0; r < P::R0; ++r) sm[t * (P::R0 + 1) + r] = v[r];
   }
   for (int t = 0; t < P::I1; ++t) {  // all loads before any store: the single-buffer hazard
     float4 *v = &regs[(size_t)t * P::RMAX];
-    for (int r = 0; r < P::R1; ++r) v[r] = sm[P::pad(t + r * P::I1)];
+    for (int r = 0; r < P::R1; ++r) v[r] = sm[P::pad(t) + P::padc(r * P::I1)];
     stage_compute<P::R1, INV>(v, tws.data(), P::R0, t & (P::R0 - 1));
   }
   for (int t = 0; t < P::I1; ++t) {
@@ -74,25 +80,28 @@ template <class P, bool INV> static void run_fast(const float2 *a, const float2 
     const int k1 = t & (P::R0 - 1), o1 = (t - k1) * P::R1 + k1;
     for (int r = 0; r < P::R1; ++r) {
       if (P::NS == 2) storeg(o1 + r * P::R0, v[r]);
-      else sm[P::pad(o1 + r * P::R0)] = v[r];
+      else sm[P::pad(o1) + P::padc(r * P::R0)] = v[r];
     }
   }
   if constexpr (P::NS == 3) {
     constexpr int Ns2 = P::R0 * P::R1;
     for (int t = 0; t < P::I2; ++t) {
       float4 v[P::RMAX];
-      for (int r = 0; r < P::R2; ++r) v[r] = sm[P::pad(t + r * P::I2)];
+      for (int r = 0; r < P::R2; ++r) v[r] = sm[P::pad(t) + P::padc(r * P::I2)];
       stage_compute<P::R2, INV>(v, tws.data() + P::TW2, Ns2, t);
       for (int r = 0; r < P::R2; ++r) storeg(t + r * Ns2, v[r]);
     }
   }
 }
 
-// two lines in, two lines out; returns 0 when length n has no compile-time plan
-extern "C" int host_fft_fast(int n, int inverse, const float *a, const float *b, float *oa, float *ob) {
+// two lines in, two lines out; returns 0 when length n has no compile-time plan.
+// half_in: the caller guarantees a[i] = b[i] = 0 for i >= n/2 and the pruned first stage is used.
+extern "C" int host_fft_fast(int n, int inverse, int half_in, const float *a, const float *b, float *oa, float *ob) {
+  const float2 *pa = (const float2 *)a, *pb = (const float2 *)b;
+  float2 *qa = (float2 *)oa, *qb = (float2 *)ob;
   B2N_FAST_PLAN_SWITCH(n,
-                       (inverse ? run_fast<P, true>((const float2 *)a, (const float2 *)b, (float2 *)oa, (float2 *)ob)
-                                : run_fast<P, false>((const float2 *)a, (const float2 *)b, (float2 *)oa, (float2 *)ob)),
+                       (half_in ? (inverse ? run_fast<P, true, true>(pa, pb, qa, qb) : run_fast<P, false, true>(pa, pb, qa, qb))
+                                : (inverse ? run_fast<P, true>(pa, pb, qa, qb) : run_fast<P, false>(pa, pb, qa, qb))),
                        return 0)
   return 1;
 }

@@ -54,16 +54,22 @@ def test_unsupported_sizes_are_rejected(n, hostfft):
 
 
 @pytest.mark.parametrize("n", [64, 128, 256, 320, 512, 640, 768, 1024])
-def test_compile_time_plans_match_numpy(n, hostfft):
-    """b2n_fft_fast.cuh: index maps, staged twiddles and the pair butterflies (incl. radix 10, 12, 16)."""
+@pytest.mark.parametrize("half_in", [False, True])
+def test_compile_time_plans_match_numpy(n, half_in, hostfft):
+    """b2n_fft_fast.cuh: index maps, staged twiddles and the pair butterflies (incl. radix 10, 12, 16),
+    with and without the pruned first stage for zero-padded inputs."""
     rng = np.random.default_rng(1000 + n)
     a = (rng.standard_normal(n) + 1j * rng.standard_normal(n)).astype(np.complex64)
     b = (rng.standard_normal(n) + 1j * rng.standard_normal(n)).astype(np.complex64)
+    if half_in:
+        a[n // 2:] = 0
+        b[n // 2:] = 0
+        a[n // 2:] = np.nan  # must never be read
     for inverse in (False, True):
         oa, ob = np.empty(n, np.complex64), np.empty(n, np.complex64)
         p = lambda x: x.ctypes.data_as(ctypes.c_void_p)
-        assert hostfft.host_fft_fast(n, int(inverse), p(a), p(b), p(oa), p(ob)) == 1
-        for x, got in ((a, oa), (b, ob)):
+        assert hostfft.host_fft_fast(n, int(inverse), int(half_in), p(a), p(b), p(oa), p(ob)) == 1
+        for x, got in ((np.nan_to_num(a), oa), (b, ob)):
             want = np.fft.ifft(x.astype(np.complex128)) * n if inverse else np.fft.fft(x.astype(np.complex128))
             err = np.linalg.norm(got - want) / np.linalg.norm(want)
             assert err < 5e-7, (n, inverse, err)
@@ -72,4 +78,4 @@ def test_compile_time_plans_match_numpy(n, hostfft):
 def test_lengths_without_a_plan_use_the_runtime_passes(hostfft):
     z = np.zeros(96, np.complex64)
     p = z.ctypes.data_as(ctypes.c_void_p)
-    assert hostfft.host_fft_fast(96, 0, p, p, p, p) == 0
+    assert hostfft.host_fft_fast(96, 0, 0, p, p, p, p) == 0

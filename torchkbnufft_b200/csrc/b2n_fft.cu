@@ -279,7 +279,7 @@ template <class P> struct FastCfg {
   static constexpr int ROW_THREADS = LP * P::T;
   static constexpr int PAIRS = P::T >= 64 ? 4 : 256 / P::T;
   static constexpr int COL_THREADS = PAIRS * P::T;
-  static constexpr int MINB = P::RMAX >= 16 ? 1 : 2;  // radix-16 butterflies on pairs want > 100 registers
+  static constexpr int MINB = P::RMAX >= 16 ? 1 : 3;  // radix-16 butterflies on pairs want > 100 registers
 };
 
 B2N_D float2 row_operand(const float2 *in, const float2 *sm, const float2 *sc, int i, float scale) {
@@ -289,7 +289,9 @@ B2N_D float2 row_operand(const float2 *in, const float2 *sm, const float2 *sc, i
   return f2(v.x * scale, v.y * scale);
 }
 
-template <class P, bool INV, int MODE>
+// HALF: the padded half of the inputs (forward) / the cropped half of the outputs (inverse) is skipped at
+// compile time (n_in <= N/2 resp. n_out <= N/2, the 2x-oversampled case).
+template <class P, bool INV, int MODE, bool HALF>
 __global__ void __launch_bounds__(FastCfg<P>::ROW_THREADS, FastCfg<P>::MINB) k_fft_rows_fast(RowArgs a) {
   extern __shared__ __align__(16) float4 fsm4[];
   constexpr int LP = FastCfg<P>::LP;
@@ -346,19 +348,19 @@ __global__ void __launch_bounds__(FastCfg<P>::ROW_THREADS, FastCfg<P>::MINB) k_f
       if (onB) outB[i] = f2(v.z, v.w);
     }
   };
-  fast::fft_line_pair<P, INV>(t, fsm4 + lp * P::NP, 1, a.tw + P::N, loadg, storeg);
+  fast::fft_line_pair<P, INV, HALF && !INV, HALF && INV>(t, fsm4 + lp * P::NP, 1, a.tw + P::N, loadg, storeg);
 }
 
-template <class P, bool INV>
+template <class P, bool INV, bool HALF>
 __global__ void __launch_bounds__(FastCfg<P>::COL_THREADS, FastCfg<P>::MINB) k_fft_cols_fast(ColArgs a) {
   extern __shared__ __align__(16) float4 fsm4[];
   constexpr int PAIRS = FastCfg<P>::PAIRS;
   const int p = threadIdx.x % PAIRS, t = threadIdx.x / PAIRS;  // pair index fastest: contiguous global segments
   const int X = (int)a.X, X2 = X >> 1, n_in = a.n_in, n_out = a.n_out;
-  const int xblocks = (X + 2 * PAIRS - 1) / (2 * PAIRS);
-  const int64_t oa = blockIdx.x / xblocks;
-  const int x = ((int)(blockIdx.x - oa * xblocks) * PAIRS + p) * 2;
-  const bool on = x < X;
+  // grid: x = block of 2*PAIRS columns, (y, z) = outer index
+  const int64_t oa = (int64_t)blockIdx.z * gridDim.y + blockIdx.y;
+  const int x = ((int)blockIdx.x * PAIRS + p) * 2;
+  const bool on = x < X && oa < a.A;
   const float4 *in = reinterpret_cast<const float4 *>(a.in + oa * n_in * a.X + x);
   float4 *out = reinterpret_cast<float4 *>(a.out + oa * n_out * a.X + x);
   const float4 *mul =
@@ -374,7 +376,7 @@ __global__ void __launch_bounds__(FastCfg<P>::COL_THREADS, FastCfg<P>::MINB) k_f
   auto storeg = [&](int i, float4 v) {
     if (on && i < n_out) out[i * X2] = fast::vscale(v, scale);
   };
-  fast::fft_line_pair<P, INV>(t, fsm4 + p, PAIRS, a.tw + P::N, loadg, storeg);
+  fast::fft_line_pair<P, INV, HALF && !INV, HALF && INV>(t, fsm4 + p, PAIRS, a.tw + P::N, loadg, storeg);
 }
 
 // staged twiddle tables of the fast plans: entry e = exp(-2 pi i r k / period)
@@ -420,25 +422,34 @@ static bool make_stages(int64_t n, FftStages *st, int max_pow2_bits = 4) {
 
 int g_fast_fft = 1;  // B2N_OPT_FAST_FFT: compile-time planned passes where a plan exists
 
-template <class P, bool INV, int MODE> static int launch_rows_fast(RowArgs &a, cudaStream_t st) {
+template <class P, bool INV, int MODE, bool HALF> static int launch_rows_fast_h(RowArgs &a, cudaStream_t st) {
   using Cfg = FastCfg<P>;
   const size_t smem = sizeof(float4) * (size_t)Cfg::LP * P::NP;
-  auto kern = k_fft_rows_fast<P, INV, MODE>;
+  auto kern = k_fft_rows_fast<P, INV, MODE, HALF>;
   B2N_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<(unsigned)ceil_div(a.lines, 2 * Cfg::LP), Cfg::ROW_THREADS, smem, st>>>(a);
   B2N_LAUNCH_OK("k_fft_rows_fast");
   return 0;
 }
+template <class P, bool INV, int MODE> static int launch_rows_fast(RowArgs &a, cudaStream_t st) {
+  const bool half = 2 * (INV ? a.n_out : a.n_in) <= P::N;
+  return half ? launch_rows_fast_h<P, INV, MODE, true>(a, st) : launch_rows_fast_h<P, INV, MODE, false>(a, st);
+}
 
-template <class P, bool INV> static int launch_cols_fast(ColArgs &a, cudaStream_t st) {
+template <class P, bool INV, bool HALF> static int launch_cols_fast_h(ColArgs &a, cudaStream_t st) {
   using Cfg = FastCfg<P>;
   const size_t smem = sizeof(float4) * (size_t)Cfg::PAIRS * P::NP;
-  auto kern = k_fft_cols_fast<P, INV>;
+  auto kern = k_fft_cols_fast<P, INV, HALF>;
   B2N_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int64_t blocks = a.A * ceil_div(a.X, 2 * Cfg::PAIRS);
-  kern<<<(unsigned)blocks, Cfg::COL_THREADS, smem, st>>>(a);
+  const int64_t gy = a.A < 32768 ? a.A : 32768;
+  const dim3 grid((unsigned)ceil_div(a.X, 2 * Cfg::PAIRS), (unsigned)gy, (unsigned)ceil_div(a.A, gy));
+  kern<<<grid, Cfg::COL_THREADS, smem, st>>>(a);
   B2N_LAUNCH_OK("k_fft_cols_fast");
   return 0;
+}
+template <class P, bool INV> static int launch_cols_fast(ColArgs &a, cudaStream_t st) {
+  const bool half = 2 * (INV ? a.n_out : a.n_in) <= P::N;
+  return half ? launch_cols_fast_h<P, INV, true>(a, st) : launch_cols_fast_h<P, INV, false>(a, st);
 }
 
 static bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }

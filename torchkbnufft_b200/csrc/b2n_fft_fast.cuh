@@ -92,11 +92,11 @@ template <bool INV> B2N_HD void dft5(float4 &v0, float4 &v1, float4 &v2, float4 
   v2 = vadd(m2, n2);
   v3 = vsub(m2, n2);
 }
-template <bool INV> B2N_HD void dft8(float4 *v) {
+// second half of the radix-8 butterfly: e = DFT4 of the even inputs, o = DFT4 of the odd inputs
+template <bool INV>
+B2N_HD void dft8_finish(float4 e0, float4 e1, float4 e2, float4 e3, float4 o0, float4 o1, float4 o2, float4 o3,
+                        float4 *v) {
   const float h = 0.70710678118654752440f;
-  float4 e0 = v[0], e1 = v[2], e2 = v[4], e3 = v[6], o0 = v[1], o1 = v[3], o2 = v[5], o3 = v[7];
-  dft4<INV>(e0, e1, e2, e3);
-  dft4<INV>(o0, o1, o2, o3);
   const float4 w1 = vmulw<INV>(o1, h, -h);  // W8^1
   const float4 w2 = vrot<INV>(o2);          // W8^2
   const float4 w3 = vmulw<INV>(o3, -h, -h); // W8^3
@@ -108,6 +108,27 @@ template <bool INV> B2N_HD void dft8(float4 *v) {
   v[6] = vsub(e2, w2);
   v[3] = vadd(e3, w3);
   v[7] = vsub(e3, w3);
+}
+template <bool INV> B2N_HD void dft8(float4 *v) {
+  float4 e0 = v[0], e1 = v[2], e2 = v[4], e3 = v[6], o0 = v[1], o1 = v[3], o2 = v[5], o3 = v[7];
+  dft4<INV>(e0, e1, e2, e3);
+  dft4<INV>(o0, o1, o2, o3);
+  dft8_finish<INV>(e0, e1, e2, e3, o0, o1, o2, o3, v);
+}
+// DFT4 of (a, b, 0, 0)
+template <bool INV> B2N_HD void dft4_half_in(float4 a, float4 b, float4 &y0, float4 &y1, float4 &y2, float4 &y3) {
+  const float4 rb = vrot<INV>(b);
+  y0 = vadd(a, b);
+  y1 = vadd(a, rb);
+  y2 = vsub(a, b);
+  y3 = vsub(a, rb);
+}
+// radix 8 with inputs 4..7 known to be zero (they lie in the zero padding)
+template <bool INV> B2N_HD void dft8_half_in(float4 *v) {
+  float4 e0, e1, e2, e3, o0, o1, o2, o3;
+  dft4_half_in<INV>(v[0], v[2], e0, e1, e2, e3);
+  dft4_half_in<INV>(v[1], v[3], o0, o1, o2, o3);
+  dft8_finish<INV>(e0, e1, e2, e3, o0, o1, o2, o3, v);
 }
 // 10 = 2 x 5: DFT5 over the even and the odd inputs, twiddle W10^k, DFT2
 template <bool INV> B2N_HD void dft10(float4 *v) {
@@ -158,19 +179,10 @@ template <bool INV> B2N_HD void dft12(float4 *v) {
     v[k2 + 9] = y[3][k2];
   }
 }
-// 16 = 4 x 4
-template <bool INV> B2N_HD void dft16(float4 *v) {
+// 16 = 4 x 4; y[n1][k2] = DFT4 over n2 of v[4*n2 + n1]
+template <bool INV> B2N_HD void dft16_finish(float4 (*y)[4], float4 *v) {
   const float c1 = 0.92387953251128675613f, s1 = 0.38268343236508977173f;  // cos, sin of pi/8
   const float h = 0.70710678118654752440f;
-  float4 y[4][4];
-#pragma unroll
-  for (int n1 = 0; n1 < 4; ++n1) {
-    y[n1][0] = v[n1];
-    y[n1][1] = v[n1 + 4];
-    y[n1][2] = v[n1 + 8];
-    y[n1][3] = v[n1 + 12];
-    dft4<INV>(y[n1][0], y[n1][1], y[n1][2], y[n1][3]);
-  }
   y[1][1] = vmulw<INV>(y[1][1], c1, -s1);   // W16^1
   y[1][2] = vmulw<INV>(y[1][2], h, -h);     // W16^2
   y[1][3] = vmulw<INV>(y[1][3], s1, -c1);   // W16^3
@@ -189,6 +201,25 @@ template <bool INV> B2N_HD void dft16(float4 *v) {
     v[k2 + 12] = y[3][k2];
   }
 }
+template <bool INV> B2N_HD void dft16(float4 *v) {
+  float4 y[4][4];
+#pragma unroll
+  for (int n1 = 0; n1 < 4; ++n1) {
+    y[n1][0] = v[n1];
+    y[n1][1] = v[n1 + 4];
+    y[n1][2] = v[n1 + 8];
+    y[n1][3] = v[n1 + 12];
+    dft4<INV>(y[n1][0], y[n1][1], y[n1][2], y[n1][3]);
+  }
+  dft16_finish<INV>(y, v);
+}
+// radix 16 with inputs 8..15 known to be zero
+template <bool INV> B2N_HD void dft16_half_in(float4 *v) {
+  float4 y[4][4];
+#pragma unroll
+  for (int n1 = 0; n1 < 4; ++n1) dft4_half_in<INV>(v[n1], v[n1 + 4], y[n1][0], y[n1][1], y[n1][2], y[n1][3]);
+  dft16_finish<INV>(y, v);
+}
 
 template <int R, bool INV> B2N_HD void dft(float4 *v) {
   static_assert(R == 2 || R == 3 || R == 4 || R == 5 || R == 8 || R == 10 || R == 12 || R == 16, "radix");
@@ -202,6 +233,13 @@ template <int R, bool INV> B2N_HD void dft(float4 *v) {
   if constexpr (R == 16) dft16<INV>(v);
 }
 
+// first-stage butterfly when legs r >= R/2 are zero
+template <int R, bool INV> B2N_HD void dft_half_in(float4 *v) {
+  static_assert(R == 8 || R == 16, "first radix");
+  if constexpr (R == 8) dft8_half_in<INV>(v);
+  if constexpr (R == 16) dft16_half_in<INV>(v);
+}
+
 // ---- compile-time plan ---------------------------------------------------------------------
 constexpr int cmax(int a, int b) { return a > b ? a : b; }
 
@@ -213,11 +251,15 @@ template <int N_, int R0_, int R1_, int R2_> struct Plan {
   static constexpr int I0 = N / R0, I1 = N / R1, I2 = R2 > 1 ? N / R2 : 0;  // butterflies per stage
   static constexpr int T = cmax(I0, cmax(I1, I2));                          // threads per line pair
   static constexpr int RMAX = cmax(R0, cmax(R1, R2));
-  static constexpr int PSH = R0 >= 16 ? 4 : 3;                // one padding slot per 2^PSH elements:
+  static constexpr int PSH = R0 >= 16 ? 4 : 3;                // one padding slot per R0 = 2^PSH elements:
   static constexpr int NP = N + (N >> PSH) + 1;               // stride-R0 stores stay conflict-free
+  static_assert(R0 == (1 << PSH), "first radix must be 8 or 16");
+  static_assert(I1 % R0 == 0 && I2 % R0 == 0, "leg strides must be multiples of the padding period");
   static constexpr int TW2 = (R1 - 1) * R0;                   // offset of the stage-2 twiddle table
   static constexpr int TW_COUNT = TW2 + (R2 > 1 ? (R2 - 1) * R0 * R1 : 0);
   B2N_HD static int pad(int i) { return i + (i >> PSH); }
+  // pad(i + c) == pad(i) + padc(c) when c is a multiple of R0
+  static constexpr int padc(int c) { return c + (c >> PSH); }
 };
 
 // staged twiddle table entry e of plan P (double precision, rounded once)
@@ -258,44 +300,58 @@ template <int R, bool INV> B2N_HD void stage_compute(float4 *v, const float2 *tw
 // both lines, storeg(i, v) takes output element i.  Every thread of the CTA must call this
 // (it contains CTA-wide barriers); threads with nothing to do pass functors that read zeros
 // and drop stores.
-template <class P, bool INV, class LoadG, class StoreG>
+// HIN : input elements i >= N/2 are zero padding (never loaded, first butterfly simplified).
+// HOUT: output elements i >= N/2 are cropped (never computed: only the legs r < R/2 of the last
+//       stage are stored and the compiler drops the rest of that butterfly).
+template <class P, bool INV, bool HIN, bool HOUT, class LoadG, class StoreG>
 __device__ __forceinline__ void fft_line_pair(int t, float4 *sm, int es, const float2 *tws, LoadG loadg,
                                               StoreG storeg) {
   float4 v[P::RMAX];
   if (t < P::I0) {
+    if constexpr (HIN) {
 #pragma unroll
-    for (int r = 0; r < P::R0; ++r) v[r] = loadg(t + r * P::I0);
-    dft<P::R0, INV>(v);
+      for (int r = 0; r < P::R0 / 2; ++r) v[r] = loadg(t + r * P::I0);
+      dft_half_in<P::R0, INV>(v);
+    } else {
 #pragma unroll
-    for (int r = 0; r < P::R0; ++r) sm[P::pad(t * P::R0 + r) * es] = v[r];
+      for (int r = 0; r < P::R0; ++r) v[r] = loadg(t + r * P::I0);
+      dft<P::R0, INV>(v);
+    }
+    float4 *dst = sm + t * (P::R0 + 1) * es;  // pad(t*R0 + r) == t*(R0+1) + r
+#pragma unroll
+    for (int r = 0; r < P::R0; ++r) dst[r * es] = v[r];
   }
   __syncthreads();
   const int k1 = t & (P::R0 - 1);
   const int o1 = (t - k1) * P::R1 + k1;
+  const float4 *src = sm + P::pad(t) * es;
   if (t < P::I1) {
 #pragma unroll
-    for (int r = 0; r < P::R1; ++r) v[r] = sm[P::pad(t + r * P::I1) * es];
+    for (int r = 0; r < P::R1; ++r) v[r] = src[P::padc(r * P::I1) * es];
     stage_compute<P::R1, INV>(v, tws, P::R0, k1);
   }
   if constexpr (P::NS == 2) {
+    constexpr int LEGS = HOUT ? (P::R1 + 1) / 2 : P::R1;
     if (t < P::I1) {
 #pragma unroll
-      for (int r = 0; r < P::R1; ++r) storeg(o1 + r * P::R0, v[r]);
+      for (int r = 0; r < LEGS; ++r) storeg(o1 + r * P::R0, v[r]);
     }
   } else {
     __syncthreads();  // everyone holds its stage-1 inputs: the buffer may be overwritten
     if (t < P::I1) {
+      float4 *dst = sm + P::pad(o1) * es;
 #pragma unroll
-      for (int r = 0; r < P::R1; ++r) sm[P::pad(o1 + r * P::R0) * es] = v[r];
+      for (int r = 0; r < P::R1; ++r) dst[P::padc(r * P::R0) * es] = v[r];
     }
     __syncthreads();
     constexpr int Ns2 = P::R0 * P::R1;  // == P::I2, so k2 == t and the output index is t + r*Ns2
+    constexpr int LEGS = HOUT ? (P::R2 + 1) / 2 : P::R2;
     if (t < P::I2) {
 #pragma unroll
-      for (int r = 0; r < P::R2; ++r) v[r] = sm[P::pad(t + r * P::I2) * es];
+      for (int r = 0; r < P::R2; ++r) v[r] = src[P::padc(r * P::I2) * es];
       stage_compute<P::R2, INV>(v, tws + P::TW2, Ns2, t);
 #pragma unroll
-      for (int r = 0; r < P::R2; ++r) storeg(t + r * Ns2, v[r]);
+      for (int r = 0; r < LEGS; ++r) storeg(t + r * Ns2, v[r]);
     }
   }
 }

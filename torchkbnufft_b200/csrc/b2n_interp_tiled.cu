@@ -992,8 +992,12 @@ int tiled_adjoint(const b2n_geom *g, const b2n_points *p, const void *kdata, int
   int rc = make_args<float>(g, p, B, C, &a);
   if (rc) return rc;
   const bool wide = C > 8 && g_adj_chunk != 8;
-  if (g_adj_rowwarp == 0) return wide ? launch_adj_warptile<2>(a, kdata, grid, st) : launch_adj_warptile<1>(a, kdata, grid, st);
-  if (wide) return g_adj_rowwarp == 1 ? launch_adj<16>(a, kdata, grid, st) : launch_adj_coilwarp(a, kdata, grid, st);
+  // variant 0 (auto): warp-owned tile rows for 16-coil CTAs (107 us vs 114 us at BASELINE config 2,
+  // profiles/r01_g), warp-private tiles for <= 8 coils; 1 / 2 / 3 force rows / coils / private tiles
+  const int v = g_adj_rowwarp;
+  if (v == 3 || (v == 0 && !wide))
+    return wide ? launch_adj_warptile<2>(a, kdata, grid, st) : launch_adj_warptile<1>(a, kdata, grid, st);
+  if (wide) return v == 2 ? launch_adj_coilwarp(a, kdata, grid, st) : launch_adj<16>(a, kdata, grid, st);
   if (C > 8) return launch_adj<8>(a, kdata, grid, st);
   if (C > 4) return launch_adj<8>(a, kdata, grid, st);
   if (C > 2) return launch_adj<4>(a, kdata, grid, st);
