@@ -154,11 +154,22 @@ __global__ void __launch_bounds__(256) k_crop_coilsum(PadGeom g, const cplx<T> *
   for (int64_t n2 = (int64_t)blockIdx.y * blockDim.x + threadIdx.x; n2 < g.N[2]; n2 += (int64_t)gridDim.y * blockDim.x) {
     cplx<T> acc = {T(0), T(0)};
     if (smaps) {
-      for (int64_t c = 0; c < g.C; ++c) {
-        const cplx<T> v = CL ? grid[(b * g.Kprod + krow + n2) * g.C + c] : grid[(b * g.C + c) * g.Kprod + krow + n2];
-        const cplx<T> s = CL ? smaps[(bs * g.Nprod + nrow + n2) * g.C + c] : smaps[(bs * g.C + c) * g.Nprod + nrow + n2];
-        cmac(acc, v, cconj(s));
+      auto gv = [&](int64_t c) {
+        return CL ? grid[(b * g.Kprod + krow + n2) * g.C + c] : grid[(b * g.C + c) * g.Kprod + krow + n2];
+      };
+      auto sv = [&](int64_t c) {
+        return CL ? smaps[(bs * g.Nprod + nrow + n2) * g.C + c] : smaps[(bs * g.C + c) * g.Nprod + nrow + n2];
+      };
+      int64_t c = 0;
+      for (; c + 4 <= g.C; c += 4) {  // eight independent loads in flight per thread; summation order unchanged
+        const cplx<T> v0 = gv(c), v1 = gv(c + 1), v2 = gv(c + 2), v3 = gv(c + 3);
+        const cplx<T> s0 = sv(c), s1 = sv(c + 1), s2 = sv(c + 2), s3 = sv(c + 3);
+        cmac(acc, v0, cconj(s0));
+        cmac(acc, v1, cconj(s1));
+        cmac(acc, v2, cconj(s2));
+        cmac(acc, v3, cconj(s3));
       }
+      for (; c < g.C; ++c) cmac(acc, gv(c), cconj(sv(c)));
     } else {
       acc = CL ? grid[(b * g.Kprod + krow + n2) * g.C + co] : grid[(b * g.C + co) * g.Kprod + krow + n2];
     }
