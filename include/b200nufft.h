@@ -105,7 +105,8 @@ enum b2n_option {
   B2N_OPT_TILED_KERNELS = 0, /* 1 (default): use the shared-memory tiled kernels where they apply */
   B2N_OPT_ADJ_ROW_OWNERSHIP = 1, /* tiled 2-D adjoint variant: 0 (default) auto = warp-owned tile rows for 16-coil CTAs,
                                     warp-private 8-coil tiles otherwise; 1 warp-owned rows, 2 warp-owned coils,
-                                    3 warp-private tiles (kept for A/B measurements) */
+                                    3 warp-private tiles, 4 / 5 warp-owned rows with 4 / 2 warps per CTA
+                                    (kept for A/B measurements) */
   B2N_OPT_FWD_COIL_CHUNK = 2, /* tiled forward for C > 8: 0 (default) one 16-coil CTA per sub-problem, 1 persistent
                                  triple-buffered kernel (measured slower, kept for A/B), 8 two 8-coil CTAs */
   B2N_OPT_ADJ_COIL_CHUNK = 3, /* 0 (default): 16 coils per CTA in the tiled adjoint; 8: two 8-coil CTAs */

@@ -420,12 +420,23 @@ __global__ void __launch_bounds__(kPersistThreads, 1)
 // -----------------------------------------------------------------------------------------
 // adjoint spread
 // -----------------------------------------------------------------------------------------
-template <int CC>
-__global__ void __launch_bounds__(kThreads) k_adj_tiled_2d(InterpArgs<float> a, const float2 *__restrict__ kdata,
+// float2 slots of one staging buffer of k_adj_tiled_2d: weights, samples ((kRound+1) per coil), base cells;
+// even, so that the second buffer stays 16-byte aligned
+template <int CC> constexpr int adj_stage_slots() { return (kRound * kNC + (kRound + 1) * CC + kRound + 1) & ~1; }
+
+// NW warps per CTA: warp w owns the tile rows r with r mod NW == w.  NW = 8: one footprint row per
+// (point, warp); NW = 4: one or two rows, with the per-point loads (base cell, sample, x-weights)
+// shared by both -- fewer shared-memory wavefronts per point, fewer warps to hide latency with.
+template <int CC, int NW>
+__global__ void __launch_bounds__(NW * 32) k_adj_tiled_2d(InterpArgs<float> a, const float2 *__restrict__ kdata,
                                                            float2 *__restrict__ grid,
                                                            const __grid_constant__ CUtensorMap tmap, int use_tma) {
   constexpr int QX = 32 / CC, NX = (kJ + QX - 1) / QX;
-  constexpr int STAGE = kRound * kNC + kRound * CC + kRound;  // float2 slots: coef, val, base
+  constexpr int NT = NW * 32;
+  // staged samples are coil-major with an odd row stride: the gather writes 32 consecutive points of one
+  // coil (conflict-free) and the spread reads 8 coils x one point per half-warp (conflict-free)
+  constexpr int VS = kRound + 1;
+  constexpr int STAGE = adj_stage_slots<CC>();  // float2 slots: coef, val, base
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float2 *tile = reinterpret_cast<float2 *>(smem_raw);  // [planes][kSY][kSX] accumulators
   float2 *stage0 = tile + planes<CC>() * kPS;           // 2 x STAGE
@@ -443,7 +454,7 @@ __global__ void __launch_bounds__(kThreads) k_adj_tiled_2d(InterpArgs<float> a, 
     if (round < rounds) {
       const int p0 = round * kRound, nb = min(kRound, sp.count - p0);
       int *dst = s_perm + (round % 3) * kRound;
-      for (int e = threadIdx.x; e < nb; e += kThreads) cp_async4(&dst[e], &a.perm[sp.start + p0 + e]);
+      for (int e = threadIdx.x; e < nb; e += NT) cp_async4(&dst[e], &a.perm[sp.start + p0 + e]);
     }
   };
   auto issue_data = [&](int round) {  // weights, base cells and gathered samples, one round ahead
@@ -452,24 +463,24 @@ __global__ void __launch_bounds__(kThreads) k_adj_tiled_2d(InterpArgs<float> a, 
       const int p0 = round * kRound, nb = min(kRound, sp.count - p0), s0 = sp.start + p0;
       const float4 *src = reinterpret_cast<const float4 *>(pcoef + (int64_t)s0 * kNC);
       float4 *dst = reinterpret_cast<float4 *>(buf);
-      for (int e = threadIdx.x; e < nb * (kNC / 2); e += kThreads) cp_async16(&dst[e], &src[e]);
+      for (int e = threadIdx.x; e < nb * (kNC / 2); e += NT) cp_async16(&dst[e], &src[e]);
       float2 *val = buf + kRound * kNC;
       const int *perm = s_perm + (round % 3) * kRound;
-      for (int e = threadIdx.x; e < kRound * CC; e += kThreads) {
+      for (int e = threadIdx.x; e < kRound * CC; e += NT) {
         const int cc = e / kRound, i = e - cc * kRound;  // consecutive threads: consecutive points, one coil
         const bool on = sp.c0 + cc < C && i < nb;
-        cp_async8(&val[i * CC + cc], &kdata[(int64_t)(sp.b * C + (on ? sp.c0 + cc : 0)) * M + (on ? perm[i] : 0)], on);
+        cp_async8(&val[cc * VS + i], &kdata[(int64_t)(sp.b * C + (on ? sp.c0 + cc : 0)) * M + (on ? perm[i] : 0)], on);
       }
-      int2 *sb = reinterpret_cast<int2 *>(val + kRound * CC);
+      int2 *sb = reinterpret_cast<int2 *>(val + VS * CC);
       const int2 *bsrc = reinterpret_cast<const int2 *>(a.base) + s0;
-      for (int e = threadIdx.x; e < nb; e += kThreads) cp_async8(&sb[e], &bsrc[e], true);
+      for (int e = threadIdx.x; e < nb; e += NT) cp_async8(&sb[e], &bsrc[e], true);
     }
   };
 
   issue_perm(0);
   issue_perm(1);
   cp_async_commit();
-  for (int e = threadIdx.x; e < planes<CC>() * kPS; e += kThreads) tile[e] = make_float2(0.f, 0.f);
+  for (int e = threadIdx.x; e < planes<CC>() * kPS; e += NT) tile[e] = make_float2(0.f, 0.f);
   cp_async_wait_all();
   __syncthreads();
   issue_data(0);
@@ -487,33 +498,42 @@ __global__ void __launch_bounds__(kThreads) k_adj_tiled_2d(InterpArgs<float> a, 
     cp_async_commit();
     const float2 *buf = stage0 + (round & 1) * STAGE;
     const float2 *s_coef = buf, *s_val = buf + kRound * kNC;
-    const int2 *s_base = reinterpret_cast<const int2 *>(s_val + kRound * CC);
+    const int2 *s_base = reinterpret_cast<const int2 *>(s_val + VS * CC);
     const int nb = min(kRound, sp.count - round * kRound);
     for (int i = 0; i < nb; ++i) {
       const int2 bs = s_base[i];
       const int by = bs.x - sp.y0, bx = bs.y - sp.x0;
-      const int jy = (warp - by) & (kWarps - 1);  // the footprint row this warp owns, if any
-      if (jy >= kJ) continue;
-      const float2 v = s_val[i * CC + c];
-      const float2 cyv = s_coef[i * kNC + jy];
-      float2 *trow = tplane + (by + jy) * kSX + bx;
-      float2 u;  // conj(cy) * v   (cy carries the fftshift phase)
-      u.x = fmaf(cyv.x, v.x, cyv.y * v.y);
-      u.y = fmaf(cyv.x, v.y, -cyv.y * v.x);
-      float2 t[NX], cxv[NX];
-#pragma unroll
-      for (int nx = 0; nx < NX; ++nx) {  // all loads first: independent, latency overlaps
-        const int jx = nx * QX + qx;
-        const bool on = kJ % QX == 0 || jx < kJ;
-        cxv[nx] = s_coef[i * kNC + kJ + (on ? jx : 0)];
-        t[nx] = trow[on ? jx : 0];
-      }
+      const int jy0 = (warp - by) & (NW - 1);  // the first footprint row this warp owns, if any
+      if (jy0 >= kJ) continue;
+      const float2 v = s_val[c * VS + i];
+      float2 cxv[NX];
 #pragma unroll
       for (int nx = 0; nx < NX; ++nx) {
         const int jx = nx * QX + qx;
-        if (kJ % QX == 0 || jx < kJ) {
-          cmacf_conj(t[nx], cxv[nx], u);  // += conj(cx) * conj(cy) * v
-          trow[jx] = t[nx];
+        cxv[nx] = s_coef[i * kNC + kJ + ((kJ % QX == 0 || jx < kJ) ? jx : 0)];
+      }
+#pragma unroll
+      for (int rr = 0; rr < (kJ + NW - 1) / NW; ++rr) {  // the rows jy0, jy0 + NW, ... of this footprint
+        const int jy = jy0 + rr * NW;
+        if (rr > 0 && jy >= kJ) break;
+        const float2 cyv = s_coef[i * kNC + jy];
+        float2 *trow = tplane + (by + jy) * kSX + bx;
+        float2 u;  // conj(cy) * v   (cy carries the fftshift phase)
+        u.x = fmaf(cyv.x, v.x, cyv.y * v.y);
+        u.y = fmaf(cyv.x, v.y, -cyv.y * v.x);
+        float2 t[NX];
+#pragma unroll
+        for (int nx = 0; nx < NX; ++nx) {  // all loads first: independent, latency overlaps
+          const int jx = nx * QX + qx;
+          t[nx] = trow[(kJ % QX == 0 || jx < kJ) ? jx : 0];
+        }
+#pragma unroll
+        for (int nx = 0; nx < NX; ++nx) {
+          const int jx = nx * QX + qx;
+          if (kJ % QX == 0 || jx < kJ) {
+            cmacf_conj(t[nx], cxv[nx], u);  // += conj(cx) * conj(cy) * v
+            trow[jx] = t[nx];
+          }
         }
       }
       __syncwarp();
@@ -531,7 +551,7 @@ __global__ void __launch_bounds__(kThreads) k_adj_tiled_2d(InterpArgs<float> a, 
     }
   } else {
     __syncthreads();
-    for (int e = threadIdx.x; e < CC * kPS; e += kThreads) {
+    for (int e = threadIdx.x; e < CC * kPS; e += NT) {
       const int cc = e / kPS, rem = e - cc * kPS;
       if (sp.c0 + cc >= C) break;
       const int r = rem / kSX, x = rem - r * kSX;
@@ -923,17 +943,18 @@ static int launch_fwd_persist(const InterpArgs<float> &a, const void *grid, void
   return 0;
 }
 
-template <int CC> static int launch_adj(const InterpArgs<float> &a, const void *kdata, void *grid, cudaStream_t st) {
+template <int CC, int NW = kWarps>
+static int launch_adj(const InterpArgs<float> &a, const void *kdata, void *grid, cudaStream_t st) {
   const size_t smem =
-      sizeof(float2) * (planes<CC>() * kPS + 2 * (kRound * kNC + kRound * CC + kRound)) + sizeof(int) * 3 * kRound;
-  auto kern = k_adj_tiled_2d<CC>;
+      sizeof(float2) * (planes<CC>() * kPS + 2 * adj_stage_slots<CC>()) + sizeof(int) * 3 * kRound;
+  auto kern = k_adj_tiled_2d<CC, NW>;
   B2N_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   B2N_CUDA_OK(cudaMemsetAsync(grid, 0, sizeof(float2) * (size_t)(a.B * a.C * a.Kprod), st));
   CUtensorMap map;
   memset(&map, 0, sizeof(map));
   const int use_tma = make_grid_tmap(&map, grid, a.B, a.C, a.K[0], a.K[1]) ? 1 : 0;
   dim3 gd((unsigned)a.n_sub_max, (unsigned)ceil_div(a.C, CC), (unsigned)(a.n_traj == 1 ? a.B : 1));
-  kern<<<gd, kThreads, smem, st>>>(a, (const float2 *)kdata, (float2 *)grid, map, use_tma);
+  kern<<<gd, NW * 32, smem, st>>>(a, (const float2 *)kdata, (float2 *)grid, map, use_tma);
   B2N_LAUNCH_OK("k_adj_tiled_2d");
   return 0;
 }
@@ -997,6 +1018,8 @@ int tiled_adjoint(const b2n_geom *g, const b2n_points *p, const void *kdata, int
   const int v = g_adj_rowwarp;
   if (v == 3 || (v == 0 && !wide))
     return wide ? launch_adj_warptile<2>(a, kdata, grid, st) : launch_adj_warptile<1>(a, kdata, grid, st);
+  if (wide && v == 4) return launch_adj<16, 4>(a, kdata, grid, st);
+  if (wide && v == 5) return launch_adj<16, 2>(a, kdata, grid, st);
   if (wide) return v == 2 ? launch_adj_coilwarp(a, kdata, grid, st) : launch_adj<16>(a, kdata, grid, st);
   if (C > 8) return launch_adj<8>(a, kdata, grid, st);
   if (C > 4) return launch_adj<8>(a, kdata, grid, st);
