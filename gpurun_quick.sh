@@ -1,3 +1,4 @@
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "tiled or cfg2 or edge" > gpurun_out/q_pytest.log 2>&1; tail -3 gpurun_out/q_pytest.log
-for o in "1=0" "1=4" "1=5"; do echo "opt $o"; timeout 600 python bench.py --steps 100 --warmup 3 --breakdown --no-cpu-baseline --opt $o 2>&1 | grep -E "stage ms|step ms"; done
+timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/q_pytest_all.log 2>&1; tail -3 gpurun_out/q_pytest_all.log
+timeout 600 python bench.py --steps 100 --warmup 3 --breakdown --no-cpu-baseline --fft cufft 2>&1 | grep -E "stage ms|step ms"
+timeout 900 python profiles/bench_configs.py cfg1 cfg3 cfg5 2>&1 | tail -6

@@ -52,6 +52,10 @@ struct RowArgs {
   const float2 *image, *smaps, *scaling;  // ROW_FWD_FIRST operands
   const float2 *tw;      // twiddle table exp(-2 pi i t / n), t < n (b2n_fft_twiddles)
   float scale;
+  // k_fft_rows_sense only: coil groups per image row, per-group partial rows, per-row arrival counters
+  int coil_groups;
+  float2 *partial;
+  unsigned int *counter;
 };
 
 // One Stockham stage over this CTA's lines.  LOADF(line, i) / STOREF(line, i, v) access the
@@ -274,12 +278,16 @@ __global__ void __launch_bounds__(kColThreads, 2) k_fft_cols(ColArgs a) {
 // fast passes: compile-time plans of b2n_fft_fast.cuh, two lines per thread
 // -----------------------------------------------------------------------------------------
 template <class P> struct FastCfg {
-  // row pass: LP line pairs per CTA (about 320 threads); column pass: PAIRS column pairs per CTA
-  static constexpr int LP = P::T >= 128 ? 2 : 320 / P::T;
+  // row pass: LP line pairs per CTA (about 160 threads: small CTAs keep the last wave of a launch short -- a
+  // launch is typically 1-3 waves of resident line pairs); column pass: PAIRS column pairs per CTA
+  static constexpr int LP = P::T >= 160 ? 1 : 160 / P::T;
   static constexpr int ROW_THREADS = LP * P::T;
   static constexpr int PAIRS = P::T >= 64 ? 4 : 256 / P::T;
   static constexpr int COL_THREADS = PAIRS * P::T;
-  static constexpr int MINB = P::RMAX >= 16 ? 1 : 3;  // radix-16 butterflies on pairs want > 100 registers
+  // register budget: 64 per thread (128 for radix-16 butterflies on pairs) -> resident CTAs per SM
+  static constexpr int REG_THREADS = P::RMAX >= 16 ? 512 : 1024;
+  static constexpr int ROW_MINB = REG_THREADS / ROW_THREADS > 0 ? REG_THREADS / ROW_THREADS : 1;
+  static constexpr int COL_MINB = REG_THREADS / COL_THREADS > 0 ? REG_THREADS / COL_THREADS : 1;
 };
 
 B2N_D float2 row_operand(const float2 *in, const float2 *sm, const float2 *sc, int i, float scale) {
@@ -292,7 +300,7 @@ B2N_D float2 row_operand(const float2 *in, const float2 *sm, const float2 *sc, i
 // HALF: the padded half of the inputs (forward) / the cropped half of the outputs (inverse) is skipped at
 // compile time (n_in <= N/2 resp. n_out <= N/2, the 2x-oversampled case).
 template <class P, bool INV, int MODE, bool HALF>
-__global__ void __launch_bounds__(FastCfg<P>::ROW_THREADS, FastCfg<P>::MINB) k_fft_rows_fast(RowArgs a) {
+__global__ void __launch_bounds__(FastCfg<P>::ROW_THREADS, FastCfg<P>::ROW_MINB) k_fft_rows_fast(RowArgs a) {
   extern __shared__ __align__(16) float4 fsm4[];
   constexpr int LP = FastCfg<P>::LP;
   const int lp = threadIdx.x / P::T, t = threadIdx.x - lp * P::T;
@@ -300,21 +308,23 @@ __global__ void __launch_bounds__(FastCfg<P>::ROW_THREADS, FastCfg<P>::MINB) k_f
   const bool onA = lA < a.lines, onB = lA + 1 < a.lines;
   const float2 *inA = nullptr, *inB = nullptr, *smA = nullptr, *smB = nullptr, *scA = nullptr, *scB = nullptr;
   float2 *outA = nullptr, *outB = nullptr;
-  auto setup = [&](int64_t l, const float2 *&in, const float2 *&sm, const float2 *&sc, float2 *&out) {
+  // 32-bit index arithmetic: the launchers guarantee every array here has < 2^31 elements
+  auto setup = [&](uint32_t l, const float2 *&in, const float2 *&sm, const float2 *&sc, float2 *&out) {
+    const uint32_t rpi = (uint32_t)a.rows_per_img, n_in = (uint32_t)a.n_in, n_out = (uint32_t)a.n_out;
+    const uint32_t bc = l / rpi, row = l - bc * rpi;
     if (MODE == ROW_FWD_FIRST) {
-      const int64_t bc = l / a.rows_per_img, row = l - bc * a.rows_per_img;
-      const int64_t b = bc / a.C, c = bc - b * a.C;
-      in = a.image + ((b * a.Ci + (a.Ci == 1 ? 0 : c)) * a.rows_per_img + row) * a.n_in;
-      sm = a.smaps ? a.smaps + (((a.Bs == 1 ? 0 : b) * a.C + c) * a.rows_per_img + row) * a.n_in : nullptr;
-      sc = a.scaling ? a.scaling + row * a.n_in : nullptr;
+      const uint32_t C = (uint32_t)a.C, b = bc / C, c = bc - b * C;
+      in = a.image + ((b * (uint32_t)a.Ci + (a.Ci == 1 ? 0u : c)) * rpi + row) * n_in;
+      sm = a.smaps ? a.smaps + (((a.Bs == 1 ? 0u : b) * C + c) * rpi + row) * n_in : nullptr;
+      sc = a.scaling ? a.scaling + row * n_in : nullptr;
     } else {
-      in = a.in + l * a.n_in;
-      sc = a.scaling ? a.scaling + (l % a.rows_per_img) * a.n_out : nullptr;
+      in = a.in + l * n_in;
+      sc = a.scaling ? a.scaling + row * n_out : nullptr;
     }
-    out = a.out + l * a.n_out;
+    out = a.out + l * n_out;
   };
-  if (onA) setup(lA, inA, smA, scA, outA);
-  if (onB) setup(lA + 1, inB, smB, scB, outB);
+  if (onA) setup((uint32_t)lA, inA, smA, scA, outA);
+  if (onB) setup((uint32_t)lA + 1, inB, smB, scB, outB);
   const int n_in = a.n_in, n_out = a.n_out;
   const float scale = a.scale;
   auto loadg = [&](int i) -> float4 {
@@ -352,7 +362,7 @@ __global__ void __launch_bounds__(FastCfg<P>::ROW_THREADS, FastCfg<P>::MINB) k_f
 }
 
 template <class P, bool INV, bool HALF>
-__global__ void __launch_bounds__(FastCfg<P>::COL_THREADS, FastCfg<P>::MINB) k_fft_cols_fast(ColArgs a) {
+__global__ void __launch_bounds__(FastCfg<P>::COL_THREADS, FastCfg<P>::COL_MINB) k_fft_cols_fast(ColArgs a) {
   extern __shared__ __align__(16) float4 fsm4[];
   constexpr int PAIRS = FastCfg<P>::PAIRS;
   const int p = threadIdx.x % PAIRS, t = threadIdx.x / PAIRS;  // pair index fastest: contiguous global segments
@@ -377,6 +387,75 @@ __global__ void __launch_bounds__(FastCfg<P>::COL_THREADS, FastCfg<P>::MINB) k_f
     if (on && i < n_out) out[i * X2] = fast::vscale(v, scale);
   };
   fast::fft_line_pair<P, INV, HALF && !INV, HALF && INV>(t, fsm4 + p, PAIRS, a.tw + P::N, loadg, storeg);
+}
+
+// Inverse row pass + SENSE coil combination (the last pass of the SENSE adjoint):
+//   image[b, row, :] = scale * conj(scaling[row, :]) * sum_c conj(smaps[b, c, row, :]) * IFFT_x(in[b, c, row, :])[:n_out]
+// CTA = one image row x 2*LP coils.  The LP pair sums meet in shared memory; when the coils span several
+// CTAs each writes its partial row to scratch and the CTA that arrives last (one atomic ticket per row) adds
+// the partial rows in coil-group order -- a fixed summation order, so the result is bit-reproducible.
+template <class P, bool HALF>
+__global__ void __launch_bounds__(FastCfg<P>::ROW_THREADS, FastCfg<P>::ROW_MINB) k_fft_rows_sense(RowArgs a) {
+  extern __shared__ __align__(16) float4 fsm4[];
+  constexpr int LP = FastCfg<P>::LP, NT = FastCfg<P>::ROW_THREADS;
+  __shared__ int s_last;
+  const int n_in = a.n_in, n_out = a.n_out;
+  float2 *red = reinterpret_cast<float2 *>(fsm4 + LP * P::NP);  // [LP][n_out] pair sums
+  const int lp = threadIdx.x / P::T, t = threadIdx.x - lp * P::T;
+  const uint32_t G = (uint32_t)a.coil_groups, rpi = (uint32_t)a.rows_per_img, C = (uint32_t)a.C;
+  const uint32_t br = blockIdx.x / G, g = blockIdx.x - br * G;  // (batch, row), coil group
+  const uint32_t b = br / rpi, row = br - b * rpi;
+  const uint32_t cA = (g * LP + lp) * 2, cB = cA + 1;
+  const bool onA = cA < C, onB = cB < C;
+  const uint32_t bs = a.Bs == 1 ? 0u : b;
+  const float2 *inA = a.in + ((b * C + (onA ? cA : 0u)) * rpi + row) * (uint32_t)n_in;
+  const float2 *inB = a.in + ((b * C + (onB ? cB : 0u)) * rpi + row) * (uint32_t)n_in;
+  const float2 *smA = a.smaps + ((bs * C + (onA ? cA : 0u)) * rpi + row) * (uint32_t)n_out;
+  const float2 *smB = a.smaps + ((bs * C + (onB ? cB : 0u)) * rpi + row) * (uint32_t)n_out;
+  auto loadg = [&](int i) -> float4 {
+    float4 v = fast::v4(0.f, 0.f, 0.f, 0.f);
+    if (i < n_in) {
+      if (onA) { const float2 x = inA[i]; v.x = x.x; v.y = x.y; }
+      if (onB) { const float2 x = inB[i]; v.z = x.x; v.w = x.y; }
+    }
+    return v;
+  };
+  auto storeg = [&](int i, float4 v) {
+    if (i >= n_out) return;
+    float2 p = f2(0.f, 0.f);
+    if (onA) { const float2 m = smA[i]; p = f2(fmaf(v.x, m.x, v.y * m.y), fmaf(v.y, m.x, -(v.x * m.y))); }
+    if (onB) { const float2 m = smB[i]; p = f2(p.x + fmaf(v.z, m.x, v.w * m.y), p.y + fmaf(v.w, m.x, -(v.z * m.y))); }
+    red[lp * n_out + i] = p;
+  };
+  fast::fft_line_pair<P, true, false, HALF>(t, fsm4 + lp * P::NP, 1, a.tw + P::N, loadg, storeg);
+  __syncthreads();
+  const float2 *sc = a.scaling ? a.scaling + row * (uint32_t)n_out : nullptr;
+  float2 *out = a.out + br * (uint32_t)n_out;
+  auto finish = [&](int j, float2 sum) {
+    if (sc) sum = cmul2(sum, f2(sc[j].x, -sc[j].y));
+    out[j] = f2(sum.x * a.scale, sum.y * a.scale);
+  };
+  float2 *mine = a.partial + ((size_t)g * gridDim.x / G + br) * (uint32_t)n_out;  // [G][B*rows][n_out]
+  for (int j = threadIdx.x; j < n_out; j += NT) {
+    float2 sum = red[j];
+#pragma unroll
+    for (int q = 1; q < LP; ++q) sum = cadd(sum, red[q * n_out + j]);
+    if (G == 1) finish(j, sum);
+    else __stcg(&mine[j], sum);
+  }
+  if (G == 1) return;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = atomicAdd(&a.counter[br], 1u) == G - 1;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  for (int j = threadIdx.x; j < n_out; j += NT) {
+    float2 sum = __ldcg(&a.partial[(size_t)br * (uint32_t)n_out + j]);
+    for (uint32_t q = 1; q < G; ++q) sum = cadd(sum, __ldcg(&a.partial[((size_t)q * gridDim.x / G + br) * (uint32_t)n_out + j]));
+    finish(j, sum);
+  }
+  if (threadIdx.x == 0) a.counter[br] = 0;  // leave the counters zero for the next call
 }
 
 // staged twiddle tables of the fast plans: entry e = exp(-2 pi i r k / period)
@@ -452,6 +531,28 @@ template <class P, bool INV> static int launch_cols_fast(ColArgs &a, cudaStream_
   return half ? launch_cols_fast_h<P, INV, true>(a, st) : launch_cols_fast_h<P, INV, false>(a, st);
 }
 
+template <class P, bool HALF> static int launch_rows_sense_h(RowArgs &a, int64_t B, cudaStream_t st) {
+  using Cfg = FastCfg<P>;
+  a.coil_groups = (int)ceil_div(a.C, 2 * Cfg::LP);
+  const int64_t rows = B * a.rows_per_img;
+  const size_t smem = sizeof(float4) * (size_t)Cfg::LP * P::NP + sizeof(float2) * (size_t)Cfg::LP * a.n_out;
+  auto kern = k_fft_rows_sense<P, HALF>;
+  B2N_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (a.coil_groups > 1) B2N_CUDA_OK(cudaMemsetAsync(a.counter, 0, sizeof(unsigned int) * (size_t)rows, st));
+  kern<<<(unsigned)(rows * a.coil_groups), Cfg::ROW_THREADS, smem, st>>>(a);
+  B2N_LAUNCH_OK("k_fft_rows_sense");
+  return 0;
+}
+// returns -1 when the length has no compile-time plan (caller takes the unfused route)
+static int launch_rows_sense(RowArgs &a, int64_t B, cudaStream_t st) {
+  if (!g_fast_fft) return -1;
+  const bool half = 2 * a.n_out <= a.st.n;
+  B2N_FAST_PLAN_SWITCH(a.st.n,
+                       return (half ? launch_rows_sense_h<P, true>(a, B, st) : launch_rows_sense_h<P, false>(a, B, st)),
+                       (void)0)
+  return -1;
+}
+
 static bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 template <bool INV, int MODE> static int launch_rows(RowArgs &a, cudaStream_t st) {
@@ -518,7 +619,7 @@ static int make_fused_geom(int ndim, const int64_t *im_size, const int64_t *grid
 
 // scratch: T1 [B*C][N0..N_{d-2}][K_last] (ndim > 1), T2 [B*C][N0][K1][K2] (3-D), T3 [B*C][prod N] (adjoint
 // with smaps: cropped, un-combined image before the coil sum)
-static void fused_work_layout(const FusedGeom &g, size_t *t1, size_t *t2, size_t *t3) {
+static void fused_work_layout(const FusedGeom &g, size_t *t1, size_t *t2, size_t *t3, size_t *cnt = nullptr) {
   size_t e1 = (size_t)g.B * g.C * g.K[g.ndim - 1];
   for (int d = 0; d < g.ndim - 1; ++d) e1 *= g.N[d];
   if (g.ndim == 1) e1 = 0;
@@ -528,6 +629,10 @@ static void fused_work_layout(const FusedGeom &g, size_t *t1, size_t *t2, size_t
   *t1 = e1;
   *t2 = e2;
   *t3 = e3;
+  // per-image-row arrival counters of k_fft_rows_sense (4-byte, in float2 slots), behind T3
+  size_t rows = (size_t)g.B;
+  for (int d = 0; d < g.ndim - 1; ++d) rows *= g.N[d];
+  if (cnt) *cnt = (rows + 1) / 2;
 }
 
 static int fused_forward(const FusedGeom &g, const float2 *image, int64_t Ci, const float2 *smaps, int64_t Bs,
@@ -665,8 +770,22 @@ static int fused_adjoint(const FusedGeom &g, const float2 *grid, const float2 *k
     r.scale = scale;
     return launch_rows<true, ROW_PLAIN>(r, st);
   }
-  // SENSE: cropped per-coil rows to scratch, then one pass multiplies conj(smaps) * conj(scaling)
+  // SENSE, compile-time planned length: coil combination fused into the row pass (T3 holds the partial rows)
+  r.out = image;
+  r.smaps = smaps;
+  r.Bs = (int)Bs;
+  r.scaling = scaling;
+  r.scale = scale;
+  r.partial = T3;
+  r.counter = reinterpret_cast<unsigned int *>(T3 + t3e);
+  {
+    const int rc = launch_rows_sense(r, g.B, st);
+    if (rc >= 0) return rc;
+  }
+  // otherwise: cropped per-coil rows to scratch, then one pass multiplies conj(smaps) * conj(scaling)
   // and sums the coils (every line of the row pass stays independent: full parallelism)
+  r.smaps = nullptr;
+  r.scaling = nullptr;
   r.out = T3;
   r.scale = 1.f;
   int rc = launch_rows<true, ROW_PLAIN>(r, st);
@@ -704,9 +823,9 @@ extern "C" int b2n_fft_work_bytes(int ndim, const int64_t *im_size, const int64_
   int rc = make_fused_geom(ndim, im_size, grid_size, n_batch, n_coils, nullptr, &g);
   if (rc) return rc;
   if (!bytes) return fail_arg(B2N_E_ARG, "bytes is NULL");
-  size_t t1, t2, t3;
-  fused_work_layout(g, &t1, &t2, &t3);
-  *bytes = sizeof(float2) * (t1 + t2 + t3);
+  size_t t1, t2, t3, cnt;
+  fused_work_layout(g, &t1, &t2, &t3, &cnt);
+  *bytes = sizeof(float2) * (t1 + t2 + t3 + cnt);
   return 0;
 }
 
