@@ -189,8 +189,8 @@ B2N_API int b2n_spectrum_mul(int dtype, void *spectrum_dev, const void *kernel_d
  *             multiply on the way in) in ndim passes.
  * b2n_fft_supported(n): 0 = not handled; 1 = length n factors into {2,3,5,7,11,13} and is <= 8192 (run-time
  * Stockham passes); 2 = n also has a compile-time plan (register-resident passes, the fast path).
- * work_dev: device scratch of b2n_fft_work_bytes() bytes (intermediate, partially
- * transformed arrays); not needed for ndim == 1.
+ * work_dev: device scratch of b2n_fft_work_bytes() bytes (intermediate, partially transformed arrays, per-coil-group
+ * partial rows and arrival counters of the fused coil sum); the forward does not need it for ndim == 1.
  * reference: fft_and_scale / ifft_and_scale / fft_filter, _nufft/fft.py:36-173. */
 B2N_API int b2n_fft_supported(int64_t n);
 /* Fill a caller buffer of 2*n complex64 entries: [0, n) = exp(-2 pi i t / n) (computed in double), [n, 2n) = the

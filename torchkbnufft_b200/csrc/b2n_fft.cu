@@ -6,8 +6,8 @@
 // coil sum are further passes (modules/kbnufft.py:182-183, :404-405).  With cuFFT that was
 // 4-5 full passes over the K-grid per direction (measured 70-95 us each way at BASELINE
 // config 2, profiles/r01_d).  Here the transform is done one dimension per pass by our own
-// shared-memory Stockham kernels (b2n_fft_core.cuh), which lets every pass skip what the
-// zero-padding / cropping makes redundant and fuse the element-wise work:
+// kernels, which lets every pass skip what the zero-padding / cropping makes redundant and
+// fuse the element-wise work:
 //   forward : rows  -- read image*smaps*scaling (N_x values), FFT_x            -> T [.., N_y, K_x]
 //             cols  -- read N_y rows only,                    FFT_y            -> grid [.., K_y, K_x]
 //   adjoint : cols  -- read the grid, IFFT_y, keep the first N_y rows           -> T [.., N_y, K_x]
@@ -17,9 +17,15 @@
 // (fft.py:121-173) is the forward passes, the inverse passes with the kernel multiply fused
 // into the first inverse pass's loads, and no separate multiply pass.
 //
-// Row pass: a CTA transforms L contiguous lines; column pass: a CTA transforms 8 adjacent
-// columns (64-byte global segments), shared layout [element][column].  Ping-pong buffers,
-// one __syncthreads per stage; the first stage loads from global, the last stores to global.
+// Two sets of passes:
+//  * compile-time planned (b2n_fft_fast.cuh; lengths 64 ... 1024 that 2x-oversampled imaging uses):
+//    k_fft_rows_fast / k_fft_cols_fast / k_fft_rows_sense -- register-resident butterflies, two lines
+//    per thread, one shared exchange buffer.  46 / 51 us per direction at BASELINE config 2
+//    (profiles/r01_g), the default whenever every grid length has a plan;
+//  * run-time Stockham (b2n_fft_core.cuh; any length <= 8192 with prime factors <= 13): k_fft_rows /
+//    k_fft_cols -- a CTA transforms 4 contiguous lines / 8 adjacent columns through ping-pong shared
+//    buffers, one __syncthreads per stage.  Slower than cuFFT (116 / 132 us), kept for lengths
+//    without a plan inside a mixed transform and for A/B runs.
 // Sizes with a prime factor > 13 are not handled (the Python layer then uses cuFFT).
 #include "b2n_common.cuh"
 #include "b2n_fft_core.cuh"
