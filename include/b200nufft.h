@@ -102,7 +102,8 @@ typedef struct b2n_points {
 
 /* engine options (process-wide; for A/B measurements and tests) */
 enum b2n_option {
-  B2N_OPT_TILED_KERNELS = 0, /* 1 (default): use the shared-memory tiled kernels where they apply */
+  B2N_OPT_TILED_KERNELS = 0, /* 1 (default): shared-memory tiled kernels where they apply and pay off (not for a single
+                                2-D (batch, coil) row); 2: wherever they apply; 0: per-point kernels only */
   B2N_OPT_ADJ_ROW_OWNERSHIP = 1, /* tiled 2-D adjoint variant: 0 (default) auto = warp-owned tile rows for 16-coil CTAs,
                                     warp-private 8-coil tiles otherwise; 1 warp-owned rows, 2 warp-owned coils,
                                     3 warp-private tiles, 4 / 5 warp-owned rows with 4 / 2 warps per CTA

@@ -274,6 +274,82 @@ def test_cfg4_shape_3d_properties_reduced():
             tkbn.set_adjoint_mode("atomic")
 
 
+def _inner(a, b):
+    return torch.sum(a.to(torch.complex128).conj() * b.to(torch.complex128))
+
+
+def test_cfg3_full_size_toeplitz_properties():
+    """BASELINE config 3 (384^2, 32 coils, ToepNufft) at full size through size-independent
+    properties: the Toeplitz normal operator equals A^H A, is Hermitian and linear; A and A^H are
+    adjoint.  A sub-sampled slice of the forward is checked against the oracle."""
+    wl = workloads.WORKLOADS["cfg3"]
+    image, smaps, kdata, omega = workloads.make_inputs(wl, seed=0)
+    x, s, y, om = dev(image), dev(smaps), dev(kdata), dev(omega)
+    nu = tkbn.KbNufft(im_size=wl.im_size, dtype=torch.complex64).to(DEV)
+    na = tkbn.KbNufftAdjoint(im_size=wl.im_size, dtype=torch.complex64).to(DEV)
+    toep = tkbn.ToepNufft()
+    kern = tkbn.calc_toeplitz_kernel(om, wl.im_size, norm="ortho")
+    ax = nu(x, om, smaps=s, norm="ortho")
+    normal = na(ax, om, smaps=s, norm="ortho")
+    tx = toep(x, kern, smaps=s, norm="ortho")
+    assert rel_l2(host(tx), host(normal)) <= 1e-4
+    x2 = dev(workloads.complex_normal(np.random.default_rng(9), image.shape))
+    tx2 = toep(x2, kern, smaps=s, norm="ortho")
+    assert float(abs(_inner(tx, x2) - _inner(x, tx2)) / abs(_inner(tx, x2))) <= 1e-4  # T = T^H
+    assert rel_l2(host(toep(x - 0.5 * x2, kern, smaps=s, norm="ortho")), host(tx - 0.5 * tx2)) <= 1e-5
+    assert float(abs(_inner(ax, y) - _inner(x, na(y, om, smaps=s, norm="ortho"))) / abs(_inner(ax, y))) <= 1e-5
+    # first 4 coils x every 7th sample against the oracle (the full 32-coil oracle run takes too long here)
+    tables = [host(t) for t in nu.tables]
+    J, L, ns = nu.numpoints.tolist(), nu.table_oversamp.tolist(), host(nu.n_shift)
+    sub = np.ascontiguousarray(omega[:, ::7])
+    want = orc.nufft_forward(image, sub, tables, ns, J, L, host(nu.scaling_coef), wl.im_size, wl.grid_size,
+                             smaps=smaps[:, :4], nthreads=os.cpu_count() or 1, norm="ortho")
+    assert rel_l2(host(ax)[:, :4, ::7], want) <= 1e-5
+
+
+def test_cfg4_full_size_3d_properties():
+    """BASELINE config 4 (128^3, 8 coils, M = 8 388 608) at full size: adjointness, linearity,
+    atomic run-to-run agreement and the autograd backward of 0.5*|Ax|^2 = A^H A x."""
+    wl = workloads.WORKLOADS["cfg4"]
+    image, smaps, kdata, omega = workloads.make_inputs(wl, seed=0)
+    x, s, y, om = dev(image), dev(smaps), dev(kdata), dev(omega)
+    nu = tkbn.KbNufft(im_size=wl.im_size, dtype=torch.complex64).to(DEV)
+    na = tkbn.KbNufftAdjoint(im_size=wl.im_size, dtype=torch.complex64).to(DEV)
+    ax = nu(x, om, smaps=s)
+    ahy = na(y, om, smaps=s)
+    assert float(abs(_inner(ax, y) - _inner(x, ahy)) / abs(_inner(ax, y))) <= 1e-5
+    x2 = dev(workloads.complex_normal(np.random.default_rng(4), image.shape))
+    assert rel_l2(host(nu(x + 3.0 * x2, om, smaps=s)), host(ax + 3.0 * nu(x2, om, smaps=s))) <= 1e-5
+    assert rel_l2(host(na(y, om, smaps=s)), host(ahy)) <= 1e-6  # atomic order differs, values agree
+    xg = x.clone().requires_grad_(True)
+    out = nu(xg, om, smaps=s)
+    (out.abs() ** 2 / 2).sum().backward()
+    assert rel_l2(host(xg.grad), host(na(ax, om, smaps=s))) <= 1e-5
+    # a random subset of samples against a direct per-sample evaluation of the oracle on the same grid
+    pick = np.random.default_rng(11).choice(wl.n_points, size=4096, replace=False)
+    tables = [host(t) for t in nu.tables]
+    J, L, ns = nu.numpoints.tolist(), nu.table_oversamp.tolist(), host(nu.n_shift)
+    want = orc.nufft_forward(image, np.ascontiguousarray(omega[:, pick]), tables, ns, J, L, host(nu.scaling_coef),
+                             wl.im_size, wl.grid_size, smaps=smaps, nthreads=os.cpu_count() or 1)
+    assert rel_l2(host(ax)[..., pick], want) <= 1e-5
+
+
+def test_cfg5_one_gpu_share_batch_consistency():
+    """BASELINE config 5, the 8 slices x 16 coils one GPU owns under 8-way batch sharding: the
+    batched calls equal slice-by-slice calls, forward and adjoint, and are mutually adjoint."""
+    wl = workloads.WORKLOADS["cfg5"]
+    image, smaps, kdata, omega = workloads.make_inputs(wl, seed=0, n_batch=8)
+    x, s, y, om = dev(image), dev(smaps), dev(kdata), dev(omega)
+    nu = tkbn.KbNufft(im_size=wl.im_size, dtype=torch.complex64).to(DEV)
+    na = tkbn.KbNufftAdjoint(im_size=wl.im_size, dtype=torch.complex64).to(DEV)
+    ax, ahy = nu(x, om, smaps=s), na(y, om, smaps=s)
+    for b in (0, 3, 7):
+        sb = s if s.shape[0] == 1 else s[b:b + 1]
+        assert rel_l2(host(nu(x[b:b + 1], om, smaps=sb)), host(ax[b:b + 1])) <= 1e-6
+        assert rel_l2(host(na(y[b:b + 1], om, smaps=sb)), host(ahy[b:b + 1])) <= 1e-5
+    assert float(abs(_inner(ax, y) - _inner(x, ahy)) / abs(_inner(ax, y))) <= 1e-5
+
+
 def test_edge_shapes():
     kw = dict(im_size=(8, 6), dtype=torch.complex64)
     interp, adj = tkbn.KbInterp(**kw).to(DEV), tkbn.KbInterpAdjoint(**kw).to(DEV)
@@ -344,7 +420,7 @@ def test_tiled_kernels_match_generic_and_oracle(grid_size, B, C, batched):
     want_a = orc.table_interp_adjoint(kdata, omega, tables, ns, J, L, grid_size)
     res = {}
     try:
-        for tiled in (True, False):
+        for tiled in ("force", False):
             tkbn.set_tiled_kernels(tiled)
             res[tiled] = (host(eng_interp.table_interp(dev(grid), dev(omega), *args)),
                           host(eng_interp.table_interp_adjoint(dev(kdata), dev(omega), *args, None, ob.grid_size,
@@ -368,11 +444,11 @@ def test_tiled_kernels_match_generic_and_oracle(grid_size, B, C, batched):
         finally:
             lib.b2n_set_option(_lib.OPT_FWD_COIL_CHUNK, 0)
         assert rel_l2(alt, want_f) <= 1e-5, f"forward variant {chunk}"
-    for tiled in (True, False):
+    for tiled in ("force", False):
         assert rel_l2(res[tiled][0], want_f) <= 1e-5, f"forward tiled={tiled}"
         assert rel_l2(res[tiled][1], want_a) <= 1e-4, f"adjoint tiled={tiled}"
-    assert rel_l2(res[True][0], res[False][0]) <= 2e-6
-    assert rel_l2(res[True][1], res[False][1]) <= 2e-6
+    assert rel_l2(res["force"][0], res[False][0]) <= 2e-6
+    assert rel_l2(res["force"][1], res[False][1]) <= 2e-6
 
 
 @pytest.mark.parametrize("N, K", [((24,), (40,)), ((19,), (64,)), ((16, 12), (32, 24)), ((13, 18), (26, 35)),
@@ -467,15 +543,15 @@ def test_tiled_3d_kernels_match_generic_and_oracle(grid_size, B, C, batched):
     want_a = orc.table_interp_adjoint(kdata, omega, tables, ns, J, L, grid_size, nthreads=4)
     res = {}
     try:
-        for tiled in (True, False):
+        for tiled in ("force", False):
             tkbn.set_tiled_kernels(tiled)
             res[tiled] = (host(eng_interp.table_interp(dev(grid), dev(omega), *args)),
                           host(eng_interp.table_interp_adjoint(dev(kdata), dev(omega), *args, None, ob.grid_size,
                                                                mode="atomic")))
     finally:
         tkbn.set_tiled_kernels(True)
-    for tiled in (True, False):
+    for tiled in ("force", False):
         assert rel_l2(res[tiled][0], want_f) <= 1e-5, f"forward tiled={tiled}"
         assert rel_l2(res[tiled][1], want_a) <= 1e-4, f"adjoint tiled={tiled}"
-    assert rel_l2(res[True][0], res[False][0]) <= 2e-6
-    assert rel_l2(res[True][1], res[False][1]) <= 2e-6
+    assert rel_l2(res["force"][0], res[False][0]) <= 2e-6
+    assert rel_l2(res["force"][1], res[False][1]) <= 2e-6

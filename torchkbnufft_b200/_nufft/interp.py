@@ -38,10 +38,12 @@ def get_adjoint_mode() -> str:
     return _default_adjoint_mode
 
 
-def set_tiled_kernels(enabled: bool) -> None:
-    """Enable (default) or disable the shared-memory tiled kernels; when disabled every
-    call takes the generic one-thread-per-(point, coil) kernels.  For A/B measurements."""
-    _lib.check(_lib.load().b2n_set_option(_lib.OPT_TILED_KERNELS, 1 if enabled else 0), "b2n_set_option")
+def set_tiled_kernels(enabled) -> None:
+    """``True`` (default): shared-memory tiled kernels where they apply and pay off (a single 2-D
+    (batch, coil) row goes to the per-point kernels, which are faster there); ``"force"``: tiled
+    wherever they apply; ``False``: per-point kernels only.  For A/B measurements and tests."""
+    value = 2 if enabled == "force" else (1 if enabled else 0)
+    _lib.check(_lib.load().b2n_set_option(_lib.OPT_TILED_KERNELS, value), "b2n_set_option")
 
 
 def get_tiled_kernels() -> bool:

@@ -241,6 +241,15 @@ extern int g_adj_chunk;
 extern int g_fast_fft;
 static int g_options[B2N_OPT_COUNT] = {1, 0, 0, 0, 1};
 
+// A single 2-D (batch, coil) row leaves 15/16 of a tiled CTA's coil lanes idle while the per-point cost stays the same:
+// the per-point kernels win there (22 vs 25 us gather, 38 vs 48 us spread at the geometry of BASELINE config 2,
+// profiles/r01_g_coil_sweep.log).  B2N_OPT_TILED_KERNELS = 2 forces the tiled kernels anyway.
+static bool use_tiled(const b2n_geom *geom, const b2n_points *pts, int64_t n_batch, int64_t n_coils) {
+  const int opt = g_options[B2N_OPT_TILED_KERNELS];
+  if (!opt || !pts) return false;
+  return opt == 2 || !(geom->ndim == 2 && n_batch * n_coils == 1);
+}
+
 }  // namespace b2n
 
 using namespace b2n;
@@ -271,7 +280,7 @@ extern "C" int b2n_interp_forward(const b2n_geom *geom, const b2n_points *pts, c
   if (!geom || !grid_dev || !kdata_dev) return fail_arg(B2N_E_ARG, "NULL geom/grid/kdata");
   if (grid_layout != B2N_COIL_MAJOR && grid_layout != B2N_CHANNEL_LAST) return fail_arg(B2N_E_ARG, "bad layout");
   cudaStream_t st = (cudaStream_t)stream;
-  if (g_options[B2N_OPT_TILED_KERNELS] && pts) {
+  if (use_tiled(geom, pts, n_batch, n_coils)) {
     int rc = tiled_forward(geom, pts, grid_dev, n_batch, n_coils, grid_layout, kdata_dev, st);
     if (rc != 1) return rc;  // 1 = not eligible, use the generic kernel
     rc = tiled3_forward(geom, pts, grid_dev, n_batch, n_coils, grid_layout, kdata_dev, st);
@@ -288,7 +297,7 @@ extern "C" int b2n_interp_adjoint(const b2n_geom *geom, const b2n_points *pts, c
   if (grid_layout != B2N_COIL_MAJOR && grid_layout != B2N_CHANNEL_LAST) return fail_arg(B2N_E_ARG, "bad layout");
   if (mode != B2N_ADJ_ATOMIC && mode != B2N_ADJ_SORTED) return fail_arg(B2N_E_ARG, "bad adjoint mode %d", mode);
   cudaStream_t st = (cudaStream_t)stream;
-  if (g_options[B2N_OPT_TILED_KERNELS] && pts && mode == B2N_ADJ_ATOMIC) {
+  if (use_tiled(geom, pts, n_batch, n_coils) && mode == B2N_ADJ_ATOMIC) {
     int rc = tiled_adjoint(geom, pts, kdata_dev, n_batch, n_coils, grid_layout, grid_dev, st);
     if (rc != 1) return rc;
     rc = tiled3_adjoint(geom, pts, kdata_dev, n_batch, n_coils, grid_layout, grid_dev, st);
