@@ -159,7 +159,7 @@ __global__ void __launch_bounds__(kThreads, 3) k_fwd_tiled_2d(InterpArgs<float> 
   const int qy = lane_on ? q / QX : 0, qx = lane_on ? q - (q / QX) * QX : 0;
   const float2 *tplane = tile + c * kPS + qy * kSX + qx;
   float2 *out = kdata + (int64_t)(sp.b * C + sp.c0 + c) * a.M;
-  const bool store = q == 0 && sp.c0 + c < C;
+  const bool store = q < 2 && sp.c0 + c < C;
   // PU points per warp iteration: their shared-memory loads are independent, which gives the
   // scheduler the ILP that one point alone (a chain LDS -> FFMA -> FFMA -> SHFL) lacks
   constexpr int PU = 2;
@@ -172,8 +172,18 @@ __global__ void __launch_bounds__(kThreads, 3) k_fwd_tiled_2d(InterpArgs<float> 
       const float2 *rec = s_coef + i * kNC;
       // this lane's weights: cy[jy] for jy = ny*QY + qy, cx[jx] for jx = nx*QX + qx
       float2 cy[NY], cx[NX];
+      if (QY == 1) {  // every lane needs all six: three 16-byte broadcast loads instead of six 8-byte ones
+        const float4 *r4 = reinterpret_cast<const float4 *>(rec);
 #pragma unroll
-      for (int ny = 0; ny < NY; ++ny) cy[ny] = rec[ny * QY + qy];
+        for (int k = 0; k < NY / 2; ++k) {
+          const float4 w = r4[k];
+          cy[2 * k] = make_float2(w.x, w.y);
+          cy[2 * k + 1] = make_float2(w.z, w.w);
+        }
+      } else {
+#pragma unroll
+        for (int ny = 0; ny < NY; ++ny) cy[ny] = rec[ny * QY + qy];
+      }
 #pragma unroll
       for (int nx = 0; nx < NX; ++nx) cx[nx] = rec[kJ + nx * QX + qx];
       const float2 *t0 = tplane + (bs.x - sp.y0) * kSX + (bs.y - sp.x0);
@@ -208,7 +218,15 @@ __global__ void __launch_bounds__(kThreads, 3) k_fwd_tiled_2d(InterpArgs<float> 
           acc[u].y += __shfl_xor_sync(0xffffffffu, acc[u].y, off);
         }
       }
-      if (store && i0 + u < sp.count) out[s_perm[i0 + u]] = acc[u];
+    }
+    // after the reduction every lane of a coil holds the sums: lane slot q stores point i0 + q, so ONE store
+    // instruction covers PU (mostly k-space-adjacent) samples of each coil -- half the L1 wavefronts of a
+    // store per point
+    static_assert(PU == 2 && Q >= PU, "store mapping");
+    {
+      const int iu = i0 + (q == 1 ? 1 : 0);
+      const float2 mine = q == 1 ? acc[1] : acc[0];
+      if (store && iu < sp.count) out[s_perm[iu]] = mine;
     }
   }
   if (a.trace) {
