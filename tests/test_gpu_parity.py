@@ -555,3 +555,32 @@ def test_tiled_3d_kernels_match_generic_and_oracle(grid_size, B, C, batched):
         assert rel_l2(res[tiled][1], want_a) <= 1e-4, f"adjoint tiled={tiled}"
     assert rel_l2(res["force"][0], res[False][0]) <= 2e-6
     assert rel_l2(res["force"][1], res[False][1]) <= 2e-6
+
+
+def test_cuda_graph_capture_of_forward_adjoint_pair():
+    """with the trajectory plan cached, a forward+adjoint SENSE pair is pure
+    stream work (no synchronisation, no host reads) and can be captured in a CUDA graph and replayed
+    on new input contents."""
+    wl = workloads.Workload("g", (64, 64), 5, 1, 40, 128, "golden", "graph capture case")
+    image, smaps, kdata, omega = workloads.make_inputs(wl, seed=2)
+    x, s, om = dev(image), dev(smaps), dev(omega)
+    nu = tkbn.KbNufft(im_size=wl.im_size, dtype=torch.complex64).to(DEV)
+    na = tkbn.KbNufftAdjoint(im_size=wl.im_size, dtype=torch.complex64).to(DEV)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):  # warm-up on the capture stream: plan, twiddles, function attributes
+        for _ in range(2):
+            na(nu(x, om, smaps=s), om, smaps=s)
+    torch.cuda.current_stream().wait_stream(side)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph, stream=side):
+        k = nu(x, om, smaps=s)
+        im = na(k, om, smaps=s)
+    for seed in (7, 8):
+        x.copy_(dev(workloads.complex_normal(np.random.default_rng(seed), image.shape)))
+        graph.replay()
+        torch.cuda.synchronize()
+        want_k = nu(x, om, smaps=s)
+        want_im = na(want_k, om, smaps=s)
+        assert rel_l2(host(k), host(want_k)) <= 1e-6
+        assert rel_l2(host(im), host(want_im)) <= 1e-5

@@ -21,7 +21,7 @@ import torch
 from torch import Tensor
 
 from .. import _lib
-from .plan import current_stream_ptr, engine_dtype, host_ints, require_cuda
+from .plan import current_stream_ptr, device_guard, engine_dtype, host_ints, require_cuda
 
 
 def check_norm(norm: Optional[str]) -> bool:
@@ -61,7 +61,7 @@ def apod_pad(image: Tensor, grid_size: Sequence[int], smaps: Optional[Tensor] = 
         return out
     if scaling_coef is not None:
         scaling_coef = scaling_coef.contiguous()
-    with torch.cuda.device(image.device):
+    with device_guard(image.device):
         _lib.check(
             lib.b2n_apod_pad(len(im_size), engine_dtype(image.dtype), _lib.i64_array(im_size), _lib.i64_array(grid_size),
                              B, C, image.data_ptr(), Ci, smaps.data_ptr() if smaps is not None else None, Bs,
@@ -95,7 +95,7 @@ def crop_apod_coilsum(grid: Tensor, im_size: Sequence[int], smaps: Optional[Tens
         return out
     if scaling_coef is not None:
         scaling_coef = scaling_coef.contiguous()
-    with torch.cuda.device(grid.device):
+    with device_guard(grid.device):
         _lib.check(
             lib.b2n_crop_apod_coilsum(len(im_size), engine_dtype(grid.dtype), _lib.i64_array(im_size),
                                       _lib.i64_array(grid_size), B, C, grid.data_ptr(), layout,
@@ -118,7 +118,7 @@ def spectrum_mul_(spectrum: Tensor, kernel: Tensor, scale: float = 1.0, layout: 
     kb = kernel.numel() // max(n_grid, 1)
     if spectrum.numel() == 0:
         return spectrum
-    with torch.cuda.device(spectrum.device):
+    with device_guard(spectrum.device):
         _lib.check(
             _lib.load().b2n_spectrum_mul(engine_dtype(spectrum.dtype), spectrum.data_ptr(), kernel.data_ptr(), B, C,
                                          n_grid, kb, layout, float(scale), current_stream_ptr(spectrum.device)),
@@ -175,29 +175,45 @@ def fused_fft_available(dtype: torch.dtype, grid_size: Sequence[int]) -> bool:
 _TWIDDLES: dict = {}
 
 
+_TWIDDLE_SETS: dict = {}
+
+
 def _twiddles(grid_size, device):
     """Per-(device, length) twiddle tables (2n entries: plain table + the staged tables of the
-    compile-time plan, see ``b2n_fft_twiddles``), built once on the device."""
+    compile-time plan, see ``b2n_fft_twiddles``), built once on the device; returns the tables
+    and the ``void*[ndim]`` argument (cached per size tuple)."""
+    key = (device.index, tuple(grid_size))
+    hit = _TWIDDLE_SETS.get(key)
+    if hit is not None:
+        return hit
     lib = _lib.load()
     tabs = []
     for n in grid_size:
-        key = (device.index, int(n))
-        t = _TWIDDLES.get(key)
+        tkey = (device.index, int(n))
+        t = _TWIDDLES.get(tkey)
         if t is None:
             t = torch.zeros(2 * int(n), dtype=torch.complex64, device=device)
-            with torch.cuda.device(device):
+            with device_guard(device):
                 _lib.check(lib.b2n_fft_twiddles(int(n), t.data_ptr(), current_stream_ptr(device)), "b2n_fft_twiddles")
-            _TWIDDLES[key] = t
+            _TWIDDLES[tkey] = t
         tabs.append(t)
     ptrs = (ctypes.c_void_p * len(tabs))(*[t.data_ptr() for t in tabs])
+    _TWIDDLE_SETS[key] = (tabs, ptrs)
     return tabs, ptrs
 
 
+_WORK_BYTES: dict = {}
+
+
 def _fft_work(im_size, grid_size, B, C, device) -> Optional[Tensor]:
-    nbytes = ctypes.c_size_t(0)
-    _lib.check(_lib.load().b2n_fft_work_bytes(len(im_size), _lib.i64_array(im_size), _lib.i64_array(grid_size), B, C,
-                                              ctypes.byref(nbytes)), "b2n_fft_work_bytes")
-    return torch.empty(int(nbytes.value), dtype=torch.uint8, device=device) if nbytes.value else None
+    key = (tuple(im_size), tuple(grid_size), B, C)
+    n = _WORK_BYTES.get(key)
+    if n is None:
+        nbytes = ctypes.c_size_t(0)
+        _lib.check(_lib.load().b2n_fft_work_bytes(len(im_size), _lib.i64_array(im_size), _lib.i64_array(grid_size), B, C,
+                                                  ctypes.byref(nbytes)), "b2n_fft_work_bytes")
+        n = _WORK_BYTES[key] = int(nbytes.value)
+    return torch.empty(n, dtype=torch.uint8, device=device) if n else None
 
 
 def fused_fft_forward(image: Tensor, grid_size: Sequence[int], smaps: Optional[Tensor] = None,
@@ -222,7 +238,7 @@ def fused_fft_forward(image: Tensor, grid_size: Sequence[int], smaps: Optional[T
         scaling_coef = scaling_coef.contiguous()
     work = _fft_work(im_size, grid_size, B, C, image.device)
     _tabs, tw = _twiddles(grid_size, image.device)
-    with torch.cuda.device(image.device):
+    with device_guard(image.device):
         _lib.check(
             _lib.load().b2n_fft_forward_fused(
                 len(im_size), _lib.i64_array(im_size), _lib.i64_array(grid_size), B, C, image.data_ptr(), Ci,
@@ -260,7 +276,7 @@ def fused_fft_adjoint(grid: Tensor, im_size: Sequence[int], smaps: Optional[Tens
         kb = kernel.shape[0] if kernel.ndim > len(grid_size) else 1
     work = _fft_work(im_size, grid_size, B, C, grid.device)
     _tabs, tw = _twiddles(grid_size, grid.device)
-    with torch.cuda.device(grid.device):
+    with device_guard(grid.device):
         _lib.check(
             _lib.load().b2n_fft_adjoint_fused(
                 len(im_size), _lib.i64_array(im_size), _lib.i64_array(grid_size), B, C, grid.data_ptr(),

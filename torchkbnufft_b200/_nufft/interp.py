@@ -18,7 +18,7 @@ import torch
 from torch import Tensor
 
 from .. import _lib
-from .plan import current_stream_ptr, get_geometry, get_plan, normalize_omega, require_cuda
+from .plan import current_stream_ptr, device_guard, get_geometry, get_plan, normalize_omega, require_cuda
 
 ADJOINT_MODES = {"atomic": _lib.ADJ_ATOMIC, "sorted": _lib.ADJ_SORTED}
 _default_adjoint_mode = os.environ.get("B200NUFFT_ADJOINT_MODE", "atomic")
@@ -122,7 +122,7 @@ def table_interp(
     out = torch.empty((B, C, plan.n_points), dtype=image.dtype, device=image.device)
     if out.numel() == 0:
         return out
-    with torch.cuda.device(image.device):
+    with device_guard(image.device):
         stop = kernel_timer.bracket("interp_fwd", image.device) if kernel_timer is not None else None
         _lib.check(
             _lib.load().b2n_interp_forward(ctypes.byref(geo.struct), ctypes.byref(plan.struct), image.data_ptr(), B, C,
@@ -174,7 +174,7 @@ def table_interp_adjoint(
     if out.numel() == 0:
         return out
     mode_id = ADJOINT_MODES[_default_adjoint_mode if mode is None else mode]
-    with torch.cuda.device(data.device):
+    with device_guard(data.device):
         stop = kernel_timer.bracket("interp_adj", data.device) if kernel_timer is not None else None
         _lib.check(
             _lib.load().b2n_interp_adjoint(ctypes.byref(geo.struct), ctypes.byref(plan.struct), data.data_ptr(), B, C,
@@ -198,7 +198,7 @@ def export_indices(omega: Tensor, tables, n_shift, numpoints, table_oversamp, gr
     M = om.shape[1]
     arr_ind = torch.empty((geo.n_offsets, M), dtype=torch.int64, device=om.device)
     tab_idx = torch.empty((geo.n_offsets, geo.ndim, M), dtype=torch.int32, device=om.device)
-    with torch.cuda.device(om.device):
+    with device_guard(om.device):
         _lib.check(
             _lib.load().b2n_export_indices(ctypes.byref(geo.struct), om.data_ptr(), M, arr_ind.data_ptr(),
                                            tab_idx.data_ptr(), current_stream_ptr(om.device)),

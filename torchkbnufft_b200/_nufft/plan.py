@@ -44,7 +44,27 @@ def engine_dtype(cdtype: torch.dtype) -> int:
 
 
 def current_stream_ptr(device: torch.device) -> ctypes.c_void_p:
-    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+    index = device.index if device.index is not None else torch.cuda.current_device()
+    return ctypes.c_void_p(torch._C._cuda_getCurrentRawStream(index))
+
+
+class _NoGuard:
+    def __enter__(self):
+        return None
+
+    def __exit__(self, *exc):
+        return False
+
+
+_NO_GUARD = _NoGuard()
+
+
+def device_guard(device: torch.device):
+    """``torch.cuda.device(device)`` only when ``device`` is not already current (the guard costs
+    several microseconds of host time per call, which matters next to 20-100 us kernels)."""
+    if device.index is None or device.index == torch.cuda.current_device():
+        return _NO_GUARD
+    return torch.cuda.device(device)
 
 
 def _tkey(t: Tensor) -> tuple:
@@ -148,7 +168,7 @@ class TrajectoryPlan:
                                                   ctypes.byref(nbytes)), "b2n_points_workspace_bytes")
         self.workspace = torch.empty(max(int(nbytes.value), 256), dtype=torch.uint8, device=omega.device)
         self.struct = _lib.Points()
-        with torch.cuda.device(omega.device):
+        with device_guard(omega.device):
             _lib.check(
                 lib.b2n_points_build(ctypes.byref(geo.struct), om.data_ptr(), self.n_points, self.n_traj,
                                      self.workspace.data_ptr(), self.workspace.numel(), ctypes.byref(self.struct),

@@ -11,8 +11,15 @@ from torch import Tensor
 from .._autograd.interp import KbTableInterpAdjoint, KbTableInterpForward
 from .._autograd.nufft import ApodPad, CropApodCoilsum, FusedFftAdjoint, FusedFftForward, ToeplitzFilter
 from .._nufft import fft as _fft
+from .._nufft import interp as _interp
 from .._nufft.plan import host_ints as _ints
 from .interp import _SPMAT_MSG, with_complex_view
+
+
+def _needs_grad(t: Tensor) -> bool:
+    """Whether autograd has to record this call; when it does not, the kernels are called directly --
+    the ``Function.apply`` round trip costs more host time than some of the kernels run."""
+    return torch.is_grad_enabled() and t.requires_grad
 
 
 def sense_nufft_forward(image: Tensor, smaps: Optional[Tensor], scaling_coef: Tensor, grid_size, omega: Tensor,
@@ -27,11 +34,16 @@ def sense_nufft_forward(image: Tensor, smaps: Optional[Tensor], scaling_coef: Te
         image, smaps = image * smaps, None  # general broadcast / d(smaps): plain torch multiply
     grid_size = _ints(grid_size)
     scale = _fft.ortho_scale(grid_size, normalized)
+    record = _needs_grad(image)
     if _fft.fused_fft_available(image.dtype, grid_size):
-        grid = FusedFftForward.apply(image, smaps, scaling_coef, grid_size, scale)
+        grid = (FusedFftForward.apply(image, smaps, scaling_coef, grid_size, scale) if record else
+                _fft.fused_fft_forward(image, grid_size, smaps, scaling_coef, scale))
     else:
-        grid = ApodPad.apply(image, smaps, scaling_coef, grid_size, scale)
+        grid = (ApodPad.apply(image, smaps, scaling_coef, grid_size, scale) if record else
+                _fft.apod_pad(image, grid_size, smaps, scaling_coef, scale))
         grid = _fft.fft_grid(grid, len(grid_size), inverse=False)
+    if not record:
+        return _interp.table_interp(grid, omega, tables, n_shift, numpoints, table_oversamp, offsets)
     return KbTableInterpForward.apply(grid, omega, tables, n_shift, numpoints, table_oversamp, offsets)
 
 
@@ -42,9 +54,15 @@ def sense_nufft_adjoint(data: Tensor, smaps: Optional[Tensor], scaling_coef: Ten
     SENSE coil combination fused into one kernel."""
     normalized = _fft.check_norm(norm)
     grid_sizes = _ints(grid_size)
-    grid = KbTableInterpAdjoint.apply(data, omega, tables, n_shift, numpoints, table_oversamp, offsets, grid_size)
     scale = _fft.ortho_scale(grid_sizes, normalized)
     fused = _fft.fused_fft_available(data.dtype, grid_sizes)
+    if not _needs_grad(data) and not (smaps is not None and smaps.requires_grad):
+        grid = _interp.table_interp_adjoint(data, omega, tables, n_shift, numpoints, table_oversamp, offsets, grid_size)
+        if fused:
+            return _fft.fused_fft_adjoint(grid, _ints(im_size), smaps, scaling_coef, scale)
+        grid = _fft.fft_grid(grid, len(grid_sizes), inverse=True)
+        return _fft.crop_apod_coilsum(grid, _ints(im_size), smaps, scaling_coef, scale)
+    grid = KbTableInterpAdjoint.apply(data, omega, tables, n_shift, numpoints, table_oversamp, offsets, grid_size)
     finish = FusedFftAdjoint if fused else CropApodCoilsum
     if not fused:
         grid = _fft.fft_grid(grid, len(grid_sizes), inverse=True)
