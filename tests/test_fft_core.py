@@ -53,7 +53,7 @@ def test_unsupported_sizes_are_rejected(n, hostfft):
     assert run(hostfft, np.ones(n, np.complex64), False)[0] == -1
 
 
-@pytest.mark.parametrize("n", [64, 128, 256, 320, 512, 640, 768, 1024])
+@pytest.mark.parametrize("n", [64, 96, 128, 192, 256, 320, 384, 512, 576, 640, 768, 1024, 1280, 2048])
 @pytest.mark.parametrize("half_in", [False, True])
 def test_compile_time_plans_match_numpy(n, half_in, hostfft):
     """b2n_fft_fast.cuh: index maps, staged twiddles and the pair butterflies (incl. radix 10, 12, 16),
@@ -76,6 +76,6 @@ def test_compile_time_plans_match_numpy(n, half_in, hostfft):
 
 
 def test_lengths_without_a_plan_use_the_runtime_passes(hostfft):
-    z = np.zeros(96, np.complex64)
+    z = np.zeros(100, np.complex64)
     p = z.ctypes.data_as(ctypes.c_void_p)
-    assert hostfft.host_fft_fast(96, 0, 0, p, p, p, p) == 0
+    assert hostfft.host_fft_fast(100, 0, 0, p, p, p, p) == 0

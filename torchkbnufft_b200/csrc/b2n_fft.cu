@@ -27,8 +27,7 @@
 //    buffers, one __syncthreads per stage.  Slower than cuFFT (116 / 132 us), kept for lengths
 //    without a plan inside a mixed transform and for A/B runs.
 // Sizes with a prime factor > 13 are not handled (the Python layer then uses cuFFT).
-#include "b2n_common.cuh"
-#include "b2n_fft_core.cuh"
+#include "b2n_fft_args.cuh"
 #include "b2n_fft_fast.cuh"
 
 namespace b2n {
@@ -40,29 +39,6 @@ constexpr int kRowsPerCta = 4;
 constexpr int kFftMaxN = 8192;
 
 B2N_HD int fft_pad(int i) { return i + (i >> 3); }  // 1 slot of padding per 8: stride-R stores stay conflict-free
-
-struct FftStages {
-  int n, n_stages, radix[kFftMaxStages];
-};
-
-enum RowMode { ROW_PLAIN = 0, ROW_FWD_FIRST = 1 };
-
-struct RowArgs {
-  FftStages st;
-  int n_in, n_out;       // nonzero inputs / kept outputs per line
-  int64_t lines;         // number of lines
-  int64_t rows_per_img;  // image rows per (batch, coil) = prod of the slower image dims
-  int C, Ci, Bs;         // coils, image coils (1 or C), smaps batch (1 or B)
-  const float2 *in;      // ROW_PLAIN: [lines][n_in]
-  float2 *out;           // [lines][n_out]
-  const float2 *image, *smaps, *scaling;  // ROW_FWD_FIRST operands
-  const float2 *tw;      // twiddle table exp(-2 pi i t / n), t < n (b2n_fft_twiddles)
-  float scale;
-  // k_fft_rows_sense only: coil groups per image row, per-group partial rows, per-row arrival counters
-  int coil_groups;
-  float2 *partial;
-  unsigned int *counter;
-};
 
 // One Stockham stage over this CTA's lines.  LOADF(line, i) / STOREF(line, i, v) access the
 // stage input / output (global memory in the first / last stage, shared memory otherwise).
@@ -207,18 +183,6 @@ __global__ void __launch_bounds__(kFftThreads, 3) k_fft_rows(RowArgs a) {
   }
 }
 
-struct ColArgs {
-  FftStages st;
-  int n_in, n_out;   // rows read / rows written along the transformed dimension
-  int64_t A, X;      // outer count, inner (contiguous) extent
-  const float2 *in;  // [A][n_in][X]
-  float2 *out;       // [A][n_out][X]
-  const float2 *mul; // optional [mul_batch][n][X] factor applied to the inputs (Toeplitz kernel)
-  int64_t a_per_mul; // outer indices per mul batch entry (0: single kernel)
-  const float2 *tw;  // twiddle table of length n
-  float scale;
-};
-
 // -----------------------------------------------------------------------------------------
 // column pass: 8 adjacent columns per CTA (64-byte global segments), 32 threads per column
 // -----------------------------------------------------------------------------------------
@@ -280,190 +244,6 @@ __global__ void __launch_bounds__(kColThreads, 2) k_fft_cols(ColArgs a) {
   }
 }
 
-// -----------------------------------------------------------------------------------------
-// fast passes: compile-time plans of b2n_fft_fast.cuh, two lines per thread
-// -----------------------------------------------------------------------------------------
-template <class P> struct FastCfg {
-  // row pass: LP line pairs per CTA (about 160 threads: small CTAs keep the last wave of a launch short -- a
-  // launch is typically 1-3 waves of resident line pairs); column pass: PAIRS column pairs per CTA
-  static constexpr int LP = P::T >= 160 ? 1 : 160 / P::T;
-  static constexpr int ROW_THREADS = LP * P::T;
-  static constexpr int PAIRS = P::T >= 64 ? 4 : 256 / P::T;
-  static constexpr int COL_THREADS = PAIRS * P::T;
-  // register budget: 64 per thread (128 for radix-16 butterflies on pairs) -> resident CTAs per SM
-  static constexpr int REG_THREADS = P::RMAX >= 16 ? 512 : 1024;
-  static constexpr int ROW_MINB = REG_THREADS / ROW_THREADS > 0 ? REG_THREADS / ROW_THREADS : 1;
-  static constexpr int COL_MINB = REG_THREADS / COL_THREADS > 0 ? REG_THREADS / COL_THREADS : 1;
-};
-
-B2N_D float2 row_operand(const float2 *in, const float2 *sm, const float2 *sc, int i, float scale) {
-  float2 v = in[i];
-  if (sm) v = cmul2(v, sm[i]);
-  if (sc) v = cmul2(v, sc[i]);
-  return f2(v.x * scale, v.y * scale);
-}
-
-// HALF: the padded half of the inputs (forward) / the cropped half of the outputs (inverse) is skipped at
-// compile time (n_in <= N/2 resp. n_out <= N/2, the 2x-oversampled case).
-template <class P, bool INV, int MODE, bool HALF>
-__global__ void __launch_bounds__(FastCfg<P>::ROW_THREADS, FastCfg<P>::ROW_MINB) k_fft_rows_fast(RowArgs a) {
-  extern __shared__ __align__(16) float4 fsm4[];
-  constexpr int LP = FastCfg<P>::LP;
-  const int lp = threadIdx.x / P::T, t = threadIdx.x - lp * P::T;
-  const int64_t lA = ((int64_t)blockIdx.x * LP + lp) * 2;
-  const bool onA = lA < a.lines, onB = lA + 1 < a.lines;
-  const float2 *inA = nullptr, *inB = nullptr, *smA = nullptr, *smB = nullptr, *scA = nullptr, *scB = nullptr;
-  float2 *outA = nullptr, *outB = nullptr;
-  // 32-bit index arithmetic: the launchers guarantee every array here has < 2^31 elements
-  auto setup = [&](uint32_t l, const float2 *&in, const float2 *&sm, const float2 *&sc, float2 *&out) {
-    const uint32_t rpi = (uint32_t)a.rows_per_img, n_in = (uint32_t)a.n_in, n_out = (uint32_t)a.n_out;
-    const uint32_t bc = l / rpi, row = l - bc * rpi;
-    if (MODE == ROW_FWD_FIRST) {
-      const uint32_t C = (uint32_t)a.C, b = bc / C, c = bc - b * C;
-      in = a.image + ((b * (uint32_t)a.Ci + (a.Ci == 1 ? 0u : c)) * rpi + row) * n_in;
-      sm = a.smaps ? a.smaps + (((a.Bs == 1 ? 0u : b) * C + c) * rpi + row) * n_in : nullptr;
-      sc = a.scaling ? a.scaling + row * n_in : nullptr;
-    } else {
-      in = a.in + l * n_in;
-      sc = a.scaling ? a.scaling + row * n_out : nullptr;
-    }
-    out = a.out + l * n_out;
-  };
-  if (onA) setup((uint32_t)lA, inA, smA, scA, outA);
-  if (onB) setup((uint32_t)lA + 1, inB, smB, scB, outB);
-  const int n_in = a.n_in, n_out = a.n_out;
-  const float scale = a.scale;
-  auto loadg = [&](int i) -> float4 {
-    float4 v = fast::v4(0.f, 0.f, 0.f, 0.f);
-    if (i < n_in) {  // zero padding is never read
-      if (MODE == ROW_FWD_FIRST) {
-        if (onA) { const float2 x = row_operand(inA, smA, scA, i, scale); v.x = x.x; v.y = x.y; }
-        if (onB) { const float2 x = row_operand(inB, smB, scB, i, scale); v.z = x.x; v.w = x.y; }
-      } else {
-        if (onA) { const float2 x = inA[i]; v.x = x.x; v.y = x.y; }
-        if (onB) { const float2 x = inB[i]; v.z = x.x; v.w = x.y; }
-      }
-    }
-    return v;
-  };
-  auto storeg = [&](int i, float4 v) {
-    if (i >= n_out) return;  // cropped outputs are never written
-    if (MODE == ROW_PLAIN) {
-      if (onA) {
-        float2 x = f2(v.x, v.y);
-        if (scA) x = cmul2(x, f2(scA[i].x, -scA[i].y));
-        outA[i] = f2(x.x * scale, x.y * scale);
-      }
-      if (onB) {
-        float2 x = f2(v.z, v.w);
-        if (scB) x = cmul2(x, f2(scB[i].x, -scB[i].y));
-        outB[i] = f2(x.x * scale, x.y * scale);
-      }
-    } else {
-      if (onA) outA[i] = f2(v.x, v.y);
-      if (onB) outB[i] = f2(v.z, v.w);
-    }
-  };
-  fast::fft_line_pair<P, INV, HALF && !INV, HALF && INV>(t, fsm4 + lp * P::NP, 1, a.tw + P::N, loadg, storeg);
-}
-
-template <class P, bool INV, bool HALF>
-__global__ void __launch_bounds__(FastCfg<P>::COL_THREADS, FastCfg<P>::COL_MINB) k_fft_cols_fast(ColArgs a) {
-  extern __shared__ __align__(16) float4 fsm4[];
-  constexpr int PAIRS = FastCfg<P>::PAIRS;
-  const int p = threadIdx.x % PAIRS, t = threadIdx.x / PAIRS;  // pair index fastest: contiguous global segments
-  const int X = (int)a.X, X2 = X >> 1, n_in = a.n_in, n_out = a.n_out;
-  // grid: x = block of 2*PAIRS columns, (y, z) = outer index
-  const int64_t oa = (int64_t)blockIdx.z * gridDim.y + blockIdx.y;
-  const int x = ((int)blockIdx.x * PAIRS + p) * 2;
-  const bool on = x < X && oa < a.A;
-  const float4 *in = reinterpret_cast<const float4 *>(a.in + oa * n_in * a.X + x);
-  float4 *out = reinterpret_cast<float4 *>(a.out + oa * n_out * a.X + x);
-  const float4 *mul =
-      a.mul ? reinterpret_cast<const float4 *>(a.mul + (a.a_per_mul ? (oa / a.a_per_mul) * (int64_t)P::N * a.X : 0) + x)
-            : nullptr;
-  const float scale = a.scale;
-  auto loadg = [&](int i) -> float4 {
-    if (!on || i >= n_in) return fast::v4(0.f, 0.f, 0.f, 0.f);
-    float4 v = in[i * X2];
-    if (mul) v = fast::vmul2(v, mul[i * X2]);
-    return v;
-  };
-  auto storeg = [&](int i, float4 v) {
-    if (on && i < n_out) out[i * X2] = fast::vscale(v, scale);
-  };
-  fast::fft_line_pair<P, INV, HALF && !INV, HALF && INV>(t, fsm4 + p, PAIRS, a.tw + P::N, loadg, storeg);
-}
-
-// Inverse row pass + SENSE coil combination (the last pass of the SENSE adjoint):
-//   image[b, row, :] = scale * conj(scaling[row, :]) * sum_c conj(smaps[b, c, row, :]) * IFFT_x(in[b, c, row, :])[:n_out]
-// CTA = one image row x 2*LP coils.  The LP pair sums meet in shared memory; when the coils span several
-// CTAs each writes its partial row to scratch and the CTA that arrives last (one atomic ticket per row) adds
-// the partial rows in coil-group order -- a fixed summation order, so the result is bit-reproducible.
-template <class P, bool HALF>
-__global__ void __launch_bounds__(FastCfg<P>::ROW_THREADS, FastCfg<P>::ROW_MINB) k_fft_rows_sense(RowArgs a) {
-  extern __shared__ __align__(16) float4 fsm4[];
-  constexpr int LP = FastCfg<P>::LP, NT = FastCfg<P>::ROW_THREADS;
-  __shared__ int s_last;
-  const int n_in = a.n_in, n_out = a.n_out;
-  float2 *red = reinterpret_cast<float2 *>(fsm4 + LP * P::NP);  // [LP][n_out] pair sums
-  const int lp = threadIdx.x / P::T, t = threadIdx.x - lp * P::T;
-  const uint32_t G = (uint32_t)a.coil_groups, rpi = (uint32_t)a.rows_per_img, C = (uint32_t)a.C;
-  const uint32_t br = blockIdx.x / G, g = blockIdx.x - br * G;  // (batch, row), coil group
-  const uint32_t b = br / rpi, row = br - b * rpi;
-  const uint32_t cA = (g * LP + lp) * 2, cB = cA + 1;
-  const bool onA = cA < C, onB = cB < C;
-  const uint32_t bs = a.Bs == 1 ? 0u : b;
-  const float2 *inA = a.in + ((b * C + (onA ? cA : 0u)) * rpi + row) * (uint32_t)n_in;
-  const float2 *inB = a.in + ((b * C + (onB ? cB : 0u)) * rpi + row) * (uint32_t)n_in;
-  const float2 *smA = a.smaps + ((bs * C + (onA ? cA : 0u)) * rpi + row) * (uint32_t)n_out;
-  const float2 *smB = a.smaps + ((bs * C + (onB ? cB : 0u)) * rpi + row) * (uint32_t)n_out;
-  auto loadg = [&](int i) -> float4 {
-    float4 v = fast::v4(0.f, 0.f, 0.f, 0.f);
-    if (i < n_in) {
-      if (onA) { const float2 x = inA[i]; v.x = x.x; v.y = x.y; }
-      if (onB) { const float2 x = inB[i]; v.z = x.x; v.w = x.y; }
-    }
-    return v;
-  };
-  auto storeg = [&](int i, float4 v) {
-    if (i >= n_out) return;
-    float2 p = f2(0.f, 0.f);
-    if (onA) { const float2 m = smA[i]; p = f2(fmaf(v.x, m.x, v.y * m.y), fmaf(v.y, m.x, -(v.x * m.y))); }
-    if (onB) { const float2 m = smB[i]; p = f2(p.x + fmaf(v.z, m.x, v.w * m.y), p.y + fmaf(v.w, m.x, -(v.z * m.y))); }
-    red[lp * n_out + i] = p;
-  };
-  fast::fft_line_pair<P, true, false, HALF>(t, fsm4 + lp * P::NP, 1, a.tw + P::N, loadg, storeg);
-  __syncthreads();
-  const float2 *sc = a.scaling ? a.scaling + row * (uint32_t)n_out : nullptr;
-  float2 *out = a.out + br * (uint32_t)n_out;
-  auto finish = [&](int j, float2 sum) {
-    if (sc) sum = cmul2(sum, f2(sc[j].x, -sc[j].y));
-    out[j] = f2(sum.x * a.scale, sum.y * a.scale);
-  };
-  float2 *mine = a.partial + ((size_t)g * gridDim.x / G + br) * (uint32_t)n_out;  // [G][B*rows][n_out]
-  for (int j = threadIdx.x; j < n_out; j += NT) {
-    float2 sum = red[j];
-#pragma unroll
-    for (int q = 1; q < LP; ++q) sum = cadd(sum, red[q * n_out + j]);
-    if (G == 1) finish(j, sum);
-    else __stcg(&mine[j], sum);
-  }
-  if (G == 1) return;
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) s_last = atomicAdd(&a.counter[br], 1u) == G - 1;
-  __syncthreads();
-  if (!s_last) return;
-  __threadfence();
-  for (int j = threadIdx.x; j < n_out; j += NT) {
-    float2 sum = __ldcg(&a.partial[(size_t)br * (uint32_t)n_out + j]);
-    for (uint32_t q = 1; q < G; ++q) sum = cadd(sum, __ldcg(&a.partial[((size_t)q * gridDim.x / G + br) * (uint32_t)n_out + j]));
-    finish(j, sum);
-  }
-  if (threadIdx.x == 0) a.counter[br] = 0;  // leave the counters zero for the next call
-}
-
 // staged twiddle tables of the fast plans: entry e = exp(-2 pi i r k / period)
 __global__ void k_fft_twiddles_staged(float2 *tw, int R0, int R1, int R2) {
   const int tw2 = (R1 - 1) * R0, count = tw2 + (R2 > 1 ? (R2 - 1) * R0 * R1 : 0);
@@ -507,55 +287,37 @@ static bool make_stages(int64_t n, FftStages *st, int max_pow2_bits = 4) {
 
 int g_fast_fft = 1;  // B2N_OPT_FAST_FFT: compile-time planned passes where a plan exists
 
-template <class P, bool INV, int MODE, bool HALF> static int launch_rows_fast_h(RowArgs &a, cudaStream_t st) {
-  using Cfg = FastCfg<P>;
-  const size_t smem = sizeof(float4) * (size_t)Cfg::LP * P::NP;
-  auto kern = k_fft_rows_fast<P, INV, MODE, HALF>;
-  B2N_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<(unsigned)ceil_div(a.lines, 2 * Cfg::LP), Cfg::ROW_THREADS, smem, st>>>(a);
-  B2N_LAUNCH_OK("k_fft_rows_fast");
-  return 0;
-}
-template <class P, bool INV, int MODE> static int launch_rows_fast(RowArgs &a, cudaStream_t st) {
-  const bool half = 2 * (INV ? a.n_out : a.n_in) <= P::N;
-  return half ? launch_rows_fast_h<P, INV, MODE, true>(a, st) : launch_rows_fast_h<P, INV, MODE, false>(a, st);
-}
+// entry points of the compile-time planned passes, defined in b2n_fft_plans_*.cu
+#define B2N_DECLARE_PLAN_X(N, R0, R1, R2, ...)                      \
+  int fast_rows_fwd_##N(RowArgs &a, cudaStream_t st);                \
+  int fast_rows_inv_##N(RowArgs &a, cudaStream_t st);                \
+  int fast_cols_##N(bool inverse, ColArgs &a, cudaStream_t st);      \
+  int fast_rows_sense_##N(RowArgs &a, int64_t B, cudaStream_t st);
+B2N_FAST_PLANS(B2N_DECLARE_PLAN_X, 0)
 
-template <class P, bool INV, bool HALF> static int launch_cols_fast_h(ColArgs &a, cudaStream_t st) {
-  using Cfg = FastCfg<P>;
-  const size_t smem = sizeof(float4) * (size_t)Cfg::PAIRS * P::NP;
-  auto kern = k_fft_cols_fast<P, INV, HALF>;
-  B2N_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int64_t gy = a.A < 32768 ? a.A : 32768;
-  const dim3 grid((unsigned)ceil_div(a.X, 2 * Cfg::PAIRS), (unsigned)gy, (unsigned)ceil_div(a.A, gy));
-  kern<<<grid, Cfg::COL_THREADS, smem, st>>>(a);
-  B2N_LAUNCH_OK("k_fft_cols_fast");
-  return 0;
-}
-template <class P, bool INV> static int launch_cols_fast(ColArgs &a, cudaStream_t st) {
-  const bool half = 2 * (INV ? a.n_out : a.n_in) <= P::N;
-  return half ? launch_cols_fast_h<P, INV, true>(a, st) : launch_cols_fast_h<P, INV, false>(a, st);
-}
+#define B2N_CASE_ROWS_FWD(N, R0, R1, R2, ...) case N: return fast_rows_fwd_##N(a, st);
+#define B2N_CASE_ROWS_INV(N, R0, R1, R2, ...) case N: return fast_rows_inv_##N(a, st);
+#define B2N_CASE_COLS(N, R0, R1, R2, ...) case N: return fast_cols_##N(inverse, a, st);
+#define B2N_CASE_SENSE(N, R0, R1, R2, ...) case N: return fast_rows_sense_##N(a, B, st);
 
-template <class P, bool HALF> static int launch_rows_sense_h(RowArgs &a, int64_t B, cudaStream_t st) {
-  using Cfg = FastCfg<P>;
-  a.coil_groups = (int)ceil_div(a.C, 2 * Cfg::LP);
-  const int64_t rows = B * a.rows_per_img;
-  const size_t smem = sizeof(float4) * (size_t)Cfg::LP * P::NP + sizeof(float2) * (size_t)Cfg::LP * a.n_out;
-  auto kern = k_fft_rows_sense<P, HALF>;
-  B2N_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  if (a.coil_groups > 1) B2N_CUDA_OK(cudaMemsetAsync(a.counter, 0, sizeof(unsigned int) * (size_t)rows, st));
-  kern<<<(unsigned)(rows * a.coil_groups), Cfg::ROW_THREADS, smem, st>>>(a);
-  B2N_LAUNCH_OK("k_fft_rows_sense");
-  return 0;
+// each returns -1 when the length has no compile-time plan (the caller takes the run-time / unfused route)
+static int fast_rows(bool inverse, RowArgs &a, cudaStream_t st) {
+  if (!g_fast_fft) return -1;
+  if (inverse) {
+    switch (a.st.n) { B2N_FAST_PLANS(B2N_CASE_ROWS_INV, 0) default: break; }
+  } else {
+    switch (a.st.n) { B2N_FAST_PLANS(B2N_CASE_ROWS_FWD, 0) default: break; }
+  }
+  return -1;
 }
-// returns -1 when the length has no compile-time plan (caller takes the unfused route)
+static int fast_cols(bool inverse, ColArgs &a, cudaStream_t st) {
+  if (!g_fast_fft) return -1;
+  switch (a.st.n) { B2N_FAST_PLANS(B2N_CASE_COLS, 0) default: break; }
+  return -1;
+}
 static int launch_rows_sense(RowArgs &a, int64_t B, cudaStream_t st) {
   if (!g_fast_fft) return -1;
-  const bool half = 2 * a.n_out <= a.st.n;
-  B2N_FAST_PLAN_SWITCH(a.st.n,
-                       return (half ? launch_rows_sense_h<P, true>(a, B, st) : launch_rows_sense_h<P, false>(a, B, st)),
-                       (void)0)
+  switch (a.st.n) { B2N_FAST_PLANS(B2N_CASE_SENSE, 0) default: break; }
   return -1;
 }
 
@@ -563,8 +325,9 @@ static bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 
 
 template <bool INV, int MODE> static int launch_rows(RowArgs &a, cudaStream_t st) {
   if (a.lines <= 0) return 0;
-  if (g_fast_fft) {
-    B2N_FAST_PLAN_SWITCH(a.st.n, return (launch_rows_fast<P, INV, MODE>(a, st)), (void)0)
+  if ((INV && MODE == ROW_PLAIN) || (!INV && MODE == ROW_FWD_FIRST)) {  // the two combinations the fused passes use
+    const int rc = fast_rows(INV, a, st);
+    if (rc >= 0) return rc;
   }
   const int NP = fft_pad(a.st.n) + 1;
   const size_t smem = sizeof(float2) * ((size_t)a.st.n + 2 * (size_t)kRowsPerCta * NP);
@@ -577,8 +340,9 @@ template <bool INV, int MODE> static int launch_rows(RowArgs &a, cudaStream_t st
 
 template <bool INV> static int launch_cols(ColArgs &a, cudaStream_t st) {
   if (a.A <= 0 || a.X <= 0) return 0;
-  if (g_fast_fft && a.X % 2 == 0 && aligned16(a.in) && aligned16(a.out) && aligned16(a.mul)) {
-    B2N_FAST_PLAN_SWITCH(a.st.n, return (launch_cols_fast<P, INV>(a, st)), (void)0)
+  if (a.X % 2 == 0 && aligned16(a.in) && aligned16(a.out) && aligned16(a.mul)) {
+    const int rc = fast_cols(INV, a, st);
+    if (rc >= 0) return rc;
   }
   const int NP = fft_pad(a.st.n) + 1;
   const size_t smem = sizeof(float2) * ((size_t)a.st.n + 2 * (size_t)NP * kColsPerCta);

@@ -357,27 +357,31 @@ __device__ __forceinline__ void fft_line_pair(int t, float4 *sm, int es, const f
 }
 #endif  // __CUDACC__
 
-// plans for the grid sizes of 2x-oversampled acquisitions (BASELINE configs use 256, 512, 640, 768)
-using Plan64 = Plan<64, 8, 8, 1>;
-using Plan128 = Plan<128, 8, 16, 1>;
-using Plan256 = Plan<256, 16, 16, 1>;
-using Plan320 = Plan<320, 8, 8, 5>;
-using Plan512 = Plan<512, 8, 8, 8>;
-using Plan640 = Plan<640, 8, 8, 10>;
-using Plan768 = Plan<768, 8, 8, 12>;
-using Plan1024 = Plan<1024, 8, 8, 16>;
+// Plans (N, R0, R1, R2) for the grid lengths 2x-oversampled acquisitions use (BASELINE configs: 256, 512, 640,
+// 768).  R0 is 8 or 16 (padding period), the leg strides N/R1 and N/R2 are multiples of R0, R2 = 1 means two
+// stages.  Every other length takes the run-time passes or cuFFT.
+#define B2N_FAST_PLANS(X, ...)                                                                                  \
+  X(64, 8, 8, 1, __VA_ARGS__) X(96, 8, 12, 1, __VA_ARGS__) X(128, 8, 16, 1, __VA_ARGS__)                       \
+  X(192, 8, 8, 3, __VA_ARGS__) X(256, 16, 16, 1, __VA_ARGS__) X(320, 8, 8, 5, __VA_ARGS__)                     \
+  X(384, 8, 16, 3, __VA_ARGS__) X(512, 8, 8, 8, __VA_ARGS__) X(576, 16, 12, 3, __VA_ARGS__)                    \
+  X(640, 8, 8, 10, __VA_ARGS__) X(768, 8, 8, 12, __VA_ARGS__) X(1024, 8, 8, 16, __VA_ARGS__)                   \
+  X(1280, 16, 8, 10, __VA_ARGS__) X(2048, 16, 16, 8, __VA_ARGS__)
 
-#define B2N_FAST_PLAN_SWITCH(n_, CALL, DEFAULT)                       \
-  switch (n_) {                                                       \
-    case 64: { using P = ::b2n::fast::Plan64; CALL; } break;          \
-    case 128: { using P = ::b2n::fast::Plan128; CALL; } break;        \
-    case 256: { using P = ::b2n::fast::Plan256; CALL; } break;        \
-    case 320: { using P = ::b2n::fast::Plan320; CALL; } break;        \
-    case 512: { using P = ::b2n::fast::Plan512; CALL; } break;        \
-    case 640: { using P = ::b2n::fast::Plan640; CALL; } break;        \
-    case 768: { using P = ::b2n::fast::Plan768; CALL; } break;        \
-    case 1024: { using P = ::b2n::fast::Plan1024; CALL; } break;      \
-    default: { DEFAULT; } break;                                      \
+#define B2N_FAST_PLAN_USING(N, R0, R1, R2, ...) using Plan##N = Plan<N, R0, R1, R2>;
+B2N_FAST_PLANS(B2N_FAST_PLAN_USING, 0)
+
+// switch over the planned lengths: CALL is evaluated with `P` naming the plan type
+#define B2N_FAST_PLAN_CASE(N, R0, R1, R2, CALL) \
+  case N: {                                     \
+    using P = ::b2n::fast::Plan##N;             \
+    CALL;                                       \
+  } break;
+#define B2N_FAST_PLAN_SWITCH(n_, CALL, DEFAULT)  \
+  switch (n_) {                                  \
+    B2N_FAST_PLANS(B2N_FAST_PLAN_CASE, CALL)     \
+    default: {                                   \
+      DEFAULT;                                   \
+    } break;                                     \
   }
 
 }  // namespace fast

@@ -1,0 +1,260 @@
+// b2n_fft_fast_kernels.cuh -- kernels and launchers of the compile-time planned FFT passes (b2n_fft_fast.cuh).
+// Included by the b2n_fft_plans_*.cu translation units, each of which instantiates a few plans (they compile in
+// parallel); b2n_fft.cu only sees the per-plan entry points declared by B2N_DECLARE_PLAN.
+#pragma once
+#include "b2n_fft_args.cuh"
+#include "b2n_fft_fast.cuh"
+
+namespace b2n {
+
+// -----------------------------------------------------------------------------------------
+// fast passes: compile-time plans of b2n_fft_fast.cuh, two lines per thread
+// -----------------------------------------------------------------------------------------
+template <class P> struct FastCfg {
+  // row pass: LP line pairs per CTA (about 160 threads: small CTAs keep the last wave of a launch short -- a
+  // launch is typically 1-3 waves of resident line pairs); column pass: PAIRS column pairs per CTA
+  static constexpr int LP = P::T >= 160 ? 1 : 160 / P::T;
+  static constexpr int ROW_THREADS = LP * P::T;
+  static constexpr int PAIRS = P::T >= 256 ? 2 : (P::T >= 64 ? 4 : 256 / P::T);
+  static constexpr int COL_THREADS = PAIRS * P::T;
+  // register budget: 64 per thread (128 for radix-16 butterflies on pairs) -> resident CTAs per SM
+  static constexpr int REG_THREADS = P::RMAX >= 16 ? 512 : 1024;
+  static constexpr int ROW_MINB = REG_THREADS / ROW_THREADS > 0 ? REG_THREADS / ROW_THREADS : 1;
+  static constexpr int COL_MINB = REG_THREADS / COL_THREADS > 0 ? REG_THREADS / COL_THREADS : 1;
+};
+
+B2N_D float2 row_operand(const float2 *in, const float2 *sm, const float2 *sc, int i, float scale) {
+  float2 v = in[i];
+  if (sm) v = cmul2(v, sm[i]);
+  if (sc) v = cmul2(v, sc[i]);
+  return f2(v.x * scale, v.y * scale);
+}
+
+// HALF: the padded half of the inputs (forward) / the cropped half of the outputs (inverse) is skipped at
+// compile time (n_in <= N/2 resp. n_out <= N/2, the 2x-oversampled case).
+template <class P, bool INV, int MODE, bool HALF>
+__global__ void __launch_bounds__(FastCfg<P>::ROW_THREADS, FastCfg<P>::ROW_MINB) k_fft_rows_fast(RowArgs a) {
+  extern __shared__ __align__(16) float4 fsm4[];
+  constexpr int LP = FastCfg<P>::LP;
+  const int lp = threadIdx.x / P::T, t = threadIdx.x - lp * P::T;
+  const int64_t lA = ((int64_t)blockIdx.x * LP + lp) * 2;
+  const bool onA = lA < a.lines, onB = lA + 1 < a.lines;
+  const float2 *inA = nullptr, *inB = nullptr, *smA = nullptr, *smB = nullptr, *scA = nullptr, *scB = nullptr;
+  float2 *outA = nullptr, *outB = nullptr;
+  // 32-bit index arithmetic: the launchers guarantee every array here has < 2^31 elements
+  auto setup = [&](uint32_t l, const float2 *&in, const float2 *&sm, const float2 *&sc, float2 *&out) {
+    const uint32_t rpi = (uint32_t)a.rows_per_img, n_in = (uint32_t)a.n_in, n_out = (uint32_t)a.n_out;
+    const uint32_t bc = l / rpi, row = l - bc * rpi;
+    if (MODE == ROW_FWD_FIRST) {
+      const uint32_t C = (uint32_t)a.C, b = bc / C, c = bc - b * C;
+      in = a.image + ((b * (uint32_t)a.Ci + (a.Ci == 1 ? 0u : c)) * rpi + row) * n_in;
+      sm = a.smaps ? a.smaps + (((a.Bs == 1 ? 0u : b) * C + c) * rpi + row) * n_in : nullptr;
+      sc = a.scaling ? a.scaling + row * n_in : nullptr;
+    } else {
+      in = a.in + l * n_in;
+      sc = a.scaling ? a.scaling + row * n_out : nullptr;
+    }
+    out = a.out + l * n_out;
+  };
+  if (onA) setup((uint32_t)lA, inA, smA, scA, outA);
+  if (onB) setup((uint32_t)lA + 1, inB, smB, scB, outB);
+  const int n_in = a.n_in, n_out = a.n_out;
+  const float scale = a.scale;
+  auto loadg = [&](int i) -> float4 {
+    float4 v = fast::v4(0.f, 0.f, 0.f, 0.f);
+    if (i < n_in) {  // zero padding is never read
+      if (MODE == ROW_FWD_FIRST) {
+        if (onA) { const float2 x = row_operand(inA, smA, scA, i, scale); v.x = x.x; v.y = x.y; }
+        if (onB) { const float2 x = row_operand(inB, smB, scB, i, scale); v.z = x.x; v.w = x.y; }
+      } else {
+        if (onA) { const float2 x = inA[i]; v.x = x.x; v.y = x.y; }
+        if (onB) { const float2 x = inB[i]; v.z = x.x; v.w = x.y; }
+      }
+    }
+    return v;
+  };
+  auto storeg = [&](int i, float4 v) {
+    if (i >= n_out) return;  // cropped outputs are never written
+    if (MODE == ROW_PLAIN) {
+      if (onA) {
+        float2 x = f2(v.x, v.y);
+        if (scA) x = cmul2(x, f2(scA[i].x, -scA[i].y));
+        outA[i] = f2(x.x * scale, x.y * scale);
+      }
+      if (onB) {
+        float2 x = f2(v.z, v.w);
+        if (scB) x = cmul2(x, f2(scB[i].x, -scB[i].y));
+        outB[i] = f2(x.x * scale, x.y * scale);
+      }
+    } else {
+      if (onA) outA[i] = f2(v.x, v.y);
+      if (onB) outB[i] = f2(v.z, v.w);
+    }
+  };
+  fast::fft_line_pair<P, INV, HALF && !INV, HALF && INV>(t, fsm4 + lp * P::NP, 1, a.tw + P::N, loadg, storeg);
+}
+
+template <class P, bool INV, bool HALF>
+__global__ void __launch_bounds__(FastCfg<P>::COL_THREADS, FastCfg<P>::COL_MINB) k_fft_cols_fast(ColArgs a) {
+  extern __shared__ __align__(16) float4 fsm4[];
+  constexpr int PAIRS = FastCfg<P>::PAIRS;
+  const int p = threadIdx.x % PAIRS, t = threadIdx.x / PAIRS;  // pair index fastest: contiguous global segments
+  const int X = (int)a.X, X2 = X >> 1, n_in = a.n_in, n_out = a.n_out;
+  // grid: x = block of 2*PAIRS columns, (y, z) = outer index
+  const int64_t oa = (int64_t)blockIdx.z * gridDim.y + blockIdx.y;
+  const int x = ((int)blockIdx.x * PAIRS + p) * 2;
+  const bool on = x < X && oa < a.A;
+  const float4 *in = reinterpret_cast<const float4 *>(a.in + oa * n_in * a.X + x);
+  float4 *out = reinterpret_cast<float4 *>(a.out + oa * n_out * a.X + x);
+  const float4 *mul =
+      a.mul ? reinterpret_cast<const float4 *>(a.mul + (a.a_per_mul ? (oa / a.a_per_mul) * (int64_t)P::N * a.X : 0) + x)
+            : nullptr;
+  const float scale = a.scale;
+  auto loadg = [&](int i) -> float4 {
+    if (!on || i >= n_in) return fast::v4(0.f, 0.f, 0.f, 0.f);
+    float4 v = in[i * X2];
+    if (mul) v = fast::vmul2(v, mul[i * X2]);
+    return v;
+  };
+  auto storeg = [&](int i, float4 v) {
+    if (on && i < n_out) out[i * X2] = fast::vscale(v, scale);
+  };
+  fast::fft_line_pair<P, INV, HALF && !INV, HALF && INV>(t, fsm4 + p, PAIRS, a.tw + P::N, loadg, storeg);
+}
+
+// Inverse row pass + SENSE coil combination (the last pass of the SENSE adjoint):
+//   image[b, row, :] = scale * conj(scaling[row, :]) * sum_c conj(smaps[b, c, row, :]) * IFFT_x(in[b, c, row, :])[:n_out]
+// CTA = one image row x 2*LP coils.  The LP pair sums meet in shared memory; when the coils span several
+// CTAs each writes its partial row to scratch and the CTA that arrives last (one atomic ticket per row) adds
+// the partial rows in coil-group order -- a fixed summation order, so the result is bit-reproducible.
+template <class P, bool HALF>
+__global__ void __launch_bounds__(FastCfg<P>::ROW_THREADS, FastCfg<P>::ROW_MINB) k_fft_rows_sense(RowArgs a) {
+  extern __shared__ __align__(16) float4 fsm4[];
+  constexpr int LP = FastCfg<P>::LP, NT = FastCfg<P>::ROW_THREADS;
+  __shared__ int s_last;
+  const int n_in = a.n_in, n_out = a.n_out;
+  float2 *red = reinterpret_cast<float2 *>(fsm4 + LP * P::NP);  // [LP][n_out] pair sums
+  const int lp = threadIdx.x / P::T, t = threadIdx.x - lp * P::T;
+  const uint32_t G = (uint32_t)a.coil_groups, rpi = (uint32_t)a.rows_per_img, C = (uint32_t)a.C;
+  const uint32_t br = blockIdx.x / G, g = blockIdx.x - br * G;  // (batch, row), coil group
+  const uint32_t b = br / rpi, row = br - b * rpi;
+  const uint32_t cA = (g * LP + lp) * 2, cB = cA + 1;
+  const bool onA = cA < C, onB = cB < C;
+  const uint32_t bs = a.Bs == 1 ? 0u : b;
+  const float2 *inA = a.in + ((b * C + (onA ? cA : 0u)) * rpi + row) * (uint32_t)n_in;
+  const float2 *inB = a.in + ((b * C + (onB ? cB : 0u)) * rpi + row) * (uint32_t)n_in;
+  const float2 *smA = a.smaps + ((bs * C + (onA ? cA : 0u)) * rpi + row) * (uint32_t)n_out;
+  const float2 *smB = a.smaps + ((bs * C + (onB ? cB : 0u)) * rpi + row) * (uint32_t)n_out;
+  auto loadg = [&](int i) -> float4 {
+    float4 v = fast::v4(0.f, 0.f, 0.f, 0.f);
+    if (i < n_in) {
+      if (onA) { const float2 x = inA[i]; v.x = x.x; v.y = x.y; }
+      if (onB) { const float2 x = inB[i]; v.z = x.x; v.w = x.y; }
+    }
+    return v;
+  };
+  auto storeg = [&](int i, float4 v) {
+    if (i >= n_out) return;
+    float2 p = f2(0.f, 0.f);
+    if (onA) { const float2 m = smA[i]; p = f2(fmaf(v.x, m.x, v.y * m.y), fmaf(v.y, m.x, -(v.x * m.y))); }
+    if (onB) { const float2 m = smB[i]; p = f2(p.x + fmaf(v.z, m.x, v.w * m.y), p.y + fmaf(v.w, m.x, -(v.z * m.y))); }
+    red[lp * n_out + i] = p;
+  };
+  fast::fft_line_pair<P, true, false, HALF>(t, fsm4 + lp * P::NP, 1, a.tw + P::N, loadg, storeg);
+  __syncthreads();
+  const float2 *sc = a.scaling ? a.scaling + row * (uint32_t)n_out : nullptr;
+  float2 *out = a.out + br * (uint32_t)n_out;
+  auto finish = [&](int j, float2 sum) {
+    if (sc) sum = cmul2(sum, f2(sc[j].x, -sc[j].y));
+    out[j] = f2(sum.x * a.scale, sum.y * a.scale);
+  };
+  float2 *mine = a.partial + ((size_t)g * gridDim.x / G + br) * (uint32_t)n_out;  // [G][B*rows][n_out]
+  for (int j = threadIdx.x; j < n_out; j += NT) {
+    float2 sum = red[j];
+#pragma unroll
+    for (int q = 1; q < LP; ++q) sum = cadd(sum, red[q * n_out + j]);
+    if (G == 1) finish(j, sum);
+    else __stcg(&mine[j], sum);
+  }
+  if (G == 1) return;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = atomicAdd(&a.counter[br], 1u) == G - 1;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  for (int j = threadIdx.x; j < n_out; j += NT) {
+    float2 sum = __ldcg(&a.partial[(size_t)br * (uint32_t)n_out + j]);
+    for (uint32_t q = 1; q < G; ++q) sum = cadd(sum, __ldcg(&a.partial[((size_t)q * gridDim.x / G + br) * (uint32_t)n_out + j]));
+    finish(j, sum);
+  }
+  if (threadIdx.x == 0) a.counter[br] = 0;  // leave the counters zero for the next call
+}
+
+template <class P, bool INV, int MODE, bool HALF> int launch_rows_fast_h(RowArgs &a, cudaStream_t st) {
+  using Cfg = FastCfg<P>;
+  const size_t smem = sizeof(float4) * (size_t)Cfg::LP * P::NP;
+  auto kern = k_fft_rows_fast<P, INV, MODE, HALF>;
+  B2N_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<(unsigned)ceil_div(a.lines, 2 * Cfg::LP), Cfg::ROW_THREADS, smem, st>>>(a);
+  B2N_LAUNCH_OK("k_fft_rows_fast");
+  return 0;
+}
+template <class P, bool INV, int MODE> int launch_rows_fast(RowArgs &a, cudaStream_t st) {
+  const bool half = 2 * (INV ? a.n_out : a.n_in) <= P::N;
+  return half ? launch_rows_fast_h<P, INV, MODE, true>(a, st) : launch_rows_fast_h<P, INV, MODE, false>(a, st);
+}
+
+template <class P, bool INV, bool HALF> int launch_cols_fast_h(ColArgs &a, cudaStream_t st) {
+  using Cfg = FastCfg<P>;
+  const size_t smem = sizeof(float4) * (size_t)Cfg::PAIRS * P::NP;
+  auto kern = k_fft_cols_fast<P, INV, HALF>;
+  B2N_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int64_t gy = a.A < 32768 ? a.A : 32768;
+  const dim3 grid((unsigned)ceil_div(a.X, 2 * Cfg::PAIRS), (unsigned)gy, (unsigned)ceil_div(a.A, gy));
+  kern<<<grid, Cfg::COL_THREADS, smem, st>>>(a);
+  B2N_LAUNCH_OK("k_fft_cols_fast");
+  return 0;
+}
+template <class P, bool INV> int launch_cols_fast(ColArgs &a, cudaStream_t st) {
+  const bool half = 2 * (INV ? a.n_out : a.n_in) <= P::N;
+  return half ? launch_cols_fast_h<P, INV, true>(a, st) : launch_cols_fast_h<P, INV, false>(a, st);
+}
+
+template <class P, bool HALF> int launch_rows_sense_h(RowArgs &a, int64_t B, cudaStream_t st) {
+  using Cfg = FastCfg<P>;
+  a.coil_groups = (int)ceil_div(a.C, 2 * Cfg::LP);
+  const int64_t rows = B * a.rows_per_img;
+  const size_t smem = sizeof(float4) * (size_t)Cfg::LP * P::NP + sizeof(float2) * (size_t)Cfg::LP * a.n_out;
+  auto kern = k_fft_rows_sense<P, HALF>;
+  B2N_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (a.coil_groups > 1) B2N_CUDA_OK(cudaMemsetAsync(a.counter, 0, sizeof(unsigned int) * (size_t)rows, st));
+  kern<<<(unsigned)(rows * a.coil_groups), Cfg::ROW_THREADS, smem, st>>>(a);
+  B2N_LAUNCH_OK("k_fft_rows_sense");
+  return 0;
+}
+
+template <class P> int launch_rows_sense_any(RowArgs &a, int64_t B, cudaStream_t st) {
+  return 2 * a.n_out <= P::N ? launch_rows_sense_h<P, true>(a, B, st) : launch_rows_sense_h<P, false>(a, B, st);
+}
+
+// per-plan entry points: forward first row pass, inverse row pass, column pass, inverse row pass + coil sum
+#define B2N_DECLARE_PLAN(N)                                                        \
+  int fast_rows_fwd_##N(RowArgs &a, cudaStream_t st);                              \
+  int fast_rows_inv_##N(RowArgs &a, cudaStream_t st);                              \
+  int fast_cols_##N(bool inverse, ColArgs &a, cudaStream_t st);                    \
+  int fast_rows_sense_##N(RowArgs &a, int64_t B, cudaStream_t st);
+
+#define B2N_DEFINE_PLAN(N)                                                                                  \
+  int fast_rows_fwd_##N(RowArgs &a, cudaStream_t st) {                                                      \
+    return launch_rows_fast<fast::Plan##N, false, ROW_FWD_FIRST>(a, st);                                    \
+  }                                                                                                         \
+  int fast_rows_inv_##N(RowArgs &a, cudaStream_t st) { return launch_rows_fast<fast::Plan##N, true, ROW_PLAIN>(a, st); } \
+  int fast_cols_##N(bool inverse, ColArgs &a, cudaStream_t st) {                                            \
+    return inverse ? launch_cols_fast<fast::Plan##N, true>(a, st) : launch_cols_fast<fast::Plan##N, false>(a, st); \
+  }                                                                                                         \
+  int fast_rows_sense_##N(RowArgs &a, int64_t B, cudaStream_t st) {                                         \
+    return launch_rows_sense_any<fast::Plan##N>(a, B, st);                                                  \
+  }
+
+}  // namespace b2n

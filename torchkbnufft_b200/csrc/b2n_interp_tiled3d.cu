@@ -273,7 +273,9 @@ __global__ void __launch_bounds__(k3Threads, 2) k_adj_tiled_3d(InterpArgs<float>
       float2 t[5];
 #pragma unroll
       for (int it = 0; it < 5; ++it) {
-        const int blk = min(2 * it + h, 8), ny = blk / 3, nx = blk - ny * 3;
+        // the half without a ninth block re-reads its own block 7 (a dummy load of another lane's cell would be
+        // a read/write hazard inside the warp, flagged by compute-sanitizer racecheck)
+        const int blk = 2 * it + h < 9 ? 2 * it + h : 7, ny = blk / 3, nx = blk - ny * 3;
         t[it] = tp[2 * ny * k3SX + 2 * nx];
       }
 #pragma unroll
