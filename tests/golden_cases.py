@@ -96,3 +96,31 @@ def case_inputs(case: dict, cdtype) -> dict:
         im_size=N,
         grid_size=K,
     )
+
+
+# ---- sparse-matrix interpolation shim (oracle/make_golden_spmat.py, tests/test_spmat.py) -------
+SPMAT_CASES = {
+    "s2d_f64": dict(im_size=(8, 8), M=30, dtype="float64"),
+    "s2d_f32": dict(im_size=(12, 10), M=41, dtype="float32"),
+    "s1d_f64": dict(im_size=(16,), M=25, dtype="float64", numpoints=4),
+    "s3d_f64": dict(im_size=(6, 8, 5), M=37, dtype="float64", grid_size=(10, 12, 9), numpoints=(4, 5, 6),
+                    n_shift=(1, 3, 2)),
+}
+
+
+def spmat_case_inputs(name):
+    """(omega (d, M), image (2, 1, *N), kdata (2, 3, M), smaps (1, 3, *N)) regenerated from the case's seed."""
+    import zlib
+
+    import numpy as np
+    cfg = SPMAT_CASES[name]
+    rng = np.random.default_rng(zlib.crc32(name.encode()))
+    real = np.dtype(cfg["dtype"])
+    cplx = np.complex64 if real == np.float32 else np.complex128
+    N, M, d = cfg["im_size"], cfg["M"], len(cfg["im_size"])
+    omega = rng.uniform(-np.pi, np.pi, size=(d, M)).astype(real)
+
+    def cn(shape):
+        return (rng.standard_normal(shape) + 1j * rng.standard_normal(shape)).astype(cplx)
+
+    return omega, cn((2, 1) + tuple(N)), cn((2, 3, M)), cn((1, 3) + tuple(N))

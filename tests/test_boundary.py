@@ -89,8 +89,12 @@ def test_missing_library_fails_loudly(monkeypatch):
         _lib.load()
 
 
-def test_spmat_mode_is_out_of_scope():
-    with pytest.raises(NotImplementedError):
-        tkbn.calc_tensor_spmatrix(torch.rand(2, 4), (8, 8))
-    with pytest.raises(NotImplementedError):
-        tkbn.functional.kb_spmat_interp(torch.zeros(1), (None, None))
+def test_spmat_mode_is_a_torch_sparse_shim():
+    """the sparse-matrix mode exists for API completeness only -- built on the host like the
+    reference does, applied with torch.sparse, never through libb200nufft.so (tests/test_spmat.py)."""
+    real, imag = tkbn.calc_tensor_spmatrix(torch.rand(2, 4), (8, 8))
+    assert real.is_sparse and imag.is_sparse and tuple(real.shape) == (4, 256)
+    import inspect
+
+    from torchkbnufft_b200._nufft import spmat
+    assert "_lib" not in inspect.getsource(spmat)

@@ -9,12 +9,8 @@ import torch
 from torch import Tensor
 
 from .._autograd.interp import KbTableInterpAdjoint, KbTableInterpForward
-
-_SPMAT_MSG = (
-    "sparse-matrix interpolation is outside the B200 engine's scope: only the table-interpolation path "
-    "is accelerated (the reference itself labels the sparse mode 'not recommended', README.md:33-37). "
-    "Pass interp_mats=None."
-)
+from .._nufft import spmat as _spmat
+from .._nufft.plan import require_cuda
 
 
 def with_complex_view(fn: Callable[[Tensor], Tensor], x: Tensor) -> Tensor:
@@ -47,8 +43,13 @@ def kb_table_interp_adjoint(data: Tensor, omega: Tensor, tables: List[Tensor], n
 
 
 def kb_spmat_interp(image: Tensor, interp_mats: Tuple[Tensor, Tensor]) -> Tensor:
-    raise NotImplementedError(_SPMAT_MSG)
+    """Sparse-matrix interpolation (reference ``functional/interp.py:14-44``): API-completeness shim
+    on ``torch.sparse``, not part of the accelerated table path (see ``_nufft/spmat.py``)."""
+    require_cuda(image, "image")
+    return with_complex_view(lambda x: _spmat.spmat_interp(x, interp_mats), image)
 
 
 def kb_spmat_interp_adjoint(data: Tensor, interp_mats: Tuple[Tensor, Tensor], grid_size: Tensor) -> Tensor:
-    raise NotImplementedError(_SPMAT_MSG)
+    """Adjoint sparse-matrix interpolation (reference ``functional/interp.py:47-79``)."""
+    require_cuda(data, "data")
+    return with_complex_view(lambda x: _spmat.spmat_interp_adjoint(x, interp_mats, grid_size), data)

@@ -13,7 +13,8 @@ from .._autograd.nufft import ApodPad, CropApodCoilsum, FusedFftAdjoint, FusedFf
 from .._nufft import fft as _fft
 from .._nufft import interp as _interp
 from .._nufft.plan import host_ints as _ints
-from .interp import _SPMAT_MSG, with_complex_view
+from .._nufft import spmat as _spmat
+from .interp import with_complex_view
 
 
 def _needs_grad(t: Tensor) -> bool:
@@ -123,9 +124,32 @@ def fft_filter(image: Tensor, kernel: Tensor, norm: Optional[str] = "ortho") -> 
 
 def kb_spmat_nufft(image: Tensor, scaling_coef: Tensor, im_size: Tensor, grid_size: Tensor,
                    interp_mats: Tuple[Tensor, Tensor], norm: Optional[str] = None) -> Tensor:
-    raise NotImplementedError(_SPMAT_MSG)
+    """Forward NUFFT with sparse-matrix interpolation (reference ``functional/nufft.py:11-64``): the
+    engine's apodise/pad/FFT step, then ``torch.sparse`` for the interpolation (API-completeness shim)."""
+    def run(x: Tensor) -> Tensor:
+        normalized = _fft.check_norm(norm)
+        sizes = _ints(grid_size)
+        scale = _fft.ortho_scale(sizes, normalized)
+        if _fft.fused_fft_available(x.dtype, sizes):
+            grid = FusedFftForward.apply(x, None, scaling_coef, sizes, scale)
+        else:
+            grid = _fft.fft_grid(ApodPad.apply(x, None, scaling_coef, sizes, scale), len(sizes), inverse=False)
+        return _spmat.spmat_interp(grid, interp_mats)
+
+    return with_complex_view(run, image)
 
 
 def kb_spmat_nufft_adjoint(data: Tensor, scaling_coef: Tensor, im_size: Tensor, grid_size: Tensor,
                            interp_mats: Tuple[Tensor, Tensor], norm: Optional[str] = None) -> Tensor:
-    raise NotImplementedError(_SPMAT_MSG)
+    """Adjoint NUFFT with sparse-matrix interpolation (reference ``functional/nufft.py:67-123``)."""
+    def run(y: Tensor) -> Tensor:
+        normalized = _fft.check_norm(norm)
+        sizes = _ints(grid_size)
+        scale = _fft.ortho_scale(sizes, normalized)
+        grid = _spmat.spmat_interp_adjoint(y, interp_mats, sizes)
+        if _fft.fused_fft_available(y.dtype, sizes):
+            return FusedFftAdjoint.apply(grid, None, scaling_coef, _ints(im_size), scale)
+        grid = _fft.fft_grid(grid, len(sizes), inverse=True)
+        return CropApodCoilsum.apply(grid, None, scaling_coef, _ints(im_size), scale)
+
+    return with_complex_view(run, data)
