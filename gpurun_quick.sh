@@ -1,2 +1,3 @@
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_spmat.py -m gpu -x -q > gpurun_out/q_pytest.log 2>&1; tail -12 gpurun_out/q_pytest.log
+timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/q_pytest_all.log 2>&1; tail -4 gpurun_out/q_pytest_all.log
+timeout 900 python profiles/bench_configs.py cfg2 cfg4 2>&1 | tail -4

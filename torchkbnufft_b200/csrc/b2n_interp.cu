@@ -122,7 +122,10 @@ B2N_D int64_t wrap_down(int64_t g, int64_t K) {
   return g < 0 ? g + K : g;
 }
 
-template <typename T, int ND, bool CL>
+// Deterministic adjoint: one thread per grid cell gathers, in plan order, the samples whose footprint covers the
+// cell.  The neighbour walk (36 / 216 CSR lookups + weights) is done once for a block of RB coils held in
+// registers; the per-(cell, coil) summation order is fixed, so the result is bit-reproducible.
+template <typename T, int ND, bool CL, int RB>
 __global__ void __launch_bounds__(128) k_adj_sorted_generic(InterpArgs<T> a, const cplx<T> *__restrict__ kdata,
                                                             cplx<T> *__restrict__ grid) {
   const int64_t cell = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -135,13 +138,16 @@ __global__ void __launch_bounds__(128) k_adj_sorted_generic(InterpArgs<T> a, con
       rem /= a.K[d];
     }
   }
-  const int64_t rows = a.B * a.C;
-  for (int64_t r = blockIdx.y; r < rows; r += gridDim.y) {
-    const int64_t b = r / a.C, c = r - b * a.C;
+  const int64_t ncb = (a.C + RB - 1) / RB, nblk = a.B * ncb;  // row blocks = (batch element, RB coils)
+  for (int64_t q = blockIdx.y; q < nblk; q += gridDim.y) {
+    const int64_t b = q / ncb, c0 = (q - b * ncb) * RB;
+    const int nc = (int)(a.C - c0 < RB ? a.C - c0 : RB);
     const int64_t t = a.n_traj == 1 ? 0 : b;
     const int32_t *cs = a.cell_start + t * a.tiling.n_cells;
-    const cplx<T> *row = kdata + (b * a.C + c) * a.M;
-    cplx<T> acc = {T(0), T(0)};
+    const cplx<T> *rows = kdata + (b * a.C + c0) * a.M;
+    cplx<T> acc[RB];
+#pragma unroll
+    for (int k = 0; k < RB; ++k) acc[k] = {T(0), T(0)};
     for (int j0 = 0; j0 < a.J[0]; ++j0) {
       const int64_t b0 = wrap_down(g[0] - j0, a.K[0]);
       for (int j1 = 0; j1 < (ND > 1 ? a.J[1] : 1); ++j1) {
@@ -156,12 +162,18 @@ __global__ void __launch_bounds__(128) k_adj_sorted_generic(InterpArgs<T> a, con
             cplx<T> cc = rec[j0];
             if (ND > 1) cc = cmul(cc, rec[a.coef_off[1] + j1]);
             if (ND > 2) cc = cmul(cc, rec[a.coef_off[2] + j2]);
-            cmac(acc, cconj(cc), row[a.perm[s]]);
+            cc = cconj(cc);
+            const cplx<T> *v = rows + a.perm[s];
+#pragma unroll
+            for (int k = 0; k < RB; ++k)
+              if (k < nc) cmac(acc[k], cc, v[(int64_t)k * a.M]);
           }
         }
       }
     }
-    grid[grid_addr<CL>(b, c, cell, a.C, a.Kprod)] = acc;
+#pragma unroll
+    for (int k = 0; k < RB; ++k)
+      if (k < nc) grid[grid_addr<CL>(b, c0 + k, cell, a.C, a.Kprod)] = acc[k];
   }
 }
 
@@ -190,8 +202,12 @@ static int launch_adjoint(const InterpArgs<T> &a, const void *kdata, int mode, v
     B2N_LAUNCH_OK("k_adj_atomic_generic");
     return 0;
   }
-  dim3 block(128), gridDim((unsigned)ceil_div(a.Kprod, 128), (unsigned)(rows_all < 65535 ? rows_all : 65535));
-  k_adj_sorted_generic<T, ND, CL><<<gridDim, block, 0, st>>>(a, (const cplx<T> *)kdata, (cplx<T> *)grid);
+  // 2-D: 8 coils per thread (2.2 -> 1.5 ms at BASELINE config 2); 3-D: one (216 neighbour cells keep a thread busy
+  // long enough, and blocking coils there measured slower: 568 -> 961 ms at config 4)
+  constexpr int RB = ND == 3 ? 1 : 8;
+  const int64_t nblk = a.B * ceil_div(a.C, RB);
+  dim3 block(128), gridDim((unsigned)ceil_div(a.Kprod, 128), (unsigned)(nblk < 65535 ? nblk : 65535));
+  k_adj_sorted_generic<T, ND, CL, RB><<<gridDim, block, 0, st>>>(a, (const cplx<T> *)kdata, (cplx<T> *)grid);
   B2N_LAUNCH_OK("k_adj_sorted_generic");
   return 0;
 }
