@@ -32,7 +32,7 @@ extern "C" {
 #define B2N_API
 #endif
 
-#define B2N_ABI_VERSION 1
+#define B2N_ABI_VERSION 2
 #define B2N_MAX_DIMS 3
 #define B2N_MAX_NUMPOINTS 16 /* max neighbours J per dimension */
 
@@ -98,6 +98,10 @@ typedef struct b2n_points {
   int32_t *sub_start;  /* [n_sub_max]       first sorted slot */
   int32_t *sub_count;  /* [n_sub_max]       number of points (<= sub_cap) */
   int32_t *n_sub;      /* device scalar: number of sub-problems actually used */
+  int32_t *sub_slot;   /* [n_sub_max]       tile-major rank of each sub-problem: the sub-problems of (traj, tile) t have
+                          the consecutive ranks [tile_sub_start[t], tile_sub_start[t+1]) (the sub_* arrays themselves
+                          are ordered longest-first for load balance) */
+  int32_t *tile_sub_start; /* [n_traj*prod(n_tiles)] first rank of each tile; the last tile ends at *n_sub */
 } b2n_points;
 
 /* engine options (process-wide; for A/B measurements and tests) */
@@ -181,6 +185,17 @@ B2N_API int b2n_crop_apod_coilsum(int ndim, int dtype, const int64_t *im_size, c
  * reference: the Toeplitz filter multiply of fft_filter, _nufft/fft.py:164-173. */
 B2N_API int b2n_spectrum_mul(int dtype, void *spectrum_dev, const void *kernel_dev, int64_t n_batch, int64_t n_coils,
                      int64_t n_grid, int64_t kernel_batch, int grid_layout, double scale, void *stream);
+
+/* Deterministic adjoint on the tiled kernels (2-D complex64, J = 6, coil-major, every K_d >= 21): each sub-problem
+ * accumulates its tile in shared memory in a fixed order and writes it to its own slot of `scratch_dev`; a second
+ * kernel adds, for every grid cell, the slots that cover it in a fixed order.  Bit-reproducible run to run, ~10x
+ * faster than B2N_ADJ_SORTED (which remains the fallback for every other case).
+ * b2n_interp_adjoint_ordered_bytes: scratch size in bytes, 0 when this path does not apply. */
+B2N_API int b2n_interp_adjoint_ordered_bytes(const b2n_geom *geom, const b2n_points *pts, int64_t n_batch, int64_t n_coils,
+                                             int grid_layout, size_t *bytes);
+B2N_API int b2n_interp_adjoint_ordered(const b2n_geom *geom, const b2n_points *pts, const void *kdata_dev, int64_t n_batch,
+                                       int64_t n_coils, int grid_layout, void *scratch_dev, size_t scratch_bytes,
+                                       void *grid_dev, void *stream);
 
 /* ---- pruned, fused FFT passes (complex64, coil-major) --------------------------------
  * Own shared-memory Stockham transforms, one dimension per pass, which skip the zero-padded

@@ -37,7 +37,7 @@ def test_library_exports_every_declared_symbol():
 def test_struct_layouts_match_header_sizes():
     # b2n_geom: 2*int32 + 3*int64 + 3*int32 + 3*int32 + 3*int64 + 3*ptr + 3*double
     assert ctypes.sizeof(_lib.Geom) == 8 + 24 + 12 + 12 + 24 + 24 + 24
-    assert ctypes.sizeof(_lib.Points) == 16 + 16 + 12 + 12 + 16 + 11 * 8
+    assert ctypes.sizeof(_lib.Points) == 16 + 16 + 12 + 12 + 16 + 13 * 8
 
 
 def test_argument_errors_are_status_codes():

@@ -5,6 +5,7 @@ oracle on the same seeded inputs, (c) size-independent properties at BASELINE's
 full sizes.  Tolerances (north_star): complex64 rel-L2 <= 1e-5 forward and <= 1e-4
 adjoint; integer grid / table indices bit-exact; complex128 <= 1e-12.
 """
+import ctypes
 import os
 
 import numpy as np
@@ -587,3 +588,44 @@ def test_cuda_graph_capture_of_forward_adjoint_pair():
         want_im = na(want_k, om, smaps=s)
         assert rel_l2(host(k), host(want_k)) <= 1e-6
         assert rel_l2(host(im), host(want_im)) <= 1e-5
+
+
+@pytest.mark.parametrize("grid_size, B, C, batched", [((64, 64), 1, 16, False), ((70, 66), 2, 3, False),
+                                                      ((21, 40), 1, 1, False), ((96, 50), 3, 5, True),
+                                                      ((37, 128), 1, 32, False)])
+def test_ordered_tiled_adjoint_is_deterministic_and_matches_oracle(grid_size, B, C, batched):
+    """'sorted' mode on the tiled kernels: per-sub-problem scratch tiles + fixed-order merge.  Bit-identical run to
+    run and across plan rebuilds; equal to the oracle and to the per-cell gather within tolerance.  Grids with a
+    partial last tile narrower than the halo (70, 66, 37), wrap-around, dense clumps (many chunks per tile),
+    batched trajectories and coil counts on every CC variant."""
+    rng = np.random.default_rng(hash((grid_size, B, C)) & 0xFFFF)
+    im_size = tuple(max(2, k // 2) for k in grid_size)
+    ob = tkbn.KbInterpAdjoint(im_size=im_size, grid_size=grid_size, dtype=torch.complex64).to(DEV)
+    M = 3000
+    shape = (B, 2, M) if batched else (2, M)
+    omega = rng.uniform(-np.pi, np.pi, size=shape)
+    omega[..., : M // 3] *= 0.05  # dense clump around k = 0: several sub-problems per tile
+    omega = np.ascontiguousarray(omega.astype(np.float32))
+    kdata = workloads.complex_normal(rng, (B, C, M))
+    args = (ob.tables, ob.n_shift, ob.numpoints, ob.table_oversamp)
+    tables = [host(t) for t in ob.tables]
+    J, L, ns = ob.numpoints.tolist(), ob.table_oversamp.tolist(), host(ob.n_shift)
+    want = orc.table_interp_adjoint(kdata, omega, tables, ns, J, L, grid_size, nthreads=4)
+    y, om = dev(kdata), dev(omega)
+    lib = _lib.load()
+    nbytes = ctypes.c_size_t(0)
+    runs = []
+    for rep in range(3):
+        if rep == 2:
+            om = om.clone()  # a new trajectory tensor: the plan is rebuilt
+        runs.append(eng_interp.table_interp_adjoint(y, om, *args, None, ob.grid_size, mode="sorted"))
+    assert torch.equal(runs[0], runs[1]) and torch.equal(runs[0], runs[2])
+    assert rel_l2(host(runs[0]), want) <= 1e-5
+    try:  # the per-cell gather (tiled kernels off) is the other deterministic implementation
+        tkbn.set_tiled_kernels(False)
+        gather = eng_interp.table_interp_adjoint(y, om, *args, None, ob.grid_size, mode="sorted")
+    finally:
+        tkbn.set_tiled_kernels(True)
+    assert rel_l2(host(gather), host(runs[0])) <= 2e-6
+    atomic = eng_interp.table_interp_adjoint(y, om, *args, None, ob.grid_size, mode="atomic")
+    assert rel_l2(host(atomic), host(runs[0])) <= 2e-6

@@ -16,7 +16,7 @@ MAX_NUMPOINTS = 16
 C64, C128 = 0, 1
 COIL_MAJOR, CHANNEL_LAST = 0, 1
 ADJ_ATOMIC, ADJ_SORTED = 0, 1
-ABI_VERSION = 1
+ABI_VERSION = 2
 OPT_TILED_KERNELS = 0
 OPT_ADJ_ROW_OWNERSHIP = 1
 OPT_FWD_COIL_CHUNK = 2
@@ -67,6 +67,8 @@ class Points(Structure):
         ("sub_start", c_void_p),
         ("sub_count", c_void_p),
         ("n_sub", c_void_p),
+        ("sub_slot", c_void_p),
+        ("tile_sub_start", c_void_p),
     ]
 
 
@@ -91,6 +93,10 @@ SIGNATURES = {
                                    c_void_p]),
     "b2n_interp_adjoint": (c_int, [POINTER(Geom), POINTER(Points), c_void_p, c_int64, c_int64, c_int, c_int,
                                    c_void_p, c_void_p]),
+    "b2n_interp_adjoint_ordered_bytes": (c_int, [POINTER(Geom), POINTER(Points), c_int64, c_int64, c_int,
+                                                 POINTER(c_size_t)]),
+    "b2n_interp_adjoint_ordered": (c_int, [POINTER(Geom), POINTER(Points), c_void_p, c_int64, c_int64, c_int, c_void_p,
+                                           c_size_t, c_void_p, c_void_p]),
     "b2n_apod_pad": (c_int, [c_int, c_int, _I64P, _I64P, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_int64,
                              c_void_p, c_double, c_int, c_void_p, c_void_p]),
     "b2n_crop_apod_coilsum": (c_int, [c_int, c_int, _I64P, _I64P, c_int64, c_int64, c_void_p, c_int, c_void_p,

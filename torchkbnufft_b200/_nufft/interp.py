@@ -174,13 +174,30 @@ def table_interp_adjoint(
     if out.numel() == 0:
         return out
     mode_id = ADJOINT_MODES[_default_adjoint_mode if mode is None else mode]
+    lib = _lib.load()
     with device_guard(data.device):
         stop = kernel_timer.bracket("interp_adj", data.device) if kernel_timer is not None else None
-        _lib.check(
-            _lib.load().b2n_interp_adjoint(ctypes.byref(geo.struct), ctypes.byref(plan.struct), data.data_ptr(), B, C,
-                                           layout, mode_id, out.data_ptr(), current_stream_ptr(data.device)),
-            "b2n_interp_adjoint",
-        )
+        scratch_bytes = ctypes.c_size_t(0)
+        if mode_id == _lib.ADJ_SORTED:
+            # deterministic mode: the tiled kernels with per-sub-problem scratch tiles and a fixed-order merge where
+            # they apply (2-D complex64, J = 6), else the per-cell gather
+            _lib.check(lib.b2n_interp_adjoint_ordered_bytes(ctypes.byref(geo.struct), ctypes.byref(plan.struct), B, C,
+                                                            layout, ctypes.byref(scratch_bytes)),
+                       "b2n_interp_adjoint_ordered_bytes")
+        if scratch_bytes.value:
+            scratch = torch.empty(scratch_bytes.value, dtype=torch.uint8, device=data.device)
+            _lib.check(
+                lib.b2n_interp_adjoint_ordered(ctypes.byref(geo.struct), ctypes.byref(plan.struct), data.data_ptr(), B,
+                                               C, layout, scratch.data_ptr(), scratch_bytes.value, out.data_ptr(),
+                                               current_stream_ptr(data.device)),
+                "b2n_interp_adjoint_ordered",
+            )
+        else:
+            _lib.check(
+                lib.b2n_interp_adjoint(ctypes.byref(geo.struct), ctypes.byref(plan.struct), data.data_ptr(), B, C,
+                                       layout, mode_id, out.data_ptr(), current_stream_ptr(data.device)),
+                "b2n_interp_adjoint",
+            )
         if stop is not None:
             stop.record(torch.cuda.current_stream(data.device))
     return out

@@ -249,6 +249,10 @@ int tiled3_forward(const b2n_geom *g, const b2n_points *p, const void *grid, int
 int tiled3_adjoint(const b2n_geom *g, const b2n_points *p, const void *kdata, int64_t B, int64_t C, int layout,
                    void *grid, cudaStream_t st);
 
+size_t tiled_adjoint_ordered_bytes(const b2n_geom *g, const b2n_points *p, int64_t B, int64_t C, int layout);
+int tiled_adjoint_ordered(const b2n_geom *g, const b2n_points *p, const void *kdata, int64_t B, int64_t C, int layout,
+                          void *scratch, size_t scratch_bytes, void *grid, cudaStream_t st);
+
 long long *g_trace_buffer = nullptr;
 int64_t g_trace_capacity = 0;
 extern int g_adj_rowwarp;
@@ -324,4 +328,21 @@ extern "C" int b2n_interp_adjoint(const b2n_geom *geom, const b2n_points *pts, c
   if (geom->dtype == B2N_C128)
     return adjoint_t<double>(geom, pts, kdata_dev, n_batch, n_coils, grid_layout, mode, grid_dev, st);
   return fail_arg(B2N_E_ARG, "bad dtype");
+}
+
+extern "C" int b2n_interp_adjoint_ordered_bytes(const b2n_geom *geom, const b2n_points *pts, int64_t n_batch,
+                                                int64_t n_coils, int grid_layout, size_t *bytes) {
+  if (!geom || !pts || !bytes) return fail_arg(B2N_E_ARG, "NULL geom/pts/bytes");
+  if (n_batch < 1 || n_coils < 1)
+    return fail_arg(B2N_E_ARG, "n_batch=%lld n_coils=%lld", (long long)n_batch, (long long)n_coils);
+  *bytes = g_options[B2N_OPT_TILED_KERNELS] ? tiled_adjoint_ordered_bytes(geom, pts, n_batch, n_coils, grid_layout) : 0;
+  return 0;
+}
+
+extern "C" int b2n_interp_adjoint_ordered(const b2n_geom *geom, const b2n_points *pts, const void *kdata_dev,
+                                          int64_t n_batch, int64_t n_coils, int grid_layout, void *scratch_dev,
+                                          size_t scratch_bytes, void *grid_dev, void *stream) {
+  if (!geom || !pts || !grid_dev || !kdata_dev) return fail_arg(B2N_E_ARG, "NULL geom/pts/grid/kdata");
+  return tiled_adjoint_ordered(geom, pts, kdata_dev, n_batch, n_coils, grid_layout, scratch_dev, scratch_bytes, grid_dev,
+                               (cudaStream_t)stream);
 }

@@ -23,6 +23,7 @@ template <typename T> struct InterpArgs {
   const cplx<T> *phase;
   const int32_t *cell_start;
   const int32_t *sub_tile, *sub_start, *sub_count, *n_sub;
+  const int32_t *sub_slot, *tile_sub_start;
   int64_t n_sub_max;
   int sub_cap;
   Tiling tiling;
@@ -67,6 +68,8 @@ static inline int make_args(const b2n_geom *g, const b2n_points *p, int64_t B, i
   a->sub_start = p->sub_start;
   a->sub_count = p->sub_count;
   a->n_sub = p->n_sub;
+  a->sub_slot = p->sub_slot;
+  a->tile_sub_start = p->tile_sub_start;
   a->n_sub_max = p->n_sub_max;
   a->sub_cap = p->sub_cap;
   a->trace = g_trace_buffer;

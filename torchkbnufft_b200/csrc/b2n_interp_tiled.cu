@@ -445,10 +445,14 @@ template <int CC> constexpr int adj_stage_slots() { return (kRound * kNC + (kRou
 // NW warps per CTA: warp w owns the tile rows r with r mod NW == w.  NW = 8: one footprint row per
 // (point, warp); NW = 4: one or two rows, with the per-point loads (base cell, sample, x-weights)
 // shared by both -- fewer shared-memory wavefronts per point, fewer warps to hide latency with.
-template <int CC, int NW>
+// ORDERED: instead of adding the tile into the grid (TMA reduce / atomics, arrival order), store it to this
+// sub-problem's slot of `scratch` ([rank][batch][coil][kPS]); k_adj_merge_2d then adds the slots per cell in a
+// fixed order.  The in-tile accumulation is order-fixed already (one warp per cell, points in plan order).
+template <int CC, int NW, bool ORDERED = false>
 __global__ void __launch_bounds__(NW * 32) k_adj_tiled_2d(InterpArgs<float> a, const float2 *__restrict__ kdata,
                                                            float2 *__restrict__ grid,
-                                                           const __grid_constant__ CUtensorMap tmap, int use_tma) {
+                                                           const __grid_constant__ CUtensorMap tmap, int use_tma,
+                                                           float2 *__restrict__ scratch = nullptr) {
   constexpr int QX = 32 / CC, NX = (kJ + QX - 1) / QX;
   constexpr int NT = NW * 32;
   // staged samples are coil-major with an odd row stride: the gather writes 32 consecutive points of one
@@ -558,6 +562,15 @@ __global__ void __launch_bounds__(NW * 32) k_adj_tiled_2d(InterpArgs<float> a, c
     }
   }
   const long long t_accum = a.trace ? gtime() : 0;
+  if (ORDERED) {
+    __syncthreads();
+    const int ncoil = min(CC, C - sp.c0);
+    const int64_t slot = a.sub_slot[blockIdx.x];
+    float4 *dst = reinterpret_cast<float4 *>(scratch + ((slot * gridDim.z + blockIdx.z) * C + sp.c0) * kPS);
+    const float4 *src = reinterpret_cast<const float4 *>(tile);
+    for (int e = threadIdx.x; e < ncoil * (kPS / 2); e += NT) dst[e] = src[e];
+    return;
+  }
   // merge the tile into the global grid
   if (use_tma && sp.interior) {
     fence_async_proxy();  // generic-proxy writes to shared memory -> visible to the TMA engine
@@ -924,6 +937,70 @@ int g_adj_rowwarp = 0;
 int g_adj_chunk = 0;     // A/B switch: adjoint coil chunk per CTA for C > 8 (0 = 16, 8 = two 8-coil CTAs)
 int g_fwd_chunk = 0;     // A/B switch for C > 8: 0 = one 16-coil CTA per sub-problem, 1 = persistent kernel, 8 = 8-coil CTAs  // A/B switch: 1 = row-ownership kernel also for 16-coil chunks
 
+// -----------------------------------------------------------------------------------------
+// deterministic merge of the per-sub-problem tiles written by k_adj_tiled_2d<.., ORDERED = true>:
+// every grid cell adds the slots of the tiles whose 21 x 21 footprint covers it -- the tile the
+// cell lies in and up to two predecessors per dimension (one normally; two when the last tile of a
+// dimension is narrower than the halo) -- in a fixed order.  Writes every cell: no memset.
+// -----------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_adj_merge_2d(InterpArgs<float> a, const float2 *__restrict__ scratch,
+                                                      float2 *__restrict__ grid) {
+  const int64_t cell = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (cell >= a.Kprod) return;
+  const int Ky = (int)a.K[0], Kx = (int)a.K[1], C = (int)a.C;
+  const int y = (int)(cell / Kx), x = (int)(cell - (int64_t)y * Kx);
+  const int nty = a.tiling.nt[0], ntx = a.tiling.nt[1];
+  const int64_t n_tiles = a.tiling.n_tiles, n_tiles_all = a.n_traj * n_tiles;
+  const int n_sub = *a.n_sub;
+  const int64_t Bz = a.n_traj == 1 ? a.B : 1;
+  const int64_t rows = a.B * a.C;
+  for (int64_t r = blockIdx.y; r < rows; r += gridDim.y) {
+    const int64_t b = r / C, c = r - b * C;
+    const int64_t traj = a.n_traj == 1 ? 0 : b, bz = a.n_traj == 1 ? b : 0;
+    float2 acc = make_float2(0.f, 0.f);
+    for (int ky = 0; ky < min(3, nty); ++ky) {
+      int ty = y / kTile - ky;
+      if (ty < 0) ty += nty;
+      int ry = y - ty * kTile;
+      if (ry < 0) ry += Ky;
+      if (ry >= kSY) continue;
+      for (int kx = 0; kx < min(3, ntx); ++kx) {
+        int tx = x / kTile - kx;
+        if (tx < 0) tx += ntx;
+        int rx = x - tx * kTile;
+        if (rx < 0) rx += Kx;
+        if (rx >= kSY) continue;  // column kSX-1 of a plane is alignment padding, never accumulated
+        const int64_t t = traj * n_tiles + (int64_t)ty * ntx + tx;
+        const int s0 = a.tile_sub_start[t], s1 = t + 1 < n_tiles_all ? a.tile_sub_start[t + 1] : n_sub;
+        for (int sl = s0; sl < s1; ++sl) {
+          const float2 v = scratch[(((int64_t)sl * Bz + bz) * C + c) * kPS + ry * kSX + rx];
+          acc.x += v.x;
+          acc.y += v.y;
+        }
+      }
+    }
+    grid[(b * C + c) * a.Kprod + cell] = acc;
+  }
+}
+
+template <int CC>
+static int launch_adj_ordered(const InterpArgs<float> &a, const void *kdata, void *scratch, void *grid, cudaStream_t st) {
+  const size_t smem =
+      sizeof(float2) * (planes<CC>() * kPS + 2 * adj_stage_slots<CC>()) + sizeof(int) * 3 * kRound;
+  auto kern = k_adj_tiled_2d<CC, kWarps, true>;
+  B2N_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CUtensorMap map;
+  memset(&map, 0, sizeof(map));
+  dim3 gd((unsigned)a.n_sub_max, (unsigned)ceil_div(a.C, CC), (unsigned)(a.n_traj == 1 ? a.B : 1));
+  kern<<<gd, kThreads, smem, st>>>(a, (const float2 *)kdata, (float2 *)grid, map, 0, (float2 *)scratch);
+  B2N_LAUNCH_OK("k_adj_tiled_2d<ordered>");
+  const int64_t rows = a.B * a.C;
+  dim3 gm((unsigned)ceil_div(a.Kprod, 256), (unsigned)(rows < 65535 ? rows : 65535));
+  k_adj_merge_2d<<<gm, 256, 0, st>>>(a, (const float2 *)scratch, (float2 *)grid);
+  B2N_LAUNCH_OK("k_adj_merge_2d");
+  return 0;
+}
+
 static bool tiled_eligible(const b2n_geom *g, const b2n_points *p, int layout) {
   return g->dtype == B2N_C64 && g->ndim == 2 && layout == B2N_COIL_MAJOR && g->numpoints[0] == kJ &&
          g->numpoints[1] == kJ && p->tile[0] == kTile && p->tile[1] == kTile && p->n_points > 0 &&
@@ -972,7 +1049,7 @@ static int launch_adj(const InterpArgs<float> &a, const void *kdata, void *grid,
   memset(&map, 0, sizeof(map));
   const int use_tma = make_grid_tmap(&map, grid, a.B, a.C, a.K[0], a.K[1]) ? 1 : 0;
   dim3 gd((unsigned)a.n_sub_max, (unsigned)ceil_div(a.C, CC), (unsigned)(a.n_traj == 1 ? a.B : 1));
-  kern<<<gd, NW * 32, smem, st>>>(a, (const float2 *)kdata, (float2 *)grid, map, use_tma);
+  kern<<<gd, NW * 32, smem, st>>>(a, (const float2 *)kdata, (float2 *)grid, map, use_tma, (float2 *)nullptr);
   B2N_LAUNCH_OK("k_adj_tiled_2d");
   return 0;
 }
@@ -1044,6 +1121,36 @@ int tiled_adjoint(const b2n_geom *g, const b2n_points *p, const void *kdata, int
   if (C > 2) return launch_adj<4>(a, kdata, grid, st);
   if (C > 1) return launch_adj<2>(a, kdata, grid, st);
   return launch_adj<1>(a, kdata, grid, st);
+}
+
+static bool ordered_eligible(const b2n_geom *g, const b2n_points *p, int layout) {
+  return tiled_eligible(g, p, layout) && g->grid_size[0] >= kSY && g->grid_size[1] >= kSY && p->sub_slot &&
+         p->tile_sub_start;
+}
+
+// scratch bytes of the deterministic tiled adjoint, 0 when it does not apply
+size_t tiled_adjoint_ordered_bytes(const b2n_geom *g, const b2n_points *p, int64_t B, int64_t C, int layout) {
+  if (!ordered_eligible(g, p, layout)) return 0;
+  const int64_t Bz = p->n_traj == 1 ? B : 1;
+  return sizeof(float2) * (size_t)p->n_sub_max * (size_t)Bz * (size_t)C * kPS;
+}
+
+int tiled_adjoint_ordered(const b2n_geom *g, const b2n_points *p, const void *kdata, int64_t B, int64_t C, int layout,
+                          void *scratch, size_t scratch_bytes, void *grid, cudaStream_t st) {
+  if (!ordered_eligible(g, p, layout))
+    return fail_arg(B2N_E_UNSUPPORTED, "ordered adjoint: 2-D complex64 J=6 coil-major grids of at least 21 cells only");
+  if (!scratch || scratch_bytes < tiled_adjoint_ordered_bytes(g, p, B, C, layout))
+    return fail_arg(B2N_E_ARG, "ordered adjoint: scratch too small");
+  if ((reinterpret_cast<uintptr_t>(scratch) & 15) != 0)
+    return fail_arg(B2N_E_ARG, "ordered adjoint: scratch must be 16-byte aligned");
+  InterpArgs<float> a;
+  int rc = make_args<float>(g, p, B, C, &a);
+  if (rc) return rc;
+  if (C > 8) return launch_adj_ordered<16>(a, kdata, scratch, grid, st);
+  if (C > 4) return launch_adj_ordered<8>(a, kdata, scratch, grid, st);
+  if (C > 2) return launch_adj_ordered<4>(a, kdata, scratch, grid, st);
+  if (C > 1) return launch_adj_ordered<2>(a, kdata, scratch, grid, st);
+  return launch_adj_ordered<1>(a, kdata, scratch, grid, st);
 }
 
 }  // namespace b2n

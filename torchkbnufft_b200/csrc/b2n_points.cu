@@ -348,6 +348,8 @@ static int build_impl(const b2n_geom *geom, const void *omega, int64_t M, int64_
   out->sub_start = (int32_t *)(ws + c.sub_start);
   out->sub_count = (int32_t *)(ws + c.sub_count);
   out->n_sub = (int32_t *)(ws + c.n_sub);
+  out->sub_slot = (int32_t *)(ws + c.sub_order);      // LPT position -> tile-major rank (output of the LPT sort)
+  out->tile_sub_start = (int32_t *)(ws + c.offsets);  // exclusive scan of the chunk counts per tile
   out->perm = (int32_t *)(ws + c.perm);
   out->inv_perm = (int32_t *)(ws + c.inv_perm);
   out->base = (int32_t *)(ws + c.base);
