@@ -943,6 +943,7 @@ int g_fwd_chunk = 0;     // A/B switch for C > 8: 0 = one 16-coil CTA per sub-pr
 // cell lies in and up to two predecessors per dimension (one normally; two when the last tile of a
 // dimension is narrower than the halo) -- in a fixed order.  Writes every cell: no memset.
 // -----------------------------------------------------------------------------------------
+constexpr int kMergeCoils = 8;  // coils per thread of the merge: the tile / slot walk is shared by all of them
 __global__ void __launch_bounds__(256) k_adj_merge_2d(InterpArgs<float> a, const float2 *__restrict__ scratch,
                                                       float2 *__restrict__ grid) {
   const int64_t cell = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -953,11 +954,14 @@ __global__ void __launch_bounds__(256) k_adj_merge_2d(InterpArgs<float> a, const
   const int64_t n_tiles = a.tiling.n_tiles, n_tiles_all = a.n_traj * n_tiles;
   const int n_sub = *a.n_sub;
   const int64_t Bz = a.n_traj == 1 ? a.B : 1;
-  const int64_t rows = a.B * a.C;
-  for (int64_t r = blockIdx.y; r < rows; r += gridDim.y) {
-    const int64_t b = r / C, c = r - b * C;
+  const int64_t ncb = (C + kMergeCoils - 1) / kMergeCoils, nblk = a.B * ncb;  // (batch element, coil block)
+  for (int64_t q = blockIdx.y; q < nblk; q += gridDim.y) {
+    const int64_t b = q / ncb, c0 = (q - b * ncb) * kMergeCoils;
+    const int nc = (int)(C - c0 < kMergeCoils ? C - c0 : kMergeCoils);
     const int64_t traj = a.n_traj == 1 ? 0 : b, bz = a.n_traj == 1 ? b : 0;
-    float2 acc = make_float2(0.f, 0.f);
+    float2 acc[kMergeCoils];
+#pragma unroll
+    for (int k = 0; k < kMergeCoils; ++k) acc[k] = make_float2(0.f, 0.f);
     for (int ky = 0; ky < min(3, nty); ++ky) {
       int ty = y / kTile - ky;
       if (ty < 0) ty += nty;
@@ -973,13 +977,20 @@ __global__ void __launch_bounds__(256) k_adj_merge_2d(InterpArgs<float> a, const
         const int64_t t = traj * n_tiles + (int64_t)ty * ntx + tx;
         const int s0 = a.tile_sub_start[t], s1 = t + 1 < n_tiles_all ? a.tile_sub_start[t + 1] : n_sub;
         for (int sl = s0; sl < s1; ++sl) {
-          const float2 v = scratch[(((int64_t)sl * Bz + bz) * C + c) * kPS + ry * kSX + rx];
-          acc.x += v.x;
-          acc.y += v.y;
+          const float2 *src = scratch + (((int64_t)sl * Bz + bz) * C + c0) * kPS + ry * kSX + rx;
+#pragma unroll
+          for (int k = 0; k < kMergeCoils; ++k)
+            if (k < nc) {
+              const float2 v = src[(int64_t)k * kPS];
+              acc[k].x += v.x;
+              acc[k].y += v.y;
+            }
         }
       }
     }
-    grid[(b * C + c) * a.Kprod + cell] = acc;
+#pragma unroll
+    for (int k = 0; k < kMergeCoils; ++k)
+      if (k < nc) grid[(b * C + c0 + k) * a.Kprod + cell] = acc[k];
   }
 }
 
@@ -994,8 +1005,8 @@ static int launch_adj_ordered(const InterpArgs<float> &a, const void *kdata, voi
   dim3 gd((unsigned)a.n_sub_max, (unsigned)ceil_div(a.C, CC), (unsigned)(a.n_traj == 1 ? a.B : 1));
   kern<<<gd, kThreads, smem, st>>>(a, (const float2 *)kdata, (float2 *)grid, map, 0, (float2 *)scratch);
   B2N_LAUNCH_OK("k_adj_tiled_2d<ordered>");
-  const int64_t rows = a.B * a.C;
-  dim3 gm((unsigned)ceil_div(a.Kprod, 256), (unsigned)(rows < 65535 ? rows : 65535));
+  const int64_t nblk = a.B * ceil_div(a.C, kMergeCoils);
+  dim3 gm((unsigned)ceil_div(a.Kprod, 256), (unsigned)(nblk < 65535 ? nblk : 65535));
   k_adj_merge_2d<<<gm, 256, 0, st>>>(a, (const float2 *)scratch, (float2 *)grid);
   B2N_LAUNCH_OK("k_adj_merge_2d");
   return 0;
