@@ -295,11 +295,13 @@ def main():
     torch.cuda.synchronize()
     sampler.start()
     eng_interp.kernel_timer = eng_interp.KernelTimer()  # events around the two interpolation launches
+    launches_before = int(_lib.load().b2n_launch_count())
     for i in range(args.steps):
         flush.fill_(i & 0xFF)
         starts[i].record()
         step()
         ends[i].record()
+    gpu_launches = int(_lib.load().b2n_launch_count()) - launches_before  # counted by the library at every launch
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -503,7 +505,10 @@ def main():
             "stages_ms": {k: round(v, 5) for k, v in stages.items()},
             "cpu_baseline": cpu_baseline,
             "e2e": e2e,
-            "gpu_launches": (7 if fused else 5) * args.steps,  # own kernels per step (memset / cuFFT not counted)
+            # kernels of libb200nufft.so launched inside the timed region, counted by the library itself
+            # (b2n_launch_count; 6 per step with the own FFT passes: rows, columns, gather / spread, columns,
+            # rows + coil sum; cudaMemsetAsync, the L2-flush fill and cuFFT are not counted)
+            "gpu_launches": gpu_launches,
             "clocks": clocks,
         }
         print(json.dumps(line), flush=True)

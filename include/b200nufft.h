@@ -128,6 +128,9 @@ B2N_API int b2n_set_trace_buffer(void *records_dev, int64_t capacity);
 
 B2N_API int b2n_abi_version(void);
 B2N_API const char *b2n_last_error(void);
+/* Number of kernels of this library launched by the process so far (every launch of an own kernel counts; memsets and
+ * cuFFT do not). */
+B2N_API long long b2n_launch_count(void);
 /* number of CUDA devices visible; 0 when there is none or the driver is unusable
  * (b2n_last_error() then says why) */
 B2N_API int b2n_device_count(void);

@@ -80,6 +80,7 @@ class EngineError(RuntimeError):
 _I64P = POINTER(c_int64)
 SIGNATURES = {
     "b2n_abi_version": (c_int, []),
+    "b2n_launch_count": (ctypes.c_longlong, []),
     "b2n_last_error": (c_char_p, []),
     "b2n_device_count": (c_int, []),
     "b2n_set_option": (c_int, [c_int, c_int]),

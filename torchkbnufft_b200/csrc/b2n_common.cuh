@@ -20,6 +20,7 @@ namespace b2n {
 void set_error(const char *fmt, ...);
 int fail_arg(int code, const char *fmt, ...);
 int check_cuda(cudaError_t err, const char *what);
+void count_launch();
 
 #define B2N_CUDA_OK(expr)                                  \
   do {                                                     \
@@ -27,10 +28,13 @@ int check_cuda(cudaError_t err, const char *what);
     if (_rc != 0) return _rc;                              \
   } while (0)
 
+// after every launch of one of the library's own kernels: error check + the process-wide launch counter
+// (b2n_launch_count(); benchmarks report it as evidence that the native kernels ran)
 #define B2N_LAUNCH_OK(name)                                \
   do {                                                     \
     int _rc = ::b2n::check_cuda(cudaGetLastError(), name); \
     if (_rc != 0) return _rc;                              \
+    ::b2n::count_launch();                                 \
   } while (0)
 
 template <typename T> struct cplx { T x, y; };

@@ -8,6 +8,8 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <atomic>
+
 #include "b2n_common.cuh"
 #include "b2n_math.cuh"
 #include "b2n_tiling.cuh"
@@ -16,6 +18,8 @@
 namespace b2n {
 
 static thread_local char g_error[512] = "";
+static std::atomic<long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 void set_error(const char *fmt, ...) {
   va_list ap;
@@ -408,6 +412,7 @@ using namespace b2n;
 
 extern "C" int b2n_abi_version(void) { return B2N_ABI_VERSION; }
 extern "C" const char *b2n_last_error(void) { return g_error; }
+extern "C" long long b2n_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 extern "C" int b2n_device_count(void) {
   int n = 0;
