@@ -1,4 +1,3 @@
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "ordered or cfg2" > gpurun_out/q_pytest.log 2>&1; tail -3 gpurun_out/q_pytest.log
-timeout 900 python profiles/bench_configs.py cfg2 cfg5 2>&1 | tail -3
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'k_adj_merge|k_adj_tiled' -c 6 --csv python bench.py --steps 3 --warmup 3 --no-cpu-baseline --adjoint-mode sorted 2>/dev/null | grep -E "k_adj" | cut -d'"' -f10,30 | cut -c1-100 | tail -4
+timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "tiled or cfg2 or edge or cases or ordered" > gpurun_out/q_pytest.log 2>&1; tail -3 gpurun_out/q_pytest.log
+timeout 600 python bench.py --steps 100 --warmup 3 --breakdown --no-cpu-baseline 2>&1 | grep -E "stage ms|step ms"
