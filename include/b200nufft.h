@@ -189,7 +189,8 @@ B2N_API int b2n_crop_apod_coilsum(int ndim, int dtype, const int64_t *im_size, c
 B2N_API int b2n_spectrum_mul(int dtype, void *spectrum_dev, const void *kernel_dev, int64_t n_batch, int64_t n_coils,
                      int64_t n_grid, int64_t kernel_batch, int grid_layout, double scale, void *stream);
 
-/* Deterministic adjoint on the tiled kernels (2-D complex64, J = 6, coil-major, every K_d >= 21): each sub-problem
+/* Deterministic adjoint on the tiled kernels (complex64, J = 6, coil-major; 2-D with every K_d >= 21 or 3-D with every
+ * K_d >= 13): each sub-problem
  * accumulates its tile in shared memory in a fixed order and writes it to its own slot of `scratch_dev`; a second
  * kernel adds, for every grid cell, the slots that cover it in a fixed order.  Bit-reproducible run to run, ~10x
  * faster than B2N_ADJ_SORTED (which remains the fallback for every other case).

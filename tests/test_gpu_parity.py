@@ -629,3 +629,30 @@ def test_ordered_tiled_adjoint_is_deterministic_and_matches_oracle(grid_size, B,
     assert rel_l2(host(gather), host(runs[0])) <= 2e-6
     atomic = eng_interp.table_interp_adjoint(y, om, *args, None, ob.grid_size, mode="atomic")
     assert rel_l2(host(atomic), host(runs[0])) <= 2e-6
+
+
+@pytest.mark.parametrize("grid_size, B, C, batched", [((16, 16, 16), 1, 4, False), ((24, 20, 28), 2, 3, False),
+                                                      ((13, 21, 17), 1, 1, False), ((32, 14, 40), 2, 8, True)])
+def test_ordered_tiled_adjoint_3d(grid_size, B, C, batched):
+    """3-D twin of the deterministic tiled adjoint: scratch tiles + 3x3x3 fixed-order merge."""
+    rng = np.random.default_rng(hash((grid_size, B, C)) & 0xFFFF)
+    im_size = tuple(max(2, k // 2) for k in grid_size)
+    ob = tkbn.KbInterpAdjoint(im_size=im_size, grid_size=grid_size, dtype=torch.complex64).to(DEV)
+    M = 2500
+    shape = (B, 3, M) if batched else (3, M)
+    omega = rng.uniform(-np.pi, np.pi, size=shape)
+    omega[..., : M // 3] *= 0.08
+    omega = np.ascontiguousarray(omega.astype(np.float32))
+    kdata = workloads.complex_normal(rng, (B, C, M))
+    args = (ob.tables, ob.n_shift, ob.numpoints, ob.table_oversamp)
+    tables = [host(t) for t in ob.tables]
+    J, L, ns = ob.numpoints.tolist(), ob.table_oversamp.tolist(), host(ob.n_shift)
+    want = orc.table_interp_adjoint(kdata, omega, tables, ns, J, L, grid_size, nthreads=4)
+    y, om = dev(kdata), dev(omega)
+    nbytes = ctypes.c_size_t(0)
+    runs = [eng_interp.table_interp_adjoint(y, om, *args, None, ob.grid_size, mode="sorted") for _ in range(2)]
+    runs.append(eng_interp.table_interp_adjoint(y, om.clone(), *args, None, ob.grid_size, mode="sorted"))
+    assert torch.equal(runs[0], runs[1]) and torch.equal(runs[0], runs[2])
+    assert rel_l2(host(runs[0]), want) <= 1e-5
+    atomic = eng_interp.table_interp_adjoint(y, om, *args, None, ob.grid_size, mode="atomic")
+    assert rel_l2(host(atomic), host(runs[0])) <= 2e-6

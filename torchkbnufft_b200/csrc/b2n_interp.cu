@@ -250,6 +250,9 @@ int tiled3_adjoint(const b2n_geom *g, const b2n_points *p, const void *kdata, in
                    void *grid, cudaStream_t st);
 
 size_t tiled_adjoint_ordered_bytes(const b2n_geom *g, const b2n_points *p, int64_t B, int64_t C, int layout);
+size_t tiled3_adjoint_ordered_bytes(const b2n_geom *g, const b2n_points *p, int64_t B, int64_t C, int layout);
+int tiled3_adjoint_ordered(const b2n_geom *g, const b2n_points *p, const void *kdata, int64_t B, int64_t C, int layout,
+                           void *scratch, size_t scratch_bytes, void *grid, cudaStream_t st);
 int tiled_adjoint_ordered(const b2n_geom *g, const b2n_points *p, const void *kdata, int64_t B, int64_t C, int layout,
                           void *scratch, size_t scratch_bytes, void *grid, cudaStream_t st);
 
@@ -335,7 +338,11 @@ extern "C" int b2n_interp_adjoint_ordered_bytes(const b2n_geom *geom, const b2n_
   if (!geom || !pts || !bytes) return fail_arg(B2N_E_ARG, "NULL geom/pts/bytes");
   if (n_batch < 1 || n_coils < 1)
     return fail_arg(B2N_E_ARG, "n_batch=%lld n_coils=%lld", (long long)n_batch, (long long)n_coils);
-  *bytes = g_options[B2N_OPT_TILED_KERNELS] ? tiled_adjoint_ordered_bytes(geom, pts, n_batch, n_coils, grid_layout) : 0;
+  *bytes = 0;
+  if (g_options[B2N_OPT_TILED_KERNELS]) {
+    *bytes = tiled_adjoint_ordered_bytes(geom, pts, n_batch, n_coils, grid_layout);
+    if (!*bytes) *bytes = tiled3_adjoint_ordered_bytes(geom, pts, n_batch, n_coils, grid_layout);
+  }
   return 0;
 }
 
@@ -343,6 +350,12 @@ extern "C" int b2n_interp_adjoint_ordered(const b2n_geom *geom, const b2n_points
                                           int64_t n_batch, int64_t n_coils, int grid_layout, void *scratch_dev,
                                           size_t scratch_bytes, void *grid_dev, void *stream) {
   if (!geom || !pts || !grid_dev || !kdata_dev) return fail_arg(B2N_E_ARG, "NULL geom/pts/grid/kdata");
+  if (geom->ndim == 3) {
+    const int rc = tiled3_adjoint_ordered(geom, pts, kdata_dev, n_batch, n_coils, grid_layout, scratch_dev, scratch_bytes,
+                                          grid_dev, (cudaStream_t)stream);
+    return rc == 1 ? fail_arg(B2N_E_UNSUPPORTED, "ordered adjoint: 3-D complex64 J=6 coil-major grids of at least 13 cells only")
+                   : rc;
+  }
   return tiled_adjoint_ordered(geom, pts, kdata_dev, n_batch, n_coils, grid_layout, scratch_dev, scratch_bytes, grid_dev,
                                (cudaStream_t)stream);
 }

@@ -179,9 +179,13 @@ __global__ void __launch_bounds__(k3Threads, 2) k_fwd_tiled_3d(InterpArgs<float>
 // -----------------------------------------------------------------------------------------
 // adjoint spread: warp w owns the tile z-planes z = w (mod 8)
 // -----------------------------------------------------------------------------------------
+// ORDERED: store the tile to this sub-problem's scratch slot instead of reducing it into the grid (see
+// k_adj_tiled_2d / k_adj_merge_3d): the deterministic mode.
+template <bool ORDERED>
 __global__ void __launch_bounds__(k3Threads, 2) k_adj_tiled_3d(InterpArgs<float> a, const float2 *__restrict__ kdata,
                                                                float2 *__restrict__ grid,
-                                                               const __grid_constant__ CUtensorMap tmap, int use_tma) {
+                                                               const __grid_constant__ CUtensorMap tmap, int use_tma,
+                                                               float2 *__restrict__ scratch) {
   constexpr int STAGE_F2 = k3Round * k3NC + k3Round * k3CC;  // coef, val (float2); base ints follow
   constexpr int STAGE_BYTES = STAGE_F2 * 8 + k3Round * 3 * 4;
   static_assert(STAGE_BYTES % 16 == 0, "stage buffers keep 16-byte alignment");
@@ -292,6 +296,15 @@ __global__ void __launch_bounds__(k3Threads, 2) k_adj_tiled_3d(InterpArgs<float>
       __syncwarp();
     }
   }
+  if (ORDERED) {
+    __syncthreads();
+    const int ncoil = min(k3CC, C - sp.c0);
+    const int64_t slot = a.sub_slot[blockIdx.x];
+    float4 *dst = reinterpret_cast<float4 *>(scratch + ((slot * gridDim.z + blockIdx.z) * C + sp.c0) * k3PS);
+    const float4 *src = reinterpret_cast<const float4 *>(tile);
+    for (int e = threadIdx.x; e < ncoil * (k3PS / 2); e += k3Threads) dst[e] = src[e];
+    return;
+  }
   // merge the tile into the global grid
   if (use_tma && sp.interior) {
     fence_async_proxy();
@@ -361,14 +374,115 @@ int tiled3_adjoint(const b2n_geom *g, const b2n_points *p, const void *kdata, in
   if (rc) return rc;
   const size_t smem = sizeof(float2) * k3TileF2 + 2 * (sizeof(float2) * (k3Round * k3NC + k3Round * k3CC) + sizeof(int) * k3Round * 3) +
                       sizeof(int) * 3 * k3Round;
-  B2N_CUDA_OK(cudaFuncSetAttribute(k_adj_tiled_3d, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  B2N_CUDA_OK(cudaFuncSetAttribute(k_adj_tiled_3d<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   B2N_CUDA_OK(cudaMemsetAsync(grid, 0, sizeof(float2) * (size_t)(a.B * a.C * a.Kprod), st));
   CUtensorMap map;
   memset(&map, 0, sizeof(map));
   const int use_tma = make_grid_tmap3(&map, grid, a.B, a.C, a.K[0], a.K[1], a.K[2]) ? 1 : 0;
   dim3 gd((unsigned)a.n_sub_max, (unsigned)ceil_div(a.C, k3CC), (unsigned)(a.n_traj == 1 ? a.B : 1));
-  k_adj_tiled_3d<<<gd, k3Threads, smem, st>>>(a, (const float2 *)kdata, (float2 *)grid, map, use_tma);
+  k_adj_tiled_3d<false><<<gd, k3Threads, smem, st>>>(a, (const float2 *)kdata, (float2 *)grid, map, use_tma, nullptr);
   B2N_LAUNCH_OK("k_adj_tiled_3d");
+  return 0;
+}
+
+// -----------------------------------------------------------------------------------------
+// deterministic mode: fixed-order merge of the scratch tiles (3-D twin of k_adj_merge_2d): each grid
+// cell adds the slots of the <= 3 x 3 x 3 tiles whose 13^3 footprint covers it.  Writes every cell.
+// -----------------------------------------------------------------------------------------
+constexpr int k3MergeCoils = 8;
+__global__ void __launch_bounds__(256) k_adj_merge_3d(InterpArgs<float> a, const float2 *__restrict__ scratch,
+                                                      float2 *__restrict__ grid) {
+  const int64_t cell = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (cell >= a.Kprod) return;
+  const int Kz = (int)a.K[0], Ky = (int)a.K[1], Kx = (int)a.K[2], C = (int)a.C;
+  const int z = (int)(cell / ((int64_t)Ky * Kx));
+  const int yx = (int)(cell - (int64_t)z * Ky * Kx), y = yx / Kx, x = yx - y * Kx;
+  const int ntz = a.tiling.nt[0], nty = a.tiling.nt[1], ntx = a.tiling.nt[2];
+  const int64_t n_tiles = a.tiling.n_tiles, n_tiles_all = a.n_traj * n_tiles;
+  const int n_sub = *a.n_sub;
+  const int64_t Bz = a.n_traj == 1 ? a.B : 1;
+  const int64_t ncb = (C + k3MergeCoils - 1) / k3MergeCoils, nblk = a.B * ncb;
+  constexpr int kFoot = k3Tile + k3J - 1;  // 13 accumulated cells per dimension (rows / columns beyond are padding)
+  for (int64_t q = blockIdx.y; q < nblk; q += gridDim.y) {
+    const int64_t b = q / ncb, c0 = (q - b * ncb) * k3MergeCoils;
+    const int nc = (int)(C - c0 < k3MergeCoils ? C - c0 : k3MergeCoils);
+    const int64_t traj = a.n_traj == 1 ? 0 : b, bz = a.n_traj == 1 ? b : 0;
+    float2 acc[k3MergeCoils];
+#pragma unroll
+    for (int k = 0; k < k3MergeCoils; ++k) acc[k] = make_float2(0.f, 0.f);
+    for (int kz = 0; kz < min(3, ntz); ++kz) {
+      int tz = z / k3Tile - kz;
+      if (tz < 0) tz += ntz;
+      int rz = z - tz * k3Tile;
+      if (rz < 0) rz += Kz;
+      if (rz >= kFoot) continue;
+      for (int ky = 0; ky < min(3, nty); ++ky) {
+        int ty = y / k3Tile - ky;
+        if (ty < 0) ty += nty;
+        int ry = y - ty * k3Tile;
+        if (ry < 0) ry += Ky;
+        if (ry >= kFoot) continue;
+        for (int kx = 0; kx < min(3, ntx); ++kx) {
+          int tx = x / k3Tile - kx;
+          if (tx < 0) tx += ntx;
+          int rx = x - tx * k3Tile;
+          if (rx < 0) rx += Kx;
+          if (rx >= kFoot) continue;
+          const int64_t t = traj * n_tiles + ((int64_t)tz * nty + ty) * ntx + tx;
+          const int s0 = a.tile_sub_start[t], s1 = t + 1 < n_tiles_all ? a.tile_sub_start[t + 1] : n_sub;
+          for (int sl = s0; sl < s1; ++sl) {
+            const float2 *src = scratch + (((int64_t)sl * Bz + bz) * C + c0) * k3PS + rz * k3ZS + ry * k3SX + rx;
+#pragma unroll
+            for (int k = 0; k < k3MergeCoils; ++k)
+              if (k < nc) {
+                const float2 v = src[(int64_t)k * k3PS];
+                acc[k].x += v.x;
+                acc[k].y += v.y;
+              }
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < k3MergeCoils; ++k)
+      if (k < nc) grid[(b * C + c0 + k) * a.Kprod + cell] = acc[k];
+  }
+}
+
+static bool ordered3_eligible(const b2n_geom *g, const b2n_points *p, int layout) {
+  constexpr int kFoot = k3Tile + k3J - 1;
+  return tiled3_eligible(g, p, layout) && g->grid_size[0] >= kFoot && g->grid_size[1] >= kFoot &&
+         g->grid_size[2] >= kFoot && p->sub_slot && p->tile_sub_start;
+}
+
+size_t tiled3_adjoint_ordered_bytes(const b2n_geom *g, const b2n_points *p, int64_t B, int64_t C, int layout) {
+  if (!ordered3_eligible(g, p, layout)) return 0;
+  const int64_t Bz = p->n_traj == 1 ? B : 1;
+  return sizeof(float2) * (size_t)p->n_sub_max * (size_t)Bz * (size_t)C * k3PS;
+}
+
+int tiled3_adjoint_ordered(const b2n_geom *g, const b2n_points *p, const void *kdata, int64_t B, int64_t C, int layout,
+                           void *scratch, size_t scratch_bytes, void *grid, cudaStream_t st) {
+  if (!ordered3_eligible(g, p, layout)) return 1;
+  if (!scratch || scratch_bytes < tiled3_adjoint_ordered_bytes(g, p, B, C, layout))
+    return fail_arg(B2N_E_ARG, "ordered adjoint: scratch too small");
+  if ((reinterpret_cast<uintptr_t>(scratch) & 15) != 0)
+    return fail_arg(B2N_E_ARG, "ordered adjoint: scratch must be 16-byte aligned");
+  InterpArgs<float> a;
+  int rc = make_args<float>(g, p, B, C, &a);
+  if (rc) return rc;
+  const size_t smem = sizeof(float2) * k3TileF2 + 2 * (sizeof(float2) * (k3Round * k3NC + k3Round * k3CC) + sizeof(int) * k3Round * 3) +
+                      sizeof(int) * 3 * k3Round;
+  B2N_CUDA_OK(cudaFuncSetAttribute(k_adj_tiled_3d<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CUtensorMap map;
+  memset(&map, 0, sizeof(map));
+  dim3 gd((unsigned)a.n_sub_max, (unsigned)ceil_div(a.C, k3CC), (unsigned)(a.n_traj == 1 ? a.B : 1));
+  k_adj_tiled_3d<true><<<gd, k3Threads, smem, st>>>(a, (const float2 *)kdata, (float2 *)grid, map, 0, (float2 *)scratch);
+  B2N_LAUNCH_OK("k_adj_tiled_3d<ordered>");
+  const int64_t nblk = a.B * ceil_div(a.C, k3MergeCoils);
+  dim3 gm((unsigned)ceil_div(a.Kprod, 256), (unsigned)(nblk < 65535 ? nblk : 65535));
+  k_adj_merge_3d<<<gm, 256, 0, st>>>(a, (const float2 *)scratch, (float2 *)grid);
+  B2N_LAUNCH_OK("k_adj_merge_3d");
   return 0;
 }
 
