@@ -100,7 +100,7 @@ def oracle_engine():
         eng_fft.apod_pad = _apod_pad
         eng_fft.crop_apod_coilsum = _crop_apod_coilsum
         eng_fft.spectrum_mul_ = _spectrum_mul_
-        eng_fft.fused_fft_available = lambda dtype, grid_size: False  # CPU stand-in uses torch.fft
+        eng_fft.fused_fft_available = lambda dtype, grid_size, n_rows=1: False  # CPU stand-in uses torch.fft
         yield
     finally:
         for mod, name, fn in saved:

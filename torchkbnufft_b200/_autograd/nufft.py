@@ -97,7 +97,8 @@ def toeplitz_apply(image, kernel, smaps, normalized: bool):
     n_grid = 1
     for k in grid_size:
         n_grid *= k
-    if ndim > 1 and _fft.fused_fft_available(image.dtype, grid_size):
+    n_rows = image.shape[0] * (smaps.shape[1] if smaps is not None else image.shape[1])
+    if ndim > 1 and _fft.fused_fft_available(image.dtype, grid_size, n_rows):
         # pruned passes both ways, kernel multiply fused into the first inverse pass
         grid = _fft.fused_fft_forward(image, grid_size, smaps, None, 1.0)
         return _fft.fused_fft_adjoint(grid, image.shape[2:], smaps, None, (1.0 / n_grid) if normalized else 1.0,

@@ -156,10 +156,13 @@ _FFT_SUPPORTED: dict = {}
 use_fused_fft = "auto"
 
 
-def fused_fft_available(dtype: torch.dtype, grid_size: Sequence[int]) -> bool:
-    """True when the engine's own FFT passes are to be used for this transform (complex64 only);
-    otherwise callers use cuFFT around the fused element-wise kernels."""
+def fused_fft_available(dtype: torch.dtype, grid_size: Sequence[int], n_rows: int = 1) -> bool:
+    """True when the engine's own FFT passes are to be used for this transform (complex64 only;
+    ``n_rows`` = batch x coils, the passes index the whole grid stack with 32 bits); otherwise callers
+    use cuFFT around the fused element-wise kernels."""
     if not use_fused_fft or dtype != torch.complex64:
+        return False
+    if n_rows * math.prod(int(k) for k in grid_size) >= 2 ** 31:
         return False
     lib = _lib.load()
     need = 2 if use_fused_fft == "auto" else 1

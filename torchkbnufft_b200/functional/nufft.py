@@ -36,7 +36,8 @@ def sense_nufft_forward(image: Tensor, smaps: Optional[Tensor], scaling_coef: Te
     grid_size = _ints(grid_size)
     scale = _fft.ortho_scale(grid_size, normalized)
     record = _needs_grad(image)
-    if _fft.fused_fft_available(image.dtype, grid_size):
+    n_rows = image.shape[0] * (smaps.shape[1] if smaps is not None else image.shape[1])
+    if _fft.fused_fft_available(image.dtype, grid_size, n_rows):
         grid = (FusedFftForward.apply(image, smaps, scaling_coef, grid_size, scale) if record else
                 _fft.fused_fft_forward(image, grid_size, smaps, scaling_coef, scale))
     else:
@@ -56,7 +57,7 @@ def sense_nufft_adjoint(data: Tensor, smaps: Optional[Tensor], scaling_coef: Ten
     normalized = _fft.check_norm(norm)
     grid_sizes = _ints(grid_size)
     scale = _fft.ortho_scale(grid_sizes, normalized)
-    fused = _fft.fused_fft_available(data.dtype, grid_sizes)
+    fused = _fft.fused_fft_available(data.dtype, grid_sizes, data.shape[0] * data.shape[1])
     if not _needs_grad(data) and not (smaps is not None and smaps.requires_grad):
         grid = _interp.table_interp_adjoint(data, omega, tables, n_shift, numpoints, table_oversamp, offsets, grid_size)
         if fused:
@@ -130,7 +131,7 @@ def kb_spmat_nufft(image: Tensor, scaling_coef: Tensor, im_size: Tensor, grid_si
         normalized = _fft.check_norm(norm)
         sizes = _ints(grid_size)
         scale = _fft.ortho_scale(sizes, normalized)
-        if _fft.fused_fft_available(x.dtype, sizes):
+        if _fft.fused_fft_available(x.dtype, sizes, x.shape[0] * x.shape[1]):
             grid = FusedFftForward.apply(x, None, scaling_coef, sizes, scale)
         else:
             grid = _fft.fft_grid(ApodPad.apply(x, None, scaling_coef, sizes, scale), len(sizes), inverse=False)
@@ -147,7 +148,7 @@ def kb_spmat_nufft_adjoint(data: Tensor, scaling_coef: Tensor, im_size: Tensor, 
         sizes = _ints(grid_size)
         scale = _fft.ortho_scale(sizes, normalized)
         grid = _spmat.spmat_interp_adjoint(y, interp_mats, sizes)
-        if _fft.fused_fft_available(y.dtype, sizes):
+        if _fft.fused_fft_available(y.dtype, sizes, y.shape[0] * y.shape[1]):
             return FusedFftAdjoint.apply(grid, None, scaling_coef, _ints(im_size), scale)
         grid = _fft.fft_grid(grid, len(sizes), inverse=True)
         return CropApodCoilsum.apply(grid, None, scaling_coef, _ints(im_size), scale)
