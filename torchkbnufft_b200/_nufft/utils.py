@@ -13,6 +13,7 @@ numbers are pinned against the reference's own buffers
 """
 from __future__ import annotations
 
+import functools
 import itertools
 from typing import List, NamedTuple, Optional, Sequence, Tuple, Union
 
@@ -85,8 +86,25 @@ def validate_args(
     return Geometry(im_size, grid_size, numpoints, n_shift, table_oversamp, order, alpha, dtype, torch.device(device))
 
 
+@functools.lru_cache(maxsize=64)
+def _kaiser_bessel_table_1d_cached(im_size: int, grid_size: int, numpoints: int, table_oversamp: int, order: float,
+                                   alpha: float) -> np.ndarray:
+    table = _kaiser_bessel_table_1d(im_size, grid_size, numpoints, table_oversamp, order, alpha)
+    table.setflags(write=False)  # shared by every caller with these parameters
+    return table
+
+
 def kaiser_bessel_table_1d(im_size: int, grid_size: int, numpoints: int, table_oversamp: int, order: float,
                            alpha: float) -> np.ndarray:
+    """One dimension's interpolation table (see ``_kaiser_bessel_table_1d``), memoised: the Bessel
+    evaluations take milliseconds, and setup-side callers (density compensation, Toeplitz kernels,
+    every module constructor) ask for the same few tables again and again.  Read-only array."""
+    return _kaiser_bessel_table_1d_cached(int(im_size), int(grid_size), int(numpoints), int(table_oversamp),
+                                          float(order), float(alpha))
+
+
+def _kaiser_bessel_table_1d(im_size: int, grid_size: int, numpoints: int, table_oversamp: int, order: float,
+                            alpha: float) -> np.ndarray:
     """One dimension's interpolation table, complex128, length ``J*L + 1``.
 
     Entry ``i`` (``i < J*L``) samples the kernel at ``x = i/L - J/2``:
@@ -122,7 +140,7 @@ def kaiser_bessel_table_1d(im_size: int, grid_size: int, numpoints: int, table_o
 def build_table(im_size, grid_size, numpoints, table_oversamp, order, alpha) -> List[Tensor]:
     """Tables for every dimension as complex128 tensors (reference name kept)."""
     return [
-        torch.from_numpy(kaiser_bessel_table_1d(n, k, j, l, o, a))
+        torch.tensor(kaiser_bessel_table_1d(n, k, j, l, o, a))  # a copy: the memoised array is read-only
         for n, k, j, l, o, a in zip(im_size, grid_size, numpoints, table_oversamp, order, alpha)
     ]
 
@@ -142,10 +160,17 @@ def compute_scaling_coefs(im_size, grid_size, numpoints, alpha, order) -> Tensor
     float64 tensor of shape ``im_size`` (all ones along a dim with J=1)."""
     coef = None
     for n, k, j, a, o in zip(im_size, grid_size, numpoints, alpha, order):
-        pos = np.arange(n) - (n - 1) / 2
-        line = np.ones(n) if j == 1 else 1 / kaiser_bessel_ft(pos / k, j, a, o, 1)
+        line = _scaling_line(int(n), int(k), int(j), float(a), float(o))
         coef = line if coef is None else coef[..., np.newaxis] * line
-    return torch.from_numpy(np.asarray(coef))
+    return torch.from_numpy(np.array(coef))
+
+
+@functools.lru_cache(maxsize=64)
+def _scaling_line(n: int, k: int, j: int, alpha: float, order: float) -> np.ndarray:
+    pos = np.arange(n) - (n - 1) / 2
+    line = np.ones(n) if j == 1 else 1 / kaiser_bessel_ft(pos / k, j, alpha, order, 1)
+    line.setflags(write=False)
+    return line
 
 
 class Precomputed(NamedTuple):
