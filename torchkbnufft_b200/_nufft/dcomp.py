@@ -9,7 +9,7 @@ from typing import Optional, Sequence, Union
 import torch
 from torch import Tensor
 
-from .._autograd.interp import KbTableInterpAdjoint, KbTableInterpForward
+from . import interp as _interp
 from .utils import init_fn
 
 
@@ -39,9 +39,11 @@ def calc_density_compensation_function(
                   device=ktraj.device)
     weights = torch.ones([batch_size, 1, ktraj.shape[-1]], dtype=pre.tables[0].dtype, device=ktraj.device)
     for _ in range(num_iterations):
-        gridded = KbTableInterpAdjoint.apply(weights, ktraj, pre.tables, pre.n_shift, pre.numpoints,
-                                             pre.table_oversamp, pre.offsets, pre.grid_size)
-        resampled = KbTableInterpForward.apply(gridded, ktraj, pre.tables, pre.n_shift, pre.numpoints,
-                                               pre.table_oversamp, pre.offsets)
+        # nothing here is differentiated (the reference's weights do not require grad either): call the
+        # engine directly rather than through the autograd Functions
+        gridded = _interp.table_interp_adjoint(weights, ktraj, pre.tables, pre.n_shift, pre.numpoints, pre.table_oversamp,
+                                               pre.offsets, pre.grid_size)
+        resampled = _interp.table_interp(gridded, ktraj, pre.tables, pre.n_shift, pre.numpoints, pre.table_oversamp,
+                                         pre.offsets)
         weights = weights / torch.abs(resampled)
     return weights
