@@ -1,3 +1,3 @@
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "ordered or cfg4 or tiled_3d" > gpurun_out/q_pytest.log 2>&1; tail -5 gpurun_out/q_pytest.log
-timeout 900 python profiles/bench_configs.py cfg4 2>&1 | tail -2
+timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/q_pytest_all.log 2>&1; tail -3 gpurun_out/q_pytest_all.log
+python profiles/coil_sweep.py cfg1 cfg2 2>&1 | grep -E "C= [1-8] " 

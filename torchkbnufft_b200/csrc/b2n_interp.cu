@@ -7,6 +7,8 @@
 // One launch covers all W = prod(J_d) neighbour offsets, every batch/coil row and
 // the fftshift phase.  The accumulation order over offsets is the reference's
 // (row-major offsets; coefficient = running product over dimensions).
+#include <type_traits>
+
 #include "b2n_common.cuh"
 #include "b2n_interp.cuh"
 
@@ -108,6 +110,102 @@ __global__ void __launch_bounds__(128) k_adj_atomic_generic(InterpArgs<T> a, con
       }
     }
   }
+}
+
+// -----------------------------------------------------------------------------
+// 2-D, J = 6, complex64, coil-major point kernels: the generic kernels above with everything the
+// common case fixes resolved at compile time (36 unrolled taps, 32-bit indexing, 16-byte weight
+// loads, wrap by compare-and-subtract).  Used for a single (batch, coil) row, where one thread per
+// point beats the tiled kernels' one warp per point (profiles/r01_g_coil_sweep.log).
+// -----------------------------------------------------------------------------
+struct Point6 {
+  float2 cy[6], cx[6];
+  int row[6], col[6];
+};
+B2N_D Point6 load_point6(const InterpArgs<float> &a, int64_t s) {
+  Point6 p;
+  const int2 bs = reinterpret_cast<const int2 *>(a.base)[s];
+  const float4 *rec = reinterpret_cast<const float4 *>(a.coef + s * 12);
+  const int Ky = (int)a.K[0], Kx = (int)a.K[1];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const float4 wy = rec[k], wx = rec[3 + k];
+    p.cy[2 * k] = make_float2(wy.x, wy.y);
+    p.cy[2 * k + 1] = make_float2(wy.z, wy.w);
+    p.cx[2 * k] = make_float2(wx.x, wx.y);
+    p.cx[2 * k + 1] = make_float2(wx.z, wx.w);
+  }
+#pragma unroll
+  for (int j = 0; j < 6; ++j) {
+    const int gy = bs.x + j, gx = bs.y + j;
+    p.row[j] = (gy >= Ky ? gy - Ky : gy) * Kx;
+    p.col[j] = gx >= Kx ? gx - Kx : gx;
+  }
+  return p;
+}
+
+__global__ void __launch_bounds__(128) k_fwd_point6_2d(InterpArgs<float> a, const float2 *__restrict__ grid,
+                                                       float2 *__restrict__ kdata) {
+  const int64_t total = a.n_traj * a.M;
+  const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= total) return;
+  const Point6 p = load_point6(a, s);
+  const int64_t m = a.perm[s];
+  const int64_t rows = a.n_traj == 1 ? a.B * a.C : a.C;
+  for (int64_t r = blockIdx.y; r < rows; r += gridDim.y) {
+    const int64_t bc = a.n_traj == 1 ? r : (s / a.M) * a.C + r;
+    const float2 *g = grid + bc * a.Kprod;
+    float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int jy = 0; jy < 6; ++jy) {
+      float2 v[6];
+#pragma unroll
+      for (int jx = 0; jx < 6; ++jx) v[jx] = __ldg(&g[p.row[jy] + p.col[jx]]);
+      float2 line = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int jx = 0; jx < 6; ++jx) {
+        line.x = fmaf(p.cx[jx].x, v[jx].x, fmaf(-p.cx[jx].y, v[jx].y, line.x));
+        line.y = fmaf(p.cx[jx].x, v[jx].y, fmaf(p.cx[jx].y, v[jx].x, line.y));
+      }
+      acc.x = fmaf(p.cy[jy].x, line.x, fmaf(-p.cy[jy].y, line.y, acc.x));
+      acc.y = fmaf(p.cy[jy].x, line.y, fmaf(p.cy[jy].y, line.x, acc.y));
+    }
+    kdata[bc * a.M + m] = acc;  // the fftshift phase is folded into the dim-0 weights
+  }
+}
+
+__global__ void __launch_bounds__(128) k_adj_point6_2d(InterpArgs<float> a, const float2 *__restrict__ kdata,
+                                                       float2 *__restrict__ grid) {
+  const int64_t total = a.n_traj * a.M;
+  const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= total) return;
+  const Point6 p = load_point6(a, s);
+  const int64_t m = a.perm[s];
+  const int64_t rows = a.n_traj == 1 ? a.B * a.C : a.C;
+  for (int64_t r = blockIdx.y; r < rows; r += gridDim.y) {
+    const int64_t bc = a.n_traj == 1 ? r : (s / a.M) * a.C + r;
+    const float2 val = kdata[bc * a.M + m];
+    float2 *g = grid + bc * a.Kprod;
+#pragma unroll
+    for (int jy = 0; jy < 6; ++jy) {
+      float2 u;  // conj(cy) * val
+      u.x = fmaf(p.cy[jy].x, val.x, p.cy[jy].y * val.y);
+      u.y = fmaf(p.cy[jy].x, val.y, -p.cy[jy].y * val.x);
+#pragma unroll
+      for (int jx = 0; jx < 6; ++jx) {
+        float2 w;  // conj(cx) * u
+        w.x = fmaf(p.cx[jx].x, u.x, p.cx[jx].y * u.y);
+        w.y = fmaf(p.cx[jx].x, u.y, -p.cx[jx].y * u.x);
+        atomicAdd(&g[p.row[jy] + p.col[jx]], w);  // one 8-byte L2 reduction
+      }
+    }
+  }
+}
+
+static bool point6_eligible(const b2n_geom *g, const b2n_points *p, int layout) {
+  return p && g->dtype == B2N_C64 && g->ndim == 2 && layout == B2N_COIL_MAJOR && g->numpoints[0] == 6 &&
+         g->numpoints[1] == 6 && g->grid_size[0] >= 6 && g->grid_size[1] >= 6 &&
+         g->grid_size[0] * g->grid_size[1] < ((int64_t)1 << 31) && p->n_points > 0;
 }
 
 // -----------------------------------------------------------------------------
@@ -218,6 +316,15 @@ static int forward_t(const b2n_geom *g, const b2n_points *p, const void *grid, i
   InterpArgs<T> a;
   int rc = make_args<T>(g, p, B, C, &a);
   if (rc) return rc;
+  if constexpr (std::is_same<T, float>::value) {
+    if (point6_eligible(g, p, layout)) {
+      const int64_t total = a.n_traj * a.M, rows = a.n_traj == 1 ? a.B * a.C : a.C;
+      dim3 gd((unsigned)ceil_div(total, 128), (unsigned)(rows < 65535 ? rows : 65535));
+      k_fwd_point6_2d<<<gd, 128, 0, st>>>(a, (const float2 *)grid, (float2 *)kdata);
+      B2N_LAUNCH_OK("k_fwd_point6_2d");
+      return 0;
+    }
+  }
   const bool cl = layout == B2N_CHANNEL_LAST;
   switch (g->ndim) {
     case 1: return cl ? launch_forward<T, 1, true>(a, grid, kdata, st) : launch_forward<T, 1, false>(a, grid, kdata, st);
@@ -232,6 +339,16 @@ static int adjoint_t(const b2n_geom *g, const b2n_points *p, const void *kdata, 
   InterpArgs<T> a;
   int rc = make_args<T>(g, p, B, C, &a);
   if (rc) return rc;
+  if constexpr (std::is_same<T, float>::value) {
+    if (mode == B2N_ADJ_ATOMIC && point6_eligible(g, p, layout)) {
+      B2N_CUDA_OK(cudaMemsetAsync(grid, 0, sizeof(float2) * (size_t)(a.B * a.C * a.Kprod), st));
+      const int64_t total = a.n_traj * a.M, rows = a.n_traj == 1 ? a.B * a.C : a.C;
+      dim3 gd((unsigned)ceil_div(total, 128), (unsigned)(rows < 65535 ? rows : 65535));
+      k_adj_point6_2d<<<gd, 128, 0, st>>>(a, (const float2 *)kdata, (float2 *)grid);
+      B2N_LAUNCH_OK("k_adj_point6_2d");
+      return 0;
+    }
+  }
   const bool cl = layout == B2N_CHANNEL_LAST;
   switch (g->ndim) {
     case 1: return cl ? launch_adjoint<T, 1, true>(a, kdata, mode, grid, st) : launch_adjoint<T, 1, false>(a, kdata, mode, grid, st);
@@ -264,13 +381,15 @@ extern int g_adj_chunk;
 extern int g_fast_fft;
 static int g_options[B2N_OPT_COUNT] = {1, 0, 0, 0, 1};
 
-// A single 2-D (batch, coil) row leaves 15/16 of a tiled CTA's coil lanes idle while the per-point cost stays the same:
-// the per-point kernels win there (22 vs 25 us gather, 38 vs 48 us spread at the geometry of BASELINE config 2,
-// profiles/r01_g_coil_sweep.log).  B2N_OPT_TILED_KERNELS = 2 forces the tiled kernels anyway.
-static bool use_tiled(const b2n_geom *geom, const b2n_points *pts, int64_t n_batch, int64_t n_coils) {
+// With very few 2-D (batch, coil) rows most coil lanes of a tiled CTA idle while its per-point cost stays the same:
+// the one-thread-per-point kernels (k_fwd_point6_2d / k_adj_point6_2d) win there -- gather up to 3 rows (16 vs 29 us
+// for one row, 30 vs 41 us for three at BASELINE config 1), spread for a single row (48 vs 64 us; it is bound by L2
+// reductions beyond that): profiles/r01_g_coil_sweep.log.  B2N_OPT_TILED_KERNELS = 2 forces the tiled kernels.
+static bool use_tiled(const b2n_geom *geom, const b2n_points *pts, int64_t n_batch, int64_t n_coils, bool forward) {
   const int opt = g_options[B2N_OPT_TILED_KERNELS];
   if (!opt || !pts) return false;
-  return opt == 2 || !(geom->ndim == 2 && n_batch * n_coils == 1);
+  if (opt == 2 || geom->ndim != 2) return true;
+  return n_batch * n_coils > (forward ? 3 : 1);
 }
 
 }  // namespace b2n
@@ -303,7 +422,7 @@ extern "C" int b2n_interp_forward(const b2n_geom *geom, const b2n_points *pts, c
   if (!geom || !grid_dev || !kdata_dev) return fail_arg(B2N_E_ARG, "NULL geom/grid/kdata");
   if (grid_layout != B2N_COIL_MAJOR && grid_layout != B2N_CHANNEL_LAST) return fail_arg(B2N_E_ARG, "bad layout");
   cudaStream_t st = (cudaStream_t)stream;
-  if (use_tiled(geom, pts, n_batch, n_coils)) {
+  if (use_tiled(geom, pts, n_batch, n_coils, true)) {
     int rc = tiled_forward(geom, pts, grid_dev, n_batch, n_coils, grid_layout, kdata_dev, st);
     if (rc != 1) return rc;  // 1 = not eligible, use the generic kernel
     rc = tiled3_forward(geom, pts, grid_dev, n_batch, n_coils, grid_layout, kdata_dev, st);
@@ -320,7 +439,7 @@ extern "C" int b2n_interp_adjoint(const b2n_geom *geom, const b2n_points *pts, c
   if (grid_layout != B2N_COIL_MAJOR && grid_layout != B2N_CHANNEL_LAST) return fail_arg(B2N_E_ARG, "bad layout");
   if (mode != B2N_ADJ_ATOMIC && mode != B2N_ADJ_SORTED) return fail_arg(B2N_E_ARG, "bad adjoint mode %d", mode);
   cudaStream_t st = (cudaStream_t)stream;
-  if (use_tiled(geom, pts, n_batch, n_coils) && mode == B2N_ADJ_ATOMIC) {
+  if (use_tiled(geom, pts, n_batch, n_coils, false) && mode == B2N_ADJ_ATOMIC) {
     int rc = tiled_adjoint(geom, pts, kdata_dev, n_batch, n_coils, grid_layout, grid_dev, st);
     if (rc != 1) return rc;
     rc = tiled3_adjoint(geom, pts, kdata_dev, n_batch, n_coils, grid_layout, grid_dev, st);
