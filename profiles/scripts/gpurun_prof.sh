@@ -1,4 +1,7 @@
 mkdir -p gpurun_out
-timeout 1200 ncu --set full --clock-control none --import-source on -k regex:'k_adj_tiled_3d|k_fwd_tiled_3d' -s 2 -c 2 -o gpurun_out/r1_prof_3d -f python profiles/run_cfg.py cfg4 2 > gpurun_out/r1_prof_3d.log 2>&1
-tail -2 gpurun_out/r1_prof_3d.log | cut -c1-200
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 30 -c 40 --csv python profiles/run_cfg.py cfg4 2 2>/dev/null | grep -E '"k_|"void' | cut -d'"' -f10,30 | cut -c1-120 | tail -24
+# launch list of the default bench command (cold-cache, serialised: shares of the step, not absolute times)
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r1_launches.csv python bench.py --steps 4 --warmup 3 --no-cpu-baseline > gpurun_out/r1_ncu_bench.log 2>&1
+# full capture of one launch of each own kernel in the step
+timeout 1200 ncu --set full --clock-control none --import-source on -k regex:'k_adj_tiled_2d|k_fwd_tiled_2d|k_fft_' -s 18 -c 6 -o gpurun_out/r1_prof_step -f python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/r1_prof_step.log 2>&1
+tail -2 gpurun_out/r1_prof_step.log | cut -c1-200
+grep -c "k_" gpurun_out/r1_launches.csv
