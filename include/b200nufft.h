@@ -110,8 +110,8 @@ enum b2n_option {
                                 2-D (batch, coil) row); 2: wherever they apply; 0: per-point kernels only */
   B2N_OPT_ADJ_ROW_OWNERSHIP = 1, /* tiled 2-D adjoint variant: 0 (default) auto = warp-owned tile rows for 16-coil CTAs,
                                     warp-private 8-coil tiles otherwise; 1 warp-owned rows, 2 warp-owned coils,
-                                    3 warp-private tiles, 4 / 5 warp-owned rows with 4 / 2 warps per CTA
-                                    (kept for A/B measurements) */
+                                    3 warp-private tiles, 4 / 5 warp-owned rows with 4 / 2 warps per CTA, 6 taps-per-lane
+                                    kernel up to 4 coils (auto uses it for 1-2 coils); kept for A/B measurements */
   B2N_OPT_FWD_COIL_CHUNK = 2, /* tiled forward for C > 8: 0 (default) one 16-coil CTA per sub-problem, 1 persistent
                                  triple-buffered kernel (measured slower, kept for A/B), 8 two 8-coil CTAs */
   B2N_OPT_ADJ_COIL_CHUNK = 3, /* 0 (default): 16 coils per CTA in the tiled adjoint; 8: two 8-coil CTAs */

@@ -22,7 +22,12 @@ def timeit(fn, reps=20, warm=3):
         ts.append(a.elapsed_time(b) * 1e3)
     return statistics.median(ts)
 
-for name in sys.argv[1:] or ["cfg2", "cfg1"]:
+args_in = [a for a in sys.argv[1:] if not a.startswith("--opt1=")]
+for a in sys.argv[1:]:
+    if a.startswith("--opt1="):  # adjoint variant (B2N_OPT_ADJ_ROW_OWNERSHIP) for A/B runs
+        from torchkbnufft_b200 import _lib
+        _lib.load().b2n_set_option(_lib.OPT_ADJ_ROW_OWNERSHIP, int(a.split("=")[1]))
+for name in args_in or ["cfg2", "cfg1"]:
     wl = workloads.WORKLOADS[name]
     om = torch.from_numpy(wl.trajectory(np.float32)).to(dev)
     ob = tkbn.KbInterp(im_size=wl.im_size, dtype=torch.complex64).to(dev)

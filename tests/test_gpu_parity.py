@@ -431,7 +431,7 @@ def test_tiled_kernels_match_generic_and_oracle(grid_size, B, C, batched):
     # the forced tiled adjoint variants (warp-owned rows / warp-owned coils / warp-private tiles) and the
     # 8-coil forward chunks
     lib = _lib.load()
-    for variant in (1, 2, 3, 4, 5):
+    for variant in (1, 2, 3, 4, 5, 6):
         try:
             lib.b2n_set_option(_lib.OPT_ADJ_ROW_OWNERSHIP, variant)
             alt = host(eng_interp.table_interp_adjoint(dev(kdata), dev(omega), *args, None, ob.grid_size, mode="atomic"))

@@ -381,15 +381,15 @@ extern int g_adj_chunk;
 extern int g_fast_fft;
 static int g_options[B2N_OPT_COUNT] = {1, 0, 0, 0, 1};
 
-// With very few 2-D (batch, coil) rows most coil lanes of a tiled CTA idle while its per-point cost stays the same:
-// the one-thread-per-point kernels (k_fwd_point6_2d / k_adj_point6_2d) win there -- gather up to 3 rows (16 vs 29 us
-// for one row, 30 vs 41 us for three at BASELINE config 1), spread for a single row (48 vs 64 us; it is bound by L2
-// reductions beyond that): profiles/r01_g_coil_sweep.log.  B2N_OPT_TILED_KERNELS = 2 forces the tiled kernels.
+// With very few 2-D (batch, coil) rows most coil lanes of a tiled gather CTA idle while its per-point cost stays the
+// same: the one-thread-per-point kernel (k_fwd_point6_2d) wins up to 3 rows (16 vs 29 us for one row, 30 vs 41 us for
+// three at BASELINE config 1, profiles/r01_g_coil_sweep.log).  The spread always stays on the tiled path, which has its
+// own few-coil kernel (k_adj_taps_2d).  B2N_OPT_TILED_KERNELS = 2 forces the tiled kernels everywhere.
 static bool use_tiled(const b2n_geom *geom, const b2n_points *pts, int64_t n_batch, int64_t n_coils, bool forward) {
   const int opt = g_options[B2N_OPT_TILED_KERNELS];
   if (!opt || !pts) return false;
-  if (opt == 2 || geom->ndim != 2) return true;
-  return n_batch * n_coils > (forward ? 3 : 1);
+  if (opt == 2 || geom->ndim != 2 || !forward) return true;
+  return n_batch * n_coils > 3;
 }
 
 }  // namespace b2n

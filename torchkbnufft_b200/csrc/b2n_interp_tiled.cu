@@ -1080,6 +1080,116 @@ static int launch_adj_coilwarp(const InterpArgs<float> &a, const void *kdata, vo
   return 0;
 }
 
+// -----------------------------------------------------------------------------------------
+// adjoint spread for very few coils (CC <= 4): lanes = the 36 taps of one point (32 + 4), every warp
+// accumulates ITS points into a warp-private tile (CC planes of 21 x 22 cells, 3.7 KB each), so the
+// read-modify-write needs neither atomics nor ownership tests; the private tiles are summed at the end and
+// added to the grid with RED.ADD.F32x2 (441 cells per coil per sub-problem instead of 36 per point).
+// Banks: tap (jy, jx) sits at jy*22 + jx; within a half-warp those 16 offsets are distinct mod 16.
+// -----------------------------------------------------------------------------------------
+constexpr int kTapWarps = 4;
+template <int CC>
+__global__ void __launch_bounds__(kTapWarps * 32) k_adj_taps_2d(InterpArgs<float> a, const float2 *__restrict__ kdata,
+                                                                float2 *__restrict__ grid) {
+  constexpr int NT = kTapWarps * 32;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float2 *tiles = reinterpret_cast<float2 *>(smem_raw);      // [kTapWarps][CC][kPS] private accumulators
+  float2 *s_coef = tiles + kTapWarps * CC * kPS;             // [kCap][kNC]
+  float2 *s_val = s_coef + kCap * kNC;                       // [CC][kCap]
+  int2 *s_base = reinterpret_cast<int2 *>(s_val + CC * kCap);  // [kCap]
+  int *s_perm = reinterpret_cast<int *>(s_base + kCap);      // [kCap]
+  const SubProblem sp = decode<CC>(a);
+  if (!sp.valid) return;
+  const int Ky = (int)a.K[0], Kx = (int)a.K[1];
+  const int C = (int)a.C;
+  const int64_t M = a.M;
+  {  // plan records of this sub-problem (contiguous in plan order), then the samples they point at
+    const float4 *src =
+        reinterpret_cast<const float4 *>(reinterpret_cast<const float2 *>(a.coef) + (int64_t)sp.start * kNC);
+    float4 *dst = reinterpret_cast<float4 *>(s_coef);
+    for (int e = threadIdx.x; e < sp.count * (kNC / 2); e += NT) cp_async16(&dst[e], &src[e]);
+    const int2 *bsrc = reinterpret_cast<const int2 *>(a.base) + sp.start;
+    for (int e = threadIdx.x; e < sp.count; e += NT) {
+      cp_async8(&s_base[e], &bsrc[e], true);
+      cp_async4(&s_perm[e], &a.perm[sp.start + e]);
+    }
+    cp_async_commit();
+  }
+  for (int e = threadIdx.x; e < kTapWarps * CC * kPS; e += NT) tiles[e] = make_float2(0.f, 0.f);
+  cp_async_wait_all();
+  __syncthreads();
+  for (int e = threadIdx.x; e < CC * sp.count; e += NT) {
+    const int cc = e / sp.count, i = e - cc * sp.count;
+    s_val[cc * kCap + i] = sp.c0 + cc < C ? kdata[(int64_t)(sp.b * C + sp.c0 + cc) * M + s_perm[i]] : make_float2(0.f, 0.f);
+  }
+  __syncthreads();
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int jy0 = lane / kJ, jx0 = lane - jy0 * kJ;  // taps 0..31
+  const int t1 = 32 + lane, jy1 = t1 / kJ, jx1 = t1 - jy1 * kJ;  // taps 32..35 (lanes 0..3)
+  const bool second = lane < kJ * kJ - 32;
+  float2 *mine = tiles + warp * CC * kPS;
+  for (int i = warp; i < sp.count; i += kTapWarps) {
+    const int2 bs = s_base[i];
+    float2 *cell = mine + (bs.x - sp.y0) * kSX + (bs.y - sp.x0);
+    const float2 *rec = s_coef + i * kNC;
+    // conj(cy * cx) for this lane's taps (cy carries the fftshift phase)
+    const float2 cy0 = rec[jy0], cx0 = rec[kJ + jx0];
+    const float2 w0 = make_float2(fmaf(cy0.x, cx0.x, -cy0.y * cx0.y), -fmaf(cy0.x, cx0.y, cy0.y * cx0.x));
+    float2 w1 = make_float2(0.f, 0.f);
+    if (second) {
+      const float2 cy1 = rec[jy1], cx1 = rec[kJ + jx1];
+      w1 = make_float2(fmaf(cy1.x, cx1.x, -cy1.y * cx1.y), -fmaf(cy1.x, cx1.y, cy1.y * cx1.x));
+    }
+#pragma unroll
+    for (int cc = 0; cc < CC; ++cc) {
+      const float2 v = s_val[cc * kCap + i];
+      float2 *p0 = cell + cc * kPS + jy0 * kSX + jx0;
+      float2 t = *p0;
+      cmacf(t, w0, v);
+      *p0 = t;
+      if (second) {
+        float2 *p1 = cell + cc * kPS + jy1 * kSX + jx1;
+        float2 u = *p1;
+        cmacf(u, w1, v);
+        *p1 = u;
+      }
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+  // sum the private tiles (fixed order) and add the result to the grid, with the periodic wrap
+  for (int e = threadIdx.x; e < CC * kPS; e += NT) {
+    const int cc = e / kPS, rem = e - cc * kPS;
+    if (sp.c0 + cc >= C) break;
+    const int r = rem / kSX, x = rem - r * kSX;
+    if (x >= kSX - 1) continue;  // padding column
+    float2 v = tiles[e];
+#pragma unroll
+    for (int w = 1; w < kTapWarps; ++w) {
+      const float2 q = tiles[w * CC * kPS + e];
+      v.x += q.x;
+      v.y += q.y;
+    }
+    if (v.x == 0.f && v.y == 0.f) continue;
+    int gy = sp.y0 + r, gx = sp.x0 + x;
+    gy = gy < Ky ? gy : gy % Ky;
+    gx = gx < Kx ? gx : gx % Kx;
+    atomicAdd(&grid[((int64_t)(sp.b * C + sp.c0 + cc) * Ky + gy) * Kx + gx], v);
+  }
+}
+
+template <int CC> static int launch_adj_taps(const InterpArgs<float> &a, const void *kdata, void *grid, cudaStream_t st) {
+  const size_t smem = sizeof(float2) * (kTapWarps * CC * kPS + kCap * kNC + CC * kCap) + sizeof(int2) * kCap + sizeof(int) * kCap;
+  auto kern = k_adj_taps_2d<CC>;
+  B2N_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  B2N_CUDA_OK(cudaMemsetAsync(grid, 0, sizeof(float2) * (size_t)(a.B * a.C * a.Kprod), st));
+  dim3 gd((unsigned)a.n_sub_max, (unsigned)ceil_div(a.C, CC), (unsigned)(a.n_traj == 1 ? a.B : 1));
+  kern<<<gd, kTapWarps * 32, smem, st>>>(a, (const float2 *)kdata, (float2 *)grid);
+  B2N_LAUNCH_OK("k_adj_taps_2d");
+  return 0;
+}
+
 template <int NW>
 static int launch_adj_warptile(const InterpArgs<float> &a, const void *kdata, void *grid, cudaStream_t st) {
   constexpr int CC = NW * 8;
@@ -1122,6 +1232,12 @@ int tiled_adjoint(const b2n_geom *g, const b2n_points *p, const void *kdata, int
   // variant 0 (auto): warp-owned tile rows for 16-coil CTAs (107 us vs 114 us at BASELINE config 2,
   // profiles/r01_g), warp-private tiles for <= 8 coils; 1 / 2 / 3 force rows / coils / private tiles
   const int v = g_adj_rowwarp;
+  if (v == 0 || v == 6) {  // one or two coils: taps-per-lane kernel with warp-private tiles (32 vs 48-64 us at
+    // BASELINE config 1; with 3-4 coils it is slower than the 8-coil private tiles: 103 vs 67 us, variant 6 for A/B)
+    if (C == 1) return launch_adj_taps<1>(a, kdata, grid, st);
+    if (C == 2) return launch_adj_taps<2>(a, kdata, grid, st);
+    if (C <= 4 && v == 6) return launch_adj_taps<4>(a, kdata, grid, st);
+  }
   if (v == 3 || (v == 0 && !wide))
     return wide ? launch_adj_warptile<2>(a, kdata, grid, st) : launch_adj_warptile<1>(a, kdata, grid, st);
   if (wide && v == 4) return launch_adj<16, 4>(a, kdata, grid, st);
