@@ -21,4 +21,4 @@ for _ in range(300):
     k = nu(x, om, **kw); na(k, om, **kw)
 pr.disable()
 torch.cuda.synchronize()
-st = pstats.Stats(pr); st.sort_stats("cumulative"); st.print_stats(45)
+st = pstats.Stats(pr); st.sort_stats("tottime"); st.print_stats(28)

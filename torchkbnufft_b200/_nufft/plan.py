@@ -125,10 +125,22 @@ def host_ints(sizes) -> Tuple[int, ...]:
     return hit[0]
 
 
+_GEOM_FAST: dict = {}  # (id, _version) of every buffer -> (Geometry, the buffers): a cheap front for _GEOM_CACHE
+
+
 def get_geometry(tables: Sequence[Tensor], n_shift: Tensor, numpoints: Tensor, table_oversamp: Tensor,
                  grid_size) -> Geometry:
     """Cached :class:`Geometry` for a set of operator buffers.  ``grid_size`` may be a
     tensor (read once) or a sequence of ints."""
+    # Hot path: the same tensor OBJECTS come back call after call (module buffers); identity + version is enough and
+    # an order of magnitude cheaper than data_ptr/shape/stride keys.  The entry keeps the tensors alive, so an id
+    # cannot be recycled while it is cached.
+    gfast = (id(grid_size), grid_size._version) if isinstance(grid_size, Tensor) else tuple(grid_size)
+    fkey = (tuple((id(t), t._version) for t in tables), id(n_shift), n_shift._version, id(numpoints),
+            numpoints._version, id(table_oversamp), table_oversamp._version, gfast)
+    hit = _GEOM_FAST.get(fkey)
+    if hit is not None:
+        return hit[0]
     # sizes as ints: the forward (sizes from image.shape) and the adjoint (grid_size buffer)
     # then share one geometry and one trajectory plan
     gkey = host_ints(grid_size)
@@ -136,15 +148,18 @@ def get_geometry(tables: Sequence[Tensor], n_shift: Tensor, numpoints: Tensor, t
     geo = _GEOM_CACHE.get(key)
     if geo is not None:
         _GEOM_CACHE.move_to_end(key)
-        return geo
-    for t in tables:
-        require_cuda(t, "tables")
-    geo = Geometry(tables, n_shift, numpoints, table_oversamp, gkey)
-    geo.key = key
-    geo._refs = (n_shift, numpoints, table_oversamp)  # keep key pointers alive
-    _GEOM_CACHE[key] = geo
-    while len(_GEOM_CACHE) > GEOM_CACHE_SIZE:
-        _GEOM_CACHE.popitem(last=False)
+    else:
+        for t in tables:
+            require_cuda(t, "tables")
+        geo = Geometry(tables, n_shift, numpoints, table_oversamp, gkey)
+        geo.key = key
+        geo._refs = (n_shift, numpoints, table_oversamp)  # keep key pointers alive
+        _GEOM_CACHE[key] = geo
+        while len(_GEOM_CACHE) > GEOM_CACHE_SIZE:
+            _GEOM_CACHE.popitem(last=False)
+    if len(_GEOM_FAST) > 8 * GEOM_CACHE_SIZE:
+        _GEOM_FAST.clear()
+    _GEOM_FAST[fkey] = (geo, (list(tables), n_shift, numpoints, table_oversamp, grid_size))
     return geo
 
 
@@ -180,23 +195,38 @@ class TrajectoryPlan:
         self.workspace.record_stream(torch.cuda.current_stream(omega.device))
 
 
+_PLAN_FAST: dict = {}  # (id(geo), id(omega), omega._version) -> plan (the plan keeps geo and omega alive)
+
+
 def get_plan(geo: Geometry, omega: Tensor) -> TrajectoryPlan:
+    fkey = (id(geo), id(omega), omega._version)
+    plan = _PLAN_FAST.get(fkey)
+    if plan is not None:
+        return plan
     key = (geo.key, _tkey(omega))
     plan = _PLAN_CACHE.get(key)
     if plan is not None:
         _PLAN_CACHE.move_to_end(key)
-        return plan
-    plan = TrajectoryPlan(geo, omega)
-    _PLAN_CACHE[key] = plan
-    while len(_PLAN_CACHE) > PLAN_CACHE_SIZE:
-        _PLAN_CACHE.popitem(last=False)
+    else:
+        plan = TrajectoryPlan(geo, omega)
+        _PLAN_CACHE[key] = plan
+        while len(_PLAN_CACHE) > PLAN_CACHE_SIZE:
+            evicted = _PLAN_CACHE.popitem(last=False)[1]
+            for k in [k for k, v in _PLAN_FAST.items() if v is evicted]:
+                del _PLAN_FAST[k]  # an evicted plan must free its device memory
+    if len(_PLAN_FAST) > 8 * PLAN_CACHE_SIZE:
+        _PLAN_FAST.clear()
+    if plan.omega is omega:  # only identity-key the tensor the plan itself keeps alive
+        _PLAN_FAST[fkey] = plan
     return plan
 
 
 def clear_caches() -> None:
     """Drop every cached geometry and trajectory plan (frees their device memory)."""
     _PLAN_CACHE.clear()
+    _PLAN_FAST.clear()
     _GEOM_CACHE.clear()
+    _GEOM_FAST.clear()
     _GRID_SIZE_CACHE.clear()
 
 

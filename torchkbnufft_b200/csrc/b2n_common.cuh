@@ -37,6 +37,19 @@ void count_launch();
     ::b2n::count_launch();                                 \
   } while (0)
 
+// Opt a kernel in to `bytes` of dynamic shared memory once per (kernel instantiation, device): the attribute call
+// costs about a microsecond of host time, which matters next to 15-100 us kernels.
+#define B2N_SMEM_OPT_IN(kern, bytes)                                                                       \
+  do {                                                                                                     \
+    static int _b2n_done[16] = {0};                                                                        \
+    int _b2n_dev = 0;                                                                                      \
+    if (cudaGetDevice(&_b2n_dev) != cudaSuccess || _b2n_dev < 0 || _b2n_dev >= 16) _b2n_dev = -1;          \
+    if (_b2n_dev < 0 || _b2n_done[_b2n_dev] < (int)(bytes)) {                                              \
+      B2N_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes)));  \
+      if (_b2n_dev >= 0) _b2n_done[_b2n_dev] = (int)(bytes);                                               \
+    }                                                                                                      \
+  } while (0)
+
 template <typename T> struct cplx { T x, y; };
 template <> struct __align__(8) cplx<float> { float x, y; };
 template <> struct __align__(16) cplx<double> { double x, y; };

@@ -332,7 +332,7 @@ template <bool INV, int MODE> static int launch_rows(RowArgs &a, cudaStream_t st
   const int NP = fft_pad(a.st.n) + 1;
   const size_t smem = sizeof(float2) * ((size_t)a.st.n + 2 * (size_t)kRowsPerCta * NP);
   auto kern = k_fft_rows<INV, MODE>;
-  B2N_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  B2N_SMEM_OPT_IN(kern, smem);
   kern<<<(unsigned)ceil_div(a.lines, kRowsPerCta), kFftThreads, smem, st>>>(a);
   B2N_LAUNCH_OK("k_fft_rows");
   return 0;
@@ -347,7 +347,7 @@ template <bool INV> static int launch_cols(ColArgs &a, cudaStream_t st) {
   const int NP = fft_pad(a.st.n) + 1;
   const size_t smem = sizeof(float2) * ((size_t)a.st.n + 2 * (size_t)NP * kColsPerCta);
   auto kern = k_fft_cols<INV>;
-  B2N_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  B2N_SMEM_OPT_IN(kern, smem);
   const int64_t blocks = a.A * ceil_div(a.X, kColsPerCta);
   kern<<<(unsigned)blocks, kColThreads, smem, st>>>(a);
   B2N_LAUNCH_OK("k_fft_cols");

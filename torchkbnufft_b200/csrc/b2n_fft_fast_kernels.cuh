@@ -195,7 +195,7 @@ template <class P, bool INV, int MODE, bool HALF> int launch_rows_fast_h(RowArgs
   using Cfg = FastCfg<P>;
   const size_t smem = sizeof(float4) * (size_t)Cfg::LP * P::NP;
   auto kern = k_fft_rows_fast<P, INV, MODE, HALF>;
-  B2N_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  B2N_SMEM_OPT_IN(kern, smem);
   kern<<<(unsigned)ceil_div(a.lines, 2 * Cfg::LP), Cfg::ROW_THREADS, smem, st>>>(a);
   B2N_LAUNCH_OK("k_fft_rows_fast");
   return 0;
@@ -209,7 +209,7 @@ template <class P, bool INV, bool HALF> int launch_cols_fast_h(ColArgs &a, cudaS
   using Cfg = FastCfg<P>;
   const size_t smem = sizeof(float4) * (size_t)Cfg::PAIRS * P::NP;
   auto kern = k_fft_cols_fast<P, INV, HALF>;
-  B2N_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  B2N_SMEM_OPT_IN(kern, smem);
   const int64_t gy = a.A < 32768 ? a.A : 32768;
   const dim3 grid((unsigned)ceil_div(a.X, 2 * Cfg::PAIRS), (unsigned)gy, (unsigned)ceil_div(a.A, gy));
   kern<<<grid, Cfg::COL_THREADS, smem, st>>>(a);
@@ -227,7 +227,7 @@ template <class P, bool HALF> int launch_rows_sense_h(RowArgs &a, int64_t B, cud
   const int64_t rows = B * a.rows_per_img;
   const size_t smem = sizeof(float4) * (size_t)Cfg::LP * P::NP + sizeof(float2) * (size_t)Cfg::LP * a.n_out;
   auto kern = k_fft_rows_sense<P, HALF>;
-  B2N_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  B2N_SMEM_OPT_IN(kern, smem);
   if (a.coil_groups > 1) B2N_CUDA_OK(cudaMemsetAsync(a.counter, 0, sizeof(unsigned int) * (size_t)rows, st));
   kern<<<(unsigned)(rows * a.coil_groups), Cfg::ROW_THREADS, smem, st>>>(a);
   B2N_LAUNCH_OK("k_fft_rows_sense");

@@ -999,7 +999,7 @@ static int launch_adj_ordered(const InterpArgs<float> &a, const void *kdata, voi
   const size_t smem =
       sizeof(float2) * (planes<CC>() * kPS + 2 * adj_stage_slots<CC>()) + sizeof(int) * 3 * kRound;
   auto kern = k_adj_tiled_2d<CC, kWarps, true>;
-  B2N_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  B2N_SMEM_OPT_IN(kern, smem);
   CUtensorMap map;
   memset(&map, 0, sizeof(map));
   dim3 gd((unsigned)a.n_sub_max, (unsigned)ceil_div(a.C, CC), (unsigned)(a.n_traj == 1 ? a.B : 1));
@@ -1022,7 +1022,7 @@ template <int CC, int QY, int QX>
 static int launch_fwd(const InterpArgs<float> &a, const void *grid, void *kdata, cudaStream_t st) {
   const size_t smem = sizeof(float2) * (planes<CC>() * kPS + kCap * kNC) + sizeof(int2) * kCap + sizeof(int) * kCap + 16;
   auto kern = k_fwd_tiled_2d<CC, QY, QX>;
-  B2N_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  B2N_SMEM_OPT_IN(kern, smem);
   CUtensorMap map;
   memset(&map, 0, sizeof(map));
   const int use_tma = make_grid_tmap(&map, grid, a.B, a.C, a.K[0], a.K[1]) ? 1 : 0;
@@ -1037,7 +1037,7 @@ static int launch_fwd_persist(const InterpArgs<float> &a, const void *grid, void
   const size_t buf_bytes = sizeof(float2) * (planes<CC>() * kPS + kCap * kNC) + sizeof(int2) * kCap + sizeof(int) * kCap;
   const size_t smem = kPersistBufs * buf_bytes + kPersistBufs * sizeof(uint64_t);
   auto kern = k_fwd_persist_2d<CC, QY, QX>;
-  B2N_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  B2N_SMEM_OPT_IN(kern, smem);
   CUtensorMap map;
   memset(&map, 0, sizeof(map));
   const int use_tma = make_grid_tmap(&map, grid, a.B, a.C, a.K[0], a.K[1]) ? 1 : 0;
@@ -1054,7 +1054,7 @@ static int launch_adj(const InterpArgs<float> &a, const void *kdata, void *grid,
   const size_t smem =
       sizeof(float2) * (planes<CC>() * kPS + 2 * adj_stage_slots<CC>()) + sizeof(int) * 3 * kRound;
   auto kern = k_adj_tiled_2d<CC, NW>;
-  B2N_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  B2N_SMEM_OPT_IN(kern, smem);
   B2N_CUDA_OK(cudaMemsetAsync(grid, 0, sizeof(float2) * (size_t)(a.B * a.C * a.Kprod), st));
   CUtensorMap map;
   memset(&map, 0, sizeof(map));
@@ -1069,7 +1069,7 @@ static int launch_adj_coilwarp(const InterpArgs<float> &a, const void *kdata, vo
   constexpr int CC = 16;
   const size_t smem = sizeof(float2) * (CC * kPS + kRoundC * kNC + kRoundC * kJ * kJ + 2 * kRoundC * CC) +
                       sizeof(int2) * 2 * kRoundC + sizeof(int) * 3 * kRoundC;
-  B2N_CUDA_OK(cudaFuncSetAttribute(k_adj_coilwarp_2d, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  B2N_SMEM_OPT_IN(k_adj_coilwarp_2d, smem);
   B2N_CUDA_OK(cudaMemsetAsync(grid, 0, sizeof(float2) * (size_t)(a.B * a.C * a.Kprod), st));
   CUtensorMap map;
   memset(&map, 0, sizeof(map));
@@ -1182,7 +1182,7 @@ __global__ void __launch_bounds__(kTapWarps * 32) k_adj_taps_2d(InterpArgs<float
 template <int CC> static int launch_adj_taps(const InterpArgs<float> &a, const void *kdata, void *grid, cudaStream_t st) {
   const size_t smem = sizeof(float2) * (kTapWarps * CC * kPS + kCap * kNC + CC * kCap) + sizeof(int2) * kCap + sizeof(int) * kCap;
   auto kern = k_adj_taps_2d<CC>;
-  B2N_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  B2N_SMEM_OPT_IN(kern, smem);
   B2N_CUDA_OK(cudaMemsetAsync(grid, 0, sizeof(float2) * (size_t)(a.B * a.C * a.Kprod), st));
   dim3 gd((unsigned)a.n_sub_max, (unsigned)ceil_div(a.C, CC), (unsigned)(a.n_traj == 1 ? a.B : 1));
   kern<<<gd, kTapWarps * 32, smem, st>>>(a, (const float2 *)kdata, (float2 *)grid);
@@ -1195,7 +1195,7 @@ static int launch_adj_warptile(const InterpArgs<float> &a, const void *kdata, vo
   constexpr int CC = NW * 8;
   const size_t smem = sizeof(float2) * (CC * kPS + 2 * (kRound * kNC + kRound * CC + kRound)) + sizeof(int) * 3 * kRound;
   auto kern = k_adj_warptile_2d<NW>;
-  B2N_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  B2N_SMEM_OPT_IN(kern, smem);
   B2N_CUDA_OK(cudaMemsetAsync(grid, 0, sizeof(float2) * (size_t)(a.B * a.C * a.Kprod), st));
   CUtensorMap map;
   memset(&map, 0, sizeof(map));

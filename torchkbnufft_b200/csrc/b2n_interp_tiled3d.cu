@@ -356,7 +356,7 @@ int tiled3_forward(const b2n_geom *g, const b2n_points *p, const void *grid, int
   int rc = make_args<float>(g, p, B, C, &a);
   if (rc) return rc;
   const size_t smem = sizeof(float2) * (k3TileF2 + k3Cap * k3NC) + sizeof(int) * k3Cap * 4 + 16;
-  B2N_CUDA_OK(cudaFuncSetAttribute(k_fwd_tiled_3d, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  B2N_SMEM_OPT_IN(k_fwd_tiled_3d, smem);
   CUtensorMap map;
   memset(&map, 0, sizeof(map));
   const int use_tma = make_grid_tmap3(&map, grid, a.B, a.C, a.K[0], a.K[1], a.K[2]) ? 1 : 0;
@@ -374,7 +374,7 @@ int tiled3_adjoint(const b2n_geom *g, const b2n_points *p, const void *kdata, in
   if (rc) return rc;
   const size_t smem = sizeof(float2) * k3TileF2 + 2 * (sizeof(float2) * (k3Round * k3NC + k3Round * k3CC) + sizeof(int) * k3Round * 3) +
                       sizeof(int) * 3 * k3Round;
-  B2N_CUDA_OK(cudaFuncSetAttribute(k_adj_tiled_3d<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  B2N_SMEM_OPT_IN(k_adj_tiled_3d<false>, smem);
   B2N_CUDA_OK(cudaMemsetAsync(grid, 0, sizeof(float2) * (size_t)(a.B * a.C * a.Kprod), st));
   CUtensorMap map;
   memset(&map, 0, sizeof(map));
@@ -473,7 +473,7 @@ int tiled3_adjoint_ordered(const b2n_geom *g, const b2n_points *p, const void *k
   if (rc) return rc;
   const size_t smem = sizeof(float2) * k3TileF2 + 2 * (sizeof(float2) * (k3Round * k3NC + k3Round * k3CC) + sizeof(int) * k3Round * 3) +
                       sizeof(int) * 3 * k3Round;
-  B2N_CUDA_OK(cudaFuncSetAttribute(k_adj_tiled_3d<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  B2N_SMEM_OPT_IN(k_adj_tiled_3d<true>, smem);
   CUtensorMap map;
   memset(&map, 0, sizeof(map));
   dim3 gd((unsigned)a.n_sub_max, (unsigned)ceil_div(a.C, k3CC), (unsigned)(a.n_traj == 1 ? a.B : 1));
