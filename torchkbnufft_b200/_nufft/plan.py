@@ -193,6 +193,28 @@ class TrajectoryPlan:
         # the build reads `om` asynchronously; keep a possible contiguous copy alive with the plan
         self._om_contig = om
         self.workspace.record_stream(torch.cuda.current_stream(omega.device))
+        # The number of sub-problems is only known on the device; kernels are launched over the upper bound
+        # n_sub_max and the surplus CTAs exit at once (~3 us of tail per launch at BASELINE config 2).  Fetch the
+        # exact count asynchronously -- no synchronisation here -- and tighten the bound once it has arrived.
+        self._n_sub_host = None
+        self._n_sub_event = None
+        if self.struct.n_sub and self.struct.n_sub_max > 0:
+            off = int(self.struct.n_sub) - self.workspace.data_ptr()
+            self._n_sub_host = torch.empty(1, dtype=torch.int32).pin_memory()
+            self._n_sub_host.copy_(self.workspace[off:off + 4].view(torch.int32), non_blocking=True)
+            self._n_sub_event = torch.cuda.Event()
+            self._n_sub_event.record(torch.cuda.current_stream(omega.device))
+
+    def tighten(self) -> None:
+        """Replace the launch bound n_sub_max by the exact sub-problem count once the asynchronous read-back of
+        the device counter has completed (cheap no-op before that and after it has been applied)."""
+        ev = self._n_sub_event
+        if ev is None or torch.cuda.is_current_stream_capturing() or not ev.query():
+            return  # (event queries are not allowed while a CUDA graph is being captured)
+        self._n_sub_event = None
+        n = int(self._n_sub_host[0])
+        if 0 < n < self.struct.n_sub_max:
+            self.struct.n_sub_max = n
 
 
 _PLAN_FAST: dict = {}  # (id(geo), id(omega), omega._version) -> plan (the plan keeps geo and omega alive)
@@ -202,6 +224,8 @@ def get_plan(geo: Geometry, omega: Tensor) -> TrajectoryPlan:
     fkey = (id(geo), id(omega), omega._version)
     plan = _PLAN_FAST.get(fkey)
     if plan is not None:
+        if plan._n_sub_event is not None:
+            plan.tighten()
         return plan
     key = (geo.key, _tkey(omega))
     plan = _PLAN_CACHE.get(key)
