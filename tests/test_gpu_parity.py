@@ -656,3 +656,27 @@ def test_ordered_tiled_adjoint_3d(grid_size, B, C, batched):
     assert rel_l2(host(runs[0]), want) <= 1e-5
     atomic = eng_interp.table_interp_adjoint(y, om, *args, None, ob.grid_size, mode="atomic")
     assert rel_l2(host(atomic), host(runs[0])) <= 2e-6
+
+
+@pytest.mark.parametrize("grid_size, B, C", [((64, 64), 1, 16), ((70, 52), 2, 32)])
+def test_channel_last_tiled_spread_matches_coil_major(grid_size, B, C):
+    """k_adj_tiled_cl_2d (channel-last grid, 16-coil lines, 128-bit read-modify-write) against the coil-major
+    tiled kernel and the oracle."""
+    rng = np.random.default_rng(C + grid_size[0])
+    im_size = tuple(k // 2 for k in grid_size)
+    ob = tkbn.KbInterpAdjoint(im_size=im_size, grid_size=grid_size, dtype=torch.complex64).to(DEV)
+    M = 3000
+    omega = rng.uniform(-np.pi, np.pi, size=(2, M))
+    omega[:, : M // 3] *= 0.05
+    omega = np.ascontiguousarray(omega.astype(np.float32))
+    kdata = workloads.complex_normal(rng, (B, C, M))
+    args = (ob.tables, ob.n_shift, ob.numpoints, ob.table_oversamp)
+    y, om = dev(kdata), dev(omega)
+    cm = eng_interp.table_interp_adjoint(y, om, *args, None, ob.grid_size, mode="atomic")
+    cl = eng_interp.table_interp_adjoint(y, om, *args, None, ob.grid_size, mode="atomic", layout=_lib.CHANNEL_LAST)
+    assert cl.shape == (B,) + tuple(grid_size) + (C,)
+    assert rel_l2(host(cl.movedim(-1, 1)), host(cm)) <= 2e-6
+    tables = [host(t) for t in ob.tables]
+    want = orc.table_interp_adjoint(kdata, omega, tables, host(ob.n_shift), ob.numpoints.tolist(),
+                                    ob.table_oversamp.tolist(), grid_size, nthreads=4)
+    assert rel_l2(host(cl.movedim(-1, 1)), want) <= 1e-5

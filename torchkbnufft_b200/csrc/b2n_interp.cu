@@ -361,6 +361,8 @@ int tiled_forward(const b2n_geom *g, const b2n_points *p, const void *grid, int6
                   void *kdata, cudaStream_t st);
 int tiled_adjoint(const b2n_geom *g, const b2n_points *p, const void *kdata, int64_t B, int64_t C, int layout,
                   void *grid, cudaStream_t st);
+int tiled_adjoint_cl(const b2n_geom *g, const b2n_points *p, const void *kdata, int64_t B, int64_t C, int layout,
+                     void *grid, cudaStream_t st);
 int tiled3_forward(const b2n_geom *g, const b2n_points *p, const void *grid, int64_t B, int64_t C, int layout,
                    void *kdata, cudaStream_t st);
 int tiled3_adjoint(const b2n_geom *g, const b2n_points *p, const void *kdata, int64_t B, int64_t C, int layout,
@@ -441,6 +443,8 @@ extern "C" int b2n_interp_adjoint(const b2n_geom *geom, const b2n_points *pts, c
   cudaStream_t st = (cudaStream_t)stream;
   if (use_tiled(geom, pts, n_batch, n_coils, false) && mode == B2N_ADJ_ATOMIC) {
     int rc = tiled_adjoint(geom, pts, kdata_dev, n_batch, n_coils, grid_layout, grid_dev, st);
+    if (rc != 1) return rc;
+    rc = tiled_adjoint_cl(geom, pts, kdata_dev, n_batch, n_coils, grid_layout, grid_dev, st);
     if (rc != 1) return rc;
     rc = tiled3_adjoint(geom, pts, kdata_dev, n_batch, n_coils, grid_layout, grid_dev, st);
     if (rc != 1) return rc;
