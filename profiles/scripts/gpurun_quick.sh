@@ -1,3 +1,3 @@
 mkdir -p gpurun_out
 timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/q_pytest_all.log 2>&1; tail -3 gpurun_out/q_pytest_all.log
-timeout 600 python bench.py --steps 100 --warmup 5 --breakdown --no-cpu-baseline 2>&1 | grep -E "stage ms|step ms"
+timeout 600 python bench.py --steps 100 --warmup 5 2>&1 | tail -1 | cut -c1-260
