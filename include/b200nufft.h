@@ -207,8 +207,9 @@ B2N_API int b2n_interp_adjoint_ordered(const b2n_geom *geom, const b2n_points *p
  *   forward = b2n_apod_pad + fftn(norm=None) in ndim passes,
  *   adjoint = ifftn(norm="forward") + b2n_crop_apod_coilsum (+ optional Toeplitz kernel
  *             multiply on the way in) in ndim passes.
- * b2n_fft_supported(n): 0 = not handled; 1 = length n factors into {2,3,5,7,11,13} and is <= 8192 (run-time
- * Stockham passes); 2 = n also has a compile-time plan (register-resident passes, the fast path).
+ * b2n_fft_supported(n): 0 = not handled; 1 = length n factors into {2,3,5,7,11,13} and its ping-pong line buffers
+ * fit in shared memory (n <= 1528: run-time Stockham passes); 2 = n has a compile-time plan (register-resident
+ * passes, the fast path).
  * work_dev: device scratch of b2n_fft_work_bytes() bytes (intermediate, partially transformed arrays, per-coil-group
  * partial rows and arrival counters of the fused coil sum); the forward does not need it for ndim == 1.
  * reference: fft_and_scale / ifft_and_scale / fft_filter, _nufft/fft.py:36-173. */

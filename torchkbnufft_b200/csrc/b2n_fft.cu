@@ -285,6 +285,12 @@ static bool make_stages(int64_t n, FftStages *st, int max_pow2_bits = 4) {
   return true;
 }
 
+// the run-time passes keep two ping-pong line buffers in shared memory: the column pass (8 columns) is the larger one
+constexpr size_t kSmemLimit = 227 * 1024;
+static bool runtime_pass_fits(int64_t n) {
+  return sizeof(float2) * ((size_t)n + 2 * (size_t)(fft_pad((int)n) + 1) * kColsPerCta) <= kSmemLimit;
+}
+
 int g_fast_fft = 1;  // B2N_OPT_FAST_FFT: compile-time planned passes where a plan exists
 
 // entry points of the compile-time planned passes, defined in b2n_fft_plans_*.cu
@@ -331,6 +337,7 @@ template <bool INV, int MODE> static int launch_rows(RowArgs &a, cudaStream_t st
   }
   const int NP = fft_pad(a.st.n) + 1;
   const size_t smem = sizeof(float2) * ((size_t)a.st.n + 2 * (size_t)kRowsPerCta * NP);
+  if (smem > kSmemLimit) return fail_arg(B2N_E_UNSUPPORTED, "FFT length %d is too long for the run-time row pass", a.st.n);
   auto kern = k_fft_rows<INV, MODE>;
   B2N_SMEM_OPT_IN(kern, smem);
   kern<<<(unsigned)ceil_div(a.lines, kRowsPerCta), kFftThreads, smem, st>>>(a);
@@ -346,6 +353,7 @@ template <bool INV> static int launch_cols(ColArgs &a, cudaStream_t st) {
   }
   const int NP = fft_pad(a.st.n) + 1;
   const size_t smem = sizeof(float2) * ((size_t)a.st.n + 2 * (size_t)NP * kColsPerCta);
+  if (smem > kSmemLimit) return fail_arg(B2N_E_UNSUPPORTED, "FFT length %d is too long for the run-time column pass", a.st.n);
   auto kern = k_fft_cols<INV>;
   B2N_SMEM_OPT_IN(kern, smem);
   const int64_t blocks = a.A * ceil_div(a.X, kColsPerCta);
@@ -571,7 +579,7 @@ extern "C" int b2n_fft_supported(int64_t n) {
   FftStages st;
   if (!make_stages(n, &st)) return 0;
   B2N_FAST_PLAN_SWITCH((int)n, return 2, (void)0)
-  return 1;
+  return runtime_pass_fits(n) ? 1 : 0;
 }
 
 extern "C" int b2n_fft_twiddles(int64_t n, void *twiddle_dev, void *stream) {
