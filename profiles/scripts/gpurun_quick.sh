@@ -1,3 +1,2 @@
-mkdir -p gpurun_out
-timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/q_pytest_all.log 2>&1; tail -3 gpurun_out/q_pytest_all.log
-timeout 600 python bench.py --steps 100 --warmup 5 2>&1 | tail -1 | cut -c1-260
+timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_autograd.py -m gpu -x -q -k "fused or cfg1 or cfg2 or toep or sense" 2>&1 | tail -2
+python profiles/host_overhead.py 2>&1 | tail -4

@@ -219,6 +219,28 @@ def _fft_work(im_size, grid_size, B, C, device) -> Optional[Tensor]:
     return torch.empty(n, dtype=torch.uint8, device=device) if n else None
 
 
+_FFT_CTX: dict = {}
+
+
+def _fft_ctx(im_size, grid_size, B, C, device):
+    """Per (sizes, batch, coils, device): the ctypes size arrays, twiddle pointer array and scratch size --
+    rebuilt arguments cost more host time than some of these kernels run."""
+    key = (tuple(im_size), tuple(grid_size), B, C, device.index)
+    ctx = _FFT_CTX.get(key)
+    if ctx is None:
+        n = _WORK_BYTES.get((tuple(im_size), tuple(grid_size), B, C))
+        if n is None:
+            nbytes = ctypes.c_size_t(0)
+            _lib.check(_lib.load().b2n_fft_work_bytes(len(im_size), _lib.i64_array(im_size), _lib.i64_array(grid_size),
+                                                      B, C, ctypes.byref(nbytes)), "b2n_fft_work_bytes")
+            n = _WORK_BYTES[(tuple(im_size), tuple(grid_size), B, C)] = int(nbytes.value)
+        tabs, tw = _twiddles(grid_size, device)
+        if len(_FFT_CTX) > 256:
+            _FFT_CTX.clear()
+        ctx = _FFT_CTX[key] = (_lib.i64_array(im_size), _lib.i64_array(grid_size), tw, n, tabs)
+    return ctx
+
+
 def fused_fft_forward(image: Tensor, grid_size: Sequence[int], smaps: Optional[Tensor] = None,
                       scaling_coef: Optional[Tensor] = None, scale: float = 1.0,
                       n_coils: Optional[int] = None) -> Tensor:
@@ -239,12 +261,12 @@ def fused_fft_forward(image: Tensor, grid_size: Sequence[int], smaps: Optional[T
         return out
     if scaling_coef is not None:
         scaling_coef = scaling_coef.contiguous()
-    work = _fft_work(im_size, grid_size, B, C, image.device)
-    _tabs, tw = _twiddles(grid_size, image.device)
+    n_arr, k_arr, tw, nwork, _tabs = _fft_ctx(im_size, grid_size, B, C, image.device)
+    work = torch.empty(nwork, dtype=torch.uint8, device=image.device) if nwork else None
     with device_guard(image.device):
         _lib.check(
             _lib.load().b2n_fft_forward_fused(
-                len(im_size), _lib.i64_array(im_size), _lib.i64_array(grid_size), B, C, image.data_ptr(), Ci,
+                len(im_size), n_arr, k_arr, B, C, image.data_ptr(), Ci,
                 smaps.data_ptr() if smaps is not None else None, Bs,
                 scaling_coef.data_ptr() if scaling_coef is not None else None, float(scale), tw, out.data_ptr(),
                 work.data_ptr() if work is not None else None, current_stream_ptr(image.device)),
@@ -277,12 +299,12 @@ def fused_fft_adjoint(grid: Tensor, im_size: Sequence[int], smaps: Optional[Tens
     if kernel is not None:
         kernel = kernel.contiguous()
         kb = kernel.shape[0] if kernel.ndim > len(grid_size) else 1
-    work = _fft_work(im_size, grid_size, B, C, grid.device)
-    _tabs, tw = _twiddles(grid_size, grid.device)
+    n_arr, k_arr, tw, nwork, _tabs = _fft_ctx(im_size, grid_size, B, C, grid.device)
+    work = torch.empty(nwork, dtype=torch.uint8, device=grid.device) if nwork else None
     with device_guard(grid.device):
         _lib.check(
             _lib.load().b2n_fft_adjoint_fused(
-                len(im_size), _lib.i64_array(im_size), _lib.i64_array(grid_size), B, C, grid.data_ptr(),
+                len(im_size), n_arr, k_arr, B, C, grid.data_ptr(),
                 kernel.data_ptr() if kernel is not None else None, kb,
                 smaps.data_ptr() if smaps is not None else None, Bs,
                 scaling_coef.data_ptr() if scaling_coef is not None else None, float(scale), tw, out.data_ptr(),

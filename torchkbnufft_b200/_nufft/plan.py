@@ -110,11 +110,17 @@ class Geometry:
         self.key: tuple = ()
 
 
+_HOST_INTS_FAST: dict = {}  # id(tensor) -> (_version, ints, tensor): identity front for _GRID_SIZE_CACHE
+
+
 def host_ints(sizes) -> Tuple[int, ...]:
     """Integer tuple of a size argument.  Device tensors (module buffers) are read
     once and then looked up by identity so the hot path never synchronises."""
     if not isinstance(sizes, Tensor):
         return tuple(int(k) for k in sizes)
+    fast = _HOST_INTS_FAST.get(id(sizes))
+    if fast is not None and fast[0] == sizes._version and fast[2] is sizes:
+        return fast[1]
     tkey = _tkey(sizes)
     hit = _GRID_SIZE_CACHE.get(tkey)
     if hit is None:
@@ -122,6 +128,9 @@ def host_ints(sizes) -> Tuple[int, ...]:
         if len(_GRID_SIZE_CACHE) > 8 * GEOM_CACHE_SIZE:
             _GRID_SIZE_CACHE.clear()
         _GRID_SIZE_CACHE[tkey] = hit
+    if len(_HOST_INTS_FAST) > 16 * GEOM_CACHE_SIZE:
+        _HOST_INTS_FAST.clear()
+    _HOST_INTS_FAST[id(sizes)] = (sizes._version, hit[0], sizes)
     return hit[0]
 
 
@@ -252,6 +261,7 @@ def clear_caches() -> None:
     _GEOM_CACHE.clear()
     _GEOM_FAST.clear()
     _GRID_SIZE_CACHE.clear()
+    _HOST_INTS_FAST.clear()
 
 
 def normalize_omega(omega: Tensor, n_batch: int, what: str) -> Tensor:
