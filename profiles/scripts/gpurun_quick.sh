@@ -1,2 +1,2 @@
-timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_autograd.py -m gpu -x -q -k "fused or cfg1 or cfg2 or toep or sense" 2>&1 | tail -2
-python profiles/host_overhead.py 2>&1 | tail -4
+timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "fused_pruned or fast_fft" 2>&1 | tail -2
+timeout 600 python bench.py --steps 100 --warmup 5 --breakdown --no-cpu-baseline 2>&1 | grep -E "stage ms|step ms"

@@ -15,11 +15,15 @@ template <class P> struct FastCfg {
   // launch is typically 1-3 waves of resident line pairs); column pass: PAIRS column pairs per CTA
   static constexpr int LP = P::T >= 160 ? 1 : 160 / P::T;
   static constexpr int ROW_THREADS = LP * P::T;
+  // row pass + coil sum: twice as many line pairs per CTA, i.e. fewer coil groups to meet through global memory
+  static constexpr int LPS = P::T >= 160 ? 1 : 320 / P::T;
+  static constexpr int SENSE_THREADS = LPS * P::T;
   static constexpr int PAIRS = P::T >= 256 ? 2 : (P::T >= 64 ? 4 : 256 / P::T);
   static constexpr int COL_THREADS = PAIRS * P::T;
   // register budget: 64 per thread (128 for radix-16 butterflies on pairs) -> resident CTAs per SM
   static constexpr int REG_THREADS = P::RMAX >= 16 ? 512 : 1024;
   static constexpr int ROW_MINB = REG_THREADS / ROW_THREADS > 0 ? REG_THREADS / ROW_THREADS : 1;
+  static constexpr int SENSE_MINB = REG_THREADS / SENSE_THREADS > 0 ? REG_THREADS / SENSE_THREADS : 1;
   static constexpr int COL_MINB = REG_THREADS / COL_THREADS > 0 ? REG_THREADS / COL_THREADS : 1;
 };
 
@@ -128,9 +132,9 @@ __global__ void __launch_bounds__(FastCfg<P>::COL_THREADS, FastCfg<P>::COL_MINB)
 // CTAs each writes its partial row to scratch and the CTA that arrives last (one atomic ticket per row) adds
 // the partial rows in coil-group order -- a fixed summation order, so the result is bit-reproducible.
 template <class P, bool HALF>
-__global__ void __launch_bounds__(FastCfg<P>::ROW_THREADS, FastCfg<P>::ROW_MINB) k_fft_rows_sense(RowArgs a) {
+__global__ void __launch_bounds__(FastCfg<P>::SENSE_THREADS, FastCfg<P>::SENSE_MINB) k_fft_rows_sense(RowArgs a) {
   extern __shared__ __align__(16) float4 fsm4[];
-  constexpr int LP = FastCfg<P>::LP, NT = FastCfg<P>::ROW_THREADS;
+  constexpr int LP = FastCfg<P>::LPS, NT = FastCfg<P>::SENSE_THREADS;
   __shared__ int s_last;
   const int n_in = a.n_in, n_out = a.n_out;
   float2 *red = reinterpret_cast<float2 *>(fsm4 + LP * P::NP);  // [LP][n_out] pair sums
@@ -223,13 +227,13 @@ template <class P, bool INV> int launch_cols_fast(ColArgs &a, cudaStream_t st) {
 
 template <class P, bool HALF> int launch_rows_sense_h(RowArgs &a, int64_t B, cudaStream_t st) {
   using Cfg = FastCfg<P>;
-  a.coil_groups = (int)ceil_div(a.C, 2 * Cfg::LP);
+  a.coil_groups = (int)ceil_div(a.C, 2 * Cfg::LPS);
   const int64_t rows = B * a.rows_per_img;
-  const size_t smem = sizeof(float4) * (size_t)Cfg::LP * P::NP + sizeof(float2) * (size_t)Cfg::LP * a.n_out;
+  const size_t smem = sizeof(float4) * (size_t)Cfg::LPS * P::NP + sizeof(float2) * (size_t)Cfg::LPS * a.n_out;
   auto kern = k_fft_rows_sense<P, HALF>;
   B2N_SMEM_OPT_IN(kern, smem);
   if (a.coil_groups > 1) B2N_CUDA_OK(cudaMemsetAsync(a.counter, 0, sizeof(unsigned int) * (size_t)rows, st));
-  kern<<<(unsigned)(rows * a.coil_groups), Cfg::ROW_THREADS, smem, st>>>(a);
+  kern<<<(unsigned)(rows * a.coil_groups), Cfg::SENSE_THREADS, smem, st>>>(a);
   B2N_LAUNCH_OK("k_fft_rows_sense");
   return 0;
 }
