@@ -718,7 +718,9 @@ __global__ void __launch_bounds__(kThreads, 3) k_adj_coilwarp_2d(InterpArgs<floa
         w2_n = w[n_it[2]];
       }
       float2 *tp = tplane + (bs.x - sp.y0) * kSX + (bs.y - sp.x0);
-      float2 t0 = tp[off_it[0]], t1 = tp[off_it[1]], t2 = tp[off_it[2]];
+      // lanes without a third cell re-read their own first one (a dummy read of another lane's cell would be an
+      // intra-warp read/write hazard for compute-sanitizer racecheck)
+      float2 t0 = tp[off_it[0]], t1 = tp[off_it[1]], t2 = tp[last_on ? off_it[2] : off_it[0]];
       cmacf(t0, w0, v);
       cmacf(t1, w1, v);
       cmacf(t2, w2, v);
