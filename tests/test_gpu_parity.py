@@ -460,7 +460,9 @@ def test_tiled_kernels_match_generic_and_oracle(grid_size, B, C, batched):
                                   ((5, 500), (7, 1024)), ((64, 9), (128, 18)), ((31, 15), (64, 30)),
                                   ((20, 33, 48), (64, 64, 128)), ((6, 128, 100), (12, 256, 320)),
                                   ((48, 96), (96, 192)), ((150, 288), (384, 576)), ((3, 640), (6, 1280)),
-                                  ((1000,), (2048,)), ((4, 700), (8, 2048)), ((40, 40, 40), (96, 96, 96))])
+                                  ((1000,), (2048,)), ((4, 700), (8, 2048)), ((40, 40, 40), (96, 96, 96)),
+                                  ((112, 224), (224, 448)), ((144, 240), (288, 480)), ((5, 448), (10, 896)),
+                                  ((480,), (960,))])
 def test_fused_pruned_fft_matches_torch(N, K):
     """Own Stockham passes (pruned inputs / cropped outputs, fused apodisation, SENSE multiply,
     coil sum and Toeplitz kernel multiply) against torch.fft + plain torch ops, complex64."""
@@ -501,7 +503,7 @@ def test_fused_pruned_fft_matches_torch(N, K):
     assert not eng_fft.fused_fft_available(dt, (57,)) and not eng_fft.fused_fft_available(torch.complex128, K)
     eng_fft.use_fused_fft = "auto"
     assert eng_fft.fused_fft_available(dt, (640, 256)) and not eng_fft.fused_fft_available(dt, (640, 24))
-    assert all(eng_fft.fused_fft_available(dt, (n,)) for n in (64, 96, 128, 192, 256, 320, 384, 512, 576, 640, 768, 1024, 1280, 2048))
+    assert all(eng_fft.fused_fft_available(dt, (n,)) for n in (64, 96, 128, 192, 224, 256, 288, 320, 384, 448, 480, 512, 576, 640, 768, 896, 960, 1024, 1280, 2048))
 
 
 def test_fast_fft_plans_agree_with_runtime_passes():

@@ -92,6 +92,26 @@ template <bool INV> B2N_HD void dft5(float4 &v0, float4 &v1, float4 &v2, float4 
   v2 = vadd(m2, n2);
   v3 = vsub(m2, n2);
 }
+template <bool INV> B2N_HD void dft7(float4 *v) {
+  const float c1 = 0.62348980185873353053f, c2 = -0.22252093395631440429f, c3 = -0.90096886790241912624f;  // cos(2 pi j/7)
+  const float s1 = 0.78183148246802980871f, s2 = 0.97492791218182360702f, s3 = 0.43388373911755812048f;   // sin(2 pi j/7)
+  const float4 a1 = vadd(v[1], v[6]), a2 = vadd(v[2], v[5]), a3 = vadd(v[3], v[4]);
+  const float4 b1 = vsub(v[1], v[6]), b2 = vsub(v[2], v[5]), b3 = vsub(v[3], v[4]);
+  const float4 x0 = v[0];
+  const float4 m1 = vaxpy(vaxpy(vaxpy(x0, c1, a1), c2, a2), c3, a3);
+  const float4 m2 = vaxpy(vaxpy(vaxpy(x0, c2, a1), c3, a2), c1, a3);
+  const float4 m3 = vaxpy(vaxpy(vaxpy(x0, c3, a1), c1, a2), c2, a3);
+  const float4 n1 = vrot<INV>(vaxpy(vaxpy(vscale(b1, s1), s2, b2), s3, b3));
+  const float4 n2 = vrot<INV>(vaxpy(vaxpy(vscale(b1, s2), -s3, b2), -s1, b3));
+  const float4 n3 = vrot<INV>(vaxpy(vaxpy(vscale(b1, s3), -s1, b2), s2, b3));
+  v[0] = vadd(x0, vadd(a1, vadd(a2, a3)));
+  v[1] = vadd(m1, n1);
+  v[6] = vsub(m1, n1);
+  v[2] = vadd(m2, n2);
+  v[5] = vsub(m2, n2);
+  v[3] = vadd(m3, n3);
+  v[4] = vsub(m3, n3);
+}
 // second half of the radix-8 butterfly: e = DFT4 of the even inputs, o = DFT4 of the odd inputs
 template <bool INV>
 B2N_HD void dft8_finish(float4 e0, float4 e1, float4 e2, float4 e3, float4 o0, float4 o1, float4 o2, float4 o3,
@@ -222,11 +242,12 @@ template <bool INV> B2N_HD void dft16_half_in(float4 *v) {
 }
 
 template <int R, bool INV> B2N_HD void dft(float4 *v) {
-  static_assert(R == 2 || R == 3 || R == 4 || R == 5 || R == 8 || R == 10 || R == 12 || R == 16, "radix");
+  static_assert(R == 2 || R == 3 || R == 4 || R == 5 || R == 7 || R == 8 || R == 10 || R == 12 || R == 16, "radix");
   if constexpr (R == 2) dft2(v[0], v[1]);
   if constexpr (R == 3) dft3<INV>(v[0], v[1], v[2]);
   if constexpr (R == 4) dft4<INV>(v[0], v[1], v[2], v[3]);
   if constexpr (R == 5) dft5<INV>(v[0], v[1], v[2], v[3], v[4]);
+  if constexpr (R == 7) dft7<INV>(v);
   if constexpr (R == 8) dft8<INV>(v);
   if constexpr (R == 10) dft10<INV>(v);
   if constexpr (R == 12) dft12<INV>(v);
@@ -362,9 +383,11 @@ __device__ __forceinline__ void fft_line_pair(int t, float4 *sm, int es, const f
 // stages.  Every other length takes the run-time passes or cuFFT.
 #define B2N_FAST_PLANS(X, ...)                                                                                  \
   X(64, 8, 8, 1, __VA_ARGS__) X(96, 8, 12, 1, __VA_ARGS__) X(128, 8, 16, 1, __VA_ARGS__)                       \
-  X(192, 8, 8, 3, __VA_ARGS__) X(256, 16, 16, 1, __VA_ARGS__) X(320, 8, 8, 5, __VA_ARGS__)                     \
-  X(384, 8, 16, 3, __VA_ARGS__) X(512, 8, 8, 8, __VA_ARGS__) X(576, 16, 12, 3, __VA_ARGS__)                    \
-  X(640, 8, 8, 10, __VA_ARGS__) X(768, 8, 8, 12, __VA_ARGS__) X(1024, 8, 8, 16, __VA_ARGS__)                   \
+  X(192, 8, 8, 3, __VA_ARGS__) X(224, 8, 4, 7, __VA_ARGS__) X(256, 16, 16, 1, __VA_ARGS__)                     \
+  X(288, 8, 12, 3, __VA_ARGS__) X(320, 8, 8, 5, __VA_ARGS__) X(384, 8, 16, 3, __VA_ARGS__)                     \
+  X(448, 8, 8, 7, __VA_ARGS__) X(480, 8, 12, 5, __VA_ARGS__) X(512, 8, 8, 8, __VA_ARGS__)                      \
+  X(576, 16, 12, 3, __VA_ARGS__) X(640, 8, 8, 10, __VA_ARGS__) X(768, 8, 8, 12, __VA_ARGS__)                   \
+  X(896, 16, 8, 7, __VA_ARGS__) X(960, 16, 12, 5, __VA_ARGS__) X(1024, 8, 8, 16, __VA_ARGS__)                  \
   X(1280, 16, 8, 10, __VA_ARGS__) X(2048, 16, 16, 8, __VA_ARGS__)
 
 #define B2N_FAST_PLAN_USING(N, R0, R1, R2, ...) using Plan##N = Plan<N, R0, R1, R2>;
