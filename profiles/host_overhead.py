@@ -40,6 +40,18 @@ for name in ("cfg2", "cfg1"):
         k = nu(x, om, **kw); na(k, om, **kw)
     e1.record(); torch.cuda.synchronize()
     print(f"{name}: host enqueue {t_host*1e6:7.1f} us/pair   wall {t_wall*1e6:7.1f} us/pair   gpu-timeline {e0.elapsed_time(e1)/n*1e3:7.1f} us/pair", flush=True)
+    # (d) the same pair captured once in a CUDA graph and replayed: no per-call host work at all
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph, stream=side):
+        k = nu(x, om, **kw); im = na(k, om, **kw)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(n):
+        graph.replay()
+    torch.cuda.synchronize()
+    print(f"{name}: CUDA-graph replay wall {(time.perf_counter()-t0)/n*1e6:7.1f} us/pair", flush=True)
     with torch.no_grad():
         t0 = time.perf_counter()
         for _ in range(n):
