@@ -345,15 +345,6 @@ template <bool INV, int MODE> static int launch_rows(RowArgs &a, cudaStream_t st
   return 0;
 }
 
-// whether launch_cols() takes the compile-time planned kernel for these arguments (the only one that honours
-// ColArgs::zero_words)
-static bool launched_fast_cols(const ColArgs &a) {
-  if (!g_fast_fft || a.A <= 0 || a.X <= 0 || a.X % 2 != 0 || !aligned16(a.in) || !aligned16(a.out) || !aligned16(a.mul))
-    return false;
-  B2N_FAST_PLAN_SWITCH(a.st.n, return true, (void)0)
-  return false;
-}
-
 template <bool INV> static int launch_cols(ColArgs &a, cudaStream_t st) {
   if (a.A <= 0 || a.X <= 0) return 0;
   if (a.X % 2 == 0 && aligned16(a.in) && aligned16(a.out) && aligned16(a.mul)) {
@@ -495,7 +486,6 @@ static int fused_adjoint(const FusedGeom &g, const float2 *grid, const float2 *k
   fused_work_layout(g, &t1e, &t2e, &t3e);
   float2 *T1 = work, *T2 = work + t1e, *T3 = work + t1e + t2e;
   const float2 *rows_in = grid;
-  bool counters_zeroed = false;
   ColArgs c;
   memset(&c, 0, sizeof(c));
   c.scale = 1.f;
@@ -535,13 +525,8 @@ static int fused_adjoint(const FusedGeom &g, const float2 *grid, const float2 *k
     c.out = T1;
     c.mul = kernel;
     c.a_per_mul = kernel_batch > 1 ? g.C : 0;
-    if (smaps) {  // the row pass + coil sum that follows wants zeroed arrival counters: let this pass do it
-      c.zero_words = reinterpret_cast<unsigned int *>(work + t1e + t2e + t3e);
-      c.n_zero_words = (int)(g.B * g.N[0]);
-    }
     int rc = launch_cols<true>(c, st);
     if (rc) return rc;
-    counters_zeroed = smaps && launched_fast_cols(c);
     rows_in = T1;
   } else if (kernel) {
     return fail_arg(B2N_E_UNSUPPORTED, "1-D Toeplitz filtering goes through the unfused path");
@@ -571,7 +556,6 @@ static int fused_adjoint(const FusedGeom &g, const float2 *grid, const float2 *k
   r.scale = scale;
   r.partial = T3;
   r.counter = reinterpret_cast<unsigned int *>(T3 + t3e);
-  r.counters_zeroed = counters_zeroed ? 1 : 0;
   {
     const int rc = launch_rows_sense(r, g.B, st);
     if (rc >= 0) return rc;

@@ -27,7 +27,6 @@ struct RowArgs {
   int coil_groups;
   float2 *partial;
   unsigned int *counter;
-  int counters_zeroed;  // the preceding column pass has zeroed `counter` (ColArgs::zero_words)
 };
 
 struct ColArgs {
@@ -40,10 +39,6 @@ struct ColArgs {
   int64_t a_per_mul; // outer indices per mul batch entry (0: single kernel)
   const float2 *tw;  // twiddle table of length n
   float scale;
-  // optional: words zeroed by CTA 0 on the side (the arrival counters of the k_fft_rows_sense launch that follows;
-  // saves a separate memset operation in the stream)
-  unsigned int *zero_words;
-  int n_zero_words;
 };
 
 }  // namespace b2n

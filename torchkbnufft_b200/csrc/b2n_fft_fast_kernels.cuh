@@ -114,8 +114,6 @@ __global__ void __launch_bounds__(FastCfg<P>::COL_THREADS, FastCfg<P>::COL_MINB)
       a.mul ? reinterpret_cast<const float4 *>(a.mul + (a.a_per_mul ? (oa / a.a_per_mul) * (int64_t)P::N * a.X : 0) + x)
             : nullptr;
   const float scale = a.scale;
-  if (a.zero_words && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0)
-    for (int e = threadIdx.x; e < a.n_zero_words; e += FastCfg<P>::COL_THREADS) a.zero_words[e] = 0u;
   auto loadg = [&](int i) -> float4 {
     if (!on || i >= n_in) return fast::v4(0.f, 0.f, 0.f, 0.f);
     float4 v = in[i * X2];
@@ -234,8 +232,7 @@ template <class P, bool HALF> int launch_rows_sense_h(RowArgs &a, int64_t B, cud
   const size_t smem = sizeof(float4) * (size_t)Cfg::LPS * P::NP + sizeof(float2) * (size_t)Cfg::LPS * a.n_out;
   auto kern = k_fft_rows_sense<P, HALF>;
   B2N_SMEM_OPT_IN(kern, smem);
-  if (a.coil_groups > 1 && !a.counters_zeroed)
-    B2N_CUDA_OK(cudaMemsetAsync(a.counter, 0, sizeof(unsigned int) * (size_t)rows, st));
+  if (a.coil_groups > 1) B2N_CUDA_OK(cudaMemsetAsync(a.counter, 0, sizeof(unsigned int) * (size_t)rows, st));
   kern<<<(unsigned)(rows * a.coil_groups), Cfg::SENSE_THREADS, smem, st>>>(a);
   B2N_LAUNCH_OK("k_fft_rows_sense");
   return 0;
