@@ -172,6 +172,11 @@ def get_geometry(tables: Sequence[Tensor], n_shift: Tensor, numpoints: Tensor, t
     return geo
 
 
+_RING = None          # pinned int32 ring for the asynchronous read-back of the sub-problem counts
+_RING_SLOTS = 256
+_RING_NEXT = 0
+
+
 class TrajectoryPlan:
     """Device-resident ``b2n_points`` plan for one ``(geometry, omega)`` pair."""
 
@@ -203,22 +208,39 @@ class TrajectoryPlan:
         self._om_contig = om
         self.workspace.record_stream(torch.cuda.current_stream(omega.device))
         # The number of sub-problems is only known on the device; kernels are launched over the upper bound
-        # n_sub_max and the surplus CTAs exit at once (~3 us of tail per launch at BASELINE config 2).  Fetch the
-        # exact count asynchronously -- no synchronisation here -- and tighten the bound once it has arrived.
+        # n_sub_max and the surplus CTAs exit at once (~3 us of tail per launch at BASELINE config 2).  When a
+        # plan is REUSED, the exact count is fetched asynchronously -- no synchronisation -- and the bound is
+        # tightened once it has arrived.  (Not at build time: a device-to-host copy in the compute stream queues
+        # behind bulk downloads on the copy engine and would stall pipelines that change trajectory every call.)
         self._n_sub_host = None
         self._n_sub_event = None
-        if self.struct.n_sub and self.struct.n_sub_max > 0:
-            off = int(self.struct.n_sub) - self.workspace.data_ptr()
-            self._n_sub_host = torch.empty(1, dtype=torch.int32).pin_memory()
-            self._n_sub_host.copy_(self.workspace[off:off + 4].view(torch.int32), non_blocking=True)
-            self._n_sub_event = torch.cuda.Event()
-            self._n_sub_event.record(torch.cuda.current_stream(omega.device))
+        self._count_requested = not (self.struct.n_sub and self.struct.n_sub_max > 0)
+
+    def request_count(self) -> None:
+        """Start the asynchronous read-back of the device-side sub-problem count (first reuse of the plan)."""
+        self._count_requested = True
+        off = int(self.struct.n_sub) - self.workspace.data_ptr()
+        # a slot of a pinned ring allocated once (pinning memory per plan would cost a blocking cudaHostAlloc)
+        global _RING, _RING_NEXT
+        if _RING is None:
+            _RING = torch.empty(_RING_SLOTS, dtype=torch.int32).pin_memory()
+        self._n_sub_token = _RING_NEXT
+        _RING_NEXT += 1
+        self._n_sub_host = _RING[self._n_sub_token % _RING_SLOTS:self._n_sub_token % _RING_SLOTS + 1]
+        self._n_sub_host.copy_(self.workspace[off:off + 4].view(torch.int32), non_blocking=True)
+        self._n_sub_event = torch.cuda.Event()
+        self._n_sub_event.record(torch.cuda.current_stream(self.omega.device))
 
     def tighten(self) -> None:
         """Replace the launch bound n_sub_max by the exact sub-problem count once the asynchronous read-back of
         the device counter has completed (cheap no-op before that and after it has been applied)."""
         ev = self._n_sub_event
-        if ev is None or torch.cuda.is_current_stream_capturing() or not ev.query():
+        if ev is None:
+            return
+        if _RING_NEXT - self._n_sub_token >= _RING_SLOTS:  # the ring slot has been handed to a newer plan
+            self._n_sub_event = None
+            return
+        if torch.cuda.is_current_stream_capturing() or not ev.query():
             return  # (event queries are not allowed while a CUDA graph is being captured)
         self._n_sub_event = None
         n = int(self._n_sub_host[0])
@@ -233,7 +255,10 @@ def get_plan(geo: Geometry, omega: Tensor) -> TrajectoryPlan:
     fkey = (id(geo), id(omega), omega._version)
     plan = _PLAN_FAST.get(fkey)
     if plan is not None:
-        if plan._n_sub_event is not None:
+        if not plan._count_requested:
+            if not torch.cuda.is_current_stream_capturing():
+                plan.request_count()
+        elif plan._n_sub_event is not None:
             plan.tighten()
         return plan
     key = (geo.key, _tkey(omega))
