@@ -473,6 +473,9 @@ def main():
     # ---- the same step captured once in a CUDA graph and replayed (no per-launch host work, no launch gaps) -----
     graph_info = None
     try:
+        step()  # the e2e section above rebuilt many plans: make sure this trajectory's plan is cached again, so
+        step()  # that the captured graph holds the six kernels of the step and not a plan build
+        torch.cuda.synchronize()
         side = torch.cuda.Stream(dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         graph = torch.cuda.CUDAGraph()
