@@ -1,1 +1,2 @@
-for i in 1 2; do timeout 600 python bench.py --steps 100 --warmup 5 --no-cpu-baseline 2>&1 | grep '^{"metric"' | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['ms_per_step'], d['cuda_graph']['ms_per_step'], d['e2e']['ms_per_step'], d['e2e']['serial_ms_per_step'])"; done
+timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "fused_pruned or fast_fft or cfg4" 2>&1 | tail -2
+timeout 900 python profiles/bench_configs.py cfg4 cfg2 2>&1 | tail -3

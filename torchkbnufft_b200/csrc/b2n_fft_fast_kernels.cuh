@@ -239,6 +239,9 @@ template <class P, bool HALF> int launch_rows_sense_h(RowArgs &a, int64_t B, cud
 }
 
 template <class P> int launch_rows_sense_any(RowArgs &a, int64_t B, cudaStream_t st) {
+  // a CTA carries FastCfg<P>::LPS coil pairs of one image row: with fewer coils than half of that most of its threads
+  // would idle through the barriers (short lines, few coils: 256^3 x 8 coils) -- take the unfused route instead
+  if (2 * ((a.C + 1) / 2) < FastCfg<P>::LPS) return -1;
   return 2 * a.n_out <= P::N ? launch_rows_sense_h<P, true>(a, B, st) : launch_rows_sense_h<P, false>(a, B, st);
 }
 
