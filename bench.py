@@ -530,7 +530,9 @@ def main():
                        "grid_size": list(wl.grid_size), "numpoints": 6, "adjoint_mode": tkbn.get_adjoint_mode(),
                        "parallelism": f"batch-sharded x{world} (no collective)",
                        "l2": "512 MiB buffer written between timed steps (L2 flush)",
-                       "plan": "trajectory plan cached across steps (built in warm-up)"},
+                       "plan": "trajectory plan cached across steps (built in warm-up)",
+                       "fft": ("own pruned passes (compile-time plans, libb200nufft.so)" if fused else
+                               "cuFFT via torch.fft + own pad/crop kernels")},
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "kernel_ms": live[dom], "kernels_ms_in_step": live,
