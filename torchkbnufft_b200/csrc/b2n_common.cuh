@@ -50,6 +50,32 @@ void count_launch();
     }                                                                                                      \
   } while (0)
 
+// ---- programmatic dependent launch (sm_90+) ----------------------------------------------------------------
+// A kernel launched with launch_pdl() and B2N_OPT_PDL set may be scheduled while the tail of the preceding kernel in
+// the stream is still running: its CTAs execute their prologue and block in griddep_wait() until the preceding grid
+// has completed and its writes are visible.  griddep_launch() in the preceding kernel lets that happen as soon as all
+// of ITS CTAs have been scheduled.  Without the launch attribute both instructions are no-ops.
+extern int g_pdl;
+#ifdef __CUDACC__
+B2N_D void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+B2N_D void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                     Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = g_pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+#endif
+
 template <typename T> struct cplx { T x, y; };
 template <> struct __align__(8) cplx<float> { float x, y; };
 template <> struct __align__(16) cplx<double> { double x, y; };

@@ -39,6 +39,8 @@ B2N_D float2 row_operand(const float2 *in, const float2 *sm, const float2 *sc, i
 template <class P, bool INV, int MODE, bool HALF>
 __global__ void __launch_bounds__(FastCfg<P>::ROW_THREADS, FastCfg<P>::ROW_MINB) k_fft_rows_fast(RowArgs a) {
   extern __shared__ __align__(16) float4 fsm4[];
+  griddep_launch();
+  griddep_wait();  // inputs may come from the preceding kernel
   constexpr int LP = FastCfg<P>::LP;
   const int lp = threadIdx.x / P::T, t = threadIdx.x - lp * P::T;
   const int64_t lA = ((int64_t)blockIdx.x * LP + lp) * 2;
@@ -101,6 +103,8 @@ __global__ void __launch_bounds__(FastCfg<P>::ROW_THREADS, FastCfg<P>::ROW_MINB)
 template <class P, bool INV, bool HALF>
 __global__ void __launch_bounds__(FastCfg<P>::COL_THREADS, FastCfg<P>::COL_MINB) k_fft_cols_fast(ColArgs a) {
   extern __shared__ __align__(16) float4 fsm4[];
+  griddep_launch();
+  griddep_wait();  // the input rows come from the preceding pass
   constexpr int PAIRS = FastCfg<P>::PAIRS;
   const int p = threadIdx.x % PAIRS, t = threadIdx.x / PAIRS;  // pair index fastest: contiguous global segments
   const int X = (int)a.X, X2 = X >> 1, n_in = a.n_in, n_out = a.n_out;
@@ -134,6 +138,8 @@ __global__ void __launch_bounds__(FastCfg<P>::COL_THREADS, FastCfg<P>::COL_MINB)
 template <class P, bool HALF>
 __global__ void __launch_bounds__(FastCfg<P>::SENSE_THREADS, FastCfg<P>::SENSE_MINB) k_fft_rows_sense(RowArgs a) {
   extern __shared__ __align__(16) float4 fsm4[];
+  griddep_launch();
+  griddep_wait();  // the input rows come from the preceding pass
   constexpr int LP = FastCfg<P>::LPS, NT = FastCfg<P>::SENSE_THREADS;
   __shared__ int s_last;
   const int n_in = a.n_in, n_out = a.n_out;
@@ -200,7 +206,7 @@ template <class P, bool INV, int MODE, bool HALF> int launch_rows_fast_h(RowArgs
   const size_t smem = sizeof(float4) * (size_t)Cfg::LP * P::NP;
   auto kern = k_fft_rows_fast<P, INV, MODE, HALF>;
   B2N_SMEM_OPT_IN(kern, smem);
-  kern<<<(unsigned)ceil_div(a.lines, 2 * Cfg::LP), Cfg::ROW_THREADS, smem, st>>>(a);
+  B2N_CUDA_OK(launch_pdl(kern, dim3((unsigned)ceil_div(a.lines, 2 * Cfg::LP)), dim3(Cfg::ROW_THREADS), smem, st, a));
   B2N_LAUNCH_OK("k_fft_rows_fast");
   return 0;
 }
@@ -216,7 +222,7 @@ template <class P, bool INV, bool HALF> int launch_cols_fast_h(ColArgs &a, cudaS
   B2N_SMEM_OPT_IN(kern, smem);
   const int64_t gy = a.A < 32768 ? a.A : 32768;
   const dim3 grid((unsigned)ceil_div(a.X, 2 * Cfg::PAIRS), (unsigned)gy, (unsigned)ceil_div(a.A, gy));
-  kern<<<grid, Cfg::COL_THREADS, smem, st>>>(a);
+  B2N_CUDA_OK(launch_pdl(kern, grid, dim3(Cfg::COL_THREADS), smem, st, a));
   B2N_LAUNCH_OK("k_fft_cols_fast");
   return 0;
 }
@@ -233,7 +239,7 @@ template <class P, bool HALF> int launch_rows_sense_h(RowArgs &a, int64_t B, cud
   auto kern = k_fft_rows_sense<P, HALF>;
   B2N_SMEM_OPT_IN(kern, smem);
   if (a.coil_groups > 1) B2N_CUDA_OK(cudaMemsetAsync(a.counter, 0, sizeof(unsigned int) * (size_t)rows, st));
-  kern<<<(unsigned)(rows * a.coil_groups), Cfg::SENSE_THREADS, smem, st>>>(a);
+  B2N_CUDA_OK(launch_pdl(kern, dim3((unsigned)(rows * a.coil_groups)), dim3(Cfg::SENSE_THREADS), smem, st, a));
   B2N_LAUNCH_OK("k_fft_rows_sense");
   return 0;
 }

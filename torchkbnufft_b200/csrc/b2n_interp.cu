@@ -148,10 +148,12 @@ __global__ void __launch_bounds__(128) k_fwd_point6_2d(InterpArgs<float> a, cons
                                                        float2 *__restrict__ kdata) {
   const int64_t total = a.n_traj * a.M;
   const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  griddep_launch();
   if (s >= total) return;
-  const Point6 p = load_point6(a, s);
+  const Point6 p = load_point6(a, s);  // plan records: independent of the kernel that produced the grid
   const int64_t m = a.perm[s];
   const int64_t rows = a.n_traj == 1 ? a.B * a.C : a.C;
+  griddep_wait();
   for (int64_t r = blockIdx.y; r < rows; r += gridDim.y) {
     const int64_t bc = a.n_traj == 1 ? r : (s / a.M) * a.C + r;
     const float2 *g = grid + bc * a.Kprod;
@@ -320,7 +322,7 @@ static int forward_t(const b2n_geom *g, const b2n_points *p, const void *grid, i
     if (point6_eligible(g, p, layout)) {
       const int64_t total = a.n_traj * a.M, rows = a.n_traj == 1 ? a.B * a.C : a.C;
       dim3 gd((unsigned)ceil_div(total, 128), (unsigned)(rows < 65535 ? rows : 65535));
-      k_fwd_point6_2d<<<gd, 128, 0, st>>>(a, (const float2 *)grid, (float2 *)kdata);
+      B2N_CUDA_OK(launch_pdl(k_fwd_point6_2d, gd, dim3(128), 0, st, a, (const float2 *)grid, (float2 *)kdata));
       B2N_LAUNCH_OK("k_fwd_point6_2d");
       return 0;
     }
@@ -381,7 +383,8 @@ extern int g_adj_rowwarp;
 extern int g_fwd_chunk;
 extern int g_adj_chunk;
 extern int g_fast_fft;
-static int g_options[B2N_OPT_COUNT] = {1, 0, 0, 0, 1};
+int g_pdl = 1;
+static int g_options[B2N_OPT_COUNT] = {1, 0, 0, 0, 1, 1};
 
 // With very few 2-D (batch, coil) rows most coil lanes of a tiled gather CTA idle while its per-point cost stays the
 // same: the one-thread-per-point kernel (k_fwd_point6_2d) wins up to 3 rows (16 vs 29 us for one row, 30 vs 41 us for
@@ -405,6 +408,7 @@ extern "C" int b2n_set_option(int option, int value) {
   if (option == B2N_OPT_FWD_COIL_CHUNK) g_fwd_chunk = value;
   if (option == B2N_OPT_ADJ_COIL_CHUNK) g_adj_chunk = value;
   if (option == B2N_OPT_FAST_FFT) g_fast_fft = value;
+  if (option == B2N_OPT_PDL) g_pdl = value;
   return 0;
 }
 

@@ -115,24 +115,15 @@ __global__ void __launch_bounds__(kThreads, 3) k_fwd_tiled_2d(InterpArgs<float> 
   int *s_perm = reinterpret_cast<int *>(s_base + kCap);                // [kCap]
   uint64_t *bar = reinterpret_cast<uint64_t *>(s_perm + kCap);
   const long long t_start = a.trace ? gtime() : 0;
+  griddep_launch();
   const SubProblem sp = decode<CC>(a);
   if (!sp.valid) return;
   const int Ky = (int)a.K[0], Kx = (int)a.K[1];
   const int C = (int)a.C;
   const bool tma = use_tma && sp.interior;
 
-  // the tile first (longest latency): one thread arms the mbarrier and issues the TMA boxes
-  if (tma) {
-    if (threadIdx.x == 0) {
-      mbar_init(bar, 1);
-      mbar_expect_tx(bar, (unsigned)(planes<CC>() * kPS * sizeof(float2)));
-      for (int p = 0; p < planes<CC>(); p += kBoxPlanes)
-        tma_load_4d(tile + p * kPS, &tmap, 2 * sp.x0, sp.y0, sp.c0 + p, sp.b, bar);
-    }
-  } else {
-    stage_tile_elementwise<CC>(tile, grid, sp, C, Ky, Kx);
-  }
-  // plan records of this sub-problem: contiguous in plan order
+  // plan records of this sub-problem (contiguous in plan order): they do not depend on the kernel that produced the
+  // grid, so under programmatic dependent launch they are fetched while that kernel's tail is still running
   {
     const float4 *src =
         reinterpret_cast<const float4 *>(reinterpret_cast<const float2 *>(a.coef) + (int64_t)sp.start * kNC);
@@ -143,6 +134,18 @@ __global__ void __launch_bounds__(kThreads, 3) k_fwd_tiled_2d(InterpArgs<float> 
       cp_async8(&s_base[e], &bsrc[e], true);
       cp_async4(&s_perm[e], &a.perm[sp.start + e]);
     }
+  }
+  if (tma && threadIdx.x == 0) mbar_init(bar, 1);
+  griddep_wait();  // the grid is complete and visible from here on
+  // the tile: one thread arms the mbarrier and issues the TMA boxes
+  if (tma) {
+    if (threadIdx.x == 0) {
+      mbar_expect_tx(bar, (unsigned)(planes<CC>() * kPS * sizeof(float2)));
+      for (int p = 0; p < planes<CC>(); p += kBoxPlanes)
+        tma_load_4d(tile + p * kPS, &tmap, 2 * sp.x0, sp.y0, sp.c0 + p, sp.b, bar);
+    }
+  } else {
+    stage_tile_elementwise<CC>(tile, grid, sp, C, Ky, Kx);
   }
   cp_async_commit();
   const long long t_issued = a.trace ? gtime() : 0;
@@ -464,6 +467,7 @@ __global__ void __launch_bounds__(NW * 32) k_adj_tiled_2d(InterpArgs<float> a, c
   float2 *stage0 = tile + planes<CC>() * kPS;           // 2 x STAGE
   int *s_perm = reinterpret_cast<int *>(stage0 + 2 * STAGE);  // 3 x kRound sample indices
   const long long t_start = a.trace ? gtime() : 0;
+  griddep_launch();  // the inverse FFT pass that follows may start its prologue during this kernel's tail
   const SubProblem sp = decode<CC>(a);
   if (!sp.valid) return;
   const int Ky = (int)a.K[0], Kx = (int)a.K[1];
@@ -1029,7 +1033,7 @@ static int launch_fwd(const InterpArgs<float> &a, const void *grid, void *kdata,
   memset(&map, 0, sizeof(map));
   const int use_tma = make_grid_tmap(&map, grid, a.B, a.C, a.K[0], a.K[1]) ? 1 : 0;
   dim3 gd((unsigned)a.n_sub_max, (unsigned)ceil_div(a.C, CC), (unsigned)(a.n_traj == 1 ? a.B : 1));
-  kern<<<gd, kThreads, smem, st>>>(a, (const float2 *)grid, (float2 *)kdata, map, use_tma);
+  B2N_CUDA_OK(launch_pdl(kern, gd, dim3(kThreads), smem, st, a, (const float2 *)grid, (float2 *)kdata, map, use_tma));
   B2N_LAUNCH_OK("k_fwd_tiled_2d");
   return 0;
 }
