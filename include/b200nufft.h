@@ -231,6 +231,19 @@ B2N_API int b2n_fft_adjoint_fused(int ndim, const int64_t *im_size, const int64_
                                   int64_t kernel_batch, const void *smaps_dev, int64_t smaps_batch,
                                   const void *scaling_dev, double scale, const void *const *twiddle_dev,
                                   void *image_dev, void *work_dev, void *stream);
+/* Toeplitz normal operator  out[b] = scale * sum_c conj(S_c) crop(IFFT(kernel * FFT(zero_pad(S_c * image[b]))))
+ * (unnormalised transforms) in THREE passes: forward rows, then one column pass that transforms, multiplies by the
+ * kernel spectrum and transforms back inside the CTA, then inverse rows + coil sum -- the full-size spectrum is never
+ * written to memory.  2-D complex64, grid_size[0] a compile-time planned length (b2n_fft_supported == 2) with
+ * 2*im_size[0] <= grid_size[0]; other shapes return B2N_E_UNSUPPORTED and take b2n_fft_forward_fused +
+ * b2n_fft_adjoint_fused (kernel_dev set).  kernel_dev: (kernel_batch, *grid_size), kernel_batch 1 or n_batch;
+ * work_dev: b2n_fft_work_bytes.  reference: the per-batch loop of ToepNufft.forward (modules/kbnufft.py:441-484)
+ * around fft_filter (_nufft/fft.py:121-173). */
+B2N_API int b2n_fft_toeplitz_fused(int ndim, const int64_t *im_size, const int64_t *grid_size, int64_t n_batch,
+                                   int64_t n_coils, const void *image_dev, int64_t image_coils,
+                                   const void *smaps_dev, int64_t smaps_batch, const void *kernel_dev,
+                                   int64_t kernel_batch, double scale, const void *const *twiddle_dev, void *out_dev,
+                                   void *work_dev, void *stream);
 
 #ifdef __cplusplus
 }

@@ -506,6 +506,77 @@ def test_fused_pruned_fft_matches_torch(N, K):
     assert all(eng_fft.fused_fft_available(dt, (n,)) for n in (64, 96, 128, 192, 224, 256, 288, 320, 384, 448, 480, 512, 576, 640, 768, 896, 960, 1024, 1280, 2048))
 
 
+@pytest.mark.parametrize("N, K", [((32, 32), (64, 64)), ((48, 30), (96, 60)), ((64, 100), (128, 200)),
+                                  ((90, 18), (192, 36)), ((112, 64), (224, 128)), ((128, 128), (256, 256)),
+                                  ((144, 33), (288, 66)), ((160, 160), (320, 320)), ((192, 50), (384, 100)),
+                                  ((224, 21), (448, 42)), ((240, 64), (480, 128)), ((256, 256), (512, 512)),
+                                  ((288, 40), (576, 80)), ((320, 320), (640, 640)), ((384, 384), (768, 768)),
+                                  ((448, 20), (896, 40)), ((480, 12), (960, 24)), ((512, 30), (1024, 60)),
+                                  ((640, 16), (1280, 32)), ((100, 150), (256, 320)), ((31, 37), (64, 96))])
+def test_toeplitz_three_pass_matches_torch_fft(N, K):
+    """b2n_fft_toeplitz_fused (forward rows, one column pass that transforms / filters / transforms back, inverse
+    rows + coil sum) against torch.fft and against the route through the full spectrum; every planned column
+    length, batched and shared kernels and smaps, with and without smaps."""
+    torch.manual_seed(3)
+    dt = torch.complex64
+    assert eng_fft.toeplitz_fused_available(dt, N, K)
+    pad = [0, K[1] - N[1], 0, K[0] - N[0]]
+    crop = (slice(None), slice(None), slice(0, N[0]), slice(0, N[1]))
+    for B, C in ((1, 1), (2, 3), (1, 16)):
+        image = torch.randn((B, 1) + N, dtype=dt, device=DEV)
+        for smaps in (torch.randn((1, C) + N, dtype=dt, device=DEV), torch.randn((B, C) + N, dtype=dt, device=DEV)):
+            for kern in (torch.randn(K, dtype=dt, device=DEV), torch.randn((B,) + K, dtype=dt, device=DEV)):
+                kb = kern if kern.ndim == 2 else kern.unsqueeze(1)
+                spec = torch.fft.fft2(torch.nn.functional.pad(image * smaps, pad)) * kb
+                want = torch.sum(torch.fft.ifft2(spec, norm="forward")[crop] * smaps.conj(), 1, keepdim=True) * 0.5
+                got = eng_fft.fused_toeplitz(image, kern, smaps, 0.5)
+                assert rel_l2(host(got), host(want)) <= 2e-6
+                two = eng_fft.fused_fft_adjoint(eng_fft.fused_fft_forward(image, K, smaps, None, 1.0), N, smaps, None,
+                                                0.5, kernel=kern)
+                assert rel_l2(host(got), host(two)) <= 1e-6
+        multi = torch.randn((B, C) + N, dtype=dt, device=DEV)
+        kern = torch.randn(K, dtype=dt, device=DEV)
+        want = torch.fft.ifft2(torch.fft.fft2(torch.nn.functional.pad(multi, pad)) * kern, norm="forward")[crop]
+        assert rel_l2(host(eng_fft.fused_toeplitz(multi, kern, None, 1.0)), host(want)) <= 2e-6
+
+
+def test_toeplitz_three_pass_dispatch_and_fallbacks():
+    """ToepNufft takes the three-pass route where it applies and the route through the full spectrum elsewhere
+    (3-D, unplanned or too long column lengths, grids under twice the image); both agree; the C entry refuses what
+    it cannot do with B2N_E_UNSUPPORTED."""
+    from torchkbnufft_b200._autograd import nufft as auto_nufft
+    torch.manual_seed(4)
+    dt = torch.complex64
+    assert not eng_fft.toeplitz_fused_available(dt, (8, 8, 8), (16, 16, 16))
+    assert not eng_fft.toeplitz_fused_available(dt, (1024, 8), (2048, 16))   # spectrum + exchange buffer > 227 KB
+    assert not eng_fft.toeplitz_fused_available(dt, (30, 30), (60, 60))      # run-time column length
+    assert not eng_fft.toeplitz_fused_available(dt, (40, 32), (64, 64))      # grid < 2 x image
+    assert not eng_fft.toeplitz_fused_available(torch.complex128, (32, 32), (64, 64))
+    image = torch.randn((1, 1, 40, 32), dtype=dt, device=DEV)
+    kern = torch.randn((64, 64), dtype=dt, device=DEV)
+    with pytest.raises(RuntimeError, match="Toeplitz"):
+        eng_fft.fused_toeplitz(image, kern, None, 1.0)
+    toep = tkbn.ToepNufft()
+    im_size = (96, 160)
+    om = torch.rand((2, 3000), device=DEV) * 2 * np.pi - np.pi
+    kern = tkbn.calc_toeplitz_kernel(om, im_size)
+    x = torch.randn((2, 1) + im_size, dtype=dt, device=DEV, requires_grad=True)
+    s = torch.randn((1, 16) + im_size, dtype=dt, device=DEV)
+    res = {}
+    try:
+        for fuse in (True, False):
+            auto_nufft.fuse_toeplitz_columns = fuse
+            before = _lib.load().b2n_launch_count()
+            y = toep(x, kern, smaps=s)
+            res[fuse] = (host(y), _lib.load().b2n_launch_count() - before)
+            (g,) = torch.autograd.grad(y.abs().pow(2).sum(), x)
+            res[fuse] += (host(g),)
+    finally:
+        auto_nufft.fuse_toeplitz_columns = True
+    assert res[True][1] == 3 and res[False][1] == 4  # kernels of the library per apply
+    assert rel_l2(res[True][0], res[False][0]) <= 1e-6 and rel_l2(res[True][2], res[False][2]) <= 1e-6
+
+
 def test_fast_fft_plans_agree_with_runtime_passes():
     """B2N_OPT_FAST_FFT on/off must give the same transform (different kernels, same maths)."""
     torch.manual_seed(2)

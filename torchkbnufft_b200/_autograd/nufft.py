@@ -88,6 +88,9 @@ class FusedFftAdjoint(Function):
         return grad, None, None, None, None
 
 
+fuse_toeplitz_columns = True  # False: forward passes + inverse passes through the full spectrum (A/B, tests)
+
+
 def toeplitz_apply(image, kernel, smaps, normalized: bool):
     """``sum_c conj(S_c) crop(IFFT(kernel * FFT(pad(S_c * image))))`` for the whole
     batch at once (the reference loops over the batch in Python,
@@ -98,6 +101,10 @@ def toeplitz_apply(image, kernel, smaps, normalized: bool):
     for k in grid_size:
         n_grid *= k
     n_rows = image.shape[0] * (smaps.shape[1] if smaps is not None else image.shape[1])
+    if (fuse_toeplitz_columns and _fft.fused_fft_available(image.dtype, grid_size, n_rows)
+            and _fft.toeplitz_fused_available(image.dtype, image.shape[2:], grid_size)):
+        # three passes: the column pass transforms, filters and transforms back inside the CTA
+        return _fft.fused_toeplitz(image, kernel, smaps, (1.0 / n_grid) if normalized else 1.0)
     if ndim > 1 and _fft.fused_fft_available(image.dtype, grid_size, n_rows):
         # pruned passes both ways, kernel multiply fused into the first inverse pass
         grid = _fft.fused_fft_forward(image, grid_size, smaps, None, 1.0)

@@ -112,6 +112,8 @@ SIGNATURES = {
                                       c_void_p, c_double, POINTER(c_void_p), c_void_p, c_void_p, c_void_p]),
     "b2n_fft_adjoint_fused": (c_int, [c_int, _I64P, _I64P, c_int64, c_int64, c_void_p, c_void_p, c_int64, c_void_p,
                                       c_int64, c_void_p, c_double, POINTER(c_void_p), c_void_p, c_void_p, c_void_p]),
+    "b2n_fft_toeplitz_fused": (c_int, [c_int, _I64P, _I64P, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_int64,
+                                       c_void_p, c_int64, c_double, POINTER(c_void_p), c_void_p, c_void_p, c_void_p]),
 }
 
 _lib: Optional[ctypes.CDLL] = None

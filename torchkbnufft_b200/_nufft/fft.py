@@ -312,3 +312,46 @@ def fused_fft_adjoint(grid: Tensor, im_size: Sequence[int], smaps: Optional[Tens
             "b2n_fft_adjoint_fused",
         )
     return out
+
+
+def toeplitz_fused_available(dtype: torch.dtype, im_size: Sequence[int], grid_size: Sequence[int]) -> bool:
+    """True when ``b2n_fft_toeplitz_fused`` takes the shape: 2-D complex64, compile-time planned column length,
+    grid at least twice the image along the slow dimension (what ``calc_toeplitz_kernel`` produces)."""
+    if use_fused_fft is False or dtype != torch.complex64 or len(grid_size) != 2:
+        return False
+    k0, k1 = int(grid_size[0]), int(grid_size[1])
+    if 2 * int(im_size[0]) > k0 or k1 % 2 or 4 * 16 * (2 * k0 + k0 // 8 + 1) > 227 * 1024:
+        return False
+    lib = _lib.load()
+    return lib.b2n_fft_supported(k0) == 2 and lib.b2n_fft_supported(k1) > 0
+
+
+def fused_toeplitz(image: Tensor, kernel: Tensor, smaps: Optional[Tensor] = None, scale: float = 1.0) -> Tensor:
+    """``scale * sum_c conj(S_c) crop(ifft2(kernel * fft2(zero_pad(S_c * image))))`` (unnormalised transforms) in
+    three passes; the column pass transforms, filters and transforms back without writing the spectrum.
+    Returns ``(B, 1, *N)`` with smaps, ``(B, C, *N)`` without."""
+    require_cuda(image, "image")
+    image = image.contiguous()
+    kernel = kernel.contiguous()
+    B, Ci = image.shape[:2]
+    im_size = list(image.shape[2:])
+    grid_size = list(kernel.shape[-2:])
+    kb = kernel.shape[0] if kernel.ndim > 2 else 1
+    Bs, C = 1, Ci
+    if smaps is not None:
+        smaps = smaps.contiguous()
+        C, Bs = smaps.shape[1], smaps.shape[0]
+    out = torch.empty([B, 1 if smaps is not None else C] + im_size, dtype=image.dtype, device=image.device)
+    if out.numel() == 0:
+        return out
+    n_arr, k_arr, tw, nwork, _tabs = _fft_ctx(im_size, grid_size, B, C, image.device)
+    work = torch.empty(nwork, dtype=torch.uint8, device=image.device)
+    with device_guard(image.device):
+        _lib.check(
+            _lib.load().b2n_fft_toeplitz_fused(
+                2, n_arr, k_arr, B, C, image.data_ptr(), Ci, smaps.data_ptr() if smaps is not None else None, Bs,
+                kernel.data_ptr(), kb, float(scale), tw, out.data_ptr(), work.data_ptr(),
+                current_stream_ptr(image.device)),
+            "b2n_fft_toeplitz_fused",
+        )
+    return out

@@ -298,6 +298,7 @@ int g_fast_fft = 1;  // B2N_OPT_FAST_FFT: compile-time planned passes where a pl
   int fast_rows_fwd_##N(RowArgs &a, cudaStream_t st);                \
   int fast_rows_inv_##N(RowArgs &a, cudaStream_t st);                \
   int fast_cols_##N(bool inverse, ColArgs &a, cudaStream_t st);      \
+  int fast_cols_toep_##N(ColArgs &a, cudaStream_t st);               \
   int fast_rows_sense_##N(RowArgs &a, int64_t B, cudaStream_t st);
 B2N_FAST_PLANS(B2N_DECLARE_PLAN_X, 0)
 
@@ -305,6 +306,7 @@ B2N_FAST_PLANS(B2N_DECLARE_PLAN_X, 0)
 #define B2N_CASE_ROWS_INV(N, R0, R1, R2, ...) case N: return fast_rows_inv_##N(a, st);
 #define B2N_CASE_COLS(N, R0, R1, R2, ...) case N: return fast_cols_##N(inverse, a, st);
 #define B2N_CASE_SENSE(N, R0, R1, R2, ...) case N: return fast_rows_sense_##N(a, B, st);
+#define B2N_CASE_TOEP(N, R0, R1, R2, ...) case N: return fast_cols_toep_##N(a, st);
 
 // each returns -1 when the length has no compile-time plan (the caller takes the run-time / unfused route)
 static int fast_rows(bool inverse, RowArgs &a, cudaStream_t st) {
@@ -319,6 +321,11 @@ static int fast_rows(bool inverse, RowArgs &a, cudaStream_t st) {
 static int fast_cols(bool inverse, ColArgs &a, cudaStream_t st) {
   if (!g_fast_fft) return -1;
   switch (a.st.n) { B2N_FAST_PLANS(B2N_CASE_COLS, 0) default: break; }
+  return -1;
+}
+static int fast_cols_toep(ColArgs &a, cudaStream_t st) {
+  if (!g_fast_fft) return -1;
+  switch (a.st.n) { B2N_FAST_PLANS(B2N_CASE_TOEP, 0) default: break; }
   return -1;
 }
 static int launch_rows_sense(RowArgs &a, int64_t B, cudaStream_t st) {
@@ -477,6 +484,104 @@ int crop_apod_coilsum_c64(int ndim, const int64_t *im_size, const int64_t *grid_
                           const void *grid, const void *smaps, int64_t Bs, const void *scaling, double scale,
                           void *image, cudaStream_t st);  // b2n_fftops.cu
 
+// last pass of the adjoint: inverse transform of the contiguous dimension of rows_in [B*C][N0..N_{d-2}][K_last],
+// crop, * conj(scaling) * scale, and the SENSE coil combination when smaps is given
+static int adjoint_rows(const FusedGeom &g, const float2 *rows_in, const float2 *smaps, int64_t Bs,
+                        const float2 *scaling, float scale, float2 *image, float2 *T3, size_t t3e, cudaStream_t st) {
+  const int d = g.ndim;
+  RowArgs r;
+  memset(&r, 0, sizeof(r));
+  r.st = g.st[d - 1];
+  r.tw = g.tw[d - 1];
+  r.n_in = (int)g.K[d - 1];
+  r.n_out = (int)g.N[d - 1];
+  r.rows_per_img = 1;
+  for (int k = 0; k < d - 1; ++k) r.rows_per_img *= g.N[k];
+  r.lines = g.B * g.C * r.rows_per_img;
+  r.C = (int)g.C;
+  r.in = rows_in;
+  if (!smaps) {  // no coil combination: crop * conj(scaling) * scale straight to the caller's image
+    r.out = image;
+    r.scaling = scaling;
+    r.scale = scale;
+    return launch_rows<true, ROW_PLAIN>(r, st);
+  }
+  // SENSE, compile-time planned length: coil combination fused into the row pass (T3 holds the partial rows)
+  r.out = image;
+  r.smaps = smaps;
+  r.Bs = (int)Bs;
+  r.scaling = scaling;
+  r.scale = scale;
+  r.partial = T3;
+  r.counter = reinterpret_cast<unsigned int *>(T3 + t3e);
+  {
+    const int rc = launch_rows_sense(r, g.B, st);
+    if (rc >= 0) return rc;
+  }
+  // otherwise: cropped per-coil rows to scratch, then one pass multiplies conj(smaps) * conj(scaling)
+  // and sums the coils (every line of the row pass stays independent: full parallelism)
+  r.smaps = nullptr;
+  r.scaling = nullptr;
+  r.out = T3;
+  r.scale = 1.f;
+  int rc = launch_rows<true, ROW_PLAIN>(r, st);
+  if (rc) return rc;
+  return crop_apod_coilsum_c64(d, g.N, g.N, g.B, g.C, T3, smaps, Bs, scaling, scale, image, st);
+}
+
+// Toeplitz normal operator in three passes (2-D, compile-time planned column length, grid >= 2 x image):
+//   rows: image * smaps -> FFT_x (pruned inputs)                         -> T1 [B*C][N0][K1]
+//   cols: FFT_y (pruned inputs) * kernel -> IFFT_y (cropped outputs), in place on T1 (k_fft_cols_toep)
+//   rows: IFFT_x (cropped outputs) * conj(smaps), coil sum               -> image
+// Returns -1 when the shape does not qualify (the caller runs fused_forward + fused_adjoint instead).
+static int fused_toeplitz(const FusedGeom &g, const float2 *image, int64_t Ci, const float2 *smaps, int64_t Bs,
+                          const float2 *kernel, int64_t kernel_batch, float scale, float2 *out, float2 *work,
+                          cudaStream_t st) {
+  if (g.ndim != 2 || !g_fast_fft || 2 * g.N[0] > g.K[0] || g.K[1] % 2) return -1;
+  if (b2n_fft_supported(g.K[0]) != 2) return -1;
+  size_t t1e, t2e, t3e;
+  fused_work_layout(g, &t1e, &t2e, &t3e);
+  float2 *T1 = work, *T3 = work + t1e + t2e;
+  if (!aligned16(T1) || !aligned16(kernel)) return -1;
+  ColArgs c;
+  memset(&c, 0, sizeof(c));
+  c.st = g.st_col[0];
+  c.tw = g.tw[0];
+  c.n_in = (int)g.N[0];
+  c.n_out = (int)g.N[0];
+  c.A = g.B * g.C;
+  c.X = g.K[1];
+  c.in = T1;
+  c.out = T1;
+  c.mul = kernel;
+  c.a_per_mul = kernel_batch > 1 ? g.C : 0;
+  c.scale = 1.f;
+  {  // probe the column kernel's limits (shared memory) before anything is launched
+    const size_t need = sizeof(float4) * 4 * (size_t)(2 * g.K[0] + (g.K[0] >> 3) + 1);
+    if (need > kSmemLimit) return -1;
+  }
+  RowArgs r;
+  memset(&r, 0, sizeof(r));
+  r.st = g.st[1];
+  r.tw = g.tw[1];
+  r.n_in = (int)g.N[1];
+  r.n_out = (int)g.K[1];
+  r.rows_per_img = g.N[0];
+  r.lines = g.B * g.C * r.rows_per_img;
+  r.C = (int)g.C;
+  r.Ci = (int)Ci;
+  r.Bs = (int)Bs;
+  r.image = image;
+  r.smaps = smaps;
+  r.scale = 1.f;
+  r.out = T1;
+  int rc = launch_rows<false, ROW_FWD_FIRST>(r, st);
+  if (rc) return rc;
+  rc = fast_cols_toep(c, st);
+  if (rc) return rc < 0 ? fail_arg(B2N_E_UNSUPPORTED, "Toeplitz column pass refused length %d", c.st.n) : rc;
+  return adjoint_rows(g, T1, smaps, Bs, nullptr, scale, out, T3, t3e, st);
+}
+
 // kernel (optional): Toeplitz factor multiplied into the loads of the first inverse pass
 static int fused_adjoint(const FusedGeom &g, const float2 *grid, const float2 *kernel, int64_t kernel_batch,
                          const float2 *smaps, int64_t Bs, const float2 *scaling, float scale, float2 *image,
@@ -531,44 +636,7 @@ static int fused_adjoint(const FusedGeom &g, const float2 *grid, const float2 *k
   } else if (kernel) {
     return fail_arg(B2N_E_UNSUPPORTED, "1-D Toeplitz filtering goes through the unfused path");
   }
-  RowArgs r;
-  memset(&r, 0, sizeof(r));
-  r.st = g.st[d - 1];
-  r.tw = g.tw[d - 1];
-  r.n_in = (int)g.K[d - 1];
-  r.n_out = (int)g.N[d - 1];
-  r.rows_per_img = 1;
-  for (int k = 0; k < d - 1; ++k) r.rows_per_img *= g.N[k];
-  r.lines = g.B * g.C * r.rows_per_img;
-  r.C = (int)g.C;
-  r.in = rows_in;
-  if (!smaps) {  // no coil combination: crop * conj(scaling) * scale straight to the caller's image
-    r.out = image;
-    r.scaling = scaling;
-    r.scale = scale;
-    return launch_rows<true, ROW_PLAIN>(r, st);
-  }
-  // SENSE, compile-time planned length: coil combination fused into the row pass (T3 holds the partial rows)
-  r.out = image;
-  r.smaps = smaps;
-  r.Bs = (int)Bs;
-  r.scaling = scaling;
-  r.scale = scale;
-  r.partial = T3;
-  r.counter = reinterpret_cast<unsigned int *>(T3 + t3e);
-  {
-    const int rc = launch_rows_sense(r, g.B, st);
-    if (rc >= 0) return rc;
-  }
-  // otherwise: cropped per-coil rows to scratch, then one pass multiplies conj(smaps) * conj(scaling)
-  // and sums the coils (every line of the row pass stays independent: full parallelism)
-  r.smaps = nullptr;
-  r.scaling = nullptr;
-  r.out = T3;
-  r.scale = 1.f;
-  int rc = launch_rows<true, ROW_PLAIN>(r, st);
-  if (rc) return rc;
-  return crop_apod_coilsum_c64(d, g.N, g.N, g.B, g.C, T3, smaps, Bs, scaling, scale, image, st);
+  return adjoint_rows(g, rows_in, smaps, Bs, scaling, scale, image, T3, t3e, st);
 }
 
 }  // namespace b2n
@@ -621,6 +689,28 @@ extern "C" int b2n_fft_forward_fused(int ndim, const int64_t *im_size, const int
   return fused_forward(g, (const float2 *)image_dev, image_coils, (const float2 *)smaps_dev, smaps_dev ? smaps_batch : 1,
                        (const float2 *)scaling_dev, (float)scale, (float2 *)grid_dev, (float2 *)work_dev,
                        (cudaStream_t)stream);
+}
+
+extern "C" int b2n_fft_toeplitz_fused(int ndim, const int64_t *im_size, const int64_t *grid_size, int64_t n_batch,
+                                      int64_t n_coils, const void *image_dev, int64_t image_coils,
+                                      const void *smaps_dev, int64_t smaps_batch, const void *kernel_dev,
+                                      int64_t kernel_batch, double scale, const void *const *twiddle_dev,
+                                      void *out_dev, void *work_dev, void *stream) {
+  FusedGeom g;
+  if (!twiddle_dev) return fail_arg(B2N_E_ARG, "twiddle_dev is NULL");
+  int rc = make_fused_geom(ndim, im_size, grid_size, n_batch, n_coils, twiddle_dev, &g);
+  if (rc) return rc;
+  if (!image_dev || !kernel_dev || !out_dev || !work_dev) return fail_arg(B2N_E_ARG, "NULL image/kernel/out/work");
+  if (image_coils != 1 && image_coils != n_coils) return fail_arg(B2N_E_ARG, "image_coils must be 1 or n_coils");
+  if (smaps_dev && smaps_batch != 1 && smaps_batch != n_batch) return fail_arg(B2N_E_ARG, "smaps_batch must be 1 or n_batch");
+  if (kernel_batch != 1 && kernel_batch != n_batch) return fail_arg(B2N_E_ARG, "kernel_batch must be 1 or n_batch");
+  rc = fused_toeplitz(g, (const float2 *)image_dev, image_coils, (const float2 *)smaps_dev, smaps_dev ? smaps_batch : 1,
+                      (const float2 *)kernel_dev, kernel_batch, (float)scale, (float2 *)out_dev, (float2 *)work_dev,
+                      (cudaStream_t)stream);
+  if (rc < 0)
+    return fail_arg(B2N_E_UNSUPPORTED, "no three-pass Toeplitz route for this shape (2-D, planned column length, "
+                                       "grid >= 2 x image): use b2n_fft_forward_fused + b2n_fft_adjoint_fused");
+  return rc;
 }
 
 extern "C" int b2n_fft_adjoint_fused(int ndim, const int64_t *im_size, const int64_t *grid_size, int64_t n_batch,

@@ -130,6 +130,42 @@ __global__ void __launch_bounds__(FastCfg<P>::COL_THREADS, FastCfg<P>::COL_MINB)
   fast::fft_line_pair<P, INV, HALF && !INV, HALF && INV>(t, fsm4 + p, PAIRS, a.tw + P::N, loadg, storeg);
 }
 
+// Toeplitz column pass: forward transform of the columns, multiply by the kernel spectrum, inverse transform, all
+// inside the CTA -- the full spectrum [A][N][X] never exists in global memory.  In and out are the half-height
+// arrays [A][n_in][X] / [A][n_out][X] (n_in, n_out <= N/2: the Toeplitz grid is twice the image), and may be the
+// same buffer: a CTA reads all of its columns before it writes any of them.
+template <class P>
+__global__ void __launch_bounds__(FastCfg<P>::COL_THREADS, FastCfg<P>::COL_MINB) k_fft_cols_toep(ColArgs a) {
+  extern __shared__ __align__(16) float4 fsm4[];
+  griddep_launch();
+  griddep_wait();  // the input rows come from the preceding pass
+  constexpr int PAIRS = FastCfg<P>::PAIRS;
+  const int p = threadIdx.x % PAIRS, t = threadIdx.x / PAIRS;
+  const int X = (int)a.X, X2 = X >> 1, n_in = a.n_in, n_out = a.n_out;
+  const int64_t oa = (int64_t)blockIdx.z * gridDim.y + blockIdx.y;
+  const int x = ((int)blockIdx.x * PAIRS + p) * 2;
+  const bool on = x < X && oa < a.A;
+  const float4 *in = reinterpret_cast<const float4 *>(a.in + oa * n_in * a.X + x);
+  float4 *out = reinterpret_cast<float4 *>(a.out + oa * n_out * a.X + x);
+  const float4 *mul =
+      reinterpret_cast<const float4 *>(a.mul + (a.a_per_mul ? (oa / a.a_per_mul) * (int64_t)P::N * a.X : 0) + x);
+  const float scale = a.scale;
+  float4 *spec = fsm4 + PAIRS * P::NP;  // the filtered spectrum of this CTA's columns, natural order [N][PAIRS]
+  auto load_in = [&](int i) -> float4 {
+    return (!on || i >= n_in) ? fast::v4(0.f, 0.f, 0.f, 0.f) : in[i * X2];
+  };
+  auto store_spec = [&](int i, float4 v) {
+    spec[i * PAIRS + p] = on ? fast::vmul2(v, mul[i * X2]) : fast::v4(0.f, 0.f, 0.f, 0.f);
+  };
+  fast::fft_line_pair<P, false, true, false>(t, fsm4 + p, PAIRS, a.tw + P::N, load_in, store_spec);
+  __syncthreads();  // spectrum complete; the exchange buffer is free again
+  auto load_spec = [&](int i) -> float4 { return spec[i * PAIRS + p]; };
+  auto store_out = [&](int i, float4 v) {
+    if (on && i < n_out) out[i * X2] = fast::vscale(v, scale);
+  };
+  fast::fft_line_pair<P, true, false, true>(t, fsm4 + p, PAIRS, a.tw + P::N, load_spec, store_out);
+}
+
 // Inverse row pass + SENSE coil combination (the last pass of the SENSE adjoint):
 //   image[b, row, :] = scale * conj(scaling[row, :]) * sum_c conj(smaps[b, c, row, :]) * IFFT_x(in[b, c, row, :])[:n_out]
 // CTA = one image row x 2*LP coils.  The LP pair sums meet in shared memory; when the coils span several
@@ -244,6 +280,20 @@ template <class P, bool HALF> int launch_rows_sense_h(RowArgs &a, int64_t B, cud
   return 0;
 }
 
+template <class P> int launch_cols_toep(ColArgs &a, cudaStream_t st) {
+  using Cfg = FastCfg<P>;
+  if (2 * a.n_in > P::N || 2 * a.n_out > P::N) return -1;
+  const size_t smem = sizeof(float4) * (size_t)Cfg::PAIRS * (P::NP + P::N);
+  if (smem > (size_t)227 * 1024) return -1;  // spectrum + exchange buffer must fit one CTA
+  auto kern = k_fft_cols_toep<P>;
+  B2N_SMEM_OPT_IN(kern, smem);
+  const int64_t gy = a.A < 32768 ? a.A : 32768;
+  const dim3 grid((unsigned)ceil_div(a.X, 2 * Cfg::PAIRS), (unsigned)gy, (unsigned)ceil_div(a.A, gy));
+  B2N_CUDA_OK(launch_pdl(kern, grid, dim3(Cfg::COL_THREADS), smem, st, a));
+  B2N_LAUNCH_OK("k_fft_cols_toep");
+  return 0;
+}
+
 template <class P> int launch_rows_sense_any(RowArgs &a, int64_t B, cudaStream_t st) {
   // a CTA carries FastCfg<P>::LPS coil pairs of one image row: with fewer coils than half of that most of its threads
   // would idle through the barriers (short lines, few coils: 256^3 x 8 coils) -- take the unfused route instead
@@ -256,6 +306,7 @@ template <class P> int launch_rows_sense_any(RowArgs &a, int64_t B, cudaStream_t
   int fast_rows_fwd_##N(RowArgs &a, cudaStream_t st);                              \
   int fast_rows_inv_##N(RowArgs &a, cudaStream_t st);                              \
   int fast_cols_##N(bool inverse, ColArgs &a, cudaStream_t st);                    \
+  int fast_cols_toep_##N(ColArgs &a, cudaStream_t st);                             \
   int fast_rows_sense_##N(RowArgs &a, int64_t B, cudaStream_t st);
 
 #define B2N_DEFINE_PLAN(N)                                                                                  \
@@ -266,6 +317,7 @@ template <class P> int launch_rows_sense_any(RowArgs &a, int64_t B, cudaStream_t
   int fast_cols_##N(bool inverse, ColArgs &a, cudaStream_t st) {                                            \
     return inverse ? launch_cols_fast<fast::Plan##N, true>(a, st) : launch_cols_fast<fast::Plan##N, false>(a, st); \
   }                                                                                                         \
+  int fast_cols_toep_##N(ColArgs &a, cudaStream_t st) { return launch_cols_toep<fast::Plan##N>(a, st); }    \
   int fast_rows_sense_##N(RowArgs &a, int64_t B, cudaStream_t st) {                                         \
     return launch_rows_sense_any<fast::Plan##N>(a, B, st);                                                  \
   }
