@@ -577,6 +577,36 @@ def test_toeplitz_three_pass_dispatch_and_fallbacks():
     assert rel_l2(res[True][0], res[False][0]) <= 1e-6 and rel_l2(res[True][2], res[False][2]) <= 1e-6
 
 
+@pytest.mark.parametrize("N, K, C", [((320, 320), (640, 640), 16), ((200, 511), (448, 1024), 16),
+                                     ((200, 510), (448, 1024), 16), ((31, 29), (64, 64), 3)])
+def test_fft_prefetch_and_pdl_options_do_not_change_results(N, K, C):
+    """B2N_OPT_FFT_PREFETCH (next-wave L2 prefetch; odd row lengths skip the bulk form) and B2N_OPT_PDL only move
+    memory traffic and launch timing: outputs are bit-identical with them on and off, over several waves of CTAs."""
+    torch.manual_seed(5)
+    dt = torch.complex64
+    lib = _lib.load()
+    image = torch.randn((1, 1) + N, dtype=dt, device=DEV)
+    smaps = torch.randn((1, C) + N, dtype=dt, device=DEV)
+    grid = torch.randn((1, C) + K, dtype=dt, device=DEV)
+    kern = torch.randn(K, dtype=dt, device=DEV)
+    assert lib.b2n_get_option(_lib.OPT_FFT_PREFETCH) == 1 and lib.b2n_get_option(_lib.OPT_PDL) == 1
+    res = []
+    try:
+        for prefetch, pdl in ((0, 0), (2, 1), (1, 1)):
+            lib.b2n_set_option(_lib.OPT_FFT_PREFETCH, prefetch)
+            lib.b2n_set_option(_lib.OPT_PDL, pdl)
+            res.append((host(eng_fft.fused_fft_forward(image, K, smaps, None, 1.0)),
+                        host(eng_fft.fused_fft_adjoint(grid, N, smaps, None, 1.0)),
+                        host(eng_fft.fused_fft_adjoint(grid, N, smaps, None, 1.0, kernel=kern)),
+                        host(eng_fft.fused_toeplitz(image, kern, smaps, 1.0))))
+    finally:
+        lib.b2n_set_option(_lib.OPT_FFT_PREFETCH, 1)
+        lib.b2n_set_option(_lib.OPT_PDL, 1)
+    for other in res[1:]:
+        for a, b in zip(res[0], other):
+            assert np.array_equal(a, b)
+
+
 def test_fast_fft_plans_agree_with_runtime_passes():
     """B2N_OPT_FAST_FFT on/off must give the same transform (different kernels, same maths)."""
     torch.manual_seed(2)

@@ -23,6 +23,7 @@ OPT_FWD_COIL_CHUNK = 2
 OPT_ADJ_COIL_CHUNK = 3
 OPT_FAST_FFT = 4
 OPT_PDL = 5
+OPT_FFT_PREFETCH = 6
 
 _CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")
 LIB_PATH = os.path.join(_CSRC, "libb200nufft.so")

@@ -56,8 +56,14 @@ void count_launch();
 // has completed and its writes are visible.  griddep_launch() in the preceding kernel lets that happen as soon as all
 // of ITS CTAs have been scheduled.  Without the launch attribute both instructions are no-ops.
 extern int g_pdl;
+extern int g_prefetch;
 #ifdef __CUDACC__
 B2N_D void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// L2 prefetch of a 16-byte aligned span (multiple of 16 bytes) / of the cache line holding p
+B2N_D void prefetch_l2_bulk(const void *p, unsigned bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+B2N_D void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 B2N_D void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 template <typename... KArgs, typename... Args>
 static inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,

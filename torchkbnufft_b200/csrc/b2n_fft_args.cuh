@@ -27,6 +27,7 @@ struct RowArgs {
   int coil_groups;
   float2 *partial;
   unsigned int *counter;
+  int prefetch;          // CTAs ahead whose operand rows this CTA pulls into L2 (0: off)
 };
 
 struct ColArgs {
@@ -39,6 +40,7 @@ struct ColArgs {
   int64_t a_per_mul; // outer indices per mul batch entry (0: single kernel)
   const float2 *tw;  // twiddle table of length n
   float scale;
+  int prefetch;      // CTAs ahead whose input columns this CTA pulls into L2 (0: off)
 };
 
 }  // namespace b2n

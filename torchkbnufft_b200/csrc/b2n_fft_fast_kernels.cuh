@@ -66,6 +66,17 @@ __global__ void __launch_bounds__(FastCfg<P>::ROW_THREADS, FastCfg<P>::ROW_MINB)
   if (onB) setup((uint32_t)lA + 1, inB, smB, scB, outB);
   const int n_in = a.n_in, n_out = a.n_out;
   const float scale = a.scale;
+  if (a.prefetch && t < 2) {  // the operand rows of the CTA that takes this one's place in the next wave -> L2
+    const int64_t lF = lA + (int64_t)a.prefetch * LP * 2 + t;
+    if (lF < a.lines) {
+      const float2 *in = nullptr, *sm = nullptr, *sc = nullptr;
+      float2 *out = nullptr;
+      setup((uint32_t)lF, in, sm, sc, out);
+      const unsigned bytes = (unsigned)n_in * 8u;
+      if (!(bytes & 15u) && !(reinterpret_cast<uintptr_t>(in) & 15)) prefetch_l2_bulk(in, bytes);
+      if (sm && !(bytes & 15u) && !(reinterpret_cast<uintptr_t>(sm) & 15)) prefetch_l2_bulk(sm, bytes);
+    }
+  }
   auto loadg = [&](int i) -> float4 {
     float4 v = fast::v4(0.f, 0.f, 0.f, 0.f);
     if (i < n_in) {  // zero padding is never read
@@ -118,6 +129,15 @@ __global__ void __launch_bounds__(FastCfg<P>::COL_THREADS, FastCfg<P>::COL_MINB)
       a.mul ? reinterpret_cast<const float4 *>(a.mul + (a.a_per_mul ? (oa / a.a_per_mul) * (int64_t)P::N * a.X : 0) + x)
             : nullptr;
   const float scale = a.scale;
+  if (a.prefetch) {  // the input columns of the CTA that takes this one's place in the next wave -> L2
+    const int64_t lin = oa * gridDim.x + blockIdx.x + a.prefetch;
+    const int64_t oaF = lin / gridDim.x;
+    const int xF = (int)(lin - oaF * gridDim.x) * PAIRS * 2;
+    if (oaF < a.A) {
+      const float2 *base = a.in + oaF * n_in * a.X + xF;
+      for (int i = threadIdx.x; i < n_in; i += FastCfg<P>::COL_THREADS) prefetch_l2(base + (int64_t)i * X);
+    }
+  }
   auto loadg = [&](int i) -> float4 {
     if (!on || i >= n_in) return fast::v4(0.f, 0.f, 0.f, 0.f);
     float4 v = in[i * X2];
@@ -150,6 +170,15 @@ __global__ void __launch_bounds__(FastCfg<P>::COL_THREADS, FastCfg<P>::COL_MINB)
   const float4 *mul =
       reinterpret_cast<const float4 *>(a.mul + (a.a_per_mul ? (oa / a.a_per_mul) * (int64_t)P::N * a.X : 0) + x);
   const float scale = a.scale;
+  if (a.prefetch) {  // the input columns of the CTA that takes this one's place in the next wave -> L2
+    const int64_t lin = oa * gridDim.x + blockIdx.x + a.prefetch;
+    const int64_t oaF = lin / gridDim.x;
+    const int xF = (int)(lin - oaF * gridDim.x) * PAIRS * 2;
+    if (oaF < a.A) {
+      const float2 *base = a.in + oaF * n_in * a.X + xF;
+      for (int i = threadIdx.x; i < n_in; i += FastCfg<P>::COL_THREADS) prefetch_l2(base + (int64_t)i * X);
+    }
+  }
   float4 *spec = fsm4 + PAIRS * P::NP;  // the filtered spectrum of this CTA's columns, natural order [N][PAIRS]
   auto load_in = [&](int i) -> float4 {
     return (!on || i >= n_in) ? fast::v4(0.f, 0.f, 0.f, 0.f) : in[i * X2];
@@ -191,6 +220,16 @@ __global__ void __launch_bounds__(FastCfg<P>::SENSE_THREADS, FastCfg<P>::SENSE_M
   const float2 *inB = a.in + ((b * C + (onB ? cB : 0u)) * rpi + row) * (uint32_t)n_in;
   const float2 *smA = a.smaps + ((bs * C + (onA ? cA : 0u)) * rpi + row) * (uint32_t)n_out;
   const float2 *smB = a.smaps + ((bs * C + (onB ? cB : 0u)) * rpi + row) * (uint32_t)n_out;
+  if (a.prefetch && t < 2 && blockIdx.x + (unsigned)a.prefetch < gridDim.x) {  // next wave's rows -> L2
+    const uint32_t blkF = blockIdx.x + (uint32_t)a.prefetch, brF = blkF / G, gF = blkF - brF * G;
+    const uint32_t bF = brF / rpi, rowF = brF - bF * rpi, cF = (gF * LP + lp) * 2 + t;
+    if (cF < C) {
+      const float2 *in = a.in + ((bF * C + cF) * rpi + rowF) * (uint32_t)n_in;
+      const float2 *sm = a.smaps + (((a.Bs == 1 ? 0u : bF) * C + cF) * rpi + rowF) * (uint32_t)n_out;
+      if (!(n_in & 1) && !(reinterpret_cast<uintptr_t>(in) & 15)) prefetch_l2_bulk(in, (unsigned)n_in * 8u);
+      if (!(n_out & 1) && !(reinterpret_cast<uintptr_t>(sm) & 15)) prefetch_l2_bulk(sm, (unsigned)n_out * 8u);
+    }
+  }
   auto loadg = [&](int i) -> float4 {
     float4 v = fast::v4(0.f, 0.f, 0.f, 0.f);
     if (i < n_in) {
@@ -237,11 +276,32 @@ __global__ void __launch_bounds__(FastCfg<P>::SENSE_THREADS, FastCfg<P>::SENSE_M
   if (threadIdx.x == 0) a.counter[br] = 0;  // leave the counters zero for the next call
 }
 
+// B2N_OPT_FFT_PREFETCH: 1 = when the pass reads at least 32 MB (it then streams from HBM: -3 % on the 384^2 x 32-coil
+// pair, -5 % on its Toeplitz apply; smaller passes find their input in L2 and the prefetch only costs issue slots:
+// +0.5 % on the 320^2 x 16-coil pair, profiles/r01_h_prefetch_ab.log), 2 = always, 0 = never
+static inline bool want_prefetch(size_t input_bytes) {
+  return g_prefetch == 2 || (g_prefetch == 1 && input_bytes >= ((size_t)32 << 20));
+}
+
+// CTAs of `kern` resident on the whole device at once (one wave), cached per kernel instantiation
+template <class K> static int resident_ctas(K kern, int threads, size_t smem) {
+  static int cached = 0;
+  if (!cached) {
+    int per_sm = 0, dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem);
+    cached = per_sm > 0 && sms > 0 ? per_sm * sms : 1;
+  }
+  return cached;
+}
+
 template <class P, bool INV, int MODE, bool HALF> int launch_rows_fast_h(RowArgs &a, cudaStream_t st) {
   using Cfg = FastCfg<P>;
   const size_t smem = sizeof(float4) * (size_t)Cfg::LP * P::NP;
   auto kern = k_fft_rows_fast<P, INV, MODE, HALF>;
   B2N_SMEM_OPT_IN(kern, smem);
+  a.prefetch = want_prefetch(sizeof(float2) * (size_t)a.lines * a.n_in) ? resident_ctas(kern, Cfg::ROW_THREADS, smem) : 0;
   B2N_CUDA_OK(launch_pdl(kern, dim3((unsigned)ceil_div(a.lines, 2 * Cfg::LP)), dim3(Cfg::ROW_THREADS), smem, st, a));
   B2N_LAUNCH_OK("k_fft_rows_fast");
   return 0;
@@ -256,6 +316,7 @@ template <class P, bool INV, bool HALF> int launch_cols_fast_h(ColArgs &a, cudaS
   const size_t smem = sizeof(float4) * (size_t)Cfg::PAIRS * P::NP;
   auto kern = k_fft_cols_fast<P, INV, HALF>;
   B2N_SMEM_OPT_IN(kern, smem);
+  a.prefetch = want_prefetch(sizeof(float2) * (size_t)a.A * a.n_in * a.X) ? resident_ctas(kern, Cfg::COL_THREADS, smem) : 0;
   const int64_t gy = a.A < 32768 ? a.A : 32768;
   const dim3 grid((unsigned)ceil_div(a.X, 2 * Cfg::PAIRS), (unsigned)gy, (unsigned)ceil_div(a.A, gy));
   B2N_CUDA_OK(launch_pdl(kern, grid, dim3(Cfg::COL_THREADS), smem, st, a));
@@ -274,6 +335,7 @@ template <class P, bool HALF> int launch_rows_sense_h(RowArgs &a, int64_t B, cud
   const size_t smem = sizeof(float4) * (size_t)Cfg::LPS * P::NP + sizeof(float2) * (size_t)Cfg::LPS * a.n_out;
   auto kern = k_fft_rows_sense<P, HALF>;
   B2N_SMEM_OPT_IN(kern, smem);
+  a.prefetch = want_prefetch(sizeof(float2) * (size_t)a.lines * a.n_in) ? resident_ctas(kern, Cfg::SENSE_THREADS, smem) : 0;
   if (a.coil_groups > 1) B2N_CUDA_OK(cudaMemsetAsync(a.counter, 0, sizeof(unsigned int) * (size_t)rows, st));
   B2N_CUDA_OK(launch_pdl(kern, dim3((unsigned)(rows * a.coil_groups)), dim3(Cfg::SENSE_THREADS), smem, st, a));
   B2N_LAUNCH_OK("k_fft_rows_sense");
@@ -287,6 +349,7 @@ template <class P> int launch_cols_toep(ColArgs &a, cudaStream_t st) {
   if (smem > (size_t)227 * 1024) return -1;  // spectrum + exchange buffer must fit one CTA
   auto kern = k_fft_cols_toep<P>;
   B2N_SMEM_OPT_IN(kern, smem);
+  a.prefetch = want_prefetch(sizeof(float2) * (size_t)a.A * a.n_in * a.X) ? resident_ctas(kern, Cfg::COL_THREADS, smem) : 0;
   const int64_t gy = a.A < 32768 ? a.A : 32768;
   const dim3 grid((unsigned)ceil_div(a.X, 2 * Cfg::PAIRS), (unsigned)gy, (unsigned)ceil_div(a.A, gy));
   B2N_CUDA_OK(launch_pdl(kern, grid, dim3(Cfg::COL_THREADS), smem, st, a));
