@@ -119,8 +119,9 @@ enum b2n_option {
                            have a plan (64, 96, 128, 192, 224, 256, 288, 320, 384, 448, 480, 512, 576, 640, 768, 896, 960, 1024, 1280, 2048); 0: run-time passes only */
   B2N_OPT_PDL = 5, /* 1 (default): launch the FFT passes and the gathers with programmatic dependent launch (their
                       prologues overlap the tail of the preceding kernel); 0: plain stream order */
-  B2N_OPT_FFT_PREFETCH = 6, /* every CTA of a planned FFT pass pulls the operand rows of the CTA one wave ahead into L2:
-                               1 (default) for passes that read >= 32 MB, 2 always, 0 never */
+  B2N_OPT_FFT_PREFETCH = 6, /* planned FFT passes whose CTAs pull the operand rows of the CTA one wave ahead into L2, as a
+                               mask: 1 forward rows, 2 forward columns, 4 inverse columns, 8 inverse rows, 16 Toeplitz
+                               columns; a pass must also read >= 32 MB unless 32 is set.  Default 19. */
   B2N_OPT_COUNT
 };
 B2N_API int b2n_set_option(int option, int value);

@@ -38,13 +38,13 @@ for name in sys.argv[1:] or ["cfg2", "cfg1"]:
 
     lib.b2n_set_option(_lib.OPT_FFT_PREFETCH, 0)
     k0, a0 = step()
-    lib.b2n_set_option(_lib.OPT_FFT_PREFETCH, 1)
+    lib.b2n_set_option(_lib.OPT_FFT_PREFETCH, 19)
     k1, a1 = step()
     torch.cuda.synchronize()
     print(name, "fwd identical:", bool(torch.equal(k0, k1)), " adj rel diff:",
           float((a0 - a1).norm() / a0.norm()))
     for rep in range(3):
-        for pdl in (0, 1, 2):
+        for pdl in (0, 3, 15):
             lib.b2n_set_option(_lib.OPT_FFT_PREFETCH, pdl)
             mean, med = timed()
             print(f"{name} rep{rep} prefetch={pdl}: mean {mean:.1f} us  median {med:.1f} us")
@@ -59,7 +59,7 @@ for name in sys.argv[1:] or ["cfg2", "cfg1"]:
     kern = tkbn.calc_toeplitz_kernel(om, wl.im_size, norm="ortho")
     toep = tkbn.ToepNufft()
     for rep in range(2):
-        for pf in (0, 1, 2):
+        for pf in (0, 16, 19, 27, 31):
             lib.b2n_set_option(_lib.OPT_FFT_PREFETCH, pf)
             for _ in range(5):
                 toep(x, kern, smaps=s, norm="ortho")
@@ -75,4 +75,4 @@ for name in sys.argv[1:] or ["cfg2", "cfg1"]:
             torch.cuda.synchronize()
             t = sorted(a.elapsed_time(b) for a, b in zip(st, en))
             print(f"{name} toeplitz apply rep{rep} prefetch={pf}: median {1e3 * t[n // 2]:.1f} us")
-    lib.b2n_set_option(_lib.OPT_FFT_PREFETCH, 1)
+    lib.b2n_set_option(_lib.OPT_FFT_PREFETCH, 19)

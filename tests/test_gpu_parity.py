@@ -589,10 +589,10 @@ def test_fft_prefetch_and_pdl_options_do_not_change_results(N, K, C):
     smaps = torch.randn((1, C) + N, dtype=dt, device=DEV)
     grid = torch.randn((1, C) + K, dtype=dt, device=DEV)
     kern = torch.randn(K, dtype=dt, device=DEV)
-    assert lib.b2n_get_option(_lib.OPT_FFT_PREFETCH) == 1 and lib.b2n_get_option(_lib.OPT_PDL) == 1
+    assert lib.b2n_get_option(_lib.OPT_FFT_PREFETCH) == 19 and lib.b2n_get_option(_lib.OPT_PDL) == 1
     res = []
     try:
-        for prefetch, pdl in ((0, 0), (2, 1), (1, 1)):
+        for prefetch, pdl in ((0, 0), (63, 1), (19, 1)):  # off; every pass at any size; default
             lib.b2n_set_option(_lib.OPT_FFT_PREFETCH, prefetch)
             lib.b2n_set_option(_lib.OPT_PDL, pdl)
             res.append((host(eng_fft.fused_fft_forward(image, K, smaps, None, 1.0)),
@@ -600,7 +600,7 @@ def test_fft_prefetch_and_pdl_options_do_not_change_results(N, K, C):
                         host(eng_fft.fused_fft_adjoint(grid, N, smaps, None, 1.0, kernel=kern)),
                         host(eng_fft.fused_toeplitz(image, kern, smaps, 1.0))))
     finally:
-        lib.b2n_set_option(_lib.OPT_FFT_PREFETCH, 1)
+        lib.b2n_set_option(_lib.OPT_FFT_PREFETCH, 19)
         lib.b2n_set_option(_lib.OPT_PDL, 1)
     for other in res[1:]:
         for a, b in zip(res[0], other):

@@ -276,11 +276,15 @@ __global__ void __launch_bounds__(FastCfg<P>::SENSE_THREADS, FastCfg<P>::SENSE_M
   if (threadIdx.x == 0) a.counter[br] = 0;  // leave the counters zero for the next call
 }
 
-// B2N_OPT_FFT_PREFETCH: 1 = when the pass reads at least 32 MB (it then streams from HBM: -3 % on the 384^2 x 32-coil
-// pair, -5 % on its Toeplitz apply; smaller passes find their input in L2 and the prefetch only costs issue slots:
-// +0.5 % on the 320^2 x 16-coil pair, profiles/r01_h_prefetch_ab.log), 2 = always, 0 = never
-static inline bool want_prefetch(size_t input_bytes) {
-  return g_prefetch == 2 || (g_prefetch == 1 && input_bytes >= ((size_t)32 << 20));
+// B2N_OPT_FFT_PREFETCH is a mask over the passes: 1 forward rows, 2 forward columns, 4 inverse columns, 8 inverse rows
+// (+ coil sum), 16 Toeplitz columns; 32 lifts the size threshold.  A pass prefetches when its bit is set and it reads
+// at least 32 MB (it then streams from HBM; smaller passes find their input in L2 and the prefetch only costs issue
+// slots).  Default 19 = forward rows + forward columns + Toeplitz columns: -12 us on the 384^2 x 32-coil forward, -8 us
+// on its Toeplitz apply; on the inverse passes the prefetch is neutral to slightly harmful (+2..6 us), so their bits
+// are off (profiles/r01_h_opts_ab.log).
+enum { PF_ROWS_FWD = 1, PF_COLS_FWD = 2, PF_COLS_INV = 4, PF_ROWS_INV = 8, PF_COLS_TOEP = 16, PF_ANY_SIZE = 32 };
+static inline bool want_prefetch(size_t input_bytes, int pass) {
+  return (g_prefetch & pass) && ((g_prefetch & PF_ANY_SIZE) || input_bytes >= ((size_t)32 << 20));
 }
 
 // CTAs of `kern` resident on the whole device at once (one wave), cached per kernel instantiation
@@ -301,7 +305,7 @@ template <class P, bool INV, int MODE, bool HALF> int launch_rows_fast_h(RowArgs
   const size_t smem = sizeof(float4) * (size_t)Cfg::LP * P::NP;
   auto kern = k_fft_rows_fast<P, INV, MODE, HALF>;
   B2N_SMEM_OPT_IN(kern, smem);
-  a.prefetch = want_prefetch(sizeof(float2) * (size_t)a.lines * a.n_in) ? resident_ctas(kern, Cfg::ROW_THREADS, smem) : 0;
+  a.prefetch = want_prefetch(sizeof(float2) * (size_t)a.lines * a.n_in, INV ? PF_ROWS_INV : PF_ROWS_FWD) ? resident_ctas(kern, Cfg::ROW_THREADS, smem) : 0;
   B2N_CUDA_OK(launch_pdl(kern, dim3((unsigned)ceil_div(a.lines, 2 * Cfg::LP)), dim3(Cfg::ROW_THREADS), smem, st, a));
   B2N_LAUNCH_OK("k_fft_rows_fast");
   return 0;
@@ -316,7 +320,7 @@ template <class P, bool INV, bool HALF> int launch_cols_fast_h(ColArgs &a, cudaS
   const size_t smem = sizeof(float4) * (size_t)Cfg::PAIRS * P::NP;
   auto kern = k_fft_cols_fast<P, INV, HALF>;
   B2N_SMEM_OPT_IN(kern, smem);
-  a.prefetch = want_prefetch(sizeof(float2) * (size_t)a.A * a.n_in * a.X) ? resident_ctas(kern, Cfg::COL_THREADS, smem) : 0;
+  a.prefetch = want_prefetch(sizeof(float2) * (size_t)a.A * a.n_in * a.X, INV ? PF_COLS_INV : PF_COLS_FWD) ? resident_ctas(kern, Cfg::COL_THREADS, smem) : 0;
   const int64_t gy = a.A < 32768 ? a.A : 32768;
   const dim3 grid((unsigned)ceil_div(a.X, 2 * Cfg::PAIRS), (unsigned)gy, (unsigned)ceil_div(a.A, gy));
   B2N_CUDA_OK(launch_pdl(kern, grid, dim3(Cfg::COL_THREADS), smem, st, a));
@@ -335,7 +339,7 @@ template <class P, bool HALF> int launch_rows_sense_h(RowArgs &a, int64_t B, cud
   const size_t smem = sizeof(float4) * (size_t)Cfg::LPS * P::NP + sizeof(float2) * (size_t)Cfg::LPS * a.n_out;
   auto kern = k_fft_rows_sense<P, HALF>;
   B2N_SMEM_OPT_IN(kern, smem);
-  a.prefetch = want_prefetch(sizeof(float2) * (size_t)a.lines * a.n_in) ? resident_ctas(kern, Cfg::SENSE_THREADS, smem) : 0;
+  a.prefetch = want_prefetch(sizeof(float2) * (size_t)a.lines * a.n_in, PF_ROWS_INV) ? resident_ctas(kern, Cfg::SENSE_THREADS, smem) : 0;
   if (a.coil_groups > 1) B2N_CUDA_OK(cudaMemsetAsync(a.counter, 0, sizeof(unsigned int) * (size_t)rows, st));
   B2N_CUDA_OK(launch_pdl(kern, dim3((unsigned)(rows * a.coil_groups)), dim3(Cfg::SENSE_THREADS), smem, st, a));
   B2N_LAUNCH_OK("k_fft_rows_sense");
@@ -349,7 +353,7 @@ template <class P> int launch_cols_toep(ColArgs &a, cudaStream_t st) {
   if (smem > (size_t)227 * 1024) return -1;  // spectrum + exchange buffer must fit one CTA
   auto kern = k_fft_cols_toep<P>;
   B2N_SMEM_OPT_IN(kern, smem);
-  a.prefetch = want_prefetch(sizeof(float2) * (size_t)a.A * a.n_in * a.X) ? resident_ctas(kern, Cfg::COL_THREADS, smem) : 0;
+  a.prefetch = want_prefetch(sizeof(float2) * (size_t)a.A * a.n_in * a.X, PF_COLS_TOEP) ? resident_ctas(kern, Cfg::COL_THREADS, smem) : 0;
   const int64_t gy = a.A < 32768 ? a.A : 32768;
   const dim3 grid((unsigned)ceil_div(a.X, 2 * Cfg::PAIRS), (unsigned)gy, (unsigned)ceil_div(a.A, gy));
   B2N_CUDA_OK(launch_pdl(kern, grid, dim3(Cfg::COL_THREADS), smem, st, a));

@@ -384,8 +384,8 @@ extern int g_fwd_chunk;
 extern int g_adj_chunk;
 extern int g_fast_fft;
 int g_pdl = 1;
-int g_prefetch = 1;
-static int g_options[B2N_OPT_COUNT] = {1, 0, 0, 0, 1, 1, 1};
+int g_prefetch = 19;
+static int g_options[B2N_OPT_COUNT] = {1, 0, 0, 0, 1, 1, 19};
 
 // With very few 2-D (batch, coil) rows most coil lanes of a tiled gather CTA idle while its per-point cost stays the
 // same: the one-thread-per-point kernel (k_fwd_point6_2d) wins up to 3 rows (16 vs 29 us for one row, 30 vs 41 us for

@@ -467,7 +467,8 @@ __global__ void __launch_bounds__(NW * 32) k_adj_tiled_2d(InterpArgs<float> a, c
   float2 *stage0 = tile + planes<CC>() * kPS;           // 2 x STAGE
   int *s_perm = reinterpret_cast<int *>(stage0 + 2 * STAGE);  // 3 x kRound sample indices
   const long long t_start = a.trace ? gtime() : 0;
-  griddep_launch();  // the inverse FFT pass that follows may start its prologue during this kernel's tail
+  // (no griddep_launch() here: letting the inverse column pass move in during this kernel's tail costs 4 us at
+  // 320^2 x 16 coils and 15-30 us at 384^2 x 32, profiles/r01_h_opts_ab.log)
   const SubProblem sp = decode<CC>(a);
   if (!sp.valid) return;
   const int Ky = (int)a.K[0], Kx = (int)a.K[1];
