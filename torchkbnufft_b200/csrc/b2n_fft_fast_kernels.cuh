@@ -287,17 +287,25 @@ static inline bool want_prefetch(size_t input_bytes, int pass) {
   return (g_prefetch & pass) && ((g_prefetch & PF_ANY_SIZE) || input_bytes >= ((size_t)32 << 20));
 }
 
-// CTAs of `kern` resident on the whole device at once (one wave), cached per kernel instantiation
+// CTAs of `kern` resident on the whole device at once (one wave).  Cached per kernel entry point and thread: kernels
+// with the same signature share a function-pointer type, so the key is the pointer, not the type.
 template <class K> static int resident_ctas(K kern, int threads, size_t smem) {
-  static int cached = 0;
-  if (!cached) {
-    int per_sm = 0, dev = 0, sms = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem);
-    cached = per_sm > 0 && sms > 0 ? per_sm * sms : 1;
-  }
-  return cached;
+  struct Entry {
+    const void *kern;
+    int ctas;
+  };
+  static thread_local Entry cache[64];
+  static thread_local int used = 0;
+  const void *key = reinterpret_cast<const void *>(kern);
+  for (int i = 0; i < used; ++i)
+    if (cache[i].kern == key) return cache[i].ctas;
+  int per_sm = 0, dev = 0, sms = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, key, threads, smem);
+  const int ctas = per_sm > 0 && sms > 0 ? per_sm * sms : 1;
+  if (used < 64) cache[used++] = {key, ctas};
+  return ctas;
 }
 
 template <class P, bool INV, int MODE, bool HALF> int launch_rows_fast_h(RowArgs &a, cudaStream_t st) {
