@@ -563,8 +563,8 @@ def main():
             "cpu_baseline": cpu_baseline,
             "e2e": e2e,
             # kernels of libb200nufft.so launched inside the timed region, counted by the library itself
-            # (b2n_launch_count; 6 per step with the own FFT passes: rows, columns, gather / spread, columns,
-            # rows + coil sum; cudaMemsetAsync, the L2-flush fill and cuFFT are not counted)
+            # (b2n_launch_count; 7 per step with the own FFT passes: rows, columns, gather / grid zeroing, spread,
+            # columns, rows + coil sum; cudaMemsetAsync, the L2-flush fill and cuFFT are not counted)
             "gpu_launches": gpu_launches,
             "clocks": clocks,
         }

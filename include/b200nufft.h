@@ -117,8 +117,10 @@ enum b2n_option {
   B2N_OPT_ADJ_COIL_CHUNK = 3, /* 0 (default): 16 coils per CTA in the tiled adjoint; 8: two 8-coil CTAs */
   B2N_OPT_FAST_FFT = 4, /* 1 (default): fused FFT passes use the compile-time planned kernels for the lengths that
                            have a plan (64, 96, 128, 192, 224, 256, 288, 320, 384, 448, 480, 512, 576, 640, 768, 896, 960, 1024, 1280, 2048); 0: run-time passes only */
-  B2N_OPT_PDL = 5, /* 1 (default): launch the FFT passes and the gathers with programmatic dependent launch (their
-                      prologues overlap the tail of the preceding kernel); 0: plain stream order */
+  B2N_OPT_PDL = 5, /* 1 (default): the FFT passes, the gathers and the tiled 2-D spread are launched with programmatic
+                      dependent launch (their prologues overlap the tail of the preceding kernel; the spread's adjoint
+                      grid is zeroed by a kernel it overlaps with); 2: the same but the grid is zeroed by
+                      cudaMemsetAsync; 0: plain stream order */
   B2N_OPT_FFT_PREFETCH = 6, /* planned FFT passes whose CTAs pull the operand rows of the CTA one wave ahead into L2, as a
                                mask: 1 forward rows, 2 forward columns, 4 inverse columns, 8 inverse rows, 16 Toeplitz
                                columns; a pass must also read >= 32 MB unless 32 is set.  Default 19. */

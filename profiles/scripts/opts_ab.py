@@ -30,8 +30,8 @@ for name in sys.argv[1:] or ["cfg3"]:
     na = tkbn.KbNufftAdjoint(im_size=wl.im_size, dtype=torch.complex64).to(dev)
     x, s, y, om = (torch.from_numpy(a).to(dev) for a in (image, smaps, kdata, omega))
     for rep in range(2):
-        for pdl in (1,):
-            for pf in (0, 3, 15, 19):
+        for pdl in (2, 1):
+            for pf in (19,):
                 lib.b2n_set_option(_lib.OPT_PDL, pdl)
                 lib.b2n_set_option(_lib.OPT_FFT_PREFETCH, pf)
                 tf = timed(lambda: nu(x, om, smaps=s))

@@ -385,6 +385,7 @@ extern int g_adj_chunk;
 extern int g_fast_fft;
 int g_pdl = 1;
 int g_prefetch = 19;
+int g_zero_kernel = 1;
 static int g_options[B2N_OPT_COUNT] = {1, 0, 0, 0, 1, 1, 19};
 
 // With very few 2-D (batch, coil) rows most coil lanes of a tiled gather CTA idle while its per-point cost stays the
@@ -409,7 +410,10 @@ extern "C" int b2n_set_option(int option, int value) {
   if (option == B2N_OPT_FWD_COIL_CHUNK) g_fwd_chunk = value;
   if (option == B2N_OPT_ADJ_COIL_CHUNK) g_adj_chunk = value;
   if (option == B2N_OPT_FAST_FFT) g_fast_fft = value;
-  if (option == B2N_OPT_PDL) g_pdl = value;
+  if (option == B2N_OPT_PDL) {
+    g_pdl = value != 0;
+    g_zero_kernel = value != 2;  // 2: dependent launches, but the adjoint grid is zeroed by cudaMemsetAsync (A/B)
+  }
   if (option == B2N_OPT_FFT_PREFETCH) g_prefetch = value;
   return 0;
 }

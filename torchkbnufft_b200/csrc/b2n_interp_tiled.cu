@@ -576,7 +576,9 @@ __global__ void __launch_bounds__(NW * 32) k_adj_tiled_2d(InterpArgs<float> a, c
     for (int e = threadIdx.x; e < ncoil * (kPS / 2); e += NT) dst[e] = src[e];
     return;
   }
-  // merge the tile into the global grid
+  // merge the tile into the global grid.  Under programmatic dependent launch the kernel before this one is
+  // k_zero_grid: everything above overlapped it, the grid itself is first touched here.
+  griddep_wait();
   if (use_tma && sp.interior) {
     fence_async_proxy();  // generic-proxy writes to shared memory -> visible to the TMA engine
     __syncthreads();
@@ -1056,18 +1058,48 @@ static int launch_fwd_persist(const InterpArgs<float> &a, const void *grid, void
   return 0;
 }
 
+// Zeroes the adjoint grid as a kernel so that the spread can be its programmatic dependent: the spread's CTAs stage
+// their samples and accumulate their tiles while this runs, and wait for it only before their write-back.  The wait
+// comes BEFORE the trigger: the spread reads k-space data that the kernel before this one may still be writing, and
+// the grid buffer may be memory that kernel still reads.
+__global__ void __launch_bounds__(256) k_zero_grid(float4 *__restrict__ p, int64_t n4) {
+  griddep_wait();
+  griddep_launch();
+  const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n4; i += (int64_t)gridDim.x * 256) p[i] = z;
+}
+
 template <int CC, int NW = kWarps>
 static int launch_adj(const InterpArgs<float> &a, const void *kdata, void *grid, cudaStream_t st) {
   const size_t smem =
       sizeof(float2) * (planes<CC>() * kPS + 2 * adj_stage_slots<CC>()) + sizeof(int) * 3 * kRound;
   auto kern = k_adj_tiled_2d<CC, NW>;
   B2N_SMEM_OPT_IN(kern, smem);
-  B2N_CUDA_OK(cudaMemsetAsync(grid, 0, sizeof(float2) * (size_t)(a.B * a.C * a.Kprod), st));
+  const int64_t n_cells = a.B * a.C * a.Kprod;
+  // measured (profiles/r01_h_opts_ab.log): -2 us at 52 MB (320^2 x 16 coils), -4 us at 151 MB (384^2 x 32), but +46 us
+  // at 268 MB (8 x 16 x 256^2): k_zero_grid's few CTAs write slower than the memset engine, so large grids keep it
+  const bool overlap = g_pdl >= 1 && g_zero_kernel && n_cells % 2 == 0 && !(reinterpret_cast<uintptr_t>(grid) & 15) &&
+                       n_cells * (int64_t)sizeof(float2) <= ((int64_t)192 << 20);
+  if (overlap) {
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int64_t want = ceil_div(n_cells / 2, (int64_t)256 * 8);
+    const unsigned blocks = (unsigned)(want < (int64_t)sms * 4 ? (want > 0 ? want : 1) : (int64_t)sms * 4);
+    B2N_CUDA_OK(launch_pdl(k_zero_grid, dim3(blocks), dim3(256), 0, st, (float4 *)grid, n_cells / 2));
+    B2N_LAUNCH_OK("k_zero_grid");
+  } else {
+    B2N_CUDA_OK(cudaMemsetAsync(grid, 0, sizeof(float2) * (size_t)n_cells, st));
+  }
   CUtensorMap map;
   memset(&map, 0, sizeof(map));
   const int use_tma = make_grid_tmap(&map, grid, a.B, a.C, a.K[0], a.K[1]) ? 1 : 0;
   dim3 gd((unsigned)a.n_sub_max, (unsigned)ceil_div(a.C, CC), (unsigned)(a.n_traj == 1 ? a.B : 1));
-  kern<<<gd, NW * 32, smem, st>>>(a, (const float2 *)kdata, (float2 *)grid, map, use_tma, (float2 *)nullptr);
+  if (overlap) {
+    B2N_CUDA_OK(launch_pdl(kern, gd, dim3(NW * 32), smem, st, a, (const float2 *)kdata, (float2 *)grid, map, use_tma,
+                           (float2 *)nullptr));
+  } else {
+    kern<<<gd, NW * 32, smem, st>>>(a, (const float2 *)kdata, (float2 *)grid, map, use_tma, (float2 *)nullptr);
+  }
   B2N_LAUNCH_OK("k_adj_tiled_2d");
   return 0;
 }
