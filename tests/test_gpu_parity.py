@@ -577,6 +577,57 @@ def test_toeplitz_three_pass_dispatch_and_fallbacks():
     assert rel_l2(res[True][0], res[False][0]) <= 1e-6 and rel_l2(res[True][2], res[False][2]) <= 1e-6
 
 
+def test_dependent_launches_respect_producers_and_buffer_reuse():
+    """Programmatic dependent launch must not let a kernel of the engine run ahead of the work it depends on: inputs
+    produced by the torch kernel right before the call (k-space for the spread, which starts under the grid zeroing;
+    the image for the first FFT pass), the forward grid's memory reused for the adjoint grid, and inputs that arrive
+    through an event from a copy stream.  Back-to-back unsynchronised calls must equal the synchronised,
+    plain-stream-order results."""
+    torch.manual_seed(6)
+    lib = _lib.load()
+    wl_im, C, M = (160, 160), 16, 40000
+    nu = tkbn.KbNufft(im_size=wl_im, dtype=torch.complex64).to(DEV)
+    na = tkbn.KbNufftAdjoint(im_size=wl_im, dtype=torch.complex64).to(DEV)
+    om = (torch.rand((2, M), device=DEV) * 2 - 1) * np.pi
+    s = torch.randn((1, C) + wl_im, dtype=torch.complex64, device=DEV)
+    x0 = torch.randn((1, 1) + wl_im, dtype=torch.complex64, device=DEV)
+    scales = [0.5 + 0.25 * i for i in range(12)]
+    want = []
+    try:
+        lib.b2n_set_option(_lib.OPT_PDL, 0)
+        for a in scales:
+            torch.cuda.synchronize()
+            k = nu(x0 * a, om, smaps=s)
+            torch.cuda.synchronize()
+            y = na(k * (1.0 + a), om, smaps=s)
+            torch.cuda.synchronize()
+            want.append((host(k), host(y)))
+    finally:
+        lib.b2n_set_option(_lib.OPT_PDL, 1)
+    got = []
+    for a in scales:  # no synchronisation anywhere: every input comes straight out of the preceding torch kernel
+        k = nu(x0 * a, om, smaps=s)
+        y = na(k * (1.0 + a), om, smaps=s)
+        got.append((k, y))
+    for (k, y), (wk, wy) in zip(got, want):
+        assert np.array_equal(host(k), wk)
+        assert rel_l2(host(y), wy) <= 1e-6
+    # inputs uploaded on a copy stream, handed over by an event
+    copy = torch.cuda.Stream()
+    hx = [(x0 * a).cpu().pin_memory() for a in scales]
+    dx = [torch.empty_like(x0) for _ in scales]
+    evs = [torch.cuda.Event() for _ in scales]
+    outs = []
+    for i in range(len(scales)):
+        with torch.cuda.stream(copy):
+            dx[i].copy_(hx[i], non_blocking=True)
+            evs[i].record(copy)
+        torch.cuda.current_stream().wait_event(evs[i])
+        outs.append(nu(dx[i], om, smaps=s))
+    for k, (wk, _) in zip(outs, want):
+        assert np.array_equal(host(k), wk)
+
+
 @pytest.mark.parametrize("N, K, C", [((320, 320), (640, 640), 16), ((200, 511), (448, 1024), 16),
                                      ((200, 510), (448, 1024), 16), ((31, 29), (64, 64), 3)])
 def test_fft_prefetch_and_pdl_options_do_not_change_results(N, K, C):
