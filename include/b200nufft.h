@@ -120,7 +120,8 @@ enum b2n_option {
   B2N_OPT_PDL = 5, /* 1 (default): the FFT passes, the gathers and the tiled 2-D spread are launched with programmatic
                       dependent launch (their prologues overlap the tail of the preceding kernel; the spread's adjoint
                       grid is zeroed by a kernel it overlaps with); 2: the same but the grid is zeroed by
-                      cudaMemsetAsync; 0: plain stream order */
+                      cudaMemsetAsync; 3: the same as 1 but the coil-sum counters are zeroed right before their kernel (A/B);
+                      0: plain stream order */
   B2N_OPT_FFT_PREFETCH = 6, /* planned FFT passes whose CTAs pull the operand rows of the CTA one wave ahead into L2, as a
                                mask: 1 forward rows, 2 forward columns, 4 inverse columns, 8 inverse rows, 16 Toeplitz
                                columns; a pass must also read >= 32 MB unless 32 is set.  Default 19. */

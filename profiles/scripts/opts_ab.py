@@ -29,13 +29,16 @@ for name in sys.argv[1:] or ["cfg3"]:
     nu = tkbn.KbNufft(im_size=wl.im_size, dtype=torch.complex64).to(dev)
     na = tkbn.KbNufftAdjoint(im_size=wl.im_size, dtype=torch.complex64).to(dev)
     x, s, y, om = (torch.from_numpy(a).to(dev) for a in (image, smaps, kdata, omega))
+    kern = tkbn.calc_toeplitz_kernel(om, wl.im_size, norm="ortho")
+    toep = tkbn.ToepNufft()
     for rep in range(2):
-        for pdl in (2, 1):
+        for pdl in (3, 1):
             for pf in (19,):
                 lib.b2n_set_option(_lib.OPT_PDL, pdl)
                 lib.b2n_set_option(_lib.OPT_FFT_PREFETCH, pf)
                 tf = timed(lambda: nu(x, om, smaps=s))
                 ta = timed(lambda: na(y, om, smaps=s))
-                print(f"{name} rep{rep} pdl={pdl} prefetch={pf}: fwd {tf:.1f} us  adj {ta:.1f} us")
+                tt = timed(lambda: toep(x, kern, smaps=s, norm="ortho"))
+                print(f"{name} rep{rep} pdl={pdl} prefetch={pf}: fwd {tf:.1f} us  adj {ta:.1f} us  toeplitz {tt:.1f} us")
     lib.b2n_set_option(_lib.OPT_PDL, 1)
     lib.b2n_set_option(_lib.OPT_FFT_PREFETCH, 19)

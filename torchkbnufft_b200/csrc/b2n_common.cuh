@@ -58,6 +58,7 @@ void count_launch();
 extern int g_pdl;
 extern int g_prefetch;
 extern int g_zero_kernel;
+extern int g_counters_early;
 #ifdef __CUDACC__
 B2N_D void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 // L2 prefetch of a 16-byte aligned span (multiple of 16 bytes) / of the cache line holding p

@@ -292,6 +292,7 @@ static bool runtime_pass_fits(int64_t n) {
 }
 
 int g_fast_fft = 1;  // B2N_OPT_FAST_FFT: compile-time planned passes where a plan exists
+int g_counters_early = 1;  // 0 (B2N_OPT_PDL = 3, for A/B): counters zeroed right before k_fft_rows_sense
 
 // entry points of the compile-time planned passes, defined in b2n_fft_plans_*.cu
 #define B2N_DECLARE_PLAN_X(N, R0, R1, R2, ...)                      \
@@ -484,6 +485,16 @@ int crop_apod_coilsum_c64(int ndim, const int64_t *im_size, const int64_t *grid_
                           const void *grid, const void *smaps, int64_t Bs, const void *scaling, double scale,
                           void *image, cudaStream_t st);  // b2n_fftops.cu
 
+// The arrival counters of k_fft_rows_sense are zeroed at the START of a fused sequence, not right before that kernel:
+// a memset between two kernels would break the programmatic dependent launch of the second one.
+static int zero_sense_counters(const FusedGeom &g, float2 *T3, size_t t3e, cudaStream_t st) {
+  if (!g_counters_early) return 0;
+  size_t rows = (size_t)g.B;
+  for (int d = 0; d < g.ndim - 1; ++d) rows *= g.N[d];
+  B2N_CUDA_OK(cudaMemsetAsync(T3 + t3e, 0, sizeof(unsigned int) * rows, st));
+  return 0;
+}
+
 // last pass of the adjoint: inverse transform of the contiguous dimension of rows_in [B*C][N0..N_{d-2}][K_last],
 // crop, * conj(scaling) * scale, and the SENSE coil combination when smaps is given
 static int adjoint_rows(const FusedGeom &g, const float2 *rows_in, const float2 *smaps, int64_t Bs,
@@ -575,7 +586,9 @@ static int fused_toeplitz(const FusedGeom &g, const float2 *image, int64_t Ci, c
   r.smaps = smaps;
   r.scale = 1.f;
   r.out = T1;
-  int rc = launch_rows<false, ROW_FWD_FIRST>(r, st);
+  int rc = smaps ? zero_sense_counters(g, T3, t3e, st) : 0;
+  if (rc) return rc;
+  rc = launch_rows<false, ROW_FWD_FIRST>(r, st);
   if (rc) return rc;
   rc = fast_cols_toep(c, st);
   if (rc) return rc < 0 ? fail_arg(B2N_E_UNSUPPORTED, "Toeplitz column pass refused length %d", c.st.n) : rc;
@@ -591,6 +604,10 @@ static int fused_adjoint(const FusedGeom &g, const float2 *grid, const float2 *k
   fused_work_layout(g, &t1e, &t2e, &t3e);
   float2 *T1 = work, *T2 = work + t1e, *T3 = work + t1e + t2e;
   const float2 *rows_in = grid;
+  if (smaps) {
+    const int rc = zero_sense_counters(g, T3, t3e, st);
+    if (rc) return rc;
+  }
   ColArgs c;
   memset(&c, 0, sizeof(c));
   c.scale = 1.f;

@@ -348,7 +348,7 @@ template <class P, bool HALF> int launch_rows_sense_h(RowArgs &a, int64_t B, cud
   auto kern = k_fft_rows_sense<P, HALF>;
   B2N_SMEM_OPT_IN(kern, smem);
   a.prefetch = want_prefetch(sizeof(float2) * (size_t)a.lines * a.n_in, PF_ROWS_INV) ? resident_ctas(kern, Cfg::SENSE_THREADS, smem) : 0;
-  if (a.coil_groups > 1) B2N_CUDA_OK(cudaMemsetAsync(a.counter, 0, sizeof(unsigned int) * (size_t)rows, st));
+  if (a.coil_groups > 1 && !g_counters_early) B2N_CUDA_OK(cudaMemsetAsync(a.counter, 0, sizeof(unsigned int) * (size_t)rows, st));
   B2N_CUDA_OK(launch_pdl(kern, dim3((unsigned)(rows * a.coil_groups)), dim3(Cfg::SENSE_THREADS), smem, st, a));
   B2N_LAUNCH_OK("k_fft_rows_sense");
   return 0;

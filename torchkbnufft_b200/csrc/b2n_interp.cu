@@ -413,6 +413,7 @@ extern "C" int b2n_set_option(int option, int value) {
   if (option == B2N_OPT_PDL) {
     g_pdl = value != 0;
     g_zero_kernel = value != 2;  // 2: dependent launches, but the adjoint grid is zeroed by cudaMemsetAsync (A/B)
+    g_counters_early = value != 3;  // 3: ... but the coil-sum counters are zeroed right before their kernel (A/B)
   }
   if (option == B2N_OPT_FFT_PREFETCH) g_prefetch = value;
   return 0;
