@@ -40,6 +40,28 @@ def test_struct_layouts_match_header_sizes():
     assert ctypes.sizeof(_lib.Points) == 16 + 16 + 12 + 12 + 16 + 13 * 8
 
 
+def test_process_wide_options_defaults_and_round_trip():
+    """b2n_set_option / b2n_get_option are host-only: defaults of the launch-overlap knobs, round trip, and the status
+    code for an unknown option; the enum in the header and the constants of the binding agree."""
+    lib = _lib.load()
+    text = open(os.path.join(ROOT, "include", "b200nufft.h")).read()
+    enum = dict((k, int(v)) for k, v in re.findall(r"(B2N_OPT_[A-Z_]+)\s*=\s*(\d+)", text))
+    assert enum["B2N_OPT_TILED_KERNELS"] == _lib.OPT_TILED_KERNELS == 0
+    assert enum["B2N_OPT_FAST_FFT"] == _lib.OPT_FAST_FFT
+    assert enum["B2N_OPT_PDL"] == _lib.OPT_PDL
+    assert enum["B2N_OPT_FFT_PREFETCH"] == _lib.OPT_FFT_PREFETCH
+    assert lib.b2n_get_option(_lib.OPT_PDL) == 1 and lib.b2n_get_option(_lib.OPT_FFT_PREFETCH) == 19
+    assert lib.b2n_get_option(_lib.OPT_FAST_FFT) == 1 and lib.b2n_get_option(_lib.OPT_TILED_KERNELS) == 1
+    try:
+        for opt, val in ((_lib.OPT_PDL, 0), (_lib.OPT_PDL, 2), (_lib.OPT_FFT_PREFETCH, 63), (_lib.OPT_FFT_PREFETCH, 0)):
+            assert lib.b2n_set_option(opt, val) == 0 and lib.b2n_get_option(opt) == val
+    finally:
+        lib.b2n_set_option(_lib.OPT_PDL, 1)
+        lib.b2n_set_option(_lib.OPT_FFT_PREFETCH, 19)
+    assert lib.b2n_set_option(max(enum.values()) + 1, 1) == -1  # B2N_E_ARG
+    assert b"unknown option" in lib.b2n_last_error()
+
+
 def test_argument_errors_are_status_codes():
     lib = _lib.load()
     g = _lib.Geom()
