@@ -80,6 +80,10 @@ def test_argument_errors_are_status_codes():
     g.numpoints[1] = 99
     assert lib.b2n_points_workspace_bytes(ctypes.byref(g), 100, 1, ctypes.byref(n)) == -2
     assert lib.b2n_interp_forward(None, None, None, 1, 1, 0, None, None) == -1  # B2N_E_ARG
+    sizes = _lib.i64_array((32, 32)), _lib.i64_array((64, 64))
+    assert lib.b2n_fft_toeplitz_fused(2, sizes[0], sizes[1], 1, 1, None, 1, None, 1, None, 1, 1.0, None, None, None,
+                                      None) == -1
+    assert b"twiddle_dev" in lib.b2n_last_error()
     assert lib.b2n_spectrum_mul(5, None, None, 1, 1, 1, 1, 0, 1.0, None) == -1
 
 
