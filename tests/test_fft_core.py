@@ -75,6 +75,28 @@ def test_compile_time_plans_match_numpy(n, half_in, hostfft):
             assert err < 5e-7, (n, inverse, err)
 
 
+@pytest.mark.parametrize("n", [64, 256, 384, 640, 768, 1280])
+def test_toeplitz_column_composition_matches_numpy(n, hostfft):
+    """What k_fft_cols_toep does to a column pair, on the host with the same butterflies: forward transform of the
+    n/2 non-zero rows (pruned first stage), multiply by the kernel spectrum, inverse transform, keep n/2 rows."""
+    rng = np.random.default_rng(2000 + n)
+    cplx = lambda m: (rng.standard_normal(m) + 1j * rng.standard_normal(m)).astype(np.complex64)
+    a, b = cplx(n), cplx(n)
+    a[n // 2:] = np.nan  # zero padding: must never be read
+    b[n // 2:] = 0
+    ka, kb = cplx(n), cplx(n)
+    p = lambda x: x.ctypes.data_as(ctypes.c_void_p)
+    fa, fb = np.empty(n, np.complex64), np.empty(n, np.complex64)
+    assert hostfft.host_fft_fast(n, 0, 1, p(a), p(b), p(fa), p(fb)) == 1
+    fa, fb = (fa * ka).astype(np.complex64), (fb * kb).astype(np.complex64)
+    oa, ob = np.empty(n, np.complex64), np.empty(n, np.complex64)
+    assert hostfft.host_fft_fast(n, 1, 0, p(fa), p(fb), p(oa), p(ob)) == 1
+    for x, k, got in ((np.nan_to_num(a), ka, oa), (b, kb, ob)):
+        want = (np.fft.ifft(np.fft.fft(x.astype(np.complex128)) * k.astype(np.complex128)) * n)[: n // 2]
+        err = np.linalg.norm(got[: n // 2] - want) / np.linalg.norm(want)
+        assert err < 1e-6, (n, err)
+
+
 def test_lengths_without_a_plan_use_the_runtime_passes(hostfft):
     z = np.zeros(100, np.complex64)
     p = z.ctypes.data_as(ctypes.c_void_p)
