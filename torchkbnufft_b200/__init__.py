@@ -13,7 +13,7 @@ from ._math import absolute, complex_mult, complex_sign, conj_complex_mult, imag
 from ._nufft import utils as nufft_utils
 from ._nufft.dcomp import calc_density_compensation_function
 from ._nufft.interp import get_adjoint_mode, get_tiled_kernels, set_adjoint_mode, set_tiled_kernels
-from ._nufft.plan import clear_caches
+from ._nufft.plan import clear_caches, get_plan_cache_mode, invalidate_plans, set_plan_cache_mode
 from ._nufft.spmat import calc_tensor_spmatrix
 from ._nufft.toep import calc_toeplitz_kernel
 from .modules import KbInterp, KbInterpAdjoint, KbNufft, KbNufftAdjoint, ToepNufft
@@ -36,10 +36,13 @@ __all__ = [
     "conj_complex_mult",
     "functional",
     "get_adjoint_mode",
+    "get_plan_cache_mode",
     "get_tiled_kernels",
     "imag_exp",
     "inner_product",
+    "invalidate_plans",
     "modules",
     "set_adjoint_mode",
+    "set_plan_cache_mode",
     "set_tiled_kernels",
 ]

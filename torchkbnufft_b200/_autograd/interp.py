@@ -9,6 +9,7 @@ from __future__ import annotations
 
 import torch
 from torch.autograd import Function
+from torch.autograd.function import once_differentiable
 
 from .._nufft.interp import table_interp, table_interp_adjoint
 
@@ -23,6 +24,7 @@ class KbTableInterpForward(Function):
         return output
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, data):
         omega, n_shift, numpoints, table_oversamp, offsets = ctx.saved_tensors[:5]
         tables = list(ctx.saved_tensors[5:])
@@ -39,6 +41,7 @@ class KbTableInterpAdjoint(Function):
         return image
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, image):
         omega, n_shift, numpoints, table_oversamp, offsets = ctx.saved_tensors[:5]
         tables = list(ctx.saved_tensors[5:])

@@ -7,6 +7,12 @@ two fused steps are exact adjoints of one another (the reference's inverse FFT i
 unnormalised, ``_nufft/fft.py:19``), which makes every backward a single call of
 the opposite kernel.  Sensitivity maps and the scaling coefficients are treated as
 constants here; callers route through plain torch ops when those need gradients.
+
+Every backward calls a raw kernel, so it is marked ``once_differentiable``: asking for a
+second derivative through these Functions (``create_graph=True``) raises instead of
+silently returning gradients cut off from the graph.  (The operators are linear in their
+differentiable argument, so Hessian-vector products of a least-squares loss never need it:
+apply the operator to the vector instead.)
 """
 from __future__ import annotations
 
@@ -14,6 +20,7 @@ from typing import Optional
 
 import torch
 from torch.autograd import Function
+from torch.autograd.function import once_differentiable
 
 from .._nufft import fft as _fft
 
@@ -29,6 +36,7 @@ class ApodPad(Function):
         return _fft.apod_pad(image, grid_size, smaps, scaling_coef, scale)
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, grad_grid):
         smaps, scaling_coef = ctx.saved_tensors
         grad = _fft.crop_apod_coilsum(grad_grid, ctx.im_size, smaps, scaling_coef, ctx.scale)
@@ -47,6 +55,7 @@ class CropApodCoilsum(Function):
         return _fft.crop_apod_coilsum(grid, im_size, smaps, scaling_coef, scale)
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, grad_image):
         smaps, scaling_coef = ctx.saved_tensors
         grad = _fft.apod_pad(grad_image, ctx.grid_size, smaps, scaling_coef, ctx.scale, n_coils=ctx.n_coils)
@@ -65,6 +74,7 @@ class FusedFftForward(Function):
         return _fft.fused_fft_forward(image, grid_size, smaps, scaling_coef, scale)
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, grad_grid):
         smaps, scaling_coef = ctx.saved_tensors
         return _fft.fused_fft_adjoint(grad_grid, ctx.im_size, smaps, scaling_coef, ctx.scale), None, None, None, None
@@ -82,6 +92,7 @@ class FusedFftAdjoint(Function):
         return _fft.fused_fft_adjoint(grid, im_size, smaps, scaling_coef, scale)
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, grad_image):
         smaps, scaling_coef = ctx.saved_tensors
         grad = _fft.fused_fft_forward(grad_image, ctx.grid_size, smaps, scaling_coef, ctx.scale, n_coils=ctx.n_coils)
@@ -128,7 +139,8 @@ class ToeplitzFilter(Function):
         return toeplitz_apply(image, kernel, smaps, normalized)
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, grad):
         kernel, smaps = ctx.saved_tensors
         # the operator is S^H P^H F^H D F P S; its adjoint swaps D for conj(D)
-        return toeplitz_apply(grad.contiguous(), kernel.conj().resolve_conj(), smaps, ctx.normalized), None, None, None
+        return toeplitz_apply(grad, kernel.conj(), smaps, ctx.normalized), None, None, None

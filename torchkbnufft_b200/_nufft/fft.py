@@ -21,7 +21,7 @@ import torch
 from torch import Tensor
 
 from .. import _lib
-from .plan import current_stream_ptr, device_guard, engine_dtype, host_ints, require_cuda
+from .plan import current_stream_ptr, dense, device_guard, engine_dtype, host_ints, require_cuda
 
 
 def check_norm(norm: Optional[str]) -> bool:
@@ -34,6 +34,35 @@ def _sizes(v) -> list:
     return list(host_ints(v))
 
 
+def _check_operands(what: str, x: Tensor, spatial: Sequence[int], smaps: Optional[Tensor],
+                    scaling_coef: Optional[Tensor], layout: int = _lib.COIL_MAJOR) -> None:
+    """The kernels take raw pointers and trust ``spatial`` for every operand: refuse anything the reference would
+    reject with a broadcast error (``_nufft/fft.py:72``, ``modules/kbnufft.py:183``, ``:405``) before it can
+    become an out-of-bounds read."""
+    spatial = tuple(int(n) for n in spatial)
+    if not x.is_complex():
+        raise TypeError(f"{what} must be complex")
+    if scaling_coef is not None:
+        if tuple(scaling_coef.shape) != spatial:
+            raise ValueError(f"scaling_coef has shape {tuple(scaling_coef.shape)} but the image size is {spatial}")
+        if scaling_coef.dtype != x.dtype:
+            raise TypeError(f"scaling_coef dtype {scaling_coef.dtype} does not match {what} dtype {x.dtype}")
+        if scaling_coef.device != x.device:
+            raise ValueError(f"scaling_coef is on {scaling_coef.device} but {what} is on {x.device}")
+    if smaps is not None:
+        if smaps.ndim != len(spatial) + 2:
+            raise ValueError(f"smaps must have {len(spatial) + 2} dimensions, got {smaps.ndim}")
+        sm_spatial = tuple(smaps.shape[1:-1]) if layout == _lib.CHANNEL_LAST else tuple(smaps.shape[2:])
+        if sm_spatial != spatial:
+            raise ValueError(f"smaps spatial size {sm_spatial} does not match the image size {spatial}")
+        if smaps.dtype != x.dtype:
+            raise TypeError(f"smaps dtype {smaps.dtype} does not match {what} dtype {x.dtype}")
+        if smaps.device != x.device:
+            raise ValueError(f"smaps is on {smaps.device} but {what} is on {x.device}")
+        if smaps.shape[0] not in (1, x.shape[0]):
+            raise ValueError(f"smaps batch size {smaps.shape[0]} must be 1 or match the batch size {x.shape[0]}")
+
+
 def apod_pad(image: Tensor, grid_size: Sequence[int], smaps: Optional[Tensor] = None,
              scaling_coef: Optional[Tensor] = None, scale: float = 1.0, n_coils: Optional[int] = None,
              layout: int = _lib.COIL_MAJOR) -> Tensor:
@@ -44,12 +73,13 @@ def apod_pad(image: Tensor, grid_size: Sequence[int], smaps: Optional[Tensor] = 
     or ``(B, *K, C)``."""
     require_cuda(image, "image")
     lib = _lib.load()
-    image = image.contiguous()
+    image = dense(image)
     B, Ci = image.shape[:2]
     im_size = list(image.shape[2:])
     grid_size = _sizes(grid_size)
+    _check_operands("image", image, im_size, smaps, scaling_coef, layout)
     if smaps is not None:
-        smaps = smaps.contiguous()
+        smaps = dense(smaps)
         C = smaps.shape[-1] if layout == _lib.CHANNEL_LAST else smaps.shape[1]
         Bs = smaps.shape[0]
     else:
@@ -60,7 +90,7 @@ def apod_pad(image: Tensor, grid_size: Sequence[int], smaps: Optional[Tensor] = 
     if out.numel() == 0:
         return out
     if scaling_coef is not None:
-        scaling_coef = scaling_coef.contiguous()
+        scaling_coef = dense(scaling_coef)
     with device_guard(image.device):
         _lib.check(
             lib.b2n_apod_pad(len(im_size), engine_dtype(image.dtype), _lib.i64_array(im_size), _lib.i64_array(grid_size),
@@ -79,7 +109,7 @@ def crop_apod_coilsum(grid: Tensor, im_size: Sequence[int], smaps: Optional[Tens
     without smaps the coil axis is kept.  Returns ``(B, 1 or C, *N)``."""
     require_cuda(grid, "grid")
     lib = _lib.load()
-    grid = grid.contiguous()
+    grid = dense(grid)
     im_size = _sizes(im_size)
     B = grid.shape[0]
     if layout == _lib.CHANNEL_LAST:
@@ -87,14 +117,17 @@ def crop_apod_coilsum(grid: Tensor, im_size: Sequence[int], smaps: Optional[Tens
     else:
         C, grid_size = grid.shape[1], list(grid.shape[2:])
     Bs = 1
+    _check_operands("grid", grid, im_size, smaps, scaling_coef, layout)
     if smaps is not None:
-        smaps = smaps.contiguous()
+        smaps = dense(smaps)
         Bs = smaps.shape[0]
+        if (smaps.shape[-1] if layout == _lib.CHANNEL_LAST else smaps.shape[1]) != C:
+            raise ValueError("smaps and grid disagree on the number of coils")
     out = torch.empty([B, 1 if smaps is not None else C] + im_size, dtype=grid.dtype, device=grid.device)
     if out.numel() == 0:
         return out
     if scaling_coef is not None:
-        scaling_coef = scaling_coef.contiguous()
+        scaling_coef = dense(scaling_coef)
     with device_guard(grid.device):
         _lib.check(
             lib.b2n_crop_apod_coilsum(len(im_size), engine_dtype(grid.dtype), _lib.i64_array(im_size),
@@ -107,11 +140,27 @@ def crop_apod_coilsum(grid: Tensor, im_size: Sequence[int], smaps: Optional[Tens
     return out
 
 
+def _check_kernel(kernel: Tensor, x: Tensor, grid_size: Sequence[int]) -> None:
+    """Toeplitz kernel ``(*K)`` or per-batch ``(B, *K)`` of the data's dtype on the data's device."""
+    grid_size = tuple(int(k) for k in grid_size)
+    nd = len(grid_size)
+    if kernel.ndim not in (nd, nd + 1) or tuple(kernel.shape[-nd:]) != grid_size:
+        raise ValueError(f"kernel shape {tuple(kernel.shape)} does not match the grid {grid_size}")
+    if kernel.ndim == nd + 1 and kernel.shape[0] not in (1, x.shape[0]):
+        raise ValueError(f"kernel batch size {kernel.shape[0]} must be 1 or match the batch size {x.shape[0]}")
+    if kernel.dtype != x.dtype:
+        raise TypeError(f"kernel dtype {kernel.dtype} does not match data dtype {x.dtype}")
+    if kernel.device != x.device:
+        raise ValueError(f"kernel is on {kernel.device} but the data is on {x.device}")
+
+
 def spectrum_mul_(spectrum: Tensor, kernel: Tensor, scale: float = 1.0, layout: int = _lib.COIL_MAJOR) -> Tensor:
     """In-place ``spectrum[b, c] *= kernel[b or 0] * scale`` (Toeplitz filter)."""
     require_cuda(spectrum, "spectrum")
-    assert spectrum.is_contiguous()
-    kernel = kernel.contiguous()
+    assert spectrum.is_contiguous() and not spectrum.is_conj()
+    if kernel.dtype != spectrum.dtype or kernel.device != spectrum.device:
+        raise TypeError("kernel must have the spectrum's dtype and device")
+    kernel = dense(kernel)
     B = spectrum.shape[0]
     C = spectrum.shape[-1] if layout == _lib.CHANNEL_LAST else spectrum.shape[1]
     n_grid = spectrum.numel() // max(B * C, 1)
@@ -195,6 +244,11 @@ def _twiddles(grid_size, device):
         tkey = (device.index, int(n))
         t = _TWIDDLES.get(tkey)
         if t is None:
+            if torch.cuda.is_current_stream_capturing():
+                # the fill kernel would be recorded instead of run, and later eager calls would read zeros
+                raise RuntimeError(
+                    f"FFT twiddle tables for length {int(n)} must be built before CUDA-graph capture: run the "
+                    "operator once eagerly (warm-up) on this device before capturing it")
             t = torch.zeros(2 * int(n), dtype=torch.complex64, device=device)
             with device_guard(device):
                 _lib.check(lib.b2n_fft_twiddles(int(n), t.data_ptr(), current_stream_ptr(device)), "b2n_fft_twiddles")
@@ -247,12 +301,13 @@ def fused_fft_forward(image: Tensor, grid_size: Sequence[int], smaps: Optional[T
     """``fftn(zero_pad(image * smaps * scaling_coef)) * scale`` (unnormalised transform) in
     ``ndim`` pruned passes; returns the coil-major grid ``(B, C, *K)``."""
     require_cuda(image, "image")
-    image = image.contiguous()
+    image = dense(image)
     B, Ci = image.shape[:2]
     im_size, grid_size = list(image.shape[2:]), _sizes(grid_size)
+    _check_operands("image", image, im_size, smaps, scaling_coef)
     Bs = 1
     if smaps is not None:
-        smaps = smaps.contiguous()
+        smaps = dense(smaps)
         C, Bs = smaps.shape[1], smaps.shape[0]
     else:
         C = Ci if n_coils is None else n_coils
@@ -260,7 +315,7 @@ def fused_fft_forward(image: Tensor, grid_size: Sequence[int], smaps: Optional[T
     if out.numel() == 0:
         return out
     if scaling_coef is not None:
-        scaling_coef = scaling_coef.contiguous()
+        scaling_coef = dense(scaling_coef)
     n_arr, k_arr, tw, nwork, _tabs = _fft_ctx(im_size, grid_size, B, C, image.device)
     work = torch.empty(nwork, dtype=torch.uint8, device=image.device) if nwork else None
     with device_guard(image.device):
@@ -282,22 +337,26 @@ def fused_fft_adjoint(grid: Tensor, im_size: Sequence[int], smaps: Optional[Tens
     in ``ndim`` pruned passes; ``kernel`` (Toeplitz, ``(*K)`` or ``(B, *K)``) is optional.
     Returns ``(B, 1, *N)`` with smaps, ``(B, C, *N)`` without."""
     require_cuda(grid, "grid")
-    grid = grid.contiguous()
+    grid = dense(grid)
     im_size = _sizes(im_size)
     B, C = grid.shape[:2]
     grid_size = list(grid.shape[2:])
     Bs = 1
+    _check_operands("grid", grid, im_size, smaps, scaling_coef)
     if smaps is not None:
-        smaps = smaps.contiguous()
+        smaps = dense(smaps)
         Bs = smaps.shape[0]
+        if smaps.shape[1] != C:
+            raise ValueError("smaps and grid disagree on the number of coils")
     out = torch.empty([B, 1 if smaps is not None else C] + im_size, dtype=grid.dtype, device=grid.device)
     if out.numel() == 0:
         return out
     if scaling_coef is not None:
-        scaling_coef = scaling_coef.contiguous()
+        scaling_coef = dense(scaling_coef)
     kb = 1
     if kernel is not None:
-        kernel = kernel.contiguous()
+        _check_kernel(kernel, grid, grid_size)
+        kernel = dense(kernel)
         kb = kernel.shape[0] if kernel.ndim > len(grid_size) else 1
     n_arr, k_arr, tw, nwork, _tabs = _fft_ctx(im_size, grid_size, B, C, grid.device)
     work = torch.empty(nwork, dtype=torch.uint8, device=grid.device) if nwork else None
@@ -331,15 +390,17 @@ def fused_toeplitz(image: Tensor, kernel: Tensor, smaps: Optional[Tensor] = None
     three passes; the column pass transforms, filters and transforms back without writing the spectrum.
     Returns ``(B, 1, *N)`` with smaps, ``(B, C, *N)`` without."""
     require_cuda(image, "image")
-    image = image.contiguous()
-    kernel = kernel.contiguous()
+    image = dense(image)
+    kernel = dense(kernel)
     B, Ci = image.shape[:2]
     im_size = list(image.shape[2:])
     grid_size = list(kernel.shape[-2:])
     kb = kernel.shape[0] if kernel.ndim > 2 else 1
+    _check_operands("image", image, im_size, smaps, None)
+    _check_kernel(kernel, image, grid_size)
     Bs, C = 1, Ci
     if smaps is not None:
-        smaps = smaps.contiguous()
+        smaps = dense(smaps)
         C, Bs = smaps.shape[1], smaps.shape[0]
     out = torch.empty([B, 1 if smaps is not None else C] + im_size, dtype=image.dtype, device=image.device)
     if out.numel() == 0:

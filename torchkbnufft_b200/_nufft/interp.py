@@ -18,7 +18,8 @@ import torch
 from torch import Tensor
 
 from .. import _lib
-from .plan import current_stream_ptr, device_guard, get_geometry, get_plan, normalize_omega, require_cuda
+from .plan import (current_stream_ptr, dense, device_guard, get_geometry, get_plan, normalize_omega, omega_for,
+                   require_cuda)
 
 ADJOINT_MODES = {"atomic": _lib.ADJ_ATOMIC, "sorted": _lib.ADJ_SORTED}
 _default_adjoint_mode = os.environ.get("B200NUFFT_ADJOINT_MODE", "atomic")
@@ -116,9 +117,9 @@ def table_interp(
     if omega.shape[-2] != geo.ndim:
         raise ValueError(f"omega has {omega.shape[-2]} coordinate rows for a {geo.ndim}-D grid")
     _check_offsets(offsets, geo.n_offsets, geo.ndim)
-    plan = get_plan(geo, omega)
+    plan = get_plan(geo, omega_for(omega, geo.cdtype, image.device, "image"))
     B = image.shape[0]
-    image = image.contiguous()
+    image = dense(image)
     out = torch.empty((B, C, plan.n_points), dtype=image.dtype, device=image.device)
     if out.numel() == 0:
         return out
@@ -161,9 +162,9 @@ def table_interp_adjoint(
     if omega.shape[-1] != data.shape[-1]:
         raise ValueError("omega and data disagree on the number of k-space samples")
     _check_offsets(offsets, geo.n_offsets, geo.ndim)
-    plan = get_plan(geo, omega)
+    plan = get_plan(geo, omega_for(omega, geo.cdtype, data.device, "data"))
     B, C = data.shape[:2]
-    data = data.contiguous()
+    data = dense(data)
     if layout == _lib.CHANNEL_LAST:
         shape = [B] + geo.grid_size + [C]
     else:
@@ -211,7 +212,9 @@ def export_indices(omega: Tensor, tables, n_shift, numpoints, table_oversamp, gr
     if omega.ndim != 2:
         raise ValueError("export_indices takes a single (d, M) trajectory")
     geo = get_geometry(tables, n_shift, numpoints, table_oversamp, grid_size)
-    om = omega.contiguous()
+    if omega.shape[0] != geo.ndim:
+        raise ValueError(f"omega has {omega.shape[0]} coordinate rows for a {geo.ndim}-D grid")
+    om = dense(omega_for(omega, geo.cdtype, geo.device, "the tables"))
     M = om.shape[1]
     arr_ind = torch.empty((geo.n_offsets, M), dtype=torch.int64, device=om.device)
     tab_idx = torch.empty((geo.n_offsets, geo.ndim, M), dtype=torch.int32, device=om.device)

@@ -11,6 +11,7 @@ recycled under a live entry; in-place edits are seen through the tensor version.
 from __future__ import annotations
 
 import ctypes
+import threading
 from collections import OrderedDict
 from typing import List, Optional, Sequence, Tuple
 
@@ -24,6 +25,65 @@ _PLAN_CACHE: "OrderedDict[tuple, TrajectoryPlan]" = OrderedDict()
 _GRID_SIZE_CACHE: dict = {}
 GEOM_CACHE_SIZE = 32
 PLAN_CACHE_SIZE = 8
+# every mutation of the process-global caches below happens under this lock (threaded / DataParallel callers)
+_LOCK = threading.RLock()
+# "version" (default): plans are keyed on (storage pointer, tensor version, shape, stride): in-place edits through
+#   torch are seen, writes that bypass the version counter (DLPack consumers, custom kernels, ``omega.data``) are not;
+# "content": additionally compare the trajectory with the copy the plan was built from (one device comparison and a
+#   host synchronisation per call -- for callers that rewrite trajectories behind torch's back);
+# "off": rebuild the plan on every call.
+_plan_cache_mode = "version"
+
+
+def set_plan_cache_mode(mode: str) -> None:
+    """``"version"`` (default), ``"content"`` or ``"off"`` -- see the comment above ``_plan_cache_mode``."""
+    global _plan_cache_mode
+    if mode not in ("version", "content", "off"):
+        raise ValueError("plan cache mode must be 'version', 'content' or 'off'")
+    _plan_cache_mode = mode
+
+
+def get_plan_cache_mode() -> str:
+    return _plan_cache_mode
+
+
+def dense(t: Tensor) -> Tensor:
+    """The tensor as plain contiguous memory, ready for ``data_ptr()``: lazy conjugate / negative bits are
+    materialised (``.contiguous()`` alone keeps them, and a raw pointer ignores them)."""
+    if t.is_conj():
+        t = t.resolve_conj()
+    if t.is_neg():
+        t = t.resolve_neg()
+    return t if t.is_contiguous() else t.contiguous()
+
+
+REAL_OF = {torch.complex64: torch.float32, torch.complex128: torch.float64}
+_OMEGA_CAST: "OrderedDict[tuple, tuple]" = OrderedDict()
+
+
+def omega_for(omega: Tensor, cdtype: torch.dtype, device: torch.device, what: str) -> Tensor:
+    """The trajectory in the real dtype the kernels read (float32 with complex64 tables, float64 with complex128):
+    the C side reinterprets the buffer by the TABLE dtype, so a mismatched omega must be converted, never passed
+    through.  Conversions are cached per (tensor, version) so that the trajectory plan keyed on the result is
+    reused across calls.  Raises when omega lives on another device than ``what``."""
+    if omega.device != device:
+        raise ValueError(f"omega is on {omega.device} but {what} is on {device}")
+    want = REAL_OF[cdtype]
+    if omega.dtype == want:
+        return omega
+    if not omega.dtype.is_floating_point:
+        raise TypeError(f"omega must be a real floating-point tensor, got {omega.dtype}")
+    key = (id(omega), omega._version, want)
+    with _LOCK:
+        hit = _OMEGA_CAST.get(key)
+        if hit is not None and hit[0] is omega:
+            _OMEGA_CAST.move_to_end(key)
+            return hit[1]
+        cast = omega.to(want)
+        _OMEGA_CAST[key] = (omega, cast)
+        while len(_OMEGA_CAST) > PLAN_CACHE_SIZE:
+            _OMEGA_CAST.popitem(last=False)
+    return cast
 
 
 def require_cuda(t: Tensor, what: str) -> None:
@@ -89,7 +149,7 @@ class Geometry:
         if not (len(self.numpoints) == len(self.table_oversamp) == len(self.n_shift) == len(self.grid_size)
                 == self.ndim):
             raise ValueError("tables, n_shift, numpoints, table_oversamp and grid_size must agree in length")
-        self.tables = [t.contiguous() for t in tables]  # strong refs keep the pointers valid
+        self.tables = [dense(t) for t in tables]  # strong refs keep the pointers valid
         self.n_grid = 1
         for k in self.grid_size:
             self.n_grid *= k
@@ -154,21 +214,22 @@ def get_geometry(tables: Sequence[Tensor], n_shift: Tensor, numpoints: Tensor, t
     # then share one geometry and one trajectory plan
     gkey = host_ints(grid_size)
     key = (tuple(_tkey(t) for t in tables), _tkey(n_shift), _tkey(numpoints), _tkey(table_oversamp), gkey)
-    geo = _GEOM_CACHE.get(key)
-    if geo is not None:
-        _GEOM_CACHE.move_to_end(key)
-    else:
-        for t in tables:
-            require_cuda(t, "tables")
-        geo = Geometry(tables, n_shift, numpoints, table_oversamp, gkey)
-        geo.key = key
-        geo._refs = (n_shift, numpoints, table_oversamp)  # keep key pointers alive
-        _GEOM_CACHE[key] = geo
-        while len(_GEOM_CACHE) > GEOM_CACHE_SIZE:
-            _GEOM_CACHE.popitem(last=False)
-    if len(_GEOM_FAST) > 8 * GEOM_CACHE_SIZE:
-        _GEOM_FAST.clear()
-    _GEOM_FAST[fkey] = (geo, (list(tables), n_shift, numpoints, table_oversamp, grid_size))
+    with _LOCK:
+        geo = _GEOM_CACHE.get(key)
+        if geo is not None:
+            _GEOM_CACHE.move_to_end(key)
+        else:
+            for t in tables:
+                require_cuda(t, "tables")
+            geo = Geometry(tables, n_shift, numpoints, table_oversamp, gkey)
+            geo.key = key
+            geo._refs = (n_shift, numpoints, table_oversamp)  # keep key pointers alive
+            _GEOM_CACHE[key] = geo
+            while len(_GEOM_CACHE) > GEOM_CACHE_SIZE:
+                _GEOM_CACHE.popitem(last=False)
+        if len(_GEOM_FAST) > 8 * GEOM_CACHE_SIZE:
+            _GEOM_FAST.clear()
+        _GEOM_FAST[fkey] = (geo, (list(tables), n_shift, numpoints, table_oversamp, grid_size))
     return geo
 
 
@@ -191,7 +252,7 @@ class TrajectoryPlan:
         else:
             self.n_traj = om.shape[0]
             self.n_points = om.shape[2]
-        om = om.contiguous()
+        om = dense(om)
         nbytes = ctypes.c_size_t(0)
         _lib.check(lib.b2n_points_workspace_bytes(ctypes.byref(geo.struct), self.n_points, self.n_traj,
                                                   ctypes.byref(nbytes)), "b2n_points_workspace_bytes")
@@ -206,7 +267,16 @@ class TrajectoryPlan:
             )
         # the build reads `om` asynchronously; keep a possible contiguous copy alive with the plan
         self._om_contig = om
-        self.workspace.record_stream(torch.cuda.current_stream(omega.device))
+        stream = torch.cuda.current_stream(omega.device)
+        self.workspace.record_stream(stream)
+        # other streams that use the plan wait for this event first (use_on_current_stream)
+        self._build_stream = stream
+        self._streams_seen = {stream.cuda_stream}
+        self._build_event = None
+        if not torch.cuda.is_current_stream_capturing():
+            self._build_event = torch.cuda.Event()
+            self._build_event.record(stream)
+        self._content = om.clone() if _plan_cache_mode == "content" else None
         # The number of sub-problems is only known on the device; kernels are launched over the upper bound
         # n_sub_max and the surplus CTAs exit at once (~3 us of tail per launch at BASELINE config 2).  When a
         # plan is REUSED, the exact count is fetched asynchronously -- no synchronisation -- and the bound is
@@ -216,16 +286,33 @@ class TrajectoryPlan:
         self._n_sub_event = None
         self._count_requested = not (self.struct.n_sub and self.struct.n_sub_max > 0)
 
+    def use_on_current_stream(self) -> None:
+        """Make the plan safe to read from the current stream: a stream other than the one that built it waits
+        for the build and is recorded as a user of the workspace (so the caching allocator does not hand the
+        memory out while that stream still reads it)."""
+        stream = torch.cuda.current_stream(self.omega.device)
+        if stream.cuda_stream in self._streams_seen:
+            return
+        if self._build_event is not None:
+            stream.wait_event(self._build_event)
+        self.workspace.record_stream(stream)
+        with _LOCK:
+            self._streams_seen.add(stream.cuda_stream)
+
+    def content_matches(self, omega: Tensor) -> bool:
+        return self._content is None or bool(torch.equal(self._content, dense(omega)))
+
     def request_count(self) -> None:
         """Start the asynchronous read-back of the device-side sub-problem count (first reuse of the plan)."""
         self._count_requested = True
         off = int(self.struct.n_sub) - self.workspace.data_ptr()
         # a slot of a pinned ring allocated once (pinning memory per plan would cost a blocking cudaHostAlloc)
         global _RING, _RING_NEXT
-        if _RING is None:
-            _RING = torch.empty(_RING_SLOTS, dtype=torch.int32).pin_memory()
-        self._n_sub_token = _RING_NEXT
-        _RING_NEXT += 1
+        with _LOCK:
+            if _RING is None:
+                _RING = torch.empty(_RING_SLOTS, dtype=torch.int32).pin_memory()
+            self._n_sub_token = _RING_NEXT
+            _RING_NEXT += 1
         self._n_sub_host = _RING[self._n_sub_token % _RING_SLOTS:self._n_sub_token % _RING_SLOTS + 1]
         self._n_sub_host.copy_(self.workspace[off:off + 4].view(torch.int32), non_blocking=True)
         self._n_sub_event = torch.cuda.Event()
@@ -252,37 +339,73 @@ _PLAN_FAST: dict = {}  # (id(geo), id(omega), omega._version) -> plan (the plan 
 
 
 def get_plan(geo: Geometry, omega: Tensor) -> TrajectoryPlan:
+    if _plan_cache_mode == "off":
+        return TrajectoryPlan(geo, omega)
     fkey = (id(geo), id(omega), omega._version)
     plan = _PLAN_FAST.get(fkey)
+    if plan is not None and plan._content is not None and not plan.content_matches(omega):
+        invalidate_plans(omega)
+        plan = None
     if plan is not None:
         if not plan._count_requested:
             if not torch.cuda.is_current_stream_capturing():
                 plan.request_count()
         elif plan._n_sub_event is not None:
             plan.tighten()
+        plan.use_on_current_stream()
         return plan
     key = (geo.key, _tkey(omega))
-    plan = _PLAN_CACHE.get(key)
-    if plan is not None:
-        _PLAN_CACHE.move_to_end(key)
-    else:
-        plan = TrajectoryPlan(geo, omega)
-        _PLAN_CACHE[key] = plan
-        while len(_PLAN_CACHE) > PLAN_CACHE_SIZE:
-            evicted = _PLAN_CACHE.popitem(last=False)[1]
-            for k in [k for k, v in _PLAN_FAST.items() if v is evicted]:
-                del _PLAN_FAST[k]  # an evicted plan must free its device memory
-    if len(_PLAN_FAST) > 8 * PLAN_CACHE_SIZE:
-        _PLAN_FAST.clear()
-    if plan.omega is omega:  # only identity-key the tensor the plan itself keeps alive
-        _PLAN_FAST[fkey] = plan
+    with _LOCK:
+        plan = _PLAN_CACHE.get(key)
+        if plan is not None and plan._content is not None and not plan.content_matches(omega):
+            del _PLAN_CACHE[key]
+            plan = None
+        if plan is not None:
+            _PLAN_CACHE.move_to_end(key)
+        else:
+            plan = TrajectoryPlan(geo, omega)
+            _PLAN_CACHE[key] = plan
+            while len(_PLAN_CACHE) > PLAN_CACHE_SIZE:
+                evicted = _PLAN_CACHE.popitem(last=False)[1]
+                for k in [k for k, v in _PLAN_FAST.items() if v is evicted]:
+                    del _PLAN_FAST[k]  # an evicted plan must free its device memory
+        if len(_PLAN_FAST) > 8 * PLAN_CACHE_SIZE:
+            _PLAN_FAST.clear()
+        if plan.omega is omega:  # only identity-key the tensor the plan itself keeps alive
+            _PLAN_FAST[fkey] = plan
+    plan.use_on_current_stream()
     return plan
+
+
+def invalidate_plans(omega: Optional[Tensor] = None) -> None:
+    """Forget the cached trajectory plans built from ``omega`` (all plans when ``None``).  Call this after writing
+    to a trajectory tensor through anything that does not bump torch's version counter (``omega.data``, DLPack,
+    a custom kernel): the cache key is (storage pointer, version), so such a write is otherwise invisible."""
+    with _LOCK:
+        if omega is None:
+            _PLAN_CACHE.clear()
+            _PLAN_FAST.clear()
+            _OMEGA_CAST.clear()
+            return
+        ptr = omega.data_ptr()
+        for k in [k for k, v in _PLAN_CACHE.items() if v.omega is omega or v.omega.data_ptr() == ptr]:
+            del _PLAN_CACHE[k]
+        for k in [k for k, v in _PLAN_FAST.items() if v.omega is omega or v.omega.data_ptr() == ptr]:
+            del _PLAN_FAST[k]
+        for k in [k for k, v in _OMEGA_CAST.items() if v[0] is omega or v[0].data_ptr() == ptr]:
+            plans = [pk for pk, pv in _PLAN_CACHE.items() if pv.omega is _OMEGA_CAST[k][1]]
+            for pk in plans:
+                del _PLAN_CACHE[pk]
+            for fk in [fk for fk, fv in _PLAN_FAST.items() if fv.omega is _OMEGA_CAST[k][1]]:
+                del _PLAN_FAST[fk]
+            del _OMEGA_CAST[k]
 
 
 def clear_caches() -> None:
     """Drop every cached geometry and trajectory plan (frees their device memory)."""
     _PLAN_CACHE.clear()
     _PLAN_FAST.clear()
+    _OMEGA_CAST.clear()
     _GEOM_CACHE.clear()
     _GEOM_FAST.clear()
     _GRID_SIZE_CACHE.clear()

@@ -119,7 +119,13 @@ def toeplitz_filter(image: Tensor, kernel: Tensor, smaps: Optional[Tensor], norm
 
 def fft_filter(image: Tensor, kernel: Tensor, norm: Optional[str] = "ortho") -> Tensor:
     """``crop(IFFT(kernel * FFT(zero_pad(image))))`` on the grid of ``kernel``
-    (reference: ``_nufft/fft.py:121-173``)."""
+    (reference: ``_nufft/fft.py:121-173``).
+
+    ``kernel`` is ``(*K)`` (shared by every batch element and coil) or ``(B, *K)`` / ``(1, *K)``: one kernel
+    PER BATCH ELEMENT, applied to all coils of that element -- which is how ``ToepNufft`` with a batched
+    trajectory uses it (``modules/kbnufft.py:441-484``).  Note the difference from calling the reference's
+    ``fft_filter`` directly with an ``(ndim+1)``-D kernel: plain broadcasting there lines the extra axis up with
+    the COIL axis.  Pass ``kernel.unsqueeze(0)`` permuted to your intent, or loop, if you relied on that."""
     return toeplitz_filter(image, kernel, None, norm)
 
 
