@@ -164,6 +164,97 @@ class ClockSampler:
         return out
 
 
+def make_config(wl, B, world, adjoint_mode, fft):
+    """The `config` object of the JSON line: identical keys (and, for one workload, values) in both arms."""
+    return {"workload": wl.name, "description": wl.description, "batch_per_gpu": B, "coils": wl.n_coils,
+            "points": wl.n_points, "im_size": list(wl.im_size), "grid_size": list(wl.grid_size), "numpoints": 6,
+            "adjoint_mode": adjoint_mode,
+            "parallelism": f"batch-sharded x{world} (no collective)",
+            "l2": "512 MiB buffer written between timed steps (L2 flush)",
+            "plan": "trajectory plan cached across steps (built in warm-up)",
+            "fft": fft}
+
+
+FFT_OWN = "own pruned passes (compile-time plans, libb200nufft.so)"
+FFT_CUFFT = "cuFFT via torch.fft + own pad/crop kernels"
+
+
+def import_stock_reference():
+    """The UNMODIFIED reference package installed by oracle/install_ref.sh under oracle/_ref (git-ignored; it
+    travels to the GPU box with the snapshot).  Returns (module, None) or (None, reason)."""
+    ref_dir = os.path.join(ROOT, "oracle", "_ref")
+    if not os.path.isdir(os.path.join(ref_dir, "torchkbnufft")):
+        return None, "oracle/_ref/torchkbnufft missing (run `sh oracle/install_ref.sh` where /root/reference exists)"
+    import importlib
+    import warnings
+
+    sys.path.insert(0, ref_dir)
+    try:
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            mod = importlib.import_module("torchkbnufft")
+        return mod, None
+    except Exception as exc:  # pragma: no cover
+        return None, f"import failed: {exc!r}"
+    finally:
+        sys.path.remove(ref_dir)
+
+
+def stock_reference_pair(wl, B, device, budget_s=25.0, warmup=1, max_steps=20):
+    """Forward + adjoint SENSE NUFFT of the workload through the STOCK torchkbnufft modules (table mode, the call
+    pattern of the reference's profile_torchkbnufft.py:98-139) on `device`: wall clock on the CPU, CUDA events with
+    the L2 flushed between steps on a GPU.  Returns a dict for the JSON line."""
+    import warnings
+
+    import torch
+
+    from torchkbnufft_b200 import workloads
+
+    ref, why = import_stock_reference()
+    if ref is None:
+        return {"unavailable": why}
+    image, smaps, kdata, omega = workloads.make_inputs(wl, seed=0, n_batch=B)
+    x, s, om = (torch.from_numpy(a).to(device) for a in (image, smaps, omega))
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        nu = ref.KbNufft(im_size=wl.im_size, dtype=torch.complex64).to(device)
+        na = ref.KbNufftAdjoint(im_size=wl.im_size, dtype=torch.complex64).to(device)
+    cuda = torch.device(device).type == "cuda"
+    flush = torch.empty(512 * 1024 * 1024, dtype=torch.uint8, device=device) if cuda else None
+
+    def pair():
+        with torch.no_grad():
+            k = nu(x, om, smaps=s)
+            return na(k, om, smaps=s)
+
+    times = []
+    t_begin = time.perf_counter()
+    for it in range(warmup + max_steps):
+        if cuda:
+            flush.fill_(it & 0xFF)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            pair()
+            e1.record()
+            torch.cuda.synchronize()
+            dt = e0.elapsed_time(e1) * 1e-3
+        else:
+            t0 = time.perf_counter()
+            pair()
+            dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+        if time.perf_counter() - t_begin > budget_s and len(times) >= 3:
+            break
+    units = 2 * B * wl.n_coils * wl.n_points
+    med = statistics.median(times)
+    return {"value": units / med, "unit": UNIT, "ms_per_step": 1e3 * med, "steps": len(times), "warmup": warmup,
+            "device": str(device), "threads": torch.get_num_threads() if not cuda else None,
+            "package": f"torchkbnufft {getattr(ref, '__version__', '?')} (unmodified, oracle/_ref)",
+            "note": "stock KbNufft / KbNufftAdjoint modules, table interpolation, complex64, same seeded inputs; "
+                    "median over the timed steps"}
+
+
 def oracle_pair_seconds(wl, B, steps, warmup, threads):
     """Time the CPU oracle (port of the reference's algorithm) on the same workload."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
@@ -207,15 +298,29 @@ def run_reference(args, wl, rank):
     units = 2 * B * sample.n_coils * sample.n_points
     total = sum(times)
     value = units * len(times) / total
+    config = make_config(wl, B if args.gpus <= 1 or wl.n_batch == 1 else max(1, wl.n_batch // args.gpus),
+                         max(1, args.gpus), "atomic", FFT_OWN)
+    sample_txt = f"{sample.n_spokes}/{wl.n_spokes} spokes" if frac < 1 else "full workload"
+    # the UNMODIFIED reference package beside the port (bounded to a few steps: it is an order of magnitude slower)
+    stock = None
+    try:
+        import torch
+
+        torch.set_num_threads(threads)
+        stock = stock_reference_pair(sample, B, "cpu", budget_s=40.0, warmup=1, max_steps=5)
+        if "value" in stock:
+            stock.update(cores=threads, kind="reference", sample=sample_txt)
+    except Exception as exc:  # pragma: no cover
+        stock = {"unavailable": repr(exc)}
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "c64", "data": "synthetic",
-        "config": {"workload": wl.name, "description": wl.description, "batch_per_gpu": B,
-                   "sample": f"{sample.n_spokes}/{wl.n_spokes} spokes" if frac < 1 else "full workload"},
+        "config": config,
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
                          "sample": f"full {wl.name} fwd+adj pair x{len(times)}" if frac == 1.0 else
                          f"{sample.n_spokes} of {wl.n_spokes} spokes, fwd+adj pair x{len(times)}"},
+        "cpu_baseline_reference": stock,
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -231,6 +336,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--adjoint-mode", default=None, choices=["atomic", "sorted"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-reference-cuda", action="store_true", help="skip timing the stock reference on the GPU")
+    ap.add_argument("--no-partitions", dest="partitions", action="store_false",
+                    help="skip the cfg5 strong-scaling and coil-sharded sections (default workload only)")
     ap.add_argument("--breakdown", action="store_true", help="print per-stage device times to stderr")
     ap.add_argument("--opt", action="append", default=[], help="engine option id=value (A/B experiments)")
     ap.add_argument("--fft", choices=["auto", "cufft", "own"], default="auto",
@@ -468,19 +576,61 @@ def main():
         n_e2e = max(6, min(30, args.steps))
         for _ in range(3):
             serial_step()
-        # best of three repetitions each: the host side of these copies is shared with whatever else runs on the node
-        serial_ms = min(timed(lambda: [serial_step() for _ in range(n_e2e)]) for _ in range(3))
+        # median of five repetitions each (the host side of these copies is shared with whatever else runs on the
+        # node; the best repetition is reported beside it)
+        serial_all = [timed(lambda: [serial_step() for _ in range(n_e2e)]) for _ in range(5)]
         pipelined(NBUF)
-        pipe_ms = min(timed(lambda: pipelined(n_e2e)) for _ in range(3))
+        pipe_all = [timed(lambda: pipelined(n_e2e)) for _ in range(5)]
+        serial_ms, pipe_ms = statistics.median(serial_all), statistics.median(pipe_all)
         h2d = sum(t.numel() * t.element_size() for t in (hx, hs, hom, hy))
         d2h = sum(t.numel() * t.element_size() for t in (hk[0], hi[0]))
+
+        # second figure -- the reconstruction-service case: sensitivity maps and trajectory stay resident on the
+        # device (their plan is cached), every step uploads only that step's image and k-space and downloads both
+        # results
+        def upload_data(b, stream):
+            dx, _ds, dy, _dom = dbuf[b]
+            with torch.cuda.stream(stream):
+                dx.copy_(hx, non_blocking=True)
+                dy.copy_(hy, non_blocking=True)
+
+        def run_resident(b):
+            dx, _ds, dy, _dom = dbuf[b]
+            return nu(dx, om, smaps=s), na(dy, om, smaps=s)
+
+        def pipelined_resident(n):
+            for i in range(n):
+                b = i % NBUF
+                if i >= NBUF:
+                    up.wait_event(freed[b])
+                    down.wait_event(drained[b])
+                upload_data(b, up)
+                ready[b].record(up)
+                compute.wait_event(ready[b])
+                k, im = run_resident(b)
+                freed[b].record(compute)
+                down.wait_event(freed[b])
+                download(b, k, im, down)
+                drained[b].record(down)
+            compute.wait_stream(up)
+            compute.wait_stream(down)
+
+        pipelined_resident(NBUF)
+        res_ms = statistics.median([timed(lambda: pipelined_resident(n_e2e)) for _ in range(5)])
+        h2d_res = sum(t.numel() * t.element_size() for t in (hx, hy))
         e2e = {"value": world * units_per_step * n_e2e / (pipe_ms * 1e-3), "unit": UNIT,
                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": pipe_ms / n_e2e,
+               "best_ms_per_step": min(pipe_all) / n_e2e,
                "serial_value": world * units_per_step * n_e2e / (serial_ms * 1e-3),
-               "serial_ms_per_step": serial_ms / n_e2e, "steps": n_e2e,
+               "serial_ms_per_step": serial_ms / n_e2e, "steps": n_e2e, "repetitions": 5,
+               "resident_operator": {"value": world * units_per_step * n_e2e / (res_ms * 1e-3), "unit": UNIT,
+                                     "ms_per_step": res_ms / n_e2e, "h2d_bytes_per_step": h2d_res,
+                                     "d2h_bytes_per_step": d2h,
+                                     "note": "sensitivity maps and trajectory resident on the device (plan cached); "
+                                             "image and k-space uploaded, both results downloaded every step"},
                "note": "pinned host buffers; image, smaps, trajectory and k-space uploaded and both results "
                        "downloaded every step, trajectory plan rebuilt every step; value = 3-deep pipeline over "
-                       "upload/compute/download streams, serial_value = one stream, no overlap; best of 3 "
+                       "upload/compute/download streams, serial_value = one stream, no overlap; MEDIAN of 5 "
                        "repetitions of `steps` steps each"}
     except Exception as exc:  # pragma: no cover
         e2e = {"error": repr(exc)}
@@ -518,6 +668,110 @@ def main():
     except Exception as exc:  # pragma: no cover
         graph_info = {"error": repr(exc)}
 
+    # ---- the north-star partitions, device-timed with the max over ranks (BASELINE.json config 5 / coil split) -----
+    def timed_steps(fn, n_steps, n_warm=3):
+        """Mean device ms per call of fn over n_steps, L2 flushed between steps, barrier + synchronize on both
+        sides, MAX over ranks."""
+        for _ in range(n_warm):
+            fn()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0 = [torch.cuda.Event(enable_timing=True) for _ in range(n_steps)]
+        e1 = [torch.cuda.Event(enable_timing=True) for _ in range(n_steps)]
+        for i in range(n_steps):
+            flush.fill_(i & 0xFF)
+            e0[i].record()
+            fn()
+            e1[i].record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ms = sum(a.elapsed_time(b) for a, b in zip(e0, e1)) / n_steps
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    partitions = {}
+    if args.partitions and wl.name == "cfg2":
+        from torchkbnufft_b200 import parallel
+
+        n_part = max(5, min(20, args.steps))
+        # (a) BASELINE config 5, STRONG scaling: 64 slices x 16 coils, 64 / N slices per rank, shared trajectory,
+        #     no collective on the data path (every slice is independent)
+        try:
+            w5 = workloads.WORKLOADS["cfg5"]
+            lo, hi = parallel.shard_bounds(w5.n_batch, rank, world)
+            im5, sm5, _kd5, om5 = workloads.make_inputs(w5, seed=100 + rank, n_batch=hi - lo)
+            nu5 = tkbn.KbNufft(im_size=w5.im_size, dtype=torch.complex64).to(dev)
+            na5 = tkbn.KbNufftAdjoint(im_size=w5.im_size, dtype=torch.complex64).to(dev)
+            x5, s5, o5 = (torch.from_numpy(a).to(dev) for a in (im5, sm5, om5))
+
+            def step5():
+                k = nu5(x5, o5, smaps=s5)
+                return na5(k, o5, smaps=s5)
+
+            ms5 = timed_steps(step5, n_part)
+            units5 = 2 * w5.n_batch * w5.n_coils * w5.n_points  # whole job: all 64 slices
+            f5, a5, _ = algorithmic_bytes(w5, hi - lo)
+            partitions["cfg5_strong"] = {
+                "value": units5 / (ms5 * 1e-3), "unit": UNIT, "ms_per_step": ms5, "scaling": "strong",
+                "slices_total": w5.n_batch, "slices_per_gpu": hi - lo, "coils": w5.n_coils, "steps": n_part,
+                "collective": None, "pair_frac_per_gpu": (f5 + a5) / (ms5 * 1e-3) / 1e9 / peak,
+                "note": "BASELINE config 5: forward + adjoint SENSE NUFFT of all 64 slices, batch-sharded; total "
+                        "work fixed as N grows; device time, max over ranks"}
+            del x5, s5, o5, nu5, na5
+            tkbn.clear_caches()
+            torch.cuda.empty_cache()
+        except Exception as exc:  # pragma: no cover
+            partitions["cfg5_strong"] = {"error": repr(exc)}
+        # (b) coil sharding of cfg2 (B = 1 < N): C / N coils per rank, replicated image / trajectory; the forward
+        #     needs no exchange, the adjoint ends with ONE NCCL sum all-reduce of the coil-combined image
+        #     (reference coupling point: modules/kbnufft.py:404-405), inside the timed region
+        try:
+            lo, hi = parallel.shard_bounds(wl.n_coils, rank, world)
+            im0, sm0, _kd0, _om0 = workloads.make_inputs(wl, seed=0, n_batch=1)  # the SAME problem on every rank
+            x0, s0 = torch.from_numpy(im0).to(dev), torch.from_numpy(sm0).to(dev)
+            s_loc = s0[:, lo:hi].contiguous()
+
+            def step_sharded():
+                k_loc = parallel.coil_sharded_forward(nu, x0, om, s_loc)
+                return parallel.coil_sharded_adjoint(na, k_loc, om, s_loc)
+
+            got = step_sharded()
+            want = na(nu(x0, om, smaps=s0), om, smaps=s0)
+            err = float(torch.linalg.vector_norm(got - want) / torch.linalg.vector_norm(want))
+            ms_sh = timed_steps(step_sharded, n_part)
+            buf = torch.zeros_like(want)
+            ms_ar = timed_steps(lambda: parallel.all_reduce_complex_(buf), n_part) if world > 1 else 0.0
+            units2 = 2 * wl.n_coils * wl.n_points  # the whole 16-coil problem, whatever N is
+            partitions["coil_sharded"] = {
+                "value": units2 / (ms_sh * 1e-3), "unit": UNIT, "ms_per_step": ms_sh, "scaling": "strong",
+                "coils_total": wl.n_coils, "coils_per_gpu": hi - lo, "steps": n_part,
+                "collective": "NCCL all-reduce(sum) of the coil-combined image, inside the timed region"
+                              if world > 1 else None,
+                "allreduce_bytes": int(want.numel() * 8), "allreduce_ms_alone": ms_ar,
+                "allreduce_share": (ms_ar / ms_sh) if ms_sh > 0 else None,
+                "rel_l2_vs_unsharded": err,
+                "note": "cfg2 forward + adjoint with the coils split over the ranks; strong scaling of ONE slice; "
+                        "device time, max over ranks"}
+            del x0, s0, s_loc, buf
+        except Exception as exc:  # pragma: no cover
+            partitions["coil_sharded"] = {"error": repr(exc)}
+
+    # ---- the stock reference package on the same GPU ("the existing Blackwell path", SURVEY 2.1) -----------------
+    reference_cuda = None
+    if rank == 0 and not args.no_reference_cuda:
+        try:
+            reference_cuda = stock_reference_pair(wl, B, dev, budget_s=20.0, warmup=5, max_steps=20)
+            tkbn.clear_caches()
+            torch.cuda.empty_cache()
+        except Exception as exc:  # pragma: no cover
+            reference_cuda = {"unavailable": repr(exc)}
+
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
@@ -540,14 +794,7 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "c64", "data": "synthetic",
-            "config": {"workload": wl.name, "description": wl.description, "batch_per_gpu": B,
-                       "coils": wl.n_coils, "points": wl.n_points, "im_size": list(wl.im_size),
-                       "grid_size": list(wl.grid_size), "numpoints": 6, "adjoint_mode": tkbn.get_adjoint_mode(),
-                       "parallelism": f"batch-sharded x{world} (no collective)",
-                       "l2": "512 MiB buffer written between timed steps (L2 flush)",
-                       "plan": "trajectory plan cached across steps (built in warm-up)",
-                       "fft": ("own pruned passes (compile-time plans, libb200nufft.so)" if fused else
-                               "cuFFT via torch.fft + own pad/crop kernels")},
+            "config": make_config(wl, B, world, tkbn.get_adjoint_mode(), FFT_OWN if fused else FFT_CUFFT),
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "kernel_ms": live[dom], "kernels_ms_in_step": live,
@@ -560,6 +807,8 @@ def main():
                          "pair_frac": pair_achieved / peak},
             "stages_ms": {k: round(v, 5) for k, v in stages.items()},
             "cuda_graph": graph_info,
+            "partitions": partitions,
+            "reference_cuda": reference_cuda,
             "cpu_baseline": cpu_baseline,
             "e2e": e2e,
             # kernels of libb200nufft.so launched inside the timed region, counted by the library itself

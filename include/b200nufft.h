@@ -32,7 +32,7 @@ extern "C" {
 #define B2N_API
 #endif
 
-#define B2N_ABI_VERSION 2
+#define B2N_ABI_VERSION 3
 #define B2N_MAX_DIMS 3
 #define B2N_MAX_NUMPOINTS 16 /* max neighbours J per dimension */
 
@@ -102,6 +102,23 @@ typedef struct b2n_points {
                           the consecutive ranks [tile_sub_start[t], tile_sub_start[t+1]) (the sub_* arrays themselves
                           are ordered longest-first for load balance) */
   int32_t *tile_sub_start; /* [n_traj*prod(n_tiles)] first rank of each tile; the last tile ends at *n_sub */
+  /* Owner-tile visit lists for the output-stationary spread (b2n_interp_adjoint_ordered; 2-D complex64 J = 6 plans on
+   * grids with every K_d >= 16 and K_d % 8 in {0, 5, 6, 7}; own_tile == 0 and NULL pointers otherwise).  The grid is cut
+   * into own_tile x own_tile OUTPUT tiles; a "visit" is one (point, output tile) pair whose J x J footprint
+   * intersects the tile (1, 2 or 4 per point); the visits of a tile are listed in a fixed order (window cell
+   * row-major, then sorted slot) and cut into work items of at most own_cap visits.  Every output tile has at
+   * least one item (an empty one writes zeros), so the spread needs no zero-initialised grid and no atomics. */
+  int32_t own_tile;          /* 8, or 0 when the lists were not built */
+  int32_t own_cap;           /* max visits per work item */
+  int32_t n_own_tiles[2];    /* output tiles per dimension = ceil(K_d / own_tile) */
+  int64_t n_own_items_max;   /* capacity of own_items (upper bound on own_counts[0]) */
+  void *own_visits;          /* int32x4 [<= 4*n_traj*M]: {sorted slot, sample index inside its trajectory, ry, rx} with
+                                (ry, rx) = base cell minus tile origin, unwrapped, each in [-(J-1), own_tile-1] */
+  void *own_items;           /* int32x4 [n_own_items_max]: {traj*prod(n_own_tiles) + tile, first visit, visits | chunk
+                                index inside the tile << 12, tile row << 16 | tile column}, longest first */
+  void *own_tiles;           /* int32x4 [n_traj*prod(n_own_tiles)]: {visits, first visit, chunks, first partial-sum slot
+                                (-1 for single-chunk tiles)} */
+  int32_t *own_counts;       /* device: [0] = items in use, [1] = partial-sum slots in use */
 } b2n_points;
 
 /* engine options (process-wide; for A/B measurements and tests) */
@@ -125,6 +142,9 @@ enum b2n_option {
   B2N_OPT_FFT_PREFETCH = 6, /* planned FFT passes whose CTAs pull the operand rows of the CTA one wave ahead into L2, as a
                                mask: 1 forward rows, 2 forward columns, 4 inverse columns, 8 inverse rows, 16 Toeplitz
                                columns; a pass must also read >= 32 MB unless 32 is set.  Default 19. */
+  B2N_OPT_ADJ_OWNED = 7, /* 1 (default): b2n_interp_adjoint_ordered uses the output-stationary owner-tile spread where
+                            the plan carries visit lists (2-D complex64 J = 6); 0: the scratch-tile + merge kernels */
+  B2N_OPT_OWN_CAP = 8, /* visits per work item of the owner-tile spread, read when a plan is built (default 64) */
   B2N_OPT_COUNT
 };
 B2N_API int b2n_set_option(int option, int value);
@@ -205,6 +225,13 @@ B2N_API int b2n_spectrum_mul(int dtype, void *spectrum_dev, const void *kernel_d
  * b2n_interp_adjoint_ordered_bytes: scratch size in bytes, 0 when this path does not apply. */
 B2N_API int b2n_interp_adjoint_ordered_bytes(const b2n_geom *geom, const b2n_points *pts, int64_t n_batch, int64_t n_coils,
                                              int grid_layout, size_t *bytes);
+/* The same query plus `zero_bytes`: the leading bytes of the scratch that hold arrival counters.  They must be zero
+ * when a scratch buffer is first handed to b2n_interp_adjoint_ordered and are left zero by every completed call, so a
+ * caller that keeps the buffer between calls zeroes it once (0 for the paths without counters).  With
+ * n_items / n_slots > 0 (the plan's own_counts read back by the caller) the size is exact instead of an upper bound. */
+B2N_API int b2n_interp_adjoint_ordered_layout(const b2n_geom *geom, const b2n_points *pts, int64_t n_batch,
+                                              int64_t n_coils, int grid_layout, int64_t n_slots, size_t *bytes,
+                                              size_t *zero_bytes);
 B2N_API int b2n_interp_adjoint_ordered(const b2n_geom *geom, const b2n_points *pts, const void *kdata_dev, int64_t n_batch,
                                        int64_t n_coils, int grid_layout, void *scratch_dev, size_t scratch_bytes,
                                        void *grid_dev, void *stream);

@@ -1,5 +1,6 @@
-"""Adjoint-spread variants (B2N_OPT_ADJ_ROW_OWNERSHIP) timed alone at 16 coils, in one process.
-python profiles/scripts/adj_variants.py [cfg2 cfg5s ...] [--variants=0,3,4]"""
+"""Adjoint-spread variants timed alone at 16 coils, in one process: the shared-memory tiled kernels
+(B2N_OPT_ADJ_ROW_OWNERSHIP values) and the owner-tile register spread with several work-item caps.
+python profiles/scripts/adj_variants.py [cfg2 cfg5 ...] [--variants=0,3,4] [--caps=32,64,128] [--coils=16]"""
 import os, statistics, sys
 import numpy as np, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -22,11 +23,16 @@ def timeit(fn, reps=20, warm=3):
         ts.append(a.elapsed_time(b) * 1e3)
     return statistics.median(ts)
 
-variants = [0, 3, 4, 5, 2]
-names = []
+variants, caps, names, coils, owned = [0], [32, 64, 128], [], [16], [1]
 for a in sys.argv[1:]:
     if a.startswith("--variants="):
-        variants = [int(v) for v in a.split("=")[1].split(",")]
+        variants = [int(v) for v in a.split("=")[1].split(",") if v]
+    elif a.startswith("--caps="):
+        caps = [int(v) for v in a.split("=")[1].split(",") if v]
+    elif a.startswith("--owned="):
+        owned = [int(v) for v in a.split("=")[1].split(",") if v]
+    elif a.startswith("--coils="):
+        coils = [int(v) for v in a.split("=")[1].split(",") if v]
     else:
         names.append(a)
 lib = _lib.load()
@@ -36,15 +42,32 @@ for name in names or ["cfg2"]:
     ob = tkbn.KbInterp(im_size=wl.im_size, dtype=torch.complex64).to(dev)
     args = (ob.tables, ob.n_shift, ob.numpoints, ob.table_oversamp)
     B = min(wl.n_batch, 8)
-    y = torch.randn((B, 16, om.shape[-1]), dtype=torch.complex64, device=dev)
-    ref = None
-    for v in variants:
-        lib.b2n_set_option(_lib.OPT_ADJ_ROW_OWNERSHIP, v)
+    for C in coils:
+        y = torch.randn((B, C, om.shape[-1]), dtype=torch.complex64, device=dev)
         fn = lambda: eng_interp.table_interp_adjoint(y, om, *args, None, ob.grid_size, mode="atomic")
-        out = fn()
-        if ref is None:
-            ref = out
-        err = float((out - ref).norm() / ref.norm())
-        t = timeit(fn)
-        print(f"{name} B={B} C=16 variant {v}: adjoint interp {t:8.1f} us   rel diff vs variant {variants[0]}: {err:.2e}", flush=True)
-    lib.b2n_set_option(_lib.OPT_ADJ_ROW_OWNERSHIP, 0)
+        ref = None
+        eng_interp.owned_spread = False
+        for v in variants:
+            lib.b2n_set_option(_lib.OPT_ADJ_ROW_OWNERSHIP, v)
+            out = fn()
+            ref = out if ref is None else ref
+            err = float((out - ref).norm() / ref.norm())
+            print(f"{name} B={B} C={C} tiled variant {v}: adjoint interp {timeit(fn):8.1f} us   rel diff {err:.2e}", flush=True)
+        lib.b2n_set_option(_lib.OPT_ADJ_ROW_OWNERSHIP, 0)
+        eng_interp.owned_spread = True
+        for cap, ow in [(c, o) for o in owned for c in caps]:
+            lib.b2n_set_option(_lib.OPT_ADJ_OWNED, ow)
+            lib.b2n_set_option(_lib.OPT_OWN_CAP, cap)
+            tkbn.clear_caches()
+            out = fn(); out2 = fn()
+            torch.cuda.synchronize()
+            err = float((out - ref).norm() / ref.norm()) if ref is not None else float("nan")
+            same = bool(torch.equal(out, out2))
+            from torchkbnufft_b200._nufft import plan as P
+            pl = list(P._PLAN_CACHE.values())[-1]
+            fn(); torch.cuda.synchronize(); fn()
+            print(f"{name} B={B} C={C} owner tiles (opt {ow}) cap {cap:4d}: adjoint interp {timeit(fn):8.1f} us   rel diff {err:.2e} "
+                  f"bit-reproducible {same} items {pl.struct.n_own_items_max} slots {pl.own_slots}", flush=True)
+        lib.b2n_set_option(_lib.OPT_OWN_CAP, 64)
+        lib.b2n_set_option(_lib.OPT_ADJ_OWNED, 1)
+        tkbn.clear_caches()

@@ -37,7 +37,8 @@ def test_library_exports_every_declared_symbol():
 def test_struct_layouts_match_header_sizes():
     # b2n_geom: 2*int32 + 3*int64 + 3*int32 + 3*int32 + 3*int64 + 3*ptr + 3*double
     assert ctypes.sizeof(_lib.Geom) == 8 + 24 + 12 + 12 + 24 + 24 + 24
-    assert ctypes.sizeof(_lib.Points) == 16 + 16 + 12 + 12 + 16 + 13 * 8
+    # ... + the owner-tile visit lists: 4*int32 + int64 + 4*ptr
+    assert ctypes.sizeof(_lib.Points) == 16 + 16 + 12 + 12 + 16 + 13 * 8 + 16 + 8 + 4 * 8
 
 
 def test_process_wide_options_defaults_and_round_trip():

@@ -351,6 +351,102 @@ def test_cfg5_one_gpu_share_batch_consistency():
     assert float(abs(_inner(ax, y) - _inner(x, ahy)) / abs(_inner(ax, y))) <= 1e-5
 
 
+def _oracle_args(nu):
+    tables = [host(t) for t in nu.tables]
+    return tables, host(nu.n_shift), nu.numpoints.tolist(), nu.table_oversamp.tolist(), host(nu.scaling_coef)
+
+
+def test_cfg4_full_size_adjoint_against_oracle_on_a_spoke_subset():
+    """BASELINE config 4 at FULL size (256^3 grid, the 8.4 M-point plan) against the oracle.  The adjoint is linear in
+    the samples: with every sample zero except those of each 64th spoke, the engine's full-plan adjoint must equal
+    the oracle's adjoint of that subset alone (131 072 points x 216 taps x 8 coils -- seconds on the host).  Both
+    accumulation modes; then the autograd gradient of 0.5*|A_sub x|^2 against the oracle's A_sub^H A_sub x."""
+    wl = workloads.WORKLOADS["cfg4"]
+    image, smaps, kdata, omega = workloads.make_inputs(wl, seed=0)
+    spoke = np.arange(wl.n_points) // wl.n_read
+    pick = np.nonzero(spoke % 64 == 0)[0]
+    assert pick.size == wl.n_points // 64
+    sparse = np.zeros_like(kdata)
+    sparse[..., pick] = kdata[..., pick]
+    x, s, om = dev(image), dev(smaps), dev(omega)
+    nu = tkbn.KbNufft(im_size=wl.im_size, dtype=torch.complex64).to(DEV)
+    na = tkbn.KbNufftAdjoint(im_size=wl.im_size, dtype=torch.complex64).to(DEV)
+    tables, ns, J, L, scaling = _oracle_args(nu)
+    threads = os.cpu_count() or 1
+    om_sub = np.ascontiguousarray(omega[:, pick])
+    want = orc.nufft_adjoint(np.ascontiguousarray(kdata[..., pick]), om_sub, tables, ns, J, L, scaling, wl.im_size,
+                             wl.grid_size, smaps=smaps, nthreads=threads)
+    y = dev(sparse)
+    for mode in ("atomic", "sorted"):
+        tkbn.set_adjoint_mode(mode)
+        try:
+            assert rel_l2(host(na(y, om, smaps=s)), want) <= 1e-4, mode
+        finally:
+            tkbn.set_adjoint_mode("atomic")
+    del y
+    # gradient of 0.5 * |A_sub x|^2 = A_sub^H A_sub x, oracle on both legs
+    oms = dev(om_sub)
+    xg = x.clone().requires_grad_(True)
+    (nu(xg, oms, smaps=s).abs() ** 2 / 2).sum().backward()
+    ax = orc.nufft_forward(image, om_sub, tables, ns, J, L, scaling, wl.im_size, wl.grid_size, smaps=smaps,
+                           nthreads=threads)
+    want_g = orc.nufft_adjoint(ax, om_sub, tables, ns, J, L, scaling, wl.im_size, wl.grid_size, smaps=smaps,
+                               nthreads=threads)
+    assert rel_l2(host(xg.grad), want_g) <= 1e-4
+
+
+def test_cfg5_slices_of_the_batch_against_oracle():
+    """BASELINE config 5, one GPU's share (8 slices x 16 coils, shared trajectory): two slices of the BATCHED forward
+    and adjoint calls against the oracle run on those slices alone."""
+    wl = workloads.WORKLOADS["cfg5"]
+    image, smaps, kdata, omega = workloads.make_inputs(wl, seed=0, n_batch=8)
+    x, s, y, om = dev(image), dev(smaps), dev(kdata), dev(omega)
+    nu = tkbn.KbNufft(im_size=wl.im_size, dtype=torch.complex64).to(DEV)
+    na = tkbn.KbNufftAdjoint(im_size=wl.im_size, dtype=torch.complex64).to(DEV)
+    tables, ns, J, L, scaling = _oracle_args(nu)
+    threads = os.cpu_count() or 1
+    ax = host(nu(x, om, smaps=s))
+    outs = {}
+    for mode in ("atomic", "sorted"):
+        tkbn.set_adjoint_mode(mode)
+        try:
+            outs[mode] = host(na(y, om, smaps=s))
+        finally:
+            tkbn.set_adjoint_mode("atomic")
+    for b in (0, 5):
+        want_f = orc.nufft_forward(image[b:b + 1], omega, tables, ns, J, L, scaling, wl.im_size, wl.grid_size,
+                                   smaps=smaps, nthreads=threads)
+        assert rel_l2(ax[b:b + 1], want_f) <= 1e-5
+        want_a = orc.nufft_adjoint(kdata[b:b + 1], omega, tables, ns, J, L, scaling, wl.im_size, wl.grid_size,
+                                   smaps=smaps, nthreads=threads)
+        for mode in outs:
+            assert rel_l2(outs[mode][b:b + 1], want_a) <= 1e-4, (b, mode)
+
+
+def test_cfg3_full_size_toeplitz_against_oracle():
+    """BASELINE config 3 at full size (384^2 image, 768^2 kernel, M = 184 320) on a 4-coil subset: the engine's
+    ToepNufft apply with the engine-built kernel against (i) the oracle's fft_filter pipeline given the same kernel
+    (the apply alone, 1e-5) and (ii) the oracle's A^H A x, which involves neither the kernel builder nor the filter
+    (the whole Toeplitz path; 1e-4, the embedding itself is exact up to the interpolation error)."""
+    wl = workloads.WORKLOADS["cfg3"]
+    image, smaps, _kdata, omega = workloads.make_inputs(wl, seed=0)
+    sub = np.ascontiguousarray(smaps[:, :4])
+    x, s4, om = dev(image), dev(sub), dev(omega)
+    nu = tkbn.KbNufft(im_size=wl.im_size, dtype=torch.complex64).to(DEV)
+    tables, ns, J, L, scaling = _oracle_args(nu)
+    threads = os.cpu_count() or 1
+    for norm in ("ortho", None):
+        kern = tkbn.calc_toeplitz_kernel(om, wl.im_size, norm=norm)
+        got = host(tkbn.ToepNufft()(x, kern, smaps=s4, norm=norm))
+        want_apply = orc.toep_nufft(image, host(kern), smaps=sub, norm=norm, workers=threads)
+        assert rel_l2(got, want_apply) <= 1e-5, norm
+        ax = orc.nufft_forward(image, omega, tables, ns, J, L, scaling, wl.im_size, wl.grid_size, smaps=sub,
+                               nthreads=threads, norm=norm)
+        want_normal = orc.nufft_adjoint(ax, omega, tables, ns, J, L, scaling, wl.im_size, wl.grid_size, smaps=sub,
+                                        nthreads=threads, norm=norm)
+        assert rel_l2(got, want_normal) <= 1e-4, norm
+
+
 def test_edge_shapes():
     kw = dict(im_size=(8, 6), dtype=torch.complex64)
     interp, adj = tkbn.KbInterp(**kw).to(DEV), tkbn.KbInterpAdjoint(**kw).to(DEV)

@@ -16,7 +16,7 @@ MAX_NUMPOINTS = 16
 C64, C128 = 0, 1
 COIL_MAJOR, CHANNEL_LAST = 0, 1
 ADJ_ATOMIC, ADJ_SORTED = 0, 1
-ABI_VERSION = 2
+ABI_VERSION = 3
 OPT_TILED_KERNELS = 0
 OPT_ADJ_ROW_OWNERSHIP = 1
 OPT_FWD_COIL_CHUNK = 2
@@ -24,6 +24,8 @@ OPT_ADJ_COIL_CHUNK = 3
 OPT_FAST_FFT = 4
 OPT_PDL = 5
 OPT_FFT_PREFETCH = 6
+OPT_ADJ_OWNED = 7
+OPT_OWN_CAP = 8
 
 _CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")
 LIB_PATH = os.path.join(_CSRC, "libb200nufft.so")
@@ -71,6 +73,14 @@ class Points(Structure):
         ("n_sub", c_void_p),
         ("sub_slot", c_void_p),
         ("tile_sub_start", c_void_p),
+        ("own_tile", c_int32),
+        ("own_cap", c_int32),
+        ("n_own_tiles", c_int32 * 2),
+        ("n_own_items_max", c_int64),
+        ("own_visits", c_void_p),
+        ("own_items", c_void_p),
+        ("own_tiles", c_void_p),
+        ("own_counts", c_void_p),
     ]
 
 
@@ -98,6 +108,8 @@ SIGNATURES = {
                                    c_void_p, c_void_p]),
     "b2n_interp_adjoint_ordered_bytes": (c_int, [POINTER(Geom), POINTER(Points), c_int64, c_int64, c_int,
                                                  POINTER(c_size_t)]),
+    "b2n_interp_adjoint_ordered_layout": (c_int, [POINTER(Geom), POINTER(Points), c_int64, c_int64, c_int, c_int64,
+                                                  POINTER(c_size_t), POINTER(c_size_t)]),
     "b2n_interp_adjoint_ordered": (c_int, [POINTER(Geom), POINTER(Points), c_void_p, c_int64, c_int64, c_int, c_void_p,
                                            c_size_t, c_void_p, c_void_p]),
     "b2n_apod_pad": (c_int, [c_int, c_int, _I64P, _I64P, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_int64,

@@ -71,6 +71,10 @@ class KernelTimer:
 
 kernel_timer: Optional[KernelTimer] = None
 
+# owner-tile (output-stationary, register-accumulator) spread: on by default; rows = batch x coils
+owned_spread = True
+owned_spread_min_rows = 3
+
 
 def _check_offsets(offsets: Optional[Tensor], n_offsets: int, ndim: int) -> None:
     # The engine always visits the full row-major neighbourhood (the only thing the
@@ -178,14 +182,35 @@ def table_interp_adjoint(
     lib = _lib.load()
     with device_guard(data.device):
         stop = kernel_timer.bracket("interp_adj", data.device) if kernel_timer is not None else None
+        done = False
+        # The output-stationary owner-tile spread (2-D complex64 J = 6 plans) is deterministic AND the fastest kernel
+        # from `owned_spread_min_rows` (batch x coil) rows on, so it serves both modes; it keeps a small persistent
+        # scratch (arrival counters + partial tiles of the dense tiles) with the plan.
+        if (plan.struct.own_tile and layout == _lib.COIL_MAJOR and owned_spread and
+                (mode_id == _lib.ADJ_SORTED or B * C >= owned_spread_min_rows)):
+            scratch, nbytes = plan.own_scratch(lib, geo, B, C, layout)
+            if scratch is not None:
+                _lib.check(
+                    lib.b2n_interp_adjoint_ordered(ctypes.byref(geo.struct), ctypes.byref(plan.struct), data.data_ptr(),
+                                                   B, C, layout, scratch.data_ptr(), nbytes, out.data_ptr(),
+                                                   current_stream_ptr(data.device)),
+                    "b2n_interp_adjoint_ordered",
+                )
+                done = True
         scratch_bytes = ctypes.c_size_t(0)
-        if mode_id == _lib.ADJ_SORTED:
-            # deterministic mode: the tiled kernels with per-sub-problem scratch tiles and a fixed-order merge where
-            # they apply (2-D complex64, J = 6), else the per-cell gather
-            _lib.check(lib.b2n_interp_adjoint_ordered_bytes(ctypes.byref(geo.struct), ctypes.byref(plan.struct), B, C,
-                                                            layout, ctypes.byref(scratch_bytes)),
-                       "b2n_interp_adjoint_ordered_bytes")
-        if scratch_bytes.value:
+        if not done and mode_id == _lib.ADJ_SORTED:
+            # deterministic mode elsewhere: the tiled kernels with per-sub-problem scratch tiles and a fixed-order
+            # merge where they apply (3-D complex64, J = 6), else the per-cell gather
+            zero_bytes = ctypes.c_size_t(0)
+            _lib.check(lib.b2n_interp_adjoint_ordered_layout(ctypes.byref(geo.struct), ctypes.byref(plan.struct), B, C,
+                                                             layout, 0, ctypes.byref(scratch_bytes),
+                                                             ctypes.byref(zero_bytes)),
+                       "b2n_interp_adjoint_ordered_layout")
+            if zero_bytes.value:  # owner-tile path switched off in Python but on in the library: needs zeroed counters
+                scratch_bytes = ctypes.c_size_t(0)
+        if done:
+            pass
+        elif scratch_bytes.value:
             scratch = torch.empty(scratch_bytes.value, dtype=torch.uint8, device=data.device)
             _lib.check(
                 lib.b2n_interp_adjoint_ordered(ctypes.byref(geo.struct), ctypes.byref(plan.struct), data.data_ptr(), B,

@@ -277,6 +277,8 @@ class TrajectoryPlan:
             self._build_event = torch.cuda.Event()
             self._build_event.record(stream)
         self._content = om.clone() if _plan_cache_mode == "content" else None
+        self.own_slots = 0      # partial-sum slots of the owner-tile spread: 0 = not read back yet (upper bound)
+        self._own_scratch = {}
         # The number of sub-problems is only known on the device; kernels are launched over the upper bound
         # n_sub_max and the surplus CTAs exit at once (~3 us of tail per launch at BASELINE config 2).  When a
         # plan is REUSED, the exact count is fetched asynchronously -- no synchronisation -- and the bound is
@@ -303,24 +305,29 @@ class TrajectoryPlan:
         return self._content is None or bool(torch.equal(self._content, dense(omega)))
 
     def request_count(self) -> None:
-        """Start the asynchronous read-back of the device-side sub-problem count (first reuse of the plan)."""
+        """Start the asynchronous read-back of the device-side counts (first reuse of the plan): sub-problems,
+        and the work items / partial-sum slots of the owner-tile spread."""
         self._count_requested = True
-        off = int(self.struct.n_sub) - self.workspace.data_ptr()
         # a slot of a pinned ring allocated once (pinning memory per plan would cost a blocking cudaHostAlloc)
         global _RING, _RING_NEXT
         with _LOCK:
             if _RING is None:
-                _RING = torch.empty(_RING_SLOTS, dtype=torch.int32).pin_memory()
+                _RING = torch.empty((_RING_SLOTS, 4), dtype=torch.int32).pin_memory()
             self._n_sub_token = _RING_NEXT
             _RING_NEXT += 1
-        self._n_sub_host = _RING[self._n_sub_token % _RING_SLOTS:self._n_sub_token % _RING_SLOTS + 1]
-        self._n_sub_host.copy_(self.workspace[off:off + 4].view(torch.int32), non_blocking=True)
+        self._n_sub_host = _RING[self._n_sub_token % _RING_SLOTS]
+        base = self.workspace.data_ptr()
+        off = int(self.struct.n_sub) - base
+        self._n_sub_host[0:1].copy_(self.workspace[off:off + 4].view(torch.int32), non_blocking=True)
+        if self.struct.own_tile:
+            off = int(self.struct.own_counts) - base
+            self._n_sub_host[1:3].copy_(self.workspace[off:off + 8].view(torch.int32), non_blocking=True)
         self._n_sub_event = torch.cuda.Event()
         self._n_sub_event.record(torch.cuda.current_stream(self.omega.device))
 
     def tighten(self) -> None:
-        """Replace the launch bound n_sub_max by the exact sub-problem count once the asynchronous read-back of
-        the device counter has completed (cheap no-op before that and after it has been applied)."""
+        """Replace the launch bounds (n_sub_max, n_own_items_max) by the exact counts once the asynchronous read-back
+        of the device counters has completed (cheap no-op before that and after it has been applied)."""
         ev = self._n_sub_event
         if ev is None:
             return
@@ -333,6 +340,36 @@ class TrajectoryPlan:
         n = int(self._n_sub_host[0])
         if 0 < n < self.struct.n_sub_max:
             self.struct.n_sub_max = n
+        if self.struct.own_tile:
+            n_items, n_slots = int(self._n_sub_host[1]), int(self._n_sub_host[2])
+            if 0 < n_items <= self.struct.n_own_items_max:
+                self.struct.n_own_items_max = n_items
+                self.own_slots = max(n_slots, 1)
+                self._own_scratch.clear()  # sized by the upper bound until now
+
+    def own_scratch(self, lib, geo, B: int, C: int, layout: int):
+        """Persistent scratch of the owner-tile spread for this (batch, coils, stream): arrival counters (zeroed once,
+        the kernel leaves them zero) followed by the partial-sum slots.  ``None`` when that path does not apply."""
+        if not self.struct.own_tile:
+            return None
+        stream = torch.cuda.current_stream(self.omega.device)
+        key = (B, C, layout, stream.cuda_stream)
+        hit = self._own_scratch.get(key)
+        if hit is None:
+            nbytes, nzero = ctypes.c_size_t(0), ctypes.c_size_t(0)
+            _lib.check(lib.b2n_interp_adjoint_ordered_layout(ctypes.byref(geo.struct), ctypes.byref(self.struct), B, C,
+                                                             layout, self.own_slots, ctypes.byref(nbytes),
+                                                             ctypes.byref(nzero)), "b2n_interp_adjoint_ordered_layout")
+            if not nzero.value:
+                hit = (None, 0)  # another deterministic path (or none) handles this case
+            else:
+                buf = torch.empty(nbytes.value, dtype=torch.uint8, device=self.omega.device)
+                buf[:nzero.value].zero_()
+                hit = (buf, nbytes.value)
+            if len(self._own_scratch) >= 4:
+                self._own_scratch.clear()
+            self._own_scratch[key] = hit
+        return hit
 
 
 _PLAN_FAST: dict = {}  # (id(geo), id(omega), omega._version) -> plan (the plan keeps geo and omega alive)

@@ -377,6 +377,13 @@ int tiled3_adjoint_ordered(const b2n_geom *g, const b2n_points *p, const void *k
 int tiled_adjoint_ordered(const b2n_geom *g, const b2n_points *p, const void *kdata, int64_t B, int64_t C, int layout,
                           void *scratch, size_t scratch_bytes, void *grid, cudaStream_t st);
 
+size_t own_adjoint_bytes(const b2n_geom *g, const b2n_points *p, int64_t B, int64_t C, int layout, int64_t n_slots,
+                         size_t *zero_bytes);
+int own_adjoint(const b2n_geom *g, const b2n_points *p, const void *kdata, int64_t B, int64_t C, int layout,
+                void *scratch, size_t scratch_bytes, void *grid, cudaStream_t st);
+extern int g_adj_owned;
+extern int g_own_cap;
+
 long long *g_trace_buffer = nullptr;
 int64_t g_trace_capacity = 0;
 extern int g_adj_rowwarp;
@@ -386,7 +393,7 @@ extern int g_fast_fft;
 int g_pdl = 1;
 int g_prefetch = 19;
 int g_zero_kernel = 1;
-static int g_options[B2N_OPT_COUNT] = {1, 0, 0, 0, 1, 1, 19};
+static int g_options[B2N_OPT_COUNT] = {1, 0, 0, 0, 1, 1, 19, 1, 64};
 
 // With very few 2-D (batch, coil) rows most coil lanes of a tiled gather CTA idle while its per-point cost stays the
 // same: the one-thread-per-point kernel (k_fwd_point6_2d) wins up to 3 rows (16 vs 29 us for one row, 30 vs 41 us for
@@ -416,6 +423,8 @@ extern "C" int b2n_set_option(int option, int value) {
     g_counters_early = value != 3;  // 3: ... but the coil-sum counters are zeroed right before their kernel (A/B)
   }
   if (option == B2N_OPT_FFT_PREFETCH) g_prefetch = value;
+  if (option == B2N_OPT_ADJ_OWNED) g_adj_owned = value;
+  if (option == B2N_OPT_OWN_CAP) g_own_cap = value;
   return 0;
 }
 
@@ -474,16 +483,35 @@ extern "C" int b2n_interp_adjoint_ordered_bytes(const b2n_geom *geom, const b2n_
     return fail_arg(B2N_E_ARG, "n_batch=%lld n_coils=%lld", (long long)n_batch, (long long)n_coils);
   *bytes = 0;
   if (g_options[B2N_OPT_TILED_KERNELS]) {
-    *bytes = tiled_adjoint_ordered_bytes(geom, pts, n_batch, n_coils, grid_layout);
+    *bytes = own_adjoint_bytes(geom, pts, n_batch, n_coils, grid_layout, 0, nullptr);
+    if (!*bytes) *bytes = tiled_adjoint_ordered_bytes(geom, pts, n_batch, n_coils, grid_layout);
     if (!*bytes) *bytes = tiled3_adjoint_ordered_bytes(geom, pts, n_batch, n_coils, grid_layout);
   }
   return 0;
+}
+
+extern "C" int b2n_interp_adjoint_ordered_layout(const b2n_geom *geom, const b2n_points *pts, int64_t n_batch,
+                                                 int64_t n_coils, int grid_layout, int64_t n_slots, size_t *bytes,
+                                                 size_t *zero_bytes) {
+  if (!geom || !pts || !bytes || !zero_bytes) return fail_arg(B2N_E_ARG, "NULL geom/pts/bytes/zero_bytes");
+  if (n_batch < 1 || n_coils < 1)
+    return fail_arg(B2N_E_ARG, "n_batch=%lld n_coils=%lld", (long long)n_batch, (long long)n_coils);
+  *bytes = *zero_bytes = 0;
+  if (!g_options[B2N_OPT_TILED_KERNELS]) return 0;
+  *bytes = own_adjoint_bytes(geom, pts, n_batch, n_coils, grid_layout, n_slots, zero_bytes);
+  if (*bytes) return 0;
+  return b2n_interp_adjoint_ordered_bytes(geom, pts, n_batch, n_coils, grid_layout, bytes);
 }
 
 extern "C" int b2n_interp_adjoint_ordered(const b2n_geom *geom, const b2n_points *pts, const void *kdata_dev,
                                           int64_t n_batch, int64_t n_coils, int grid_layout, void *scratch_dev,
                                           size_t scratch_bytes, void *grid_dev, void *stream) {
   if (!geom || !pts || !grid_dev || !kdata_dev) return fail_arg(B2N_E_ARG, "NULL geom/pts/grid/kdata");
+  {
+    const int rc = own_adjoint(geom, pts, kdata_dev, n_batch, n_coils, grid_layout, scratch_dev, scratch_bytes, grid_dev,
+                               (cudaStream_t)stream);
+    if (rc != 1) return rc;
+  }
   if (geom->ndim == 3) {
     const int rc = tiled3_adjoint_ordered(geom, pts, kdata_dev, n_batch, n_coils, grid_layout, scratch_dev, scratch_bytes,
                                           grid_dev, (cudaStream_t)stream);

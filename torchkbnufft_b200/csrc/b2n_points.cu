@@ -251,17 +251,180 @@ __global__ void k_export_indices(GeomT<T> g, const T *__restrict__ omega, int64_
   arr_ind[i] = flat;
 }
 
+
+// ---- owner-tile visit lists (output-stationary spread, b2n_interp_own.cu) ----------------------------------------
+// The spread kernel gives every own_tile x own_tile OUTPUT tile of the grid to one warp, which keeps the tile in
+// registers and visits every point whose J x J footprint intersects it.  The lists are derived from the cell-sorted
+// plan without a second sort and without atomics on the visit order: the base cells that can touch a tile form a
+// (T+J-1)^2 window; cell_start gives the sorted slots of each window cell, and the window is walked in a fixed order.
+constexpr int kOwnBuckets = 16;  // LPT buckets of the work items by size (+ one for empty tiles)
+
+struct OwnGeom {
+  int Ky, Kx, nty, ntx, J, T, cap;
+  int64_t n_traj, n_own_tiles;  // tiles per trajectory
+  Tiling tl;                    // tiling of the cell-sorted plan (cell_start index)
+};
+
+B2N_D int own_wrap(int v, int K) { return v < 0 ? v + K : (v >= K ? v - K : v); }
+
+// sorted-slot range of window cell w (row-major over (th+J-1) x (tw+J-1)) of tile (y0, x0) of trajectory traj
+B2N_D void own_window_cell(const OwnGeom &g, const int32_t *__restrict__ cell_start, int64_t traj, int y0, int x0, int ww,
+                           int w, int &s0, int &s1, int &ry, int &rx) {
+  const int wy = w / ww, wx = w - wy * ww;
+  ry = wy - (g.J - 1);
+  rx = wx - (g.J - 1);
+  int64_t cell[B2N_MAX_DIMS] = {own_wrap(y0 + ry, g.Ky), own_wrap(x0 + rx, g.Kx), 0};
+  const int64_t idx = traj * g.tl.n_cells + tiled_cell(g.tl, cell);
+  s0 = cell_start[idx];
+  s1 = cell_start[idx + 1];
+}
+
+B2N_D int own_bucket(int size, int cap) { return size <= 0 ? kOwnBuckets : (cap - size) * kOwnBuckets / cap; }
+
+// one warp per output tile: number of visits, number of work items, LPT histogram
+__global__ void __launch_bounds__(256) k_own_count(OwnGeom g, const int32_t *__restrict__ cell_start,
+                                                   int4 *__restrict__ tiles, int32_t *__restrict__ hist) {
+  const int64_t t = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (t >= g.n_traj * g.n_own_tiles) return;
+  const int64_t traj = t / g.n_own_tiles, tid = t - traj * g.n_own_tiles;
+  const int ty = (int)(tid / g.ntx), tx = (int)(tid - (int64_t)ty * g.ntx);
+  const int y0 = ty * g.T, x0 = tx * g.T;
+  const int th = min(g.T, g.Ky - y0), tw = min(g.T, g.Kx - x0);
+  const int wh = th + g.J - 1, ww = tw + g.J - 1;
+  int n = 0;
+  for (int w = lane; w < wh * ww; w += 32) {
+    int s0, s1, ry, rx;
+    own_window_cell(g, cell_start, traj, y0, x0, ww, w, s0, s1, ry, rx);
+    n += s1 - s0;
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) n += __shfl_xor_sync(0xffffffffu, n, off);
+  if (lane == 0) {
+    const int nch = n > 0 ? (n + g.cap - 1) / g.cap : 1;
+    tiles[t] = make_int4(n, 0, nch, -1);
+    if (nch > 1) atomicAdd(&hist[0], nch - 1);  // full chunks
+    // the short last chunk of a multi-chunk tile goes with the full ones: it must not be the item that arrives last
+    // and merges the tile's partial sums at the very end of the launch
+    atomicAdd(&hist[nch > 1 ? 0 : own_bucket(n, g.cap)], 1);
+  }
+}
+
+// single CTA: exclusive scans over the tiles (first visit, first partial slot), bucket bases, totals
+__global__ void __launch_bounds__(1024) k_own_scan(int64_t n_tiles_all, int4 *__restrict__ tiles,
+                                                   int32_t *__restrict__ hist, int32_t *__restrict__ bucket_base,
+                                                   int32_t *__restrict__ bucket_fill, int32_t *__restrict__ counts) {
+  __shared__ int s_v[1024], s_s[1024];
+  __shared__ int run_v, run_s;
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    run_v = 0;
+    run_s = 0;
+    int acc = 0;
+    for (int b = 0; b <= kOwnBuckets; ++b) {
+      bucket_base[b] = acc;
+      acc += hist[b];
+      bucket_fill[b] = 0;
+    }
+    counts[0] = acc;
+  }
+  __syncthreads();
+  for (int64_t base = 0; base < n_tiles_all; base += 1024) {
+    const int64_t t = base + tid;
+    int4 ti = make_int4(0, 0, 0, -1);
+    if (t < n_tiles_all) ti = tiles[t];
+    const int v = ti.x, sl = ti.z > 1 ? ti.z : 0;
+    s_v[tid] = v;
+    s_s[tid] = sl;
+    __syncthreads();
+    for (int off = 1; off < 1024; off <<= 1) {  // Hillis-Steele inclusive scan of both arrays
+      const int a = tid >= off ? s_v[tid - off] : 0, b = tid >= off ? s_s[tid - off] : 0;
+      __syncthreads();
+      s_v[tid] += a;
+      s_s[tid] += b;
+      __syncthreads();
+    }
+    if (t < n_tiles_all) {
+      ti.y = run_v + s_v[tid] - v;
+      ti.w = sl ? run_s + s_s[tid] - sl : -1;
+      tiles[t] = ti;
+    }
+    __syncthreads();
+    if (tid == 1023) {
+      run_v += s_v[1023];
+      run_s += s_s[1023];
+    }
+    __syncthreads();
+  }
+  if (tid == 0) counts[1] = run_s;
+}
+
+// one warp per output tile: write its visits in window order and its work items into their LPT bucket
+__global__ void __launch_bounds__(256) k_own_fill(OwnGeom g, const int32_t *__restrict__ cell_start,
+                                                  const int32_t *__restrict__ perm, const int4 *__restrict__ tiles,
+                                                  const int32_t *__restrict__ bucket_base,
+                                                  int32_t *__restrict__ bucket_fill, int4 *__restrict__ visits,
+                                                  int4 *__restrict__ items) {
+  const int64_t t = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (t >= g.n_traj * g.n_own_tiles) return;
+  const int64_t traj = t / g.n_own_tiles, tid = t - traj * g.n_own_tiles;
+  const int ty = (int)(tid / g.ntx), tx = (int)(tid - (int64_t)ty * g.ntx);
+  const int y0 = ty * g.T, x0 = tx * g.T;
+  const int th = min(g.T, g.Ky - y0), tw = min(g.T, g.Kx - x0);
+  const int wh = th + g.J - 1, ww = tw + g.J - 1;
+  const int4 ti = tiles[t];
+  int run = ti.y;
+  for (int w0 = 0; w0 < wh * ww; w0 += 32) {
+    const int w = w0 + lane;
+    int s0 = 0, s1 = 0, ry = 0, rx = 0;
+    if (w < wh * ww) own_window_cell(g, cell_start, traj, y0, x0, ww, w, s0, s1, ry, rx);
+    const int cnt = s1 - s0;
+    int incl = cnt;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const int up = __shfl_up_sync(0xffffffffu, incl, off);
+      if (lane >= off) incl += up;
+    }
+    int4 *dst = visits + run + incl - cnt;
+    for (int k = 0; k < cnt; ++k) dst[k] = make_int4(s0 + k, perm[s0 + k], ry, rx);
+    run += __shfl_sync(0xffffffffu, incl, 31);
+  }
+  for (int j = lane; j < ti.z; j += 32) {
+    const int size = max(0, min(g.cap, ti.x - j * g.cap));
+    const int b = ti.z > 1 ? 0 : own_bucket(size, g.cap);
+    const int pos = bucket_base[b] + atomicAdd(&bucket_fill[b], 1);
+    items[pos] = make_int4((int)t, ti.y + j * g.cap, size | (j << 12), (ty << 16) | tx);
+  }
+}
+
 // ---- workspace carving --------------------------------------------------------
 struct Carve {
   size_t perm, inv_perm, base, coef, phase, cell_start, keys, sub_tile, sub_start, sub_count, n_sub;
   size_t keys_in, idx_in, idx_out, chunks, offsets, tmp_tile, tmp_start, tmp_count, sub_keys, sub_keys_out, sub_idx,
       sub_order, cub, total, cub_bytes;
+  size_t own_visits, own_items, own_tiles, own_counts, own_hist;
+  int64_t n_own_items_max, n_own_tiles;  // per trajectory; 0 = no visit lists for this geometry
+  int own_nt[2], own_cap;
   int64_t n_sub_max;
   int sub_cap;
   Tiling tiling;
 };
 
 static int default_sub_cap(int ndim) { return ndim == 3 ? 128 : 128; }
+
+constexpr int kOwnTile = 8;
+int g_own_cap = 64;  // visits per work item of the owner-tile spread (b2n_set_option(B2N_OPT_OWN_CAP) for A/B)
+// Visit lists are built for what the owner-tile spread handles: 2-D complex64, J = 6, and grids whose footprints
+// touch at most two tiles per dimension (every K_d >= 16; a last, partial tile of at least J-1 cells).
+static bool own_eligible(const b2n_geom *g) {
+  if (g->ndim != 2 || g->dtype != B2N_C64) return false;
+  for (int d = 0; d < 2; ++d) {
+    const int64_t K = g->grid_size[d], rem = K % kOwnTile;
+    if (g->numpoints[d] != 6 || K < 16 || (rem != 0 && rem < g->numpoints[d] - 1)) return false;
+  }
+  return true;
+}
 
 static int sort_bits(int64_t n_keys) {
   int bits = 1;
@@ -326,6 +489,20 @@ static int carve(const b2n_geom *g, int64_t M, int64_t n_traj, Carve *c) {
   if (sub_sort_bytes > cub_bytes) cub_bytes = sub_sort_bytes;
   c->cub_bytes = cub_bytes;
   c->cub = take(cub_bytes + 256);
+  c->n_own_tiles = 0;
+  c->n_own_items_max = 0;
+  if (own_eligible(g) && 4 * total < ((int64_t)1 << 31) - 1) {
+    c->own_nt[0] = (int)ceil_div(g->grid_size[0], kOwnTile);
+    c->own_nt[1] = (int)ceil_div(g->grid_size[1], kOwnTile);
+    c->n_own_tiles = (int64_t)c->own_nt[0] * c->own_nt[1];
+    c->own_cap = g_own_cap < 8 ? 8 : (g_own_cap > 4095 ? 4095 : g_own_cap);
+    c->n_own_items_max = c->n_own_tiles * n_traj + 4 * total / c->own_cap + 1;
+    c->own_visits = take(sizeof(int4) * (size_t)(4 * total + 1));
+    c->own_items = take(sizeof(int4) * (size_t)c->n_own_items_max);
+    c->own_tiles = take(sizeof(int4) * (size_t)(c->n_own_tiles * n_traj));
+    c->own_counts = take(sizeof(int32_t) * 2);
+    c->own_hist = take(sizeof(int32_t) * 3 * (kOwnBuckets + 1));
+  }
   c->total = off;
   return 0;
 }
@@ -403,6 +580,47 @@ static int build_impl(const b2n_geom *geom, const void *omega, int64_t M, int64_
                                                                              tmp_count, out->sub_tile, out->sub_start,
                                                                              out->sub_count);
   B2N_LAUNCH_OK("k_sub_gather");
+  out->own_tile = 0;
+  out->own_cap = 0;
+  out->n_own_tiles[0] = out->n_own_tiles[1] = 0;
+  out->n_own_items_max = 0;
+  out->own_visits = out->own_items = out->own_tiles = nullptr;
+  out->own_counts = nullptr;
+  if (c.n_own_tiles > 0) {
+    OwnGeom og;
+    og.Ky = (int)g.K[0];
+    og.Kx = (int)g.K[1];
+    og.nty = c.own_nt[0];
+    og.ntx = c.own_nt[1];
+    og.J = g.J[0];
+    og.T = kOwnTile;
+    og.cap = c.own_cap;
+    og.n_traj = n_traj;
+    og.n_own_tiles = c.n_own_tiles;
+    og.tl = tl;
+    const int64_t nt_all = c.n_own_tiles * n_traj;
+    int4 *tiles = (int4 *)(ws + c.own_tiles);
+    int32_t *hist = (int32_t *)(ws + c.own_hist), *bucket_base = hist + (kOwnBuckets + 1),
+            *bucket_fill = bucket_base + (kOwnBuckets + 1);
+    B2N_CUDA_OK(cudaMemsetAsync(hist, 0, sizeof(int32_t) * 3 * (kOwnBuckets + 1), st));
+    k_own_count<<<(unsigned)ceil_div(nt_all * 32, threads), threads, 0, st>>>(og, out->cell_start, tiles, hist);
+    B2N_LAUNCH_OK("k_own_count");
+    k_own_scan<<<1, 1024, 0, st>>>(nt_all, tiles, hist, bucket_base, bucket_fill, (int32_t *)(ws + c.own_counts));
+    B2N_LAUNCH_OK("k_own_scan");
+    k_own_fill<<<(unsigned)ceil_div(nt_all * 32, threads), threads, 0, st>>>(
+        og, out->cell_start, out->perm, tiles, bucket_base, bucket_fill, (int4 *)(ws + c.own_visits),
+        (int4 *)(ws + c.own_items));
+    B2N_LAUNCH_OK("k_own_fill");
+    out->own_tile = kOwnTile;
+    out->own_cap = og.cap;
+    out->n_own_tiles[0] = c.own_nt[0];
+    out->n_own_tiles[1] = c.own_nt[1];
+    out->n_own_items_max = c.n_own_items_max;
+    out->own_visits = ws + c.own_visits;
+    out->own_items = ws + c.own_items;
+    out->own_tiles = tiles;
+    out->own_counts = (int32_t *)(ws + c.own_counts);
+  }
   return 0;
 }
 

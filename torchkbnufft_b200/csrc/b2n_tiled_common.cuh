@@ -27,6 +27,10 @@ B2N_D unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shar
 B2N_D void cp_async4(void *dst, const void *src) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(smem_u32(dst)), "l"(src) : "memory");
 }
+B2N_D void cp_async4z(void *dst, const void *src, bool valid) {
+  const int src_size = valid ? 4 : 0;  // 0 -> destination bytes are zero-filled
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;\n" ::"r"(smem_u32(dst)), "l"(src), "r"(src_size) : "memory");
+}
 B2N_D void cp_async8(void *dst, const void *src, bool valid) {
   const int src_size = valid ? 8 : 0;  // 0 -> destination bytes are zero-filled
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(smem_u32(dst)), "l"(src), "r"(src_size) : "memory");
