@@ -104,15 +104,16 @@ typedef struct b2n_points {
   int32_t *tile_sub_start; /* [n_traj*prod(n_tiles)] first rank of each tile; the last tile ends at *n_sub */
   /* Owner-tile visit lists for the output-stationary spread (b2n_interp_adjoint_ordered; 2-D complex64 J = 6 plans on
    * grids with every K_d >= 16 and K_d % 8 in {0, 5, 6, 7}; own_tile == 0 and NULL pointers otherwise).  The grid is cut
-   * into own_tile x own_tile OUTPUT tiles; a "visit" is one (point, output tile) pair whose J x J footprint
-   * intersects the tile (1, 2 or 4 per point); the visits of a tile are listed in a fixed order (window cell
+   * into OUTPUT tiles of own_tile rows x 8 columns (own_tile = 4 when K_y is a multiple of 4 and B2N_OPT_OWN_ROWS is 4,
+   * else 8); a "visit" is one (point, output tile) pair whose J x J footprint intersects the tile (at most 6 per
+   * point with 4-row tiles, 4 with 8-row tiles); the visits of a tile are listed in a fixed order (window cell
    * row-major, then sorted slot) and cut into work items of at most own_cap visits.  Every output tile has at
    * least one item (an empty one writes zeros), so the spread needs no zero-initialised grid and no atomics. */
-  int32_t own_tile;          /* 8, or 0 when the lists were not built */
+  int32_t own_tile;          /* rows of an output tile (4 or 8; 8 columns), or 0 when the lists were not built */
   int32_t own_cap;           /* max visits per work item */
-  int32_t n_own_tiles[2];    /* output tiles per dimension = ceil(K_d / own_tile) */
+  int32_t n_own_tiles[2];    /* output tiles per dimension = {ceil(K_y / own_tile), ceil(K_x / 8)} */
   int64_t n_own_items_max;   /* capacity of own_items (upper bound on own_counts[0]) */
-  void *own_visits;          /* int32x4 [<= 4*n_traj*M]: {sorted slot, sample index inside its trajectory, ry, rx} with
+  void *own_visits;          /* int32x4 [<= 6*n_traj*M]: {sorted slot, sample index inside its trajectory, ry, rx} with
                                 (ry, rx) = base cell minus tile origin, unwrapped, each in [-(J-1), own_tile-1] */
   void *own_items;           /* int32x4 [n_own_items_max]: {traj*prod(n_own_tiles) + tile, first visit, visits | chunk
                                 index inside the tile << 12, tile row << 16 | tile column}, longest first */
@@ -145,6 +146,8 @@ enum b2n_option {
   B2N_OPT_ADJ_OWNED = 7, /* 1 (default): b2n_interp_adjoint_ordered uses the output-stationary owner-tile spread where
                             the plan carries visit lists (2-D complex64 J = 6); 0: the scratch-tile + merge kernels */
   B2N_OPT_OWN_CAP = 8, /* visits per work item of the owner-tile spread, read when a plan is built (default 64) */
+  B2N_OPT_OWN_ROWS = 9, /* rows of an output tile of the owner-tile spread, read when a plan is built: 4 (default; one
+                           branch-free inner loop) or 8 (row-window classes) */
   B2N_OPT_COUNT
 };
 B2N_API int b2n_set_option(int option, int value);

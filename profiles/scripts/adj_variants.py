@@ -1,6 +1,6 @@
 """Adjoint-spread variants timed alone at 16 coils, in one process: the shared-memory tiled kernels
 (B2N_OPT_ADJ_ROW_OWNERSHIP values) and the owner-tile register spread with several work-item caps.
-python profiles/scripts/adj_variants.py [cfg2 cfg5 ...] [--variants=0,3,4] [--caps=32,64,128] [--coils=16]"""
+python profiles/scripts/adj_variants.py [cfg2 cfg5 ...] [--variants=0,3,4] [--caps=32,64,128] [--rows=4,8] [--owned=1,5] [--coils=16]"""
 import os, statistics, sys
 import numpy as np, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -23,7 +23,7 @@ def timeit(fn, reps=20, warm=3):
         ts.append(a.elapsed_time(b) * 1e3)
     return statistics.median(ts)
 
-variants, caps, names, coils, owned = [0], [32, 64, 128], [], [16], [1]
+variants, caps, names, coils, owned, rows_list = [0], [32, 64, 128], [], [16], [1], [4]
 for a in sys.argv[1:]:
     if a.startswith("--variants="):
         variants = [int(v) for v in a.split("=")[1].split(",") if v]
@@ -31,6 +31,8 @@ for a in sys.argv[1:]:
         caps = [int(v) for v in a.split("=")[1].split(",") if v]
     elif a.startswith("--owned="):
         owned = [int(v) for v in a.split("=")[1].split(",") if v]
+    elif a.startswith("--rows="):
+        rows_list = [int(v) for v in a.split("=")[1].split(",") if v]
     elif a.startswith("--coils="):
         coils = [int(v) for v in a.split("=")[1].split(",") if v]
     else:
@@ -55,7 +57,8 @@ for name in names or ["cfg2"]:
             print(f"{name} B={B} C={C} tiled variant {v}: adjoint interp {timeit(fn):8.1f} us   rel diff {err:.2e}", flush=True)
         lib.b2n_set_option(_lib.OPT_ADJ_ROW_OWNERSHIP, 0)
         eng_interp.owned_spread = True
-        for cap, ow in [(c, o) for o in owned for c in caps]:
+        for rows, cap, ow in [(r, c, o) for r in rows_list for o in owned for c in caps]:
+            lib.b2n_set_option(_lib.OPT_OWN_ROWS, rows)
             lib.b2n_set_option(_lib.OPT_ADJ_OWNED, ow)
             lib.b2n_set_option(_lib.OPT_OWN_CAP, cap)
             tkbn.clear_caches()
@@ -66,8 +69,9 @@ for name in names or ["cfg2"]:
             from torchkbnufft_b200._nufft import plan as P
             pl = list(P._PLAN_CACHE.values())[-1]
             fn(); torch.cuda.synchronize(); fn()
-            print(f"{name} B={B} C={C} owner tiles (opt {ow}) cap {cap:4d}: adjoint interp {timeit(fn):8.1f} us   rel diff {err:.2e} "
+            print(f"{name} B={B} C={C} owner tiles rows {rows} (opt {ow}) cap {cap:4d}: adjoint interp {timeit(fn):8.1f} us   rel diff {err:.2e} "
                   f"bit-reproducible {same} items {pl.struct.n_own_items_max} slots {pl.own_slots}", flush=True)
         lib.b2n_set_option(_lib.OPT_OWN_CAP, 64)
+        lib.b2n_set_option(_lib.OPT_OWN_ROWS, 4)
         lib.b2n_set_option(_lib.OPT_ADJ_OWNED, 1)
         tkbn.clear_caches()

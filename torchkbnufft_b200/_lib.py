@@ -26,6 +26,7 @@ OPT_PDL = 5
 OPT_FFT_PREFETCH = 6
 OPT_ADJ_OWNED = 7
 OPT_OWN_CAP = 8
+OPT_OWN_ROWS = 9
 
 _CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")
 LIB_PATH = os.path.join(_CSRC, "libb200nufft.so")

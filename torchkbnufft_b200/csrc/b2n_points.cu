@@ -260,7 +260,7 @@ __global__ void k_export_indices(GeomT<T> g, const T *__restrict__ omega, int64_
 constexpr int kOwnBuckets = 16;  // LPT buckets of the work items by size (+ one for empty tiles)
 
 struct OwnGeom {
-  int Ky, Kx, nty, ntx, J, T, cap;
+  int Ky, Kx, nty, ntx, J, Ty, Tx, cap;  // Ty x Tx cells per output tile
   int64_t n_traj, n_own_tiles;  // tiles per trajectory
   Tiling tl;                    // tiling of the cell-sorted plan (cell_start index)
 };
@@ -289,8 +289,8 @@ __global__ void __launch_bounds__(256) k_own_count(OwnGeom g, const int32_t *__r
   if (t >= g.n_traj * g.n_own_tiles) return;
   const int64_t traj = t / g.n_own_tiles, tid = t - traj * g.n_own_tiles;
   const int ty = (int)(tid / g.ntx), tx = (int)(tid - (int64_t)ty * g.ntx);
-  const int y0 = ty * g.T, x0 = tx * g.T;
-  const int th = min(g.T, g.Ky - y0), tw = min(g.T, g.Kx - x0);
+  const int y0 = ty * g.Ty, x0 = tx * g.Tx;
+  const int th = min(g.Ty, g.Ky - y0), tw = min(g.Tx, g.Kx - x0);
   const int wh = th + g.J - 1, ww = tw + g.J - 1;
   int n = 0;
   for (int w = lane; w < wh * ww; w += 32) {
@@ -370,8 +370,8 @@ __global__ void __launch_bounds__(256) k_own_fill(OwnGeom g, const int32_t *__re
   if (t >= g.n_traj * g.n_own_tiles) return;
   const int64_t traj = t / g.n_own_tiles, tid = t - traj * g.n_own_tiles;
   const int ty = (int)(tid / g.ntx), tx = (int)(tid - (int64_t)ty * g.ntx);
-  const int y0 = ty * g.T, x0 = tx * g.T;
-  const int th = min(g.T, g.Ky - y0), tw = min(g.T, g.Kx - x0);
+  const int y0 = ty * g.Ty, x0 = tx * g.Tx;
+  const int th = min(g.Ty, g.Ky - y0), tw = min(g.Tx, g.Kx - x0);
   const int wh = th + g.J - 1, ww = tw + g.J - 1;
   const int4 ti = tiles[t];
   int run = ti.y;
@@ -405,7 +405,7 @@ struct Carve {
       sub_order, cub, total, cub_bytes;
   size_t own_visits, own_items, own_tiles, own_counts, own_hist;
   int64_t n_own_items_max, n_own_tiles;  // per trajectory; 0 = no visit lists for this geometry
-  int own_nt[2], own_cap;
+  int own_nt[2], own_cap, own_rows;
   int64_t n_sub_max;
   int sub_cap;
   Tiling tiling;
@@ -413,14 +413,19 @@ struct Carve {
 
 static int default_sub_cap(int ndim) { return ndim == 3 ? 128 : 128; }
 
-constexpr int kOwnTile = 8;
+constexpr int kOwnTileCols = 8;
 int g_own_cap = 64;  // visits per work item of the owner-tile spread (b2n_set_option(B2N_OPT_OWN_CAP) for A/B)
-// Visit lists are built for what the owner-tile spread handles: 2-D complex64, J = 6, and grids whose footprints
-// touch at most two tiles per dimension (every K_d >= 16; a last, partial tile of at least J-1 cells).
+int g_own_rows = 4;  // rows of an output tile, 4 or 8 (B2N_OPT_OWN_ROWS), read when a plan is built
+// Visit lists are built for what the owner-tile spread handles: 2-D complex64, J = 6, and grids on which a footprint
+// touches a bounded number of tiles: two per dimension with 8 cells per tile (every K_d >= 16; a last, partial tile of
+// at least J-1 cells), three tile rows with 4-row tiles (K_y a multiple of 4).  own_visits_per_point is that bound.
+static int own_rows(const b2n_geom *g) { return g_own_rows == 4 && g->grid_size[0] % 4 == 0 ? 4 : 8; }
+static int own_visits_per_point(const b2n_geom *g) { return own_rows(g) == 4 ? 6 : 4; }
 static bool own_eligible(const b2n_geom *g) {
   if (g->ndim != 2 || g->dtype != B2N_C64) return false;
   for (int d = 0; d < 2; ++d) {
-    const int64_t K = g->grid_size[d], rem = K % kOwnTile;
+    const int T = d == 0 ? own_rows(g) : kOwnTileCols;
+    const int64_t K = g->grid_size[d], rem = K % T;
     if (g->numpoints[d] != 6 || K < 16 || (rem != 0 && rem < g->numpoints[d] - 1)) return false;
   }
   return true;
@@ -491,13 +496,15 @@ static int carve(const b2n_geom *g, int64_t M, int64_t n_traj, Carve *c) {
   c->cub = take(cub_bytes + 256);
   c->n_own_tiles = 0;
   c->n_own_items_max = 0;
-  if (own_eligible(g) && 4 * total < ((int64_t)1 << 31) - 1) {
-    c->own_nt[0] = (int)ceil_div(g->grid_size[0], kOwnTile);
-    c->own_nt[1] = (int)ceil_div(g->grid_size[1], kOwnTile);
+  const int64_t vpp = own_visits_per_point(g);
+  if (own_eligible(g) && vpp * total < ((int64_t)1 << 31) - 1) {
+    c->own_rows = own_rows(g);
+    c->own_nt[0] = (int)ceil_div(g->grid_size[0], c->own_rows);
+    c->own_nt[1] = (int)ceil_div(g->grid_size[1], kOwnTileCols);
     c->n_own_tiles = (int64_t)c->own_nt[0] * c->own_nt[1];
     c->own_cap = g_own_cap < 8 ? 8 : (g_own_cap > 4095 ? 4095 : g_own_cap);
-    c->n_own_items_max = c->n_own_tiles * n_traj + 4 * total / c->own_cap + 1;
-    c->own_visits = take(sizeof(int4) * (size_t)(4 * total + 1));
+    c->n_own_items_max = c->n_own_tiles * n_traj + vpp * total / c->own_cap + 1;
+    c->own_visits = take(sizeof(int4) * (size_t)(vpp * total + 1));
     c->own_items = take(sizeof(int4) * (size_t)c->n_own_items_max);
     c->own_tiles = take(sizeof(int4) * (size_t)(c->n_own_tiles * n_traj));
     c->own_counts = take(sizeof(int32_t) * 2);
@@ -593,7 +600,8 @@ static int build_impl(const b2n_geom *geom, const void *omega, int64_t M, int64_
     og.nty = c.own_nt[0];
     og.ntx = c.own_nt[1];
     og.J = g.J[0];
-    og.T = kOwnTile;
+    og.Ty = c.own_rows;
+    og.Tx = kOwnTileCols;
     og.cap = c.own_cap;
     og.n_traj = n_traj;
     og.n_own_tiles = c.n_own_tiles;
@@ -611,7 +619,7 @@ static int build_impl(const b2n_geom *geom, const void *omega, int64_t M, int64_
         og, out->cell_start, out->perm, tiles, bucket_base, bucket_fill, (int4 *)(ws + c.own_visits),
         (int4 *)(ws + c.own_items));
     B2N_LAUNCH_OK("k_own_fill");
-    out->own_tile = kOwnTile;
+    out->own_tile = c.own_rows;
     out->own_cap = og.cap;
     out->n_own_tiles[0] = c.own_nt[0];
     out->n_own_tiles[1] = c.own_nt[1];
