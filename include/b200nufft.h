@@ -32,7 +32,7 @@ extern "C" {
 #define B2N_API
 #endif
 
-#define B2N_ABI_VERSION 3
+#define B2N_ABI_VERSION 4
 #define B2N_MAX_DIMS 3
 #define B2N_MAX_NUMPOINTS 16 /* max neighbours J per dimension */
 
@@ -64,6 +64,14 @@ typedef struct b2n_geom {
   int64_t table_len[B2N_MAX_DIMS];      /* J_d*L_d + 1 */
   const void *table_dev[B2N_MAX_DIMS];  /* device, interleaved complex of `dtype` */
   double n_shift[B2N_MAX_DIMS];         /* fftshift phase offsets (values of the real-dtype buffer) */
+  /* Optional: the tables the reference builds are a REAL kernel times a linear phase,
+   * table_d[i] = r_d[i] * exp(-1i * table_phase[d] * x_i), x_i = i / L_d - J_d / 2, table_phase[d] = pi (N_d - 1) / K_d
+   * (torchkbnufft/_nufft/utils.py:160-204, Fessler's column trick).  When the caller has verified that for its
+   * tables it passes r_d (device, real of the same precision, table_len[d] entries) and the slopes; the spread then
+   * works with real weights (half the arithmetic): the phase factors into a per-point, a per-grid-cell and a wrap-sign
+   * part.  NULL pointers = tables are used as they are. */
+  const void *rtable_dev[B2N_MAX_DIMS];
+  double table_phase[B2N_MAX_DIMS];
 } b2n_geom;
 
 /* A trajectory plan: points sorted by the TILE of their wrapped base grid cell (then by
@@ -103,23 +111,39 @@ typedef struct b2n_points {
                           are ordered longest-first for load balance) */
   int32_t *tile_sub_start; /* [n_traj*prod(n_tiles)] first rank of each tile; the last tile ends at *n_sub */
   /* Owner-tile visit lists for the output-stationary spread (b2n_interp_adjoint_ordered; 2-D complex64 J = 6 plans on
-   * grids with every K_d >= 16 and K_d % 8 in {0, 5, 6, 7}; own_tile == 0 and NULL pointers otherwise).  The grid is cut
-   * into OUTPUT tiles of own_tile rows x 8 columns (own_tile = 4 when K_y is a multiple of 4 and B2N_OPT_OWN_ROWS is 4,
-   * else 8); a "visit" is one (point, output tile) pair whose J x J footprint intersects the tile (at most 6 per
-   * point with 4-row tiles, 4 with 8-row tiles); the visits of a tile are listed in a fixed order (window cell
+   * grids with every K_d >= 16 whose geometry carries rtable_dev and power-of-two L_d, so that the table index of
+   * neighbour j is exactly that of neighbour 0 minus j L_d; own_tile == 0 and NULL pointers otherwise).  The grid is cut
+   * into OUTPUT tiles of own_tile = 4 rows x 8 columns; a "visit" is one (point, output tile) pair whose J x J
+   * footprint intersects the tile (3.66 per point on average, at most 6, or 12 where the last tile of an axis has
+   * fewer than J - 1 cells); the visits of a tile are listed in a fixed order (window cell
    * row-major, then sorted slot) and cut into work items of at most own_cap visits.  Every output tile has at
    * least one item (an empty one writes zeros), so the spread needs no zero-initialised grid and no atomics. */
-  int32_t own_tile;          /* rows of an output tile (4 or 8; 8 columns), or 0 when the lists were not built */
+  int32_t own_tile;          /* rows of an output tile (4; 8 columns), or 0 when the lists were not built */
   int32_t own_cap;           /* max visits per work item */
   int32_t n_own_tiles[2];    /* output tiles per dimension = {ceil(K_y / own_tile), ceil(K_x / 8)} */
   int64_t n_own_items_max;   /* capacity of own_items (upper bound on own_counts[0]) */
-  void *own_visits;          /* int32x4 [<= 6*n_traj*M]: {sorted slot, sample index inside its trajectory, ry, rx} with
-                                (ry, rx) = base cell minus tile origin, unwrapped, each in [-(J-1), own_tile-1] */
+  void *own_visits;          /* 64-byte records [<= 6*n_traj*M, see above]: float hy[4] (row weights r_y[row - ry]),
+                                float hx[8] (column weights +-r_x[column - rx]; zero outside the footprint; the sign
+                                is negative when the footprint wrapped around the grid and exp(1i table_phase K) =
+                                -1), int32 sample index inside its trajectory, 12 unused bytes; (ry, rx) = base
+                                cell minus tile origin */
   void *own_items;           /* int32x4 [n_own_items_max]: {traj*prod(n_own_tiles) + tile, first visit, visits | chunk
                                 index inside the tile << 12, tile row << 16 | tile column}, longest first */
   void *own_tiles;           /* int32x4 [n_traj*prod(n_own_tiles)]: {visits, first visit, chunks, first partial-sum slot
                                 (-1 for single-chunk tiles)} */
-  int32_t *own_counts;       /* device: [0] = items in use, [1] = partial-sum slots in use */
+  int32_t *own_counts;       /* device: [0] = items in use, [1] = partial-sum slots in use, [2] = exception points */
+  float *own_hw;             /* [n_traj*M][12]: r_y[0..5], r_x[0..5] of the point's neighbours */
+  void *own_fac;             /* complex64 [n_traj*M]: conj of the point's phase factor (adjoint form): fftshift phase
+                                times exp(-1i sum_d table_phase[d] (x_d(neighbour 0) + wrapped base_d)) */
+  void *own_q;               /* complex64 [K_y + K_x]: exp(-1i table_phase[d] cell), the per-cell factor of the adjoint */
+  /* Exception points: the factored phase needs table_index(neighbour j) == table_index(neighbour 0) - j L_d.  That
+   * holds whenever tm - (base + j) is exact in the trajectory's precision; it can fail by one table step for a
+   * point within J cells of the k-space origin whose distance to a neighbour is a rounding tie.  Such points get
+   * zero weights in own_hw / own_visits and are spread afterwards, in list order, with their complex records (coef)
+   * by a fix-up kernel, so the result keeps the reference's table indices for every neighbour. */
+  int32_t *own_exc;          /* [n_own_exc_max] sorted slots of the exception points, ascending */
+  int64_t n_own_exc_max;     /* capacity of own_exc = n_traj*M; a caller that has read own_counts[2] back may lower it
+                                (0 = no fix-up launch) */
 } b2n_points;
 
 /* engine options (process-wide; for A/B measurements and tests) */
@@ -146,8 +170,6 @@ enum b2n_option {
   B2N_OPT_ADJ_OWNED = 7, /* 1 (default): b2n_interp_adjoint_ordered uses the output-stationary owner-tile spread where
                             the plan carries visit lists (2-D complex64 J = 6); 0: the scratch-tile + merge kernels */
   B2N_OPT_OWN_CAP = 8, /* visits per work item of the owner-tile spread, read when a plan is built (default 64) */
-  B2N_OPT_OWN_ROWS = 9, /* rows of an output tile of the owner-tile spread, read when a plan is built: 4 (default; one
-                           branch-free inner loop) or 8 (row-window classes) */
   B2N_OPT_COUNT
 };
 B2N_API int b2n_set_option(int option, int value);
@@ -158,6 +180,8 @@ B2N_API int b2n_get_option(int option);
 B2N_API int b2n_set_trace_buffer(void *records_dev, int64_t capacity);
 
 B2N_API int b2n_abi_version(void);
+/* sizeof(b2n_geom) / sizeof(b2n_points) as compiled into the library: a binding checks its own struct mirrors */
+B2N_API int b2n_struct_sizes(size_t *geom_bytes, size_t *points_bytes);
 B2N_API const char *b2n_last_error(void);
 /* Number of kernels of this library launched by the process so far (every launch of an own kernel counts; memsets and
  * cuFFT do not). */

@@ -58,7 +58,6 @@ for name in names or ["cfg2"]:
         lib.b2n_set_option(_lib.OPT_ADJ_ROW_OWNERSHIP, 0)
         eng_interp.owned_spread = True
         for rows, cap, ow in [(r, c, o) for r in rows_list for o in owned for c in caps]:
-            lib.b2n_set_option(_lib.OPT_OWN_ROWS, rows)
             lib.b2n_set_option(_lib.OPT_ADJ_OWNED, ow)
             lib.b2n_set_option(_lib.OPT_OWN_CAP, cap)
             tkbn.clear_caches()
@@ -72,6 +71,5 @@ for name in names or ["cfg2"]:
             print(f"{name} B={B} C={C} owner tiles rows {rows} (opt {ow}) cap {cap:4d}: adjoint interp {timeit(fn):8.1f} us   rel diff {err:.2e} "
                   f"bit-reproducible {same} items {pl.struct.n_own_items_max} slots {pl.own_slots}", flush=True)
         lib.b2n_set_option(_lib.OPT_OWN_CAP, 64)
-        lib.b2n_set_option(_lib.OPT_OWN_ROWS, 4)
         lib.b2n_set_option(_lib.OPT_ADJ_OWNED, 1)
         tkbn.clear_caches()

@@ -35,10 +35,15 @@ def test_library_exports_every_declared_symbol():
 
 
 def test_struct_layouts_match_header_sizes():
-    # b2n_geom: 2*int32 + 3*int64 + 3*int32 + 3*int32 + 3*int64 + 3*ptr + 3*double
-    assert ctypes.sizeof(_lib.Geom) == 8 + 24 + 12 + 12 + 24 + 24 + 24
-    # ... + the owner-tile visit lists: 4*int32 + int64 + 4*ptr
-    assert ctypes.sizeof(_lib.Points) == 16 + 16 + 12 + 12 + 16 + 13 * 8 + 16 + 8 + 4 * 8
+    # b2n_geom: 2*int32 + 3*int64 + 3*int32 + 3*int32 + 3*int64 + 3*ptr + 3*double + 3*ptr + 3*double
+    assert ctypes.sizeof(_lib.Geom) == 8 + 24 + 12 + 12 + 24 + 24 + 24 + 24 + 24
+    # ... + the owner-tile visit lists: 4*int32 + int64 + 4*ptr + 3*ptr (real-weight records) + ptr + int64 (exceptions)
+    assert ctypes.sizeof(_lib.Points) == 16 + 16 + 12 + 12 + 16 + 13 * 8 + 16 + 8 + 4 * 8 + 3 * 8 + 16
+    # and the library's own sizeof (compiled from the header) agrees with the ctypes mirrors
+    lib = _lib.load()
+    gsz, psz = ctypes.c_size_t(0), ctypes.c_size_t(0)
+    assert lib.b2n_struct_sizes(ctypes.byref(gsz), ctypes.byref(psz)) == 0
+    assert (gsz.value, psz.value) == (ctypes.sizeof(_lib.Geom), ctypes.sizeof(_lib.Points))
 
 
 def test_process_wide_options_defaults_and_round_trip():

@@ -21,6 +21,10 @@ pytestmark = pytest.mark.gpu
 REF_TESTS = os.path.join(ROOT, "oracle", "_ref", "reference_tests")
 FILES = ["test_interp.py", "test_nufft.py", "test_sense_nufft.py", "test_toep.py", "test_dcomp.py", "test_math.py"]
 
+# upstream tests that cannot run anywhere: the pickle they open is not part of the reference checkout either
+# (/root/reference/tests/data holds interp_data.pkl and nufft_data.pkl only), so they fail on the stock package too
+MISSING_UPSTREAM_DATA = {"test_sense_nufft.py": [("test_sense_nufft_accuracy", "sense_nufft_data.pkl")]}
+
 _CONFTEST = '''
 import os, sys
 sys.path.insert(0, {tests!r})
@@ -42,7 +46,11 @@ def test_upstream_test_file_passes_on_the_engine(name, tmp_path):
     os.symlink(os.path.join(REF_TESTS, "tests"), work / "tests")
     env = dict(os.environ, PYTHONDONTWRITEBYTECODE="1")
     env.pop("PYTHONPATH", None)
-    res = subprocess.run([sys.executable, "-m", "pytest", "-p", "no:cacheprovider", "-q", "-x", f"tests/{name}"],
+    deselect = []
+    for test, data in MISSING_UPSTREAM_DATA.get(name, []):
+        if not os.path.exists(os.path.join(REF_TESTS, "tests", "data", data)):
+            deselect += ["--deselect", f"tests/{name}::{test}"]
+    res = subprocess.run([sys.executable, "-m", "pytest", "-p", "no:cacheprovider", "-q", "-x", f"tests/{name}"] + deselect,
                          cwd=work, env=env, capture_output=True, text=True, timeout=1500)
     tail = "\n".join((res.stdout + res.stderr).splitlines()[-25:])
     assert res.returncode == 0, f"upstream {name} failed on the engine:\n{tail}"

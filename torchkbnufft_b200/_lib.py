@@ -16,7 +16,7 @@ MAX_NUMPOINTS = 16
 C64, C128 = 0, 1
 COIL_MAJOR, CHANNEL_LAST = 0, 1
 ADJ_ATOMIC, ADJ_SORTED = 0, 1
-ABI_VERSION = 3
+ABI_VERSION = 4
 OPT_TILED_KERNELS = 0
 OPT_ADJ_ROW_OWNERSHIP = 1
 OPT_FWD_COIL_CHUNK = 2
@@ -26,7 +26,6 @@ OPT_PDL = 5
 OPT_FFT_PREFETCH = 6
 OPT_ADJ_OWNED = 7
 OPT_OWN_CAP = 8
-OPT_OWN_ROWS = 9
 
 _CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")
 LIB_PATH = os.path.join(_CSRC, "libb200nufft.so")
@@ -44,6 +43,8 @@ class Geom(Structure):
         ("table_len", c_int64 * MAX_DIMS),
         ("table_dev", c_void_p * MAX_DIMS),
         ("n_shift", c_double * MAX_DIMS),
+        ("rtable_dev", c_void_p * MAX_DIMS),
+        ("table_phase", c_double * MAX_DIMS),
     ]
 
 
@@ -82,6 +83,11 @@ class Points(Structure):
         ("own_items", c_void_p),
         ("own_tiles", c_void_p),
         ("own_counts", c_void_p),
+        ("own_hw", c_void_p),
+        ("own_fac", c_void_p),
+        ("own_q", c_void_p),
+        ("own_exc", c_void_p),
+        ("n_own_exc_max", c_int64),
     ]
 
 
@@ -93,6 +99,7 @@ class EngineError(RuntimeError):
 _I64P = POINTER(c_int64)
 SIGNATURES = {
     "b2n_abi_version": (c_int, []),
+    "b2n_struct_sizes": (c_int, [POINTER(c_size_t), POINTER(c_size_t)]),
     "b2n_launch_count": (ctypes.c_longlong, []),
     "b2n_last_error": (c_char_p, []),
     "b2n_device_count": (c_int, []),
@@ -150,6 +157,11 @@ def load() -> ctypes.CDLL:
         fn.argtypes = argtypes
     if lib.b2n_abi_version() != ABI_VERSION:
         raise EngineError(f"libb200nufft ABI {lib.b2n_abi_version()} != expected {ABI_VERSION}; rebuild")
+    gsz, psz = c_size_t(0), c_size_t(0)
+    lib.b2n_struct_sizes(ctypes.byref(gsz), ctypes.byref(psz))
+    if gsz.value != ctypes.sizeof(Geom) or psz.value != ctypes.sizeof(Points):
+        raise EngineError(f"struct mirrors out of date: b2n_geom {gsz.value} vs {ctypes.sizeof(Geom)} bytes, "
+                          f"b2n_points {psz.value} vs {ctypes.sizeof(Points)} bytes")
     _lib = lib
     return lib
 

@@ -166,8 +166,47 @@ class Geometry:
             g.table_len[d] = self.tables[d].numel()
             g.table_dev[d] = self.tables[d].data_ptr()
             g.n_shift[d] = self.n_shift[d]
+        # real kernel + linear phase form of the tables (b2n_geom.rtable_dev): checked once per geometry on the host
+        self.rtables = real_table_form(self.tables, self.numpoints, self.table_oversamp, self.grid_size)
+        if self.rtables is not None:
+            for d, (rt, slope) in enumerate(self.rtables):
+                g.rtable_dev[d] = rt.data_ptr()
+                g.table_phase[d] = slope
         self.struct = g
         self.key: tuple = ()
+
+
+REAL_TABLE_TOL = 2e-6  # |table - r exp(-i p x)| / max|table| allowed when the tables are declared to be of that form
+
+
+def real_table_form(tables: Sequence[Tensor], numpoints, table_oversamp, grid_size):
+    """``[(real table on the device, phase slope p_d)]`` if every table is ``r_d[i] exp(-1j p_d x_i)`` with real
+    ``r_d``, ``x_i = i / L_d - J_d / 2`` and ``p_d = pi (N_d - 1) / K_d`` for an integer ``N_d`` -- the form the
+    reference builds (``torchkbnufft/_nufft/utils.py:160-204``) -- else ``None`` (modified tables keep the complex
+    kernels).  One host read of the tables per geometry."""
+    import numpy as np
+    out = []
+    for t, J, L, K in zip(tables, numpoints, table_oversamp, grid_size):
+        tab = t.detach().cpu().numpy().astype(np.complex128)
+        if tab.shape[0] != J * L + 1 or not np.all(np.isfinite(tab)):
+            return None
+        x = np.arange(J * L + 1) / L - J / 2
+        mag = np.abs(tab)
+        big = mag > 0.25 * mag.max()
+        if big.sum() < 4:
+            return None
+        # slope from a least-squares line through the unwrapped phase of the significant entries
+        ang = np.unwrap(np.angle(tab[big]))
+        slope = -np.polyfit(x[big], ang, 1)[0]
+        n_minus_1 = round(slope * K / np.pi)
+        slope = np.pi * n_minus_1 / K
+        real = tab * np.exp(1j * slope * x)
+        scale = mag.max()
+        if scale == 0 or np.abs(real.imag).max() > REAL_TABLE_TOL * scale:
+            return None
+        rdtype = torch.float32 if t.dtype == torch.complex64 else torch.float64
+        out.append((torch.from_numpy(np.ascontiguousarray(real.real)).to(device=t.device, dtype=rdtype), float(slope)))
+    return out
 
 
 _HOST_INTS_FAST: dict = {}  # id(tensor) -> (_version, ints, tensor): identity front for _GRID_SIZE_CACHE
@@ -321,7 +360,7 @@ class TrajectoryPlan:
         self._n_sub_host[0:1].copy_(self.workspace[off:off + 4].view(torch.int32), non_blocking=True)
         if self.struct.own_tile:
             off = int(self.struct.own_counts) - base
-            self._n_sub_host[1:3].copy_(self.workspace[off:off + 8].view(torch.int32), non_blocking=True)
+            self._n_sub_host[1:4].copy_(self.workspace[off:off + 12].view(torch.int32), non_blocking=True)
         self._n_sub_event = torch.cuda.Event()
         self._n_sub_event.record(torch.cuda.current_stream(self.omega.device))
 
@@ -341,11 +380,13 @@ class TrajectoryPlan:
         if 0 < n < self.struct.n_sub_max:
             self.struct.n_sub_max = n
         if self.struct.own_tile:
-            n_items, n_slots = int(self._n_sub_host[1]), int(self._n_sub_host[2])
+            n_items, n_slots, n_exc = (int(v) for v in self._n_sub_host[1:4])
             if 0 < n_items <= self.struct.n_own_items_max:
                 self.struct.n_own_items_max = n_items
                 self.own_slots = max(n_slots, 1)
                 self._own_scratch.clear()  # sized by the upper bound until now
+                if 0 <= n_exc <= self.struct.n_own_exc_max:
+                    self.struct.n_own_exc_max = n_exc  # 0 (the usual case): no fix-up launch from now on
 
     def own_scratch(self, lib, geo, B: int, C: int, layout: int):
         """Persistent scratch of the owner-tile spread for this (batch, coils, stream): arrival counters (zeroed once,

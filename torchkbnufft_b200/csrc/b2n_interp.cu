@@ -383,7 +383,6 @@ int own_adjoint(const b2n_geom *g, const b2n_points *p, const void *kdata, int64
                 void *scratch, size_t scratch_bytes, void *grid, cudaStream_t st);
 extern int g_adj_owned;
 extern int g_own_cap;
-extern int g_own_rows;
 
 long long *g_trace_buffer = nullptr;
 int64_t g_trace_capacity = 0;
@@ -394,7 +393,7 @@ extern int g_fast_fft;
 int g_pdl = 1;
 int g_prefetch = 19;
 int g_zero_kernel = 1;
-static int g_options[B2N_OPT_COUNT] = {1, 0, 0, 0, 1, 1, 19, 1, 64, 4};
+static int g_options[B2N_OPT_COUNT] = {1, 0, 0, 0, 1, 1, 19, 1, 64};
 
 // With very few 2-D (batch, coil) rows most coil lanes of a tiled gather CTA idle while its per-point cost stays the
 // same: the one-thread-per-point kernel (k_fwd_point6_2d) wins up to 3 rows (16 vs 29 us for one row, 30 vs 41 us for
@@ -426,7 +425,6 @@ extern "C" int b2n_set_option(int option, int value) {
   if (option == B2N_OPT_FFT_PREFETCH) g_prefetch = value;
   if (option == B2N_OPT_ADJ_OWNED) g_adj_owned = value;
   if (option == B2N_OPT_OWN_CAP) g_own_cap = value;
-  if (option == B2N_OPT_OWN_ROWS) g_own_rows = value == 8 ? 8 : 4;
   return 0;
 }
 

@@ -54,6 +54,8 @@ template <typename T> struct GeomT {
   int64_t table_len[B2N_MAX_DIMS];
   const cplx<T> *table[B2N_MAX_DIMS];
   T n_shift[B2N_MAX_DIMS];
+  const T *rtable[B2N_MAX_DIMS];      // real kernel values (b2n_geom.rtable_dev) or NULL
+  double table_phase[B2N_MAX_DIMS];   // slope of the tables' linear phase
 };
 
 template <typename T> static GeomT<T> make_geom(const b2n_geom *g) {
@@ -70,6 +72,8 @@ template <typename T> static GeomT<T> make_geom(const b2n_geom *g) {
     r.table_len[d] = g->table_len[d];
     r.table[d] = (const cplx<T> *)g->table_dev[d];
     r.n_shift[d] = (T)g->n_shift[d];
+    r.rtable[d] = (const T *)g->rtable_dev[d];
+    r.table_phase[d] = g->table_phase[d];
     r.coef_off[d] = off;
     off += g->numpoints[d];
   }
@@ -143,7 +147,8 @@ template <typename T>
 __global__ void k_point_records(GeomT<T> g, const T *__restrict__ omega, int64_t M, int64_t total,
                                 const uint32_t *__restrict__ sorted_idx, int32_t *__restrict__ perm,
                                 int32_t *__restrict__ inv_perm, int32_t *__restrict__ base_out, cplx<T> *__restrict__ coef,
-                                cplx<T> *__restrict__ phase) {
+                                cplx<T> *__restrict__ phase, float *__restrict__ hw, float2 *__restrict__ fac,
+                                unsigned char *__restrict__ exc_flag) {
   const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= total) return;
   const int64_t i = sorted_idx[s];
@@ -160,11 +165,27 @@ __global__ void k_point_records(GeomT<T> g, const T *__restrict__ omega, int64_t
   ph.x = cs;
   ph.y = sn;
   phase[s] = ph;
+  double fac_arg = 0.0;  // sum_d table_phase[d] * (x_d(neighbour 0) + wrapped base_d)
+  bool exc = false;      // a neighbour whose table index is not that of neighbour 0 minus j L (see b2n_points.own_exc)
   for (int d = 0; d < g.ndim; ++d) {
     T tm;
     int64_t base;
     locate<T>(omv[d], g.K[d], g.J[d], tm, base);
     base_out[s * g.ndim + d] = (int32_t)wrap_cell(base, g.K[d]);
+    if (hw) {
+      // real-weight records (2-D, J = 6 on both axes; see b2n_geom.rtable_dev): neighbour j of this point has the
+      // table index t0 - j L, so its complex weight is r(t0 - j L) exp(-1i p (x0 - j)); the part that does not
+      // depend on j goes into the point's factor
+      const int64_t t0 = table_index<T>(tm, base, g.J[d], g.L[d]);
+      fac_arg += g.table_phase[d] * ((double)t0 / g.L[d] - 0.5 * g.J[d] + (double)wrap_cell(base, g.K[d]));
+      for (int j = 0; j < 6; ++j) {
+        int64_t ti = table_index<T>(tm, base + j, g.J[d], g.L[d]);
+        exc |= ti != t0 - (int64_t)j * g.L[d] || ti < 0 || ti >= g.table_len[d];
+        if (ti < 0) ti += g.table_len[d];
+        ti = ti < 0 ? 0 : (ti >= g.table_len[d] ? g.table_len[d] - 1 : ti);
+        hw[s * 12 + 6 * d + j] = (float)g.rtable[d][ti];
+      }
+    }
     cplx<T> *rec = coef + s * g.coef_stride + g.coef_off[d];
     for (int j = 0; j < g.J[d]; ++j) {
       int64_t ti = table_index<T>(tm, base + j, g.J[d], g.L[d]);
@@ -176,6 +197,49 @@ __global__ void k_point_records(GeomT<T> g, const T *__restrict__ omega, int64_t
       rec[j] = d == 0 ? cmul(tv, ph) : tv;
     }
   }
+  if (hw) {
+    exc_flag[s] = exc ? 1 : 0;
+    if (exc)
+      for (int k = 0; k < 12; ++k) hw[s * 12 + k] = 0.f;
+  }
+  if (fac) {
+    // conj(fftshift phase * exp(-1i fac_arg)): the angle reaches thousands of radians, so it is reduced in double
+    double sn2, cs2;
+    sincos(fac_arg - (double)arg, &sn2, &cs2);
+    fac[s] = make_float2((float)cs2, (float)sn2);
+  }
+}
+
+// sorted slots of the exception points, ascending (one CTA: per-thread segments, block scan, ordered write)
+__global__ void __launch_bounds__(1024) k_own_exc_list(const unsigned char *__restrict__ flag, int64_t total,
+                                                       int32_t *__restrict__ list, int32_t *__restrict__ count) {
+  __shared__ int s_cnt[1024];
+  const int tid = threadIdx.x;
+  const int64_t per = (total + 1023) / 1024, lo = tid * per, hi = lo + per < total ? lo + per : total;
+  int n = 0;
+  for (int64_t i = lo; i < hi; ++i) n += flag[i];
+  s_cnt[tid] = n;
+  __syncthreads();
+  for (int off = 1; off < 1024; off <<= 1) {
+    const int a = tid >= off ? s_cnt[tid - off] : 0;
+    __syncthreads();
+    s_cnt[tid] += a;
+    __syncthreads();
+  }
+  int at = s_cnt[tid] - n;
+  for (int64_t i = lo; i < hi; ++i)
+    if (flag[i]) list[at++] = (int32_t)i;
+  if (tid == 1023) *count = s_cnt[1023];
+}
+
+// exp(-1i * slope_d * cell) for every row and column of the grid: the per-cell factor of the real-weight adjoint
+__global__ void k_own_cell_phase(int Ky, int Kx, double py, double px, float2 *__restrict__ q) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= Ky + Kx) return;
+  const double a = i < Ky ? py * i : px * (i - Ky);
+  double sn, cs;
+  sincos(a, &sn, &cs);
+  q[i] = make_float2((float)cs, (float)-sn);
 }
 
 // Longest-processing-time-first order of the sub-problems: CTAs are dispatched in block
@@ -261,6 +325,7 @@ constexpr int kOwnBuckets = 16;  // LPT buckets of the work items by size (+ one
 
 struct OwnGeom {
   int Ky, Kx, nty, ntx, J, Ty, Tx, cap;  // Ty x Tx cells per output tile
+  int neg_y, neg_x;  // 1: a footprint that wraps around this axis flips the sign of the real-weight form
   int64_t n_traj, n_own_tiles;  // tiles per trajectory
   Tiling tl;                    // tiling of the cell-sorted plan (cell_start index)
 };
@@ -361,9 +426,10 @@ __global__ void __launch_bounds__(1024) k_own_scan(int64_t n_tiles_all, int4 *__
 
 // one warp per output tile: write its visits in window order and its work items into their LPT bucket
 __global__ void __launch_bounds__(256) k_own_fill(OwnGeom g, const int32_t *__restrict__ cell_start,
-                                                  const int32_t *__restrict__ perm, const int4 *__restrict__ tiles,
+                                                  const int32_t *__restrict__ perm, const float *__restrict__ hw,
+                                                  const int4 *__restrict__ tiles,
                                                   const int32_t *__restrict__ bucket_base,
-                                                  int32_t *__restrict__ bucket_fill, int4 *__restrict__ visits,
+                                                  int32_t *__restrict__ bucket_fill, float4 *__restrict__ visits,
                                                   int4 *__restrict__ items) {
   const int64_t t = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
@@ -386,8 +452,23 @@ __global__ void __launch_bounds__(256) k_own_fill(OwnGeom g, const int32_t *__re
       const int up = __shfl_up_sync(0xffffffffu, incl, off);
       if (lane >= off) incl += up;
     }
-    int4 *dst = visits + run + incl - cnt;
-    for (int k = 0; k < cnt; ++k) dst[k] = make_int4(s0 + k, perm[s0 + k], ry, rx);
+    // 64-byte visit record: the four row weights hy[k] = r_y[k - ry], the eight column weights hx[x] = +-r_x[x - rx]
+    // (zero outside the footprint), the sample index.  (ry, rx) are unwrapped: a negative base cell means the
+    // footprint reached this tile around the grid's edge, which flips the sign where exp(1i table_phase K) = -1.
+    float4 *dst = visits + (int64_t)(run + incl - cnt) * 4;
+    const float sgn = (((y0 + ry < 0) & g.neg_y) ^ ((x0 + rx < 0) & g.neg_x)) ? -1.f : 1.f;
+    for (int k = 0; k < cnt; ++k) {
+      const float *h = hw + (int64_t)(s0 + k) * 12;
+      float hy[4], hx[8];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) hy[r] = (unsigned)(r - ry) < 6u ? h[r - ry] : 0.f;
+#pragma unroll
+      for (int x = 0; x < 8; ++x) hx[x] = (unsigned)(x - rx) < 6u ? sgn * h[6 + x - rx] : 0.f;
+      dst[4 * k] = make_float4(hy[0], hy[1], hy[2], hy[3]);
+      dst[4 * k + 1] = make_float4(hx[0], hx[1], hx[2], hx[3]);
+      dst[4 * k + 2] = make_float4(hx[4], hx[5], hx[6], hx[7]);
+      dst[4 * k + 3] = make_float4(__int_as_float(perm[s0 + k]), 0.f, 0.f, 0.f);
+    }
     run += __shfl_sync(0xffffffffu, incl, 31);
   }
   for (int j = lane; j < ti.z; j += 32) {
@@ -403,7 +484,8 @@ struct Carve {
   size_t perm, inv_perm, base, coef, phase, cell_start, keys, sub_tile, sub_start, sub_count, n_sub;
   size_t keys_in, idx_in, idx_out, chunks, offsets, tmp_tile, tmp_start, tmp_count, sub_keys, sub_keys_out, sub_idx,
       sub_order, cub, total, cub_bytes;
-  size_t own_visits, own_items, own_tiles, own_counts, own_hist;
+  size_t own_visits, own_items, own_tiles, own_counts, own_hist, own_hw, own_fac, own_q, own_excf, own_exc;
+  bool own_real;
   int64_t n_own_items_max, n_own_tiles;  // per trajectory; 0 = no visit lists for this geometry
   int own_nt[2], own_cap, own_rows;
   int64_t n_sub_max;
@@ -413,20 +495,32 @@ struct Carve {
 
 static int default_sub_cap(int ndim) { return ndim == 3 ? 128 : 128; }
 
-constexpr int kOwnTileCols = 8;
+constexpr int kOwnTileRows = 4, kOwnTileCols = 8;
 int g_own_cap = 64;  // visits per work item of the owner-tile spread (b2n_set_option(B2N_OPT_OWN_CAP) for A/B)
-int g_own_rows = 4;  // rows of an output tile, 4 or 8 (B2N_OPT_OWN_ROWS), read when a plan is built
-// Visit lists are built for what the owner-tile spread handles: 2-D complex64, J = 6, and grids on which a footprint
-// touches a bounded number of tiles: two per dimension with 8 cells per tile (every K_d >= 16; a last, partial tile of
-// at least J-1 cells), three tile rows with 4-row tiles (K_y a multiple of 4).  own_visits_per_point is that bound.
-static int own_rows(const b2n_geom *g) { return g_own_rows == 4 && g->grid_size[0] % 4 == 0 ? 4 : 8; }
-static int own_visits_per_point(const b2n_geom *g) { return own_rows(g) == 4 ? 6 : 4; }
+// Visit lists are built for what the owner-tile spread handles: 2-D complex64, J = 6, K_d >= 16, tables of the
+// reference's form with the real kernel supplied by the caller (own_real).
 static bool own_eligible(const b2n_geom *g) {
   if (g->ndim != 2 || g->dtype != B2N_C64) return false;
+  for (int d = 0; d < 2; ++d)
+    if (g->numpoints[d] != 6 || g->grid_size[d] < 16) return false;
+  return true;
+}
+// upper bound on the tiles one footprint touches: ceil((T + J - 1) / T) per axis, one more where the last tile of the
+// axis is a partial one of fewer than J - 1 cells (the footprint can then cover it and reach around the grid's edge)
+static int own_visits_per_point(const b2n_geom *g) {
+  int v = 1;
   for (int d = 0; d < 2; ++d) {
-    const int T = d == 0 ? own_rows(g) : kOwnTileCols;
-    const int64_t K = g->grid_size[d], rem = K % T;
-    if (g->numpoints[d] != 6 || K < 16 || (rem != 0 && rem < g->numpoints[d] - 1)) return false;
+    const int T = d == 0 ? kOwnTileRows : kOwnTileCols, rem = (int)(g->grid_size[d] % T);
+    v *= (T + 4) / T + 1 + (rem != 0 && rem < 5 ? 1 : 0);
+  }
+  return v;
+}
+// real-weight records: the caller vouches for the tables' form, and the table step per neighbour must be exact
+static bool own_real(const b2n_geom *g) {
+  if (!own_eligible(g)) return false;
+  for (int d = 0; d < 2; ++d) {
+    const int L = g->table_oversamp[d];
+    if (!g->rtable_dev[d] || (L & (L - 1)) != 0) return false;
   }
   return true;
 }
@@ -496,19 +590,27 @@ static int carve(const b2n_geom *g, int64_t M, int64_t n_traj, Carve *c) {
   c->cub = take(cub_bytes + 256);
   c->n_own_tiles = 0;
   c->n_own_items_max = 0;
-  const int64_t vpp = own_visits_per_point(g);
-  if (own_eligible(g) && vpp * total < ((int64_t)1 << 31) - 1) {
-    c->own_rows = own_rows(g);
+  const int64_t vpp = own_eligible(g) ? own_visits_per_point(g) : 0;
+  c->own_hw = c->own_fac = c->own_q = 0;
+  c->own_real = false;
+  if (own_real(g) && vpp * total < ((int64_t)1 << 31) - 1) {
+    c->own_rows = kOwnTileRows;
     c->own_nt[0] = (int)ceil_div(g->grid_size[0], c->own_rows);
     c->own_nt[1] = (int)ceil_div(g->grid_size[1], kOwnTileCols);
     c->n_own_tiles = (int64_t)c->own_nt[0] * c->own_nt[1];
     c->own_cap = g_own_cap < 8 ? 8 : (g_own_cap > 4095 ? 4095 : g_own_cap);
     c->n_own_items_max = c->n_own_tiles * n_traj + vpp * total / c->own_cap + 1;
-    c->own_visits = take(sizeof(int4) * (size_t)(vpp * total + 1));
+    c->own_visits = take(64 * (size_t)(vpp * total + 1));
     c->own_items = take(sizeof(int4) * (size_t)c->n_own_items_max);
     c->own_tiles = take(sizeof(int4) * (size_t)(c->n_own_tiles * n_traj));
-    c->own_counts = take(sizeof(int32_t) * 2);
+    c->own_counts = take(sizeof(int32_t) * 4);
     c->own_hist = take(sizeof(int32_t) * 3 * (kOwnBuckets + 1));
+    c->own_real = true;
+    c->own_hw = take(sizeof(float) * 12 * (size_t)total);
+    c->own_fac = take(sizeof(float2) * (size_t)total);
+    c->own_q = take(sizeof(float2) * (size_t)(g->grid_size[0] + g->grid_size[1]));
+    c->own_excf = take((size_t)total);
+    c->own_exc = take(sizeof(int32_t) * (size_t)total);
   }
   c->total = off;
   return 0;
@@ -557,7 +659,9 @@ static int build_impl(const b2n_geom *geom, const void *omega, int64_t M, int64_
     B2N_CUDA_OK(cub::DeviceRadixSort::SortPairs(ws + c.cub, cub_bytes, keys_in, out->keys, idx_in, idx_out, (int)total,
                                                 0, sort_bits(n_cells), st));
     k_point_records<T><<<(unsigned)ceil_div(total, threads), threads, 0, st>>>(
-        g, (const T *)omega, M, total, idx_out, out->perm, out->inv_perm, out->base, (cplx<T> *)out->coef, (cplx<T> *)out->phase);
+        g, (const T *)omega, M, total, idx_out, out->perm, out->inv_perm, out->base, (cplx<T> *)out->coef,
+        (cplx<T> *)out->phase, c.own_real ? (float *)(ws + c.own_hw) : nullptr,
+        c.own_real ? (float2 *)(ws + c.own_fac) : nullptr, c.own_real ? (unsigned char *)(ws + c.own_excf) : nullptr);
     B2N_LAUNCH_OK("k_point_records");
   }
   k_cell_start<<<(unsigned)ceil_div(n_cells + 1, threads), threads, 0, st>>>(out->keys, total, n_cells,
@@ -593,6 +697,10 @@ static int build_impl(const b2n_geom *geom, const void *omega, int64_t M, int64_
   out->n_own_items_max = 0;
   out->own_visits = out->own_items = out->own_tiles = nullptr;
   out->own_counts = nullptr;
+  out->own_hw = nullptr;
+  out->own_fac = out->own_q = nullptr;
+  out->own_exc = nullptr;
+  out->n_own_exc_max = 0;
   if (c.n_own_tiles > 0) {
     OwnGeom og;
     og.Ky = (int)g.K[0];
@@ -603,6 +711,22 @@ static int build_impl(const b2n_geom *geom, const void *omega, int64_t M, int64_
     og.Ty = c.own_rows;
     og.Tx = kOwnTileCols;
     og.cap = c.own_cap;
+    {
+      // exp(1i table_phase K) = (-1)^(N - 1): the sign a neighbour picks up when it wraps around the grid
+      og.neg_y = (int)(llround(geom->table_phase[0] * (double)g.K[0] / 3.14159265358979323846) & 1);
+      og.neg_x = (int)(llround(geom->table_phase[1] * (double)g.K[1] / 3.14159265358979323846) & 1);
+      out->own_hw = (float *)(ws + c.own_hw);
+      out->own_fac = ws + c.own_fac;
+      out->own_q = ws + c.own_q;
+      k_own_cell_phase<<<(unsigned)ceil_div(g.K[0] + g.K[1], threads), threads, 0, st>>>(
+          og.Ky, og.Kx, geom->table_phase[0], geom->table_phase[1], (float2 *)out->own_q);
+      B2N_LAUNCH_OK("k_own_cell_phase");
+      out->own_exc = (int32_t *)(ws + c.own_exc);
+      out->n_own_exc_max = total;
+      k_own_exc_list<<<1, 1024, 0, st>>>((const unsigned char *)(ws + c.own_excf), total, out->own_exc,
+                                         (int32_t *)(ws + c.own_counts) + 2);
+      B2N_LAUNCH_OK("k_own_exc_list");
+    }
     og.n_traj = n_traj;
     og.n_own_tiles = c.n_own_tiles;
     og.tl = tl;
@@ -616,8 +740,8 @@ static int build_impl(const b2n_geom *geom, const void *omega, int64_t M, int64_
     k_own_scan<<<1, 1024, 0, st>>>(nt_all, tiles, hist, bucket_base, bucket_fill, (int32_t *)(ws + c.own_counts));
     B2N_LAUNCH_OK("k_own_scan");
     k_own_fill<<<(unsigned)ceil_div(nt_all * 32, threads), threads, 0, st>>>(
-        og, out->cell_start, out->perm, tiles, bucket_base, bucket_fill, (int4 *)(ws + c.own_visits),
-        (int4 *)(ws + c.own_items));
+        og, out->cell_start, out->perm, (const float *)(ws + c.own_hw), tiles, bucket_base, bucket_fill,
+        (float4 *)(ws + c.own_visits), (int4 *)(ws + c.own_items));
     B2N_LAUNCH_OK("k_own_fill");
     out->own_tile = c.own_rows;
     out->own_cap = og.cap;
@@ -637,6 +761,12 @@ static int build_impl(const b2n_geom *geom, const void *omega, int64_t M, int64_
 using namespace b2n;
 
 extern "C" int b2n_abi_version(void) { return B2N_ABI_VERSION; }
+extern "C" int b2n_struct_sizes(size_t *geom_bytes, size_t *points_bytes) {
+  if (!geom_bytes || !points_bytes) return fail_arg(B2N_E_ARG, "NULL output");
+  *geom_bytes = sizeof(b2n_geom);
+  *points_bytes = sizeof(b2n_points);
+  return 0;
+}
 extern "C" const char *b2n_last_error(void) { return g_error; }
 extern "C" long long b2n_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
