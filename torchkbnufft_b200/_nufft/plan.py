@@ -149,7 +149,10 @@ class Geometry:
         if not (len(self.numpoints) == len(self.table_oversamp) == len(self.n_shift) == len(self.grid_size)
                 == self.ndim):
             raise ValueError("tables, n_shift, numpoints, table_oversamp and grid_size must agree in length")
-        self.tables = [dense(t) for t in tables]  # strong refs keep the pointers valid
+        # private copies (a few KB each): the geometry is shared by every operator with the same contents (see
+        # get_geometry), so nobody else may hold a handle that can rewrite its tables
+        self.tables = [dense(t).detach().clone() for t in tables]
+        self.content_key: tuple = ()
         self.n_grid = 1
         for k in self.grid_size:
             self.n_grid *= k
@@ -233,6 +236,19 @@ def host_ints(sizes) -> Tuple[int, ...]:
     return hit[0]
 
 
+_GEOM_BY_CONTENT: "OrderedDict[tuple, Geometry]" = OrderedDict()
+
+
+def _content_key(tables, n_shift, numpoints, table_oversamp, grid_ints) -> tuple:
+    import hashlib
+    parts = []
+    for t in tables:
+        raw = torch.view_as_real(dense(t).detach()).cpu().numpy().tobytes()
+        parts.append((str(t.dtype), t.numel(), hashlib.blake2b(raw, digest_size=16).digest()))
+    return (tables[0].device.index, tuple(parts), tuple(float(v) for v in n_shift.tolist()),
+            tuple(int(v) for v in numpoints.tolist()), tuple(int(v) for v in table_oversamp.tolist()), tuple(grid_ints))
+
+
 _GEOM_FAST: dict = {}  # (id, _version) of every buffer -> (Geometry, the buffers): a cheap front for _GEOM_CACHE
 
 
@@ -260,7 +276,20 @@ def get_geometry(tables: Sequence[Tensor], n_shift: Tensor, numpoints: Tensor, t
         else:
             for t in tables:
                 require_cuda(t, "tables")
-            geo = Geometry(tables, n_shift, numpoints, table_oversamp, gkey)
+            # Operators with the same CONTENTS share one geometry, hence one trajectory plan: KbNufft and
+            # KbNufftAdjoint built with the same arguments own different buffer tensors, and a trajectory that changes
+            # every call would otherwise be planned once per operator (measured: two plan builds per forward+adjoint
+            # pair, profiles/r02_spread_notes.txt).  One host read of the small buffers per new buffer identity.
+            ckey = _content_key(tables, n_shift, numpoints, table_oversamp, gkey)
+            geo = _GEOM_BY_CONTENT.get(ckey)
+            if geo is None:
+                geo = Geometry(tables, n_shift, numpoints, table_oversamp, gkey)
+                geo.content_key = ckey
+                _GEOM_BY_CONTENT[ckey] = geo
+                while len(_GEOM_BY_CONTENT) > GEOM_CACHE_SIZE:
+                    _GEOM_BY_CONTENT.popitem(last=False)
+            else:
+                _GEOM_BY_CONTENT.move_to_end(ckey)
             geo.key = key
             geo._refs = (n_shift, numpoints, table_oversamp)  # keep key pointers alive
             _GEOM_CACHE[key] = geo
@@ -333,6 +362,11 @@ class TrajectoryPlan:
         memory out while that stream still reads it)."""
         stream = torch.cuda.current_stream(self.omega.device)
         if stream.cuda_stream in self._streams_seen:
+            return
+        if torch.cuda.is_current_stream_capturing():
+            # A capturing stream must not wait on work recorded outside its capture (cudaErrorStreamCaptureIsolation).
+            # The build was enqueued before the capture began, and torch.cuda.graph synchronises the device on entry,
+            # so the plan is complete; the stream is not remembered, a later eager use of it takes the normal path.
             return
         if self._build_event is not None:
             stream.wait_event(self._build_event)
@@ -485,6 +519,7 @@ def clear_caches() -> None:
     _PLAN_FAST.clear()
     _OMEGA_CAST.clear()
     _GEOM_CACHE.clear()
+    _GEOM_BY_CONTENT.clear()
     _GEOM_FAST.clear()
     _GRID_SIZE_CACHE.clear()
     _HOST_INTS_FAST.clear()

@@ -210,26 +210,61 @@ __global__ void k_point_records(GeomT<T> g, const T *__restrict__ omega, int64_t
   }
 }
 
-// sorted slots of the exception points, ascending (one CTA: per-thread segments, block scan, ordered write)
-__global__ void __launch_bounds__(1024) k_own_exc_list(const unsigned char *__restrict__ flag, int64_t total,
-                                                       int32_t *__restrict__ list, int32_t *__restrict__ count) {
-  __shared__ int s_cnt[1024];
-  const int tid = threadIdx.x;
-  const int64_t per = (total + 1023) / 1024, lo = tid * per, hi = lo + per < total ? lo + per : total;
-  int n = 0;
-  for (int64_t i = lo; i < hi; ++i) n += flag[i];
-  s_cnt[tid] = n;
+// sorted slots of the exception points, ascending: flags counted per block, then every block writes its flagged
+// slots behind those of the blocks before it
+__global__ void __launch_bounds__(1024) k_own_exc_count(const unsigned char *__restrict__ flag, int64_t total,
+                                                        int32_t *__restrict__ block_count) {
+  const int64_t i = (int64_t)blockIdx.x * 1024 + threadIdx.x;
+  const int n = __syncthreads_count(i < total && flag[i]);
+  if (threadIdx.x == 0) block_count[blockIdx.x] = n;
+}
+
+__global__ void __launch_bounds__(1024) k_own_exc_write(const unsigned char *__restrict__ flag, int64_t total,
+                                                        const int32_t *__restrict__ block_count,
+                                                        int32_t *__restrict__ list, int32_t *__restrict__ count) {
+  __shared__ int s_warp[32];
+  __shared__ int s_base;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // slots flagged in the blocks before this one (every block: all of them, for the total)
+  int before = 0, all = 0;
+  for (int b = tid; b < (int)gridDim.x; b += 1024) {
+    const int c = block_count[b];
+    all += c;
+    if (b < (int)blockIdx.x) before += c;
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    before += __shfl_xor_sync(0xffffffffu, before, off);
+    all += __shfl_xor_sync(0xffffffffu, all, off);
+  }
+  if (lane == 0) s_warp[warp] = before;
   __syncthreads();
-  for (int off = 1; off < 1024; off <<= 1) {
-    const int a = tid >= off ? s_cnt[tid - off] : 0;
+  if (tid == 0) {
+    int t = 0;
+    for (int w = 0; w < 32; ++w) t += s_warp[w];
+    s_base = t;
+  }
+  __syncthreads();
+  if (blockIdx.x == 0) {  // the total, by the same reduction
     __syncthreads();
-    s_cnt[tid] += a;
+    if (lane == 0) s_warp[warp] = all;
+    __syncthreads();
+    if (tid == 0) {
+      int t = 0;
+      for (int w = 0; w < 32; ++w) t += s_warp[w];
+      *count = t;
+    }
     __syncthreads();
   }
-  int at = s_cnt[tid] - n;
-  for (int64_t i = lo; i < hi; ++i)
-    if (flag[i]) list[at++] = (int32_t)i;
-  if (tid == 1023) *count = s_cnt[1023];
+  const int64_t i = (int64_t)blockIdx.x * 1024 + tid;
+  const bool f = i < total && flag[i];
+  const unsigned m = __ballot_sync(0xffffffffu, f);
+  __syncthreads();
+  if (lane == 0) s_warp[warp] = __popc(m);
+  __syncthreads();
+  int at = s_base;
+  for (int w = 0; w < warp; ++w) at += s_warp[w];
+  if (f) list[at + __popc(m & ((1u << lane) - 1))] = (int32_t)i;
 }
 
 // exp(-1i * slope_d * cell) for every row and column of the grid: the per-cell factor of the real-weight adjoint
@@ -375,16 +410,14 @@ __global__ void __launch_bounds__(256) k_own_count(OwnGeom g, const int32_t *__r
   }
 }
 
-// single CTA: exclusive scans over the tiles (first visit, first partial slot), bucket bases, totals
+// single CTA: exclusive scans over the tiles (first visit, first partial slot), bucket bases, totals; 1024 tiles per
+// round with coalesced loads (the next round's are issued before this round's scan), warp shuffles inside the round
 __global__ void __launch_bounds__(1024) k_own_scan(int64_t n_tiles_all, int4 *__restrict__ tiles,
                                                    int32_t *__restrict__ hist, int32_t *__restrict__ bucket_base,
                                                    int32_t *__restrict__ bucket_fill, int32_t *__restrict__ counts) {
-  __shared__ int s_v[1024], s_s[1024];
-  __shared__ int run_v, run_s;
-  const int tid = threadIdx.x;
+  __shared__ int s_v[32], s_s[32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) {
-    run_v = 0;
-    run_s = 0;
     int acc = 0;
     for (int b = 0; b <= kOwnBuckets; ++b) {
       bucket_base[b] = acc;
@@ -393,58 +426,75 @@ __global__ void __launch_bounds__(1024) k_own_scan(int64_t n_tiles_all, int4 *__
     }
     counts[0] = acc;
   }
-  __syncthreads();
+  int run_v = 0, run_s = 0;
+  int4 nxt = make_int4(0, 0, 0, -1);
+  if (tid < n_tiles_all) nxt = tiles[tid];
   for (int64_t base = 0; base < n_tiles_all; base += 1024) {
     const int64_t t = base + tid;
-    int4 ti = make_int4(0, 0, 0, -1);
-    if (t < n_tiles_all) ti = tiles[t];
+    int4 ti = nxt;
+    nxt = make_int4(0, 0, 0, -1);
+    if (t + 1024 < n_tiles_all) nxt = tiles[t + 1024];
     const int v = ti.x, sl = ti.z > 1 ? ti.z : 0;
-    s_v[tid] = v;
-    s_s[tid] = sl;
+    int iv = v, is = sl;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const int a = __shfl_up_sync(0xffffffffu, iv, off), b = __shfl_up_sync(0xffffffffu, is, off);
+      if (lane >= off) {
+        iv += a;
+        is += b;
+      }
+    }
+    if (lane == 31) {
+      s_v[warp] = iv;
+      s_s[warp] = is;
+    }
     __syncthreads();
-    for (int off = 1; off < 1024; off <<= 1) {  // Hillis-Steele inclusive scan of both arrays
-      const int a = tid >= off ? s_v[tid - off] : 0, b = tid >= off ? s_s[tid - off] : 0;
-      __syncthreads();
-      s_v[tid] += a;
-      s_s[tid] += b;
-      __syncthreads();
+    int bv = 0, bs = 0, tv = 0, ts = 0;
+    for (int w = 0; w < 32; ++w) {
+      if (w < warp) {
+        bv += s_v[w];
+        bs += s_s[w];
+      }
+      tv += s_v[w];
+      ts += s_s[w];
     }
     if (t < n_tiles_all) {
-      ti.y = run_v + s_v[tid] - v;
-      ti.w = sl ? run_s + s_s[tid] - sl : -1;
+      ti.y = run_v + bv + iv - v;
+      ti.w = sl ? run_s + bs + is - sl : -1;
       tiles[t] = ti;
     }
-    __syncthreads();
-    if (tid == 1023) {
-      run_v += s_v[1023];
-      run_s += s_s[1023];
-    }
+    run_v += tv;
+    run_s += ts;
     __syncthreads();
   }
   if (tid == 0) counts[1] = run_s;
 }
 
-// one warp per output tile: write its visits in window order and its work items into their LPT bucket
-__global__ void __launch_bounds__(256) k_own_fill(OwnGeom g, const int32_t *__restrict__ cell_start,
+// one CTA per output tile: write its visits in window order and its work items into their LPT bucket.
+// The window (at most 9 x 13 base cells) is scanned once into shared memory; then every group of 4 lanes takes visits
+// v, v + 32, ... of the tile, finds the window cell of each by bisection of the cell offsets and writes the four
+// 16-byte parts of its record -- the dense tiles at the centre of a radial trajectory (thousands of visits) are
+// spread over the whole CTA instead of one lane per cell.
+constexpr int kOwnFillThreads = 128, kOwnWinMax = 128;
+__global__ void __launch_bounds__(kOwnFillThreads) k_own_fill(OwnGeom g, const int32_t *__restrict__ cell_start,
                                                   const int32_t *__restrict__ perm, const float *__restrict__ hw,
                                                   const int4 *__restrict__ tiles,
                                                   const int32_t *__restrict__ bucket_base,
                                                   int32_t *__restrict__ bucket_fill, float4 *__restrict__ visits,
                                                   int4 *__restrict__ items) {
-  const int64_t t = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (t >= g.n_traj * g.n_own_tiles) return;
+  __shared__ int s_first[kOwnWinMax + 1], s_s0[kOwnWinMax], s_warp[kOwnFillThreads / 32];
+  const int64_t t = blockIdx.x;
+  const int tid_in = threadIdx.x, lane = tid_in & 31, warp = tid_in >> 5;
   const int64_t traj = t / g.n_own_tiles, tid = t - traj * g.n_own_tiles;
   const int ty = (int)(tid / g.ntx), tx = (int)(tid - (int64_t)ty * g.ntx);
   const int y0 = ty * g.Ty, x0 = tx * g.Tx;
   const int th = min(g.Ty, g.Ky - y0), tw = min(g.Tx, g.Kx - x0);
-  const int wh = th + g.J - 1, ww = tw + g.J - 1;
+  const int wh = th + g.J - 1, ww = tw + g.J - 1, nw = wh * ww;  // nw <= 117
   const int4 ti = tiles[t];
-  int run = ti.y;
-  for (int w0 = 0; w0 < wh * ww; w0 += 32) {
-    const int w = w0 + lane;
-    int s0 = 0, s1 = 0, ry = 0, rx = 0;
-    if (w < wh * ww) own_window_cell(g, cell_start, traj, y0, x0, ww, w, s0, s1, ry, rx);
+  {
+    // thread w holds window cell w: exclusive scan of the point counts over the CTA
+    int s0 = 0, s1 = 0, ry, rx;
+    if (tid_in < nw) own_window_cell(g, cell_start, traj, y0, x0, ww, tid_in, s0, s1, ry, rx);
     const int cnt = s1 - s0;
     int incl = cnt;
 #pragma unroll
@@ -452,26 +502,45 @@ __global__ void __launch_bounds__(256) k_own_fill(OwnGeom g, const int32_t *__re
       const int up = __shfl_up_sync(0xffffffffu, incl, off);
       if (lane >= off) incl += up;
     }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    int before = 0;
+    for (int w = 0; w < warp; ++w) before += s_warp[w];
+    s_first[tid_in] = before + incl - cnt;
+    s_s0[tid_in] = s0;
+    if (tid_in == kOwnFillThreads - 1) s_first[kOwnWinMax] = before + incl;  // = ti.x
+    __syncthreads();
+  }
+  const int n = ti.x, part = tid_in & 3;
+#pragma unroll 4
+  for (int v = tid_in >> 2; v < n; v += kOwnFillThreads / 4) {
+    int lo = 0, hi = nw - 1;  // last window cell whose first visit is <= v (empty cells share their successor's offset)
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (s_first[mid] <= v) lo = mid; else hi = mid - 1;
+    }
+    const int wy = lo / ww, ry = wy - (g.J - 1), rx = lo - wy * ww - (g.J - 1);
+    const int slot = s_s0[lo] + (v - s_first[lo]);
     // 64-byte visit record: the four row weights hy[k] = r_y[k - ry], the eight column weights hx[x] = +-r_x[x - rx]
     // (zero outside the footprint), the sample index.  (ry, rx) are unwrapped: a negative base cell means the
     // footprint reached this tile around the grid's edge, which flips the sign where exp(1i table_phase K) = -1.
-    float4 *dst = visits + (int64_t)(run + incl - cnt) * 4;
-    const float sgn = (((y0 + ry < 0) & g.neg_y) ^ ((x0 + rx < 0) & g.neg_x)) ? -1.f : 1.f;
-    for (int k = 0; k < cnt; ++k) {
-      const float *h = hw + (int64_t)(s0 + k) * 12;
-      float hy[4], hx[8];
+    float4 rec;
+    if (part == 3) {
+      rec = make_float4(__int_as_float(perm[slot]), 0.f, 0.f, 0.f);
+    } else {
+      const float sgn = (((y0 + ry < 0) & g.neg_y) ^ ((x0 + rx < 0) & g.neg_x)) ? -1.f : 1.f;
+      // part 0: rows 0..3 against ry; parts 1, 2: columns 0..3 / 4..7 against rx
+      const int j0 = part == 0 ? -ry : 4 * (part - 1) - rx;
+      const float *hp = hw + (int64_t)slot * 12 + (part == 0 ? 0 : 6);
+      const float sc = part == 0 ? 1.f : sgn;
+      float e[4];
 #pragma unroll
-      for (int r = 0; r < 4; ++r) hy[r] = (unsigned)(r - ry) < 6u ? h[r - ry] : 0.f;
-#pragma unroll
-      for (int x = 0; x < 8; ++x) hx[x] = (unsigned)(x - rx) < 6u ? sgn * h[6 + x - rx] : 0.f;
-      dst[4 * k] = make_float4(hy[0], hy[1], hy[2], hy[3]);
-      dst[4 * k + 1] = make_float4(hx[0], hx[1], hx[2], hx[3]);
-      dst[4 * k + 2] = make_float4(hx[4], hx[5], hx[6], hx[7]);
-      dst[4 * k + 3] = make_float4(__int_as_float(perm[s0 + k]), 0.f, 0.f, 0.f);
+      for (int q = 0; q < 4; ++q) e[q] = (unsigned)(j0 + q) < 6u ? sc * hp[j0 + q] : 0.f;
+      rec = make_float4(e[0], e[1], e[2], e[3]);
     }
-    run += __shfl_sync(0xffffffffu, incl, 31);
+    visits[(int64_t)(ti.y + v) * 4 + part] = rec;
   }
-  for (int j = lane; j < ti.z; j += 32) {
+  for (int j = tid_in; j < ti.z; j += kOwnFillThreads) {
     const int size = max(0, min(g.cap, ti.x - j * g.cap));
     const int b = ti.z > 1 ? 0 : own_bucket(size, g.cap);
     const int pos = bucket_base[b] + atomicAdd(&bucket_fill[b], 1);
@@ -484,7 +553,7 @@ struct Carve {
   size_t perm, inv_perm, base, coef, phase, cell_start, keys, sub_tile, sub_start, sub_count, n_sub;
   size_t keys_in, idx_in, idx_out, chunks, offsets, tmp_tile, tmp_start, tmp_count, sub_keys, sub_keys_out, sub_idx,
       sub_order, cub, total, cub_bytes;
-  size_t own_visits, own_items, own_tiles, own_counts, own_hist, own_hw, own_fac, own_q, own_excf, own_exc;
+  size_t own_visits, own_items, own_tiles, own_counts, own_hist, own_hw, own_fac, own_q, own_excf, own_excb, own_exc;
   bool own_real;
   int64_t n_own_items_max, n_own_tiles;  // per trajectory; 0 = no visit lists for this geometry
   int own_nt[2], own_cap, own_rows;
@@ -610,6 +679,7 @@ static int carve(const b2n_geom *g, int64_t M, int64_t n_traj, Carve *c) {
     c->own_fac = take(sizeof(float2) * (size_t)total);
     c->own_q = take(sizeof(float2) * (size_t)(g->grid_size[0] + g->grid_size[1]));
     c->own_excf = take((size_t)total);
+    c->own_excb = take(sizeof(int32_t) * (size_t)ceil_div(total > 0 ? total : 1, 1024));
     c->own_exc = take(sizeof(int32_t) * (size_t)total);
   }
   c->total = off;
@@ -723,9 +793,13 @@ static int build_impl(const b2n_geom *geom, const void *omega, int64_t M, int64_
       B2N_LAUNCH_OK("k_own_cell_phase");
       out->own_exc = (int32_t *)(ws + c.own_exc);
       out->n_own_exc_max = total;
-      k_own_exc_list<<<1, 1024, 0, st>>>((const unsigned char *)(ws + c.own_excf), total, out->own_exc,
-                                         (int32_t *)(ws + c.own_counts) + 2);
-      B2N_LAUNCH_OK("k_own_exc_list");
+      const unsigned nb = (unsigned)ceil_div(total > 0 ? total : 1, 1024);
+      k_own_exc_count<<<nb, 1024, 0, st>>>((const unsigned char *)(ws + c.own_excf), total, (int32_t *)(ws + c.own_excb));
+      B2N_LAUNCH_OK("k_own_exc_count");
+      k_own_exc_write<<<nb, 1024, 0, st>>>((const unsigned char *)(ws + c.own_excf), total,
+                                           (const int32_t *)(ws + c.own_excb), out->own_exc,
+                                           (int32_t *)(ws + c.own_counts) + 2);
+      B2N_LAUNCH_OK("k_own_exc_write");
     }
     og.n_traj = n_traj;
     og.n_own_tiles = c.n_own_tiles;
@@ -739,7 +813,7 @@ static int build_impl(const b2n_geom *geom, const void *omega, int64_t M, int64_
     B2N_LAUNCH_OK("k_own_count");
     k_own_scan<<<1, 1024, 0, st>>>(nt_all, tiles, hist, bucket_base, bucket_fill, (int32_t *)(ws + c.own_counts));
     B2N_LAUNCH_OK("k_own_scan");
-    k_own_fill<<<(unsigned)ceil_div(nt_all * 32, threads), threads, 0, st>>>(
+    k_own_fill<<<(unsigned)nt_all, kOwnFillThreads, 0, st>>>(
         og, out->cell_start, out->perm, (const float *)(ws + c.own_hw), tiles, bucket_base, bucket_fill,
         (float4 *)(ws + c.own_visits), (int4 *)(ws + c.own_items));
     B2N_LAUNCH_OK("k_own_fill");
