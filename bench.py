@@ -175,6 +175,9 @@ def make_config(wl, B, world, adjoint_mode, fft):
             "fft": fft}
 
 
+LAUNCH_GRAPH = ("library-owned CUDA-graph replay (torchkbnufft_b200.set_graph_mode(True)): each operator call of the "
+                "timed steps is one cudaGraphLaunch of its captured kernels")
+LAUNCH_EAGER = "eager: every kernel launched by the host path of the module call"
 FFT_OWN = "own pruned passes (compile-time plans, libb200nufft.so)"
 FFT_CUFFT = "cuFFT via torch.fft + own pad/crop kernels"
 
@@ -340,6 +343,8 @@ def main():
     ap.add_argument("--no-partitions", dest="partitions", action="store_false",
                     help="skip the cfg5 strong-scaling and coil-sharded sections (default workload only)")
     ap.add_argument("--breakdown", action="store_true", help="print per-stage device times to stderr")
+    ap.add_argument("--launch", choices=["graph", "eager"], default="eager",
+                    help="measured steps go through the library's CUDA-graph replay (tkbn.set_graph_mode) or eager launches")
     ap.add_argument("--opt", action="append", default=[], help="engine option id=value (A/B experiments)")
     ap.add_argument("--fft", choices=["auto", "cufft", "own"], default="auto",
                     help="FFT passes: auto (default; own compile-time planned passes when every grid length has a "
@@ -395,6 +400,15 @@ def main():
         k = nu(x, om, smaps=s)
         return k, na(k, om, smaps=s)
 
+    # Launch mode of the measured steps: the library's own CUDA-graph replay (tkbn.set_graph_mode, public API: from the
+    # fourth call with the same argument buffers an operator call is one cudaGraphLaunch) or plain eager launches.
+    # Setup (plan build, twiddles, scratch, graph capture) happens in untimed calls BEFORE the W warm-up steps.
+    from torchkbnufft_b200._nufft import graphs as eng_graphs
+    use_graphs = args.launch == "graph"
+    tkbn.set_graph_mode(use_graphs)
+    for _ in range(6):
+        step()
+    torch.cuda.synchronize()
     for _ in range(args.warmup):
         step()
     torch.cuda.synchronize()
@@ -407,18 +421,40 @@ def main():
         dist.barrier()
     torch.cuda.synchronize()
     sampler.start()
-    launches_before = int(_lib.load().b2n_launch_count())
+    def own_launches():  # kernels of the library: launched eagerly (counted at every launch) + replayed from graphs
+        return int(_lib.load().b2n_launch_count()) + eng_graphs.replayed_kernel_count()
+
+    launches_before = own_launches()
     for i in range(args.steps):
         flush.fill_(i & 0xFF)
         starts[i].record()
         step()
         ends[i].record()
-    gpu_launches = int(_lib.load().b2n_launch_count()) - launches_before  # counted by the library at every launch
+    gpu_launches = own_launches() - launches_before
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     step_ms = [a.elapsed_time(b) for a, b in zip(starts, ends)]
     total_ms = sum(step_ms)
+    # the same K steps in the other launch mode (reported beside value as "other_launch_mode")
+    tkbn.set_graph_mode(not use_graphs)
+    for _ in range(6):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    for i in range(args.steps):
+        flush.fill_(i & 0xFF)
+        starts[i].record()
+        step()
+        ends[i].record()
+    torch.cuda.synchronize()
+    eager_ms = sum(a.elapsed_time(b) for a, b in zip(starts, ends))
+    if world > 1:
+        t = torch.tensor([eager_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        eager_ms = float(t.item())
+    tkbn.set_graph_mode(False)
     # The same K steps once more, back to back, now with CUDA events around the two interpolation launches (the
     # dominant kernels): their durations feed "roofline".  The four extra event records per step cost 11-15 us of
     # stream time (profiles/r01_h_pdl_ab.log), so this pass is kept out of "value" and reported beside it.
@@ -669,7 +705,7 @@ def main():
         graph_info = {"error": repr(exc)}
 
     # ---- the north-star partitions, device-timed with the max over ranks (BASELINE.json config 5 / coil split) -----
-    def timed_steps(fn, n_steps, n_warm=3):
+    def timed_steps(fn, n_steps, n_warm=6):
         """Mean device ms per call of fn over n_steps, L2 flushed between steps, barrier + synchronize on both
         sides, MAX over ranks."""
         for _ in range(n_warm):
@@ -700,6 +736,7 @@ def main():
         from torchkbnufft_b200 import parallel
 
         n_part = max(5, min(20, args.steps))
+        tkbn.set_graph_mode(use_graphs)  # as in the headline loop (timed_steps warms up before it times)
         # (a) BASELINE config 5, STRONG scaling: 64 slices x 16 coils, 64 / N slices per rank, shared trajectory,
         #     no collective on the data path (every slice is independent)
         try:
@@ -761,6 +798,7 @@ def main():
             del x0, s0, s_loc, buf
         except Exception as exc:  # pragma: no cover
             partitions["coil_sharded"] = {"error": repr(exc)}
+        tkbn.set_graph_mode(False)
 
     # ---- the stock reference package on the same GPU ("the existing Blackwell path") -----------------
     reference_cuda = None
@@ -806,14 +844,21 @@ def main():
                          "pair_algorithmic_bytes": fwd_b + adj_b, "pair_achieved": pair_achieved,
                          "pair_frac": pair_achieved / peak},
             "stages_ms": {k: round(v, 5) for k, v in stages.items()},
+            "launch": LAUNCH_GRAPH if use_graphs else LAUNCH_EAGER,
+            "other_launch_mode": {"launch": LAUNCH_EAGER if use_graphs else LAUNCH_GRAPH,
+                                  "ms_per_step": eager_ms / args.steps,
+                                  "value": world * units_per_step * args.steps / (eager_ms * 1e-3), "unit": UNIT,
+                                  "note": "the same K steps through the same module calls in the other launch mode "
+                                          "(bench.py --launch)"},
             "cuda_graph": graph_info,
             "partitions": partitions,
             "reference_cuda": reference_cuda,
             "cpu_baseline": cpu_baseline,
             "e2e": e2e,
-            # kernels of libb200nufft.so launched inside the timed region, counted by the library itself
-            # (b2n_launch_count; 7 per step with the own FFT passes: rows, columns, gather / grid zeroing, spread,
-            # columns, rows + coil sum; cudaMemsetAsync, the L2-flush fill and cuFFT are not counted)
+            # kernels of libb200nufft.so launched inside the timed region: counted by the library at every eager
+            # launch (b2n_launch_count) and, for replayed graphs, as the launches recorded at capture x replays
+            # (7 per step with the own FFT passes: rows, columns, gather / sample pre-pass, spread, columns,
+            # rows + coil sum; cudaMemsetAsync, the L2-flush fill and cuFFT are not counted)
             "gpu_launches": gpu_launches,
             "clocks": clocks,
         }

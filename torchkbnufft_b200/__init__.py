@@ -12,6 +12,7 @@ from . import functional, modules
 from ._math import absolute, complex_mult, complex_sign, conj_complex_mult, imag_exp, inner_product
 from ._nufft import utils as nufft_utils
 from ._nufft.dcomp import calc_density_compensation_function
+from ._nufft.graphs import get_graph_mode, set_graph_mode
 from ._nufft.interp import get_adjoint_mode, get_tiled_kernels, set_adjoint_mode, set_tiled_kernels
 from ._nufft.plan import clear_caches, get_plan_cache_mode, invalidate_plans, set_plan_cache_mode
 from ._nufft.spmat import calc_tensor_spmatrix
@@ -36,6 +37,7 @@ __all__ = [
     "conj_complex_mult",
     "functional",
     "get_adjoint_mode",
+    "get_graph_mode",
     "get_plan_cache_mode",
     "get_tiled_kernels",
     "imag_exp",
@@ -43,6 +45,7 @@ __all__ = [
     "invalidate_plans",
     "modules",
     "set_adjoint_mode",
+    "set_graph_mode",
     "set_plan_cache_mode",
     "set_tiled_kernels",
 ]

@@ -73,7 +73,7 @@ kernel_timer: Optional[KernelTimer] = None
 
 # owner-tile (output-stationary, register-accumulator) spread: on by default; rows = batch x coils
 owned_spread = True
-owned_spread_min_rows = 3
+owned_spread_min_rows = 2
 
 
 def _check_offsets(offsets: Optional[Tensor], n_offsets: int, ndim: int) -> None:
@@ -83,6 +83,14 @@ def _check_offsets(offsets: Optional[Tensor], n_offsets: int, ndim: int) -> None
         raise ValueError(
             f"offsets must list all {n_offsets} neighbour offsets (shape {(n_offsets, ndim)}), got {tuple(offsets.shape)}"
         )
+
+
+def lookup_plan(omega: Tensor, n_batch: int, tables: List[Tensor], n_shift: Tensor, numpoints: Tensor,
+                table_oversamp: Tensor, grid_size, device) -> TrajectoryPlan:
+    """The cached trajectory plan an interpolation call with these operator buffers uses (built if missing)."""
+    omega = normalize_omega(omega, n_batch, "image")
+    geo = get_geometry(tables, n_shift, numpoints, table_oversamp, tuple(grid_size))
+    return get_plan(geo, omega_for(omega, geo.cdtype, device, "image"))
 
 
 def table_interp(

@@ -493,6 +493,8 @@ def invalidate_plans(omega: Optional[Tensor] = None) -> None:
     """Forget the cached trajectory plans built from ``omega`` (all plans when ``None``).  Call this after writing
     to a trajectory tensor through anything that does not bump torch's version counter (``omega.data``, DLPack,
     a custom kernel): the cache key is (storage pointer, version), so such a write is otherwise invisible."""
+    from . import graphs as _graphs
+    _graphs.clear_graphs()  # captured graphs hold pointers into the plans
     with _LOCK:
         if omega is None:
             _PLAN_CACHE.clear()
@@ -515,6 +517,8 @@ def invalidate_plans(omega: Optional[Tensor] = None) -> None:
 
 def clear_caches() -> None:
     """Drop every cached geometry and trajectory plan (frees their device memory)."""
+    from . import graphs as _graphs
+    _graphs.clear_graphs()
     _PLAN_CACHE.clear()
     _PLAN_FAST.clear()
     _OMEGA_CAST.clear()

@@ -11,6 +11,7 @@ from torch import Tensor
 from .._autograd.interp import KbTableInterpAdjoint, KbTableInterpForward
 from .._autograd.nufft import ApodPad, CropApodCoilsum, FusedFftAdjoint, FusedFftForward, ToeplitzFilter
 from .._nufft import fft as _fft
+from .._nufft import graphs as _graphs
 from .._nufft import interp as _interp
 from .._nufft.plan import host_ints as _ints
 from .._nufft import spmat as _spmat
@@ -36,6 +37,15 @@ def sense_nufft_forward(image: Tensor, smaps: Optional[Tensor], scaling_coef: Te
     grid_size = _ints(grid_size)
     scale = _fft.ortho_scale(grid_size, normalized)
     record = _needs_grad(image)
+    if not record and _graphs.get_graph_mode() and not _graphs.in_replay_scope():
+        with _graphs.replay_scope():
+            return _graphs.replay_or_run(
+                "nufft_forward", (image, smaps), (scaling_coef, n_shift, numpoints, table_oversamp) + tuple(tables), omega,
+                (grid_size, scale),
+                lambda: sense_nufft_forward(image, smaps, scaling_coef, grid_size, omega, tables, n_shift, numpoints,
+                                            table_oversamp, offsets, norm),
+                lambda: _interp.lookup_plan(omega, image.shape[0], tables, n_shift, numpoints, table_oversamp, grid_size,
+                                            image.device))
     n_rows = image.shape[0] * (smaps.shape[1] if smaps is not None else image.shape[1])
     if _fft.fused_fft_available(image.dtype, grid_size, n_rows):
         grid = (FusedFftForward.apply(image, smaps, scaling_coef, grid_size, scale) if record else
@@ -58,6 +68,16 @@ def sense_nufft_adjoint(data: Tensor, smaps: Optional[Tensor], scaling_coef: Ten
     grid_sizes = _ints(grid_size)
     scale = _fft.ortho_scale(grid_sizes, normalized)
     fused = _fft.fused_fft_available(data.dtype, grid_sizes, data.shape[0] * data.shape[1])
+    if (_graphs.get_graph_mode() and not _graphs.in_replay_scope() and not _needs_grad(data)
+            and not (smaps is not None and smaps.requires_grad)):
+        with _graphs.replay_scope():
+            return _graphs.replay_or_run(
+                "nufft_adjoint", (data, smaps), (scaling_coef, n_shift, numpoints, table_oversamp) + tuple(tables), omega,
+                (grid_sizes, _ints(im_size), scale, _interp.get_adjoint_mode()),
+                lambda: sense_nufft_adjoint(data, smaps, scaling_coef, im_size, grid_size, omega, tables, n_shift,
+                                            numpoints, table_oversamp, offsets, norm),
+                lambda: _interp.lookup_plan(omega, data.shape[0], tables, n_shift, numpoints, table_oversamp, grid_sizes,
+                                            data.device))
     if not _needs_grad(data) and not (smaps is not None and smaps.requires_grad):
         grid = _interp.table_interp_adjoint(data, omega, tables, n_shift, numpoints, table_oversamp, offsets, grid_size)
         if fused:
