@@ -379,7 +379,7 @@ __device__ __forceinline__ void fft_line_pair(int t, float4 *sm, int es, const f
 #endif  // __CUDACC__
 
 // Plans (N, R0, R1, R2) for the grid lengths 2x-oversampled acquisitions use (BASELINE configs: 256, 512, 640,
-// 768).  R0 is 8 or 16 (padding period), the leg strides N/R1 and N/R2 are multiples of R0, R2 = 1 means two
+// 768; the reference notebooks' 400 -> 800; 1152, 1536 and other 5-smooth sizes).  R0 is 8 or 16 (padding period), the leg strides N/R1 and N/R2 are multiples of R0, R2 = 1 means two
 // stages.  Every other length takes the run-time passes or cuFFT.
 #define B2N_FAST_PLANS(X, ...)                                                                                  \
   X(64, 8, 8, 1, __VA_ARGS__) X(96, 8, 12, 1, __VA_ARGS__) X(128, 8, 16, 1, __VA_ARGS__)                       \
@@ -388,7 +388,10 @@ __device__ __forceinline__ void fft_line_pair(int t, float4 *sm, int es, const f
   X(448, 8, 8, 7, __VA_ARGS__) X(480, 8, 12, 5, __VA_ARGS__) X(512, 8, 8, 8, __VA_ARGS__)                      \
   X(576, 16, 12, 3, __VA_ARGS__) X(640, 8, 8, 10, __VA_ARGS__) X(768, 8, 8, 12, __VA_ARGS__)                   \
   X(896, 16, 8, 7, __VA_ARGS__) X(960, 16, 12, 5, __VA_ARGS__) X(1024, 8, 8, 16, __VA_ARGS__)                  \
-  X(1280, 16, 8, 10, __VA_ARGS__) X(2048, 16, 16, 8, __VA_ARGS__)
+  X(1280, 16, 8, 10, __VA_ARGS__) X(2048, 16, 16, 8, __VA_ARGS__)                                               \
+  X(160, 8, 4, 5, __VA_ARGS__) X(200, 8, 5, 5, __VA_ARGS__) X(240, 8, 10, 3, __VA_ARGS__)                      \
+  X(400, 8, 10, 5, __VA_ARGS__) X(800, 8, 10, 10, __VA_ARGS__) X(1152, 8, 12, 12, __VA_ARGS__)                 \
+  X(1536, 16, 8, 12, __VA_ARGS__) X(1600, 16, 10, 10, __VA_ARGS__) X(1920, 16, 12, 10, __VA_ARGS__)
 
 #define B2N_FAST_PLAN_USING(N, R0, R1, R2, ...) using Plan##N = Plan<N, R0, R1, R2>;
 B2N_FAST_PLANS(B2N_FAST_PLAN_USING, 0)
