@@ -110,40 +110,54 @@ typedef struct b2n_points {
                           the consecutive ranks [tile_sub_start[t], tile_sub_start[t+1]) (the sub_* arrays themselves
                           are ordered longest-first for load balance) */
   int32_t *tile_sub_start; /* [n_traj*prod(n_tiles)] first rank of each tile; the last tile ends at *n_sub */
-  /* Owner-tile visit lists for the output-stationary spread (b2n_interp_adjoint_ordered; 2-D complex64 J = 6 plans on
-   * grids with every K_d >= 16 whose geometry carries rtable_dev and power-of-two L_d, so that the table index of
-   * neighbour j is exactly that of neighbour 0 minus j L_d; own_tile == 0 and NULL pointers otherwise).  The grid is cut
-   * into OUTPUT tiles of own_tile = 4 rows x 8 columns; a "visit" is one (point, output tile) pair whose J x J
-   * footprint intersects the tile (3.66 per point on average, at most 6, or 12 where the last tile of an axis has
-   * fewer than J - 1 cells); the visits of a tile are listed in a fixed order (window cell
+  /* Owner-tile visit lists for the output-stationary spread (b2n_interp_adjoint_ordered; 2-D / 3-D complex64 J = 6
+   * plans on grids with every K_d >= 16 whose geometry carries rtable_dev and power-of-two L_d, so that the table index
+   * of neighbour j is exactly that of neighbour 0 minus j L_d; own_tile == 0 and NULL pointers otherwise).  The grid is
+   * cut into OUTPUT tiles of 4 x 8 cells (2-D) or 4 x 4 x 8 cells (3-D; 8 along the last, contiguous axis); a "visit" is
+   * one (point, output tile) pair whose footprint intersects the tile (3.66 per point on average in 2-D, 8.2 in 3-D);
+   * the visits of a tile are listed in a fixed order (window cell
    * row-major, then sorted slot) and cut into work items of at most own_cap visits.  Every output tile has at
    * least one item (an empty one writes zeros), so the spread needs no zero-initialised grid and no atomics. */
   int32_t own_tile;          /* rows of an output tile (4; 8 columns), or 0 when the lists were not built */
   int32_t own_cap;           /* max visits per work item */
-  int32_t n_own_tiles[2];    /* output tiles per dimension = {ceil(K_y / own_tile), ceil(K_x / 8)} */
+  int32_t n_own_tiles[3];    /* output tiles per dimension: ceil(K_d / own_tile), ceil(K_last / 8) along the last one */
+  int32_t own_pad_;
   int64_t n_own_items_max;   /* capacity of own_items (upper bound on own_counts[0]) */
-  void *own_visits;          /* 64-byte records [<= 6*n_traj*M, see above]: float hy[4] (row weights r_y[row - ry]),
+  void *own_visits;          /* 2-D: 64-byte records [<= 6*n_traj*M, see above]: float hy[4] (row weights r_y[row - ry]),
                                 float hx[8] (column weights +-r_x[column - rx]; zero outside the footprint; the sign
                                 is negative when the footprint wrapped around the grid and exp(1i table_phase K) =
                                 -1), int32 sample index inside its trajectory, 12 unused bytes; (ry, rx) = base
-                                cell minus tile origin */
+                                cell minus tile origin.
+                                3-D: int32x4 index records [<= 18*n_traj*M]: {sorted slot, sample index,
+                                (r0+16) | (r1+16) << 8 | (r2+16) << 16, sign flag}; the kernel forms the window
+                                weights from own_hw while staging */
   void *own_items;           /* int32x4 [n_own_items_max]: {traj*prod(n_own_tiles) + tile, first visit, visits | chunk
-                                index inside the tile << 12, tile row << 16 | tile column}, longest first */
+                                index inside the tile << 12, tile row << 16 | tile column (2-D) or the tile's row-major
+                                index (3-D)}, longest first */
   void *own_tiles;           /* int32x4 [n_traj*prod(n_own_tiles)]: {visits, first visit, chunks, first partial-sum slot
                                 (-1 for single-chunk tiles)} */
-  int32_t *own_counts;       /* device: [0] = items in use, [1] = partial-sum slots in use, [2] = exception points */
-  float *own_hw;             /* [n_traj*M][12]: r_y[0..5], r_x[0..5] of the point's neighbours */
+  int32_t *own_counts;       /* device: [0] = items in use, [1] = partial-sum slots in use, [2] = exception points,
+                                [3] = entries of own_xv in use */
+  float *own_hw;             /* [n_traj*M][12] (2-D): r_y[0..5], r_x[0..5] of the point's neighbours; [n_traj*M][24] (3-D):
+                                r_0, r_1, r_2, -r_2 */
   void *own_fac;             /* complex64 [n_traj*M]: conj of the point's phase factor (adjoint form): fftshift phase
                                 times exp(-1i sum_d table_phase[d] (x_d(neighbour 0) + wrapped base_d)) */
-  void *own_q;               /* complex64 [K_y + K_x]: exp(-1i table_phase[d] cell), the per-cell factor of the adjoint */
+  void *own_q;               /* complex64 [sum_d K_d]: exp(-1i table_phase[d] cell), the per-cell factor of the adjoint */
   /* Exception points: the factored phase needs table_index(neighbour j) == table_index(neighbour 0) - j L_d.  That
    * holds whenever tm - (base + j) is exact in the trajectory's precision; it can fail by one table step for a
-   * point within J cells of the k-space origin whose distance to a neighbour is a rounding tie.  Such points get
-   * zero weights in own_hw / own_visits and are spread afterwards, in list order, with their complex records (coef)
-   * by a fix-up kernel, so the result keeps the reference's table indices for every neighbour. */
+   * point within J cells of the k-space origin whose distance to a neighbour is a rounding tie (radial trajectories
+   * sampled on exact multiples of the grid spacing have a few thousand of them around the centre).  Such points get
+   * zero weights in own_hw / own_visits and are spread afterwards with their complex records (coef) by a fix-up kernel
+   * that is output-stationary as well: every output tile has the list of the exception points that reach it, in
+   * ascending slot order, and adds their contributions to its cells once -- deterministic, and the result keeps the
+   * reference's table indices for every neighbour. */
   int32_t *own_exc;          /* [n_own_exc_max] sorted slots of the exception points, ascending */
   int64_t n_own_exc_max;     /* capacity of own_exc = n_traj*M; a caller that has read own_counts[2] back may lower it
                                 (0 = no fix-up launch) */
+  void *own_xt;              /* int32x2 [n_traj*prod(n_own_tiles)]: {first entry, entries} of the tile in own_xv */
+  void *own_xv;              /* int32x2 [n_own_xv_max]: {sorted slot, (r0+16) | (r1+16) << 8 | (r2+16) << 16} per
+                                (exception point, output tile) pair, r = footprint origin minus tile origin */
+  int64_t n_own_xv_max;      /* capacity of own_xv (own_counts[3] = entries in use; the fix-up traps beyond it) */
 } b2n_points;
 
 /* engine options (process-wide; for A/B measurements and tests) */
@@ -169,7 +183,8 @@ enum b2n_option {
                                columns; a pass must also read >= 32 MB unless 32 is set.  Default 19. */
   B2N_OPT_ADJ_OWNED = 7, /* 1 (default): b2n_interp_adjoint_ordered uses the output-stationary owner-tile spread where
                             the plan carries visit lists (2-D complex64 J = 6); 0: the scratch-tile + merge kernels */
-  B2N_OPT_OWN_CAP = 8, /* visits per work item of the owner-tile spread, read when a plan is built (default 64) */
+  B2N_OPT_OWN_CAP = 8, /* visits per work item of the owner-tile spread, read when a plan is built (0 = default: 128 in
+                          2-D, 1024 in 3-D; at most 4095) */
   B2N_OPT_COUNT
 };
 B2N_API int b2n_set_option(int option, int value);

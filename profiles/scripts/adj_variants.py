@@ -70,6 +70,6 @@ for name in names or ["cfg2"]:
             fn(); torch.cuda.synchronize(); fn()
             print(f"{name} B={B} C={C} owner tiles rows {rows} (opt {ow}) cap {cap:4d}: adjoint interp {timeit(fn):8.1f} us   rel diff {err:.2e} "
                   f"bit-reproducible {same} items {pl.struct.n_own_items_max} slots {pl.own_slots}", flush=True)
-        lib.b2n_set_option(_lib.OPT_OWN_CAP, 64)
+        lib.b2n_set_option(_lib.OPT_OWN_CAP, 0)
         lib.b2n_set_option(_lib.OPT_ADJ_OWNED, 1)
         tkbn.clear_caches()

@@ -38,7 +38,7 @@ def test_struct_layouts_match_header_sizes():
     # b2n_geom: 2*int32 + 3*int64 + 3*int32 + 3*int32 + 3*int64 + 3*ptr + 3*double + 3*ptr + 3*double
     assert ctypes.sizeof(_lib.Geom) == 8 + 24 + 12 + 12 + 24 + 24 + 24 + 24 + 24
     # ... + the owner-tile visit lists: 4*int32 + int64 + 4*ptr + 3*ptr (real-weight records) + ptr + int64 (exceptions)
-    assert ctypes.sizeof(_lib.Points) == 16 + 16 + 12 + 12 + 16 + 13 * 8 + 16 + 8 + 4 * 8 + 3 * 8 + 16
+    assert ctypes.sizeof(_lib.Points) == 16 + 16 + 12 + 12 + 16 + 13 * 8 + 16 + 8 + 8 + 4 * 8 + 3 * 8 + 16 + 24
     # and the library's own sizeof (compiled from the header) agrees with the ctypes mirrors
     lib = _lib.load()
     gsz, psz = ctypes.c_size_t(0), ctypes.c_size_t(0)

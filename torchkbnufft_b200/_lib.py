@@ -77,7 +77,8 @@ class Points(Structure):
         ("tile_sub_start", c_void_p),
         ("own_tile", c_int32),
         ("own_cap", c_int32),
-        ("n_own_tiles", c_int32 * 2),
+        ("n_own_tiles", c_int32 * 3),
+        ("own_pad_", c_int32),
         ("n_own_items_max", c_int64),
         ("own_visits", c_void_p),
         ("own_items", c_void_p),
@@ -88,6 +89,9 @@ class Points(Structure):
         ("own_q", c_void_p),
         ("own_exc", c_void_p),
         ("n_own_exc_max", c_int64),
+        ("own_xt", c_void_p),
+        ("own_xv", c_void_p),
+        ("n_own_xv_max", c_int64),
     ]
 
 

@@ -179,6 +179,7 @@ class Geometry:
         self.key: tuple = ()
 
 
+OWN_SCRATCH_SYNC_BYTES = 1 << 30  # upper-bound scratch size from which the plan's counts are read synchronously
 REAL_TABLE_TOL = 2e-6  # |table - r exp(-i p x)| / max|table| allowed when the tables are declared to be of that form
 
 
@@ -432,6 +433,22 @@ class TrajectoryPlan:
         hit = self._own_scratch.get(key)
         if hit is None:
             nbytes, nzero = ctypes.c_size_t(0), ctypes.c_size_t(0)
+            if self.own_slots == 0 and not torch.cuda.is_current_stream_capturing():
+                # The partial-sum slots are sized by the plan's upper bound until the device counts have been read
+                # back; for large 3-D plans that bound is gigabytes, so read the counts now (one synchronisation per
+                # plan) rather than allocate it.
+                _lib.check(lib.b2n_interp_adjoint_ordered_layout(ctypes.byref(geo.struct), ctypes.byref(self.struct), B,
+                                                                 C, layout, 0, ctypes.byref(nbytes), ctypes.byref(nzero)),
+                           "b2n_interp_adjoint_ordered_layout")
+                if nbytes.value > OWN_SCRATCH_SYNC_BYTES:
+                    base = self.workspace.data_ptr()
+                    off = int(self.struct.own_counts) - base
+                    n_items, n_slots, n_exc = (int(v) for v in self.workspace[off:off + 12].view(torch.int32).cpu())
+                    if 0 < n_items <= self.struct.n_own_items_max:
+                        self.struct.n_own_items_max = n_items
+                        self.own_slots = max(n_slots, 1)
+                        if 0 <= n_exc <= self.struct.n_own_exc_max:
+                            self.struct.n_own_exc_max = n_exc
             _lib.check(lib.b2n_interp_adjoint_ordered_layout(ctypes.byref(geo.struct), ctypes.byref(self.struct), B, C,
                                                              layout, self.own_slots, ctypes.byref(nbytes),
                                                              ctypes.byref(nzero)), "b2n_interp_adjoint_ordered_layout")

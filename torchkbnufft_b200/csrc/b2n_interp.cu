@@ -393,7 +393,7 @@ extern int g_fast_fft;
 int g_pdl = 1;
 int g_prefetch = 19;
 int g_zero_kernel = 1;
-static int g_options[B2N_OPT_COUNT] = {1, 0, 0, 0, 1, 1, 19, 1, 64};
+static int g_options[B2N_OPT_COUNT] = {1, 0, 0, 0, 1, 1, 19, 1, 0};
 
 // With very few 2-D (batch, coil) rows most coil lanes of a tiled gather CTA idle while its per-point cost stays the
 // same: the one-thread-per-point kernel (k_fwd_point6_2d) wins up to 3 rows (16 vs 29 us for one row, 30 vs 41 us for

@@ -57,7 +57,7 @@ struct OwnArgs {
 // (B, coil chunk, M, 4 CPL coils) in the form the inner loop reads -- per coil pair (re, re', im, im') for CPL >= 2,
 // (re, im) for CPL = 1 -- and multiplies every sample by its point's phase factor (own_fac, looked up through
 // inv_perm), so that a visit is ONE contiguous 32 CPL byte row fetched with 16-byte copies.
-template <int CPL>
+template <int CPL, bool PLANAR>
 __global__ void __launch_bounds__(256) k_own_pack(const float2 *__restrict__ kdata, float4 *__restrict__ packed, int C,
                                                   int64_t M, int n_chunks, int n_traj, const int32_t *__restrict__ inv_perm,
                                                   const float2 *__restrict__ fac) {
@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(256) k_own_pack(const float2 *__restrict__ kda
     const int m = e / PARTS, part = e - m * PARTS;
     if (m0 + m < M) {
       const float2 a = tile[2 * part][m], c = tile[2 * part + 1][m];
-      out[(int64_t)m * PARTS + part] = CPL >= 2 ? make_float4(a.x, c.x, a.y, c.y) : make_float4(a.x, a.y, c.x, c.y);
+      out[(int64_t)m * PARTS + part] = PLANAR ? make_float4(a.x, c.x, a.y, c.y) : make_float4(a.x, a.y, c.x, c.y);
     }
   }
 }
@@ -298,41 +298,286 @@ __global__ void __launch_bounds__(32, MINB) k_adj_own_2d(OwnArgs a, const float4
   }
 }
 
+// ---- 3-D: 4 x 4 x 8 output tiles ------------------------------------------------------------------------------------
+// Same scheme one dimension up (216 neighbours per point).  Lanes = 8 cells along the last (contiguous) axis x 4 along
+// the middle axis; registers = 4 cells along the first axis x CK coils, ALL coils of the chunk in every lane (8 at
+// BASELINE config 4), planar over coil pairs.  Per visit a lane forms its weight h1[y] h2[x] once, then
+//   acc[z][c] += (h0[z] * h1[y] * h2[x]) * v[c]         5 FMUL + 4 CK FFMA2 (32 at 8 coils)
+// with the samples read as warp-uniform 16-byte loads.  A point is visited by 8.2 tiles on average, so a 64-byte record
+// per visit as in 2-D would be gigabytes: the visit list holds 16-byte index records and the window weights are formed
+// while staging -- copies of 4 bytes with a zero source size outside the footprint, lanes = 2 visits x 16 weight slots
+// so that one instruction touches two points' records (two cache lines) only.
+constexpr int kO3Z = 4, kO3Y = 4, kO3X = 8;  // tile edges: axis 0 (registers), axis 1 (lane groups), axis 2 (lanes)
+constexpr int kO3HW = 24;                    // floats per point record: h0[6], h1[6], h2[6], -h2[6]
+constexpr int kO3W = 16;                     // staged weight slots per visit: h0[4], h1[4], h2[8]
+
+struct Own3Args {
+  int K[3], nt[3], C;
+  int64_t M, Kprod, n_own_tiles;
+  int n_traj, n_chunks;
+  const int4 *visits, *items, *tiles;
+  const int32_t *counts;
+  const float *hw;
+  const float2 *q;  // per-cell phase factors: [K0], [K1], [K2]
+};
+
+template <int CK> constexpr size_t own3_smem_bytes() {
+  return sizeof(int4) * 3 * kOR + sizeof(float) * (2 * kOR + 1) * kO3W + sizeof(float4) * (2 * kOR + 1) * (CK / 2);
+}
+
+template <int CK> struct Own3Ops {
+  float4 h0;
+  float h1, h2;
+  float4 v[CK / 2];  // (re, re', im, im') per coil pair
+};
+
+template <int CK>
+B2N_D void own3_load(Own3Ops<CK> &o, const float *__restrict__ w, const float *__restrict__ h1p,
+                     const float *__restrict__ h2p, const float4 *__restrict__ vp) {
+  o.h0 = *reinterpret_cast<const float4 *>(w);
+  o.h1 = *h1p;
+  o.h2 = *h2p;
+#pragma unroll
+  for (int p = 0; p < CK / 2; ++p) o.v[p] = vp[p];
+}
+
+template <int CK> B2N_D void own3_update(float2 (&acc)[kO3Z][CK], const Own3Ops<CK> &o) {
+  const float wl = o.h1 * o.h2;
+  const float w[kO3Z] = {o.h0.x * wl, o.h0.y * wl, o.h0.z * wl, o.h0.w * wl};
+#pragma unroll
+  for (int z = 0; z < kO3Z; ++z) {
+    const float2 ww = make_float2(w[z], w[z]);
+#pragma unroll
+    for (int p = 0; p < CK / 2; ++p) {
+      acc[z][2 * p] = __ffma2_rn(ww, make_float2(o.v[p].x, o.v[p].y), acc[z][2 * p]);
+      acc[z][2 * p + 1] = __ffma2_rn(ww, make_float2(o.v[p].z, o.v[p].w), acc[z][2 * p + 1]);
+    }
+  }
+}
+
+template <int CK, int MINB, int U>
+__global__ void __launch_bounds__(32, MINB) k_adj_own_3d(Own3Args a, const float4 *__restrict__ packed, float2 *__restrict__ grid,
+                                                   float2 *__restrict__ partials, unsigned *__restrict__ counters,
+                                                   int slot_cap) {
+  constexpr int PARTS = CK / 2;  // 16-byte parts per sample row
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  int4 *s_idx = reinterpret_cast<int4 *>(smem_raw);                       // [3][kOR] index records
+  float *s_w = reinterpret_cast<float *>(s_idx + 3 * kOR);                // [2][kOR][kO3W] window weights (+ 1 spare)
+  float4 *s_val = reinterpret_cast<float4 *>(s_w + (2 * kOR + 1) * kO3W);  // [2][kOR][PARTS] samples (+ 1 spare)
+  const int lane = threadIdx.x;
+  const int n_items = a.counts[0];
+  const int4 item = a.items[blockIdx.x];
+  if ((int)blockIdx.x >= n_items) return;
+  const int4 tinfo = a.tiles[item.x];
+  const int t2 = item.w % a.nt[2], t01 = item.w / a.nt[2], t1 = t01 % a.nt[1], t0 = t01 / a.nt[1];
+  const int o0 = t0 * kO3Z, o1 = t1 * kO3Y, o2 = t2 * kO3X;
+  const int b = a.n_traj == 1 ? (int)blockIdx.z : item.x / (int)a.n_own_tiles;
+  const int c0 = blockIdx.y * CK;
+  const int n = item.z & 0xfff, chunk = item.z >> 12;
+  const int rounds = (n + kOR - 1) / kOR;
+  const int4 *vis = a.visits + item.y;
+
+  // staging roles, fixed per lane.  Weights: lane = (visit of 2, slot of 16); slot class 0 / 1 / 2 = axis.
+  const int wv = lane >> 4, slot = lane & 15;
+  const int cls = slot < 4 ? 0 : (slot < 8 ? 1 : 2);
+  const int local = slot - (cls == 2 ? 8 : 4 * cls);  // cell of the tile along the slot's axis
+  // Samples: lane = (visit of 32 / PARTS, 16-byte part).
+  constexpr int VPI = 32 / PARTS;
+  const int vi = lane / PARTS, part = lane - vi * PARTS;
+  const float4 *pk_lane = packed + ((int64_t)b * a.n_chunks + blockIdx.y) * a.M * PARTS + part;
+
+  auto issue_idx = [&](int round) {
+    if (round < rounds && lane < kOR) {
+      const int i = round * kOR + lane;
+      cp_async16(&s_idx[(round % 3) * kOR + lane], &vis[i < n ? i : n - 1]);  // past the end: repeat the last visit
+    }
+  };
+  auto issue_data = [&](int round) {
+    if (round >= rounds) return;
+    const int4 *idx = s_idx + (round % 3) * kOR;
+    float *w = s_w + (round & 1) * kOR * kO3W;
+    float4 *val = s_val + (round & 1) * kOR * PARTS;
+#pragma unroll
+    for (int k = 0; k < kOR / 2; ++k) {
+      const int i = 2 * k + wv;
+      const int4 e = idx[i];
+      const int r = ((e.z >> (8 * cls)) & 0xff) - 16;  // footprint origin along this axis, relative to the tile
+      const int j = local - r;
+      const bool on = (unsigned)j < (unsigned)kOJ;
+      // the record's fourth block is -h2: visits whose footprint wrapped around the grid with a sign flip read it
+      const float *src = a.hw + (int64_t)e.x * kO3HW + 6 * cls + (cls == 2 && e.w ? 6 : 0) + (on ? j : 0);
+      cp_async4z(w + i * kO3W + slot, src, on);
+    }
+#pragma unroll
+    for (int k = 0; k < kOR / VPI; ++k) {
+      const int i = vi + VPI * k;
+      cp_async16(val + i * PARTS + part, pk_lane + (size_t)(unsigned)idx[i].y * PARTS);
+    }
+  };
+
+  issue_idx(0);
+  issue_idx(1);
+  cp_async_commit();
+  griddep_wait();
+  float2 acc[kO3Z][CK];
+#pragma unroll
+  for (int z = 0; z < kO3Z; ++z)
+#pragma unroll
+    for (int k = 0; k < CK; ++k) acc[z][k] = make_float2(0.f, 0.f);
+  const int xl = lane & 7, yl = lane >> 3;
+  if (n > 0) {
+    cp_async_wait_all();
+    __syncwarp();
+    issue_data(0);
+    cp_async_commit();
+    for (int round = 0; round < rounds; ++round) {
+      cp_async_wait_all();
+      __syncwarp();
+      issue_data(round + 1);
+      issue_idx(round + 2);
+      cp_async_commit();
+      const float *w = s_w + (round & 1) * kOR * kO3W;
+      const float *h1p = w + 4 + yl, *h2p = w + 8 + xl;
+      const float4 *vp = s_val + (round & 1) * kOR * PARTS;
+      const int nb = min(kOR, n - round * kOR);
+      Own3Ops<CK> cur;
+      own3_load<CK>(cur, w, h1p, h2p, vp);
+#pragma unroll U
+      for (int i = 0; i < nb; ++i) {
+        w += kO3W;
+        h1p += kO3W;
+        h2p += kO3W;
+        vp += PARTS;
+        Own3Ops<CK> nxt;
+        own3_load<CK>(nxt, w, h1p, h2p, vp);
+        own3_update<CK>(acc, cur);
+        cur = nxt;
+      }
+    }
+  }
+
+  const int nch = tinfo.z;
+  if (nch > 1) {
+    const int64_t Bz = gridDim.z, per_slot = (int64_t)Bz * a.n_chunks;
+    const int64_t sub = (int64_t)blockIdx.z * a.n_chunks + blockIdx.y;
+    if (tinfo.w + nch > slot_cap) __trap();
+    float2 *mine = partials + (((int64_t)(tinfo.w + chunk)) * per_slot + sub) * (kO3Z * CK * 32);
+#pragma unroll
+    for (int z = 0; z < kO3Z; ++z)
+#pragma unroll
+      for (int k = 0; k < CK; ++k) __stcg(&mine[(z * CK + k) * 32 + lane], acc[z][k]);
+    __threadfence();
+    __syncwarp();
+    unsigned old = 0;
+    unsigned *ctr = counters + (int64_t)item.x * per_slot + sub;
+    if (lane == 0) old = atomicAdd(ctr, 1u);
+    old = __shfl_sync(0xffffffffu, old, 0);
+    if (old != (unsigned)(nch - 1)) return;
+    if (lane == 0) *ctr = 0u;
+    __threadfence();
+#pragma unroll
+    for (int z = 0; z < kO3Z; ++z)
+#pragma unroll
+      for (int k = 0; k < CK; ++k) acc[z][k] = make_float2(0.f, 0.f);
+    for (int j = 0; j < nch; ++j) {
+      const float2 *src = partials + (((int64_t)(tinfo.w + j)) * per_slot + sub) * (kO3Z * CK * 32);
+#pragma unroll
+      for (int z = 0; z < kO3Z; ++z)
+#pragma unroll
+        for (int k = 0; k < CK; ++k) {
+          const float2 p = __ldcg(&src[(z * CK + k) * 32 + lane]);
+          acc[z][k].x += p.x;
+          acc[z][k].y += p.y;
+        }
+    }
+  }
+  // store the tile times the per-cell phase factor: 8 lanes x 8 bytes = one 64-byte segment per (z, y, coil)
+  if (o1 + yl < a.K[1] && o2 + xl < a.K[2]) {
+    const float2 q1 = a.q[a.K[0] + o1 + yl], q2 = a.q[a.K[0] + a.K[1] + o2 + xl];
+    const float2 q12 = make_float2(q1.x * q2.x - q1.y * q2.y, q1.x * q2.y + q1.y * q2.x);
+#pragma unroll
+    for (int z = 0; z < kO3Z; ++z) {
+      if (o0 + z >= a.K[0]) break;
+      const float2 q0 = a.q[o0 + z];
+      const float2 qq = make_float2(q0.x * q12.x - q0.y * q12.y, q0.x * q12.y + q0.y * q12.x);
+      const int64_t cell = ((int64_t)(o0 + z) * a.K[1] + o1 + yl) * a.K[2] + o2 + xl;
+#pragma unroll
+      for (int k = 0; k < CK; ++k) {
+        const int c = c0 + k;
+        if (c < a.C) {
+          const float2 s2 = (k & 1) ? make_float2(acc[z][k - 1].y, acc[z][k].y) : make_float2(acc[z][k].x, acc[z][k + 1].x);
+          grid[((int64_t)b * a.C + c) * a.Kprod + cell] = make_float2(s2.x * qq.x - s2.y * qq.y, s2.x * qq.y + s2.y * qq.x);
+        }
+      }
+    }
+  }
+}
+
 // ---- exception points ---------------------------------------------------------------------------------------------
 // Points whose neighbours do not share one table offset (b2n_points.own_exc: rounding ties next to the k-space
-// origin; none on ordinary trajectories) carry zero weights in the visit lists.  They are spread here with their
-// complex records, one after the other in list order (two of them may touch the same cell), each (coil, neighbour) by
-// its own thread: deterministic, and launched only while the plan's exception count is not known to be zero.
+// origin) carry zero weights in the visit lists.  They are spread here with their complex records, output-stationary
+// like the main kernel: a CTA owns an output tile, a thread one of its cells, and adds the contributions of the
+// tile's exception points (own_xt / own_xv, ascending slot order) to that cell once -- parallel over tiles and
+// deterministic.  Launched only while the plan's exception count is not known to be zero.
 struct OwnFixArgs {
-  int Ky, Kx, C, n_traj;
-  int64_t M, Kprod, cap;
-  const int32_t *counts, *exc, *perm, *base;
+  int K[3], nt[3], C, n_traj;
+  int64_t M, Kprod, n_own_tiles, xcap;
+  const int32_t *counts, *perm;
+  const int2 *xt, *xv;
   const float2 *coef;
 };
 
-__global__ void __launch_bounds__(256) k_own_fix(OwnFixArgs a, const float2 *__restrict__ kdata, float2 *__restrict__ grid) {
+template <int ND>
+__global__ void __launch_bounds__(128) k_own_fix(OwnFixArgs a, const float2 *__restrict__ kdata, float2 *__restrict__ grid) {
   griddep_wait();
-  const int64_t n = min((int64_t)a.counts[2], a.cap);
-  for (int64_t e = 0; e < n; ++e) {
-    const int64_t s = a.exc[e];
-    const int b = a.n_traj == 1 ? (int)blockIdx.z : (int)(s / a.M);
-    const int64_t m = a.perm[s];
-    const int by = a.base[2 * s], bx = a.base[2 * s + 1];
-    const float2 *rec = a.coef + s * 2 * kOJ;
-    for (int idx = threadIdx.x; idx < kOJ * kOJ * a.C; idx += blockDim.x) {
-      const int c = idx / (kOJ * kOJ), t = idx - c * kOJ * kOJ, jy = t / kOJ, jx = t - jy * kOJ;
-      const float2 cy = rec[jy], cx = rec[kOJ + jx];
-      const float2 w = make_float2(cy.x * cx.x - cy.y * cx.y, cy.x * cx.y + cy.y * cx.x);
-      const float2 v = kdata[((int64_t)b * a.C + c) * a.M + m];
-      int y = by + jy, x = bx + jx;
-      y -= y >= a.Ky ? a.Ky : 0;
-      x -= x >= a.Kx ? a.Kx : 0;
-      float2 *dst = grid + ((int64_t)b * a.C + c) * a.Kprod + (int64_t)y * a.Kx + x;
-      float2 g = *dst;
-      cmacf_conj(g, w, v);
-      *dst = g;
+  if (a.counts[3] > a.xcap) __trap();  // more (exception point, tile) pairs than own_xv holds: fail loudly
+  const int2 seg = a.xt[blockIdx.x];
+  if (seg.y == 0) return;
+  const int64_t traj = blockIdx.x / a.n_own_tiles;
+  int64_t tid = blockIdx.x - traj * a.n_own_tiles;
+  int o[3] = {0, 0, 0}, cl[3] = {0, 0, 0};
+  const int t = threadIdx.x;
+  if (ND == 3) {
+    cl[0] = t >> 5;
+    cl[1] = (t >> 3) & 3;
+    cl[2] = t & 7;
+  } else {
+    cl[0] = t >> 3;
+    cl[1] = t & 7;
+  }
+  int64_t cell = 0;
+  bool inside = true;
+  for (int d = ND - 1; d >= 0; --d) {
+    o[d] = (int)(tid % a.nt[d]) * (d == ND - 1 ? 8 : 4);
+    tid /= a.nt[d];
+  }
+  for (int d = 0; d < ND; ++d) {
+    inside = inside && o[d] + cl[d] < a.K[d];
+    cell = cell * a.K[d] + o[d] + cl[d];
+  }
+  if (!inside) return;
+  const int b = a.n_traj == 1 ? (int)blockIdx.z : (int)traj;
+  for (int c = 0; c < a.C; ++c) {
+    float2 acc = make_float2(0.f, 0.f);
+    for (int e = 0; e < seg.y; ++e) {
+      const int2 xv = a.xv[seg.x + e];
+      const float2 *rec = a.coef + (int64_t)xv.x * ND * kOJ;
+      float2 w = make_float2(1.f, 0.f);
+      bool on = true;
+#pragma unroll
+      for (int d = 0; d < ND; ++d) {
+        const int j = cl[d] - (((xv.y >> (8 * d)) & 0xff) - 16);
+        on = on && (unsigned)j < (unsigned)kOJ;
+        const float2 cw = rec[d * kOJ + (on ? j : 0)];
+        w = make_float2(w.x * cw.x - w.y * cw.y, w.x * cw.y + w.y * cw.x);
+      }
+      if (on) cmacf_conj(acc, w, kdata[((int64_t)b * a.C + c) * a.M + a.perm[xv.x]]);
     }
-    __syncthreads();
+    float2 *dst = grid + ((int64_t)b * a.C + c) * a.Kprod + cell;
+    float2 gv = *dst;
+    gv.x += acc.x;
+    gv.y += acc.y;
+    *dst = gv;
   }
 }
 
@@ -340,12 +585,18 @@ __global__ void __launch_bounds__(256) k_own_fix(OwnFixArgs a, const float2 *__r
 int g_adj_owned = 1;
 
 static bool own_ready(const b2n_geom *g, const b2n_points *p, int layout) {
-  return g_adj_owned && g->dtype == B2N_C64 && g->ndim == 2 && layout == B2N_COIL_MAJOR && g->numpoints[0] == kOJ &&
-         g->numpoints[1] == kOJ && p->own_tile == kOTR && p->own_visits && p->own_items && p->own_tiles &&
-         p->own_counts && p->own_fac && p->own_q && p->own_exc && p->n_points > 0;
+  if (!g_adj_owned || g->dtype != B2N_C64 || (g->ndim != 2 && g->ndim != 3) || layout != B2N_COIL_MAJOR) return false;
+  for (int d = 0; d < g->ndim; ++d)
+    if (g->numpoints[d] != kOJ) return false;
+  return p->own_tile == kOTR && p->own_visits && p->own_items && p->own_tiles && p->own_counts && p->own_fac &&
+         p->own_q && p->own_exc && p->own_xt && p->own_xv && p->own_hw && p->n_points > 0;
 }
 
-static int own_cpl(int64_t C) { return C > 8 ? 4 : (C > 4 ? 2 : 1); }
+// coils per warp: 2-D 4 CPL (lanes hold coil groups), 3-D CK (every lane holds all of them)
+static int own_chunk_coils(int ndim, int64_t C) {
+  if (ndim == 3) return C > 4 ? 8 : 4;
+  return C > 8 ? 16 : (C > 4 ? 8 : 4);
+}
 
 // scratch = [arrival counters][pre-packed samples][partial tiles]; the partial tiles are sized by the plan's upper
 // bound unless the caller passes the partial-slot count it read back from own_counts[1]
@@ -354,12 +605,13 @@ struct OwnScratch {
 };
 static OwnScratch own_scratch_layout(const b2n_points *p, int64_t B, int64_t C, int64_t n_slots) {
   OwnScratch o;
-  const int cpl = own_cpl(C);
-  const int64_t n_chunks = ceil_div(C, 4 * cpl), Bz = p->n_traj == 1 ? B : 1;
-  const int64_t n_tiles_all = (int64_t)p->n_own_tiles[0] * p->n_own_tiles[1] * p->n_traj;
+  const int cc = own_chunk_coils(p->ndim, C);
+  const int64_t n_chunks = ceil_div(C, cc), Bz = p->n_traj == 1 ? B : 1;
+  const int64_t n_tiles_all = (int64_t)p->n_own_tiles[0] * p->n_own_tiles[1] * p->n_own_tiles[2] * p->n_traj;
   o.ctr = align_up(sizeof(unsigned) * (size_t)(n_tiles_all * Bz * n_chunks), 256);
-  o.packed = align_up(sizeof(float2) * (size_t)(B * n_chunks * 4 * cpl) * (size_t)p->n_points, 256);
-  o.slot = sizeof(float2) * (size_t)(Bz * n_chunks) * (size_t)(kOTR * cpl * 32);
+  o.packed = align_up(sizeof(float2) * (size_t)(B * n_chunks * cc) * (size_t)p->n_points, 256);
+  // accumulators of one warp: 2-D 4 rows x CPL coils x 32 lanes, 3-D 4 planes x CK coils x 32 lanes
+  o.slot = sizeof(float2) * (size_t)(Bz * n_chunks) * (size_t)(p->ndim == 3 ? kO3Z * cc * 32 : kOTR * (cc / 4) * 32);
   o.total = o.ctr + o.packed + o.slot * (size_t)(n_slots > 0 ? n_slots : p->n_own_items_max);
   return o;
 }
@@ -374,9 +626,11 @@ size_t own_adjoint_bytes(const b2n_geom *g, const b2n_points *p, int64_t B, int6
 }
 
 struct OwnLaunch {
+  const b2n_geom *g;
   const b2n_points *p;
   const void *kdata;
-  int64_t B;
+  int64_t B, C;
+  int n_chunks;
   char *scratch;
   OwnScratch lay;
   int slot_cap;
@@ -384,36 +638,97 @@ struct OwnLaunch {
   cudaStream_t st;
 };
 
-template <int CPL, int MINB, int U> static int launch_own(const OwnArgs &a, const OwnLaunch &l) {
-  float4 *packed = (float4 *)(l.scratch + l.lay.ctr);
-  dim3 gp((unsigned)ceil_div(a.M, 64), (unsigned)a.n_chunks, (unsigned)l.B);
-  B2N_CUDA_OK(launch_pdl(k_own_pack<CPL>, gp, dim3(256), 0, l.st, (const float2 *)l.kdata, packed, a.C, a.M, a.n_chunks,
-                         a.n_traj, (const int32_t *)l.p->inv_perm, (const float2 *)l.p->own_fac));
+template <int CPL, bool PLANAR> static int launch_pack(const OwnLaunch &l) {
+  dim3 gp((unsigned)ceil_div(l.p->n_points, 64), (unsigned)l.n_chunks, (unsigned)l.B);
+  B2N_CUDA_OK(launch_pdl(k_own_pack<CPL, PLANAR>, gp, dim3(256), 0, l.st, (const float2 *)l.kdata,
+                         (float4 *)(l.scratch + l.lay.ctr), (int)l.C, l.p->n_points, l.n_chunks, (int)l.p->n_traj,
+                         (const int32_t *)l.p->inv_perm, (const float2 *)l.p->own_fac));
   B2N_LAUNCH_OK("k_own_pack");
+  return 0;
+}
+
+static int launch_fix(const OwnLaunch &l) {
+  if (l.p->n_own_exc_max <= 0) return 0;
+  OwnFixArgs f;
+  f.Kprod = 1;
+  f.n_own_tiles = 1;
+  for (int d = 0; d < 3; ++d) {
+    f.K[d] = d < l.g->ndim ? (int)l.g->grid_size[d] : 1;
+    f.nt[d] = d < l.g->ndim ? l.p->n_own_tiles[d] : 1;
+    f.Kprod *= f.K[d];
+    f.n_own_tiles *= f.nt[d];
+  }
+  f.C = (int)l.C;
+  f.n_traj = (int)l.p->n_traj;
+  f.M = l.p->n_points;
+  f.xcap = l.p->n_own_xv_max;
+  f.counts = l.p->own_counts;
+  f.perm = l.p->perm;
+  f.xt = (const int2 *)l.p->own_xt;
+  f.xv = (const int2 *)l.p->own_xv;
+  f.coef = (const float2 *)l.p->coef;
+  dim3 gf((unsigned)(f.n_own_tiles * l.p->n_traj), 1, (unsigned)(l.p->n_traj == 1 ? l.B : 1));
+  if (l.g->ndim == 3)
+    B2N_CUDA_OK(launch_pdl(k_own_fix<3>, gf, dim3(128), 0, l.st, f, (const float2 *)l.kdata, (float2 *)l.grid));
+  else
+    B2N_CUDA_OK(launch_pdl(k_own_fix<2>, gf, dim3(32), 0, l.st, f, (const float2 *)l.kdata, (float2 *)l.grid));
+  B2N_LAUNCH_OK("k_own_fix");
+  return 0;
+}
+
+template <int CPL, int MINB, int U> static int launch_own(const OwnLaunch &l) {
+  OwnArgs a;
+  a.Ky = (int)l.g->grid_size[0];
+  a.Kx = (int)l.g->grid_size[1];
+  a.C = (int)l.C;
+  a.M = l.p->n_points;
+  a.Kprod = l.g->grid_size[0] * l.g->grid_size[1];
+  a.n_own_tiles = (int64_t)l.p->n_own_tiles[0] * l.p->n_own_tiles[1];
+  a.n_traj = (int)l.p->n_traj;
+  a.n_chunks = l.n_chunks;
+  a.visits = (const float4 *)l.p->own_visits;
+  a.items = (const int4 *)l.p->own_items;
+  a.tiles = (const int4 *)l.p->own_tiles;
+  a.counts = l.p->own_counts;
+  a.q = (const float2 *)l.p->own_q;
+  if (int rc = launch_pack<CPL, (CPL >= 2)>(l)) return rc;
   auto kern = k_adj_own_2d<CPL, MINB, U>;
   dim3 gd((unsigned)l.p->n_own_items_max, (unsigned)a.n_chunks, (unsigned)(l.p->n_traj == 1 ? l.B : 1));
-  B2N_CUDA_OK(launch_pdl(kern, gd, dim3(32), own_smem_bytes<CPL>(), l.st, a, (const float4 *)packed, (float2 *)l.grid,
-                         (float2 *)(l.scratch + l.lay.ctr + l.lay.packed), (unsigned *)l.scratch, l.slot_cap));
+  B2N_CUDA_OK(launch_pdl(kern, gd, dim3(32), own_smem_bytes<CPL>(), l.st, a, (const float4 *)(l.scratch + l.lay.ctr),
+                         (float2 *)l.grid, (float2 *)(l.scratch + l.lay.ctr + l.lay.packed), (unsigned *)l.scratch,
+                         l.slot_cap));
   B2N_LAUNCH_OK("k_adj_own_2d");
-  if (l.p->n_own_exc_max > 0) {
-    OwnFixArgs f;
-    f.Ky = a.Ky;
-    f.Kx = a.Kx;
-    f.C = a.C;
-    f.n_traj = a.n_traj;
-    f.M = a.M;
-    f.Kprod = a.Kprod;
-    f.cap = l.p->n_own_exc_max;
-    f.counts = l.p->own_counts;
-    f.exc = l.p->own_exc;
-    f.perm = l.p->perm;
-    f.base = l.p->base;
-    f.coef = (const float2 *)l.p->coef;
-    B2N_CUDA_OK(launch_pdl(k_own_fix, dim3(1, 1, (unsigned)(l.p->n_traj == 1 ? l.B : 1)), dim3(256), 0, l.st, f,
-                           (const float2 *)l.kdata, (float2 *)l.grid));
-    B2N_LAUNCH_OK("k_own_fix");
+  return launch_fix(l);
+}
+
+template <int CK, int MINB, int U> static int launch_own3(const OwnLaunch &l) {
+  Own3Args a;
+  a.Kprod = 1;
+  a.n_own_tiles = 1;
+  for (int d = 0; d < 3; ++d) {
+    a.K[d] = (int)l.g->grid_size[d];
+    a.nt[d] = l.p->n_own_tiles[d];
+    a.Kprod *= l.g->grid_size[d];
+    a.n_own_tiles *= l.p->n_own_tiles[d];
   }
-  return 0;
+  a.C = (int)l.C;
+  a.M = l.p->n_points;
+  a.n_traj = (int)l.p->n_traj;
+  a.n_chunks = l.n_chunks;
+  a.visits = (const int4 *)l.p->own_visits;
+  a.items = (const int4 *)l.p->own_items;
+  a.tiles = (const int4 *)l.p->own_tiles;
+  a.counts = l.p->own_counts;
+  a.hw = l.p->own_hw;
+  a.q = (const float2 *)l.p->own_q;
+  if (int rc = launch_pack<CK / 4, true>(l)) return rc;
+  auto kern = k_adj_own_3d<CK, MINB, U>;
+  dim3 gd((unsigned)l.p->n_own_items_max, (unsigned)a.n_chunks, (unsigned)(l.p->n_traj == 1 ? l.B : 1));
+  B2N_CUDA_OK(launch_pdl(kern, gd, dim3(32), own3_smem_bytes<CK>(), l.st, a, (const float4 *)(l.scratch + l.lay.ctr),
+                         (float2 *)l.grid, (float2 *)(l.scratch + l.lay.ctr + l.lay.packed), (unsigned *)l.scratch,
+                         l.slot_cap));
+  B2N_LAUNCH_OK("k_adj_own_3d");
+  return launch_fix(l);
 }
 
 // returns 1 when the owner-tile path does not apply
@@ -431,34 +746,30 @@ int own_adjoint(const b2n_geom *g, const b2n_points *p, const void *kdata, int64
   // with a slot count that is not the plan's)
   const int64_t cap64 = (int64_t)((scratch_bytes - l.lay.ctr - l.lay.packed) / l.lay.slot);
   l.slot_cap = (int)(cap64 > 0x7fffffff ? 0x7fffffff : cap64);
+  l.g = g;
   l.p = p;
   l.kdata = kdata;
   l.B = B;
+  l.C = C;
+  const int cc = own_chunk_coils(g->ndim, C);
+  l.n_chunks = (int)ceil_div(C, cc);
   l.scratch = (char *)scratch;
   l.grid = grid;
   l.st = st;
-  const int cpl = own_cpl(C);
-  OwnArgs a;
-  a.Ky = (int)g->grid_size[0];
-  a.Kx = (int)g->grid_size[1];
-  a.C = (int)C;
-  a.M = p->n_points;
-  a.Kprod = g->grid_size[0] * g->grid_size[1];
-  a.n_own_tiles = (int64_t)p->n_own_tiles[0] * p->n_own_tiles[1];
-  a.n_traj = (int)p->n_traj;
-  a.n_chunks = (int)ceil_div(C, 4 * cpl);
-  a.visits = (const float4 *)p->own_visits;
-  a.items = (const int4 *)p->own_items;
-  a.tiles = (const int4 *)p->own_tiles;
-  a.counts = p->own_counts;
-  a.q = (const float2 *)p->own_q;
+  if (g->ndim == 3) {
+    // B2N_OPT_ADJ_OWNED (A/B): 4 = 12 resident warps per SM (168 registers) instead of 16, 5 = loop not unrolled
+    if (cc == 8 && g_adj_owned == 4) return launch_own3<8, 12, 2>(l);
+    if (cc == 8 && g_adj_owned == 5) return launch_own3<8, 16, 1>(l);
+    if (cc == 8) return launch_own3<8, 16, 2>(l);
+    return launch_own3<4, 24, 2>(l);
+  }
   // B2N_OPT_ADJ_OWNED (A/B of the 16-coil kernel): 4 / 5 = 20 / 32 resident warps per SM instead of 24, 6 = unroll 4
-  if (cpl == 4 && g_adj_owned == 4) return launch_own<4, 20, 2>(a, l);
-  if (cpl == 4 && g_adj_owned == 5) return launch_own<4, 32, 2>(a, l);
-  if (cpl == 4 && g_adj_owned == 6) return launch_own<4, 24, 4>(a, l);
-  if (cpl == 4) return launch_own<4, 24, 2>(a, l);
-  if (cpl == 2) return launch_own<2, 32, 2>(a, l);
-  return launch_own<1, 32, 2>(a, l);
+  if (cc == 16 && g_adj_owned == 4) return launch_own<4, 20, 2>(l);
+  if (cc == 16 && g_adj_owned == 5) return launch_own<4, 32, 2>(l);
+  if (cc == 16 && g_adj_owned == 6) return launch_own<4, 24, 4>(l);
+  if (cc == 16) return launch_own<4, 24, 2>(l);
+  if (cc == 8) return launch_own<2, 32, 2>(l);
+  return launch_own<1, 32, 2>(l);
 }
 
 }  // namespace b2n

@@ -147,8 +147,8 @@ template <typename T>
 __global__ void k_point_records(GeomT<T> g, const T *__restrict__ omega, int64_t M, int64_t total,
                                 const uint32_t *__restrict__ sorted_idx, int32_t *__restrict__ perm,
                                 int32_t *__restrict__ inv_perm, int32_t *__restrict__ base_out, cplx<T> *__restrict__ coef,
-                                cplx<T> *__restrict__ phase, float *__restrict__ hw, float2 *__restrict__ fac,
-                                unsigned char *__restrict__ exc_flag) {
+                                cplx<T> *__restrict__ phase, float *__restrict__ hw, int hw_stride,
+                                float2 *__restrict__ fac, unsigned char *__restrict__ exc_flag) {
   const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= total) return;
   const int64_t i = sorted_idx[s];
@@ -173,7 +173,7 @@ __global__ void k_point_records(GeomT<T> g, const T *__restrict__ omega, int64_t
     locate<T>(omv[d], g.K[d], g.J[d], tm, base);
     base_out[s * g.ndim + d] = (int32_t)wrap_cell(base, g.K[d]);
     if (hw) {
-      // real-weight records (2-D, J = 6 on both axes; see b2n_geom.rtable_dev): neighbour j of this point has the
+      // real-weight records (2-D / 3-D, J = 6 on every axis; see b2n_geom.rtable_dev): neighbour j of this point has the
       // table index t0 - j L, so its complex weight is r(t0 - j L) exp(-1i p (x0 - j)); the part that does not
       // depend on j goes into the point's factor
       const int64_t t0 = table_index<T>(tm, base, g.J[d], g.L[d]);
@@ -183,7 +183,9 @@ __global__ void k_point_records(GeomT<T> g, const T *__restrict__ omega, int64_t
         exc |= ti != t0 - (int64_t)j * g.L[d] || ti < 0 || ti >= g.table_len[d];
         if (ti < 0) ti += g.table_len[d];
         ti = ti < 0 ? 0 : (ti >= g.table_len[d] ? g.table_len[d] - 1 : ti);
-        hw[s * 12 + 6 * d + j] = (float)g.rtable[d][ti];
+        const float r = (float)g.rtable[d][ti];
+        hw[s * hw_stride + 6 * d + j] = r;
+        if (d == 2) hw[s * hw_stride + 18 + j] = -r;  // 3-D: the staging copies cannot negate (wrap sign), so both
       }
     }
     cplx<T> *rec = coef + s * g.coef_stride + g.coef_off[d];
@@ -200,7 +202,7 @@ __global__ void k_point_records(GeomT<T> g, const T *__restrict__ omega, int64_t
   if (hw) {
     exc_flag[s] = exc ? 1 : 0;
     if (exc)
-      for (int k = 0; k < 12; ++k) hw[s * 12 + k] = 0.f;
+      for (int k = 0; k < hw_stride; ++k) hw[s * hw_stride + k] = 0.f;
   }
   if (fac) {
     // conj(fftshift phase * exp(-1i fac_arg)): the angle reaches thousands of radians, so it is reduced in double
@@ -268,10 +270,10 @@ __global__ void __launch_bounds__(1024) k_own_exc_write(const unsigned char *__r
 }
 
 // exp(-1i * slope_d * cell) for every row and column of the grid: the per-cell factor of the real-weight adjoint
-__global__ void k_own_cell_phase(int Ky, int Kx, double py, double px, float2 *__restrict__ q) {
+__global__ void k_own_cell_phase(int K0, int K1, int K2, double p0, double p1, double p2, float2 *__restrict__ q) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= Ky + Kx) return;
-  const double a = i < Ky ? py * i : px * (i - Ky);
+  if (i >= K0 + K1 + K2) return;
+  const double a = i < K0 ? p0 * i : (i < K0 + K1 ? p1 * (i - K0) : p2 * (i - K0 - K1));
   double sn, cs;
   sincos(a, &sn, &cs);
   q[i] = make_float2((float)cs, (float)-sn);
@@ -548,15 +550,199 @@ __global__ void __launch_bounds__(kOwnFillThreads) k_own_fill(OwnGeom g, const i
   }
 }
 
+// ---- owner-tile visit lists, 3-D (4 x 4 x 8 output tiles, k_adj_own_3d) ---------------------------------------------
+// Same construction one dimension up: the base cells that can touch a tile form a (4+5) x (4+5) x (8+5) window.  A
+// visit is an index record {sorted slot, sample index, footprint origin relative to the tile, sign}; the spread
+// kernel forms the window weights from the per-point records while staging (a 64-byte record per visit as in 2-D
+// would be 4.4 GB at BASELINE config 4).
+struct Own3Geom {
+  int K[3], nt[3], T[3], neg[3], cap;
+  int64_t n_traj, n_own_tiles;
+  Tiling tl;
+};
+constexpr int kOwn3WinMax = 9 * 9 * 13;
+
+B2N_D void own3_tile(const Own3Geom &g, int64_t t, int64_t &traj, int *o, int *wd, int &tile_id) {
+  traj = t / g.n_own_tiles;
+  int64_t tid = t - traj * g.n_own_tiles;
+  tile_id = (int)tid;
+  const int t2 = (int)(tid % g.nt[2]);
+  tid /= g.nt[2];
+  const int t1 = (int)(tid % g.nt[1]), t0 = (int)(tid / g.nt[1]);
+  o[0] = t0 * g.T[0];
+  o[1] = t1 * g.T[1];
+  o[2] = t2 * g.T[2];
+  for (int d = 0; d < 3; ++d) wd[d] = min(g.T[d], g.K[d] - o[d]) + 5;
+}
+
+// sorted-slot range of window cell w (row-major over wd[0] x wd[1] x wd[2])
+B2N_D void own3_window_cell(const Own3Geom &g, const int32_t *__restrict__ cell_start, int64_t traj, const int *o,
+                            const int *wd, int w, int &s0, int &s1, int *r) {
+  const int w2 = w % wd[2], w01 = w / wd[2], w1 = w01 % wd[1], w0 = w01 / wd[1];
+  r[0] = w0 - 5;
+  r[1] = w1 - 5;
+  r[2] = w2 - 5;
+  int64_t cell[B2N_MAX_DIMS] = {own_wrap(o[0] + r[0], g.K[0]), own_wrap(o[1] + r[1], g.K[1]),
+                                own_wrap(o[2] + r[2], g.K[2])};
+  const int64_t idx = traj * g.tl.n_cells + tiled_cell(g.tl, cell);
+  s0 = cell_start[idx];
+  s1 = cell_start[idx + 1];
+}
+
+// one warp per output tile: number of visits, number of work items, LPT histogram
+__global__ void __launch_bounds__(256) k_own3_count(Own3Geom g, const int32_t *__restrict__ cell_start,
+                                                    int4 *__restrict__ tiles, int32_t *__restrict__ hist) {
+  const int64_t t = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (t >= g.n_traj * g.n_own_tiles) return;
+  int64_t traj;
+  int o[3], wd[3], tile_id;
+  own3_tile(g, t, traj, o, wd, tile_id);
+  int n = 0;
+  for (int w = lane; w < wd[0] * wd[1] * wd[2]; w += 32) {
+    int s0, s1, r[3];
+    own3_window_cell(g, cell_start, traj, o, wd, w, s0, s1, r);
+    n += s1 - s0;
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) n += __shfl_xor_sync(0xffffffffu, n, off);
+  if (lane == 0) {
+    const int nch = n > 0 ? (n + g.cap - 1) / g.cap : 1;
+    tiles[t] = make_int4(n, 0, nch, -1);
+    if (nch > 1) atomicAdd(&hist[0], nch - 1);
+    atomicAdd(&hist[nch > 1 ? 0 : own_bucket(n, g.cap)], 1);
+  }
+}
+
+// one CTA per output tile: index records of its visits in window order, work items into their LPT bucket
+__global__ void __launch_bounds__(256) k_own3_fill(Own3Geom g, const int32_t *__restrict__ cell_start,
+                                                   const int32_t *__restrict__ perm, const int4 *__restrict__ tiles,
+                                                   const int32_t *__restrict__ bucket_base,
+                                                   int32_t *__restrict__ bucket_fill, int4 *__restrict__ visits,
+                                                   int4 *__restrict__ items) {
+  __shared__ int s_first[kOwn3WinMax + 1], s_s0[kOwn3WinMax], s_warp[8], s_run;
+  const int64_t t = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  int64_t traj;
+  int o[3], wd[3], tile_id;
+  own3_tile(g, t, traj, o, wd, tile_id);
+  const int nw = wd[0] * wd[1] * wd[2];
+  const int4 ti = tiles[t];
+  if (tid == 0) s_run = 0;
+  __syncthreads();
+  for (int w0 = 0; w0 < nw; w0 += 256) {  // exclusive scan of the point counts over the window, 256 cells a round
+    const int w = w0 + tid;
+    int s0 = 0, s1 = 0, r[3];
+    if (w < nw) own3_window_cell(g, cell_start, traj, o, wd, w, s0, s1, r);
+    const int cnt = s1 - s0;
+    int incl = cnt;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const int up = __shfl_up_sync(0xffffffffu, incl, off);
+      if (lane >= off) incl += up;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    int before = s_run;
+    for (int k = 0; k < warp; ++k) before += s_warp[k];
+    if (w < nw) {
+      s_first[w] = before + incl - cnt;
+      s_s0[w] = s0;
+    }
+    __syncthreads();
+    if (tid == 255) s_run = before + incl;
+    __syncthreads();
+  }
+  const int n = ti.x;
+#pragma unroll 2
+  for (int v = tid; v < n; v += 256) {
+    int lo = 0, hi = nw - 1;  // last window cell whose first visit is <= v
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (s_first[mid] <= v) lo = mid; else hi = mid - 1;
+    }
+    const int w2 = lo % wd[2], w01 = lo / wd[2], w1 = w01 % wd[1], w0 = w01 / wd[1];
+    const int r0 = w0 - 5, r1 = w1 - 5, r2 = w2 - 5;
+    const int slot = s_s0[lo] + (v - s_first[lo]);
+    // a negative (unwrapped) base cell: the footprint reached this tile around the grid's edge
+    const int neg = ((o[0] + r0 < 0) & g.neg[0]) ^ ((o[1] + r1 < 0) & g.neg[1]) ^ ((o[2] + r2 < 0) & g.neg[2]);
+    visits[(int64_t)ti.y + v] = make_int4(slot, perm[slot], (r0 + 16) | ((r1 + 16) << 8) | ((r2 + 16) << 16), neg);
+  }
+  for (int j = tid; j < ti.z; j += 256) {
+    const int size = max(0, min(g.cap, ti.x - j * g.cap));
+    const int b = ti.z > 1 ? 0 : own_bucket(size, g.cap);
+    const int pos = bucket_base[b] + atomicAdd(&bucket_fill[b], 1);
+    items[pos] = make_int4((int)t, ti.y + j * g.cap, size | (j << 12), tile_id);
+  }
+}
+
+// Exception points per output tile (b2n_points.own_xt / own_xv): one warp per tile tests every exception point (a few
+// thousand at most on real trajectories) for a footprint that reaches the tile, counts, reserves a segment of own_xv
+// and writes the pairs in ascending slot order.  The segment's position depends on the order of the reservations, its
+// contents do not.
+template <int ND>
+__global__ void __launch_bounds__(256) k_own_exc_tiles(int K0, int K1, int K2, int nt0, int nt1, int nt2, int64_t n_tiles,
+                                                       int64_t n_traj, int64_t M, const int32_t *__restrict__ exc,
+                                                       const int32_t *__restrict__ counts, const int32_t *__restrict__ base,
+                                                       int2 *__restrict__ xt, int2 *__restrict__ xv, int64_t xcap,
+                                                       int32_t *__restrict__ cursor) {
+  const int64_t t = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const int64_t traj = t / n_tiles;
+  if (traj >= n_traj) return;
+  int64_t tid = t - traj * n_tiles;
+  const int K[3] = {K0, K1, K2}, nt[3] = {nt0, nt1, nt2};
+  int o[3] = {0, 0, 0}, T[3] = {1, 1, 1};
+  for (int d = ND - 1; d >= 0; --d) {
+    T[d] = d == ND - 1 ? 8 : 4;
+    o[d] = (int)(tid % nt[d]) * T[d];
+    tid /= nt[d];
+  }
+  const int n_exc = counts[2];
+  // footprint origin relative to the tile along every axis, or "no overlap"
+  auto rel = [&](int e, int &packed) {
+    const int64_t s = exc[e];
+    if (s / M != traj) return false;
+    packed = 0;
+    for (int d = 0; d < ND; ++d) {
+      int r = base[s * ND + d] - o[d];           // wrapped base in [0, K): bring r into [-(J-1), T-1] modulo K
+      if (r > T[d] - 1) r -= K[d];
+      if (r < -5 || r > min(T[d], K[d] - o[d]) - 1) return false;
+      packed |= (r + 16) << (8 * d);
+    }
+    return true;
+  };
+  int n = 0;
+  for (int e0 = 0; e0 < n_exc; e0 += 32) {
+    int packed;
+    const bool hit = e0 + lane < n_exc && rel(e0 + lane, packed);
+    n += __popc(__ballot_sync(0xffffffffu, hit));
+  }
+  int first = 0;
+  if (lane == 0 && n > 0) first = atomicAdd(cursor, n);
+  first = __shfl_sync(0xffffffffu, first, 0);
+  if (lane == 0) xt[t] = make_int2(first, n);
+  if (n == 0 || (int64_t)first + n > xcap) return;  // over capacity: the fix-up kernel traps on counts[3] > capacity
+  int at = first;
+  for (int e0 = 0; e0 < n_exc; e0 += 32) {
+    int packed = 0;
+    const bool hit = e0 + lane < n_exc && rel(e0 + lane, packed);
+    const unsigned m = __ballot_sync(0xffffffffu, hit);
+    if (hit) xv[at + __popc(m & ((1u << lane) - 1))] = make_int2(exc[e0 + lane], packed);
+    at += __popc(m);
+  }
+}
+
 // ---- workspace carving --------------------------------------------------------
 struct Carve {
   size_t perm, inv_perm, base, coef, phase, cell_start, keys, sub_tile, sub_start, sub_count, n_sub;
   size_t keys_in, idx_in, idx_out, chunks, offsets, tmp_tile, tmp_start, tmp_count, sub_keys, sub_keys_out, sub_idx,
       sub_order, cub, total, cub_bytes;
-  size_t own_visits, own_items, own_tiles, own_counts, own_hist, own_hw, own_fac, own_q, own_excf, own_excb, own_exc;
+  size_t own_visits, own_items, own_tiles, own_counts, own_hist, own_hw, own_fac, own_q, own_excf, own_excb, own_exc, own_xt, own_xv;
+  int64_t n_own_xv_max;
   bool own_real;
   int64_t n_own_items_max, n_own_tiles;  // per trajectory; 0 = no visit lists for this geometry
-  int own_nt[2], own_cap, own_rows;
+  int own_nt[3], own_cap, own_rows;
   int64_t n_sub_max;
   int sub_cap;
   Tiling tiling;
@@ -565,12 +751,13 @@ struct Carve {
 static int default_sub_cap(int ndim) { return ndim == 3 ? 128 : 128; }
 
 constexpr int kOwnTileRows = 4, kOwnTileCols = 8;
-int g_own_cap = 64;  // visits per work item of the owner-tile spread (b2n_set_option(B2N_OPT_OWN_CAP) for A/B)
-// Visit lists are built for what the owner-tile spread handles: 2-D complex64, J = 6, K_d >= 16, tables of the
-// reference's form with the real kernel supplied by the caller (own_real).
+int g_own_cap = 0;  // visits per work item of the owner-tile spread: 0 = 128 (2-D) / 1024 (3-D); B2N_OPT_OWN_CAP for A/B
+// Visit lists are built for what the owner-tile spreads handle: 2-D / 3-D complex64, J = 6, K_d >= 16, tables of the
+// reference's form with the real kernel supplied by the caller (own_real).  Tiles: 4 x 8 cells (2-D), 4 x 4 x 8 (3-D).
+static int own_tile_edge(int ndim, int d) { return d == ndim - 1 ? kOwnTileCols : kOwnTileRows; }
 static bool own_eligible(const b2n_geom *g) {
-  if (g->ndim != 2 || g->dtype != B2N_C64) return false;
-  for (int d = 0; d < 2; ++d)
+  if ((g->ndim != 2 && g->ndim != 3) || g->dtype != B2N_C64) return false;
+  for (int d = 0; d < g->ndim; ++d)
     if (g->numpoints[d] != 6 || g->grid_size[d] < 16) return false;
   return true;
 }
@@ -578,8 +765,8 @@ static bool own_eligible(const b2n_geom *g) {
 // axis is a partial one of fewer than J - 1 cells (the footprint can then cover it and reach around the grid's edge)
 static int own_visits_per_point(const b2n_geom *g) {
   int v = 1;
-  for (int d = 0; d < 2; ++d) {
-    const int T = d == 0 ? kOwnTileRows : kOwnTileCols, rem = (int)(g->grid_size[d] % T);
+  for (int d = 0; d < g->ndim; ++d) {
+    const int T = own_tile_edge(g->ndim, d), rem = (int)(g->grid_size[d] % T);
     v *= (T + 4) / T + 1 + (rem != 0 && rem < 5 ? 1 : 0);
   }
   return v;
@@ -587,7 +774,7 @@ static int own_visits_per_point(const b2n_geom *g) {
 // real-weight records: the caller vouches for the tables' form, and the table step per neighbour must be exact
 static bool own_real(const b2n_geom *g) {
   if (!own_eligible(g)) return false;
-  for (int d = 0; d < 2; ++d) {
+  for (int d = 0; d < g->ndim; ++d) {
     const int L = g->table_oversamp[d];
     if (!g->rtable_dev[d] || (L & (L - 1)) != 0) return false;
   }
@@ -664,23 +851,29 @@ static int carve(const b2n_geom *g, int64_t M, int64_t n_traj, Carve *c) {
   c->own_real = false;
   if (own_real(g) && vpp * total < ((int64_t)1 << 31) - 1) {
     c->own_rows = kOwnTileRows;
-    c->own_nt[0] = (int)ceil_div(g->grid_size[0], c->own_rows);
-    c->own_nt[1] = (int)ceil_div(g->grid_size[1], kOwnTileCols);
-    c->n_own_tiles = (int64_t)c->own_nt[0] * c->own_nt[1];
-    c->own_cap = g_own_cap < 8 ? 8 : (g_own_cap > 4095 ? 4095 : g_own_cap);
+    c->n_own_tiles = 1;
+    c->own_nt[0] = c->own_nt[1] = c->own_nt[2] = 1;
+    for (int d = 0; d < g->ndim; ++d) {
+      c->own_nt[d] = (int)ceil_div(g->grid_size[d], own_tile_edge(g->ndim, d));
+      c->n_own_tiles *= c->own_nt[d];
+    }
+    c->own_cap = g_own_cap <= 0 ? (g->ndim == 2 ? 128 : 1024) : (g_own_cap < 8 ? 8 : (g_own_cap > 4095 ? 4095 : g_own_cap));
     c->n_own_items_max = c->n_own_tiles * n_traj + vpp * total / c->own_cap + 1;
-    c->own_visits = take(64 * (size_t)(vpp * total + 1));
+    c->own_visits = take((g->ndim == 2 ? 64 : sizeof(int4)) * (size_t)(vpp * total + 1));
     c->own_items = take(sizeof(int4) * (size_t)c->n_own_items_max);
     c->own_tiles = take(sizeof(int4) * (size_t)(c->n_own_tiles * n_traj));
     c->own_counts = take(sizeof(int32_t) * 4);
     c->own_hist = take(sizeof(int32_t) * 3 * (kOwnBuckets + 1));
     c->own_real = true;
-    c->own_hw = take(sizeof(float) * 12 * (size_t)total);
+    c->own_hw = take(sizeof(float) * (g->ndim == 2 ? 12 : 24) * (size_t)total);
     c->own_fac = take(sizeof(float2) * (size_t)total);
-    c->own_q = take(sizeof(float2) * (size_t)(g->grid_size[0] + g->grid_size[1]));
+    c->own_q = take(sizeof(float2) * (size_t)(g->grid_size[0] + g->grid_size[1] + (g->ndim == 3 ? g->grid_size[2] : 0)));
     c->own_excf = take((size_t)total);
     c->own_excb = take(sizeof(int32_t) * (size_t)ceil_div(total > 0 ? total : 1, 1024));
     c->own_exc = take(sizeof(int32_t) * (size_t)total);
+    c->own_xt = take(sizeof(int2) * (size_t)(c->n_own_tiles * n_traj));
+    c->n_own_xv_max = vpp * (total < 262144 ? total : 262144) + 1;
+    c->own_xv = take(sizeof(int2) * (size_t)c->n_own_xv_max);
   }
   c->total = off;
   return 0;
@@ -730,7 +923,7 @@ static int build_impl(const b2n_geom *geom, const void *omega, int64_t M, int64_
                                                 0, sort_bits(n_cells), st));
     k_point_records<T><<<(unsigned)ceil_div(total, threads), threads, 0, st>>>(
         g, (const T *)omega, M, total, idx_out, out->perm, out->inv_perm, out->base, (cplx<T> *)out->coef,
-        (cplx<T> *)out->phase, c.own_real ? (float *)(ws + c.own_hw) : nullptr,
+        (cplx<T> *)out->phase, c.own_real ? (float *)(ws + c.own_hw) : nullptr, geom->ndim == 2 ? 12 : 24,
         c.own_real ? (float2 *)(ws + c.own_fac) : nullptr, c.own_real ? (unsigned char *)(ws + c.own_excf) : nullptr);
     B2N_LAUNCH_OK("k_point_records");
   }
@@ -763,7 +956,7 @@ static int build_impl(const b2n_geom *geom, const void *omega, int64_t M, int64_
   B2N_LAUNCH_OK("k_sub_gather");
   out->own_tile = 0;
   out->own_cap = 0;
-  out->n_own_tiles[0] = out->n_own_tiles[1] = 0;
+  out->n_own_tiles[0] = out->n_own_tiles[1] = out->n_own_tiles[2] = 0;
   out->n_own_items_max = 0;
   out->own_visits = out->own_items = out->own_tiles = nullptr;
   out->own_counts = nullptr;
@@ -771,56 +964,99 @@ static int build_impl(const b2n_geom *geom, const void *omega, int64_t M, int64_
   out->own_fac = out->own_q = nullptr;
   out->own_exc = nullptr;
   out->n_own_exc_max = 0;
+  out->own_xt = out->own_xv = nullptr;
+  out->n_own_xv_max = 0;
   if (c.n_own_tiles > 0) {
-    OwnGeom og;
-    og.Ky = (int)g.K[0];
-    og.Kx = (int)g.K[1];
-    og.nty = c.own_nt[0];
-    og.ntx = c.own_nt[1];
-    og.J = g.J[0];
-    og.Ty = c.own_rows;
-    og.Tx = kOwnTileCols;
-    og.cap = c.own_cap;
-    {
-      // exp(1i table_phase K) = (-1)^(N - 1): the sign a neighbour picks up when it wraps around the grid
-      og.neg_y = (int)(llround(geom->table_phase[0] * (double)g.K[0] / 3.14159265358979323846) & 1);
-      og.neg_x = (int)(llround(geom->table_phase[1] * (double)g.K[1] / 3.14159265358979323846) & 1);
-      out->own_hw = (float *)(ws + c.own_hw);
-      out->own_fac = ws + c.own_fac;
-      out->own_q = ws + c.own_q;
-      k_own_cell_phase<<<(unsigned)ceil_div(g.K[0] + g.K[1], threads), threads, 0, st>>>(
-          og.Ky, og.Kx, geom->table_phase[0], geom->table_phase[1], (float2 *)out->own_q);
-      B2N_LAUNCH_OK("k_own_cell_phase");
-      out->own_exc = (int32_t *)(ws + c.own_exc);
-      out->n_own_exc_max = total;
-      const unsigned nb = (unsigned)ceil_div(total > 0 ? total : 1, 1024);
-      k_own_exc_count<<<nb, 1024, 0, st>>>((const unsigned char *)(ws + c.own_excf), total, (int32_t *)(ws + c.own_excb));
-      B2N_LAUNCH_OK("k_own_exc_count");
-      k_own_exc_write<<<nb, 1024, 0, st>>>((const unsigned char *)(ws + c.own_excf), total,
-                                           (const int32_t *)(ws + c.own_excb), out->own_exc,
-                                           (int32_t *)(ws + c.own_counts) + 2);
-      B2N_LAUNCH_OK("k_own_exc_write");
-    }
-    og.n_traj = n_traj;
-    og.n_own_tiles = c.n_own_tiles;
-    og.tl = tl;
+    const int nd = geom->ndim;
+    // exp(1i table_phase K) = (-1)^(N - 1): the sign a neighbour picks up when it wraps around the grid
+    int neg[3] = {0, 0, 0};
+    for (int d = 0; d < nd; ++d)
+      neg[d] = (int)(llround(geom->table_phase[d] * (double)g.K[d] / 3.14159265358979323846) & 1);
+    out->own_hw = (float *)(ws + c.own_hw);
+    out->own_fac = ws + c.own_fac;
+    out->own_q = ws + c.own_q;
+    const int64_t Kq = g.K[0] + g.K[1] + (nd == 3 ? g.K[2] : 0);
+    k_own_cell_phase<<<(unsigned)ceil_div(Kq, threads), threads, 0, st>>>(
+        (int)g.K[0], (int)g.K[1], nd == 3 ? (int)g.K[2] : 0, geom->table_phase[0], geom->table_phase[1],
+        nd == 3 ? geom->table_phase[2] : 0.0, (float2 *)out->own_q);
+    B2N_LAUNCH_OK("k_own_cell_phase");
+    out->own_exc = (int32_t *)(ws + c.own_exc);
+    out->n_own_exc_max = total;
+    const unsigned nb = (unsigned)ceil_div(total > 0 ? total : 1, 1024);
+    k_own_exc_count<<<nb, 1024, 0, st>>>((const unsigned char *)(ws + c.own_excf), total, (int32_t *)(ws + c.own_excb));
+    B2N_LAUNCH_OK("k_own_exc_count");
+    k_own_exc_write<<<nb, 1024, 0, st>>>((const unsigned char *)(ws + c.own_excf), total,
+                                         (const int32_t *)(ws + c.own_excb), out->own_exc,
+                                         (int32_t *)(ws + c.own_counts) + 2);
+    B2N_LAUNCH_OK("k_own_exc_write");
     const int64_t nt_all = c.n_own_tiles * n_traj;
+    {
+      out->own_xt = ws + c.own_xt;
+      out->own_xv = ws + c.own_xv;
+      out->n_own_xv_max = c.n_own_xv_max;
+      int32_t *cnts = (int32_t *)(ws + c.own_counts);
+      B2N_CUDA_OK(cudaMemsetAsync(cnts + 3, 0, sizeof(int32_t), st));
+      const unsigned gx = (unsigned)ceil_div(c.n_own_tiles * 32 * n_traj, threads);
+      if (nd == 2)
+        k_own_exc_tiles<2><<<gx, threads, 0, st>>>((int)g.K[0], (int)g.K[1], 1, c.own_nt[0], c.own_nt[1], 1, c.n_own_tiles,
+                                                   n_traj, M, out->own_exc, cnts, out->base, (int2 *)out->own_xt,
+                                                   (int2 *)out->own_xv, c.n_own_xv_max, cnts + 3);
+      else
+        k_own_exc_tiles<3><<<gx, threads, 0, st>>>((int)g.K[0], (int)g.K[1], (int)g.K[2], c.own_nt[0], c.own_nt[1],
+                                                   c.own_nt[2], c.n_own_tiles, n_traj, M, out->own_exc, cnts, out->base,
+                                                   (int2 *)out->own_xt, (int2 *)out->own_xv, c.n_own_xv_max, cnts + 3);
+      B2N_LAUNCH_OK("k_own_exc_tiles");
+    }
     int4 *tiles = (int4 *)(ws + c.own_tiles);
     int32_t *hist = (int32_t *)(ws + c.own_hist), *bucket_base = hist + (kOwnBuckets + 1),
             *bucket_fill = bucket_base + (kOwnBuckets + 1);
     B2N_CUDA_OK(cudaMemsetAsync(hist, 0, sizeof(int32_t) * 3 * (kOwnBuckets + 1), st));
-    k_own_count<<<(unsigned)ceil_div(nt_all * 32, threads), threads, 0, st>>>(og, out->cell_start, tiles, hist);
-    B2N_LAUNCH_OK("k_own_count");
-    k_own_scan<<<1, 1024, 0, st>>>(nt_all, tiles, hist, bucket_base, bucket_fill, (int32_t *)(ws + c.own_counts));
-    B2N_LAUNCH_OK("k_own_scan");
-    k_own_fill<<<(unsigned)nt_all, kOwnFillThreads, 0, st>>>(
-        og, out->cell_start, out->perm, (const float *)(ws + c.own_hw), tiles, bucket_base, bucket_fill,
-        (float4 *)(ws + c.own_visits), (int4 *)(ws + c.own_items));
-    B2N_LAUNCH_OK("k_own_fill");
+    if (nd == 2) {
+      OwnGeom og;
+      og.Ky = (int)g.K[0];
+      og.Kx = (int)g.K[1];
+      og.nty = c.own_nt[0];
+      og.ntx = c.own_nt[1];
+      og.J = g.J[0];
+      og.Ty = c.own_rows;
+      og.Tx = kOwnTileCols;
+      og.cap = c.own_cap;
+      og.neg_y = neg[0];
+      og.neg_x = neg[1];
+      og.n_traj = n_traj;
+      og.n_own_tiles = c.n_own_tiles;
+      og.tl = tl;
+      k_own_count<<<(unsigned)ceil_div(nt_all * 32, threads), threads, 0, st>>>(og, out->cell_start, tiles, hist);
+      B2N_LAUNCH_OK("k_own_count");
+      k_own_scan<<<1, 1024, 0, st>>>(nt_all, tiles, hist, bucket_base, bucket_fill, (int32_t *)(ws + c.own_counts));
+      B2N_LAUNCH_OK("k_own_scan");
+      k_own_fill<<<(unsigned)nt_all, kOwnFillThreads, 0, st>>>(
+          og, out->cell_start, out->perm, (const float *)(ws + c.own_hw), tiles, bucket_base, bucket_fill,
+          (float4 *)(ws + c.own_visits), (int4 *)(ws + c.own_items));
+      B2N_LAUNCH_OK("k_own_fill");
+    } else {
+      Own3Geom og;
+      for (int d = 0; d < 3; ++d) {
+        og.K[d] = (int)g.K[d];
+        og.nt[d] = c.own_nt[d];
+        og.T[d] = own_tile_edge(3, d);
+        og.neg[d] = neg[d];
+      }
+      og.cap = c.own_cap;
+      og.n_traj = n_traj;
+      og.n_own_tiles = c.n_own_tiles;
+      og.tl = tl;
+      k_own3_count<<<(unsigned)ceil_div(nt_all * 32, threads), threads, 0, st>>>(og, out->cell_start, tiles, hist);
+      B2N_LAUNCH_OK("k_own3_count");
+      k_own_scan<<<1, 1024, 0, st>>>(nt_all, tiles, hist, bucket_base, bucket_fill, (int32_t *)(ws + c.own_counts));
+      B2N_LAUNCH_OK("k_own_scan");
+      k_own3_fill<<<(unsigned)nt_all, 256, 0, st>>>(og, out->cell_start, out->perm, tiles, bucket_base, bucket_fill,
+                                                    (int4 *)(ws + c.own_visits), (int4 *)(ws + c.own_items));
+      B2N_LAUNCH_OK("k_own3_fill");
+    }
     out->own_tile = c.own_rows;
-    out->own_cap = og.cap;
-    out->n_own_tiles[0] = c.own_nt[0];
-    out->n_own_tiles[1] = c.own_nt[1];
+    out->own_cap = c.own_cap;
+    for (int d = 0; d < 3; ++d) out->n_own_tiles[d] = c.own_nt[d];
     out->n_own_items_max = c.n_own_items_max;
     out->own_visits = ws + c.own_visits;
     out->own_items = ws + c.own_items;
