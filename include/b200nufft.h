@@ -172,7 +172,7 @@ enum b2n_option {
                                  triple-buffered kernel (measured slower, kept for A/B), 8 two 8-coil CTAs */
   B2N_OPT_ADJ_COIL_CHUNK = 3, /* 0 (default): 16 coils per CTA in the tiled adjoint; 8: two 8-coil CTAs */
   B2N_OPT_FAST_FFT = 4, /* 1 (default): fused FFT passes use the compile-time planned kernels for the lengths that
-                           have a plan (64, 96, 128, 160, 192, 200, 224, 240, 256, 288, 320, 384, 400, 448, 480, 512, 576, 640, 768, 800, 896, 960, 1024, 1152, 1280, 1536, 1600, 1920, 2048); 0: run-time passes only */
+                           have a plan (64, 72, 96, 120, 128, 144, 160, 192, 200, 224, 240, 256, 288, 320, 360, 384, 400, 448, 480, 512, 576, 600, 640, 720, 768, 800, 896, 960, 1024, 1152, 1200, 1280, 1440, 1536, 1600, 1920, 2048); 0: run-time passes only */
   B2N_OPT_PDL = 5, /* 1 (default): the FFT passes, the gathers and the tiled 2-D spread are launched with programmatic
                       dependent launch (their prologues overlap the tail of the preceding kernel; the spread's adjoint
                       grid is zeroed by a kernel it overlaps with); 2: the same but the grid is zeroed by

@@ -53,7 +53,7 @@ def test_unsupported_sizes_are_rejected(n, hostfft):
     assert run(hostfft, np.ones(n, np.complex64), False)[0] == -1
 
 
-@pytest.mark.parametrize("n", [64, 96, 128, 160, 192, 200, 224, 240, 256, 288, 320, 384, 400, 448, 480, 512, 576, 640, 768, 800, 896, 960, 1024, 1152, 1280, 1536, 1600, 1920, 2048])
+@pytest.mark.parametrize("n", [64, 72, 96, 120, 128, 144, 160, 192, 200, 224, 240, 256, 288, 320, 360, 384, 400, 448, 480, 512, 576, 600, 640, 720, 768, 800, 896, 960, 1024, 1152, 1200, 1280, 1440, 1536, 1600, 1920, 2048])
 @pytest.mark.parametrize("half_in", [False, True])
 def test_compile_time_plans_match_numpy(n, half_in, hostfft):
     """b2n_fft_fast.cuh: index maps, staged twiddles and the pair butterflies (incl. radix 10, 12, 16),

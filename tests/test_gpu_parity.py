@@ -563,7 +563,10 @@ def test_tiled_kernels_match_generic_and_oracle(grid_size, B, C, batched):
                                   # lengths added in round 2
                                   ((400, 400), (800, 800)), ((80, 100), (160, 200)), ((120, 200), (240, 400)),
                                   ((6, 576), (12, 1152)), ((5, 768), (8, 1536)), ((4, 800), (8, 1600)),
-                                  ((3, 900), (6, 1920))])
+                                  ((3, 900), (6, 1920)),
+                                  # radix-9 / radix-15 stages
+                                  ((36, 60), (72, 120)), ((70, 180), (144, 360)), ((300, 5), (600, 10)),
+                                  ((360, 4), (720, 8)), ((4, 600), (8, 1200)), ((5, 720), (10, 1440))])
 def test_fused_pruned_fft_matches_torch(N, K):
     """Own Stockham passes (pruned inputs / cropped outputs, fused apodisation, SENSE multiply,
     coil sum and Toeplitz kernel multiply) against torch.fft + plain torch ops, complex64."""
@@ -604,7 +607,7 @@ def test_fused_pruned_fft_matches_torch(N, K):
     assert not eng_fft.fused_fft_available(dt, (57,)) and not eng_fft.fused_fft_available(torch.complex128, K)
     eng_fft.use_fused_fft = "auto"
     assert eng_fft.fused_fft_available(dt, (640, 256)) and not eng_fft.fused_fft_available(dt, (640, 24))
-    assert all(eng_fft.fused_fft_available(dt, (n,)) for n in (64, 96, 128, 160, 192, 200, 224, 240, 256, 288, 320, 384, 400, 448, 480, 512, 576, 640, 768, 800, 896, 960, 1024, 1152, 1280, 1536, 1600, 1920, 2048))
+    assert all(eng_fft.fused_fft_available(dt, (n,)) for n in (64, 72, 96, 120, 128, 144, 160, 192, 200, 224, 240, 256, 288, 320, 360, 384, 400, 448, 480, 512, 576, 600, 640, 720, 768, 800, 896, 960, 1024, 1152, 1200, 1280, 1440, 1536, 1600, 1920, 2048))
 
 
 @pytest.mark.parametrize("N, K", [((32, 32), (64, 64)), ((48, 30), (96, 60)), ((64, 100), (128, 200)),

@@ -199,6 +199,66 @@ template <bool INV> B2N_HD void dft12(float4 *v) {
     v[k2 + 9] = y[3][k2];
   }
 }
+// 9 = 3 x 3; y[n1][k2] = DFT3 over n2 of v[3*n2 + n1], twiddles W9^(n1*k2), then DFT3 over n1
+template <bool INV> B2N_HD void dft9(float4 *v) {
+  const float c1 = 0.76604444311897803520f, s1 = 0.64278760968653932632f;   // 2 pi / 9
+  const float c2 = 0.17364817766693034885f, s2 = 0.98480775301220805937f;   // 4 pi / 9
+  const float c4 = -0.93969262078590838405f, s4 = 0.34202014332566873304f;  // 8 pi / 9
+  float4 y[3][3];
+#pragma unroll
+  for (int n1 = 0; n1 < 3; ++n1) {
+    y[n1][0] = v[n1];
+    y[n1][1] = v[n1 + 3];
+    y[n1][2] = v[n1 + 6];
+    dft3<INV>(y[n1][0], y[n1][1], y[n1][2]);
+  }
+  y[1][1] = vmulw<INV>(y[1][1], c1, -s1);  // W9^1
+  y[1][2] = vmulw<INV>(y[1][2], c2, -s2);  // W9^2
+  y[2][1] = vmulw<INV>(y[2][1], c2, -s2);  // W9^2
+  y[2][2] = vmulw<INV>(y[2][2], c4, -s4);  // W9^4
+#pragma unroll
+  for (int k2 = 0; k2 < 3; ++k2) {
+    dft3<INV>(y[0][k2], y[1][k2], y[2][k2]);
+    v[k2] = y[0][k2];
+    v[k2 + 3] = y[1][k2];
+    v[k2 + 6] = y[2][k2];
+  }
+}
+// 15 = 5 x 3; y[n1][k2] = DFT3 over n2 of v[5*n2 + n1], twiddles W15^(n1*k2), then DFT5 over n1
+template <bool INV> B2N_HD void dft15(float4 *v) {
+  // cos / sin of 2 pi k / 15 for the exponents k = n1 * k2 that occur
+  const float c1 = 0.91354545764260089550f, s1 = 0.40673664307580020775f;
+  const float c2 = 0.66913060635885821383f, s2 = 0.74314482547739423501f;
+  const float c3 = 0.30901699437494742410f, s3 = 0.95105651629515357212f;
+  const float c4 = -0.10452846326765347140f, s4 = 0.99452189536827333692f;
+  const float c6 = -0.80901699437494742410f, s6 = 0.58778525229247312917f;
+  const float c8 = -0.97814760073380563793f, s8 = -0.20791169081775933710f;
+  float4 y[5][3];
+#pragma unroll
+  for (int n1 = 0; n1 < 5; ++n1) {
+    y[n1][0] = v[n1];
+    y[n1][1] = v[n1 + 5];
+    y[n1][2] = v[n1 + 10];
+    dft3<INV>(y[n1][0], y[n1][1], y[n1][2]);
+  }
+  y[1][1] = vmulw<INV>(y[1][1], c1, -s1);
+  y[1][2] = vmulw<INV>(y[1][2], c2, -s2);
+  y[2][1] = vmulw<INV>(y[2][1], c2, -s2);
+  y[2][2] = vmulw<INV>(y[2][2], c4, -s4);
+  y[3][1] = vmulw<INV>(y[3][1], c3, -s3);
+  y[3][2] = vmulw<INV>(y[3][2], c6, -s6);
+  y[4][1] = vmulw<INV>(y[4][1], c4, -s4);
+  y[4][2] = vmulw<INV>(y[4][2], c8, -s8);
+#pragma unroll
+  for (int k2 = 0; k2 < 3; ++k2) {
+    dft5<INV>(y[0][k2], y[1][k2], y[2][k2], y[3][k2], y[4][k2]);
+    v[k2] = y[0][k2];
+    v[k2 + 3] = y[1][k2];
+    v[k2 + 6] = y[2][k2];
+    v[k2 + 9] = y[3][k2];
+    v[k2 + 12] = y[4][k2];
+  }
+}
 // 16 = 4 x 4; y[n1][k2] = DFT4 over n2 of v[4*n2 + n1]
 template <bool INV> B2N_HD void dft16_finish(float4 (*y)[4], float4 *v) {
   const float c1 = 0.92387953251128675613f, s1 = 0.38268343236508977173f;  // cos, sin of pi/8
@@ -242,15 +302,19 @@ template <bool INV> B2N_HD void dft16_half_in(float4 *v) {
 }
 
 template <int R, bool INV> B2N_HD void dft(float4 *v) {
-  static_assert(R == 2 || R == 3 || R == 4 || R == 5 || R == 7 || R == 8 || R == 10 || R == 12 || R == 16, "radix");
+  static_assert(R == 2 || R == 3 || R == 4 || R == 5 || R == 7 || R == 8 || R == 9 || R == 10 || R == 12 || R == 15 ||
+                    R == 16,
+                "radix");
   if constexpr (R == 2) dft2(v[0], v[1]);
   if constexpr (R == 3) dft3<INV>(v[0], v[1], v[2]);
   if constexpr (R == 4) dft4<INV>(v[0], v[1], v[2], v[3]);
   if constexpr (R == 5) dft5<INV>(v[0], v[1], v[2], v[3], v[4]);
   if constexpr (R == 7) dft7<INV>(v);
   if constexpr (R == 8) dft8<INV>(v);
+  if constexpr (R == 9) dft9<INV>(v);
   if constexpr (R == 10) dft10<INV>(v);
   if constexpr (R == 12) dft12<INV>(v);
+  if constexpr (R == 15) dft15<INV>(v);
   if constexpr (R == 16) dft16<INV>(v);
 }
 
@@ -391,7 +455,10 @@ __device__ __forceinline__ void fft_line_pair(int t, float4 *sm, int es, const f
   X(1280, 16, 8, 10, __VA_ARGS__) X(2048, 16, 16, 8, __VA_ARGS__)                                               \
   X(160, 8, 4, 5, __VA_ARGS__) X(200, 8, 5, 5, __VA_ARGS__) X(240, 8, 10, 3, __VA_ARGS__)                      \
   X(400, 8, 10, 5, __VA_ARGS__) X(800, 8, 10, 10, __VA_ARGS__) X(1152, 8, 12, 12, __VA_ARGS__)                 \
-  X(1536, 16, 8, 12, __VA_ARGS__) X(1600, 16, 10, 10, __VA_ARGS__) X(1920, 16, 12, 10, __VA_ARGS__)
+  X(1536, 16, 8, 12, __VA_ARGS__) X(1600, 16, 10, 10, __VA_ARGS__) X(1920, 16, 12, 10, __VA_ARGS__)              \
+  X(72, 8, 9, 1, __VA_ARGS__) X(120, 8, 15, 1, __VA_ARGS__) X(144, 16, 9, 1, __VA_ARGS__)                      \
+  X(360, 8, 5, 9, __VA_ARGS__) X(600, 8, 5, 15, __VA_ARGS__) X(720, 16, 5, 9, __VA_ARGS__)                     \
+  X(1200, 16, 5, 15, __VA_ARGS__) X(1440, 16, 10, 9, __VA_ARGS__)
 
 #define B2N_FAST_PLAN_USING(N, R0, R1, R2, ...) using Plan##N = Plan<N, R0, R1, R2>;
 B2N_FAST_PLANS(B2N_FAST_PLAN_USING, 0)

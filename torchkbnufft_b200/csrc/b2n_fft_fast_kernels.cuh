@@ -21,7 +21,7 @@ template <class P> struct FastCfg {
   static constexpr int PAIRS = P::T >= 256 ? 2 : (P::T >= 64 ? 4 : 256 / P::T);
   static constexpr int COL_THREADS = PAIRS * P::T;
   // register budget: 64 per thread (128 for radix-16 butterflies on pairs) -> resident CTAs per SM
-  static constexpr int REG_THREADS = P::RMAX >= 16 ? 512 : 1024;
+  static constexpr int REG_THREADS = P::RMAX >= 15 ? 512 : 1024;
   static constexpr int ROW_MINB = REG_THREADS / ROW_THREADS > 0 ? REG_THREADS / ROW_THREADS : 1;
   static constexpr int SENSE_MINB = REG_THREADS / SENSE_THREADS > 0 ? REG_THREADS / SENSE_THREADS : 1;
   static constexpr int COL_MINB = REG_THREADS / COL_THREADS > 0 ? REG_THREADS / COL_THREADS : 1;
