@@ -73,7 +73,7 @@ kernel_timer: Optional[KernelTimer] = None
 
 # owner-tile (output-stationary, register-accumulator) spread: on by default; rows = batch x coils
 owned_spread = True
-owned_spread_min_rows = 2
+owned_spread_min_rows = 1
 
 
 def _check_offsets(offsets: Optional[Tensor], n_offsets: int, ndim: int) -> None:

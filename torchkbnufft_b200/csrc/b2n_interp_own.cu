@@ -298,6 +298,173 @@ __global__ void __launch_bounds__(32, MINB) k_adj_own_2d(OwnArgs a, const float4
   }
 }
 
+// ---- 2-D, one to four coils: lanes = the 32 cells of the tile ------------------------------------------------------
+// With few coils the coil-group lanes of k_adj_own_2d idle.  Here a lane owns ONE cell of the 4 x 8 tile and keeps all
+// CK coils of the chunk in registers; a visit costs it one weight product and CK FMAs (complex sample x real weight):
+//   acc[c] += (hy[row] * hx[col]) * v[c]
+// Same visit records, same partial-sum scheme; the sample pre-pass writes rows of CK coils.
+template <int CK>
+__global__ void __launch_bounds__(256) k_own_pack_small(const float2 *__restrict__ kdata, float2 *__restrict__ packed, int C,
+                                                        int64_t M, int n_chunks, int n_traj,
+                                                        const int32_t *__restrict__ inv_perm, const float2 *__restrict__ fac) {
+  const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int chunk = blockIdx.y, b = blockIdx.z;
+  if (m >= M) return;
+  const float2 f = fac[inv_perm[(n_traj == 1 ? 0 : (int64_t)b * M) + m]];
+  griddep_wait();
+  float2 v[CK];
+#pragma unroll
+  for (int k = 0; k < CK; ++k) {
+    const int c = chunk * CK + k;
+    float2 x = make_float2(0.f, 0.f);
+    if (c < C) x = __ldg(&kdata[((int64_t)b * C + c) * M + m]);
+    v[k] = make_float2(x.x * f.x - x.y * f.y, x.x * f.y + x.y * f.x);
+  }
+  float2 *out = packed + (((int64_t)b * n_chunks + chunk) * M + m) * CK;
+  if constexpr (CK == 1) {
+    out[0] = v[0];
+  } else {
+#pragma unroll
+    for (int p = 0; p < CK / 2; ++p)  // planar per coil pair: (re, re', im, im')
+      reinterpret_cast<float4 *>(out)[p] = make_float4(v[2 * p].x, v[2 * p + 1].x, v[2 * p].y, v[2 * p + 1].y);
+  }
+}
+
+template <int CK> constexpr size_t own_cell_smem_bytes() {
+  return sizeof(float) * 3 * kOR * kOVF + sizeof(float2) * (2 * kOR + 1) * CK;
+}
+
+template <int CK, int U>
+__global__ void __launch_bounds__(32, 32) k_adj_own_2d_cell(OwnArgs a, const float2 *__restrict__ packed, float2 *__restrict__ grid,
+                                                      float2 *__restrict__ partials, unsigned *__restrict__ counters,
+                                                      int slot_cap) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float *s_rec = reinterpret_cast<float *>(smem_raw);                 // [3][kOR][kOVF] visit records
+  float2 *s_val = reinterpret_cast<float2 *>(s_rec + 3 * kOR * kOVF);  // [2][kOR][CK] samples (+ 1 spare visit)
+  const int lane = threadIdx.x;
+  const int n_items = a.counts[0];
+  const int4 item = a.items[blockIdx.x];
+  if ((int)blockIdx.x >= n_items) return;
+  const int4 tinfo = a.tiles[item.x];
+  const int y0 = (item.w >> 16) * kOTR, x0 = (item.w & 0xffff) * kOTC;
+  const int b = a.n_traj == 1 ? (int)blockIdx.z : item.x / (int)a.n_own_tiles;
+  const int c0 = blockIdx.y * CK;
+  const int n = item.z & 0xfff, chunk = item.z >> 12;
+  const int rounds = (n + kOR - 1) / kOR;
+  const float4 *vis = a.visits + (int64_t)item.y * (kOVF / 4);
+  // sample staging: 8-byte (CK = 1) or 16-byte copies; lane = (visit, part)
+  constexpr int PARTS = CK == 1 ? 1 : CK / 2;
+  const int vi = lane / PARTS, part = lane - vi * PARTS;
+  const float2 *pk = packed + ((int64_t)b * a.n_chunks + blockIdx.y) * a.M * CK;
+
+  auto issue_rec = [&](int round) {
+    if (round >= rounds) return;
+    float4 *dst = reinterpret_cast<float4 *>(s_rec + (round % 3) * kOR * kOVF);
+    const int base = round * kOR * (kOVF / 4), last = n * (kOVF / 4) - 1;
+#pragma unroll
+    for (int k = 0; k < kOR * (kOVF / 4) / 32; ++k) {
+      const int e = base + lane + 32 * k;
+      cp_async16(dst + lane + 32 * k, vis + (e <= last ? e : last));
+    }
+  };
+  auto issue_val = [&](int round) {
+    if (round >= rounds) return;
+    const int *rec = reinterpret_cast<const int *>(s_rec + (round % 3) * kOR * kOVF);
+    float2 *val = s_val + (round & 1) * kOR * CK;
+    if (vi < kOR) {
+      const float2 *src = pk + (size_t)(unsigned)rec[vi * kOVF + 12] * CK;
+      if constexpr (CK == 1) cp_async8(val + vi, src, true);
+      else cp_async16(val + vi * CK + part * 2, src + part * 2);
+    }
+  };
+
+  issue_rec(0);
+  issue_rec(1);
+  cp_async_commit();
+  griddep_wait();
+  float2 acc[CK];
+#pragma unroll
+  for (int k = 0; k < CK; ++k) acc[k] = make_float2(0.f, 0.f);
+  const int xl = lane & 7, yl = lane >> 3;
+  if (n > 0) {
+    cp_async_wait_all();
+    __syncwarp();
+    issue_val(0);
+    cp_async_commit();
+    for (int round = 0; round < rounds; ++round) {
+      cp_async_wait_all();
+      __syncwarp();
+      issue_val(round + 1);
+      issue_rec(round + 2);
+      cp_async_commit();
+      const float *rec = s_rec + (round % 3) * kOR * kOVF;
+      const float2 *vp = s_val + (round & 1) * kOR * CK;
+      const int nb = min(kOR, n - round * kOR);
+#pragma unroll U
+      for (int i = 0; i < nb; ++i) {
+        const float w = rec[i * kOVF + yl] * rec[i * kOVF + 4 + xl];
+        if constexpr (CK == 1) {
+          const float2 v = vp[i];
+          acc[0].x = fmaf(w, v.x, acc[0].x);
+          acc[0].y = fmaf(w, v.y, acc[0].y);
+        } else {
+          const float2 ww = make_float2(w, w);
+#pragma unroll
+          for (int p = 0; p < CK / 2; ++p) {
+            const float4 v = reinterpret_cast<const float4 *>(vp + i * CK)[p];
+            acc[2 * p] = __ffma2_rn(ww, make_float2(v.x, v.y), acc[2 * p]);
+            acc[2 * p + 1] = __ffma2_rn(ww, make_float2(v.z, v.w), acc[2 * p + 1]);
+          }
+        }
+      }
+    }
+  }
+  const int nch = tinfo.z;
+  if (nch > 1) {
+    const int64_t Bz = gridDim.z, per_slot = (int64_t)Bz * a.n_chunks;
+    const int64_t sub = (int64_t)blockIdx.z * a.n_chunks + blockIdx.y;
+    if (tinfo.w + nch > slot_cap) __trap();
+    float2 *mine = partials + (((int64_t)(tinfo.w + chunk)) * per_slot + sub) * (CK * 32);
+#pragma unroll
+    for (int k = 0; k < CK; ++k) __stcg(&mine[k * 32 + lane], acc[k]);
+    __threadfence();
+    __syncwarp();
+    unsigned old = 0;
+    unsigned *ctr = counters + (int64_t)item.x * per_slot + sub;
+    if (lane == 0) old = atomicAdd(ctr, 1u);
+    old = __shfl_sync(0xffffffffu, old, 0);
+    if (old != (unsigned)(nch - 1)) return;
+    if (lane == 0) *ctr = 0u;
+    __threadfence();
+#pragma unroll
+    for (int k = 0; k < CK; ++k) acc[k] = make_float2(0.f, 0.f);
+    for (int j = 0; j < nch; ++j) {
+      const float2 *src = partials + (((int64_t)(tinfo.w + j)) * per_slot + sub) * (CK * 32);
+#pragma unroll
+      for (int k = 0; k < CK; ++k) {
+        const float2 p = __ldcg(&src[k * 32 + lane]);
+        acc[k].x += p.x;
+        acc[k].y += p.y;
+      }
+    }
+  }
+  if (y0 + yl < a.Ky && x0 + xl < a.Kx) {
+    const float2 qy = a.q[y0 + yl], qx = a.q[a.Ky + x0 + xl];
+    const float2 qq = make_float2(qy.x * qx.x - qy.y * qx.y, qy.x * qx.y + qy.y * qx.x);
+#pragma unroll
+    for (int k = 0; k < CK; ++k) {
+      const int c = c0 + k;
+      if (c < a.C) {
+        float2 s2;
+        if constexpr (CK == 1) s2 = acc[0];
+        else s2 = (k & 1) ? make_float2(acc[k - 1].y, acc[k].y) : make_float2(acc[k].x, acc[k + 1].x);
+        grid[((int64_t)b * a.C + c) * a.Kprod + (int64_t)(y0 + yl) * a.Kx + x0 + xl] =
+            make_float2(s2.x * qq.x - s2.y * qq.y, s2.x * qq.y + s2.y * qq.x);
+      }
+    }
+  }
+}
+
 // ---- 3-D: 4 x 4 x 8 output tiles ------------------------------------------------------------------------------------
 // Same scheme one dimension up (216 neighbours per point).  Lanes = 8 cells along the last (contiguous) axis x 4 along
 // the middle axis; registers = 4 cells along the first axis x CK coils, ALL coils of the chunk in every lane (8 at
@@ -595,7 +762,7 @@ static bool own_ready(const b2n_geom *g, const b2n_points *p, int layout) {
 // coils per warp: 2-D 4 CPL (lanes hold coil groups), 3-D CK (every lane holds all of them)
 static int own_chunk_coils(int ndim, int64_t C) {
   if (ndim == 3) return C > 4 ? 8 : 4;
-  return C > 8 ? 16 : (C > 4 ? 8 : 4);
+  return C > 8 ? 16 : (C > 4 ? 8 : (C > 2 ? 4 : (int)C));  // <= 4 coils: the lane-per-cell kernel, 1 / 2 / 4 coils
 }
 
 // scratch = [arrival counters][pre-packed samples][partial tiles]; the partial tiles are sized by the plan's upper
@@ -611,7 +778,7 @@ static OwnScratch own_scratch_layout(const b2n_points *p, int64_t B, int64_t C, 
   o.ctr = align_up(sizeof(unsigned) * (size_t)(n_tiles_all * Bz * n_chunks), 256);
   o.packed = align_up(sizeof(float2) * (size_t)(B * n_chunks * cc) * (size_t)p->n_points, 256);
   // accumulators of one warp: 2-D 4 rows x CPL coils x 32 lanes, 3-D 4 planes x CK coils x 32 lanes
-  o.slot = sizeof(float2) * (size_t)(Bz * n_chunks) * (size_t)(p->ndim == 3 ? kO3Z * cc * 32 : kOTR * (cc / 4) * 32);
+  o.slot = sizeof(float2) * (size_t)(Bz * n_chunks) * (size_t)(p->ndim == 3 ? kO3Z * cc * 32 : cc * 32);
   o.total = o.ctr + o.packed + o.slot * (size_t)(n_slots > 0 ? n_slots : p->n_own_items_max);
   return o;
 }
@@ -676,8 +843,7 @@ static int launch_fix(const OwnLaunch &l) {
   return 0;
 }
 
-template <int CPL, int MINB, int U> static int launch_own(const OwnLaunch &l) {
-  OwnArgs a;
+static void own_args_2d(OwnArgs &a, const OwnLaunch &l) {
   a.Ky = (int)l.g->grid_size[0];
   a.Kx = (int)l.g->grid_size[1];
   a.C = (int)l.C;
@@ -691,6 +857,28 @@ template <int CPL, int MINB, int U> static int launch_own(const OwnLaunch &l) {
   a.tiles = (const int4 *)l.p->own_tiles;
   a.counts = l.p->own_counts;
   a.q = (const float2 *)l.p->own_q;
+}
+
+template <int CK> static int launch_own_cell(const OwnLaunch &l) {
+  OwnArgs a;
+  own_args_2d(a, l);
+  dim3 gp((unsigned)ceil_div(a.M, 256), (unsigned)l.n_chunks, (unsigned)l.B);
+  B2N_CUDA_OK(launch_pdl(k_own_pack_small<CK>, gp, dim3(256), 0, l.st, (const float2 *)l.kdata,
+                         (float2 *)(l.scratch + l.lay.ctr), (int)l.C, a.M, l.n_chunks, a.n_traj,
+                         (const int32_t *)l.p->inv_perm, (const float2 *)l.p->own_fac));
+  B2N_LAUNCH_OK("k_own_pack_small");
+  auto kern = k_adj_own_2d_cell<CK, 4>;
+  dim3 gd((unsigned)l.p->n_own_items_max, (unsigned)a.n_chunks, (unsigned)(l.p->n_traj == 1 ? l.B : 1));
+  B2N_CUDA_OK(launch_pdl(kern, gd, dim3(32), own_cell_smem_bytes<CK>(), l.st, a, (const float2 *)(l.scratch + l.lay.ctr),
+                         (float2 *)l.grid, (float2 *)(l.scratch + l.lay.ctr + l.lay.packed), (unsigned *)l.scratch,
+                         l.slot_cap));
+  B2N_LAUNCH_OK("k_adj_own_2d_cell");
+  return launch_fix(l);
+}
+
+template <int CPL, int MINB, int U> static int launch_own(const OwnLaunch &l) {
+  OwnArgs a;
+  own_args_2d(a, l);
   if (int rc = launch_pack<CPL, (CPL >= 2)>(l)) return rc;
   auto kern = k_adj_own_2d<CPL, MINB, U>;
   dim3 gd((unsigned)l.p->n_own_items_max, (unsigned)a.n_chunks, (unsigned)(l.p->n_traj == 1 ? l.B : 1));
@@ -769,7 +957,9 @@ int own_adjoint(const b2n_geom *g, const b2n_points *p, const void *kdata, int64
   if (cc == 16 && g_adj_owned == 6) return launch_own<4, 24, 4>(l);
   if (cc == 16) return launch_own<4, 24, 2>(l);
   if (cc == 8) return launch_own<2, 32, 2>(l);
-  return launch_own<1, 32, 2>(l);
+  if (cc == 4) return launch_own_cell<4>(l);
+  if (cc == 2) return launch_own_cell<2>(l);
+  return launch_own_cell<1>(l);
 }
 
 }  // namespace b2n
