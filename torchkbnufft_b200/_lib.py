@@ -28,7 +28,8 @@ OPT_ADJ_OWNED = 7
 OPT_OWN_CAP = 8
 
 _CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")
-LIB_PATH = os.path.join(_CSRC, "libb200nufft.so")
+# B2N_LIB_PATH: an alternative build of the same sources (A/B of compile-time kernel configurations, profiles/scripts)
+LIB_PATH = os.environ.get("B2N_LIB_PATH") or os.path.join(_CSRC, "libb200nufft.so")
 
 
 class Geom(Structure):

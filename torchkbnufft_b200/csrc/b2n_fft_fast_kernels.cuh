@@ -13,12 +13,18 @@ namespace b2n {
 template <class P> struct FastCfg {
   // row pass: LP line pairs per CTA (about 160 threads: small CTAs keep the last wave of a launch short -- a
   // launch is typically 1-3 waves of resident line pairs); column pass: PAIRS column pairs per CTA
-  static constexpr int LP = P::T >= 160 ? 1 : 160 / P::T;
+#ifndef B2N_FFT_ROW_TARGET
+#define B2N_FFT_ROW_TARGET 160  // threads per row-pass CTA (A/B: profiles/scripts/fft_cfg_ab.sh)
+#endif
+#ifndef B2N_FFT_COL_PAIRS
+#define B2N_FFT_COL_PAIRS 4     // column pairs per column-pass CTA for 64 <= T < 256
+#endif
+  static constexpr int LP = P::T >= B2N_FFT_ROW_TARGET ? 1 : B2N_FFT_ROW_TARGET / P::T;
   static constexpr int ROW_THREADS = LP * P::T;
   // row pass + coil sum: twice as many line pairs per CTA, i.e. fewer coil groups to meet through global memory
   static constexpr int LPS = P::T >= 160 ? 1 : 320 / P::T;
   static constexpr int SENSE_THREADS = LPS * P::T;
-  static constexpr int PAIRS = P::T >= 256 ? 2 : (P::T >= 64 ? 4 : 256 / P::T);
+  static constexpr int PAIRS = P::T >= 256 ? 2 : (P::T >= 64 ? B2N_FFT_COL_PAIRS : 256 / P::T);
   static constexpr int COL_THREADS = PAIRS * P::T;
   // register budget: 64 per thread (128 for radix-16 butterflies on pairs) -> resident CTAs per SM
   static constexpr int REG_THREADS = P::RMAX >= 15 ? 512 : 1024;

@@ -472,20 +472,19 @@ __global__ void __launch_bounds__(1024) k_own_scan(int64_t n_tiles_all, int4 *__
   if (tid == 0) counts[1] = run_s;
 }
 
-// one CTA per output tile: write its visits in window order and its work items into their LPT bucket.
-// The window (at most 9 x 13 base cells) is scanned once into shared memory; then every group of 4 lanes takes visits
-// v, v + 32, ... of the tile, finds the window cell of each by bisection of the cell offsets and writes the four
-// 16-byte parts of its record -- the dense tiles at the centre of a radial trajectory (thousands of visits) are
-// spread over the whole CTA instead of one lane per cell.
+// one CTA per WORK ITEM (at most cap visits of one tile -- the dense tiles at the centre of a radial trajectory hold
+// thousands of visits and would serialise on one CTA): the tile's window (at most 9 x 13 base cells) is scanned into
+// shared memory; then every group of 4 lanes takes visits of the item, finds the window cell of each by bisection of
+// the cell offsets and writes the four 16-byte parts of its record.
 constexpr int kOwnFillThreads = 128, kOwnWinMax = 128;
 __global__ void __launch_bounds__(kOwnFillThreads) k_own_fill(OwnGeom g, const int32_t *__restrict__ cell_start,
                                                   const int32_t *__restrict__ perm, const float *__restrict__ hw,
-                                                  const int4 *__restrict__ tiles,
-                                                  const int32_t *__restrict__ bucket_base,
-                                                  int32_t *__restrict__ bucket_fill, float4 *__restrict__ visits,
-                                                  int4 *__restrict__ items) {
+                                                  const int4 *__restrict__ tiles, const int32_t *__restrict__ counts,
+                                                  const int4 *__restrict__ items, float4 *__restrict__ visits) {
   __shared__ int s_first[kOwnWinMax + 1], s_s0[kOwnWinMax], s_warp[kOwnFillThreads / 32];
-  const int64_t t = blockIdx.x;
+  if ((int)blockIdx.x >= counts[0]) return;
+  const int4 item = items[blockIdx.x];
+  const int64_t t = item.x;
   const int tid_in = threadIdx.x, lane = tid_in & 31, warp = tid_in >> 5;
   const int64_t traj = t / g.n_own_tiles, tid = t - traj * g.n_own_tiles;
   const int ty = (int)(tid / g.ntx), tx = (int)(tid - (int64_t)ty * g.ntx);
@@ -513,9 +512,10 @@ __global__ void __launch_bounds__(kOwnFillThreads) k_own_fill(OwnGeom g, const i
     if (tid_in == kOwnFillThreads - 1) s_first[kOwnWinMax] = before + incl;  // = ti.x
     __syncthreads();
   }
-  const int n = ti.x, part = tid_in & 3;
-#pragma unroll 4
-  for (int v = tid_in >> 2; v < n; v += kOwnFillThreads / 4) {
+  // this item's visits of the tile: [chunk * cap, chunk * cap + size)
+  const int v_lo = (item.z >> 12) * g.cap, n = v_lo + (item.z & 0xfff), part = tid_in & 3;
+#pragma unroll 2
+  for (int v = v_lo + (tid_in >> 2); v < n; v += kOwnFillThreads / 4) {
     int lo = 0, hi = nw - 1;  // last window cell whose first visit is <= v (empty cells share their successor's offset)
     while (lo < hi) {
       const int mid = (lo + hi + 1) >> 1;
@@ -542,11 +542,24 @@ __global__ void __launch_bounds__(kOwnFillThreads) k_own_fill(OwnGeom g, const i
     }
     visits[(int64_t)(ti.y + v) * 4 + part] = rec;
   }
-  for (int j = tid_in; j < ti.z; j += kOwnFillThreads) {
-    const int size = max(0, min(g.cap, ti.x - j * g.cap));
-    const int b = ti.z > 1 ? 0 : own_bucket(size, g.cap);
+}
+
+// one thread per output tile: its work items (chunks of at most cap visits) go into their LPT bucket
+__global__ void __launch_bounds__(256) k_own_items(int64_t n_tiles_all, int64_t n_own_tiles, int nt1, int nt2, int ndim,
+                                                   int cap, const int4 *__restrict__ tiles,
+                                                   const int32_t *__restrict__ bucket_base,
+                                                   int32_t *__restrict__ bucket_fill, int4 *__restrict__ items) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_tiles_all) return;
+  const int4 ti = tiles[t];
+  const int64_t tid = t % n_own_tiles;
+  // 2-D: tile row << 16 | tile column; 3-D: the tile's row-major index
+  const int where = ndim == 2 ? (int)(((tid / nt1) << 16) | (tid % nt1)) : (int)tid;
+  for (int j = 0; j < ti.z; ++j) {
+    const int size = max(0, min(cap, ti.x - j * cap));
+    const int b = ti.z > 1 ? 0 : own_bucket(size, cap);
     const int pos = bucket_base[b] + atomicAdd(&bucket_fill[b], 1);
-    items[pos] = make_int4((int)t, ti.y + j * g.cap, size | (j << 12), (ty << 16) | tx);
+    items[pos] = make_int4((int)t, ti.y + j * cap, size | (j << 12), where);
   }
 }
 
@@ -614,14 +627,15 @@ __global__ void __launch_bounds__(256) k_own3_count(Own3Geom g, const int32_t *_
   }
 }
 
-// one CTA per output tile: index records of its visits in window order, work items into their LPT bucket
+// one CTA per work item: index records of its visits (window order)
 __global__ void __launch_bounds__(256) k_own3_fill(Own3Geom g, const int32_t *__restrict__ cell_start,
                                                    const int32_t *__restrict__ perm, const int4 *__restrict__ tiles,
-                                                   const int32_t *__restrict__ bucket_base,
-                                                   int32_t *__restrict__ bucket_fill, int4 *__restrict__ visits,
-                                                   int4 *__restrict__ items) {
+                                                   const int32_t *__restrict__ counts, const int4 *__restrict__ items,
+                                                   int4 *__restrict__ visits) {
   __shared__ int s_first[kOwn3WinMax + 1], s_s0[kOwn3WinMax], s_warp[8], s_run;
-  const int64_t t = blockIdx.x;
+  if ((int)blockIdx.x >= counts[0]) return;
+  const int4 item = items[blockIdx.x];
+  const int64_t t = item.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   int64_t traj;
   int o[3], wd[3], tile_id;
@@ -653,9 +667,9 @@ __global__ void __launch_bounds__(256) k_own3_fill(Own3Geom g, const int32_t *__
     if (tid == 255) s_run = before + incl;
     __syncthreads();
   }
-  const int n = ti.x;
+  const int v_lo = (item.z >> 12) * g.cap, n = v_lo + (item.z & 0xfff);  // this item's visits of the tile
 #pragma unroll 2
-  for (int v = tid; v < n; v += 256) {
+  for (int v = v_lo + tid; v < n; v += 256) {
     int lo = 0, hi = nw - 1;  // last window cell whose first visit is <= v
     while (lo < hi) {
       const int mid = (lo + hi + 1) >> 1;
@@ -667,12 +681,6 @@ __global__ void __launch_bounds__(256) k_own3_fill(Own3Geom g, const int32_t *__
     // a negative (unwrapped) base cell: the footprint reached this tile around the grid's edge
     const int neg = ((o[0] + r0 < 0) & g.neg[0]) ^ ((o[1] + r1 < 0) & g.neg[1]) ^ ((o[2] + r2 < 0) & g.neg[2]);
     visits[(int64_t)ti.y + v] = make_int4(slot, perm[slot], (r0 + 16) | ((r1 + 16) << 8) | ((r2 + 16) << 16), neg);
-  }
-  for (int j = tid; j < ti.z; j += 256) {
-    const int size = max(0, min(g.cap, ti.x - j * g.cap));
-    const int b = ti.z > 1 ? 0 : own_bucket(size, g.cap);
-    const int pos = bucket_base[b] + atomicAdd(&bucket_fill[b], 1);
-    items[pos] = make_int4((int)t, ti.y + j * g.cap, size | (j << 12), tile_id);
   }
 }
 
@@ -1030,9 +1038,13 @@ static int build_impl(const b2n_geom *geom, const void *omega, int64_t M, int64_
       B2N_LAUNCH_OK("k_own_count");
       k_own_scan<<<1, 1024, 0, st>>>(nt_all, tiles, hist, bucket_base, bucket_fill, (int32_t *)(ws + c.own_counts));
       B2N_LAUNCH_OK("k_own_scan");
-      k_own_fill<<<(unsigned)nt_all, kOwnFillThreads, 0, st>>>(
-          og, out->cell_start, out->perm, (const float *)(ws + c.own_hw), tiles, bucket_base, bucket_fill,
-          (float4 *)(ws + c.own_visits), (int4 *)(ws + c.own_items));
+      k_own_items<<<(unsigned)ceil_div(nt_all, threads), threads, 0, st>>>(nt_all, c.n_own_tiles, c.own_nt[1], 1, 2, c.own_cap,
+                                                                           tiles, bucket_base, bucket_fill,
+                                                                           (int4 *)(ws + c.own_items));
+      B2N_LAUNCH_OK("k_own_items");
+      k_own_fill<<<(unsigned)c.n_own_items_max, kOwnFillThreads, 0, st>>>(
+          og, out->cell_start, out->perm, (const float *)(ws + c.own_hw), tiles, (const int32_t *)(ws + c.own_counts),
+          (const int4 *)(ws + c.own_items), (float4 *)(ws + c.own_visits));
       B2N_LAUNCH_OK("k_own_fill");
     } else {
       Own3Geom og;
@@ -1050,8 +1062,13 @@ static int build_impl(const b2n_geom *geom, const void *omega, int64_t M, int64_
       B2N_LAUNCH_OK("k_own3_count");
       k_own_scan<<<1, 1024, 0, st>>>(nt_all, tiles, hist, bucket_base, bucket_fill, (int32_t *)(ws + c.own_counts));
       B2N_LAUNCH_OK("k_own_scan");
-      k_own3_fill<<<(unsigned)nt_all, 256, 0, st>>>(og, out->cell_start, out->perm, tiles, bucket_base, bucket_fill,
-                                                    (int4 *)(ws + c.own_visits), (int4 *)(ws + c.own_items));
+      k_own_items<<<(unsigned)ceil_div(nt_all, threads), threads, 0, st>>>(nt_all, c.n_own_tiles, c.own_nt[1], c.own_nt[2], 3,
+                                                                           c.own_cap, tiles, bucket_base, bucket_fill,
+                                                                           (int4 *)(ws + c.own_items));
+      B2N_LAUNCH_OK("k_own_items");
+      k_own3_fill<<<(unsigned)c.n_own_items_max, 256, 0, st>>>(og, out->cell_start, out->perm, tiles,
+                                                               (const int32_t *)(ws + c.own_counts),
+                                                               (const int4 *)(ws + c.own_items), (int4 *)(ws + c.own_visits));
       B2N_LAUNCH_OK("k_own3_fill");
     }
     out->own_tile = c.own_rows;
