@@ -47,6 +47,18 @@ for name in which:
     finally:
         tkbn.set_adjoint_mode("atomic")
     print(line, flush=True)
+    # roofline fractions of each direction: HBM (algorithmic bytes of SURVEY 8(d) over the measured copy bandwidth) and
+    # FP32 (8 flops per complex multiply-add x J^d neighbours x coil-points over 148 SMs x 128 lanes x 2 x 1.965 GHz)
+    d = len(wl.im_size)
+    N, K = int(np.prod(wl.im_size)), int(np.prod(wl.grid_size))
+    C, M = wl.n_coils, wl.n_points
+    fwd_b = 8 * (B * N + C * N + N + 4 * B * C * K + B * C * M) + 4 * d * M
+    adj_b = 8 * (B * C * M + 3 * B * C * K + B * C * N + C * N + B * N + N) + 4 * d * M
+    flops = 8.0 * 6 ** d * units
+    hbm, fp32 = 6559.4e9, 148 * 128 * 2 * 1.965e9
+    print(f"{name}: roofline  fwd HBM {fwd_b / (tf * 1e-3) / hbm:.3f} FP32 {flops / (tf * 1e-3) / fp32:.3f}   "
+          f"adj HBM {adj_b / (ta * 1e-3) / hbm:.3f} FP32 {flops / (ta * 1e-3) / fp32:.3f}   "
+          f"(interpolation flops {flops / 1e9:.1f} G per direction)", flush=True)
     if name == "cfg3":
         t_k = time.time(); kern = tkbn.calc_toeplitz_kernel(om, wl.im_size, norm="ortho"); torch.cuda.synchronize(); t_k = time.time() - t_k
         toep = tkbn.ToepNufft()
