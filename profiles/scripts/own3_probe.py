@@ -12,12 +12,15 @@ dev = torch.device("cuda:0")
 wl = workloads.WORKLOADS["cfg4"]
 if len(sys.argv) > 1:
     wl = wl.scaled(float(sys.argv[1]))
+FWD = len(sys.argv) > 2 and sys.argv[2] == "fwd"  # also run the forward gather once (for ncu captures)
 om = torch.from_numpy(wl.trajectory(np.float32)).to(dev)
 ob = tkbn.KbInterp(im_size=wl.im_size, dtype=torch.complex64).to(dev)
 args = (ob.tables, ob.n_shift, ob.numpoints, ob.table_oversamp)
 y = torch.randn((1, wl.n_coils, om.shape[-1]), dtype=torch.complex64, device=dev)
 fn = lambda: eng_interp.table_interp_adjoint(y, om, *args, None, ob.grid_size, mode="atomic")
 out = fn(); torch.cuda.synchronize()
+if FWD:
+    k = eng_interp.table_interp(out, om, *args, None); torch.cuda.synchronize()
 pl = list(P._PLAN_CACHE.values())[-1]
 st = pl.struct
 base = pl.workspace.data_ptr()

@@ -694,16 +694,18 @@ struct OwnFixArgs {
   const float2 *coef;
 };
 
+constexpr int kFixTiles = 32;  // output tiles looked at by one CTA (most of them have no exception points)
+
 template <int ND>
 __global__ void __launch_bounds__(128) k_own_fix(OwnFixArgs a, const float2 *__restrict__ kdata, float2 *__restrict__ grid) {
   griddep_wait();
   if (a.counts[3] > a.xcap) __trap();  // more (exception point, tile) pairs than own_xv holds: fail loudly
-  const int2 seg = a.xt[blockIdx.x];
-  if (seg.y == 0) return;
-  const int64_t traj = blockIdx.x / a.n_own_tiles;
-  int64_t tid = blockIdx.x - traj * a.n_own_tiles;
-  int o[3] = {0, 0, 0}, cl[3] = {0, 0, 0};
+  const int64_t n_tiles_all = a.n_own_tiles * a.n_traj;
+  const int64_t t_mine = (int64_t)blockIdx.x * kFixTiles + (threadIdx.x & 31);
+  const int2 seg_mine = t_mine < n_tiles_all ? a.xt[t_mine] : make_int2(0, 0);
+  unsigned todo = __ballot_sync(0xffffffffu, seg_mine.y > 0);  // the same in every warp of the CTA
   const int t = threadIdx.x;
+  int cl[3] = {0, 0, 0};
   if (ND == 3) {
     cl[0] = t >> 5;
     cl[1] = (t >> 3) & 3;
@@ -712,39 +714,48 @@ __global__ void __launch_bounds__(128) k_own_fix(OwnFixArgs a, const float2 *__r
     cl[0] = t >> 3;
     cl[1] = t & 7;
   }
-  int64_t cell = 0;
-  bool inside = true;
-  for (int d = ND - 1; d >= 0; --d) {
-    o[d] = (int)(tid % a.nt[d]) * (d == ND - 1 ? 8 : 4);
-    tid /= a.nt[d];
-  }
-  for (int d = 0; d < ND; ++d) {
-    inside = inside && o[d] + cl[d] < a.K[d];
-    cell = cell * a.K[d] + o[d] + cl[d];
-  }
-  if (!inside) return;
-  const int b = a.n_traj == 1 ? (int)blockIdx.z : (int)traj;
-  for (int c = 0; c < a.C; ++c) {
-    float2 acc = make_float2(0.f, 0.f);
-    for (int e = 0; e < seg.y; ++e) {
-      const int2 xv = a.xv[seg.x + e];
-      const float2 *rec = a.coef + (int64_t)xv.x * ND * kOJ;
-      float2 w = make_float2(1.f, 0.f);
-      bool on = true;
-#pragma unroll
-      for (int d = 0; d < ND; ++d) {
-        const int j = cl[d] - (((xv.y >> (8 * d)) & 0xff) - 16);
-        on = on && (unsigned)j < (unsigned)kOJ;
-        const float2 cw = rec[d * kOJ + (on ? j : 0)];
-        w = make_float2(w.x * cw.x - w.y * cw.y, w.x * cw.y + w.y * cw.x);
-      }
-      if (on) cmacf_conj(acc, w, kdata[((int64_t)b * a.C + c) * a.M + a.perm[xv.x]]);
+  while (todo) {
+    const int src = __ffs(todo) - 1;
+    todo &= todo - 1;
+    const int2 seg = make_int2(__shfl_sync(0xffffffffu, seg_mine.x, src), __shfl_sync(0xffffffffu, seg_mine.y, src));
+    const int64_t tile_all = (int64_t)blockIdx.x * kFixTiles + src;
+    const int64_t traj = tile_all / a.n_own_tiles;
+    int64_t tid = tile_all - traj * a.n_own_tiles;
+    int o[3] = {0, 0, 0};
+    for (int d = ND - 1; d >= 0; --d) {
+      o[d] = (int)(tid % a.nt[d]) * (d == ND - 1 ? 8 : 4);
+      tid /= a.nt[d];
     }
-    float2 *dst = grid + ((int64_t)b * a.C + c) * a.Kprod + cell;
-    float2 gv = *dst;
-    gv.x += acc.x;
-    gv.y += acc.y;
-    *dst = gv;
+    int64_t cell = 0;
+    bool inside = ND == 3 || t < 32;
+    for (int d = 0; d < ND; ++d) {
+      inside = inside && o[d] + cl[d] < a.K[d];
+      cell = cell * a.K[d] + o[d] + cl[d];
+    }
+    if (!inside) continue;
+    const int b = a.n_traj == 1 ? (int)blockIdx.z : (int)traj;
+    for (int c = 0; c < a.C; ++c) {
+      float2 acc = make_float2(0.f, 0.f);
+      for (int e = 0; e < seg.y; ++e) {
+        const int2 xv = a.xv[seg.x + e];
+        const float2 *rec = a.coef + (int64_t)xv.x * ND * kOJ;
+        float2 w = make_float2(1.f, 0.f);
+        bool on = true;
+#pragma unroll
+        for (int d = 0; d < ND; ++d) {
+          const int j = cl[d] - (((xv.y >> (8 * d)) & 0xff) - 16);
+          on = on && (unsigned)j < (unsigned)kOJ;
+          const float2 cw = rec[d * kOJ + (on ? j : 0)];
+          w = make_float2(w.x * cw.x - w.y * cw.y, w.x * cw.y + w.y * cw.x);
+        }
+        if (on) cmacf_conj(acc, w, kdata[((int64_t)b * a.C + c) * a.M + a.perm[xv.x]]);
+      }
+      float2 *dst = grid + ((int64_t)b * a.C + c) * a.Kprod + cell;
+      float2 gv = *dst;
+      gv.x += acc.x;
+      gv.y += acc.y;
+      *dst = gv;
+    }
   }
 }
 
@@ -834,7 +845,7 @@ static int launch_fix(const OwnLaunch &l) {
   f.xt = (const int2 *)l.p->own_xt;
   f.xv = (const int2 *)l.p->own_xv;
   f.coef = (const float2 *)l.p->coef;
-  dim3 gf((unsigned)(f.n_own_tiles * l.p->n_traj), 1, (unsigned)(l.p->n_traj == 1 ? l.B : 1));
+  dim3 gf((unsigned)ceil_div(f.n_own_tiles * l.p->n_traj, kFixTiles), 1, (unsigned)(l.p->n_traj == 1 ? l.B : 1));
   if (l.g->ndim == 3)
     B2N_CUDA_OK(launch_pdl(k_own_fix<3>, gf, dim3(128), 0, l.st, f, (const float2 *)l.kdata, (float2 *)l.grid));
   else
