@@ -493,13 +493,15 @@ def test_plan_cache_tracks_trajectory_edits():
     assert torch.equal(b, interp(grid, om.clone()))
 
 
-@pytest.mark.parametrize("grid_size", [(32, 32), (40, 56), (16, 20), (13, 37), (64, 19)])
+@pytest.mark.parametrize("grid_size", [(32, 32), (40, 56), (16, 20), (13, 37), (64, 19), (18, 27), (22, 36)])
 @pytest.mark.parametrize("B, C, batched", [(1, 1, False), (2, 2, False), (1, 3, False), (1, 5, False), (2, 8, True),
                                            (1, 12, False), (1, 16, False), (1, 20, False), (3, 32, True)])
 def test_tiled_kernels_match_generic_and_oracle(grid_size, B, C, batched):
-    """The shared-memory tiled kernels (complex64, 2-D, J=6) against the generic kernels
-    and the oracle: every coil-chunk width, partial tiles, grids smaller than a tile,
-    periodic wrap, dense sub-problems (> sub_cap points in one tile), batched trajectories."""
+    """The tiled / owner-tile kernels (complex64, 2-D, J=6) against the generic kernels
+    and the oracle: every coil-chunk width, partial tiles (also of the 4 x 8 owner tiles: 18, 22, 27, 19 cells),
+    grids smaller than a tile, periodic wrap, dense sub-problems / work items, batched trajectories.  "force" runs the
+    owner-tile spread where the plan carries visit lists; the round-1 shared-memory variants (the fallback for
+    non-standard tables) are exercised with the owner path switched off."""
     rng = np.random.default_rng(hash((grid_size, B, C)) & 0xFFFF)
     im_size = tuple(max(2, k // 2) for k in grid_size)
     ob = tkbn.KbInterp(im_size=im_size, grid_size=grid_size, dtype=torch.complex64).to(DEV)
@@ -527,11 +529,13 @@ def test_tiled_kernels_match_generic_and_oracle(grid_size, B, C, batched):
     # the forced tiled adjoint variants (warp-owned rows / warp-owned coils / warp-private tiles) and the
     # 8-coil forward chunks
     lib = _lib.load()
-    for variant in (1, 2, 3, 4, 5, 6):
+    for variant in (0, 1, 2, 3, 4, 5, 6):
         try:
+            eng_interp.owned_spread = False
             lib.b2n_set_option(_lib.OPT_ADJ_ROW_OWNERSHIP, variant)
             alt = host(eng_interp.table_interp_adjoint(dev(kdata), dev(omega), *args, None, ob.grid_size, mode="atomic"))
         finally:
+            eng_interp.owned_spread = True
             lib.b2n_set_option(_lib.OPT_ADJ_ROW_OWNERSHIP, 0)
         assert rel_l2(alt, want_a) <= 1e-4, f"adjoint variant {variant}"
     for chunk in (8, 1):  # default 0 = one 16-coil CTA per sub-problem; 1 = persistent kernel; 8 = 8-coil CTAs
@@ -938,3 +942,31 @@ def test_channel_last_tiled_spread_matches_coil_major(grid_size, B, C):
     want = orc.table_interp_adjoint(kdata, omega, tables, host(ob.n_shift), ob.numpoints.tolist(),
                                     ob.table_oversamp.tolist(), grid_size, nthreads=4)
     assert rel_l2(host(cl.movedim(-1, 1)), want) <= 1e-5
+
+
+@pytest.mark.parametrize("grid_size", [(48, 40), (20, 24, 32)])
+def test_modified_tables_take_the_complex_weight_kernels(grid_size):
+    """The owner-tile spread needs tables of the reference's form (real kernel x linear phase).  A module whose table
+    buffer was edited must not get visit lists -- its adjoint runs on the complex-weight kernels -- and still agrees
+    with the oracle evaluated with the SAME edited tables; the untouched module keeps the fast path."""
+    rng = np.random.default_rng(len(grid_size))
+    d = len(grid_size)
+    im_size = tuple(k // 2 for k in grid_size)
+    M, C = 2500, 4
+    omega = np.ascontiguousarray(rng.uniform(-np.pi, np.pi, size=(d, M)).astype(np.float32))
+    kdata = workloads.complex_normal(rng, (1, C, M))
+    from torchkbnufft_b200._nufft import plan as P
+
+    for edit in (False, True):
+        ob = tkbn.KbInterpAdjoint(im_size=im_size, grid_size=grid_size, dtype=torch.complex64).to(DEV)
+        if edit:
+            with torch.no_grad():
+                ob.table_1[1000:1100] *= torch.polar(torch.tensor(1.0), torch.tensor(0.3)).to(DEV)  # foreign phase
+        got = host(ob(dev(kdata), dev(omega)))
+        geo = P.get_geometry(ob.tables, ob.n_shift, ob.numpoints, ob.table_oversamp, ob.grid_size)
+        plan = P.get_plan(geo, dev(omega))
+        assert bool(plan.struct.own_tile) == (not edit)
+        tables = [host(t) for t in ob.tables]
+        want = orc.table_interp_adjoint(kdata, omega, tables, host(ob.n_shift), ob.numpoints.tolist(),
+                                        ob.table_oversamp.tolist(), grid_size)
+        assert rel_l2(got, want) <= 1e-4, edit

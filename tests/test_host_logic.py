@@ -184,3 +184,32 @@ def test_batched_dcomp_equals_loop():
     batched = tkbn.calc_density_compensation_function(ktraj, (10, 8), num_iterations=4)
     looped = torch.cat([tkbn.calc_density_compensation_function(k, (10, 8), num_iterations=4) for k in ktraj])
     assert torch.allclose(batched, looped)
+
+
+def test_real_table_form_accepts_reference_tables_and_rejects_modified_ones():
+    """The owner-tile spread works with the REAL Kaiser-Bessel kernel when the tables are r(x) exp(-1j p x) with
+    p = pi (N - 1) / K (what the reference builds, torchkbnufft/_nufft/utils.py:160-204); the host check that decides
+    it must recover p exactly, reproduce the table to float32 rounding, and refuse anything else."""
+    import numpy as np
+
+    from torchkbnufft_b200._nufft import plan as P
+    from torchkbnufft_b200._nufft import utils
+
+    for N, K in ((320, 640), (75, 150), (128, 200), (9, 16)):
+        tabs = utils.build_table((N,), (K,), (6,), (1024,), (0,), (2.34 * 6,))
+        for dt, tol in ((torch.complex64, 1e-7), (torch.complex128, 1e-14)):
+            got = P.real_table_form([tabs[0].to(dt)], [6], [1024], [K])
+            assert got is not None, (N, K, dt)
+            real, slope = got[0]
+            assert abs(slope * K / np.pi - (N - 1)) < 1e-9
+            x = np.arange(6 * 1024 + 1) / 1024 - 3
+            rebuilt = real.numpy().astype(np.float64) * np.exp(-1j * slope * x)
+            want = tabs[0].to(dt).numpy().astype(np.complex128)
+            assert np.abs(rebuilt - want).max() <= tol * np.abs(want).max()
+            assert float(real.min()) >= 0.0  # a Kaiser-Bessel kernel is non-negative
+    tab = utils.build_table((64,), (128,), (6,), (1024,), (0,), (2.34 * 6,))[0].to(torch.complex64)
+    bad = tab.clone()
+    bad[3000] = bad[3000] * torch.tensor(np.exp(0.01j), dtype=torch.complex64)  # one entry with a foreign phase
+    assert P.real_table_form([bad], [6], [1024], [128]) is None
+    assert P.real_table_form([torch.randn(6145, dtype=torch.complex64)], [6], [1024], [128]) is None
+    assert P.real_table_form([tab[:-5]], [6], [1024], [128]) is None  # wrong length
