@@ -39,11 +39,12 @@ def replayed_kernel_count() -> int:
 
 
 class _Entry:
-    __slots__ = ("calls", "graph", "out", "refs", "n_kernels")
+    __slots__ = ("calls", "graph", "out", "refs", "n_kernels", "failed")
 
     def __init__(self):
         self.calls = 0
         self.n_kernels = 0
+        self.failed = False
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         self.out: Optional[Tensor] = None
         self.refs: tuple = ()
@@ -116,7 +117,7 @@ def replay_or_run(kind: str, operands: Sequence[Optional[Tensor]], statics: Sequ
         ent.graph.replay()
         _REPLAYED_KERNELS += ent.n_kernels
         return ent.out
-    if ent.calls < 3:
+    if ent.calls < 3 or ent.failed:
         return fn()  # first sights: run eagerly (builds the plan, twiddles, scratch -- nothing of that may be captured)
     plan = pin()
     if getattr(plan, "_n_sub_event", None) is not None or not getattr(plan, "_count_requested", True):
@@ -125,8 +126,13 @@ def replay_or_run(kind: str, operands: Sequence[Optional[Tensor]], statics: Sequ
     lib = _lib.load()
     graph = torch.cuda.CUDAGraph()
     before = lib.b2n_launch_count()
-    with torch.cuda.graph(graph):
-        out = fn()
+    try:
+        with torch.cuda.graph(graph):
+            out = fn()
+    except Exception:  # something in this call cannot be captured (e.g. a lazy allocation): stay eager for this key
+        ent.failed = True
+        torch.cuda.synchronize(dev)
+        return fn()
     ent.n_kernels = int(lib.b2n_launch_count() - before)  # launches recorded into the graph, not executed
     ent.graph, ent.out = graph, out
     ent.refs = (tuple(operands), tuple(statics), omega, plan)
