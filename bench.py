@@ -711,11 +711,13 @@ def main():
         graph_info = {"error": repr(exc)}
 
     # ---- the north-star partitions, device-timed with the max over ranks (BASELINE.json config 5 / coil split) -----
-    def timed_steps(fn, n_steps, n_warm=6):
+    def timed_steps(fn, n_steps, n_warm=7):
         """Mean device ms per call of fn over n_steps, L2 flushed between steps, barrier + synchronize on both
         sides, MAX over ranks."""
-        for _ in range(n_warm):
+        for i in range(n_warm):
             fn()
+            if i == 2:
+                torch.cuda.synchronize()  # plan counts read back before the calls that capture graphs (graph mode)
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
