@@ -25,6 +25,7 @@ _PLAN_CACHE: "OrderedDict[tuple, TrajectoryPlan]" = OrderedDict()
 _GRID_SIZE_CACHE: dict = {}
 GEOM_CACHE_SIZE = 32
 PLAN_CACHE_SIZE = 8
+PLAN_CACHE_BYTES = 16 << 30  # device memory the cached plans may hold together (the newest plan always stays)
 # every mutation of the process-global caches below happens under this lock (threaded / DataParallel callers)
 _LOCK = threading.RLock()
 # "version" (default): plans are keyed on (storage pointer, tensor version, shape, stride): in-place edits through
@@ -494,7 +495,10 @@ def get_plan(geo: Geometry, omega: Tensor) -> TrajectoryPlan:
         else:
             plan = TrajectoryPlan(geo, omega)
             _PLAN_CACHE[key] = plan
-            while len(_PLAN_CACHE) > PLAN_CACHE_SIZE:
+            # bounded by count AND by bytes: a 3-D plan with owner-tile visit lists is gigabytes (5 GB at BASELINE
+            # config 4), a 2-D one tens of megabytes
+            while len(_PLAN_CACHE) > 1 and (len(_PLAN_CACHE) > PLAN_CACHE_SIZE or
+                                            sum(p.workspace.numel() for p in _PLAN_CACHE.values()) > PLAN_CACHE_BYTES):
                 evicted = _PLAN_CACHE.popitem(last=False)[1]
                 for k in [k for k, v in _PLAN_FAST.items() if v is evicted]:
                     del _PLAN_FAST[k]  # an evicted plan must free its device memory
