@@ -185,6 +185,12 @@ enum b2n_option {
                             the plan carries visit lists (2-D complex64 J = 6); 0: the scratch-tile + merge kernels */
   B2N_OPT_OWN_CAP = 8, /* visits per work item of the owner-tile spread, read when a plan is built (0 = default: 128 in
                           2-D, 1024 in 3-D; at most 4095) */
+  B2N_OPT_FFT_STREAM = 9, /* planned FFT passes that run as persistent kernels whose CTAs keep the operands of their next
+                             tile in flight (asynchronous copies into shared memory) while they transform the current
+                             one, as a mask: 1 forward columns, 2 inverse columns (16 / 32: the same with half as many
+                             columns per CTA, for A/B).  Default 1: -3 % on the 384^2 x 32-coil forward, neutral where
+                             the input is L2-resident; the inverse pass holds twice the operands per tile and loses a
+                             resident CTA (profiles/r02_fft_stream_ab.log).  Results are bit-identical either way. */
   B2N_OPT_COUNT
 };
 B2N_API int b2n_set_option(int option, int value);
@@ -319,6 +325,32 @@ B2N_API int b2n_fft_toeplitz_fused(int ndim, const int64_t *im_size, const int64
                                    const void *smaps_dev, int64_t smaps_batch, const void *kernel_dev,
                                    int64_t kernel_batch, double scale, const void *const *twiddle_dev, void *out_dev,
                                    void *work_dev, void *stream);
+
+/* ---- sum all-reduce over NVLink peer memory (coil-sharded SENSE adjoint; one process per GPU on one node) ------------
+ * The reference has no multi-GPU code; the coupling point this replaces is the coil sum of the SENSE adjoint
+ * (modules/kbnufft.py:404-405) when the coils are split over GPUs.  Each rank creates a *window* (library-owned device
+ * memory -- the one exception to "the library never allocates": CUDA IPC needs the base of an allocation), hands its
+ * 64-byte handle to the other ranks (any host channel: torch.distributed, MPI, a pipe), opens theirs, and from then on
+ * one kernel per rank and call pushes the partial result into every peer's window, flags it, waits for the peers' and
+ * adds the slots in rank order (bit-identical results on all ranks).  Every rank must issue the same sequence of
+ * b2n_peer_allreduce_sum calls with the same n_floats; a window serves one stream at a time.  */
+#define B2N_PEER_MAX_RANKS 16
+#define B2N_PEER_HANDLE_BYTES 64
+typedef struct b2n_peer_comm {
+  int32_t rank, world;               /* this process, processes (<= B2N_PEER_MAX_RANKS) */
+  int64_t max_floats;                /* capacity the windows were sized for (b2n_peer_window_bytes) */
+  void *window[B2N_PEER_MAX_RANKS];  /* [world] device pointers in THIS process: own window, peers' mappings */
+} b2n_peer_comm;
+B2N_API int b2n_peer_window_bytes(int world, int64_t max_floats, size_t *bytes);
+/* cudaMalloc + zero-fill + cudaIpcGetMemHandle; synchronises the device.  handle_out: B2N_PEER_HANDLE_BYTES bytes */
+B2N_API int b2n_peer_window_create(size_t bytes, void **window_dev, void *handle_out);
+B2N_API int b2n_peer_window_open(const void *handle, void **window_dev);  /* a peer's window, mapped here */
+B2N_API int b2n_peer_window_close(void *window_dev);                      /* unmap a peer's window */
+B2N_API int b2n_peer_window_destroy(void *window_dev);                    /* free this rank's own window */
+/* out = sum over ranks of in (float32 units: a complex64 image is 2 floats per value); in place allowed; enqueued on
+ * `stream`, CUDA-graph capturable (the call counter lives in the window). */
+B2N_API int b2n_peer_allreduce_sum(const b2n_peer_comm *comm, const void *in_dev, void *out_dev, int64_t n_floats,
+                                   void *stream);
 
 #ifdef __cplusplus
 }

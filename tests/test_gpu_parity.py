@@ -766,6 +766,34 @@ def test_fft_prefetch_and_pdl_options_do_not_change_results(N, K, C):
             assert np.array_equal(a, b)
 
 
+@pytest.mark.parametrize("N, K, C", [((320, 320), (640, 640), 16), ((200, 511), (448, 1024), 16),
+                                     ((31, 29), (64, 64), 3), ((20, 33, 48), (64, 64, 128), 4),
+                                     ((96, 90), (192, 192), 40), ((64, 35), (128, 70), 5)])
+def test_streamed_fft_passes_do_not_change_results(N, K, C):
+    """B2N_OPT_FFT_STREAM (persistent column passes whose CTAs keep the operands of their next tile in flight with
+    asynchronous copies) runs the same butterflies in the same order: outputs are bit-identical with the classic
+    one-tile-per-CTA passes, over several tiles per CTA, partial column blocks, odd inner extents (classic route)
+    and 3-D grids."""
+    torch.manual_seed(7)
+    dt = torch.complex64
+    lib = _lib.load()
+    image = torch.randn((2, 1) + N, dtype=dt, device=DEV)
+    smaps = torch.randn((1, C) + N, dtype=dt, device=DEV)
+    grid = torch.randn((2, C) + K, dtype=dt, device=DEV)
+    assert lib.b2n_get_option(_lib.OPT_FFT_STREAM) == 1
+    res = []
+    try:
+        for mask in (0, 1, 3, 51):
+            lib.b2n_set_option(_lib.OPT_FFT_STREAM, mask)
+            res.append((host(eng_fft.fused_fft_forward(image, K, smaps, None, 1.0)),
+                        host(eng_fft.fused_fft_adjoint(grid, N, smaps, None, 1.0))))
+    finally:
+        lib.b2n_set_option(_lib.OPT_FFT_STREAM, 1)
+    for other in res[1:]:
+        for a, b in zip(res[0], other):
+            assert np.array_equal(a, b)
+
+
 def test_fast_fft_plans_agree_with_runtime_passes():
     """B2N_OPT_FAST_FFT on/off must give the same transform (different kernels, same maths)."""
     torch.manual_seed(2)

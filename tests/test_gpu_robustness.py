@@ -264,3 +264,56 @@ def test_library_owned_graph_replay_matches_eager():
     finally:
         tkbn.set_graph_mode(False)
     assert not graphs._CACHE
+
+
+@pytest.mark.parametrize("world", [1, 2, 5])
+def test_peer_allreduce_protocol_on_one_device(world):
+    """b2n_peer_allreduce_sum with every "rank" on ONE device (windows of the same process, one stream per rank, no
+    IPC): pushes, flags, rank-ordered sums, double-buffered slots over repeated calls, the scalar path for odd and
+    unaligned lengths, in place and out of place.  The multi-process version over NVLink is tests/test_gpu_multi.py."""
+    import ctypes
+
+    lib = _lib.load()
+    max_floats = 50000
+    nbytes = ctypes.c_size_t(0)
+    assert lib.b2n_peer_window_bytes(world, max_floats, ctypes.byref(nbytes)) == 0
+    assert lib.b2n_peer_window_bytes(0, max_floats, ctypes.byref(nbytes)) == -1
+    assert lib.b2n_peer_window_bytes(_lib.PEER_MAX_RANKS + 1, max_floats, ctypes.byref(nbytes)) == -1
+    windows, comms = [], []
+    for r in range(world):
+        w, h = ctypes.c_void_p(None), ctypes.create_string_buffer(_lib.PEER_HANDLE_BYTES)
+        _lib.check(lib.b2n_peer_window_create(nbytes.value, ctypes.byref(w), h), "b2n_peer_window_create")
+        windows.append(w)
+    for r in range(world):
+        c = _lib.PeerComm()
+        c.rank, c.world, c.max_floats = r, world, max_floats
+        for q in range(world):
+            c.window[q] = windows[q].value
+        comms.append(c)
+    streams = [torch.cuda.Stream() for _ in range(world)]
+    gen = torch.Generator(device="cpu").manual_seed(17)
+    try:
+        assert lib.b2n_peer_allreduce_sum(ctypes.byref(comms[0]), 16, 16, max_floats + 1, 0) == -2  # B2N_E_RANGE
+        for n, in_place in ((4096, True), (1, False), (8192 + 4, True), (12345, False), (49999, True), (50000, False),
+                            (4, True), (20480, True), (20480, False)):
+            parts = [torch.randn(n + 1, generator=gen).to(DEV) for _ in range(world)]
+            want = parts[0].clone()
+            for p in parts[1:]:
+                want += p
+            for off in (0, 1):  # off = 1: 4-byte aligned only -> scalar kernel
+                ins = [p[off:off + n] if off else p[:n] for p in parts]
+                outs = [x if in_place else torch.empty_like(x) for x in (i.clone() for i in ins)]
+                srcs = outs if in_place else [i.clone() for i in ins]
+                torch.cuda.synchronize()
+                for r in range(world):
+                    with torch.cuda.stream(streams[r]):
+                        _lib.check(lib.b2n_peer_allreduce_sum(ctypes.byref(comms[r]), srcs[r].data_ptr(),
+                                                              outs[r].data_ptr(), n, streams[r].cuda_stream),
+                                   "b2n_peer_allreduce_sum")
+                torch.cuda.synchronize()
+                for r in range(world):
+                    assert torch.equal(outs[r], want[off:off + n]), (n, off, r)
+    finally:
+        torch.cuda.synchronize()
+        for w in windows:
+            lib.b2n_peer_window_destroy(w)

@@ -26,6 +26,7 @@ OPT_PDL = 5
 OPT_FFT_PREFETCH = 6
 OPT_ADJ_OWNED = 7
 OPT_OWN_CAP = 8
+OPT_FFT_STREAM = 9
 
 _CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")
 # B2N_LIB_PATH: an alternative build of the same sources (A/B of compile-time kernel configurations, profiles/scripts)
@@ -96,6 +97,21 @@ class Points(Structure):
     ]
 
 
+PEER_MAX_RANKS = 16
+PEER_HANDLE_BYTES = 64
+
+
+class PeerComm(Structure):
+    """struct b2n_peer_comm"""
+
+    _fields_ = [
+        ("rank", c_int32),
+        ("world", c_int32),
+        ("max_floats", c_int64),
+        ("window", c_void_p * PEER_MAX_RANKS),
+    ]
+
+
 class EngineError(RuntimeError):
     """A libb200nufft call returned a non-zero status."""
 
@@ -140,6 +156,12 @@ SIGNATURES = {
                                       c_int64, c_void_p, c_double, POINTER(c_void_p), c_void_p, c_void_p, c_void_p]),
     "b2n_fft_toeplitz_fused": (c_int, [c_int, _I64P, _I64P, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_int64,
                                        c_void_p, c_int64, c_double, POINTER(c_void_p), c_void_p, c_void_p, c_void_p]),
+    "b2n_peer_window_bytes": (c_int, [c_int, c_int64, POINTER(c_size_t)]),
+    "b2n_peer_window_create": (c_int, [c_size_t, POINTER(c_void_p), c_void_p]),
+    "b2n_peer_window_open": (c_int, [c_void_p, POINTER(c_void_p)]),
+    "b2n_peer_window_close": (c_int, [c_void_p]),
+    "b2n_peer_window_destroy": (c_int, [c_void_p]),
+    "b2n_peer_allreduce_sum": (c_int, [POINTER(PeerComm), c_void_p, c_void_p, c_int64, c_void_p]),
 }
 
 _lib: Optional[ctypes.CDLL] = None

@@ -292,6 +292,7 @@ static bool runtime_pass_fits(int64_t n) {
 }
 
 int g_fast_fft = 1;  // B2N_OPT_FAST_FFT: compile-time planned passes where a plan exists
+int g_fft_stream = 1;  // B2N_OPT_FFT_STREAM: mask of the planned passes that run as streamed persistent kernels
 int g_counters_early = 1;  // 0 (B2N_OPT_PDL = 3, for A/B): counters zeroed right before k_fft_rows_sense
 
 // entry points of the compile-time planned passes, defined in b2n_fft_plans_*.cu

@@ -381,25 +381,30 @@ template <int R, bool INV> B2N_HD void stage_compute(float4 *v, const float2 *tw
 
 #ifdef __CUDACC__
 // One line pair through all stages.  `t` = this thread's item index (0 <= t < P::T), `sm` = the
-// pair's shared exchange buffer, element i at sm[P::pad(i) * es].  loadg(i) returns input element i of
-// both lines, storeg(i, v) takes output element i.  Every thread of the CTA must call this
+// pair's shared exchange buffer, element i at sm[P::pad(i) * es].  loadg(i, r) returns input element i = t + r*I0
+// of both lines (r = the leg: a staged pass keeps leg r in its own slot), storeg(i, v) takes output element i,
+// after0() runs once behind the first barrier (every first-stage operand has been consumed: a streamed pass
+// issues the asynchronous copies of its next tile there).  Every thread of the CTA must call this
 // (it contains CTA-wide barriers); threads with nothing to do pass functors that read zeros
 // and drop stores.
 // HIN : input elements i >= N/2 are zero padding (never loaded, first butterfly simplified).
 // HOUT: output elements i >= N/2 are cropped (never computed: only the legs r < R/2 of the last
 //       stage are stored and the compiler drops the rest of that butterfly).
-template <class P, bool INV, bool HIN, bool HOUT, class LoadG, class StoreG>
+struct NoHook {
+  __device__ __forceinline__ void operator()() const {}
+};
+template <class P, bool INV, bool HIN, bool HOUT, class LoadG, class StoreG, class After0 = NoHook>
 __device__ __forceinline__ void fft_line_pair(int t, float4 *sm, int es, const float2 *tws, LoadG loadg,
-                                              StoreG storeg) {
+                                              StoreG storeg, After0 after0 = After0()) {
   float4 v[P::RMAX];
   if (t < P::I0) {
     if constexpr (HIN) {
 #pragma unroll
-      for (int r = 0; r < P::R0 / 2; ++r) v[r] = loadg(t + r * P::I0);
+      for (int r = 0; r < P::R0 / 2; ++r) v[r] = loadg(t + r * P::I0, r);
       dft_half_in<P::R0, INV>(v);
     } else {
 #pragma unroll
-      for (int r = 0; r < P::R0; ++r) v[r] = loadg(t + r * P::I0);
+      for (int r = 0; r < P::R0; ++r) v[r] = loadg(t + r * P::I0, r);
       dft<P::R0, INV>(v);
     }
     float4 *dst = sm + t * (P::R0 + 1) * es;  // pad(t*R0 + r) == t*(R0+1) + r
@@ -407,6 +412,7 @@ __device__ __forceinline__ void fft_line_pair(int t, float4 *sm, int es, const f
     for (int r = 0; r < P::R0; ++r) dst[r * es] = v[r];
   }
   __syncthreads();
+  after0();
   const int k1 = t & (P::R0 - 1);
   const int o1 = (t - k1) * P::R1 + k1;
   const float4 *src = sm + P::pad(t) * es;

@@ -4,6 +4,7 @@
 #pragma once
 #include "b2n_fft_args.cuh"
 #include "b2n_fft_fast.cuh"
+#include "b2n_tiled_common.cuh"
 
 namespace b2n {
 
@@ -83,7 +84,7 @@ __global__ void __launch_bounds__(FastCfg<P>::ROW_THREADS, FastCfg<P>::ROW_MINB)
       if (sm && !(bytes & 15u) && !(reinterpret_cast<uintptr_t>(sm) & 15)) prefetch_l2_bulk(sm, bytes);
     }
   }
-  auto loadg = [&](int i) -> float4 {
+  auto loadg = [&](int i, int) -> float4 {
     float4 v = fast::v4(0.f, 0.f, 0.f, 0.f);
     if (i < n_in) {  // zero padding is never read
       if (MODE == ROW_FWD_FIRST) {
@@ -144,7 +145,7 @@ __global__ void __launch_bounds__(FastCfg<P>::COL_THREADS, FastCfg<P>::COL_MINB)
       for (int i = threadIdx.x; i < n_in; i += FastCfg<P>::COL_THREADS) prefetch_l2(base + (int64_t)i * X);
     }
   }
-  auto loadg = [&](int i) -> float4 {
+  auto loadg = [&](int i, int) -> float4 {
     if (!on || i >= n_in) return fast::v4(0.f, 0.f, 0.f, 0.f);
     float4 v = in[i * X2];
     if (mul) v = fast::vmul2(v, mul[i * X2]);
@@ -154,6 +155,68 @@ __global__ void __launch_bounds__(FastCfg<P>::COL_THREADS, FastCfg<P>::COL_MINB)
     if (on && i < n_out) out[i * X2] = fast::vscale(v, scale);
   };
   fast::fft_line_pair<P, INV, HALF && !INV, HALF && INV>(t, fsm4 + p, PAIRS, a.tw + P::N, loadg, storeg);
+}
+
+// Streamed column pass: a persistent CTA walks tiles (blocks of 2*PAIRS columns of one outer index) and keeps the
+// first-stage operands of its NEXT tile in flight while it transforms the current one.  Every thread copies the
+// operands of its own first butterfly (cp.async, 16 bytes each, zero-filled beyond n_in / X) into slots only it reads,
+// so consuming them needs no barrier -- just cp.async.wait_group -- and no registers are held across the tile (a
+// register prefetch cost a resident CTA: profiles/r02_fft_persist_ab.log).  The copies are issued behind the first
+// barrier of the tile, when the previous operands have been consumed, and land during the remaining stages and stores.
+template <class P, bool INV, bool HALF, int PAIRS_ = FastCfg<P>::PAIRS> struct StreamCfg {
+  static constexpr int PAIRS = PAIRS_, NT = PAIRS_ * P::T;
+  static constexpr int NL = (HALF && !INV) ? P::R0 / 2 : P::R0;  // first-stage operands per thread
+  static constexpr size_t SMEM = sizeof(float4) * ((size_t)PAIRS * P::NP + (size_t)NL * NT);
+  static constexpr int BY_SMEM = (int)((size_t)226 * 1024 / (SMEM + 1024));
+  static constexpr int BY_REGS = FastCfg<P>::REG_THREADS / NT > 0 ? FastCfg<P>::REG_THREADS / NT : 1;
+  static constexpr int MINB = BY_SMEM < 1 ? 1 : (BY_SMEM < BY_REGS ? BY_SMEM : BY_REGS);
+};
+
+template <class P, bool INV, bool HALF, int PAIRS_>
+__global__ void __launch_bounds__(StreamCfg<P, INV, HALF, PAIRS_>::NT, StreamCfg<P, INV, HALF, PAIRS_>::MINB)
+    k_fft_cols_stream(ColArgs a, uint32_t tiles_x, uint32_t tiles) {
+  extern __shared__ __align__(16) float4 fsm4[];
+  using S = StreamCfg<P, INV, HALF, PAIRS_>;
+  constexpr int PAIRS = S::PAIRS, NT = S::NT, NL = S::NL;
+  griddep_launch();
+  griddep_wait();  // the input rows come from the preceding pass
+  const int p = threadIdx.x % PAIRS, t = threadIdx.x / PAIRS;
+  const int X = (int)a.X, X2 = X >> 1, n_in = a.n_in, n_out = a.n_out;
+  float4 *slot = fsm4 + PAIRS * P::NP + threadIdx.x;  // leg r of this thread at slot[r * NT]
+  const float scale = a.scale;
+  auto issue = [&](uint32_t tile) {
+    if (t < P::I0) {
+      const uint32_t oa = tile / tiles_x, bx = tile - oa * tiles_x;
+      const int x = ((int)bx * PAIRS + p) * 2;
+      const bool on = x < X;
+      const float4 *in = reinterpret_cast<const float4 *>(a.in + (int64_t)oa * n_in * a.X + (on ? x : 0));
+#pragma unroll
+      for (int r = 0; r < NL; ++r) {
+        const int i = t + r * P::I0;
+        const bool ok = on && i < n_in;
+        cp_async16z(slot + r * NT, in + (ok ? i * X2 : 0), ok);
+      }
+    }
+    cp_async_commit();
+  };
+  uint32_t tile = blockIdx.x;
+  if (tile < tiles) issue(tile);
+  for (; tile < tiles; tile += gridDim.x) {
+    const uint32_t oa = tile / tiles_x, bx = tile - oa * tiles_x;
+    const int x = ((int)bx * PAIRS + p) * 2;
+    const bool on = x < X;
+    float4 *out = reinterpret_cast<float4 *>(a.out + (int64_t)oa * n_out * a.X + (on ? x : 0));
+    cp_async_wait_all();  // this thread's own operands have landed
+    auto loadg = [&](int, int r) -> float4 { return slot[r * NT]; };
+    auto storeg = [&](int i, float4 v) {
+      if (on && i < n_out) out[i * X2] = fast::vscale(v, scale);
+    };
+    auto after0 = [&]() {
+      if (tile + gridDim.x < tiles) issue(tile + gridDim.x);
+    };
+    fast::fft_line_pair<P, INV, HALF && !INV, HALF && INV>(t, fsm4 + p, PAIRS, a.tw + P::N, loadg, storeg, after0);
+    __syncthreads();  // the exchange buffer is rewritten by the next tile's first stage
+  }
 }
 
 // Toeplitz column pass: forward transform of the columns, multiply by the kernel spectrum, inverse transform, all
@@ -186,7 +249,7 @@ __global__ void __launch_bounds__(FastCfg<P>::COL_THREADS, FastCfg<P>::COL_MINB)
     }
   }
   float4 *spec = fsm4 + PAIRS * P::NP;  // the filtered spectrum of this CTA's columns, natural order [N][PAIRS]
-  auto load_in = [&](int i) -> float4 {
+  auto load_in = [&](int i, int) -> float4 {
     return (!on || i >= n_in) ? fast::v4(0.f, 0.f, 0.f, 0.f) : in[i * X2];
   };
   auto store_spec = [&](int i, float4 v) {
@@ -194,7 +257,7 @@ __global__ void __launch_bounds__(FastCfg<P>::COL_THREADS, FastCfg<P>::COL_MINB)
   };
   fast::fft_line_pair<P, false, true, false>(t, fsm4 + p, PAIRS, a.tw + P::N, load_in, store_spec);
   __syncthreads();  // spectrum complete; the exchange buffer is free again
-  auto load_spec = [&](int i) -> float4 { return spec[i * PAIRS + p]; };
+  auto load_spec = [&](int i, int) -> float4 { return spec[i * PAIRS + p]; };
   auto store_out = [&](int i, float4 v) {
     if (on && i < n_out) out[i * X2] = fast::vscale(v, scale);
   };
@@ -236,7 +299,7 @@ __global__ void __launch_bounds__(FastCfg<P>::SENSE_THREADS, FastCfg<P>::SENSE_M
       if (!(n_out & 1) && !(reinterpret_cast<uintptr_t>(sm) & 15)) prefetch_l2_bulk(sm, (unsigned)n_out * 8u);
     }
   }
-  auto loadg = [&](int i) -> float4 {
+  auto loadg = [&](int i, int) -> float4 {
     float4 v = fast::v4(0.f, 0.f, 0.f, 0.f);
     if (i < n_in) {
       if (onA) { const float2 x = inA[i]; v.x = x.x; v.y = x.y; }
@@ -341,8 +404,29 @@ template <class P, bool INV, bool HALF> int launch_cols_fast_h(ColArgs &a, cudaS
   B2N_LAUNCH_OK("k_fft_cols_fast");
   return 0;
 }
+// B2N_OPT_FFT_STREAM: mask of the passes that run as streamed persistent kernels (1 forward columns, 2 inverse columns)
+extern int g_fft_stream;
+template <class P, bool INV, bool HALF, int PAIRS_> int launch_cols_stream_h(ColArgs &a, cudaStream_t st) {
+  using S = StreamCfg<P, INV, HALF, PAIRS_>;
+  auto kern = k_fft_cols_stream<P, INV, HALF, PAIRS_>;
+  B2N_SMEM_OPT_IN(kern, S::SMEM);
+  const int64_t tiles_x = ceil_div(a.X, 2 * S::PAIRS), tiles = tiles_x * a.A;
+  const int resident = resident_ctas(kern, S::NT, S::SMEM);
+  a.prefetch = 0;
+  B2N_CUDA_OK(launch_pdl(kern, dim3((unsigned)(tiles < resident ? tiles : resident)), dim3(S::NT), S::SMEM, st, a,
+                         (uint32_t)tiles_x, (uint32_t)tiles));
+  B2N_LAUNCH_OK("k_fft_cols_stream");
+  return 0;
+}
 template <class P, bool INV> int launch_cols_fast(ColArgs &a, cudaStream_t st) {
   const bool half = 2 * (INV ? a.n_out : a.n_in) <= P::N;
+  // streamed variant: no fused multiply, 32-bit tile arithmetic, operand slots + exchange buffer within one CTA's share
+  if ((g_fft_stream & (INV ? 2 : 1)) && !a.mul && half && !(a.X & 1) && ceil_div(a.X, 2 * FastCfg<P>::PAIRS) * a.A < ((int64_t)1 << 31) &&
+      a.A * a.n_in * a.X < ((int64_t)1 << 31) && StreamCfg<P, INV, true>::SMEM <= (size_t)113 * 1024) {
+    constexpr int PF = FastCfg<P>::PAIRS, PH = PF >= 2 ? PF / 2 : 1;
+    if (g_fft_stream & (INV ? 32 : 16)) return launch_cols_stream_h<P, INV, true, PH>(a, st);  // A/B: narrower tiles
+    return launch_cols_stream_h<P, INV, true, PF>(a, st);
+  }
   return half ? launch_cols_fast_h<P, INV, true>(a, st) : launch_cols_fast_h<P, INV, false>(a, st);
 }
 

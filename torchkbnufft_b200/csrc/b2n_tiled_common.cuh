@@ -38,6 +38,11 @@ B2N_D void cp_async8(void *dst, const void *src, bool valid) {
 B2N_D void cp_async16(void *dst, const void *src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_u32(dst)), "l"(src) : "memory");
 }
+// 16-byte copy, zero-filled when !valid (src must still be a mapped address)
+B2N_D void cp_async16z(void *dst, const void *src, bool valid) {
+  const int src_size = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(smem_u32(dst)), "l"(src), "r"(src_size) : "memory");
+}
 B2N_D void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 B2N_D void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
 
