@@ -2,18 +2,19 @@
 //
 // The one collective on the NUFFT path is the sum over coils of the adjoint (reference coupling point:
 // torchkbnufft/modules/kbnufft.py:404-405) when the coils are split over GPUs.  The message is small (B*N complex
-// values, 0.8 MB at BASELINE config 2), so a ring / tree all-reduce is bound by its launch and hop latencies
+// values, 0.8 MB at BASELINE config 2), so the all-reduce is bound by launch and link latencies, not by bandwidth
 // (21-35 us through NCCL, profiles/r02_bench_*gpu.log).  Here every rank owns a *window* of device memory that all the
-// other ranks of the node map through CUDA IPC; ONE kernel per rank
+// other ranks of the node map through CUDA IPC, and ONE kernel per rank
 //   1. pushes its partial image into slot [rank] of every peer's window (plain 16-byte stores over NVLink / NVSwitch),
-//   2. publishes one flag per (peer, chunk) with release semantics at system scope,
-//   3. waits for the flags of the same chunk from every peer (acquire, system scope) and
-//   4. adds the slots in RANK ORDER, so that every rank computes bit-identical sums.
-// Chunks (4096 floats, one CTA each) are independent: a CTA starts adding as soon as its own chunk has arrived from
-// everyone, the rest of the image is still in flight.  Data slots are double-buffered on the parity of a call counter
-// that lives in the window (device side: the kernel is CUDA-graph capturable and needs no host state); a rank can be
-// at most one call ahead of its peers because it needs their flags of call k to finish call k, and those are only
-// written after the peer has finished reading call k-1.
+//   2. polls its own window until the peers' values have replaced the fill pattern, and
+//   3. adds the slots in RANK ORDER, so that every rank computes bit-identical sums.
+// There are no flags and no fences: the windows are pre-filled with a value that never travels (negative zero, sent
+// as +0), and every 4-byte element announces itself by differing from it (Lamport-style; a first version with
+// per-chunk flags behind a system-scope release paid an extra link round trip: 20 vs 13 us at 2 GPUs,
+// profiles/r02_peer_allreduce_2gpu.log, r02_peer_allreduce_flags_2gpu.log).  Three generations of slots rotate on a call counter that lives in the window
+// (device side: the kernel is CUDA-graph capturable and needs no host state): a call reads generation e % 3, peers
+// that are one call ahead already write (e + 1) % 3, and (e + 2) % 3 -- last used by call e - 1, which every rank has
+// finished reading, or this call could not have been reached -- is reset to the fill pattern for call e + 2.
 #include <string.h>
 
 #include <type_traits>
@@ -23,113 +24,156 @@
 namespace b2n {
 
 constexpr int kPeerThreads = 256;
-constexpr int kPeerChunk = 4096;   // floats per CTA: 256 threads x 4 x float4
-constexpr int kPeerHeader = 128;   // bytes: {calls completed, CTAs of the running call that are done}
+constexpr int kPeerChunk = 4096;          // floats per CTA and round: 256 threads x 4 x float4
+constexpr int kPeerHeader = 256;          // bytes: {calls completed, CTAs of the running call that are done, -, -, floats of generation 0 / 1 / 2}
+constexpr uint32_t kPeerFill = 0x80000000u;  // -0.0f
 
 struct PeerLayout {
-  int64_t n_chunks_max, slot_floats;
-  size_t flags_off, data_off, bytes;
+  int64_t slot_floats;
+  size_t data_off, bytes;
 };
 
 static PeerLayout peer_layout(int world, int64_t max_floats) {
   PeerLayout l;
-  l.n_chunks_max = ceil_div(max_floats, kPeerChunk);
-  l.slot_floats = l.n_chunks_max * kPeerChunk;
-  l.flags_off = kPeerHeader;
-  l.data_off = align_up(l.flags_off + sizeof(uint32_t) * (size_t)world * l.n_chunks_max, 256);
-  l.bytes = l.data_off + sizeof(float) * 2 * (size_t)world * l.slot_floats;
+  l.slot_floats = ceil_div(max_floats, kPeerChunk) * kPeerChunk;
+  l.data_off = kPeerHeader;
+  l.bytes = l.data_off + sizeof(float) * 3 * (size_t)world * l.slot_floats;
   return l;
 }
 
 struct PeerArgs {
   int rank, world;
-  int64_t n_chunks_max, slot_floats;
-  size_t flags_off, data_off;
+  int64_t slot_floats;
+  size_t data_off;
   unsigned char *window[B2N_PEER_MAX_RANKS];
 };
 
-B2N_D uint32_t ld_acquire_sys(const uint32_t *p) {
-  uint32_t v;
-  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+__global__ void k_peer_fill(uint32_t *p, size_t n, uint32_t v) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
+}
+
+B2N_D float not_fill(float x) { return __float_as_uint(x) == kPeerFill ? 0.f : x; }
+B2N_D float4 ld_volatile4(const float *p) {
+  float4 v;
+  asm volatile("ld.volatile.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
   return v;
 }
-B2N_D void st_release_sys(uint32_t *p, uint32_t v) {
-  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+B2N_D float ld_volatile1(const float *p) {
+  float v;
+  asm volatile("ld.volatile.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+  return v;
+}
+B2N_D bool arrived(float4 v) {
+  return __float_as_uint(v.x) != kPeerFill && __float_as_uint(v.y) != kPeerFill && __float_as_uint(v.z) != kPeerFill &&
+         __float_as_uint(v.w) != kPeerFill;
+}
+B2N_D bool arrived(float v) { return __float_as_uint(v) != kPeerFill; }
+// a peer that never issues the matching call is a usage error: trap after ~20 s instead of hanging the device
+B2N_D void spin_guard(unsigned &spins, unsigned long long &t0) {
+  if ((++spins & 0xFFFFu) != 0) return;
+  unsigned long long now;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+  if (!t0) t0 = now;
+  else if (now - t0 > 20000000000ull) __trap();
 }
 
 // VEC = 4: n a multiple of 4 and 16-byte aligned pointers; VEC = 1: anything
 template <int VEC>
 __global__ void __launch_bounds__(kPeerThreads) k_peer_allreduce_sum(PeerArgs a, const float *__restrict__ in,
                                                                      float *__restrict__ out, int64_t n) {
-  constexpr int PER = kPeerChunk / (kPeerThreads * VEC);  // values (float or float4) per thread
+  constexpr int PER = kPeerChunk / (kPeerThreads * VEC);  // values (float or float4) per thread and chunk
   using V = typename std::conditional<VEC == 4, float4, float>::type;
-  __shared__ uint32_t s_epoch;
+  __shared__ uint32_t s_epoch, s_prev;
   griddep_wait();  // the partial image comes from the preceding kernel; the call counter from the preceding call
   unsigned char *mine = a.window[a.rank];
   uint32_t *hdr = reinterpret_cast<uint32_t *>(mine);
-  if (threadIdx.x == 0) s_epoch = *reinterpret_cast<volatile uint32_t *>(hdr) + 1u;
-  __syncthreads();
-  const uint32_t epoch = s_epoch;
   const int64_t n_chunks = (n + kPeerChunk - 1) / kPeerChunk;
-  // chunks blockIdx.x, blockIdx.x + gridDim.x, ... in the same order on every rank; the grid is small enough to be
-  // resident as a whole, so a CTA waiting for a peer never keeps that peer's partner CTA off its GPU
-  for (int64_t chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
-  const int64_t lo = chunk * kPeerChunk;
-  const size_t slot = ((size_t)(epoch & 1u) * a.world + a.rank) * a.slot_floats + lo;  // where this rank's chunk goes
+  const bool single = n_chunks <= (int64_t)gridDim.x;  // one chunk per CTA: the values stay in registers
   V v[PER];
   bool on[PER];
+  auto load = [&](int64_t lo) {
 #pragma unroll
-  for (int k = 0; k < PER; ++k) {
-    const int64_t i = lo + ((int64_t)k * kPeerThreads + threadIdx.x) * VEC;
-    on[k] = i < n;
-    if (on[k]) v[k] = *reinterpret_cast<const V *>(in + i);
-  }
-  for (int p = 0; p < a.world; ++p) {
-    if (p == a.rank) continue;
-    float *dst = reinterpret_cast<float *>(a.window[p] + a.data_off) + slot;
-#pragma unroll
-    for (int k = 0; k < PER; ++k)
-      if (on[k]) *reinterpret_cast<V *>(dst + ((int64_t)k * kPeerThreads + threadIdx.x) * VEC) = v[k];
-  }
-  __threadfence_system();
-  __syncthreads();  // every thread's stores are ordered before the flags
-  if ((int)threadIdx.x < a.world && (int)threadIdx.x != a.rank)
-    st_release_sys(reinterpret_cast<uint32_t *>(a.window[threadIdx.x] + a.flags_off) + (size_t)a.rank * a.n_chunks_max + chunk,
-                   epoch);
-  if ((int)threadIdx.x < a.world && (int)threadIdx.x != a.rank) {
-    const uint32_t *flag = reinterpret_cast<const uint32_t *>(mine + a.flags_off) + (size_t)threadIdx.x * a.n_chunks_max + chunk;
-    // a peer that never issues the matching call is a usage error: trap after ~20 s instead of hanging the device
-    unsigned long long t0 = 0;
-    for (unsigned spins = 0; (int32_t)(ld_acquire_sys(flag) - epoch) < 0; ++spins) {
-      __nanosleep(20);
-      if ((spins & 0xFFFFu) == 0xFFFFu) {
-        unsigned long long now;
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
-        if (!t0) t0 = now;
-        else if (now - t0 > 20000000000ull) __trap();
+    for (int k = 0; k < PER; ++k) {
+      const int64_t i = lo + ((int64_t)k * kPeerThreads + threadIdx.x) * VEC;
+      on[k] = i < n;
+      if (on[k]) {
+        v[k] = *reinterpret_cast<const V *>(in + i);
+        if constexpr (VEC == 4) v[k] = make_float4(not_fill(v[k].x), not_fill(v[k].y), not_fill(v[k].z), not_fill(v[k].w));
+        else v[k] = not_fill(v[k]);
       }
     }
+  };
+  load((int64_t)blockIdx.x * kPeerChunk);  // in flight while the call counter is read
+  if (threadIdx.x == 0) {
+    const uint32_t e = *reinterpret_cast<volatile uint32_t *>(hdr) + 1u;
+    s_epoch = e;
+    s_prev = *reinterpret_cast<volatile uint32_t *>(hdr + 4 + (e + 2u) % 3u);
   }
   __syncthreads();
-  const float *slots = reinterpret_cast<const float *>(mine + a.data_off) + (size_t)(epoch & 1u) * a.world * a.slot_floats + lo;
+  const uint32_t epoch = s_epoch, gen = epoch % 3u, gclr = (epoch + 2u) % 3u;
+  const size_t gen_off = (size_t)gen * a.world * a.slot_floats;
+  // 1. push: chunks blockIdx.x, blockIdx.x + gridDim.x, ...
+  for (int64_t chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
+    const int64_t lo = chunk * kPeerChunk;
+    if (chunk != (int64_t)blockIdx.x) load(lo);
+    for (int q = 1; q < a.world; ++q) {
+      const int p = (a.rank + q) % a.world;  // start with the next rank: the peers' ingress is spread evenly
+      float *dst = reinterpret_cast<float *>(a.window[p] + a.data_off) + gen_off + (size_t)a.rank * a.slot_floats + lo;
 #pragma unroll
-  for (int k = 0; k < PER; ++k) {
-    if (!on[k]) continue;
-    const int64_t off = ((int64_t)k * kPeerThreads + threadIdx.x) * VEC;
-    V acc;
-    for (int r = 0; r < a.world; ++r) {  // rank order on every rank: identical sums everywhere
-      const V x = r == a.rank ? v[k] : __ldcg(reinterpret_cast<const V *>(slots + (size_t)r * a.slot_floats + off));
-      if (r == 0) acc = x;
-      else if constexpr (VEC == 4) acc = make_float4(acc.x + x.x, acc.y + x.y, acc.z + x.z, acc.w + x.w);
-      else acc = acc + x;
+      for (int k = 0; k < PER; ++k)
+        if (on[k]) *reinterpret_cast<V *>(dst + ((int64_t)k * kPeerThreads + threadIdx.x) * VEC) = v[k];
     }
-    *reinterpret_cast<V *>(out + lo + off) = acc;
   }
+  // 2. reset the generation call e - 1 used (every rank is done with it) while the peers' values are in flight
+  {
+    const size_t prev4 = ((size_t)s_prev + 3) / 4;
+    const float4 fill = make_float4(__uint_as_float(kPeerFill), __uint_as_float(kPeerFill), __uint_as_float(kPeerFill),
+                                    __uint_as_float(kPeerFill));
+    for (int r = 0; r < a.world; ++r) {
+      if (r == a.rank) continue;
+      float4 *dst = reinterpret_cast<float4 *>(reinterpret_cast<float *>(mine + a.data_off) +
+                                               ((size_t)gclr * a.world + r) * a.slot_floats);
+      for (size_t i = (size_t)blockIdx.x * kPeerThreads + threadIdx.x; i < prev4; i += (size_t)gridDim.x * kPeerThreads)
+        dst[i] = fill;
+    }
+  }
+  // 3. wait for the peers' values element by element and add them in rank order (identical sums on every rank)
+  const float *slots = reinterpret_cast<const float *>(mine + a.data_off) + gen_off;
+  unsigned spins = 0;
+  unsigned long long t0 = 0;
+  for (int64_t chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
+    const int64_t lo = chunk * kPeerChunk;
+    if (!single) load(lo);
+#pragma unroll
+    for (int k = 0; k < PER; ++k) {
+      if (!on[k]) continue;
+      const int64_t i = lo + ((int64_t)k * kPeerThreads + threadIdx.x) * VEC;
+      V acc;
+      for (int r = 0; r < a.world; ++r) {
+        V x;
+        if (r == a.rank) {
+          x = v[k];
+        } else {
+          const float *src = slots + (size_t)r * a.slot_floats + i;
+          if constexpr (VEC == 4) {
+            for (x = ld_volatile4(src); !arrived(x); x = ld_volatile4(src)) spin_guard(spins, t0);
+          } else {
+            for (x = ld_volatile1(src); !arrived(x); x = ld_volatile1(src)) spin_guard(spins, t0);
+          }
+        }
+        if (r == 0) acc = x;
+        else if constexpr (VEC == 4) acc = make_float4(acc.x + x.x, acc.y + x.y, acc.z + x.z, acc.w + x.w);
+        else acc = acc + x;
+      }
+      *reinterpret_cast<V *>(out + i) = acc;
+    }
   }
   __syncthreads();
-  if (threadIdx.x == 0) {  // the last CTA of the call advances the call counter
+  if (threadIdx.x == 0) {  // the last CTA of the call advances the call counter and records the size of its generation
+    __threadfence();
     if (atomicAdd(hdr + 1, 1u) == gridDim.x - 1) {
       hdr[1] = 0;
+      hdr[4 + gen] = (uint32_t)n;
       __threadfence();
       *reinterpret_cast<volatile uint32_t *>(hdr) = epoch;
     }
@@ -141,8 +185,9 @@ __global__ void __launch_bounds__(kPeerThreads) k_peer_allreduce_sum(PeerArgs a,
 using namespace b2n;
 
 extern "C" int b2n_peer_window_bytes(int world, int64_t max_floats, size_t *bytes) {
-  if (!bytes || world < 1 || world > B2N_PEER_MAX_RANKS || max_floats < 1)
-    return fail_arg(B2N_E_ARG, "peer window: world %d (1..%d), max_floats %lld", world, B2N_PEER_MAX_RANKS, (long long)max_floats);
+  if (!bytes || world < 1 || world > B2N_PEER_MAX_RANKS || max_floats < 1 || max_floats >= ((int64_t)1 << 31))
+    return fail_arg(B2N_E_ARG, "peer window: world %d (1..%d), max_floats %lld (1..2^31-1)", world, B2N_PEER_MAX_RANKS,
+                    (long long)max_floats);
   *bytes = peer_layout(world, max_floats).bytes;
   return 0;
 }
@@ -152,7 +197,12 @@ extern "C" int b2n_peer_window_create(size_t bytes, void **window_dev, void *han
   static_assert(sizeof(cudaIpcMemHandle_t) == B2N_PEER_HANDLE_BYTES, "handle size");
   void *p = nullptr;
   B2N_CUDA_OK(cudaMalloc(&p, bytes));
-  int rc = check_cuda(cudaMemset(p, 0, bytes), "cudaMemset(peer window)");
+  int rc = check_cuda(cudaMemset(p, 0, kPeerHeader), "cudaMemset(peer window)");
+  if (rc == 0) {  // every slot starts out as "nothing has arrived"
+    k_peer_fill<<<592, 256>>>(reinterpret_cast<uint32_t *>(static_cast<unsigned char *>(p) + kPeerHeader),
+                              (bytes - kPeerHeader) / sizeof(uint32_t), kPeerFill);
+    rc = check_cuda(cudaGetLastError(), "k_peer_fill");
+  }
   if (rc == 0) rc = check_cuda(cudaDeviceSynchronize(), "cudaDeviceSynchronize(peer window)");
   cudaIpcMemHandle_t h;
   if (rc == 0) rc = check_cuda(cudaIpcGetMemHandle(&h, p), "cudaIpcGetMemHandle");
@@ -196,9 +246,7 @@ extern "C" int b2n_peer_allreduce_sum(const b2n_peer_comm *comm, const void *in_
   PeerArgs a;
   a.rank = comm->rank;
   a.world = comm->world;
-  a.n_chunks_max = l.n_chunks_max;
   a.slot_floats = l.slot_floats;
-  a.flags_off = l.flags_off;
   a.data_off = l.data_off;
   for (int r = 0; r < B2N_PEER_MAX_RANKS; ++r) {
     a.window[r] = r < comm->world ? static_cast<unsigned char *>(comm->window[r]) : nullptr;
