@@ -12,7 +12,7 @@ import torch.distributed as dist
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torchkbnufft_b200 as tkbn  # noqa: E402
-from torchkbnufft_b200 import parallel, workloads  # noqa: E402
+from torchkbnufft_b200 import _lib, parallel, workloads  # noqa: E402
 
 
 def rel(a, b):
@@ -55,6 +55,18 @@ def main():
         assert err_p < 1e-5, f"coil-sharded adjoint through the peer all-reduce: rel-L2 {err_p} (call {rep})"
         dist.all_gather(gathered, im_p)
         assert all(torch.equal(g, gathered[0]) for g in gathered), "ranks disagree after the peer all-reduce"
+    # library-owned graph replay: the all-reduce kernel is the last launch of the adjoint's captured graph
+    tkbn.set_graph_mode(True)
+    y_loc = y[:, lo:hi].contiguous()
+    launches = _lib.load().b2n_launch_count
+    for rep in range(8):
+        y_loc.copy_(y[:, lo:hi] * (1.0 + rep))
+        before = launches()
+        im_g = parallel.coil_sharded_adjoint(na, y_loc, om, s_loc, reducer=peer).clone()
+        eager_launches = launches() - before
+        assert rel(im_g, want_im * (1.0 + rep)) < 1e-5, f"graph-mode coil-sharded adjoint, call {rep}"
+    assert eager_launches == 0, f"{eager_launches} eager launches in a replayed coil-sharded adjoint"
+    tkbn.set_graph_mode(False)
     gen = torch.Generator(device="cpu").manual_seed(100 + rank)
     for n in (1, 5, 4096, 4097, 12345, 3 * want_im.numel() + 1):
         mine = torch.randn(n, generator=gen).to(dev)

@@ -84,6 +84,29 @@ def in_replay_scope() -> bool:
     return getattr(_SCOPE, "depth", 0) > 0
 
 
+class adjoint_epilogue:
+    """Context manager: ``fn(image) -> image`` runs on the coil-combined result of every SENSE adjoint that autograd
+    does not record inside the block, as the last step OF the operator -- so that it is captured into the operator's
+    graph and replayed with it.  ``parallel.coil_sharded_adjoint`` puts the peer-memory all-reduce of the partial
+    coil sums here: one ``cudaGraphLaunch`` per adjoint, collective included.  ``key`` distinguishes epilogues in the
+    graph cache; ``applied`` tells the caller whether the operator ran it (it does not on the autograd path)."""
+
+    def __init__(self, fn: Callable[[Tensor], Tensor], key):
+        self.fn, self.key, self.applied = fn, key, False
+
+    def __enter__(self):
+        self._prev = getattr(_SCOPE, "epilogue", None)
+        _SCOPE.epilogue = self
+        return self
+
+    def __exit__(self, *exc):
+        _SCOPE.epilogue = self._prev
+
+
+def current_epilogue() -> Optional[adjoint_epilogue]:
+    return getattr(_SCOPE, "epilogue", None)
+
+
 def _tensor_key(t: Optional[Tensor]) -> tuple:
     if t is None:
         return ()

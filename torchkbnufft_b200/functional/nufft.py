@@ -68,22 +68,31 @@ def sense_nufft_adjoint(data: Tensor, smaps: Optional[Tensor], scaling_coef: Ten
     grid_sizes = _ints(grid_size)
     scale = _fft.ortho_scale(grid_sizes, normalized)
     fused = _fft.fused_fft_available(data.dtype, grid_sizes, data.shape[0] * data.shape[1])
+    epilogue = _graphs.current_epilogue()  # e.g. the all-reduce of a coil-sharded adjoint (parallel.py)
     if (_graphs.get_graph_mode() and not _graphs.in_replay_scope() and not _needs_grad(data)
             and not (smaps is not None and smaps.requires_grad)):
         with _graphs.replay_scope():
-            return _graphs.replay_or_run(
+            out = _graphs.replay_or_run(
                 "nufft_adjoint", (data, smaps), (scaling_coef, n_shift, numpoints, table_oversamp) + tuple(tables), omega,
-                (grid_sizes, _ints(im_size), scale, _interp.get_adjoint_mode()),
+                (grid_sizes, _ints(im_size), scale, _interp.get_adjoint_mode(), epilogue.key if epilogue else None),
                 lambda: sense_nufft_adjoint(data, smaps, scaling_coef, im_size, grid_size, omega, tables, n_shift,
                                             numpoints, table_oversamp, offsets, norm),
                 lambda: _interp.lookup_plan(omega, data.shape[0], tables, n_shift, numpoints, table_oversamp, grid_sizes,
                                             data.device))
+        if epilogue is not None:
+            epilogue.applied = True  # by the eager body or by the replayed graph
+        return out
     if not _needs_grad(data) and not (smaps is not None and smaps.requires_grad):
         grid = _interp.table_interp_adjoint(data, omega, tables, n_shift, numpoints, table_oversamp, offsets, grid_size)
         if fused:
-            return _fft.fused_fft_adjoint(grid, _ints(im_size), smaps, scaling_coef, scale)
-        grid = _fft.fft_grid(grid, len(grid_sizes), inverse=True)
-        return _fft.crop_apod_coilsum(grid, _ints(im_size), smaps, scaling_coef, scale)
+            out = _fft.fused_fft_adjoint(grid, _ints(im_size), smaps, scaling_coef, scale)
+        else:
+            grid = _fft.fft_grid(grid, len(grid_sizes), inverse=True)
+            out = _fft.crop_apod_coilsum(grid, _ints(im_size), smaps, scaling_coef, scale)
+        if epilogue is not None:
+            out = epilogue.fn(out)
+            epilogue.applied = True
+        return out
     grid = KbTableInterpAdjoint.apply(data, omega, tables, n_shift, numpoints, table_oversamp, offsets, grid_size)
     finish = FusedFftAdjoint if fused else CropApodCoilsum
     if not fused:

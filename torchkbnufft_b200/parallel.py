@@ -20,6 +20,7 @@ The reference has no distributed code at all; this module is new surface.
 """
 from __future__ import annotations
 
+import math
 from typing import Optional, Tuple
 
 import torch
@@ -119,6 +120,18 @@ class PeerAllReduce:
             dist.barrier(group=group)  # nobody pushes into a window that is not mapped and zeroed yet
         self._group = group
 
+    # one-shot pushes move (world - 1) copies of the message per rank: past this many bytes per rank a ring / tree
+    # all-reduce (NCCL) wins (profiles/r02_peer_allreduce_8gpu.log: 4 MB at 8 GPUs is already slower than NCCL)
+    ONE_SHOT_BYTES = 8 << 20
+
+    def takes(self, n_values: int, dtype: torch.dtype) -> bool:
+        """Whether a tensor of ``n_values`` elements of ``dtype`` should go through this reducer (it fits the window,
+        is float32 / complex64 and small enough for the one-shot exchange to beat a bandwidth-optimal all-reduce)."""
+        if self._own is None or dtype not in (torch.complex64, torch.float32):
+            return False
+        n = int(n_values) * (2 if dtype.is_complex else 1)
+        return 0 < n <= self.max_floats and 4 * n * max(self.world - 1, 1) <= self.ONE_SHOT_BYTES
+
     def __call__(self, x: Tensor) -> Tensor:
         if x.device != self.device or x.dtype not in (torch.complex64, torch.float32) or not x.is_contiguous():
             raise ValueError("PeerAllReduce needs a contiguous float32 / complex64 tensor on its own device")
@@ -164,10 +177,20 @@ def coil_sharded_adjoint(adj_ob, data_local: Tensor, omega: Tensor, smaps_local:
     if data_local.shape[1] == 0:  # more ranks than coils: contribute zeros
         shape = (data_local.shape[0], 1) + tuple(smaps_local.shape[2:])
         partial = torch.zeros(shape, dtype=data_local.dtype, device=data_local.device)
+    elif reducer is not None and reducer.takes(data_local.shape[0] * math.prod(smaps_local.shape[2:]), data_local.dtype):
+        # the all-reduce kernel is the last launch OF the adjoint: in graph mode it is replayed with it
+        from ._nufft import graphs as _graphs
+
+        with _graphs.adjoint_epilogue(reducer, ("peer_allreduce", id(reducer))) as epilogue:
+            partial = adj_ob(data_local, omega, smaps=smaps_local, norm=norm)
+        if epilogue.applied:
+            return partial
     else:
         partial = adj_ob(data_local, omega, smaps=smaps_local, norm=norm)
     partial = partial.contiguous()
-    return reducer(partial) if reducer is not None else all_reduce_complex_(partial, group)
+    if reducer is not None and reducer.takes(partial.numel(), partial.dtype):
+        return reducer(partial)
+    return all_reduce_complex_(partial, group)
 
 
 def batch_sharded_pair(nufft_ob, adj_ob, image_local: Tensor, omega: Tensor, smaps: Tensor,
