@@ -808,12 +808,19 @@ def main():
                     same = [torch.empty_like(got_p) for _ in range(world)]
                     dist.all_gather(same, got_p)
                     ms_p = timed_steps(step_peer, n_part)
+                    parallel.fuse_allreduce = False  # A/B: the all-reduce as one more kernel behind the last pass
+                    try:
+                        ms_p_sep = timed_steps(step_peer, n_part)
+                    finally:
+                        parallel.fuse_allreduce = True
                     ms_par = timed_steps(lambda: peer(buf), n_part)
                     peer_info = {
                         "value": units2 / (ms_p * 1e-3), "unit": UNIT, "ms_per_step": ms_p,
-                        "collective": "b2n_peer_allreduce_sum: one kernel per rank pushes the partial image into every "
-                                      "peer's CUDA-IPC window over NVLink and adds the arrivals in rank order; last "
-                                      "launch of the adjoint (replayed with its graph); inside the timed region",
+                        "collective": "b2n_fft_adjoint_fused_allreduce: the adjoint's last inverse FFT pass pushes "
+                                      "every finished image row into the peers' CUDA-IPC windows over NVLink and adds "
+                                      "the arrivals in rank order (compute and collective in one kernel, replayed with "
+                                      "the adjoint's graph); inside the timed region",
+                        "ms_per_step_allreduce_as_separate_kernel": ms_p_sep,
                         "allreduce_ms_alone": ms_par, "rel_l2_vs_unsharded": err_p,
                         "bit_identical_on_all_ranks": bool(all(torch.equal(g, same[0]) for g in same))}
                     peer.close()

@@ -351,6 +351,18 @@ B2N_API int b2n_peer_window_destroy(void *window_dev);                    /* fre
  * `stream`, CUDA-graph capturable (the call counter lives in the window). */
 B2N_API int b2n_peer_allreduce_sum(const b2n_peer_comm *comm, const void *in_dev, void *out_dev, int64_t n_floats,
                                    void *stream);
+/* b2n_fft_adjoint_fused followed by the sum all-reduce of image_dev over the ranks of `comm` (every rank calls it
+ * with its own coils; all end up with the full coil sum).  Where the last pass is the row pass with the fused coil
+ * combination and its grid is resident as a whole, each finished image row goes straight from that kernel into the
+ * peers' windows and comes back summed -- compute and collective in one launch; otherwise the stand-alone all-reduce
+ * kernel runs behind the last pass.  Same arguments as b2n_fft_adjoint_fused plus `comm`.  reference coupling point:
+ * the coil sum of the SENSE adjoint (modules/kbnufft.py:404-405) with the coils split over GPUs. */
+B2N_API int b2n_fft_adjoint_fused_allreduce(int ndim, const int64_t *im_size, const int64_t *grid_size,
+                                            int64_t n_batch, int64_t n_coils, const void *grid_dev,
+                                            const void *kernel_dev, int64_t kernel_batch, const void *smaps_dev,
+                                            int64_t smaps_batch, const void *scaling_dev, double scale,
+                                            const void *const *twiddle_dev, void *image_dev, void *work_dev,
+                                            const b2n_peer_comm *comm, void *stream);
 
 #ifdef __cplusplus
 }

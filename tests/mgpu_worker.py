@@ -67,6 +67,13 @@ def main():
         assert rel(im_g, want_im * (1.0 + rep)) < 1e-5, f"graph-mode coil-sharded adjoint, call {rep}"
     assert eager_launches == 0, f"{eager_launches} eager launches in a replayed coil-sharded adjoint"
     tkbn.set_graph_mode(False)
+    # Toeplitz normal operator with the coils sharded: NCCL and peer all-reduce against the unsharded apply
+    toep = tkbn.ToepNufft()
+    kern = tkbn.calc_toeplitz_kernel(om, wl.im_size)
+    want_t = toep(x, kern, smaps=s)
+    for red in (None, peer):
+        got_t = parallel.coil_sharded_toeplitz(toep, x, kern, s_loc, reducer=red)
+        assert rel(got_t, want_t) < 1e-5, f"coil-sharded Toeplitz ({'peer' if red else 'NCCL'}): rel-L2 {rel(got_t, want_t)}"
     gen = torch.Generator(device="cpu").manual_seed(100 + rank)
     for n in (1, 5, 4096, 4097, 12345, 3 * want_im.numel() + 1):
         mine = torch.randn(n, generator=gen).to(dev)

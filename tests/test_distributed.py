@@ -61,6 +61,12 @@ def _worker(rank, world, port, out_dir):
         ok_f = torch.allclose(f_local, full_f[:, lo:hi])
         a_all = parallel.coil_sharded_adjoint(na, kdata_l, T("omega"), smaps_l, norm="ortho")
         ok_a = torch.allclose(a_all, full_a)
+        # Toeplitz normal operator with sharded coils: same all-reduce after the local coil sum
+        toep = tkbn.ToepNufft()
+        kern = tkbn.calc_toeplitz_kernel(T("omega"), case["im_size"], norm="ortho")
+        full_t = toep(T("image"), kern, smaps=T("smaps"), norm="ortho")
+        t_all = parallel.coil_sharded_toeplitz(toep, T("image"), kern, smaps_l, norm="ortho")
+        ok_a = ok_a and torch.allclose(t_all, full_t)
         # batch sharding: no communication
         case_b = CASES["d2"]  # B=2
         inp_b = case_inputs(case_b, np.complex128)

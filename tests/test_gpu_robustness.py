@@ -317,3 +317,60 @@ def test_peer_allreduce_protocol_on_one_device(world):
         torch.cuda.synchronize()
         for w in windows:
             lib.b2n_peer_window_destroy(w)
+
+
+@pytest.mark.parametrize("N, K, C, world", [((32, 320), (64, 640), 4, 2), ((24, 320), (64, 640), 16, 3),
+                                            ((32, 320), (64, 640), 2, 2), ((40, 48), (96, 96), 3, 2)])
+def test_adjoint_fft_with_the_allreduce_inside_its_last_pass(N, K, C, world):
+    """b2n_fft_adjoint_fused_allreduce with every "rank" on ONE device (one stream per rank): the last inverse pass
+    pushes its finished rows into the other ranks' windows and adds what arrives (k_fft_rows_sense, one and several
+    coil groups per row), or the stand-alone kernel runs behind the unfused route (few coils, short rows).  All ranks
+    must hold the rank-ordered sum of the separately computed partial images, over repeated calls."""
+    import ctypes
+
+    torch.manual_seed(11)
+    lib = _lib.load()
+    dt = torch.complex64
+    n_img = 2 * N[0] * N[1]
+    nbytes = ctypes.c_size_t(0)
+    assert lib.b2n_peer_window_bytes(world, 2 * n_img, ctypes.byref(nbytes)) == 0
+    windows, comms = [], []
+    for r in range(world):
+        w, h = ctypes.c_void_p(None), ctypes.create_string_buffer(_lib.PEER_HANDLE_BYTES)
+        _lib.check(lib.b2n_peer_window_create(nbytes.value, ctypes.byref(w), h), "b2n_peer_window_create")
+        windows.append(w)
+    for r in range(world):
+        c = _lib.PeerComm()
+        c.rank, c.world, c.max_floats = r, world, 2 * n_img
+        for q in range(world):
+            c.window[q] = windows[q].value
+        comms.append(c)
+    streams = [torch.cuda.Stream() for _ in range(world)]
+    scal = torch.randn(N, dtype=dt, device=DEV)
+    try:
+        for rep in range(4):
+            grids = [torch.randn((1, C) + K, dtype=dt, device=DEV) for _ in range(world)]
+            smaps = [torch.randn((1, C) + N, dtype=dt, device=DEV) for _ in range(world)]
+            parts = [eng_fft.fused_fft_adjoint(g, N, s, scal, 0.5) for g, s in zip(grids, smaps)]
+            want = parts[0].clone()
+            for p in parts[1:]:
+                want += p
+            torch.cuda.synchronize()
+            before = lib.b2n_launch_count()
+            outs = []
+            for r in range(world):
+                with torch.cuda.stream(streams[r]):
+                    outs.append(eng_fft.fused_fft_adjoint(grids[r], N, smaps[r], scal, 0.5, peer_comm=comms[r]))
+            torch.cuda.synchronize()
+            launches = (lib.b2n_launch_count() - before) // world
+            for r in range(world):
+                assert torch.equal(outs[r], want), (rep, r, float((outs[r] - want).abs().max()))
+        # the long-row shapes with enough coils carry the exchange in the row pass itself: two launches per call
+        if K[1] == 640 and C >= 3:
+            assert launches == 2
+        else:
+            assert launches >= 3
+    finally:
+        torch.cuda.synchronize()
+        for w in windows:
+            lib.b2n_peer_window_destroy(w)

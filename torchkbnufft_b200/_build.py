@@ -19,7 +19,7 @@ LIB_PATH = os.path.join(CSRC, LIB_NAME)
 SOURCES = ["b2n_points.cu", "b2n_interp.cu", "b2n_interp_tiled.cu", "b2n_interp_tiled_cl.cu", "b2n_interp_own.cu", "b2n_interp_tiled3d.cu", "b2n_fftops.cu", "b2n_fft.cu", "b2n_peer.cu",
            "b2n_fft_plans_a.cu", "b2n_fft_plans_b.cu", "b2n_fft_plans_c.cu", "b2n_fft_plans_d.cu", "b2n_fft_plans_e.cu", "b2n_fft_plans_f.cu", "b2n_fft_plans_g.cu", "b2n_fft_plans_h.cu"]
 HEADERS = ["b2n_common.cuh", "b2n_math.cuh", "b2n_tiling.cuh", "b2n_interp.cuh", "b2n_fft_core.cuh", "b2n_fft_fast.cuh",
-           "b2n_fft_args.cuh", "b2n_fft_fast_kernels.cuh", "b2n_tiled_common.cuh", os.path.join("..", "..", "include", "b200nufft.h")]
+           "b2n_fft_args.cuh", "b2n_fft_fast_kernels.cuh", "b2n_tiled_common.cuh", "b2n_peer.cuh", os.path.join("..", "..", "include", "b200nufft.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

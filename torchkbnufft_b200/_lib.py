@@ -162,6 +162,9 @@ SIGNATURES = {
     "b2n_peer_window_close": (c_int, [c_void_p]),
     "b2n_peer_window_destroy": (c_int, [c_void_p]),
     "b2n_peer_allreduce_sum": (c_int, [POINTER(PeerComm), c_void_p, c_void_p, c_int64, c_void_p]),
+    "b2n_fft_adjoint_fused_allreduce": (c_int, [c_int, _I64P, _I64P, c_int64, c_int64, c_void_p, c_void_p, c_int64,
+                                                c_void_p, c_int64, c_void_p, c_double, POINTER(c_void_p), c_void_p,
+                                                c_void_p, POINTER(PeerComm), c_void_p]),
 }
 
 _lib: Optional[ctypes.CDLL] = None

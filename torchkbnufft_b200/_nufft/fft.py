@@ -332,10 +332,12 @@ def fused_fft_forward(image: Tensor, grid_size: Sequence[int], smaps: Optional[T
 
 def fused_fft_adjoint(grid: Tensor, im_size: Sequence[int], smaps: Optional[Tensor] = None,
                       scaling_coef: Optional[Tensor] = None, scale: float = 1.0,
-                      kernel: Optional[Tensor] = None) -> Tensor:
+                      kernel: Optional[Tensor] = None, peer_comm=None) -> Tensor:
     """``sum_c crop(ifftn_unnormalised(grid * kernel)) * conj(scaling_coef) * conj(smaps) * scale``
     in ``ndim`` pruned passes; ``kernel`` (Toeplitz, ``(*K)`` or ``(B, *K)``) is optional.
-    Returns ``(B, 1, *N)`` with smaps, ``(B, C, *N)`` without."""
+    Returns ``(B, 1, *N)`` with smaps, ``(B, C, *N)`` without.  ``peer_comm`` (a ``_lib.PeerComm``, see
+    ``parallel.PeerAllReduce``): the result is additionally summed over the ranks of the communicator, inside the
+    last pass where that pass can carry the exchange (``b2n_fft_adjoint_fused_allreduce``)."""
     require_cuda(grid, "grid")
     grid = dense(grid)
     im_size = _sizes(im_size)
@@ -361,15 +363,19 @@ def fused_fft_adjoint(grid: Tensor, im_size: Sequence[int], smaps: Optional[Tens
     n_arr, k_arr, tw, nwork, _tabs = _fft_ctx(im_size, grid_size, B, C, grid.device)
     work = torch.empty(nwork, dtype=torch.uint8, device=grid.device) if nwork else None
     with device_guard(grid.device):
-        _lib.check(
-            _lib.load().b2n_fft_adjoint_fused(
-                len(im_size), n_arr, k_arr, B, C, grid.data_ptr(),
+        args = (len(im_size), n_arr, k_arr, B, C, grid.data_ptr(),
                 kernel.data_ptr() if kernel is not None else None, kb,
                 smaps.data_ptr() if smaps is not None else None, Bs,
                 scaling_coef.data_ptr() if scaling_coef is not None else None, float(scale), tw, out.data_ptr(),
-                work.data_ptr() if work is not None else None, current_stream_ptr(grid.device)),
-            "b2n_fft_adjoint_fused",
-        )
+                work.data_ptr() if work is not None else None)
+        if peer_comm is None:
+            _lib.check(_lib.load().b2n_fft_adjoint_fused(*args, current_stream_ptr(grid.device)), "b2n_fft_adjoint_fused")
+        else:
+            import ctypes
+
+            _lib.check(_lib.load().b2n_fft_adjoint_fused_allreduce(*args, ctypes.byref(peer_comm),
+                                                                   current_stream_ptr(grid.device)),
+                       "b2n_fft_adjoint_fused_allreduce")
     return out
 
 

@@ -91,8 +91,10 @@ class adjoint_epilogue:
     coil sums here: one ``cudaGraphLaunch`` per adjoint, collective included.  ``key`` distinguishes epilogues in the
     graph cache; ``applied`` tells the caller whether the operator ran it (it does not on the autograd path)."""
 
-    def __init__(self, fn: Callable[[Tensor], Tensor], key):
-        self.fn, self.key, self.applied = fn, key, False
+    def __init__(self, fn: Callable[[Tensor], Tensor], key, peer_comm=None):
+        # peer_comm: the epilogue is the engine's own all-reduce over this communicator, which the last FFT pass can
+        # perform itself (b2n_fft_adjoint_fused_allreduce) -- fn is then only the fallback for the unfused FFT route
+        self.fn, self.key, self.applied, self.peer_comm = fn, key, False, peer_comm
 
     def __enter__(self):
         self._prev = getattr(_SCOPE, "epilogue", None)

@@ -498,8 +498,26 @@ static int zero_sense_counters(const FusedGeom &g, float2 *T3, size_t t3e, cudaS
 
 // last pass of the adjoint: inverse transform of the contiguous dimension of rows_in [B*C][N0..N_{d-2}][K_last],
 // crop, * conj(scaling) * scale, and the SENSE coil combination when smaps is given
+// `peer` (optional): sum all-reduce of the output image over peer memory -- inside the row pass where it can carry
+// the exchange (k_fft_rows_sense with its whole grid resident), as one more kernel behind the last pass otherwise
+static int adjoint_rows_local(const FusedGeom &g, const float2 *rows_in, const float2 *smaps, int64_t Bs,
+                              const float2 *scaling, float scale, float2 *image, float2 *T3, size_t t3e,
+                              cudaStream_t st, const b2n_peer_comm *peer, int *peer_fused);
+
 static int adjoint_rows(const FusedGeom &g, const float2 *rows_in, const float2 *smaps, int64_t Bs,
-                        const float2 *scaling, float scale, float2 *image, float2 *T3, size_t t3e, cudaStream_t st) {
+                        const float2 *scaling, float scale, float2 *image, float2 *T3, size_t t3e, cudaStream_t st,
+                        const b2n_peer_comm *peer = nullptr) {
+  int fused = 0;
+  const int rc = adjoint_rows_local(g, rows_in, smaps, Bs, scaling, scale, image, T3, t3e, st, peer, &fused);
+  if (rc || !peer || peer->world <= 1 || fused) return rc;
+  int64_t n = 2 * g.B * (smaps ? 1 : g.C);
+  for (int k = 0; k < g.ndim; ++k) n *= g.N[k];
+  return peer_allreduce_launch(peer, image, image, n, st);
+}
+
+static int adjoint_rows_local(const FusedGeom &g, const float2 *rows_in, const float2 *smaps, int64_t Bs,
+                              const float2 *scaling, float scale, float2 *image, float2 *T3, size_t t3e,
+                              cudaStream_t st, const b2n_peer_comm *peer, int *peer_fused) {
   const int d = g.ndim;
   RowArgs r;
   memset(&r, 0, sizeof(r));
@@ -526,10 +544,18 @@ static int adjoint_rows(const FusedGeom &g, const float2 *rows_in, const float2 
   r.scale = scale;
   r.partial = T3;
   r.counter = reinterpret_cast<unsigned int *>(T3 + t3e);
+  if (peer && peer->world > 1) {
+    const int rc = peer_args_from_comm(peer, &r.peer);
+    if (rc) return rc;
+  }
   {
     const int rc = launch_rows_sense(r, g.B, st);
-    if (rc >= 0) return rc;
+    if (rc >= 0) {
+      *peer_fused = r.peer_fused;
+      return rc;
+    }
   }
+  r.peer.world = 0;
   // otherwise: cropped per-coil rows to scratch, then one pass multiplies conj(smaps) * conj(scaling)
   // and sums the coils (every line of the row pass stays independent: full parallelism)
   r.smaps = nullptr;
@@ -599,7 +625,7 @@ static int fused_toeplitz(const FusedGeom &g, const float2 *image, int64_t Ci, c
 // kernel (optional): Toeplitz factor multiplied into the loads of the first inverse pass
 static int fused_adjoint(const FusedGeom &g, const float2 *grid, const float2 *kernel, int64_t kernel_batch,
                          const float2 *smaps, int64_t Bs, const float2 *scaling, float scale, float2 *image,
-                         float2 *work, cudaStream_t st) {
+                         float2 *work, cudaStream_t st, const b2n_peer_comm *peer = nullptr) {
   const int d = g.ndim;
   size_t t1e, t2e, t3e;
   fused_work_layout(g, &t1e, &t2e, &t3e);
@@ -654,7 +680,7 @@ static int fused_adjoint(const FusedGeom &g, const float2 *grid, const float2 *k
   } else if (kernel) {
     return fail_arg(B2N_E_UNSUPPORTED, "1-D Toeplitz filtering goes through the unfused path");
   }
-  return adjoint_rows(g, rows_in, smaps, Bs, scaling, scale, image, T3, t3e, st);
+  return adjoint_rows(g, rows_in, smaps, Bs, scaling, scale, image, T3, t3e, st, peer);
 }
 
 }  // namespace b2n
@@ -746,4 +772,26 @@ extern "C" int b2n_fft_adjoint_fused(int ndim, const int64_t *im_size, const int
   return fused_adjoint(g, (const float2 *)grid_dev, (const float2 *)kernel_dev, kernel_dev ? kernel_batch : 1,
                        (const float2 *)smaps_dev, smaps_dev ? smaps_batch : 1, (const float2 *)scaling_dev, (float)scale,
                        (float2 *)image_dev, (float2 *)work_dev, (cudaStream_t)stream);
+}
+
+extern "C" int b2n_fft_adjoint_fused_allreduce(int ndim, const int64_t *im_size, const int64_t *grid_size,
+                                               int64_t n_batch, int64_t n_coils, const void *grid_dev,
+                                               const void *kernel_dev, int64_t kernel_batch, const void *smaps_dev,
+                                               int64_t smaps_batch, const void *scaling_dev, double scale,
+                                               const void *const *twiddle_dev, void *image_dev, void *work_dev,
+                                               const b2n_peer_comm *comm, void *stream) {
+  FusedGeom g;
+  if (!twiddle_dev) return fail_arg(B2N_E_ARG, "twiddle_dev is NULL");
+  if (!comm) return fail_arg(B2N_E_ARG, "comm is NULL");
+  int rc = make_fused_geom(ndim, im_size, grid_size, n_batch, n_coils, twiddle_dev, &g);
+  if (rc) return rc;
+  if (!image_dev || !grid_dev || !work_dev) return fail_arg(B2N_E_ARG, "NULL image/grid/work");
+  if (smaps_dev && smaps_batch != 1 && smaps_batch != n_batch) return fail_arg(B2N_E_ARG, "smaps_batch must be 1 or n_batch");
+  if (kernel_dev && kernel_batch != 1 && kernel_batch != n_batch) return fail_arg(B2N_E_ARG, "kernel_batch must be 1 or n_batch");
+  int64_t n = 2 * n_batch * (smaps_dev ? 1 : n_coils);
+  for (int k = 0; k < ndim; ++k) n *= im_size[k];
+  if (n > comm->max_floats) return fail_arg(B2N_E_RANGE, "image of %lld floats, window sized for %lld", (long long)n, (long long)comm->max_floats);
+  return fused_adjoint(g, (const float2 *)grid_dev, (const float2 *)kernel_dev, kernel_dev ? kernel_batch : 1,
+                       (const float2 *)smaps_dev, smaps_dev ? smaps_batch : 1, (const float2 *)scaling_dev, (float)scale,
+                       (float2 *)image_dev, (float2 *)work_dev, (cudaStream_t)stream, comm);
 }

@@ -3,6 +3,7 @@
 #pragma once
 #include "b2n_common.cuh"
 #include "b2n_fft_core.cuh"
+#include "b2n_peer.cuh"
 
 namespace b2n {
 
@@ -28,6 +29,12 @@ struct RowArgs {
   float2 *partial;
   unsigned int *counter;
   int prefetch;          // CTAs ahead whose operand rows this CTA pulls into L2 (0: off)
+  // k_fft_rows_sense only: sum all-reduce of the coil-combined image over peer memory, fused into the pass (each
+  // finished row goes straight into the peers' windows, b2n_peer.cuh).  The caller sets peer.world > 1 to ask for it;
+  // the launcher clears it when the pass cannot carry the exchange and reports what happened in peer_fused.
+  PeerArgs peer;
+  int64_t peer_floats;   // floats of the whole image (recorded as the size of this call's slot generation)
+  int peer_fused;        // host side, out: 1 when the launched kernel performed the all-reduce
 };
 
 struct ColArgs {

@@ -276,6 +276,14 @@ __global__ void __launch_bounds__(FastCfg<P>::SENSE_THREADS, FastCfg<P>::SENSE_M
   griddep_wait();  // the input rows come from the preceding pass
   constexpr int LP = FastCfg<P>::LPS, NT = FastCfg<P>::SENSE_THREADS;
   __shared__ int s_last;
+  __shared__ uint32_t s_epoch, s_prev;
+  const bool peer_on = a.peer.world > 1;  // the finished rows go through the peer-memory all-reduce
+  if (peer_on && threadIdx.x == 0) {      // read behind griddep_wait: the preceding call has advanced the counter
+    const uint32_t *hdr = reinterpret_cast<const uint32_t *>(a.peer.window[a.peer.rank]);
+    const uint32_t e = *reinterpret_cast<const volatile uint32_t *>(hdr) + 1u;
+    s_epoch = e;
+    s_prev = *reinterpret_cast<const volatile uint32_t *>(hdr + 4 + (e + 2u) % 3u);
+  }
   const int n_in = a.n_in, n_out = a.n_out;
   float2 *red = reinterpret_cast<float2 *>(fsm4 + LP * P::NP);  // [LP][n_out] pair sums
   const int lp = threadIdx.x / P::T, t = threadIdx.x - lp * P::T;
@@ -318,9 +326,40 @@ __global__ void __launch_bounds__(FastCfg<P>::SENSE_THREADS, FastCfg<P>::SENSE_M
   __syncthreads();
   const float2 *sc = a.scaling ? a.scaling + row * (uint32_t)n_out : nullptr;
   float2 *out = a.out + br * (uint32_t)n_out;
+  unsigned spins = 0;
+  unsigned long long t0 = 0;
   auto finish = [&](int j, float2 sum) {
     if (sc) sum = cmul2(sum, f2(sc[j].x, -sc[j].y));
-    out[j] = f2(sum.x * a.scale, sum.y * a.scale);
+    float2 val = f2(sum.x * a.scale, sum.y * a.scale);
+    // s_epoch was written before the barriers of the transform above
+    if (peer_on) val = peer_exchange(a.peer, s_epoch, (int64_t)br * (uint32_t)n_out + j, val, spins, t0);
+    out[j] = val;
+  };
+  // the CTA that finishes a row: after its last value, reset what an earlier, larger call left beyond this image
+  // (row 0 only) and take a ticket; the last ticket advances the window's call counter
+  auto peer_done = [&]() {
+    if (!peer_on) return;
+    const uint32_t epoch = s_epoch, gclr = (epoch + 2u) % 3u;
+    float *mine_w = reinterpret_cast<float *>(a.peer.window[a.peer.rank] + a.peer.data_off);
+    if (br == 0 && (int64_t)s_prev > a.peer_floats) {
+      const float fill = __uint_as_float(kPeerFill);
+      for (int r = 0; r < a.peer.world; ++r) {
+        if (r == a.peer.rank) continue;
+        float *dst = mine_w + ((size_t)gclr * a.peer.world + r) * a.peer.slot_floats;
+        for (int64_t i = a.peer_floats + threadIdx.x; i < (int64_t)s_prev; i += NT) dst[i] = fill;
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      uint32_t *hdr = reinterpret_cast<uint32_t *>(a.peer.window[a.peer.rank]);
+      __threadfence();
+      if (atomicAdd(hdr + 1, 1u) == gridDim.x / G - 1) {
+        hdr[1] = 0;
+        hdr[4 + epoch % 3u] = (uint32_t)a.peer_floats;
+        __threadfence();
+        *reinterpret_cast<volatile uint32_t *>(hdr) = epoch;
+      }
+    }
   };
   float2 *mine = a.partial + ((size_t)g * gridDim.x / G + br) * (uint32_t)n_out;  // [G][B*rows][n_out]
   for (int j = threadIdx.x; j < n_out; j += NT) {
@@ -330,7 +369,10 @@ __global__ void __launch_bounds__(FastCfg<P>::SENSE_THREADS, FastCfg<P>::SENSE_M
     if (G == 1) finish(j, sum);
     else __stcg(&mine[j], sum);
   }
-  if (G == 1) return;
+  if (G == 1) {
+    peer_done();
+    return;
+  }
   __threadfence();
   __syncthreads();
   if (threadIdx.x == 0) s_last = atomicAdd(&a.counter[br], 1u) == G - 1;
@@ -343,6 +385,7 @@ __global__ void __launch_bounds__(FastCfg<P>::SENSE_THREADS, FastCfg<P>::SENSE_M
     finish(j, sum);
   }
   if (threadIdx.x == 0) a.counter[br] = 0;  // leave the counters zero for the next call
+  peer_done();
 }
 
 // B2N_OPT_FFT_PREFETCH is a mask over the passes: 1 forward rows, 2 forward columns, 4 inverse columns, 8 inverse rows
@@ -438,6 +481,14 @@ template <class P, bool HALF> int launch_rows_sense_h(RowArgs &a, int64_t B, cud
   auto kern = k_fft_rows_sense<P, HALF>;
   B2N_SMEM_OPT_IN(kern, smem);
   a.prefetch = want_prefetch(sizeof(float2) * (size_t)a.lines * a.n_in, PF_ROWS_INV) ? resident_ctas(kern, Cfg::SENSE_THREADS, smem) : 0;
+  // the fused all-reduce makes CTAs wait for the same rows of the peers: only with the whole grid resident (no CTA
+  // of a peer can be kept off its GPU by CTAs that wait for it) and the image inside the window
+  a.peer_fused = 0;
+  if (a.peer.world > 1) {
+    a.peer_floats = 2 * rows * a.n_out;
+    if (rows * a.coil_groups <= resident_ctas(kern, Cfg::SENSE_THREADS, smem) && a.peer_floats <= a.peer.slot_floats) a.peer_fused = 1;
+    else a.peer.world = 0;
+  }
   if (a.coil_groups > 1 && !g_counters_early) B2N_CUDA_OK(cudaMemsetAsync(a.counter, 0, sizeof(unsigned int) * (size_t)rows, st));
   B2N_CUDA_OK(launch_pdl(kern, dim3((unsigned)(rows * a.coil_groups)), dim3(Cfg::SENSE_THREADS), smem, st, a));
   B2N_LAUNCH_OK("k_fft_rows_sense");

@@ -19,62 +19,12 @@
 
 #include <type_traits>
 
-#include "b2n_common.cuh"
+#include "b2n_peer.cuh"
 
 namespace b2n {
 
-constexpr int kPeerThreads = 256;
-constexpr int kPeerChunk = 4096;          // floats per CTA and round: 256 threads x 4 x float4
-constexpr int kPeerHeader = 256;          // bytes: {calls completed, CTAs of the running call that are done, -, -, floats of generation 0 / 1 / 2}
-constexpr uint32_t kPeerFill = 0x80000000u;  // -0.0f
-
-struct PeerLayout {
-  int64_t slot_floats;
-  size_t data_off, bytes;
-};
-
-static PeerLayout peer_layout(int world, int64_t max_floats) {
-  PeerLayout l;
-  l.slot_floats = ceil_div(max_floats, kPeerChunk) * kPeerChunk;
-  l.data_off = kPeerHeader;
-  l.bytes = l.data_off + sizeof(float) * 3 * (size_t)world * l.slot_floats;
-  return l;
-}
-
-struct PeerArgs {
-  int rank, world;
-  int64_t slot_floats;
-  size_t data_off;
-  unsigned char *window[B2N_PEER_MAX_RANKS];
-};
-
 __global__ void k_peer_fill(uint32_t *p, size_t n, uint32_t v) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
-}
-
-B2N_D float not_fill(float x) { return __float_as_uint(x) == kPeerFill ? 0.f : x; }
-B2N_D float4 ld_volatile4(const float *p) {
-  float4 v;
-  asm volatile("ld.volatile.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
-  return v;
-}
-B2N_D float ld_volatile1(const float *p) {
-  float v;
-  asm volatile("ld.volatile.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
-  return v;
-}
-B2N_D bool arrived(float4 v) {
-  return __float_as_uint(v.x) != kPeerFill && __float_as_uint(v.y) != kPeerFill && __float_as_uint(v.z) != kPeerFill &&
-         __float_as_uint(v.w) != kPeerFill;
-}
-B2N_D bool arrived(float v) { return __float_as_uint(v) != kPeerFill; }
-// a peer that never issues the matching call is a usage error: trap after ~20 s instead of hanging the device
-B2N_D void spin_guard(unsigned &spins, unsigned long long &t0) {
-  if ((++spins & 0xFFFFu) != 0) return;
-  unsigned long long now;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
-  if (!t0) t0 = now;
-  else if (now - t0 > 20000000000ull) __trap();
 }
 
 // VEC = 4: n a multiple of 4 and 16-byte aligned pointers; VEC = 1: anything
@@ -235,13 +185,14 @@ extern "C" int b2n_peer_window_destroy(void *window_dev) {
   return 0;
 }
 
-extern "C" int b2n_peer_allreduce_sum(const b2n_peer_comm *comm, const void *in_dev, void *out_dev, int64_t n_floats,
-                                      void *stream) {
-  if (!comm || !in_dev || !out_dev) return fail_arg(B2N_E_ARG, "peer all-reduce: NULL comm/in/out");
+namespace b2n {
+
+int peer_args_from_comm(const b2n_peer_comm *comm, PeerArgs *out) {
+  if (!comm) return fail_arg(B2N_E_ARG, "peer all-reduce: NULL comm");
   if (comm->world < 1 || comm->world > B2N_PEER_MAX_RANKS || comm->rank < 0 || comm->rank >= comm->world)
     return fail_arg(B2N_E_ARG, "peer all-reduce: rank %d of %d", comm->rank, comm->world);
-  if (n_floats < 1 || n_floats > comm->max_floats)
-    return fail_arg(B2N_E_RANGE, "peer all-reduce: %lld floats, window sized for %lld", (long long)n_floats, (long long)comm->max_floats);
+  if (comm->max_floats < 1 || comm->max_floats >= ((int64_t)1 << 31))
+    return fail_arg(B2N_E_ARG, "peer all-reduce: max_floats %lld", (long long)comm->max_floats);
   const PeerLayout l = peer_layout(comm->world, comm->max_floats);
   PeerArgs a;
   a.rank = comm->rank;
@@ -252,7 +203,17 @@ extern "C" int b2n_peer_allreduce_sum(const b2n_peer_comm *comm, const void *in_
     a.window[r] = r < comm->world ? static_cast<unsigned char *>(comm->window[r]) : nullptr;
     if (r < comm->world && !a.window[r]) return fail_arg(B2N_E_ARG, "peer all-reduce: window of rank %d is NULL", r);
   }
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  *out = a;
+  return 0;
+}
+
+int peer_allreduce_launch(const b2n_peer_comm *comm, const void *in_dev, void *out_dev, int64_t n_floats, cudaStream_t st) {
+  if (!in_dev || !out_dev) return fail_arg(B2N_E_ARG, "peer all-reduce: NULL in/out");
+  PeerArgs a;
+  const int rc = peer_args_from_comm(comm, &a);
+  if (rc) return rc;
+  if (n_floats < 1 || n_floats > comm->max_floats)
+    return fail_arg(B2N_E_RANGE, "peer all-reduce: %lld floats, window sized for %lld", (long long)n_floats, (long long)comm->max_floats);
   const int64_t chunks = ceil_div(n_floats, kPeerChunk);
   int dev = 0, sms = 0;
   B2N_CUDA_OK(cudaGetDevice(&dev));
@@ -269,4 +230,11 @@ extern "C" int b2n_peer_allreduce_sum(const b2n_peer_comm *comm, const void *in_
                            static_cast<float *>(out_dev), n_floats));
   B2N_LAUNCH_OK("k_peer_allreduce_sum");
   return 0;
+}
+
+}  // namespace b2n
+
+extern "C" int b2n_peer_allreduce_sum(const b2n_peer_comm *comm, const void *in_dev, void *out_dev, int64_t n_floats,
+                                      void *stream) {
+  return peer_allreduce_launch(comm, in_dev, out_dev, n_floats, static_cast<cudaStream_t>(stream));
 }

@@ -84,6 +84,11 @@ def sense_nufft_adjoint(data: Tensor, smaps: Optional[Tensor], scaling_coef: Ten
         return out
     if not _needs_grad(data) and not (smaps is not None and smaps.requires_grad):
         grid = _interp.table_interp_adjoint(data, omega, tables, n_shift, numpoints, table_oversamp, offsets, grid_size)
+        if fused and epilogue is not None and epilogue.peer_comm is not None:
+            # the all-reduce is part of the last inverse pass (or one kernel behind it: the C side decides)
+            out = _fft.fused_fft_adjoint(grid, _ints(im_size), smaps, scaling_coef, scale, peer_comm=epilogue.peer_comm)
+            epilogue.applied = True
+            return out
         if fused:
             out = _fft.fused_fft_adjoint(grid, _ints(im_size), smaps, scaling_coef, scale)
         else:

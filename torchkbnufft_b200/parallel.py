@@ -67,6 +67,11 @@ def all_reduce_complex_(x: Tensor, group=None) -> Tensor:
     return x
 
 
+# coil_sharded_adjoint with a PeerAllReduce: let the last inverse FFT pass push its rows into the peers' windows itself
+# (b2n_fft_adjoint_fused_allreduce) instead of launching the all-reduce kernel behind it; off for A/B measurements
+fuse_allreduce = True
+
+
 class PeerAllReduce:
     """In-place sum all-reduce of a float32 / complex64 CUDA tensor over NVLink peer memory
     (``b2n_peer_allreduce_sum``): one process per GPU, all on one node.
@@ -94,31 +99,61 @@ class PeerAllReduce:
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.max_floats = int(max_values) * (2 if dtype.is_complex else 1)
         lib = _lib.load()
-        nbytes = ctypes.c_size_t(0)
-        _lib.check(lib.b2n_peer_window_bytes(self.world, self.max_floats, ctypes.byref(nbytes)), "b2n_peer_window_bytes")
-        self._own = ctypes.c_void_p(None)
-        handle = ctypes.create_string_buffer(_lib.PEER_HANDLE_BYTES)
-        with torch.cuda.device(self.device):
-            _lib.check(lib.b2n_peer_window_create(nbytes.value, ctypes.byref(self._own), handle), "b2n_peer_window_create")
-        handles = [None] * self.world
-        if self.world > 1:
-            dist.all_gather_object(handles, bytes(handle.raw), group=group)
+        self._group = group
+        self._own, self._peers = None, []
         self._comm = _lib.PeerComm()
         self._comm.rank, self._comm.world, self._comm.max_floats = self.rank, self.world, self.max_floats
-        self._peers = []
-        for r in range(self.world):
-            if r == self.rank:
-                self._comm.window[r] = self._own.value
-                continue
-            mapped = ctypes.c_void_p(None)
+        # every step below is followed by an exchange of its outcome, so that a failure on ONE rank (no peer access,
+        # IPC refused by the container) raises on ALL of them instead of leaving the others in a collective
+        error, handle = None, ctypes.create_string_buffer(_lib.PEER_HANDLE_BYTES)
+        try:
+            nbytes = ctypes.c_size_t(0)
+            _lib.check(lib.b2n_peer_window_bytes(self.world, self.max_floats, ctypes.byref(nbytes)), "b2n_peer_window_bytes")
+            own = ctypes.c_void_p(None)
             with torch.cuda.device(self.device):
-                _lib.check(lib.b2n_peer_window_open(ctypes.create_string_buffer(handles[r], _lib.PEER_HANDLE_BYTES),
-                                                    ctypes.byref(mapped)), f"b2n_peer_window_open(rank {r})")
-            self._comm.window[r] = mapped.value
-            self._peers.append(mapped)
-        if self.world > 1:
-            dist.barrier(group=group)  # nobody pushes into a window that is not mapped and zeroed yet
-        self._group = group
+                _lib.check(lib.b2n_peer_window_create(nbytes.value, ctypes.byref(own), handle), "b2n_peer_window_create")
+            self._own = own
+            self._comm.window[self.rank] = own.value
+        except Exception as exc:  # noqa: BLE001
+            error = f"rank {self.rank}: {exc}"
+        handles = self._exchange((error, bytes(handle.raw)))
+        self._raise_if_any([h[0] for h in handles])
+        try:
+            for r in range(self.world):
+                if r == self.rank:
+                    continue
+                mapped = ctypes.c_void_p(None)
+                with torch.cuda.device(self.device):
+                    _lib.check(lib.b2n_peer_window_open(ctypes.create_string_buffer(handles[r][1], _lib.PEER_HANDLE_BYTES),
+                                                        ctypes.byref(mapped)), f"b2n_peer_window_open(rank {r})")
+                self._comm.window[r] = mapped.value
+                self._peers.append(mapped)
+        except Exception as exc:  # noqa: BLE001
+            error = f"rank {self.rank}: {exc}"
+        # also the barrier that keeps anyone from pushing into a window that is not mapped and filled yet
+        self._raise_if_any(self._exchange(error))
+
+    def _exchange(self, item):
+        if self.world == 1:
+            return [item]
+        out = [None] * self.world
+        dist.all_gather_object(out, item, group=self._group)
+        return out
+
+    def _raise_if_any(self, errors) -> None:
+        errors = [e for e in errors if e]
+        if errors:
+            self._release()
+            raise RuntimeError("PeerAllReduce could not be set up: " + "; ".join(errors))
+
+    def _release(self) -> None:
+        lib = self._lib.load()
+        for mapped in self._peers:
+            lib.b2n_peer_window_close(mapped)
+        self._peers = []
+        if self._own is not None:
+            lib.b2n_peer_window_destroy(self._own)
+            self._own = None
 
     # one-shot pushes move (world - 1) copies of the message per rank: past this many bytes per rank a ring / tree
     # all-reduce (NCCL) wins (profiles/r02_peer_allreduce_8gpu.log: 4 MB at 8 GPUs is already slower than NCCL)
@@ -132,6 +167,13 @@ class PeerAllReduce:
         n = int(n_values) * (2 if dtype.is_complex else 1)
         return 0 < n <= self.max_floats and 4 * n * max(self.world - 1, 1) <= self.ONE_SHOT_BYTES
 
+    @property
+    def comm(self):
+        """The ``_lib.PeerComm`` (``struct b2n_peer_comm``) of this rank, for C entries that take a communicator."""
+        if self._own is None:
+            raise RuntimeError("PeerAllReduce is closed")
+        return self._comm
+
     def __call__(self, x: Tensor) -> Tensor:
         if x.device != self.device or x.dtype not in (torch.complex64, torch.float32) or not x.is_contiguous():
             raise ValueError("PeerAllReduce needs a contiguous float32 / complex64 tensor on its own device")
@@ -140,8 +182,10 @@ class PeerAllReduce:
         n = x.numel() * (2 if x.is_complex() else 1)
         if n == 0:
             return x
+        if x.is_complex() and (x.is_conj() or x.is_neg()):
+            raise ValueError("PeerAllReduce works in place: materialise lazy conj / neg views first (resolve_conj())")
         stream = torch.cuda.current_stream(self.device).cuda_stream
-        ptr = x.resolve_conj().data_ptr() if x.is_complex() else x.data_ptr()
+        ptr = x.data_ptr()
         self._lib.check(self._lib.load().b2n_peer_allreduce_sum(self._ctypes.byref(self._comm), ptr, ptr, n, stream),
                         "b2n_peer_allreduce_sum")
         return x
@@ -157,8 +201,7 @@ class PeerAllReduce:
         self._peers = []
         if self.world > 1 and dist.is_initialized():
             dist.barrier(group=self._group)
-        lib.b2n_peer_window_destroy(self._own)
-        self._own = None
+        self._release()
 
 
 def coil_sharded_forward(nufft_ob, image: Tensor, omega: Tensor, smaps_local: Tensor,
@@ -181,12 +224,28 @@ def coil_sharded_adjoint(adj_ob, data_local: Tensor, omega: Tensor, smaps_local:
         # the all-reduce kernel is the last launch OF the adjoint: in graph mode it is replayed with it
         from ._nufft import graphs as _graphs
 
-        with _graphs.adjoint_epilogue(reducer, ("peer_allreduce", id(reducer))) as epilogue:
+        with _graphs.adjoint_epilogue(reducer, ("peer_allreduce", id(reducer), fuse_allreduce),
+                                      peer_comm=reducer.comm if fuse_allreduce else None) as epilogue:
             partial = adj_ob(data_local, omega, smaps=smaps_local, norm=norm)
         if epilogue.applied:
             return partial
     else:
         partial = adj_ob(data_local, omega, smaps=smaps_local, norm=norm)
+    partial = partial.contiguous()
+    if reducer is not None and reducer.takes(partial.numel(), partial.dtype):
+        return reducer(partial)
+    return all_reduce_complex_(partial, group)
+
+
+def coil_sharded_toeplitz(toep_ob, image: Tensor, kernel: Tensor, smaps_local: Tensor, norm: Optional[str] = None,
+                          group=None, reducer: Optional[PeerAllReduce] = None) -> Tensor:
+    """Toeplitz normal operator ``sum_c conj(S_c) filter(S_c x)`` with the coils sharded over ranks: the local
+    ``ToepNufft`` apply on this rank's coils (image and kernel replicated), then the same sum all-reduce of
+    ``(B, 1, *N)`` as the adjoint (reference coupling point ``modules/kbnufft.py:484``)."""
+    if smaps_local.shape[1] == 0:
+        partial = torch.zeros_like(image)
+    else:
+        partial = toep_ob(image, kernel, smaps=smaps_local, norm=norm)
     partial = partial.contiguous()
     if reducer is not None and reducer.takes(partial.numel(), partial.dtype):
         return reducer(partial)
