@@ -694,15 +694,20 @@ struct OwnFixArgs {
   const float2 *coef;
 };
 
-constexpr int kFixTiles = 32;  // output tiles looked at by one CTA (most of them have no exception points)
+// Output tiles looked at by one CTA (most of them have no exception points).  2-D: 32 (config 2: 9 us).  3-D: the
+// tiles with exceptions cluster around the k-space origin, where one CTA then works through its whole group tile after
+// tile (1.7 ms at config 4 with 32 tiles per CTA; 4 keep the serial part short and the grid
+// a quarter of the tile count: 0.65 ms; one tile per CTA, what ships: 0.5 ms).
+template <int ND> constexpr int fix_tiles() { return ND == 3 ? 1 : 32; }
 
 template <int ND>
 __global__ void __launch_bounds__(128) k_own_fix(OwnFixArgs a, const float2 *__restrict__ kdata, float2 *__restrict__ grid) {
   griddep_wait();
   if (a.counts[3] > a.xcap) __trap();  // more (exception point, tile) pairs than own_xv holds: fail loudly
   const int64_t n_tiles_all = a.n_own_tiles * a.n_traj;
+  constexpr int kFixTiles = fix_tiles<ND>();
   const int64_t t_mine = (int64_t)blockIdx.x * kFixTiles + (threadIdx.x & 31);
-  const int2 seg_mine = t_mine < n_tiles_all ? a.xt[t_mine] : make_int2(0, 0);
+  const int2 seg_mine = (int)(threadIdx.x & 31) < kFixTiles && t_mine < n_tiles_all ? a.xt[t_mine] : make_int2(0, 0);
   unsigned todo = __ballot_sync(0xffffffffu, seg_mine.y > 0);  // the same in every warp of the CTA
   const int t = threadIdx.x;
   int cl[3] = {0, 0, 0};
@@ -845,7 +850,8 @@ static int launch_fix(const OwnLaunch &l) {
   f.xt = (const int2 *)l.p->own_xt;
   f.xv = (const int2 *)l.p->own_xv;
   f.coef = (const float2 *)l.p->coef;
-  dim3 gf((unsigned)ceil_div(f.n_own_tiles * l.p->n_traj, kFixTiles), 1, (unsigned)(l.p->n_traj == 1 ? l.B : 1));
+  dim3 gf((unsigned)ceil_div(f.n_own_tiles * l.p->n_traj, l.g->ndim == 3 ? fix_tiles<3>() : fix_tiles<2>()), 1,
+          (unsigned)(l.p->n_traj == 1 ? l.B : 1));
   if (l.g->ndim == 3)
     B2N_CUDA_OK(launch_pdl(k_own_fix<3>, gf, dim3(128), 0, l.st, f, (const float2 *)l.kdata, (float2 *)l.grid));
   else
