@@ -130,3 +130,27 @@ def test_spmat_mode_is_a_torch_sparse_shim():
 
     from torchkbnufft_b200._nufft import spmat
     assert "_lib" not in inspect.getsource(spmat)
+
+
+def test_peer_window_entries_are_host_checkable():
+    """The peer-memory all-reduce entries: header constants vs the binding, the communicator mirror's layout, and the
+    host-only size query with its argument errors (no device work)."""
+    lib = _lib.load()
+    text = open(os.path.join(ROOT, "include", "b200nufft.h")).read()
+    consts = dict((k, int(v)) for k, v in re.findall(r"#define (B2N_PEER_[A-Z_]+) (\d+)", text))
+    assert consts["B2N_PEER_MAX_RANKS"] == _lib.PEER_MAX_RANKS == 16
+    assert consts["B2N_PEER_HANDLE_BYTES"] == _lib.PEER_HANDLE_BYTES == 64
+    assert ctypes.sizeof(_lib.PeerComm) == 4 + 4 + 8 + 8 * _lib.PEER_MAX_RANKS
+    n = ctypes.c_size_t(0)
+    assert lib.b2n_peer_window_bytes(8, 2 * 320 * 320, ctypes.byref(n)) == 0
+    # header + three slot generations x ranks x the image rounded up to 4096-float chunks
+    assert n.value == 256 + 4 * 3 * 8 * (2 * 320 * 320)
+    assert lib.b2n_peer_window_bytes(1, 1, ctypes.byref(n)) == 0 and n.value == 256 + 4 * 3 * 4096
+    for world, floats in ((0, 10), (17, 10), (2, 0), (2, 1 << 31)):
+        assert lib.b2n_peer_window_bytes(world, floats, ctypes.byref(n)) == -1  # B2N_E_ARG
+    assert b"peer window" in lib.b2n_last_error()
+    assert lib.b2n_peer_window_bytes(2, 10, None) == -1
+    comm = _lib.PeerComm()
+    comm.rank, comm.world, comm.max_floats = 3, 2, 100
+    assert lib.b2n_peer_allreduce_sum(ctypes.byref(comm), 16, 16, 10, None) == -1  # rank outside the world
+    assert lib.b2n_peer_window_close(None) == 0 and lib.b2n_peer_window_destroy(None) == 0
