@@ -35,6 +35,14 @@ namespace b2n {
 constexpr int kTile = 16;   // must match make_tiling() for ndim == 2
 constexpr int kWarps = 8;   // warps per CTA (== row-ownership modulus of the adjoint)
 constexpr int kThreads = kWarps * 32;
+// forward gather: its own CTA shape (A/B: profiles/scripts/gather_cfg_ab.sh)
+#ifndef B2N_FWD2_WARPS
+#define B2N_FWD2_WARPS 8
+#endif
+#ifndef B2N_FWD2_MINB
+#define B2N_FWD2_MINB 3
+#endif
+constexpr int kFwdWarps = B2N_FWD2_WARPS, kFwdThreads = kFwdWarps * 32, kFwdMinB = B2N_FWD2_MINB;
 constexpr int kCap = 128;   // max points per sub-problem the forward kernel stages at once
 constexpr int kRound = 32;  // points per staging round of the adjoint kernel
 constexpr int kJ = 6;       // neighbours per dimension handled here
@@ -85,10 +93,10 @@ template <int CC> B2N_D void lane_map(int lane, int &c, int &q) {
 template <int CC> constexpr int planes() { return CC < kBoxPlanes ? kBoxPlanes : CC; }
 
 // element-wise staging of the tile with periodic wrap (boundary tiles / no tensor map)
-template <int CC>
+template <int CC, int NT = kThreads>
 B2N_D void stage_tile_elementwise(float2 *tile, const float2 *__restrict__ grid, const SubProblem &sp, int C, int Ky,
                                   int Kx) {
-  for (int e = threadIdx.x; e < CC * kPS; e += kThreads) {
+  for (int e = threadIdx.x; e < CC * kPS; e += NT) {
     const int c = e / kPS, rem = e - c * kPS;
     const int r = rem / kSX, x = rem - r * kSX;
     int gy = sp.y0 + r, gx = sp.x0 + x;
@@ -103,7 +111,7 @@ B2N_D void stage_tile_elementwise(float2 *tile, const float2 *__restrict__ grid,
 // forward gather
 // -----------------------------------------------------------------------------------------
 template <int CC, int QY, int QX>
-__global__ void __launch_bounds__(kThreads, 3) k_fwd_tiled_2d(InterpArgs<float> a, const float2 *__restrict__ grid,
+__global__ void __launch_bounds__(kFwdThreads, kFwdMinB) k_fwd_tiled_2d(InterpArgs<float> a, const float2 *__restrict__ grid,
                                                            float2 *__restrict__ kdata,
                                                            const __grid_constant__ CUtensorMap tmap, int use_tma) {
   constexpr int Q = QY * QX, NY = kJ / QY, NX = kJ / QX;
@@ -128,9 +136,9 @@ __global__ void __launch_bounds__(kThreads, 3) k_fwd_tiled_2d(InterpArgs<float> 
     const float4 *src =
         reinterpret_cast<const float4 *>(reinterpret_cast<const float2 *>(a.coef) + (int64_t)sp.start * kNC);
     float4 *dst = reinterpret_cast<float4 *>(s_coef);
-    for (int e = threadIdx.x; e < sp.count * (kNC / 2); e += kThreads) cp_async16(&dst[e], &src[e]);
+    for (int e = threadIdx.x; e < sp.count * (kNC / 2); e += kFwdThreads) cp_async16(&dst[e], &src[e]);
     const int2 *bsrc = reinterpret_cast<const int2 *>(a.base) + sp.start;
-    for (int e = threadIdx.x; e < sp.count; e += kThreads) {
+    for (int e = threadIdx.x; e < sp.count; e += kFwdThreads) {
       cp_async8(&s_base[e], &bsrc[e], true);
       cp_async4(&s_perm[e], &a.perm[sp.start + e]);
     }
@@ -145,7 +153,7 @@ __global__ void __launch_bounds__(kThreads, 3) k_fwd_tiled_2d(InterpArgs<float> 
         tma_load_4d(tile + p * kPS, &tmap, 2 * sp.x0, sp.y0, sp.c0 + p, sp.b, bar);
     }
   } else {
-    stage_tile_elementwise<CC>(tile, grid, sp, C, Ky, Kx);
+    stage_tile_elementwise<CC, kFwdThreads>(tile, grid, sp, C, Ky, Kx);
   }
   cp_async_commit();
   const long long t_issued = a.trace ? gtime() : 0;
@@ -166,7 +174,7 @@ __global__ void __launch_bounds__(kThreads, 3) k_fwd_tiled_2d(InterpArgs<float> 
   // PU points per warp iteration: their shared-memory loads are independent, which gives the
   // scheduler the ILP that one point alone (a chain LDS -> FFMA -> FFMA -> SHFL) lacks
   constexpr int PU = 2;
-  for (int i0 = warp * PU; i0 < sp.count; i0 += kWarps * PU) {
+  for (int i0 = warp * PU; i0 < sp.count; i0 += kFwdWarps * PU) {
     float2 acc[PU];
 #pragma unroll
     for (int u = 0; u < PU; ++u) {
@@ -1036,7 +1044,7 @@ static int launch_fwd(const InterpArgs<float> &a, const void *grid, void *kdata,
   memset(&map, 0, sizeof(map));
   const int use_tma = make_grid_tmap(&map, grid, a.B, a.C, a.K[0], a.K[1]) ? 1 : 0;
   dim3 gd((unsigned)a.n_sub_max, (unsigned)ceil_div(a.C, CC), (unsigned)(a.n_traj == 1 ? a.B : 1));
-  B2N_CUDA_OK(launch_pdl(kern, gd, dim3(kThreads), smem, st, a, (const float2 *)grid, (float2 *)kdata, map, use_tma));
+  B2N_CUDA_OK(launch_pdl(kern, gd, dim3(kFwdThreads), smem, st, a, (const float2 *)grid, (float2 *)kdata, map, use_tma));
   B2N_LAUNCH_OK("k_fwd_tiled_2d");
   return 0;
 }

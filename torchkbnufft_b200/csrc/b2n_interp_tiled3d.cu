@@ -25,6 +25,12 @@ namespace b2n {
 constexpr int k3Tile = 8;   // must match make_tiling() for ndim == 3
 constexpr int k3Warps = 8;
 constexpr int k3Threads = k3Warps * 32;
+// forward gather's own CTA shape: 16 warps (two 100 KB CTAs per SM = 32 resident warps at 56 registers) measured 2.5 %
+// faster than 8 at config 4 (7.75 vs 7.95 ms); in 2-D more warps per CTA lose (profiles/r02_gather_cta_shape_ab.log)
+#ifndef B2N_FWD3_WARPS
+#define B2N_FWD3_WARPS 16
+#endif
+constexpr int k3FwdWarps = B2N_FWD3_WARPS, k3FwdThreads = k3FwdWarps * 32;
 constexpr int k3Cap = 128;  // max points per sub-problem staged at once (forward)
 constexpr int k3Round = 32;
 constexpr int k3J = 6;
@@ -90,7 +96,7 @@ B2N_D void lane_map3(int lane, int &c, int &qz, int &qy, int &qx) {
 // -----------------------------------------------------------------------------------------
 // forward gather
 // -----------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(k3Threads, 2) k_fwd_tiled_3d(InterpArgs<float> a, const float2 *__restrict__ grid,
+__global__ void __launch_bounds__(k3FwdThreads, 2) k_fwd_tiled_3d(InterpArgs<float> a, const float2 *__restrict__ grid,
                                                                float2 *__restrict__ kdata,
                                                                const __grid_constant__ CUtensorMap tmap, int use_tma) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -112,7 +118,7 @@ __global__ void __launch_bounds__(k3Threads, 2) k_fwd_tiled_3d(InterpArgs<float>
       tma_load_5d(tile, &tmap, 2 * sp.x0, sp.y0, sp.z0, sp.c0, sp.b, bar);
     }
   } else {
-    for (int e = threadIdx.x; e < k3TileF2; e += k3Threads) {
+    for (int e = threadIdx.x; e < k3TileF2; e += k3FwdThreads) {
       bool on, pad;
       const int64_t gi = tile_global_index(sp, e, C, Kz, Ky, Kx, on, pad);
       cp_async8(&tile[e], &grid[gi], on);
@@ -122,9 +128,9 @@ __global__ void __launch_bounds__(k3Threads, 2) k_fwd_tiled_3d(InterpArgs<float>
     const float4 *src =
         reinterpret_cast<const float4 *>(reinterpret_cast<const float2 *>(a.coef) + (int64_t)sp.start * k3NC);
     float4 *dst = reinterpret_cast<float4 *>(s_coef);
-    for (int e = threadIdx.x; e < sp.count * (k3NC / 2); e += k3Threads) cp_async16(&dst[e], &src[e]);
-    for (int e = threadIdx.x; e < sp.count * 3; e += k3Threads) cp_async4(&s_base[e], &a.base[(int64_t)sp.start * 3 + e]);
-    for (int e = threadIdx.x; e < sp.count; e += k3Threads) cp_async4(&s_perm[e], &a.perm[sp.start + e]);
+    for (int e = threadIdx.x; e < sp.count * (k3NC / 2); e += k3FwdThreads) cp_async16(&dst[e], &src[e]);
+    for (int e = threadIdx.x; e < sp.count * 3; e += k3FwdThreads) cp_async4(&s_base[e], &a.base[(int64_t)sp.start * 3 + e]);
+    for (int e = threadIdx.x; e < sp.count; e += k3FwdThreads) cp_async4(&s_perm[e], &a.perm[sp.start + e]);
   }
   cp_async_commit();
   cp_async_wait_all();
@@ -137,7 +143,7 @@ __global__ void __launch_bounds__(k3Threads, 2) k_fwd_tiled_3d(InterpArgs<float>
   const float2 *tplane = tile + c * k3PS + qz * k3ZS + qy * k3SX + qx;
   float2 *out = kdata + (int64_t)(sp.b * C + sp.c0 + c) * a.M;
   const bool store = lane < 4 && sp.c0 + c < C;
-  for (int i = warp; i < sp.count; i += k3Warps) {
+  for (int i = warp; i < sp.count; i += k3FwdWarps) {
     const float2 *rec = s_coef + i * k3NC;
     float2 cz[3], cy[3], cx[3];
 #pragma unroll
@@ -361,7 +367,7 @@ int tiled3_forward(const b2n_geom *g, const b2n_points *p, const void *grid, int
   memset(&map, 0, sizeof(map));
   const int use_tma = make_grid_tmap3(&map, grid, a.B, a.C, a.K[0], a.K[1], a.K[2]) ? 1 : 0;
   dim3 gd((unsigned)a.n_sub_max, (unsigned)ceil_div(a.C, k3CC), (unsigned)(a.n_traj == 1 ? a.B : 1));
-  k_fwd_tiled_3d<<<gd, k3Threads, smem, st>>>(a, (const float2 *)grid, (float2 *)kdata, map, use_tma);
+  k_fwd_tiled_3d<<<gd, k3FwdThreads, smem, st>>>(a, (const float2 *)grid, (float2 *)kdata, map, use_tma);
   B2N_LAUNCH_OK("k_fwd_tiled_3d");
   return 0;
 }
