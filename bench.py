@@ -615,7 +615,9 @@ def main():
                 ms = float(t.item())
             return ms
 
-        n_e2e = max(6, min(30, args.steps))
+        # enough steps for the fill and drain of the 3-deep pipeline (one upload, one compute + download that overlap
+        # nothing) to be a few per cent of the region, not 10 % as with 20 steps
+        n_e2e = max(60, min(200, args.steps))
         for _ in range(3):
             serial_step()
         # median of five repetitions each (the host side of these copies is shared with whatever else runs on the
