@@ -84,6 +84,8 @@ class PeerAllReduce:
     of the tensor's own dtype (complex counts double internally).
     """
 
+    _serial = 0
+
     def __init__(self, max_values: int, dtype: torch.dtype = torch.complex64, group=None,
                  device: Optional[torch.device] = None):
         import ctypes
@@ -91,6 +93,8 @@ class PeerAllReduce:
         from . import _lib
 
         self._lib, self._ctypes = _lib, ctypes
+        PeerAllReduce._serial += 1
+        self.key = ("peer_allreduce", PeerAllReduce._serial)  # identifies this reducer in the CUDA-graph cache
         self.rank, self.world = _rank_world(group)
         if self.world > _lib.PEER_MAX_RANKS:
             raise ValueError(f"PeerAllReduce serves up to {_lib.PEER_MAX_RANKS} ranks, got {self.world}")
@@ -194,6 +198,9 @@ class PeerAllReduce:
         """Collective: unmap the peers' windows, then free this rank's own (after everyone has unmapped)."""
         if self._own is None:
             return
+        from ._nufft import graphs as _graphs
+
+        _graphs.clear_graphs()  # captured adjoints may hold this reducer's kernel and window pointers
         lib = self._lib.load()
         torch.cuda.synchronize(self.device)
         for mapped in self._peers:
@@ -224,7 +231,7 @@ def coil_sharded_adjoint(adj_ob, data_local: Tensor, omega: Tensor, smaps_local:
         # the all-reduce kernel is the last launch OF the adjoint: in graph mode it is replayed with it
         from ._nufft import graphs as _graphs
 
-        with _graphs.adjoint_epilogue(reducer, ("peer_allreduce", id(reducer), fuse_allreduce),
+        with _graphs.adjoint_epilogue(reducer, reducer.key + (fuse_allreduce,),
                                       peer_comm=reducer.comm if fuse_allreduce else None) as epilogue:
             partial = adj_ob(data_local, omega, smaps=smaps_local, norm=norm)
         if epilogue.applied:
