@@ -513,7 +513,10 @@ template <class P> int launch_cols_toep(ColArgs &a, cudaStream_t st) {
 template <class P> int launch_rows_sense_any(RowArgs &a, int64_t B, cudaStream_t st) {
   // a CTA carries FastCfg<P>::LPS coil pairs of one image row: with fewer coils than half of that most of its threads
   // would idle through the barriers (short lines, few coils: 256^3 x 8 coils) -- take the unfused route instead
-  if (2 * ((a.C + 1) / 2) < FastCfg<P>::LPS) return -1;
+  // ... unless the pass is to carry the all-reduce of a coil-sharded adjoint (2 coils per rank at 8 ranks): as a plain
+  // adjoint the mostly idle CTAs cost 0.8 us against the unfused route (profiles/r02_few_coil_sense_ab.log), but they
+  // save the all-reduce kernel behind it
+  if (2 * ((a.C + 1) / 2) < FastCfg<P>::LPS && !((a.peer.world > 1 || (g_fft_stream & 128)) && a.C >= 2)) return -1;
   return 2 * a.n_out <= P::N ? launch_rows_sense_h<P, true>(a, B, st) : launch_rows_sense_h<P, false>(a, B, st);
 }
 
