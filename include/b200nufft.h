@@ -191,6 +191,9 @@ enum b2n_option {
                              columns per CTA, for A/B).  Default 1: -3 % on the 384^2 x 32-coil forward, neutral where
                              the input is L2-resident; the inverse pass holds twice the operands per tile and loses a
                              resident CTA (profiles/r02_fft_stream_ab.log).  Results are bit-identical either way. */
+  B2N_OPT_PEER_FORM = 10, /* b2n_peer_allreduce_sum: 0 (default) one-shot or two-shot exchange by message size and number
+                             of ranks, 1 always one-shot, 2 always two-shot (reduce-scatter + all-gather through the same
+                             windows; needs float4-aligned operands) */
   B2N_OPT_COUNT
 };
 B2N_API int b2n_set_option(int option, int value);
@@ -348,7 +351,9 @@ B2N_API int b2n_peer_window_open(const void *handle, void **window_dev);  /* a p
 B2N_API int b2n_peer_window_close(void *window_dev);                      /* unmap a peer's window */
 B2N_API int b2n_peer_window_destroy(void *window_dev);                    /* free this rank's own window */
 /* out = sum over ranks of in (float32 units: a complex64 image is 2 floats per value); in place allowed; enqueued on
- * `stream`, CUDA-graph capturable (the call counter lives in the window). */
+ * `stream`, CUDA-graph capturable (the call counter lives in the window).  One kernel: a one-shot exchange (every rank
+ * pushes its whole message to every peer) for latency-bound sizes, a two-shot exchange (reduce-scatter + all-gather of
+ * shards) where that moves enough fewer bytes to pay for its second link latency (B2N_OPT_PEER_FORM forces a form). */
 B2N_API int b2n_peer_allreduce_sum(const b2n_peer_comm *comm, const void *in_dev, void *out_dev, int64_t n_floats,
                                    void *stream);
 /* b2n_fft_adjoint_fused followed by the sum all-reduce of image_dev over the ranks of `comm` (every rank calls it

@@ -5,7 +5,9 @@ import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 import torch.distributed as dist
-from torchkbnufft_b200 import parallel
+from torchkbnufft_b200 import _lib, parallel
+
+lib = _lib.load()
 
 rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
 torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
@@ -38,15 +40,22 @@ def timed(fn, n=40, do_flush=True):
 for values in (320 * 320, 64 * 1024, 256 * 256 * 8, 1 << 22):
     buf = torch.randn(values, dtype=torch.complex64, device=dev)
     peer = parallel.PeerAllReduce(max_values=values, dtype=torch.complex64)
+    lib.b2n_set_option(_lib.OPT_PEER_FORM, 1)
     for do_flush in (True, False):
         t_nccl = timed(lambda: parallel.all_reduce_complex_(buf), do_flush=do_flush)
         t_peer = timed(lambda: peer(buf), do_flush=do_flush)
+        lib.b2n_set_option(_lib.OPT_PEER_FORM, 2)
+        t_two = timed(lambda: peer(buf), do_flush=do_flush)
+        t_two10 = timed(lambda: [peer(buf) for _ in range(10)], do_flush=do_flush)
+        lib.b2n_set_option(_lib.OPT_PEER_FORM, 1)
         # back to back without events in between: 10 calls per timed region
         t_peer10 = timed(lambda: [peer(buf) for _ in range(10)], do_flush=do_flush)
         t_nccl10 = timed(lambda: [parallel.all_reduce_complex_(buf) for _ in range(10)], do_flush=do_flush)
         if rank == 0:
             print(f"world {world} {values * 8 / 1e6:7.2f} MB flush={int(do_flush)}: NCCL mean {t_nccl[0]:6.1f} median {t_nccl[1]:6.1f} us | "
-                  f"peer mean {t_peer[0]:6.1f} median {t_peer[1]:6.1f} us | 10 back to back: NCCL {t_nccl10[0] / 10:6.1f} peer {t_peer10[0] / 10:6.1f} us per call",
+                  f"peer one-shot mean {t_peer[0]:6.1f} median {t_peer[1]:6.1f} us | two-shot mean {t_two[0]:6.1f} median {t_two[1]:6.1f} us | "
+                  f"10 back to back: NCCL {t_nccl10[0] / 10:6.1f} one-shot {t_peer10[0] / 10:6.1f} two-shot {t_two10[0] / 10:6.1f} us per call",
                   flush=True)
+    lib.b2n_set_option(_lib.OPT_PEER_FORM, 0)
     peer.close()
 dist.destroy_process_group()

@@ -48,7 +48,7 @@ def main():
     # the same partition with the engine's own all-reduce over NVLink peer memory (b2n_peer_allreduce_sum): equal to
     # the NCCL result up to summation order, bit-identical on every rank, and stable over repeated calls of different
     # sizes (double-buffered slots, odd lengths take the scalar path)
-    peer = parallel.PeerAllReduce(max_values=4 * want_im.numel(), dtype=torch.complex64)
+    peer = parallel.PeerAllReduce(max_values=4 * want_im.numel(), dtype=torch.complex64)  # = 8 x numel floats
     for rep in range(5):
         im_p = parallel.coil_sharded_adjoint(na, y[:, lo:hi].contiguous(), om, s_loc, reducer=peer)
         err_p = rel(im_p, want_im)
@@ -83,6 +83,20 @@ def main():
         for p in parts[1:]:
             want_sum += p  # rank order, as the kernel adds
         assert torch.equal(peer(mine.clone()), want_sum), f"peer all-reduce of {n} floats is not the rank-ordered sum"
+    # the two-shot form (reduce-scatter + all-gather through the same windows), forced: the same rank-ordered sums, mixed
+    # freely with one-shot calls (the scalar path of an odd length is always one-shot)
+    lib = _lib.load()
+    for form in (2, 1, 2):
+        lib.b2n_set_option(_lib.OPT_PEER_FORM, form)
+        for n in (4, 4096, 8192 + 4, 12345, 4 * 30001, 8 * want_im.numel()):
+            mine = torch.randn(n, generator=gen).to(dev)
+            parts = [torch.empty_like(mine) for _ in range(world)]
+            dist.all_gather(parts, mine)
+            want_sum = parts[0].clone()
+            for p in parts[1:]:
+                want_sum += p
+            assert torch.equal(peer(mine.clone()), want_sum), f"peer all-reduce (form {form}) of {n} floats"
+    lib.b2n_set_option(_lib.OPT_PEER_FORM, 0)
     # captured into a CUDA graph: the call counter lives in the window, replays stay in step across ranks
     buf = torch.full((8192,), float(rank + 1), device=dev)
     side = torch.cuda.Stream()

@@ -143,9 +143,9 @@ def test_peer_window_entries_are_host_checkable():
     assert ctypes.sizeof(_lib.PeerComm) == 4 + 4 + 8 + 8 * _lib.PEER_MAX_RANKS
     n = ctypes.c_size_t(0)
     assert lib.b2n_peer_window_bytes(8, 2 * 320 * 320, ctypes.byref(n)) == 0
-    # header + three slot generations x ranks x the image rounded up to 4096-float chunks
-    assert n.value == 256 + 4 * 3 * 8 * (2 * 320 * 320)
-    assert lib.b2n_peer_window_bytes(1, 1, ctypes.byref(n)) == 0 and n.value == 256 + 4 * 3 * 4096
+    # header + three slot generations x ranks x (the image rounded up to 4096-float chunks + one chunk of slack)
+    assert n.value == 256 + 4 * 3 * 8 * (2 * 320 * 320 + 4096)
+    assert lib.b2n_peer_window_bytes(1, 1, ctypes.byref(n)) == 0 and n.value == 256 + 4 * 3 * 2 * 4096
     for world, floats in ((0, 10), (17, 10), (2, 0), (2, 1 << 31)):
         assert lib.b2n_peer_window_bytes(world, floats, ctypes.byref(n)) == -1  # B2N_E_ARG
     assert b"peer window" in lib.b2n_last_error()

@@ -266,14 +266,17 @@ def test_library_owned_graph_replay_matches_eager():
     assert not graphs._CACHE
 
 
+@pytest.mark.parametrize("form", [1, 2])
 @pytest.mark.parametrize("world", [1, 2, 5])
-def test_peer_allreduce_protocol_on_one_device(world):
+def test_peer_allreduce_protocol_on_one_device(world, form):
     """b2n_peer_allreduce_sum with every "rank" on ONE device (windows of the same process, one stream per rank, no
     IPC): pushes, flags, rank-ordered sums, double-buffered slots over repeated calls, the scalar path for odd and
     unaligned lengths, in place and out of place.  The multi-process version over NVLink is tests/test_gpu_multi.py."""
     import ctypes
 
     lib = _lib.load()
+    # form 1: one-shot exchange; form 2: two-shot (reduce-scatter + all-gather) wherever the operands are float4-aligned
+    lib.b2n_set_option(_lib.OPT_PEER_FORM, form)
     max_floats = 50000
     nbytes = ctypes.c_size_t(0)
     assert lib.b2n_peer_window_bytes(world, max_floats, ctypes.byref(nbytes)) == 0
@@ -314,6 +317,7 @@ def test_peer_allreduce_protocol_on_one_device(world):
                 for r in range(world):
                     assert torch.equal(outs[r], want[off:off + n]), (n, off, r)
     finally:
+        lib.b2n_set_option(_lib.OPT_PEER_FORM, 0)
         torch.cuda.synchronize()
         for w in windows:
             lib.b2n_peer_window_destroy(w)

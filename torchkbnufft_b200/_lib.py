@@ -27,6 +27,7 @@ OPT_FFT_PREFETCH = 6
 OPT_ADJ_OWNED = 7
 OPT_OWN_CAP = 8
 OPT_FFT_STREAM = 9
+OPT_PEER_FORM = 10
 
 _CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")
 # B2N_LIB_PATH: an alternative build of the same sources (A/B of compile-time kernel configurations, profiles/scripts)

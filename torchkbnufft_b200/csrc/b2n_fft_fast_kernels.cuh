@@ -486,7 +486,10 @@ template <class P, bool HALF> int launch_rows_sense_h(RowArgs &a, int64_t B, cud
   a.peer_fused = 0;
   if (a.peer.world > 1) {
     a.peer_floats = 2 * rows * a.n_out;
-    if (rows * a.coil_groups <= resident_ctas(kern, Cfg::SENSE_THREADS, smem) && a.peer_floats <= a.peer.slot_floats) a.peer_fused = 1;
+    // ... and in the latency-bound regime of the one-shot exchange (larger images: the stand-alone kernel's two-shot form)
+    const bool one_shot = 4 * a.peer_floats * (a.peer.world - 1) <= ((int64_t)8 << 20);
+    if (one_shot && rows * a.coil_groups <= resident_ctas(kern, Cfg::SENSE_THREADS, smem) && a.peer_floats <= a.peer.slot_floats)
+      a.peer_fused = 1;
     else a.peer.world = 0;
   }
   if (a.coil_groups > 1 && !g_counters_early) B2N_CUDA_OK(cudaMemsetAsync(a.counter, 0, sizeof(unsigned int) * (size_t)rows, st));

@@ -394,7 +394,8 @@ int g_pdl = 1;
 int g_prefetch = 19;
 int g_zero_kernel = 1;
 extern int g_fft_stream;
-static int g_options[B2N_OPT_COUNT] = {1, 0, 0, 0, 1, 1, 19, 1, 0, 1};
+extern int g_peer_form;
+static int g_options[B2N_OPT_COUNT] = {1, 0, 0, 0, 1, 1, 19, 1, 0, 1, 0};
 
 // With very few 2-D (batch, coil) rows most coil lanes of a tiled gather CTA idle while its per-point cost stays the
 // same: the one-thread-per-point kernel (k_fwd_point6_2d) wins up to 3 rows (16 vs 29 us for one row, 30 vs 41 us for
@@ -427,6 +428,7 @@ extern "C" int b2n_set_option(int option, int value) {
   if (option == B2N_OPT_ADJ_OWNED) g_adj_owned = value;
   if (option == B2N_OPT_OWN_CAP) g_own_cap = value;
   if (option == B2N_OPT_FFT_STREAM) g_fft_stream = value;
+  if (option == B2N_OPT_PEER_FORM) g_peer_form = value;
   return 0;
 }
 

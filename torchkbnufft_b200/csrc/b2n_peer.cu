@@ -15,6 +15,10 @@
 // (device side: the kernel is CUDA-graph capturable and needs no host state): a call reads generation e % 3, peers
 // that are one call ahead already write (e + 1) % 3, and (e + 2) % 3 -- last used by call e - 1, which every rank has
 // finished reading, or this call could not have been reached -- is reset to the fill pattern for call e + 2.
+// Past the latency-bound regime the one-shot exchange moves (world - 1) copies of the message per rank; the TWO-SHOT form
+// (k_peer_allreduce_two_shot, same windows and protocol) is a reduce-scatter followed by an all-gather: rank r receives
+// everyone's values of shard r only, adds them in rank order, and pushes the reduced shard to everyone -- 2 (world - 1) /
+// world copies per rank, one more link latency.  peer_allreduce_launch picks the form from the message size.
 #include <string.h>
 
 #include <type_traits>
@@ -130,6 +134,113 @@ __global__ void __launch_bounds__(kPeerThreads) k_peer_allreduce_sum(PeerArgs a,
   }
 }
 
+// Two-shot form (float4 only).  Shards are runs of `cps` chunks: shard r = chunks [r cps, (r + 1) cps).  Slot [q] of the
+// current generation is used twice: floats [0, cps chunks) receive rank q's contribution to MY shard (phase 1), floats
+// [cps chunks, 2 cps chunks) receive rank q's reduced shard (phase 2).  A CTA works on the same shard-local chunk j of
+// every shard, so that its phase-2 push follows its own phase-1 reduction directly.
+__global__ void __launch_bounds__(kPeerThreads) k_peer_allreduce_two_shot(PeerArgs a, const float *__restrict__ in,
+                                                                          float *__restrict__ out, int64_t n, int cps) {
+  constexpr int PER = kPeerChunk / (kPeerThreads * 4);
+  __shared__ uint32_t s_epoch, s_prev;
+  griddep_wait();
+  unsigned char *mine = a.window[a.rank];
+  uint32_t *hdr = reinterpret_cast<uint32_t *>(mine);
+  if (threadIdx.x == 0) {
+    const uint32_t e = *reinterpret_cast<volatile uint32_t *>(hdr) + 1u;
+    s_epoch = e;
+    s_prev = *reinterpret_cast<volatile uint32_t *>(hdr + 4 + (e + 2u) % 3u);
+  }
+  __syncthreads();
+  const uint32_t epoch = s_epoch, gen = epoch % 3u, gclr = (epoch + 2u) % 3u;
+  const size_t gen_off = (size_t)gen * a.world * a.slot_floats;
+  const int64_t n_chunks = (n + kPeerChunk - 1) / kPeerChunk;
+  const int64_t half = (int64_t)cps * kPeerChunk;  // floats of a slot's phase-1 part
+  float *win = reinterpret_cast<float *>(mine + a.data_off);
+  {  // reset the generation the call before last used (all of what it used of every slot)
+    const size_t prev4 = ((size_t)s_prev + 3) / 4;
+    const float4 fill = make_float4(__uint_as_float(kPeerFill), __uint_as_float(kPeerFill), __uint_as_float(kPeerFill),
+                                    __uint_as_float(kPeerFill));
+    for (int r = 0; r < a.world; ++r) {
+      if (r == a.rank) continue;
+      float4 *dst = reinterpret_cast<float4 *>(win + ((size_t)gclr * a.world + r) * a.slot_floats);
+      for (size_t i = (size_t)blockIdx.x * kPeerThreads + threadIdx.x; i < prev4; i += (size_t)gridDim.x * kPeerThreads)
+        dst[i] = fill;
+    }
+  }
+  unsigned spins = 0;
+  unsigned long long t0 = 0;
+  for (int64_t j = blockIdx.x; j < cps; j += gridDim.x) {
+    const int64_t loc = j * kPeerChunk;  // offset inside a shard / a slot half
+    // phase 1: my values of every other rank's shard go to that rank
+    for (int q = 1; q < a.world; ++q) {
+      const int p = (a.rank + q) % a.world;
+      const int64_t g = (int64_t)p * cps + j;
+      if (g >= n_chunks) continue;
+      float *dst = reinterpret_cast<float *>(a.window[p] + a.data_off) + gen_off + (size_t)a.rank * a.slot_floats + loc;
+#pragma unroll
+      for (int k = 0; k < PER; ++k) {
+        const int64_t off = ((int64_t)k * kPeerThreads + threadIdx.x) * 4, i = g * kPeerChunk + off;
+        if (i < n) {
+          float4 v = *reinterpret_cast<const float4 *>(in + i);
+          v = make_float4(not_fill(v.x), not_fill(v.y), not_fill(v.z), not_fill(v.w));
+          *reinterpret_cast<float4 *>(dst + off) = v;
+        }
+      }
+    }
+    // my shard: add the arrivals in rank order, publish the result (phase 2)
+    const int64_t g_own = (int64_t)a.rank * cps + j;
+    if (g_own < n_chunks) {
+#pragma unroll
+      for (int k = 0; k < PER; ++k) {
+        const int64_t off = ((int64_t)k * kPeerThreads + threadIdx.x) * 4, i = g_own * kPeerChunk + off;
+        if (i >= n) continue;
+        const float4 own = *reinterpret_cast<const float4 *>(in + i);
+        float4 acc;
+        for (int r = 0; r < a.world; ++r) {
+          float4 x = own;
+          if (r != a.rank) {
+            const float *src = win + gen_off + (size_t)r * a.slot_floats + loc + off;
+            for (x = ld_volatile4(src); !arrived(x); x = ld_volatile4(src)) spin_guard(spins, t0);
+          }
+          acc = r == 0 ? x : make_float4(acc.x + x.x, acc.y + x.y, acc.z + x.z, acc.w + x.w);
+        }
+        const float4 pub = make_float4(not_fill(acc.x), not_fill(acc.y), not_fill(acc.z), not_fill(acc.w));
+        for (int q = 1; q < a.world; ++q) {
+          const int p = (a.rank + q) % a.world;
+          float *dst = reinterpret_cast<float *>(a.window[p] + a.data_off) + gen_off + (size_t)a.rank * a.slot_floats + half + loc;
+          *reinterpret_cast<float4 *>(dst + off) = pub;
+        }
+        *reinterpret_cast<float4 *>(out + i) = pub;
+      }
+    }
+    // the other ranks' reduced shards
+    for (int q = 1; q < a.world; ++q) {
+      const int r = (a.rank + q) % a.world;
+      const int64_t g = (int64_t)r * cps + j;
+      if (g >= n_chunks) continue;
+      const float *src = win + gen_off + (size_t)r * a.slot_floats + half + loc;
+#pragma unroll
+      for (int k = 0; k < PER; ++k) {
+        const int64_t off = ((int64_t)k * kPeerThreads + threadIdx.x) * 4, i = g * kPeerChunk + off;
+        if (i >= n) continue;
+        float4 x;
+        for (x = ld_volatile4(src + off); !arrived(x); x = ld_volatile4(src + off)) spin_guard(spins, t0);
+        *reinterpret_cast<float4 *>(out + i) = x;
+      }
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(hdr + 1, 1u) == gridDim.x - 1) {
+      hdr[1] = 0;
+      hdr[4 + gen] = (uint32_t)(2 * half);  // what this call used of every slot
+      __threadfence();
+      *reinterpret_cast<volatile uint32_t *>(hdr) = epoch;
+    }
+  }
+}
+
 }  // namespace b2n
 
 using namespace b2n;
@@ -187,6 +298,8 @@ extern "C" int b2n_peer_window_destroy(void *window_dev) {
 
 namespace b2n {
 
+int g_peer_form = 0;  // B2N_OPT_PEER_FORM: 0 = by message size, 1 = one-shot, 2 = two-shot
+
 int peer_args_from_comm(const b2n_peer_comm *comm, PeerArgs *out) {
   if (!comm) return fail_arg(B2N_E_ARG, "peer all-reduce: NULL comm");
   if (comm->world < 1 || comm->world > B2N_PEER_MAX_RANKS || comm->rank < 0 || comm->rank >= comm->world)
@@ -218,8 +331,22 @@ int peer_allreduce_launch(const b2n_peer_comm *comm, const void *in_dev, void *o
   int dev = 0, sms = 0;
   B2N_CUDA_OK(cudaGetDevice(&dev));
   B2N_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  const dim3 grid((unsigned)(chunks < 4 * (int64_t)sms ? chunks : 4 * (int64_t)sms));  // <= 4 CTAs per SM: all resident
   const bool vec = !(n_floats & 3) && !(reinterpret_cast<uintptr_t>(in_dev) & 15) && !(reinterpret_cast<uintptr_t>(out_dev) & 15);
+  // one-shot moves (S - 1) n, two-shot 2 (S - 1) / S n and pays one more link latency (~6 us): two-shot from the size
+  // where the saved bytes outweigh it (never for two ranks); g_peer_form forces a form for tests and A/B runs
+  const int64_t S = a.world;
+  const double saved_bytes = 4.0 * (double)n_floats * (double)(S - 1) * (double)(S - 2) / (double)S;
+  const bool two_shot = vec && S >= 2 && (g_peer_form == 2 || (g_peer_form == 0 && S >= 3 && saved_bytes > 6.0e6));
+  if (two_shot) {
+    const int64_t cps = ceil_div(chunks, S);
+    if (2 * cps * kPeerChunk > a.slot_floats) return fail_arg(B2N_E_RANGE, "peer all-reduce: window too small for the two-shot form");
+    const dim3 grid2((unsigned)(cps < 4 * (int64_t)sms ? cps : 4 * (int64_t)sms));
+    B2N_CUDA_OK(launch_pdl(k_peer_allreduce_two_shot, grid2, dim3(kPeerThreads), 0, st, a, static_cast<const float *>(in_dev),
+                           static_cast<float *>(out_dev), n_floats, (int)cps));
+    B2N_LAUNCH_OK("k_peer_allreduce_two_shot");
+    return 0;
+  }
+  const dim3 grid((unsigned)(chunks < 4 * (int64_t)sms ? chunks : 4 * (int64_t)sms));  // <= 4 CTAs per SM: all resident
   // launched with programmatic stream serialization like the FFT passes: the CTAs are resident (and have read their
   // kernel arguments) while the last inverse pass drains, and start pushing the moment it has completed
   if (vec)

@@ -17,7 +17,7 @@ struct PeerLayout {
 
 static inline PeerLayout peer_layout(int world, int64_t max_floats) {
   PeerLayout l;
-  l.slot_floats = ceil_div(max_floats, kPeerChunk) * kPeerChunk;
+  l.slot_floats = (ceil_div(max_floats, kPeerChunk) + 1) * kPeerChunk;  // + 1: the two-shot form rounds its shards up
   l.data_off = kPeerHeader;
   l.bytes = l.data_off + sizeof(float) * 3 * (size_t)world * l.slot_floats;
   return l;

@@ -159,17 +159,17 @@ class PeerAllReduce:
             lib.b2n_peer_window_destroy(self._own)
             self._own = None
 
-    # one-shot pushes move (world - 1) copies of the message per rank: past this many bytes per rank a ring / tree
-    # all-reduce (NCCL) wins (profiles/r02_peer_allreduce_8gpu.log: 4 MB at 8 GPUs is already slower than NCCL)
-    ONE_SHOT_BYTES = 8 << 20
+    # Past this size a pipelined ring (NCCL) is the better tool; up to it the engine's kernel picks the one-shot exchange
+    # (latency-bound messages) or the two-shot form (reduce-scatter + all-gather through the same windows) by itself.
+    MAX_BYTES = 64 << 20
 
     def takes(self, n_values: int, dtype: torch.dtype) -> bool:
-        """Whether a tensor of ``n_values`` elements of ``dtype`` should go through this reducer (it fits the window,
-        is float32 / complex64 and small enough for the one-shot exchange to beat a bandwidth-optimal all-reduce)."""
+        """Whether a tensor of ``n_values`` elements of ``dtype`` should go through this reducer: float32 / complex64,
+        inside the window, at most ``MAX_BYTES``."""
         if self._own is None or dtype not in (torch.complex64, torch.float32):
             return False
         n = int(n_values) * (2 if dtype.is_complex else 1)
-        return 0 < n <= self.max_floats and 4 * n * max(self.world - 1, 1) <= self.ONE_SHOT_BYTES
+        return 0 < n <= self.max_floats and 4 * n <= self.MAX_BYTES
 
     @property
     def comm(self):
