@@ -61,6 +61,23 @@ def _worker(rank, world, port, out_dir):
         ok_f = torch.allclose(f_local, full_f[:, lo:hi])
         a_all = parallel.coil_sharded_adjoint(na, kdata_l, T("omega"), smaps_l, norm="ortho")
         ok_a = torch.allclose(a_all, full_a)
+        # a reducer object (the role parallel.PeerAllReduce plays on GPUs) runs as the adjoint's epilogue, exactly once
+        class GlooReducer:
+            key, comm, calls = ("gloo_reducer", 1), None, 0
+
+            def takes(self, n_values, dtype):
+                return True
+
+            def __call__(self, x):
+                GlooReducer.calls += 1
+                return parallel.all_reduce_complex_(x)
+
+        parallel.fuse_allreduce = False  # .comm is a C communicator on GPUs; here the callable is the whole reducer
+        try:
+            a_red = parallel.coil_sharded_adjoint(na, kdata_l, T("omega"), smaps_l, norm="ortho", reducer=GlooReducer())
+        finally:
+            parallel.fuse_allreduce = True
+        ok_a = ok_a and torch.allclose(a_red, full_a) and GlooReducer.calls == 1
         # Toeplitz normal operator with sharded coils: same all-reduce after the local coil sum
         toep = tkbn.ToepNufft()
         kern = tkbn.calc_toeplitz_kernel(T("omega"), case["im_size"], norm="ortho")
