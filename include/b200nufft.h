@@ -360,7 +360,10 @@ B2N_API int b2n_peer_allreduce_sum(const b2n_peer_comm *comm, const void *in_dev
  * with its own coils; all end up with the full coil sum).  Where the last pass is the row pass with the fused coil
  * combination and its grid is resident as a whole, each finished image row goes straight from that kernel into the
  * peers' windows and comes back summed -- compute and collective in one launch; otherwise the stand-alone all-reduce
- * kernel runs behind the last pass.  Same arguments as b2n_fft_adjoint_fused plus `comm`.  reference coupling point:
+ * kernel runs behind the last pass.  CTAs of the fused pass wait for the same rows of the peers: work that co-runs on
+ * other streams must terminate on its own (a kernel that holds its SMs until this call finishes can stall the exchange;
+ * a wait of more than ~20 s traps instead of hanging the device).  Same arguments as b2n_fft_adjoint_fused plus `comm`.
+ * reference coupling point:
  * the coil sum of the SENSE adjoint (modules/kbnufft.py:404-405) with the coils split over GPUs. */
 B2N_API int b2n_fft_adjoint_fused_allreduce(int ndim, const int64_t *im_size, const int64_t *grid_size,
                                             int64_t n_batch, int64_t n_coils, const void *grid_dev,
